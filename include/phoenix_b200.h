@@ -1,0 +1,121 @@
+/*
+ * phoenix_b200 — C ABI of the B200-native PHOENIX NeuralODE hot path (libphoenix_b200.so).
+ *
+ * The reference (QuackenbushLab/phoenix) has no process / FFI boundary on this path: it is Python calling Python
+ * (SURVEY.md section 8b).  The entry points below are what a binding for that path would bind; each one names the
+ * reference interface it replaces.  Citations are relative to the reference root, `ode_net/code/...`.
+ *
+ * Conventions
+ *   - every data pointer is a DEVICE pointer to contiguous fp32 unless the name ends in `_host`;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*); nothing is allocated or freed
+ *     behind the caller's back except inside phx_ctx_create / phx_ctx_destroy;
+ *   - the library only borrows the caller's buffers for the duration of the enqueued work;
+ *   - return value: PHX_OK or a negative phx_err; phx_last_error() returns a thread-local message;
+ *   - solver-side conditions the reference reports with Python `assert` (dt underflow, non-finite state,
+ *     max_num_steps; torchdiffeq/_impl/rk_common.py:154,175-176) are written to a phx_status record that the
+ *     caller reads after synchronising the stream.
+ *   - parameter order is the reference's `ODENet.parameters()` order: gene_multipliers[1,G], Wp[H,G], bp[H],
+ *     Ws[H,G], bs[H], Wa[G,2H]  (odenet.py:49-61); "flat grads" is their concatenation, P = 4GH + 2H + G floats.
+ */
+#ifndef PHOENIX_B200_H
+#define PHOENIX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct phx_ctx phx_ctx;
+
+typedef enum phx_err {
+    PHX_OK = 0,
+    PHX_ERR_INVALID = -1,      /* bad argument (shape, null pointer, unsupported size)            */
+    PHX_ERR_CUDA = -2,         /* a CUDA runtime call failed                                      */
+    PHX_ERR_UNSUPPORTED = -3,  /* valid request this build has no kernel for                      */
+    PHX_ERR_WORKSPACE = -4     /* workspace too small                                             */
+} phx_err;
+
+/* torchdiffeq method strings (torchdiffeq/_impl/odeint.py:9-22) this path implements */
+typedef enum phx_method {
+    PHX_EULER = 0,     /* 'euler'    fixed_grid.py:6-14                                           */
+    PHX_MIDPOINT = 1,  /* 'midpoint' fixed_grid.py:17-27                                          */
+    PHX_RK4 = 2,       /* 'rk4' = 3/8 rule, fixed_grid.py:30-38 + rk_common.py:96-103             */
+    PHX_DOPRI5 = 3     /* 'dopri5'   dopri5.py:5-36 + rk_common.py:111-228                        */
+} phx_method;
+
+/* solver status codes written to phx_status.code */
+enum {
+    PHX_ST_OK = 0,
+    PHX_ST_DT_UNDERFLOW = 1,  /* assert t0 + dt > t0          rk_common.py:175                    */
+    PHX_ST_NONFINITE = 2,     /* assert isfinite(y0).all()    rk_common.py:176                    */
+    PHX_ST_MAX_STEPS = 3,     /* assert n_steps < max_num_steps rk_common.py:154                  */
+    PHX_ST_RUNNING = 99       /* kernel has not finished (status record not yet written)          */
+};
+
+typedef struct phx_status {
+    int32_t code;        /* PHX_ST_*                                                              */
+    int32_t n_accepted;  /* accepted adaptive steps                                               */
+    int32_t n_rejected;  /* rejected adaptive steps                                               */
+    int32_t n_rhs;       /* RHS (forward) or RHS-VJP (adjoint) evaluations                        */
+    int32_t n_logged;    /* entries written to the step log                                       */
+    int32_t reserved;
+    double t_fail;       /* time at which a non-OK code was raised                                */
+    double dt_fail;      /* dt at that moment                                                     */
+} phx_status;
+
+/* ---- context --------------------------------------------------------------------------------------------- */
+int phx_ctx_create(int device, phx_ctx** out);
+void phx_ctx_destroy(phx_ctx* ctx);
+const char* phx_last_error(void);
+/* number of SMs the persistent kernels will use on this device, and the largest B the resident solver accepts */
+int phx_ctx_num_sms(const phx_ctx* ctx);
+int phx_resident_max_rows(int adjoint);
+
+/* ---- weights --------------------------------------------------------------------------------------------- */
+/* Bytes of the packed (kernel-layout) copy of the six parameters for an ODENet(ndim=G, neurons=H). */
+size_t phx_packed_bytes(int G, int H);
+/* Re-lay the six reference parameter tensors (odenet.py:49-61) into the kernel layout:
+ * W1[G][K2] = [Ws^T | Wp^T], WA[G][K2] = Wa (halves padded to a multiple of 4), bias[K2], relu(m)[G], (m>0)[G]. */
+int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* gene_multipliers, const float* Wp, const float* bp,
+                     const float* Ws, const float* bs, const float* Wa, float* packed, void* stream);
+
+/* ---- RHS: ODENet.forward / ODENet.prior_only_forward (odenet.py:85-98) ----------------------------------- */
+/* f[B][G] = relu(m) * (joint(y) - y)   (decay != 0)    or    joint(y)   (decay == 0) */
+int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, float* f, int decay,
+                    void* workspace, size_t workspace_bytes, void* stream);
+/* VJP of the call above for cotangent g[B][G] (what torch.autograd computes through odenet.py:85-98):
+ * ybar[B][G] (may be NULL) and the flat parameter cotangents grads_flat[P] (may be NULL); accumulate != 0 adds into
+ * grads_flat instead of overwriting it. */
+int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, const float* g, int decay,
+                float* ybar, float* grads_flat, int accumulate, void* workspace, size_t workspace_bytes,
+                void* stream);
+size_t phx_rhs_workspace_bytes(int G, int H, int B);
+
+/* ---- odeint (torchdiffeq/_impl/odeint.py:25-69) ---------------------------------------------------------- */
+size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint);
+/* y_out[T][B][G] = solution at the T increasing times t_host (float64; t_is_f32 != 0 says the caller's tensor was
+ * float32, which changes how fixed-grid dt is rounded, solvers.py:84-86).  reversed != 0: the caller's t was
+ * decreasing and has been negated, so the kernel integrates -f (misc.py:159-162,210-212).  Reference defaults: rtol 1e-7,
+ * atol 1e-9, max_num_steps 2^31-1, norm = RMS over the whole [B][G] state (misc.py:198-201).
+ * steplog (may be NULL): steplog_cap rows of (t0, dt, accepted) float64, one per attempted adaptive step. */
+int phx_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y0,
+                      const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol,
+                      double atol, int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
+                      phx_status* status, double* steplog, int steplog_cap, void* stream);
+
+/* ---- OdeintAdjointMethod.backward (torchdiffeq/_impl/adjoint.py:32-162) ---------------------------------- */
+/* Integrates the augmented system (y, adj_y, adj_params) backwards over every output interval with the forward
+ * method / tolerances and the mixed max-of-RMS norm (adjoint.py:72-78,198-200).  y_saved and grad_y are
+ * [T][B][G]; outputs adj_y0[B][G] and grads_flat[P] (overwritten). */
+int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
+                      int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                      const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
+                      void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                      int steplog_cap, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PHOENIX_B200_H */

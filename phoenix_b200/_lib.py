@@ -1,0 +1,123 @@
+"""ctypes binding of libphoenix_b200.so (the C ABI declared in include/phoenix_b200.h).
+
+There is no CPU fallback: if the library has not been built, or no sm_100a device is present, the product path
+raises.  Build with ``python -m phoenix_b200.build`` (nvcc, sm_100a).
+"""
+import ctypes
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libphoenix_b200.so")
+
+PHX_OK = 0
+METHOD_IDS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
+ST_OK, ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING = 0, 1, 2, 3, 99
+
+EXPORTS = [
+    "phx_ctx_create", "phx_ctx_destroy", "phx_last_error", "phx_ctx_num_sms", "phx_resident_max_rows",
+    "phx_packed_bytes", "phx_pack_weights", "phx_rhs_forward", "phx_rhs_vjp", "phx_rhs_workspace_bytes",
+    "phx_solve_workspace_bytes", "phx_solve_forward", "phx_solve_adjoint",
+    "phx_stream_workspace_bytes", "phx_stream_solve_forward", "phx_stream_solve_adjoint",
+]
+
+
+class PhxStatus(ctypes.Structure):
+    _fields_ = [("code", ctypes.c_int32), ("n_accepted", ctypes.c_int32), ("n_rejected", ctypes.c_int32),
+                ("n_rhs", ctypes.c_int32), ("n_logged", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("t_fail", ctypes.c_double), ("dt_fail", ctypes.c_double)]
+
+
+class PhoenixLibraryError(RuntimeError):
+    pass
+
+
+_lib = None
+_lock = threading.Lock()
+_ctx = {}
+
+
+def _declare(lib):
+    c_int, c_size_t, c_void_p, c_double, c_int64 = (ctypes.c_int, ctypes.c_size_t, ctypes.c_void_p, ctypes.c_double,
+                                                   ctypes.c_int64)
+    lib.phx_ctx_create.argtypes = [c_int, ctypes.POINTER(c_void_p)]
+    lib.phx_ctx_create.restype = c_int
+    lib.phx_ctx_destroy.argtypes = [c_void_p]
+    lib.phx_ctx_destroy.restype = None
+    lib.phx_last_error.argtypes = []
+    lib.phx_last_error.restype = ctypes.c_char_p
+    lib.phx_ctx_num_sms.argtypes = [c_void_p]
+    lib.phx_ctx_num_sms.restype = c_int
+    lib.phx_resident_max_rows.argtypes = [c_int]
+    lib.phx_resident_max_rows.restype = c_int
+    lib.phx_packed_bytes.argtypes = [c_int, c_int]
+    lib.phx_packed_bytes.restype = c_size_t
+    lib.phx_pack_weights.argtypes = [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_void_p]
+    lib.phx_pack_weights.restype = c_int
+    lib.phx_rhs_workspace_bytes.argtypes = [c_int, c_int, c_int]
+    lib.phx_rhs_workspace_bytes.restype = c_size_t
+    lib.phx_rhs_forward.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                    c_size_t, c_void_p]
+    lib.phx_rhs_forward.restype = c_int
+    lib.phx_rhs_vjp.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                c_void_p, c_int, c_void_p, c_size_t, c_void_p]
+    lib.phx_rhs_vjp.restype = c_int
+    lib.phx_solve_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int]
+    lib.phx_solve_workspace_bytes.restype = c_size_t
+    fwd = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, ctypes.POINTER(c_double), c_int, c_int, c_int,
+           c_int, c_double, c_double, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]
+    adj = [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_double), c_int, c_int, c_int, c_double,
+           c_double, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p,
+           c_int, c_void_p]
+    lib.phx_solve_forward.argtypes = fwd
+    lib.phx_solve_forward.restype = c_int
+    lib.phx_solve_adjoint.argtypes = adj
+    lib.phx_solve_adjoint.restype = c_int
+    lib.phx_stream_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int]
+    lib.phx_stream_workspace_bytes.restype = c_size_t
+    lib.phx_stream_solve_forward.argtypes = fwd
+    lib.phx_stream_solve_forward.restype = c_int
+    lib.phx_stream_solve_adjoint.argtypes = adj
+    lib.phx_stream_solve_adjoint.restype = c_int
+
+
+def load():
+    """Load the shared library (once).  Raises PhoenixLibraryError if it is missing — never falls back."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is None:
+            if not os.path.exists(LIB_PATH):
+                raise PhoenixLibraryError(
+                    "phoenix_b200: %s not found. Build it with `python -m phoenix_b200.build` (needs nvcc, "
+                    "sm_100a). There is no CPU fallback." % LIB_PATH)
+            lib = ctypes.CDLL(LIB_PATH)
+            _declare(lib)
+            _lib = lib
+    return _lib
+
+
+def last_error():
+    msg = load().phx_last_error()
+    return msg.decode() if msg else ""
+
+
+def check(rc, what):
+    if rc != PHX_OK:
+        msg = last_error()
+        if rc == -3:
+            raise NotImplementedError("phoenix_b200 %s: %s" % (what, msg))
+        raise PhoenixLibraryError("phoenix_b200 %s failed (code %d): %s" % (what, rc, msg))
+
+
+def ctx(device_index):
+    """phx_ctx for a CUDA device index (cached for the life of the process)."""
+    c = _ctx.get(device_index)
+    if c is None:
+        lib = load()
+        out = ctypes.c_void_p()
+        check(lib.phx_ctx_create(int(device_index), ctypes.byref(out)), "ctx_create")
+        c = out
+        _ctx[device_index] = c
+    return c

@@ -1,0 +1,246 @@
+// extern "C" entry points of libphoenix_b200.so (declared in include/phoenix_b200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+#include <vector>
+#include "phx_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void phx_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+struct phx_ctx {
+    int device;
+    int num_sms;
+    int coop;
+};
+
+namespace {
+
+__global__ void pack_kernel(int G, int H, int Hp, int K2, const float* __restrict__ m, const float* __restrict__ Wp,
+                            const float* __restrict__ bp, const float* __restrict__ Ws, const float* __restrict__ bs,
+                            const float* __restrict__ Wa, float* __restrict__ W1, float* __restrict__ WA,
+                            float* __restrict__ bias, float* __restrict__ relum, float* __restrict__ maskm) {
+    const size_t n = (size_t)G * K2;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        int g = (int)(i / K2), k = (int)(i % K2);
+        int half = k >= Hp, h = half ? k - Hp : k;
+        float w1 = 0.f, wa = 0.f;
+        if (h < H) {
+            w1 = half ? Wp[(size_t)h * G + g] : Ws[(size_t)h * G + g];
+            wa = Wa[(size_t)g * 2 * H + (half ? H + h : h)];
+        }
+        W1[i] = w1;
+        WA[i] = wa;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)K2; i += stride) {
+        int k = (int)i, half = k >= Hp, h = half ? k - Hp : k;
+        bias[k] = (h < H) ? (half ? bp[h] : bs[h]) : 0.f;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)G; i += stride) {
+        float v = m[i];
+        relum[i] = v > 0.f ? v : 0.f;
+        maskm[i] = v > 0.f ? 1.f : 0.f;
+    }
+}
+
+bool check_dims(int G, int H, int B) {
+    if (G < 1 || H < 1 || B < 1) {
+        phx_set_error("invalid dims G=%d H=%d B=%d", G, H, B);
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* phx_last_error(void) { return g_err; }
+
+int phx_ctx_create(int device, phx_ctx** out) {
+    if (!out) return PHX_ERR_INVALID;
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) {
+        phx_set_error("cudaGetDeviceProperties(%d): %s", device, cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    if (prop.major < 10) {
+        phx_set_error("phoenix_b200 needs an sm_100a (B200) device; device %d is sm_%d%d", device, prop.major,
+                      prop.minor);
+        return PHX_ERR_UNSUPPORTED;
+    }
+    phx_ctx* c = new phx_ctx;
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    c->coop = prop.cooperativeLaunch;
+    if (!c->coop) {
+        delete c;
+        phx_set_error("device %d does not support cooperative launch", device);
+        return PHX_ERR_UNSUPPORTED;
+    }
+    *out = c;
+    return PHX_OK;
+}
+
+void phx_ctx_destroy(phx_ctx* ctx) { delete ctx; }
+
+int phx_ctx_num_sms(const phx_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+int phx_resident_max_rows(int adjoint) { return adjoint ? PHX_MAX_B_ADJ : PHX_MAX_B_FWD; }
+
+size_t phx_packed_bytes(int G, int H) { return phx_packed_floats(G, H) * sizeof(float); }
+
+int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* m, const float* Wp, const float* bp, const float* Ws,
+                     const float* bs, const float* Wa, float* packed, void* stream) {
+    if (!ctx || !check_dims(G, H, 1) || !m || !Wp || !bp || !Ws || !bs || !Wa || !packed) return PHX_ERR_INVALID;
+    const int Hp = phx_Hp(H), K2 = 2 * Hp;
+    PhxPacked v = phx_packed_view(packed, G, H);
+    pack_kernel<<<ctx->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(
+        G, H, Hp, K2, m, Wp, bp, Ws, bs, Wa, (float*)v.W1, (float*)v.WA, (float*)v.bias, (float*)v.relum,
+        (float*)v.maskm);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("pack_weights launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+size_t phx_rhs_workspace_bytes(int G, int H, int B) { return phx_rhs_workspace_floats(G, H, B) * sizeof(float); }
+
+int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, float* f, int decay,
+                    void* workspace, size_t workspace_bytes, void* stream) {
+    if (!ctx || !check_dims(G, H, B) || !packed || !y || !f || !workspace) return PHX_ERR_INVALID;
+    if (workspace_bytes < phx_rhs_workspace_bytes(G, H, B)) {
+        phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
+        return PHX_ERR_WORKSPACE;
+    }
+    return phx_rhs_forward_launch(G, H, B, phx_packed_view(packed, G, H), y, f, decay, (float*)workspace,
+                                  (cudaStream_t)stream);
+}
+
+int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, const float* g, int decay,
+                float* ybar, float* grads_flat, int accumulate, void* workspace, size_t workspace_bytes,
+                void* stream) {
+    if (!ctx || !check_dims(G, H, B) || !packed || !y || !g || !workspace) return PHX_ERR_INVALID;
+    if (workspace_bytes < phx_rhs_workspace_bytes(G, H, B)) {
+        phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
+        return PHX_ERR_WORKSPACE;
+    }
+    return phx_rhs_vjp_launch(G, H, B, phx_packed_view(packed, G, H), y, g, decay, ybar, grads_flat, accumulate,
+                              (float*)workspace, (cudaStream_t)stream);
+}
+
+size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint) {
+    if (!ctx) return 0;
+    ResLaunchPlan plan;
+    if (phx_resident_plan(ctx->num_sms, G, H, B, adjoint, &plan) != PHX_OK) return 0;
+    return phx_resident_workspace_floats(plan.nCTA, G, H, B, T, adjoint, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                         nullptr) * sizeof(float);
+}
+
+static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
+                        int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps, int adjoint,
+                        void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                        int steplog_cap, cudaStream_t stream, ResParams* p, ResLaunchPlan* plan) {
+    if (!ctx || !check_dims(G, H, B) || !packed || !t_host || !workspace) {
+        if (g_err[0] == 0) phx_set_error("null argument");
+        return PHX_ERR_INVALID;
+    }
+    if (T < 2) {
+        phx_set_error("t must hold at least two time points (got %d)", T);
+        return PHX_ERR_INVALID;
+    }
+    for (int i = 1; i < T; ++i) {
+        if (!(t_host[i] > t_host[i - 1])) {
+            phx_set_error("t must be strictly increasing at the C boundary (the Python shim negates decreasing t)");
+            return PHX_ERR_INVALID;
+        }
+    }
+    if (method < PHX_EULER || method > PHX_DOPRI5) {
+        phx_set_error("unknown method id %d", method);
+        return PHX_ERR_INVALID;
+    }
+    int rc = phx_resident_plan(ctx->num_sms, G, H, B, adjoint, plan);
+    if (rc != PHX_OK) return rc;
+    size_t o_st, o_part, o_red, o_partd, o_t, o_th;
+    size_t need = phx_resident_workspace_floats(plan->nCTA, G, H, B, T, adjoint, &o_st, &o_part, &o_red, &o_partd,
+                                                &o_t, &o_th) * sizeof(float);
+    if (workspace_bytes < need) {
+        phx_set_error("solve workspace too small: %zu < %zu", workspace_bytes, need);
+        return PHX_ERR_WORKSPACE;
+    }
+    float* ws = (float*)workspace;
+    memset(p, 0, sizeof(*p));
+    p->G = G; p->H = H; p->Hp = phx_Hp(H); p->K2 = 2 * p->Hp; p->K2q = p->K2 / 4; p->B = B; p->T = T;
+    p->method = method; p->gpc = plan->gpc; p->t_is_f32 = t_is_f32; p->adjoint = adjoint;
+    p->rtol_f = (float)rtol; p->atol_f = (float)atol; p->fsign = 1.f;
+    p->max_steps = (long long)max_num_steps;
+    p->w = phx_packed_view(packed, G, H);
+    p->t = (const double*)(ws + o_t);
+    p->st = ws + o_st; p->part = ws + o_part; p->redout = ws + o_red; p->partd = (double*)(ws + o_partd);
+    p->theta1 = adjoint ? ws + o_th : nullptr;
+    p->status = status; p->steplog = steplog; p->steplog_cap = steplog ? steplog_cap : 0;
+    cudaError_t e = cudaMemcpyAsync((void*)p->t, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+        phx_set_error("cudaMemcpyAsync(t): %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+int phx_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y0,
+                      const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol, double atol,
+                      int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
+                      phx_status* status, double* steplog, int steplog_cap, void* stream) {
+    g_err[0] = 0;
+    if (!y0 || !y_out) {
+        phx_set_error("null y0 / y_out");
+        return PHX_ERR_INVALID;
+    }
+    ResParams p;
+    ResLaunchPlan plan;
+    int rc = solve_common(ctx, G, H, B, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 0, workspace,
+                          workspace_bytes, status, steplog, steplog_cap, (cudaStream_t)stream, &p, &plan);
+    if (rc != PHX_OK) return rc;
+    p.y0 = y0;
+    p.yout = y_out;
+    p.fsign = reversed ? -1.f : 1.f;
+    return phx_resident_launch(p, plan, (cudaStream_t)stream);
+}
+
+int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
+                      int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                      const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat, void* workspace,
+                      size_t workspace_bytes, phx_status* status, double* steplog, int steplog_cap, void* stream) {
+    g_err[0] = 0;
+    if (!y_saved || !grad_y || !adj_y0 || !grads_flat) {
+        phx_set_error("null y_saved / grad_y / adj_y0 / grads_flat");
+        return PHX_ERR_INVALID;
+    }
+    ResParams p;
+    ResLaunchPlan plan;
+    int rc = solve_common(ctx, G, H, B, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 1, workspace,
+                          workspace_bytes, status, steplog, steplog_cap, (cudaStream_t)stream, &p, &plan);
+    if (rc != PHX_OK) return rc;
+    p.ysaved = y_saved;
+    p.grad_y = grad_y;
+    p.adj_y0 = adj_y0;
+    p.theta0 = grads_flat;
+    cudaError_t e = cudaMemsetAsync(grads_flat, 0, phx_grad_offsets(G, H).total * sizeof(float), (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        phx_set_error("cudaMemsetAsync(grads): %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return phx_resident_launch(p, plan, (cudaStream_t)stream);
+}
+
+}  // extern "C"

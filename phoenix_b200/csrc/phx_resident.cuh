@@ -1,0 +1,1347 @@
+// Persistent ("resident") PHOENIX solver kernels for sm_100a: one cooperative launch integrates a whole odeint call
+// (forward) or a whole adjoint sweep (backward) with the step controller on the device.
+//
+// Decomposition (B200-first):
+//   * the G genes are split into contiguous slices, one CTA (one SM) per slice; the CTA owns every per-gene
+//     quantity of its slice: solver state, RK stage derivatives, Hill activations, and the rows W1[g][:], WA[g][:]
+//     of the packed weights (contiguous, streamed with 128-bit loads; L2-resident after the first stage because
+//     16GH bytes <= 64 MB << 126 MB L2);
+//   * an RHS evaluation is: phase A (branch pre-activations, reduce over the slice's genes) -> ONE grid-wide
+//     all-reduce of the K2-long branch vector -> phase B (combination row-dots, decay) -> the RK stage combine for
+//     the slice, all inside the same kernel, so the state never makes an HBM round trip between stages;
+//   * the adjoint adds a second all-reduce (gS|gLP) and phase C (state cotangent), and keeps the parameter
+//     cotangents FACTORISED per stage (rank-B outer-product factors in shared memory); they are folded into the
+//     P-long accumulator once per step together with their error-norm contribution (the reference instead carries
+//     seven P-long stage tensors through every stage, adjoint.py:86-151 + rk_common.py:62-76);
+//   * reductions are fixed-order (warp butterflies, ordered cross-warp / cross-CTA sums): results are run-to-run
+//     deterministic, which the dopri5 accept/reject sequence needs.
+//
+// Arithmetic mirrors the reference op by op where it is elementwise (compiled with -fmad=false, explicit fmaf only
+// inside dot products), fp32 state, float64 time-like scalars (rk_common.py:115-131).
+#include <cooperative_groups.h>
+#include <math.h>
+#include <stdio.h>
+#pragma once
+#include "phx_common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int THREADS = PHX_THREADS;
+constexpr int WARPS = PHX_WARPS;
+
+// Dormand-Prince tableau (dopri5.py:5-30), float64 constants rounded to fp32 at use like `.to(dtype=y0.dtype)`.
+__constant__ double c_beta[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+__constant__ double c_err[7] = {35.0 / 384 - 1951.0 / 21600,
+                                0,
+                                500.0 / 1113 - 22642.0 / 50085,
+                                125.0 / 192 - 451.0 / 720,
+                                -2187.0 / 6784 - -12231.0 / 42400,
+                                11.0 / 84 - 649.0 / 6300,
+                                -1.0 / 60.0};
+__constant__ double c_mid[7] = {6025192743.0 / 30085553152.0 / 2,
+                                0,
+                                51252292925.0 / 65400821598.0 / 2,
+                                -2691868925.0 / 45128329728.0 / 2,
+                                187940372067.0 / 1594534317056.0 / 2,
+                                -1776094331.0 / 19743644256.0 / 2,
+                                11237099.0 / 235043384.0 / 2};
+
+struct Ctrl {
+    double tcur, tprev, dt, dt_used, t_end;
+    double dsum[8];
+    float cb[6][6];
+    float cerr[7];
+    float cmid[7];
+    float xs[4];  // x, x^2, x^3, x^4 for the dense output (interp.py:40-47)
+    float dtf, h0, d1;
+    int accept, stop, nonfinite_prev;
+    int n_acc, n_rej, n_rhs, n_log, n_steps_interval;
+    int slot[7];
+};
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+__device__ __forceinline__ void hill(float y, float& s, float& l, float& den) {
+    float z = y - 0.5f;
+    den = 1.0f + fabsf(z);
+    s = z / den;
+    l = log1pf(s);
+}
+
+__device__ __forceinline__ float4 ld4(const float4* p) { return __ldg(p); }
+
+// ---- block / grid reductions ------------------------------------------------------------------------------------
+template <int N>
+__device__ void block_sum_d(double (&v)[N], double* dred, double* out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        double s = warp_sum_d(v[i]);
+        if (lane == 0) dred[warp * N + i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double s = 0;
+        for (int w = 0; w < WARPS; ++w) s += dred[w * N + threadIdx.x];
+        out[threadIdx.x] = s;
+    }
+    __syncthreads();
+}
+
+// sum over all CTAs of up to 8 doubles held in vals[] (smem); result replaces vals[] in every CTA.
+__device__ void grid_allreduce_d(cg::grid_group& grid, const ResParams& p, double* vals, int nd, int& parity) {
+    const int nC = gridDim.x;
+    if (nC == 1) return;
+    double* buf = p.partd + (size_t)parity * nC * 8;
+    parity ^= 1;
+    if (threadIdx.x < nd) __stcg(buf + (size_t)blockIdx.x * 8 + threadIdx.x, vals[threadIdx.x]);
+    grid.sync();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp < nd) {
+        double s = 0;
+        for (int c = lane; c < nC; c += 32) s += __ldcg(buf + (size_t)c * 8 + warp);
+        s = warp_sum_d(s);
+        if (lane == 0) vals[warp] = s;
+    }
+    __syncthreads();
+}
+
+// sum over all CTAs of the n-float vector vec[] (smem); two-level, fixed order.
+__device__ void grid_allreduce_f(cg::grid_group& grid, const ResParams& p, float* vec, int n) {
+    const int nC = gridDim.x;
+    if (nC == 1) return;
+    float* mine = p.part + (size_t)blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += THREADS) __stcg(mine + i, vec[i]);
+    grid.sync();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int i = blockIdx.x + nC * warp; i < n; i += nC * WARPS) {
+        float s = 0.f;
+        for (int c = lane; c < nC; c += 32) s += __ldcg(p.part + (size_t)c * n + i);
+        s = warp_sum(s);
+        if (lane == 0) __stcg(p.redout + i, s);
+    }
+    grid.sync();
+    for (int i = threadIdx.x; i < n; i += THREADS) vec[i] = __ldcg(p.redout + i);
+    __syncthreads();
+}
+
+// ---- shared-memory carve-up ---------------------------------------------------------------------------------------
+struct Smem {
+    Ctrl* ctrl;
+    double* dred;  // [WARPS][8]
+    float* sp;     // [B][K2]   S | Pr
+    float* gsp;    // [B][K2]   gS | gLP             (adjoint)
+    float* red;    // [WARPS][K2]
+    float *acts, *actl, *ysb, *jb;        // [B][gpc]
+    float *asb, *gjb, *ub, *vb, *mt;      // [B][gpc]  (adjoint)
+    float *pSP, *pG;                      // [7][B][K2] (adjoint, per-stage factors)
+    float *pS, *pL, *pGJ;                 // [7][B][gpc]
+    float* pM;                            // [7][gpc]
+};
+
+__host__ __device__ inline size_t smem_layout(int B, int K2, int gpc, int adjoint, Smem* s, unsigned char* base) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off += (bytes + 15) & ~size_t(15);
+        return o;
+    };
+    size_t o_ctrl = take(sizeof(Ctrl));
+    size_t o_dred = take(sizeof(double) * WARPS * 8);
+    size_t o_sp = take(sizeof(float) * B * K2);
+    size_t o_gsp = adjoint ? take(sizeof(float) * B * K2) : 0;
+    size_t o_red = take(sizeof(float) * WARPS * K2);
+    size_t bl = sizeof(float) * B * gpc;
+    size_t o_loc[9];
+    int nloc = adjoint ? 9 : 4;
+    for (int i = 0; i < nloc; ++i) o_loc[i] = take(bl);
+    size_t o_pSP = 0, o_pG = 0, o_pS = 0, o_pL = 0, o_pGJ = 0, o_pM = 0;
+    if (adjoint) {
+        o_pSP = take(sizeof(float) * 7 * B * K2);
+        o_pG = take(sizeof(float) * 7 * B * K2);
+        o_pS = take(7 * bl);
+        o_pL = take(7 * bl);
+        o_pGJ = take(7 * bl);
+        o_pM = take(sizeof(float) * 7 * gpc);
+    }
+    if (s) {
+        s->ctrl = reinterpret_cast<Ctrl*>(base + o_ctrl);
+        s->dred = reinterpret_cast<double*>(base + o_dred);
+        s->sp = reinterpret_cast<float*>(base + o_sp);
+        s->gsp = reinterpret_cast<float*>(base + o_gsp);
+        s->red = reinterpret_cast<float*>(base + o_red);
+        s->acts = reinterpret_cast<float*>(base + o_loc[0]);
+        s->actl = reinterpret_cast<float*>(base + o_loc[1]);
+        s->ysb = reinterpret_cast<float*>(base + o_loc[2]);
+        s->jb = reinterpret_cast<float*>(base + o_loc[3]);
+        if (adjoint) {
+            s->asb = reinterpret_cast<float*>(base + o_loc[4]);
+            s->gjb = reinterpret_cast<float*>(base + o_loc[5]);
+            s->ub = reinterpret_cast<float*>(base + o_loc[6]);
+            s->vb = reinterpret_cast<float*>(base + o_loc[7]);
+            s->mt = reinterpret_cast<float*>(base + o_loc[8]);
+            s->pSP = reinterpret_cast<float*>(base + o_pSP);
+            s->pG = reinterpret_cast<float*>(base + o_pG);
+            s->pS = reinterpret_cast<float*>(base + o_pS);
+            s->pL = reinterpret_cast<float*>(base + o_pL);
+            s->pGJ = reinterpret_cast<float*>(base + o_pGJ);
+            s->pM = reinterpret_cast<float*>(base + o_pM);
+        }
+    }
+    return off;
+}
+
+// ---- the three weight passes ------------------------------------------------------------------------------------
+// Mapping common to all passes: a warp owns gene rows j = warp, warp+16, ... of the CTA's slice; lane l owns the
+// float4 columns q = l + 32 v (v < NV) of the K2-long row.
+
+// Phase A: partial[b][k] = sum_{g in slice} act[b][g] * W1[g][k], act = s for k < Hp, l for k >= Hp.
+// Result (this CTA's partial) is left in s.sp[b][:].
+template <int NV, int BT>
+__device__ void phaseA(const ResParams& p, const Smem& s, int g_lo, int n_loc, int b0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K2q = p.K2q, Hq = p.Hp >> 2;
+    float4 acc[BT][NV];
+#pragma unroll
+    for (int b = 0; b < BT; ++b)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int j = warp; j < n_loc; j += WARPS) {
+        const float4* row = p.w.W1 + (size_t)(g_lo + j) * K2q;
+        float4 w[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            int q = lane + 32 * v;
+            w[v] = (q < K2q) ? ld4(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            if (b < nb) {
+                float sv = s.acts[(b0 + b) * p.gpc + j], lv = s.actl[(b0 + b) * p.gpc + j];
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    int q = lane + 32 * v;
+                    float c = (q >= Hq) ? lv : sv;
+                    acc[b][v].x = fmaf(w[v].x, c, acc[b][v].x);
+                    acc[b][v].y = fmaf(w[v].y, c, acc[b][v].y);
+                    acc[b][v].z = fmaf(w[v].z, c, acc[b][v].z);
+                    acc[b][v].w = fmaf(w[v].w, c, acc[b][v].w);
+                }
+            }
+        }
+    }
+    float4* red4 = reinterpret_cast<float4*>(s.red);
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+        if (b < nb) {
+            __syncthreads();
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                int q = lane + 32 * v;
+                if (q < K2q) red4[warp * K2q + q] = acc[b][v];
+            }
+            __syncthreads();
+            for (int k = threadIdx.x; k < p.K2; k += THREADS) {
+                float t = 0.f;
+#pragma unroll
+                for (int w = 0; w < WARPS; ++w) t += s.red[w * p.K2 + k];
+                s.sp[(b0 + b) * p.K2 + k] = t;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Phase B: jb[b][j] = sum_k WA[g][k] * sp[b][k]; adjoint additionally partial gsp[b][k] = sum_g gj[b][g] WA[g][k].
+template <int NV, int BT, bool ADJ>
+__device__ void phaseB(const ResParams& p, const Smem& s, int g_lo, int n_loc, int b0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K2q = p.K2q;
+    const float4* sp4 = reinterpret_cast<const float4*>(s.sp);
+    float4 acc[ADJ ? BT : 1][NV];
+    if (ADJ) {
+#pragma unroll
+        for (int b = 0; b < BT; ++b)
+#pragma unroll
+            for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int j = warp; j < n_loc; j += WARPS) {
+        const float4* row = p.w.WA + (size_t)(g_lo + j) * K2q;
+        float4 w[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            int q = lane + 32 * v;
+            w[v] = (q < K2q) ? ld4(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            if (b < nb) {
+                float d = 0.f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    int q = lane + 32 * v;
+                    if (q < K2q) {
+                        float4 x = sp4[(b0 + b) * K2q + q];
+                        d = fmaf(w[v].x, x.x, d);
+                        d = fmaf(w[v].y, x.y, d);
+                        d = fmaf(w[v].z, x.z, d);
+                        d = fmaf(w[v].w, x.w, d);
+                    }
+                }
+                d = warp_sum(d);
+                if (lane == 0) s.jb[(b0 + b) * p.gpc + j] = d;
+                if (ADJ) {
+                    float gj = s.gjb[(b0 + b) * p.gpc + j];
+#pragma unroll
+                    for (int v = 0; v < NV; ++v) {
+                        acc[b][v].x = fmaf(w[v].x, gj, acc[b][v].x);
+                        acc[b][v].y = fmaf(w[v].y, gj, acc[b][v].y);
+                        acc[b][v].z = fmaf(w[v].z, gj, acc[b][v].z);
+                        acc[b][v].w = fmaf(w[v].w, gj, acc[b][v].w);
+                    }
+                }
+            }
+        }
+    }
+    if (ADJ) {
+        float4* red4 = reinterpret_cast<float4*>(s.red);
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            if (b < nb) {
+                __syncthreads();
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    int q = lane + 32 * v;
+                    if (q < K2q) red4[warp * K2q + q] = acc[b][v];
+                }
+                __syncthreads();
+                for (int k = threadIdx.x; k < p.K2; k += THREADS) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int w = 0; w < WARPS; ++w) t += s.red[w * p.K2 + k];
+                    s.gsp[(b0 + b) * p.K2 + k] = t;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// Phase C (adjoint): ub[b][j] = sum_{k<Hp} W1[g][k] gS[b][k],  vb[b][j] = sum_{k>=Hp} W1[g][k] gLP[b][k].
+template <int NV, int BT>
+__device__ void phaseC(const ResParams& p, const Smem& s, int g_lo, int n_loc, int b0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K2q = p.K2q, Hq = p.Hp >> 2;
+    const float4* g4 = reinterpret_cast<const float4*>(s.gsp);
+    for (int j = warp; j < n_loc; j += WARPS) {
+        const float4* row = p.w.W1 + (size_t)(g_lo + j) * K2q;
+        float4 w[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            int q = lane + 32 * v;
+            w[v] = (q < K2q) ? ld4(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int b = 0; b < BT; ++b) {
+            if (b < nb) {
+                float du = 0.f, dv = 0.f;
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    int q = lane + 32 * v;
+                    if (q < K2q) {
+                        float4 x = g4[(b0 + b) * K2q + q];
+                        float t = 0.f;
+                        t = fmaf(w[v].x, x.x, t);
+                        t = fmaf(w[v].y, x.y, t);
+                        t = fmaf(w[v].z, x.z, t);
+                        t = fmaf(w[v].w, x.w, t);
+                        if (q >= Hq) dv += t; else du += t;
+                    }
+                }
+                du = warp_sum(du);
+                dv = warp_sum(dv);
+                if (lane == 0) {
+                    s.ub[(b0 + b) * p.gpc + j] = du;
+                    s.vb[(b0 + b) * p.gpc + j] = dv;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+template <typename F>
+__device__ __forceinline__ void for_local(const ResParams& p, int g_lo, int n_loc, F f) {
+    const int tot = p.B * n_loc;
+    for (int e = threadIdx.x; e < tot; e += THREADS) {
+        int b = e / n_loc, j = e - b * n_loc;
+        f(b, j, g_lo + j, (size_t)b * p.G + g_lo + j, b * p.gpc + j);
+    }
+}
+
+// branch vector after the all-reduce: add bias, exponentiate the prods half (odenet.py:86-87); padded columns -> 0
+__device__ void finalize_sp(const ResParams& p, const Smem& s) {
+    for (int i = threadIdx.x; i < p.B * p.K2; i += THREADS) {
+        int k = i % p.K2;
+        float v = s.sp[i] + p.w.bias[k];
+        if (k >= p.Hp) v = (k - p.Hp < p.H) ? expf(v) : 0.f;
+        s.sp[i] = v;
+    }
+    __syncthreads();
+}
+
+// One RHS evaluation at the stage input whose activations are in s.acts / s.actl; leaves joint(y) in s.jb.
+template <int NV, int BT>
+__device__ void eval_fwd(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc) {
+    for (int b0 = 0; b0 < p.B; b0 += BT) phaseA<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    grid_allreduce_f(grid, p, s.sp, p.B * p.K2);
+    finalize_sp(p, s);
+    for (int b0 = 0; b0 < p.B; b0 += BT) phaseB<NV, BT, false>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+}
+
+// RHS + VJP evaluation at the stage input (ysb, asb) with activations / gj already in smem.  Leaves jb, ub, vb and
+// stores this stage's branch factors in slot `slot` of pSP / pG.
+template <int NV, int BT>
+__device__ void eval_adj(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc, int slot) {
+    for (int b0 = 0; b0 < p.B; b0 += BT) phaseA<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    grid_allreduce_f(grid, p, s.sp, p.B * p.K2);
+    finalize_sp(p, s);
+    for (int b0 = 0; b0 < p.B; b0 += BT) phaseB<NV, BT, true>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    grid_allreduce_f(grid, p, s.gsp, p.B * p.K2);
+    const int n = p.B * p.K2;
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        int k = i % p.K2;
+        float spv = s.sp[i];
+        float gv = s.gsp[i];
+        if (k >= p.Hp) gv = gv * spv;  // gLP = gPr * Pr (exp backward)
+        s.gsp[i] = gv;
+        s.pSP[slot * n + i] = spv;
+        s.pG[slot * n + i] = gv;
+    }
+    __syncthreads();
+    for (int b0 = 0; b0 < p.B; b0 += BT) phaseC<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+}
+
+__device__ __forceinline__ float* slot_ptr(const ResParams& p, int slot) {
+    return p.st + (size_t)slot * p.B * p.G;
+}
+
+// controller pieces (thread 0 only) --------------------------------------------------------------------------------
+__device__ void set_step_coeffs(Ctrl* c) {
+    float dtf = (float)c->dt;
+    c->dtf = dtf;
+    for (int i = 0; i < 6; ++i)
+        for (int j = 0; j <= i; ++j) c->cb[i][j] = (float)c_beta[i][j] * dtf;
+    for (int j = 0; j < 7; ++j) {
+        c->cerr[j] = dtf * (float)c_err[j];
+        c->cmid[j] = dtf * (float)c_mid[j];
+    }
+}
+
+// misc.py:94-103 with safety 0.9, ifactor 10, dfactor 0.2, order 5
+__device__ double next_dt(double dt, float ratio) {
+    if (ratio == 0.f) return dt * 10.0;
+    double dfactor = (ratio < 1.f) ? 1.0 : 0.2;
+    double r = (double)ratio;
+    if (isnan(r)) return nan("");
+    double f = 0.9 / pow(r, 0.2);
+    f = fmax(f, dfactor);
+    f = fmin(10.0, f);
+    return dt * f;
+}
+
+// misc.py:47-86 tail: h0 from d0, d1
+__device__ float init_h0(float d0, float d1) {
+    if (d0 < 1e-5f || d1 < 1e-5f) return 1e-6f;
+    return 0.01f * d0 / d1;
+}
+__device__ double init_dt(float h0, float d1, float d2) {
+    float h1;
+    if (d1 <= 1e-15f && d2 <= 1e-15f)
+        h1 = fmaxf(1e-6f, h0 * 1e-3f);
+    else
+        h1 = powf(0.01f / fmaxf(d1, d2), 0.2f);
+    return (double)fminf(100.f * h0, h1);
+}
+
+__device__ void log_step(const ResParams& p, Ctrl* c, double t0, double dt, int accepted) {
+    if (blockIdx.x == 0 && p.steplog && c->n_log < p.steplog_cap) {
+        p.steplog[3 * c->n_log + 0] = t0;
+        p.steplog[3 * c->n_log + 1] = dt;
+        p.steplog[3 * c->n_log + 2] = (double)accepted;
+    }
+    c->n_log++;
+}
+
+__device__ void set_interp_x(Ctrl* c, double t) {
+    double x = (t - c->tprev) / (c->tcur - c->tprev);
+    double xp = x;
+    c->xs[0] = (float)xp;
+    xp = xp * x;
+    c->xs[1] = (float)xp;
+    xp = xp * x;
+    c->xs[2] = (float)xp;
+    xp = xp * x;
+    c->xs[3] = (float)xp;
+}
+
+// quartic dense output (interp.py:1-47) from the step's end values and derivatives
+__device__ __forceinline__ float interp_eval(float y0, float y1, float ymid, float f0, float f1, float dt,
+                                             const float* xs) {
+    float a = 2.f * dt * (f1 - f0) - 8.f * (y1 + y0) + 16.f * ymid;
+    float b = dt * (5.f * f0 - 3.f * f1) + 18.f * y0 + 14.f * y1 - 32.f * ymid;
+    float c = dt * (f1 - 4.f * f0) - 11.f * y0 - 5.f * y1 + 16.f * ymid;
+    float d = dt * f0;
+    float total = y0 + xs[0] * d;
+    total = total + xs[1] * c;
+    total = total + xs[2] * b;
+    total = total + xs[3] * a;
+    return total;
+}
+
+__device__ void write_status(const ResParams& p, const Ctrl* c, int code) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && p.status) {
+        p.status->n_accepted = c->n_acc;
+        p.status->n_rejected = c->n_rej;
+        p.status->n_rhs = c->n_rhs;
+        p.status->n_logged = min(c->n_log, p.steplog_cap);
+        p.status->reserved = 0;
+        p.status->t_fail = c->tcur;
+        p.status->dt_fail = c->dt;
+        __threadfence_system();
+        p.status->code = code;
+    }
+}
+
+// =====================================================================================================================
+// Forward solve
+// =====================================================================================================================
+template <int NV, int BT>
+__global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s;
+    smem_layout(p.B, p.K2, p.gpc, 0, &s, smem_raw);
+    Ctrl* c = s.ctrl;
+    const int g_lo = blockIdx.x * p.gpc;
+    const int n_loc = max(0, min(p.gpc, p.G - g_lo));
+    const size_t BG = (size_t)p.B * p.G;
+    const double Nel = (double)p.B * (double)p.G;
+    float* Y = slot_ptr(p, 0);
+    float* Y1 = slot_ptr(p, 1);
+    int dpar = 0;
+
+    if (threadIdx.x == 0) {
+        c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
+        c->stop = 0;
+        c->tcur = p.t[0];
+        c->dt = 0;
+        for (int i = 0; i < 7; ++i) c->slot[i] = i;
+    }
+    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+        float y = p.y0[gi];
+        Y[gi] = y;
+        p.yout[gi] = y;
+        s.ysb[li] = y;
+        float sv, lv, den;
+        hill(y, sv, lv, den);
+        s.acts[li] = sv;
+        s.actl[li] = lv;
+    });
+    __syncthreads();
+
+    auto K = [&](int i) { return slot_ptr(p, 2 + i); };
+    auto set_stage_input = [&](int li, float ys) {
+        s.ysb[li] = ys;
+        float sv, lv, den;
+        hill(ys, sv, lv, den);
+        s.acts[li] = sv;
+        s.actl[li] = lv;
+    };
+
+    if (p.method != PHX_DOPRI5) {
+        // ---- fixed grid: one step per output interval (solvers.py:48-50, 77-95) ----
+        const float third = (float)(1.0 / 3.0);
+        for (int i = 0; i + 1 < p.T; ++i) {
+            const float dtf = p.t_is_f32 ? ((float)p.t[i + 1] - (float)p.t[i]) : (float)(p.t[i + 1] - p.t[i]);
+            float* yo = p.yout + (size_t)(i + 1) * BG;
+            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+            if (p.method == PHX_EULER) {
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float y = s.ysb[li];
+                    float f = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
+                    float y1 = y + dtf * f;
+                    Y[gi] = y1;
+                    yo[gi] = y1;
+                    set_stage_input(li, y1);
+                });
+            } else if (p.method == PHX_MIDPOINT) {
+                const float half = 0.5f * dtf;
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float y = s.ysb[li];
+                    float f = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
+                    set_stage_input(li, y + f * half);
+                });
+                __syncthreads();
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float f = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
+                    float y1 = Y[gi] + dtf * f;
+                    Y[gi] = y1;
+                    yo[gi] = y1;
+                    set_stage_input(li, y1);
+                });
+            } else {  // 3/8-rule RK4 (rk_common.py:96-103)
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float y = s.ysb[li];
+                    float k1 = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
+                    K(0)[gi] = k1;
+                    set_stage_input(li, y + dtf * k1 * third);
+                });
+                __syncthreads();
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float k2 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
+                    K(1)[gi] = k2;
+                    set_stage_input(li, Y[gi] + dtf * (k2 - K(0)[gi] * third));
+                });
+                __syncthreads();
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float k3 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
+                    K(2)[gi] = k3;
+                    set_stage_input(li, Y[gi] + dtf * (K(0)[gi] - K(1)[gi] + k3));
+                });
+                __syncthreads();
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float k4 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
+                    float dy = (K(0)[gi] + 3.f * (K(1)[gi] + K(2)[gi]) + k4) * dtf * 0.125f;
+                    float y1 = Y[gi] + dy;
+                    Y[gi] = y1;
+                    yo[gi] = y1;
+                    set_stage_input(li, y1);
+                });
+            }
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) {
+            int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
+            c->n_rhs = per * (p.T - 1);
+            c->tcur = p.t[p.T - 1];
+        }
+        __syncthreads();
+        write_status(p, c, PHX_ST_OK);
+        return;
+    }
+
+    // ---- dopri5 (rk_common.py:111-228) ----
+    // f0 and the initial step (misc.py:47-86)
+    eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+    {
+        double acc[3] = {0, 0, 0};
+        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+            float y = s.ysb[li];
+            float f0 = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
+            K(0)[gi] = f0;
+            float scale = p.atol_f + fabsf(y) * p.rtol_f;
+            float r0 = y / scale, r1 = f0 / scale;
+            acc[0] += (double)(r0 * r0);
+            acc[1] += (double)(r1 * r1);
+            if (!isfinite(y)) acc[2] += 1.0;
+        });
+        block_sum_d<3>(acc, s.dred, c->dsum);
+        grid_allreduce_d(grid, p, c->dsum, 3, dpar);
+        if (threadIdx.x == 0) {
+            float d0 = sqrtf((float)(c->dsum[0] / Nel));
+            float d1 = sqrtf((float)(c->dsum[1] / Nel));
+            c->d1 = d1;
+            c->h0 = init_h0(d0, d1);
+            c->nonfinite_prev = c->dsum[2] > 0.0;
+        }
+        __syncthreads();
+        const float h0 = c->h0;
+        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+            set_stage_input(li, Y[gi] + h0 * K(0)[gi]);
+        });
+        __syncthreads();
+        eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+        double acc2[1] = {0};
+        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+            float f1 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
+            float scale = p.atol_f + fabsf(Y[gi]) * p.rtol_f;
+            float r = (f1 - K(0)[gi]) / scale;
+            acc2[0] += (double)(r * r);
+        });
+        block_sum_d<1>(acc2, s.dred, c->dsum);
+        grid_allreduce_d(grid, p, c->dsum, 1, dpar);
+        if (threadIdx.x == 0) {
+            float d2 = sqrtf((float)(c->dsum[0] / Nel)) / c->h0;
+            c->dt = init_dt(c->h0, c->d1, d2);
+            c->tprev = c->tcur;
+            c->n_rhs = 2;
+            c->n_steps_interval = 0;
+        }
+        __syncthreads();
+    }
+
+    int next_out = 1;
+    int code = PHX_ST_OK;
+    while (next_out < p.T) {
+        // ---- assertions of rk_common.py:154,175-176 + coefficient table for this dt ----
+        if (threadIdx.x == 0) {
+            int st = 0;
+            if ((long long)c->n_steps_interval >= p.max_steps) st = PHX_ST_MAX_STEPS;
+            else if (!(c->tcur + c->dt > c->tcur)) st = PHX_ST_DT_UNDERFLOW;
+            else if (c->nonfinite_prev) st = PHX_ST_NONFINITE;
+            c->stop = st;
+            if (!st) set_step_coeffs(c);
+        }
+        __syncthreads();
+        if (c->stop) {
+            code = c->stop;
+            break;
+        }
+        int sl[7];
+#pragma unroll
+        for (int i = 0; i < 7; ++i) sl[i] = c->slot[i];
+        {
+            const float c00 = c->cb[0][0];
+            const float* K0 = K(sl[0]);
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                set_stage_input(li, Y[gi] + K0[gi] * c00);
+            });
+            __syncthreads();
+        }
+        double acc[2] = {0, 0};
+        for (int st = 1; st <= 6; ++st) {
+            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                float ys = s.ysb[li];
+                float f = p.fsign * (p.w.relum[g] * (s.jb[li] - ys));
+                K(sl[st])[gi] = f;
+                if (st < 6) {
+                    float a = K(sl[0])[gi] * c->cb[st][0];
+                    for (int q = 1; q < st; ++q) a = fmaf(K(sl[q])[gi], c->cb[st][q], a);
+                    a = fmaf(f, c->cb[st][st], a);
+                    float yn = Y[gi] + a;
+                    if (st == 5) Y1[gi] = yn;
+                    set_stage_input(li, yn);
+                } else {
+                    float e = K(sl[0])[gi] * c->cerr[0];
+                    for (int q = 1; q < 6; ++q) e = fmaf(K(sl[q])[gi], c->cerr[q], e);
+                    e = fmaf(f, c->cerr[6], e);
+                    float tol = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[gi]), fabsf(ys));
+                    float r = e / tol;
+                    acc[0] += (double)(r * r);
+                    if (!isfinite(ys)) acc[1] += 1.0;
+                }
+            });
+            __syncthreads();
+        }
+        block_sum_d<2>(acc, s.dred, c->dsum);
+        grid_allreduce_d(grid, p, c->dsum, 2, dpar);
+        if (threadIdx.x == 0) {
+            float ratio = sqrtf((float)(c->dsum[0] / Nel));
+            int accept = ratio <= 1.f;
+            log_step(p, c, c->tcur, c->dt, accept);
+            c->dt_used = c->dt;
+            c->tprev = c->tcur;
+            if (accept) {
+                c->tcur = c->tcur + c->dt;
+                c->n_acc++;
+                c->nonfinite_prev = c->dsum[1] > 0.0;
+            } else {
+                c->n_rej++;
+            }
+            c->dt = next_dt(c->dt, ratio);
+            c->accept = accept;
+            c->n_rhs += 6;
+            c->n_steps_interval++;
+        }
+        __syncthreads();
+        if (c->accept) {
+            // emit every pending output inside (tprev, tcur] from the quartic interpolant (rk_common.py:157)
+            while (next_out < p.T && p.t[next_out] <= c->tcur) {
+                if (threadIdx.x == 0) set_interp_x(c, p.t[next_out]);
+                __syncthreads();
+                float* yo = p.yout + (size_t)next_out * BG;
+                const float dtf = c->dtf;
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float y0 = Y[gi], y1 = Y1[gi];
+                    float m = K(sl[0])[gi] * c->cmid[0];
+                    for (int q = 1; q < 7; ++q) m = fmaf(K(sl[q])[gi], c->cmid[q], m);
+                    float ymid = y0 + m;
+                    yo[gi] = interp_eval(y0, y1, ymid, K(sl[0])[gi], K(sl[6])[gi], dtf, c->xs);
+                });
+                __syncthreads();
+                ++next_out;
+                if (threadIdx.x == 0) c->n_steps_interval = 0;
+            }
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { Y[gi] = Y1[gi]; });
+            if (threadIdx.x == 0) {
+                int t0 = c->slot[0];
+                c->slot[0] = c->slot[6];
+                c->slot[6] = t0;
+            }
+            __syncthreads();
+        }
+    }
+    __syncthreads();
+    write_status(p, c, code);
+}
+
+// =====================================================================================================================
+// Adjoint sweep
+// =====================================================================================================================
+enum { PP_D01 = 0, PP_D2 = 1, PP_STEP = 2, PP_INTERP = 3, PP_EULER = 4, PP_MIDPOINT = 5, PP_RK4 = 6, PP_COPY = 7 };
+
+struct PPArgs {
+    const float* src;  // theta at step start
+    float* dst;        // where the pass writes (may alias src for the in-place fixed-grid modes)
+    unsigned mask;     // physical stage slots whose derivative is needed
+    int s0, s1, s2, s3;  // slots referenced by name (D01: s0; D2: s0,s1; EULER: s0; MIDPOINT: s1; RK4: s0..s3)
+    float coef_sol[7];   // indexed by PHYSICAL slot
+    float coef_err[7];
+    float coef_mid[7];
+    int slot_first, slot_last;
+    float dtf;
+    float xs[4];
+};
+
+template <int MODE>
+__device__ __forceinline__ void theta_elem(const ResParams& p, const PPArgs& a, size_t idx, const float (&k)[7],
+                                           double& acc0, double& acc1) {
+    if (MODE == PP_COPY) {
+        a.dst[idx] = a.src[idx];
+        return;
+    }
+    float th0 = a.src[idx];
+    if (MODE == PP_D01) {
+        float scale = p.atol_f + fabsf(th0) * p.rtol_f;
+        float r0 = th0 / scale, r1 = k[a.s0] / scale;
+        acc0 += (double)(r0 * r0);
+        acc1 += (double)(r1 * r1);
+    } else if (MODE == PP_D2) {
+        float scale = p.atol_f + fabsf(th0) * p.rtol_f;
+        float r = (k[a.s1] - k[a.s0]) / scale;
+        acc0 += (double)(r * r);
+    } else if (MODE == PP_STEP || MODE == PP_INTERP) {
+        float inc = 0.f, e = 0.f, md = 0.f;
+        bool first = true;
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            if (first) {
+                inc = k[q] * a.coef_sol[q];
+                e = k[q] * a.coef_err[q];
+                md = k[q] * a.coef_mid[q];
+                first = false;
+            } else {
+                inc = fmaf(k[q], a.coef_sol[q], inc);
+                e = fmaf(k[q], a.coef_err[q], e);
+                md = fmaf(k[q], a.coef_mid[q], md);
+            }
+        }
+        float th1 = th0 + inc;
+        if (MODE == PP_STEP) {
+            float tol = p.atol_f + p.rtol_f * fmaxf(fabsf(th0), fabsf(th1));
+            float r = e / tol;
+            acc0 += (double)(r * r);
+            if (!isfinite(th1)) acc1 += 1.0;
+            a.dst[idx] = th1;
+        } else {
+            float ymid = th0 + md;
+            a.dst[idx] = interp_eval(th0, th1, ymid, k[a.slot_first], k[a.slot_last], a.dtf, a.xs);
+        }
+    } else if (MODE == PP_EULER) {
+        a.dst[idx] = th0 + a.dtf * k[a.s0];
+    } else if (MODE == PP_MIDPOINT) {
+        a.dst[idx] = th0 + a.dtf * k[a.s1];
+    } else if (MODE == PP_RK4) {
+        float dy = (k[a.s0] + 3.f * (k[a.s1] + k[a.s2]) + k[a.s3]) * a.dtf * 0.125f;
+        a.dst[idx] = th0 + dy;
+    }
+}
+
+// calls f(r, c) for every (r < R, c < C) with c fastest across threads
+template <typename F>
+__device__ __forceinline__ void tile2d(int R, int C, F f) {
+    if (C >= THREADS) {
+        for (int r = 0; r < R; ++r)
+            for (int c = threadIdx.x; c < C; c += THREADS) f(r, c);
+    } else {
+        const int RY = THREADS / C;
+        const int ry = threadIdx.x / C, cx = threadIdx.x - ry * C;
+        if (ry < RY)
+            for (int r = ry; r < R; r += RY) f(r, cx);
+    }
+}
+
+// One pass over this CTA's share of the P-long parameter-cotangent vector.  Stage derivative of an element in
+// physical slot q is the rank-B outer product of that stage's factors:
+//   m[g]      : pM[q][g]
+//   Wp[h][g]  : sum_b gLP[q][b][h] * l[q][b][g]        bp[h] : sum_b gLP[q][b][h]
+//   Ws[h][g]  : sum_b gS [q][b][h] * s[q][b][g]        bs[h] : sum_b gS [q][b][h]
+//   Wa[g][k]  : sum_b gJ [q][b][g] * SP[q][b][k]
+template <int MODE>
+__device__ void ppass(const ResParams& p, const Smem& s, int g_lo, int n_loc, const PPArgs& a, double& acc0,
+                      double& acc1) {
+    const PhxGradOff off = phx_grad_offsets(p.G, p.H);
+    const int B = p.B, K2 = p.K2, Hp = p.Hp, H = p.H, G = p.G, gpc = p.gpc;
+    const unsigned mask = (MODE == PP_COPY) ? 0u : a.mask;
+    // m
+    for (int j = threadIdx.x; j < n_loc; j += THREADS) {
+        float k[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) k[q] = (mask >> q & 1u) ? s.pM[q * gpc + j] : 0.f;
+        theta_elem<MODE>(p, a, off.m + g_lo + j, k, acc0, acc1);
+    }
+    // Wp, Ws : rows h, this CTA's gene columns
+    tile2d(H, n_loc, [&](int h, int j) {
+        float kp[7], ks[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            float tp = 0.f, ts = 0.f;
+            if (mask >> q & 1u) {
+                for (int b = 0; b < B; ++b) {
+                    const float* g = s.pG + (size_t)(q * B + b) * K2;
+                    tp = fmaf(g[Hp + h], s.pL[(q * B + b) * gpc + j], tp);
+                    ts = fmaf(g[h], s.pS[(q * B + b) * gpc + j], ts);
+                }
+            }
+            kp[q] = tp;
+            ks[q] = ts;
+        }
+        theta_elem<MODE>(p, a, off.Wp + (size_t)h * G + g_lo + j, kp, acc0, acc1);
+        theta_elem<MODE>(p, a, off.Ws + (size_t)h * G + g_lo + j, ks, acc0, acc1);
+    });
+    // Wa : this CTA's gene rows, 2H columns
+    tile2d(n_loc, 2 * H, [&](int j, int kk) {
+        const int kcol = (kk < H) ? kk : (Hp + kk - H);
+        float k[7];
+#pragma unroll
+        for (int q = 0; q < 7; ++q) {
+            float t = 0.f;
+            if (mask >> q & 1u) {
+                for (int b = 0; b < B; ++b)
+                    t = fmaf(s.pGJ[(q * B + b) * gpc + j], s.pSP[(size_t)(q * B + b) * K2 + kcol], t);
+            }
+            k[q] = t;
+        }
+        theta_elem<MODE>(p, a, off.Wa + (size_t)(g_lo + j) * 2 * H + kk, k, acc0, acc1);
+    });
+    // biases : CTA 0
+    if (blockIdx.x == 0) {
+        for (int h = threadIdx.x; h < H; h += THREADS) {
+            float kp[7], ks[7];
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                float tp = 0.f, ts = 0.f;
+                if (mask >> q & 1u) {
+                    for (int b = 0; b < B; ++b) {
+                        const float* g = s.pG + (size_t)(q * B + b) * K2;
+                        tp += g[Hp + h];
+                        ts += g[h];
+                    }
+                }
+                kp[q] = tp;
+                ks[q] = ts;
+            }
+            theta_elem<MODE>(p, a, off.bp + h, kp, acc0, acc1);
+            theta_elem<MODE>(p, a, off.bs + h, ks, acc0, acc1);
+        }
+    }
+}
+
+template <int NV, int BT>
+__global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Smem s;
+    smem_layout(p.B, p.K2, p.gpc, 1, &s, smem_raw);
+    Ctrl* c = s.ctrl;
+    const int g_lo = blockIdx.x * p.gpc;
+    const int n_loc = max(0, min(p.gpc, p.G - g_lo));
+    const size_t BG = (size_t)p.B * p.G;
+    const double Nel = (double)p.B * (double)p.G;
+    const PhxGradOff goff = phx_grad_offsets(p.G, p.H);
+    const double Pel = (double)goff.total;
+    float* Y = slot_ptr(p, 0);
+    float* A = slot_ptr(p, 1);
+    float* Y1 = slot_ptr(p, 2);
+    float* A1 = slot_ptr(p, 3);
+    auto KY = [&](int i) { return slot_ptr(p, 4 + i); };
+    auto KA = [&](int i) { return slot_ptr(p, 11 + i); };
+    int dpar = 0;
+    int cur = 0;  // which theta buffer holds the current value
+    float* theta[2] = {p.theta0, p.theta1};
+
+    if (threadIdx.x == 0) {
+        c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
+        c->stop = 0;
+        c->tcur = 0;
+        c->dt = 0;
+    }
+    __syncthreads();
+
+    // stage input (y, a) -> smem activations and gJ = a * relu(m)
+    auto set_stage_input = [&](int li, int g, float ys, float as) {
+        s.ysb[li] = ys;
+        s.asb[li] = as;
+        float sv, lv, den;
+        hill(ys, sv, lv, den);
+        s.acts[li] = sv;
+        s.actl[li] = lv;
+        s.gjb[li] = as * p.w.relum[g];
+    };
+    // after eval_adj: stage derivatives of the y and a blocks (reverse time: ky = -f, ka = VJP_y with cotangent a)
+    // and this stage's per-gene factors into slot `slot`
+    auto stage_epilogue = [&](int slot) {
+        float* ky = KY(slot);
+        float* ka = KA(slot);
+        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+            float y = s.ysb[li], av = s.asb[li];
+            float jm = s.jb[li] - y;
+            float f = p.w.relum[g] * jm;
+            float sv = s.acts[li];
+            float z = y - 0.5f;
+            float den = 1.0f + fabsf(z);
+            float yb = (s.ub[li] + s.vb[li] / (1.0f + sv)) / (den * den);
+            yb = yb - s.gjb[li];
+            ky[gi] = -f;
+            ka[gi] = yb;
+            s.mt[li] = av * jm;
+            s.pS[slot * p.B * p.gpc + li] = sv;
+            s.pL[slot * p.B * p.gpc + li] = s.actl[li];
+            s.pGJ[slot * p.B * p.gpc + li] = s.gjb[li];
+        });
+        __syncthreads();
+        for (int j = threadIdx.x; j < n_loc; j += THREADS) {
+            float t = 0.f;
+            for (int b = 0; b < p.B; ++b) t += s.mt[b * p.gpc + j];
+            s.pM[slot * p.gpc + j] = t * p.w.maskm[g_lo + j];
+        }
+        __syncthreads();
+    };
+
+    int code = PHX_ST_OK;
+    for (int iv = p.T - 1; iv >= 1 && code == PHX_ST_OK; --iv) {
+        const float* ysv = p.ysaved + (size_t)iv * BG;
+        const float* gy = p.grad_y + (size_t)iv * BG;
+        const bool first_iv = (iv == p.T - 1);
+        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+            float y = ysv[gi];
+            float av = first_iv ? gy[gi] : A[gi];
+            Y[gi] = y;
+            A[gi] = av;
+            set_stage_input(li, g, y, av);
+        });
+        __syncthreads();
+        const double t_start = -p.t[iv], t_end = -p.t[iv - 1];
+
+        if (p.method != PHX_DOPRI5) {
+            const float dtf = p.t_is_f32 ? ((float)p.t[iv] - (float)p.t[iv - 1]) : (float)(p.t[iv] - p.t[iv - 1]);
+            const float third = (float)(1.0 / 3.0);
+            PPArgs pa;
+            pa.src = theta[0];
+            pa.dst = theta[0];
+            pa.dtf = dtf;
+            pa.s0 = 0; pa.s1 = 1; pa.s2 = 2; pa.s3 = 3;
+            double d0 = 0, d1 = 0;
+            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0);
+            stage_epilogue(0);
+            if (p.method == PHX_EULER) {
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    A[gi] = A[gi] + dtf * KA(0)[gi];
+                });
+                pa.mask = 1u;
+                ppass<PP_EULER>(p, s, g_lo, n_loc, pa, d0, d1);
+            } else if (p.method == PHX_MIDPOINT) {
+                const float half = 0.5f * dtf;
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    set_stage_input(li, g, Y[gi] + KY(0)[gi] * half, A[gi] + KA(0)[gi] * half);
+                });
+                __syncthreads();
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1);
+                stage_epilogue(1);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    A[gi] = A[gi] + dtf * KA(1)[gi];
+                });
+                pa.mask = 2u;
+                ppass<PP_MIDPOINT>(p, s, g_lo, n_loc, pa, d0, d1);
+            } else {
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    set_stage_input(li, g, Y[gi] + dtf * KY(0)[gi] * third, A[gi] + dtf * KA(0)[gi] * third);
+                });
+                __syncthreads();
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1);
+                stage_epilogue(1);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    set_stage_input(li, g, Y[gi] + dtf * (KY(1)[gi] - KY(0)[gi] * third),
+                                    A[gi] + dtf * (KA(1)[gi] - KA(0)[gi] * third));
+                });
+                __syncthreads();
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 2);
+                stage_epilogue(2);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    set_stage_input(li, g, Y[gi] + dtf * (KY(0)[gi] - KY(1)[gi] + KY(2)[gi]),
+                                    A[gi] + dtf * (KA(0)[gi] - KA(1)[gi] + KA(2)[gi]));
+                });
+                __syncthreads();
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 3);
+                stage_epilogue(3);
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float dy = (KA(0)[gi] + 3.f * (KA(1)[gi] + KA(2)[gi]) + KA(3)[gi]) * dtf * 0.125f;
+                    A[gi] = A[gi] + dy;
+                });
+                pa.mask = 15u;
+                ppass<PP_RK4>(p, s, g_lo, n_loc, pa, d0, d1);
+            }
+            if (threadIdx.x == 0) {
+                int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
+                c->n_rhs += per;
+                c->tcur = t_end;
+            }
+            __syncthreads();
+        } else {
+            // ------------------------------ dopri5 on the augmented state ------------------------------
+            if (threadIdx.x == 0) {
+                c->tcur = t_start;
+                c->tprev = t_start;
+                c->t_end = t_end;
+                c->n_steps_interval = 0;
+                for (int i = 0; i < 7; ++i) c->slot[i] = i;
+            }
+            __syncthreads();
+            // f0 and Hairer's initial step under the mixed norm max(RMS_y, RMS_a, RMS_theta)
+            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0);
+            stage_epilogue(0);
+            {
+                double acc[7] = {0, 0, 0, 0, 0, 0, 0};
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float y = Y[gi], av = A[gi];
+                    float sy = p.atol_f + fabsf(y) * p.rtol_f, sa = p.atol_f + fabsf(av) * p.rtol_f;
+                    float r;
+                    r = y / sy; acc[0] += (double)(r * r);
+                    r = av / sa; acc[1] += (double)(r * r);
+                    r = KY(0)[gi] / sy; acc[3] += (double)(r * r);
+                    r = KA(0)[gi] / sa; acc[4] += (double)(r * r);
+                    if (!isfinite(y) || !isfinite(av)) acc[6] += 1.0;
+                });
+                PPArgs pa;
+                pa.src = theta[cur];
+                pa.dst = nullptr;
+                pa.mask = 1u;
+                pa.s0 = 0;
+                ppass<PP_D01>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
+                block_sum_d<7>(acc, s.dred, c->dsum);
+                grid_allreduce_d(grid, p, c->dsum, 7, dpar);
+                if (threadIdx.x == 0) {
+                    float d0 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
+                                     sqrtf((float)(c->dsum[2] / Pel)));
+                    float d1 = fmaxf(fmaxf(sqrtf((float)(c->dsum[3] / Nel)), sqrtf((float)(c->dsum[4] / Nel))),
+                                     sqrtf((float)(c->dsum[5] / Pel)));
+                    c->d1 = d1;
+                    c->h0 = init_h0(d0, d1);
+                    c->nonfinite_prev = c->dsum[6] > 0.0;
+                }
+                __syncthreads();
+                const float h0 = c->h0;
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    set_stage_input(li, g, Y[gi] + h0 * KY(0)[gi], A[gi] + h0 * KA(0)[gi]);
+                });
+                __syncthreads();
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1);
+                stage_epilogue(1);
+                double acc2[3] = {0, 0, 0};
+                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                    float sy = p.atol_f + fabsf(Y[gi]) * p.rtol_f, sa = p.atol_f + fabsf(A[gi]) * p.rtol_f;
+                    float r;
+                    r = (KY(1)[gi] - KY(0)[gi]) / sy; acc2[0] += (double)(r * r);
+                    r = (KA(1)[gi] - KA(0)[gi]) / sa; acc2[1] += (double)(r * r);
+                });
+                pa.mask = 3u;
+                pa.s0 = 0;
+                pa.s1 = 1;
+                double dummy = 0;
+                ppass<PP_D2>(p, s, g_lo, n_loc, pa, acc2[2], dummy);
+                block_sum_d<3>(acc2, s.dred, c->dsum);
+                grid_allreduce_d(grid, p, c->dsum, 3, dpar);
+                if (threadIdx.x == 0) {
+                    float d2 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
+                                     sqrtf((float)(c->dsum[2] / Pel))) / c->h0;
+                    c->dt = init_dt(c->h0, c->d1, d2);
+                    c->n_rhs += 2;
+                }
+                __syncthreads();
+            }
+            bool done = false;
+            while (!done) {
+                if (threadIdx.x == 0) {
+                    int st = 0;
+                    if ((long long)c->n_steps_interval >= p.max_steps) st = PHX_ST_MAX_STEPS;
+                    else if (!(c->tcur + c->dt > c->tcur)) st = PHX_ST_DT_UNDERFLOW;
+                    else if (c->nonfinite_prev) st = PHX_ST_NONFINITE;
+                    c->stop = st;
+                    if (!st) set_step_coeffs(c);
+                }
+                __syncthreads();
+                if (c->stop) {
+                    code = c->stop;
+                    break;
+                }
+                int sl[7];
+#pragma unroll
+                for (int i = 0; i < 7; ++i) sl[i] = c->slot[i];
+                {
+                    const float c00 = c->cb[0][0];
+                    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                        set_stage_input(li, g, Y[gi] + KY(sl[0])[gi] * c00, A[gi] + KA(sl[0])[gi] * c00);
+                    });
+                    __syncthreads();
+                }
+                double acc[4] = {0, 0, 0, 0};
+                for (int st = 1; st <= 6; ++st) {
+                    eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, sl[st]);
+                    stage_epilogue(sl[st]);
+                    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                        if (st < 6) {
+                            float ay = KY(sl[0])[gi] * c->cb[st][0];
+                            float aa = KA(sl[0])[gi] * c->cb[st][0];
+                            for (int q = 1; q <= st; ++q) {
+                                ay = fmaf(KY(sl[q])[gi], c->cb[st][q], ay);
+                                aa = fmaf(KA(sl[q])[gi], c->cb[st][q], aa);
+                            }
+                            float yn = Y[gi] + ay, an = A[gi] + aa;
+                            if (st == 5) {
+                                Y1[gi] = yn;
+                                A1[gi] = an;
+                            }
+                            set_stage_input(li, g, yn, an);
+                        } else {
+                            float ey = KY(sl[0])[gi] * c->cerr[0];
+                            float ea = KA(sl[0])[gi] * c->cerr[0];
+                            for (int q = 1; q < 7; ++q) {
+                                ey = fmaf(KY(sl[q])[gi], c->cerr[q], ey);
+                                ea = fmaf(KA(sl[q])[gi], c->cerr[q], ea);
+                            }
+                            float y1 = s.ysb[li], a1 = s.asb[li];
+                            float ty = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[gi]), fabsf(y1));
+                            float ta = p.atol_f + p.rtol_f * fmaxf(fabsf(A[gi]), fabsf(a1));
+                            float r;
+                            r = ey / ty; acc[0] += (double)(r * r);
+                            r = ea / ta; acc[1] += (double)(r * r);
+                            if (!isfinite(y1) || !isfinite(a1)) acc[3] += 1.0;
+                        }
+                    });
+                    __syncthreads();
+                }
+                PPArgs pa;
+                pa.src = theta[cur];
+                pa.dst = theta[cur ^ 1];
+                pa.mask = 127u;
+                pa.dtf = c->dtf;
+                for (int q = 0; q < 7; ++q) {
+                    pa.coef_sol[sl[q]] = (q < 6) ? c->cb[5][q] : 0.f;
+                    pa.coef_err[sl[q]] = c->cerr[q];
+                    pa.coef_mid[sl[q]] = c->cmid[q];
+                }
+                pa.slot_first = sl[0];
+                pa.slot_last = sl[6];
+                ppass<PP_STEP>(p, s, g_lo, n_loc, pa, acc[2], acc[3]);
+                block_sum_d<4>(acc, s.dred, c->dsum);
+                grid_allreduce_d(grid, p, c->dsum, 4, dpar);
+                if (threadIdx.x == 0) {
+                    float ratio = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
+                                        sqrtf((float)(c->dsum[2] / Pel)));
+                    // torch's max() over 0-dim tensors is Python max: a NaN in a later block does not propagate the
+                    // same way; treat any NaN as NaN (step rejected, dt -> NaN -> underflow assertion)
+                    if (isnan(c->dsum[0]) || isnan(c->dsum[1]) || isnan(c->dsum[2])) ratio = nanf("");
+                    int accept = ratio <= 1.f;
+                    log_step(p, c, c->tcur, c->dt, accept);
+                    c->tprev = c->tcur;
+                    if (accept) {
+                        c->tcur = c->tcur + c->dt;
+                        c->n_acc++;
+                        c->nonfinite_prev = c->dsum[3] > 0.0;
+                    } else {
+                        c->n_rej++;
+                    }
+                    c->dt = next_dt(c->dt, ratio);
+                    c->accept = accept;
+                    c->n_rhs += 6;
+                    c->n_steps_interval++;
+                    if (accept && !(c->t_end > c->tcur)) set_interp_x(c, c->t_end);
+                }
+                __syncthreads();
+                if (c->accept) {
+                    if (!(c->t_end > c->tcur)) {
+                        // last step of the interval: dense output at t_end for adj_y and adj_params
+                        const float dtf = c->dtf;
+                        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                            float a0 = A[gi], a1 = A1[gi];
+                            float m = KA(sl[0])[gi] * c->cmid[0];
+                            for (int q = 1; q < 7; ++q) m = fmaf(KA(sl[q])[gi], c->cmid[q], m);
+                            A[gi] = interp_eval(a0, a1, a0 + m, KA(sl[0])[gi], KA(sl[6])[gi], dtf, c->xs);
+                        });
+                        for (int q = 0; q < 4; ++q) pa.xs[q] = c->xs[q];
+                        double d0 = 0, d1 = 0;
+                        ppass<PP_INTERP>(p, s, g_lo, n_loc, pa, d0, d1);
+                        cur ^= 1;
+                        done = true;
+                    } else {
+                        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                            Y[gi] = Y1[gi];
+                            A[gi] = A1[gi];
+                        });
+                        cur ^= 1;
+                        if (threadIdx.x == 0) {
+                            int t0 = c->slot[0];
+                            c->slot[0] = c->slot[6];
+                            c->slot[6] = t0;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+        }
+        // interval done: adj_y picks up the loss gradient at t[iv-1] (adjoint.py:152-154)
+        if (code == PHX_ST_OK) {
+            const float* gprev = p.grad_y + (size_t)(iv - 1) * BG;
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { A[gi] = A[gi] + gprev[gi]; });
+            __syncthreads();
+        }
+    }
+    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { p.adj_y0[gi] = A[gi]; });
+    if (cur != 0) {
+        PPArgs pa;
+        pa.src = theta[1];
+        pa.dst = theta[0];
+        pa.mask = 0;
+        double d0 = 0, d1 = 0;
+        const float zero[7] = {0, 0, 0, 0, 0, 0, 0};
+        (void)zero;
+        ppass<PP_COPY>(p, s, g_lo, n_loc, pa, d0, d1);
+    }
+    __syncthreads();
+    write_status(p, c, code);
+}
+
+}  // namespace

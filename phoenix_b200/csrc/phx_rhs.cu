@@ -1,0 +1,333 @@
+// Stand-alone batched RHS and RHS-VJP for any number of rows B (ODENet.forward / prior_only_forward called directly,
+// e.g. the 10 000-row prior batch of train_insilico.py:134, and their ordinary-autograd backward).
+//
+// fp32 CUDA-core path: every contraction is one launch of a functor-driven tiled SGEMM (64x64x16 tiles, 4x4 register
+// micro-tiles) whose operand loaders fuse the Hill activations / decay factors and whose epilogues fuse bias, exp, the
+// decay term and the cotangent algebra, so no activation tensor is ever materialised in HBM:
+//   SP  [B][K2] = act(y) W1            (+bias, exp on the prods half)                    odenet.py:86-88
+//   f   [B][G]  = relu(m) (SP WA^T - y)                                                 odenet.py:89-90
+//   GS  [B][K2] = (g relu(m)) WA       (prods half scaled by Pr)                         exp / Linear backward
+//   ybar[B][G]  = (GS_s Ws + (GS_p Wp)/(1+s)) / (1+|y-.5|)^2 - g relu(m)                 soft-sign / log1p backward
+//   Wa_bar = gJ^T SP,  Ws_bar = GS_s^T s,  Wp_bar = GS_p^T l,  biases / multipliers: column sums
+// The tcgen05 (3xTF32) variant of the same decomposition replaces sgemm_kernel for large B in a later round.
+#include <math.h>
+#include "phx_common.cuh"
+
+namespace {
+
+constexpr int BM = 64, BN = 64, BK = 16, GT = 256;
+
+template <typename LA, typename LB, typename EPI>
+__global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, LA la, LB lb, EPI epi) {
+    __shared__ float As[BK][BM + 4];
+    __shared__ float Bs[BK][BN + 4];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    float acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+        for (int i = tid; i < BM * BK; i += GT) {
+            int m, kk;
+            if (LA::k_contig) { kk = i % BK; m = i / BK; } else { m = i % BM; kk = i / BM; }
+            As[kk][m] = (m0 + m < M && k0 + kk < K) ? la(m0 + m, k0 + kk) : 0.f;
+        }
+        for (int i = tid; i < BN * BK; i += GT) {
+            int n, kk;
+            if (LB::n_contig) { n = i % BN; kk = i / BN; } else { kk = i % BK; n = i / BK; }
+            Bs[kk][n] = (n0 + n < N && k0 + kk < K) ? lb(k0 + kk, n0 + n) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            float a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            int m = m0 + ty * 4 + i, n = n0 + tx * 4 + j;
+            if (m < M && n < N) epi(m, n, acc[i][j]);
+        }
+}
+
+template <typename LA, typename LB, typename EPI>
+void sgemm(int M, int N, int K, LA la, LB lb, EPI epi, cudaStream_t st) {
+    if (M <= 0 || N <= 0) return;
+    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+    sgemm_kernel<<<grid, GT, 0, st>>>(M, N, K, la, lb, epi);
+}
+
+__device__ __forceinline__ void hill(float y, float& s, float& l, float& den) {
+    float z = y - 0.5f;
+    den = 1.0f + fabsf(z);
+    s = z / den;
+    l = log1pf(s);
+}
+
+// ---- operand loaders -----------------------------------------------------------------------------------------------
+// A(b, g) = s(y[b][g]) or l(y[b][g])
+struct LoadAct {
+    static constexpr bool k_contig = true;
+    const float* y; int G; int use_l;
+    __device__ float operator()(int b, int g) const {
+        float s, l, den;
+        hill(y[(size_t)b * G + g], s, l, den);
+        return use_l ? l : s;
+    }
+};
+// B(g, n) = W[g][col0 + n]   (row-major packed weight, n contiguous)
+struct LoadWrow {
+    static constexpr bool n_contig = true;
+    const float* W; int ld; int col0;
+    __device__ float operator()(int g, int n) const { return __ldg(W + (size_t)g * ld + col0 + n); }
+};
+// A(b, k) = X[b][col0 + k]
+struct LoadRowMajorA {
+    static constexpr bool k_contig = true;
+    const float* X; int ld; int col0;
+    __device__ float operator()(int b, int k) const { return X[(size_t)b * ld + col0 + k]; }
+};
+// B(k, g) = W[g][col0 + k]  (transposed use of a packed weight: k contiguous)
+struct LoadWcol {
+    static constexpr bool n_contig = false;
+    const float* W; int ld; int col0;
+    __device__ float operator()(int k, int g) const { return __ldg(W + (size_t)g * ld + col0 + k); }
+};
+// A(b, g) = g_cot[b][g] * (decay ? relum[g] : 1)
+struct LoadGJ {
+    static constexpr bool k_contig = true;
+    const float* g; const float* relum; int G; int decay;
+    __device__ float operator()(int b, int gg) const {
+        float v = g[(size_t)b * G + gg];
+        return decay ? v * relum[gg] : v;
+    }
+};
+// A(m, b) = X[b][col0 + m]  (X^T, m contiguous)
+struct LoadTransA {
+    static constexpr bool k_contig = false;
+    const float* X; int ld; int col0;
+    __device__ float operator()(int m, int b) const { return X[(size_t)b * ld + col0 + m]; }
+};
+struct LoadGJT {  // A(g, b) = gJ[b][g]
+    static constexpr bool k_contig = false;
+    const float* g; const float* relum; int G; int decay;
+    __device__ float operator()(int gg, int b) const {
+        float v = g[(size_t)b * G + gg];
+        return decay ? v * relum[gg] : v;
+    }
+};
+struct LoadActB {  // B(b, g) = s or l of y[b][g]
+    static constexpr bool n_contig = true;
+    const float* y; int G; int use_l;
+    __device__ float operator()(int b, int g) const {
+        float s, l, den;
+        hill(y[(size_t)b * G + g], s, l, den);
+        return use_l ? l : s;
+    }
+};
+struct LoadRowMajorB {  // B(b, n) = X[b][col0+n]
+    static constexpr bool n_contig = true;
+    const float* X; int ld; int col0;
+    __device__ float operator()(int b, int n) const { return X[(size_t)b * ld + col0 + n]; }
+};
+
+// ---- epilogues --------------------------------------------------------------------------------------------------------
+struct EpiSP {  // SP[b][col0+n] = acc + bias ; exp on prods half ; pads -> 0
+    float* SP; const float* bias; int K2, Hp, H, col0;
+    __device__ void operator()(int b, int n, float acc) const {
+        int k = col0 + n;
+        float v = acc + bias[k];
+        if (k >= Hp) v = (k - Hp < H) ? expf(v) : 0.f;
+        SP[(size_t)b * K2 + k] = v;
+    }
+};
+struct EpiF {  // f = decay ? relum*(J - y) : J
+    float* f; const float* y; const float* relum; int G; int decay;
+    __device__ void operator()(int b, int g, float acc) const {
+        size_t i = (size_t)b * G + g;
+        f[i] = decay ? relum[g] * (acc - y[i]) : acc;
+    }
+};
+struct EpiGS {  // GS[b][k] = acc (sums half) or acc * Pr (prods half)
+    float* GS; const float* SP; int K2, Hp;
+    __device__ void operator()(int b, int k, float acc) const {
+        size_t i = (size_t)b * K2 + k;
+        GS[i] = (k >= Hp) ? acc * SP[i] : acc;
+    }
+};
+struct EpiStore {  // plain store into [M][ld]
+    float* C; int ld;
+    __device__ void operator()(int m, int n, float acc) const { C[(size_t)m * ld + n] = acc; }
+};
+struct EpiYbar {  // ybar = (u + v/(1+s))/den^2 - gJ   (u held in ybar from the first pass, acc = v)
+    float* ybar; const float* y; const float* g; const float* relum; int G; int decay;
+    __device__ void operator()(int b, int gg, float acc) const {
+        size_t i = (size_t)b * G + gg;
+        float s, l, den;
+        hill(y[i], s, l, den);
+        float r = (ybar[i] + acc / (1.0f + s)) / (den * den);
+        if (decay) r = r - g[i] * relum[gg];
+        ybar[i] = r;
+    }
+};
+struct EpiGrad {  // grads[off + m*ld + n] (+)= acc
+    float* dst; int ld; int accumulate;
+    __device__ void operator()(int m, int n, float acc) const {
+        size_t i = (size_t)m * ld + n;
+        dst[i] = accumulate ? dst[i] + acc : acc;
+    }
+};
+struct EpiGradWa {  // m = gene, n = packed column -> Wa_bar[g][2H] (skip pads)
+    float* dst; int H, Hp; int accumulate;
+    __device__ void operator()(int gg, int k, float acc) const {
+        int col;
+        if (k < Hp) { if (k >= H) return; col = k; } else { if (k - Hp >= H) return; col = H + k - Hp; }
+        size_t i = (size_t)gg * 2 * H + col;
+        dst[i] = accumulate ? dst[i] + acc : acc;
+    }
+};
+
+// column sums over the B rows (biases, multipliers): one thread per column, fixed order
+__global__ void colsum_bias_kernel(const float* GS, int B, int K2, int Hp, int H, float* bs_bar, float* bp_bar,
+                                   int accumulate) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= 2 * H) return;
+    int col = (k < H) ? k : (Hp + k - H);
+    float t = 0.f;
+    for (int b = 0; b < B; ++b) t += GS[(size_t)b * K2 + col];
+    float* dst = (k < H) ? (bs_bar + k) : (bp_bar + (k - H));
+    *dst = accumulate ? *dst + t : t;
+}
+__global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const float* y, const float* maskm, int B,
+                                   int G, float* m_bar, int accumulate, int decay) {
+    int gg = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gg >= G) return;
+    float t = 0.f;
+    if (decay) {
+        for (int b = 0; b < B; ++b) {
+            size_t i = (size_t)b * G + gg;
+            t += g[i] * (f_nodecay[i] - y[i]);
+        }
+        t *= maskm[gg];
+    }
+    m_bar[gg] = accumulate ? m_bar[gg] + t : t;
+}
+
+}  // namespace
+
+size_t phx_rhs_workspace_floats(int G, int H, int B) {
+    size_t K2 = (size_t)phx_K2(H);
+    // SP, GS : [B][K2] each ; J : [B][G]
+    return 2 * (size_t)B * K2 + (size_t)B * G + 16;
+}
+
+static void rhs_sp(int G, int H, int B, const PhxPacked& w, const float* y, float* SP, cudaStream_t st) {
+    const int Hp = phx_Hp(H), K2 = 2 * Hp;
+    const float* W1 = reinterpret_cast<const float*>(w.W1);
+    for (int half = 0; half < 2; ++half) {
+        LoadAct la{y, G, half};
+        LoadWrow lb{W1, K2, half * Hp};
+        EpiSP ep{SP, w.bias, K2, Hp, H, half * Hp};
+        sgemm(B, Hp, G, la, lb, ep, st);
+    }
+}
+
+int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float* ws,
+                           cudaStream_t st) {
+    const int K2 = phx_K2(H);
+    float* SP = ws;
+    rhs_sp(G, H, B, w, y, SP, st);
+    LoadRowMajorA la{SP, K2, 0};
+    LoadWcol lb{reinterpret_cast<const float*>(w.WA), K2, 0};
+    EpiF ep{f, y, w.relum, G, decay};
+    sgemm(B, G, K2, la, lb, ep, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("rhs_forward launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
+                       float* ybar, float* grads, int accumulate, float* ws, cudaStream_t st) {
+    const int Hp = phx_Hp(H), K2 = 2 * Hp;
+    float* SP = ws;
+    float* GS = ws + (size_t)B * K2;
+    float* J = GS + (size_t)B * K2;
+    const float* W1 = reinterpret_cast<const float*>(w.W1);
+    const float* WA = reinterpret_cast<const float*>(w.WA);
+    rhs_sp(G, H, B, w, y, SP, st);
+    // GS = gJ WA, prods half scaled by Pr
+    {
+        LoadGJ la{g, w.relum, G, decay};
+        LoadWrow lb{WA, K2, 0};
+        EpiGS ep{GS, SP, K2, Hp};
+        sgemm(B, K2, G, la, lb, ep, st);
+    }
+    if (ybar) {
+        {   // u = GS_s Ws
+            LoadRowMajorA la{GS, K2, 0};
+            LoadWcol lb{W1, K2, 0};
+            EpiStore ep{ybar, G};
+            sgemm(B, G, Hp, la, lb, ep, st);
+        }
+        {   // v = GS_p Wp, combine
+            LoadRowMajorA la{GS, K2, Hp};
+            LoadWcol lb{W1, K2, Hp};
+            EpiYbar ep{ybar, y, g, w.relum, G, decay};
+            sgemm(B, G, Hp, la, lb, ep, st);
+        }
+    }
+    if (grads) {
+        const PhxGradOff off = phx_grad_offsets(G, H);
+        {   // Wa_bar[g][k] = sum_b gJ[b][g] SP[b][k]
+            LoadGJT la{g, w.relum, G, decay};
+            LoadRowMajorB lb{SP, K2, 0};
+            EpiGradWa ep{grads + off.Wa, H, Hp, accumulate};
+            sgemm(G, K2, B, la, lb, ep, st);
+        }
+        {   // Ws_bar[h][g] = sum_b GS[b][h] s[b][g]
+            LoadTransA la{GS, K2, 0};
+            LoadActB lb{y, G, 0};
+            EpiGrad ep{grads + off.Ws, G, accumulate};
+            sgemm(H, G, B, la, lb, ep, st);
+        }
+        {   // Wp_bar[h][g] = sum_b GS[b][Hp+h] l[b][g]
+            LoadTransA la{GS, K2, Hp};
+            LoadActB lb{y, G, 1};
+            EpiGrad ep{grads + off.Wp, G, accumulate};
+            sgemm(H, G, B, la, lb, ep, st);
+        }
+        colsum_bias_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(GS, B, K2, Hp, H, grads + off.bs, grads + off.bp,
+                                                                accumulate);
+        if (decay) {   // J (no decay) for the multiplier cotangent
+            LoadRowMajorA la{SP, K2, 0};
+            LoadWcol lb{WA, K2, 0};
+            EpiF ep{J, y, w.relum, G, 0};
+            sgemm(B, G, K2, la, lb, ep, st);
+        }
+        colsum_mult_kernel<<<(G + 127) / 128, 128, 0, st>>>(g, J, y, w.maskm, B, G, grads + off.m, accumulate,
+                                                            decay);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("rhs_vjp launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}

@@ -1,0 +1,318 @@
+"""Host-side glue between torch tensors and the C ABI: packed-weight cache, workspaces, status records.
+
+PyTorch is used here only as the owner of device memory and streams; every kernel lives in libphoenix_b200.so.
+"""
+import ctypes
+import threading
+import weakref
+
+import torch
+
+from . import _lib
+
+# solver "assert" conditions (rk_common.py:154,175-176) are checked when the status record is read.  With
+# SYNC_ERRORS the stream is synchronised after every solve and the reference's AssertionError is raised at the call
+# site (exact reference behaviour); otherwise the records are inspected lazily (next call / check_errors()), which
+# keeps the host running ahead of the GPU.
+SYNC_ERRORS = False
+STEP_LOGGING = False
+STEPLOG_CAP = 4096
+
+_state = threading.local()
+
+
+def set_sync_errors(flag):
+    global SYNC_ERRORS
+    SYNC_ERRORS = bool(flag)
+
+
+def set_step_logging(flag):
+    """Record (t0, dt, accepted) for every attempted adaptive step of subsequent solves (tests / diagnostics)."""
+    global STEP_LOGGING
+    STEP_LOGGING = bool(flag)
+
+
+def _tls():
+    if not hasattr(_state, "pending"):
+        _state.pending = []       # [(status_tensor, what)]
+        _state.free_status = []
+        _state.last_log = None
+        _state.last_status = None
+        _state.workspaces = {}
+    return _state
+
+
+def _device_index(t):
+    if not t.is_cuda:
+        raise RuntimeError(
+            "phoenix_b200 runs the PHOENIX hot path on a B200 only: got a tensor on %s. Move the model and its inputs "
+            "to 'cuda' (there is no CPU fallback)." % t.device)
+    return t.device.index if t.device.index is not None else torch.cuda.current_device()
+
+
+def _stream_ptr(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _workspace(dev, nbytes, tag):
+    tls = _tls()
+    key = (dev, tag, torch.cuda.current_stream(dev).cuda_stream)
+    ws = tls.workspaces.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=torch.device("cuda", dev))
+        tls.workspaces[key] = ws
+    return ws
+
+
+# ---- packed weights ------------------------------------------------------------------------------------------------
+_PARAM_GETTERS = (
+    lambda n: n.gene_multipliers,
+    lambda n: n.net_prods.linear_out.weight,
+    lambda n: n.net_prods.linear_out.bias,
+    lambda n: n.net_sums.linear_out.weight,
+    lambda n: n.net_sums.linear_out.bias,
+    lambda n: n.net_alpha_combine.linear_out.weight,
+)
+
+
+def net_params(net):
+    """The six parameters in the reference's ``ODENet.parameters()`` order (adjoint.py:185,207-220)."""
+    return [g(net) for g in _PARAM_GETTERS]
+
+
+def net_dims(net):
+    W = net.net_sums.linear_out.weight
+    return int(W.shape[1]), int(W.shape[0])
+
+
+_pack_cache = weakref.WeakKeyDictionary()
+
+
+def packed_weights(net):
+    """Kernel-layout copy of the parameters, rebuilt only when a parameter changed (``_version`` / storage)."""
+    params = net_params(net)
+    G, H = net_dims(net)
+    dev = _device_index(params[0])
+    for p in params:
+        if p.dtype != torch.float32:
+            raise TypeError("phoenix_b200 computes in float32; parameter has dtype %s (call odenet.float())" % p.dtype)
+        if _device_index(p) != dev:
+            raise RuntimeError("all ODENet parameters must live on the same CUDA device")
+    key = tuple((p.data_ptr(), p._version) for p in params) + (torch.cuda.current_stream(dev).cuda_stream,)
+    ent = _pack_cache.get(net)
+    if ent is not None and ent[0] == key:
+        return ent[1], G, H, dev
+    lib = _lib.load()
+    nbytes = lib.phx_packed_bytes(G, H)
+    buf = ent[1] if ent is not None and ent[1].numel() * 4 == nbytes and ent[1].device.index == dev else \
+        torch.empty(nbytes // 4, dtype=torch.float32, device=torch.device("cuda", dev))
+    ps = [p.detach().contiguous() for p in params]
+    _lib.check(lib.phx_pack_weights(_lib.ctx(dev), G, H, *[_ptr(p) for p in ps], _ptr(buf), _stream_ptr(dev)),
+               "pack_weights")
+    _pack_cache[net] = (key, buf)
+    return buf, G, H, dev
+
+
+# ---- status records -----------------------------------------------------------------------------------------------------
+def _new_status():
+    tls = _tls()
+    if tls.free_status:
+        st = tls.free_status.pop()
+    else:
+        st = torch.empty(ctypes.sizeof(_lib.PhxStatus) // 4, dtype=torch.int32).pin_memory()
+    st.zero_()
+    st[0] = _lib.ST_RUNNING
+    return st
+
+
+def _status_struct(st):
+    return _lib.PhxStatus.from_address(st.data_ptr())
+
+
+def _raise_for(st, what):
+    s = _status_struct(st)
+    if s.code == _lib.ST_DT_UNDERFLOW:
+        raise AssertionError("underflow in dt {}".format(s.dt_fail))
+    if s.code == _lib.ST_NONFINITE:
+        raise AssertionError("non-finite values in state `y` ({}, t={})".format(what, s.t_fail))
+    if s.code == _lib.ST_MAX_STEPS:
+        raise AssertionError("max_num_steps exceeded ({}, t={})".format(what, s.t_fail))
+
+
+def check_errors(synchronize=True):
+    """Raise the reference's AssertionError for any finished solve that hit a solver assertion."""
+    tls = _tls()
+    if synchronize and torch.cuda.is_available():
+        torch.cuda.synchronize()
+    still = []
+    err = None
+    for st, what in tls.pending:
+        code = _status_struct(st).code
+        if code == _lib.ST_RUNNING:
+            still.append((st, what))
+            continue
+        if code != _lib.ST_OK and err is None:
+            err = (st, what)
+        else:
+            tls.free_status.append(st)
+    tls.pending = still
+    if err is not None:
+        _raise_for(*err)
+
+
+def last_step_log():
+    """(t0, dt, accepted) rows of the most recent solve (requires set_step_logging(True)); synchronises."""
+    tls = _tls()
+    if tls.last_log is None:
+        return []
+    torch.cuda.synchronize()
+    n = _status_struct(tls.last_status).n_logged
+    return [tuple(r) for r in tls.last_log[:n].tolist()]
+
+
+def last_status():
+    tls = _tls()
+    if tls.last_status is None:
+        return None
+    torch.cuda.synchronize()
+    s = _status_struct(tls.last_status)
+    return {"code": s.code, "n_accepted": s.n_accepted, "n_rejected": s.n_rejected, "n_rhs": s.n_rhs,
+            "n_logged": s.n_logged}
+
+
+def _finish(st, what, dev):
+    tls = _tls()
+    tls.last_status = st
+    if SYNC_ERRORS:
+        torch.cuda.current_stream(dev).synchronize()
+        code = _status_struct(st).code
+        if code != _lib.ST_OK:
+            _raise_for(st, what)
+        tls.free_status.append(st)
+    else:
+        tls.pending.append((st, what))
+        if len(tls.pending) > 64:
+            check_errors(synchronize=False)
+
+
+def _steplog():
+    tls = _tls()
+    if not STEP_LOGGING:
+        tls.last_log = None
+        return None, 0
+    log = torch.zeros(STEPLOG_CAP, 3, dtype=torch.float64).pin_memory()
+    tls.last_log = log
+    return log, STEPLOG_CAP
+
+
+# ---- RHS -----------------------------------------------------------------------------------------------------------------
+def rhs_forward(net, y, decay):
+    packed, G, H, dev = packed_weights(net)
+    if y.shape[-1] != G:
+        raise RuntimeError("last dimension of y (%d) must equal ndim (%d)" % (y.shape[-1], G))
+    y2 = y.detach().to(torch.float32).contiguous()
+    B = y2.numel() // G
+    lib = _lib.load()
+    f = torch.empty_like(y2)
+    nb = lib.phx_rhs_workspace_bytes(G, H, B)
+    ws = _workspace(dev, nb, "rhs")
+    _lib.check(lib.phx_rhs_forward(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(f), int(decay), _ptr(ws),
+                                   ws.numel(), _stream_ptr(dev)), "rhs_forward")
+    return f
+
+
+def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True):
+    packed, G, H, dev = packed_weights(net)
+    y2 = y.detach().to(torch.float32).contiguous()
+    g2 = g.detach().to(torch.float32).contiguous()
+    B = y2.numel() // G
+    lib = _lib.load()
+    ybar = torch.empty_like(y2) if need_ybar else None
+    P = 4 * G * H + 2 * H + G
+    grads = torch.empty(P, dtype=torch.float32, device=y2.device) if need_grads else None
+    nb = lib.phx_rhs_workspace_bytes(G, H, B)
+    ws = _workspace(dev, nb, "rhs")
+    _lib.check(lib.phx_rhs_vjp(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(g2), int(decay), _ptr(ybar),
+                               _ptr(grads), 0, _ptr(ws), ws.numel(), _stream_ptr(dev)), "rhs_vjp")
+    return ybar, (split_flat_grads(grads, G, H) if need_grads else None)
+
+
+def split_flat_grads(flat, G, H):
+    """Views of the flat cotangent vector in the reference parameter order and shapes."""
+    o, out = 0, []
+    for shape in ((1, G), (H, G), (H,), (H, G), (H,), (G, 2 * H)):
+        n = 1
+        for d in shape:
+            n *= d
+        out.append(flat[o:o + n].view(shape))
+        o += n
+    return out
+
+
+# ---- solves ----------------------------------------------------------------------------------------------------------------
+def _t_array(t_list):
+    arr = (ctypes.c_double * len(t_list))(*t_list)
+    return arr
+
+
+def _pick_engine(lib, dev, G, H, B, T, adjoint):
+    """Resident (one persistent cooperative launch) when the rows fit on chip, else the streaming engine."""
+    if B <= lib.phx_resident_max_rows(int(adjoint)):
+        nb = lib.phx_solve_workspace_bytes(_lib.ctx(dev), G, H, B, T, int(adjoint))
+        if nb > 0:
+            return "resident", nb
+    nb = lib.phx_stream_workspace_bytes(_lib.ctx(dev), G, H, B, T, int(adjoint))
+    if nb == 0:
+        raise NotImplementedError("phoenix_b200: no kernel for G=%d H=%d B=%d (%s)" % (G, H, B, _lib.last_error()))
+    return "stream", nb
+
+
+def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, max_num_steps):
+    packed, G, H, dev = packed_weights(net)
+    if y0.shape[-1] != G:
+        raise RuntimeError("last dimension of y0 (%d) must equal ndim (%d)" % (y0.shape[-1], G))
+    if _device_index(y0) != dev:
+        raise RuntimeError("y0 and the ODENet parameters must be on the same CUDA device")
+    y0c = y0.detach().contiguous()
+    B = y0c.numel() // G
+    T = len(t_list)
+    lib = _lib.load()
+    engine, nb = _pick_engine(lib, dev, G, H, B, T, False)
+    ws = _workspace(dev, nb, "solve")
+    yout = torch.empty((T,) + tuple(y0c.shape), dtype=torch.float32, device=y0c.device)
+    st = _new_status()
+    log, cap = _steplog()
+    fn = lib.phx_solve_forward if engine == "resident" else lib.phx_stream_solve_forward
+    rc = fn(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y0c), _t_array(t_list), T, int(t_is_f32),
+            int(reversed_time), _lib.METHOD_IDS[method], float(rtol), float(atol), int(max_num_steps), _ptr(yout),
+            _ptr(ws), ws.numel(), _ptr(st), _ptr(log), cap, _stream_ptr(dev))
+    _lib.check(rc, "solve_forward")
+    _finish(st, "forward solve", dev)
+    return yout
+
+
+def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_saved, grad_y):
+    packed, G, H, dev = packed_weights(net)
+    ys = y_saved.detach().contiguous()
+    gy = grad_y.detach().to(torch.float32).contiguous()
+    T = len(t_list)
+    B = ys[0].numel() // G
+    lib = _lib.load()
+    engine, nb = _pick_engine(lib, dev, G, H, B, T, True)
+    ws = _workspace(dev, nb, "solve")
+    adj_y0 = torch.empty_like(ys[0])
+    P = 4 * G * H + 2 * H + G
+    grads = torch.empty(P, dtype=torch.float32, device=ys.device)
+    st = _new_status()
+    log, cap = _steplog()
+    fn = lib.phx_solve_adjoint if engine == "resident" else lib.phx_stream_solve_adjoint
+    rc = fn(_lib.ctx(dev), G, H, B, _ptr(packed), _t_array(t_list), T, int(t_is_f32), _lib.METHOD_IDS[method],
+            float(rtol), float(atol), int(max_num_steps), _ptr(ys), _ptr(gy), _ptr(adj_y0), _ptr(grads), _ptr(ws),
+            ws.numel(), _ptr(st), _ptr(log), cap, _stream_ptr(dev))
+    _lib.check(rc, "solve_adjoint")
+    _finish(st, "adjoint solve", dev)
+    return adj_y0, split_flat_grads(grads, G, H)

@@ -1,0 +1,132 @@
+"""``odeint`` / ``odeint_adjoint`` with the reference's call surface (torchdiffeq/_impl/odeint.py:25-69,
+adjoint.py:165-204) — argument normalisation follows misc.py:165-241 — dispatching to the CUDA solvers."""
+import warnings
+
+import torch
+import torch.nn as nn
+
+from .. import engine
+from ..odenet import ODENet
+
+# every method string the vendored package registers (odeint.py:9-22); only the four PHOENIX uses are accelerated
+_REFERENCE_SOLVERS = ('dopri8', 'dopri5', 'bosh3', 'adaptive_heun', 'euler', 'midpoint', 'rk4', 'explicit_adams',
+                      'implicit_adams', 'fixed_adams')
+_SUPPORTED = ('dopri5', 'euler', 'midpoint', 'rk4')
+_DEFAULT_MAX_STEPS = 2 ** 31 - 1
+
+
+def _normalise(func, y0, t, rtol, atol, method, options):
+    """The checks of misc.py:165-241 that apply to a single-tensor state; returns the pieces the kernels need."""
+    if not torch.is_tensor(y0):
+        assert isinstance(y0, tuple), 'y0 must be either a torch.Tensor or a tuple'
+        raise NotImplementedError("tuple-valued states are not part of the PHOENIX path (ODENet has a tensor state)")
+    if not torch.is_floating_point(y0):
+        raise TypeError('`y0` must be a floating point Tensor but is a {}'.format(y0.type()))
+    options = {} if options is None else dict(options)
+    if method is None:
+        method = 'dopri5'
+    if method not in _REFERENCE_SOLVERS:
+        raise ValueError('Invalid method "{}". Must be one of {}'.format(
+            method, '{"' + '", "'.join(_REFERENCE_SOLVERS) + '"}.'))
+    if method not in _SUPPORTED:
+        raise NotImplementedError('method "{}" is registered by torchdiffeq but never selected by PHOENIX; the B200 '
+                                  'path implements {}'.format(method, _SUPPORTED))
+    max_num_steps = int(options.pop('max_num_steps', _DEFAULT_MAX_STEPS))
+    options.pop('dtype', None)
+    if options:
+        raise NotImplementedError("solver options {} are not supported on the B200 path (the reference never passes "
+                                  "options)".format(sorted(options)))
+    assert torch.is_tensor(t), 't must be a torch.Tensor'
+    assert t.ndimension() == 1, "{} must be one dimensional".format('t')
+    if not torch.is_floating_point(t):
+        raise TypeError('`{}` must be a floating point Tensor but is a {}'.format('t', t.type()))
+    if t.requires_grad:
+        raise NotImplementedError("gradients with respect to t are not computed on the B200 path")
+    if t.device != y0.device:
+        # same coercion as misc.py:236-239, minus the copy: the times are consumed on the host
+        pass
+    t_is_f32 = t.dtype != torch.float64
+    tl = t.detach().to('cpu', torch.float64)
+    reversed_time = False
+    if len(tl) > 1 and bool((tl[1:] < tl[:-1]).all()):
+        tl = -tl
+        reversed_time = True
+    assert bool((tl[1:] > tl[:-1]).all()), '{} must be strictly increasing or decreasing'.format('t')
+    if torch.is_tensor(rtol):
+        assert not rtol.requires_grad, "rtol cannot require gradient"
+        rtol = float(rtol)
+    if torch.is_tensor(atol):
+        assert not atol.requires_grad, "atol cannot require gradient"
+        atol = float(atol)
+    if not isinstance(func, ODENet):
+        raise TypeError("phoenix_b200.torchdiffeq integrates phoenix ODENet right-hand sides only (got {}); there is "
+                        "no generic / CPU fallback".format(type(func).__name__))
+    if y0.dtype != torch.float32:
+        raise TypeError("the B200 path keeps the state in float32 like the reference (got {})".format(y0.dtype))
+    return tl.tolist(), t_is_f32, reversed_time, float(rtol), float(atol), method, max_num_steps
+
+
+def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """Integrate dy/dt = func(t, y) from y(t[0]) = y0 and return y at every t: ``[len(t), *y0.shape]``
+    (odeint.py:25-69).  Not differentiable — use ``odeint_adjoint`` (what every PHOENIX script imports as ``odeint``,
+    train_insilico.py:15-18) when gradients are needed."""
+    tl, t_is_f32, rev, rtol, atol, method, max_steps = _normalise(func, y0, t, rtol, atol, method, options)
+    if torch.is_grad_enabled() and (y0.requires_grad or any(p.requires_grad for p in func.parameters())):
+        warnings.warn("phoenix_b200.odeint does not record an autograd graph; use odeint_adjoint for gradients",
+                      stacklevel=2)
+    with torch.no_grad():
+        return engine.solve_forward(func, y0, tl, t_is_f32, rev, method, rtol, atol, max_steps)
+
+
+class OdeintAdjointMethod(torch.autograd.Function):
+    """adjoint.py:10-162: forward = solve under no_grad, keep only y(t); backward = one device-side sweep of the
+    augmented system per output interval."""
+
+    @staticmethod
+    def forward(ctx, func, tl, t_is_f32, method, rtol, atol, max_steps, adj, y0, *adjoint_params):
+        ctx.func, ctx.tl, ctx.t_is_f32, ctx.adj = func, tl, t_is_f32, adj
+        with torch.no_grad():
+            y = engine.solve_forward(func, y0, tl, t_is_f32, False, method, rtol, atol, max_steps)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (y,) = ctx.saved_tensors
+        a_method, a_rtol, a_atol, a_max = ctx.adj
+        with torch.no_grad():
+            adj_y0, grads = engine.solve_adjoint(ctx.func, ctx.tl, ctx.t_is_f32, a_method, a_rtol, a_atol, a_max,
+                                                 y, grad_y)
+        out = [None] * 8 + [adj_y0 if ctx.needs_input_grad[8] else None]
+        for i, need in enumerate(ctx.needs_input_grad[9:]):
+            out.append(grads[i] if need else None)
+        return tuple(out)
+
+
+def odeint_adjoint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None, adjoint_rtol=None,
+                   adjoint_atol=None, adjoint_method=None, adjoint_options=None, adjoint_params=None):
+    """adjoint.py:165-204: same as ``odeint`` but differentiable w.r.t. y0 and the ODENet parameters through the
+    continuous adjoint, solved backwards with the forward method / tolerances unless overridden."""
+    if adjoint_params is None and not isinstance(func, nn.Module):
+        raise ValueError('func must be an instance of nn.Module to specify the adjoint parameters; alternatively they '
+                         'can be specified explicitly via the `adjoint_params` argument. If there are no parameters '
+                         'then it is allowable to set `adjoint_params=()`.')
+    if adjoint_params is not None:
+        raise NotImplementedError("explicit adjoint_params are not supported: the adjoint kernel always produces the "
+                                  "six ODENet parameter cotangents")
+    if adjoint_rtol is None:
+        adjoint_rtol = rtol
+    if adjoint_atol is None:
+        adjoint_atol = atol
+    if adjoint_method is None:
+        adjoint_method = method
+    if adjoint_options is None:
+        adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    tl, t_is_f32, rev, rtol, atol, method, max_steps = _normalise(func, y0, t, rtol, atol, method, options)
+    _, _, _, a_rtol, a_atol, a_method, a_max = _normalise(func, y0, t, adjoint_rtol, adjoint_atol, adjoint_method,
+                                                          adjoint_options)
+    if rev:
+        raise NotImplementedError("odeint_adjoint with decreasing t is not part of the PHOENIX path")
+    params = engine.net_params(func)
+    return OdeintAdjointMethod.apply(func, tl, t_is_f32, method, rtol, atol, max_steps,
+                                     (a_method, a_rtol, a_atol, a_max), y0, *params)
