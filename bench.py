@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py — PHOENIX NeuralODE hot path on B200: gene-steps/s (forward solve + adjoint) at the genome-scale shape.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[3], the configuration the metric "at ~11k genes" is quoted on):
+ODENet(ndim=11165, neurons=200); one step = one training-step batch of the hot path = 17 independent samples, each
+`odeint_adjoint(odenet, y0[1,G], t=[tau, tau+0.0051], method='dopri5')` + MSE loss + `.backward()`
+(train_insilico.py:124-140 with config_breast.cfg batch_size=17; desmedt 178-point pseudotime spacing 0.0051).
+Synthetic expression values U[0,1), weights with the reference init distribution (odenet.py:61-75).
+
+metric  gene-steps/s = B * G * (RHS evals forward + RHS-VJP evals adjoint) / time, evaluations counted by the solver.
+value   device-resident inputs, C-ABI calls (phx_solve_forward / phx_solve_adjoint) issued back to back.
+e2e     the same step through the reference-facing Python API (phoenix_b200.odeint_adjoint + backward) from pinned
+        HOST buffers, H2D of every sample and D2H of the loss inside the timed region.
+N > 1   weak scaling: every rank runs its own 17 samples, then ONE NCCL sum-allreduce of the flat gradient.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+G, H, BATCH, DT = 11165, 200, 17, 0.0051
+METHOD = os.environ.get("PHX_BENCH_METHOD", "dopri5")
+METRIC = "ODE RHS gene-steps/sec (fwd+adjoint) at ~11k genes"
+UNIT = "gene-steps/s"
+P = 4 * G * H + 2 * H + G
+
+
+def workload(seed, device):
+    from oracle.phoenix_oracle import make_weights  # deterministic input generator only (no compute)
+    w = make_weights(G, H, 1003, dense=bool(int(os.environ.get("PHX_BENCH_DENSE", "0"))))
+    gen = torch.Generator().manual_seed(seed)
+    y0 = torch.rand(BATCH, 1, G, generator=gen)
+    target = torch.rand(BATCH, 1, G, generator=gen)
+    tau = torch.rand(BATCH, generator=gen)
+    t = torch.stack([tau, tau + DT], dim=1)            # [BATCH, 2] float32, like datahandler.py:107
+    return w, y0, target, t
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the oracle port of the reference's torch-CPU path, all host threads
+# ------------------------------------------------------------------------------------------------------------------
+def cpu_sample(w, y0, target, t, n_samples):
+    from oracle import phoenix_oracle as O
+    evals = 0
+    t0 = time.perf_counter()
+    for i in range(n_samples):
+        y, flog = O.odeint(w, y0[i], t[i], method=METHOD)
+        gy = torch.zeros_like(y)
+        gy[1] = 2.0 * (y[1] - target[i]) / target[i].numel()
+        _, _, blog = O.adjoint_backward(w, t[i], y, gy, method=METHOD)
+        evals += flog.nfe + blog.nfe
+    dt = time.perf_counter() - t0
+    return evals, dt
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    w, y0, target, t = workload(2000, "cpu")
+    n_samples = 2
+    cpu_sample(w, y0, target, t, 1)  # first call carries one-time overhead
+    for _ in range(max(0, args.warmup - 1)):
+        cpu_sample(w, y0, target, t, 1)
+    evals, secs = 0, 0.0
+    for _ in range(args.steps):
+        e, s = cpu_sample(w, y0, target, t, n_samples)
+        evals += e
+        secs += s
+    value = G * evals / secs
+    sample = "%d of the %d samples of a step per timed step (fwd+adjoint, %s)" % (n_samples, BATCH, METHOD)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "breast 11165 genes x 200 neurons, %s, dt=0.0051 (bounded sample)" % METHOD,
+                   "genes": G, "neurons": H, "samples_per_step": n_samples},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                f = [x.strip() for x in out.stdout.strip().split(",")]
+                if len(f) >= 8:
+                    self.rows.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = max([float(r[2]) for r in self.rows if r[2].replace(".", "").isdigit()] or [0.0])
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(self.rows)}
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    import phoenix_b200 as pb
+    from phoenix_b200 import _lib, engine, parallel
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w, y0_h, target_h, t_h = workload(2000 + rank, "cpu")
+    net = pb.ODENet(dev, G, neurons=H)
+    with torch.no_grad():
+        for p, src in zip(net.parameters(), w.as_list()):
+            p.copy_(src)
+    parallel.broadcast_parameters(net)
+    lib = _lib.load()
+    ctx = _lib.ctx(local)
+    packed, _, _, _ = engine.packed_weights(net)
+    stream = torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(stream.cuda_stream)
+
+    # ---- device-resident leg: raw C-ABI calls --------------------------------------------------------------
+    y0_d, target_d = y0_h.to(dev), target_h.to(dev)
+    tl = [[float(a), float(b)] for a, b in t_h.tolist()]
+    tarr = [(ctypes.c_double * 2)(*x) for x in tl]
+    ws_f = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 0), dtype=torch.uint8, device=dev)
+    ws_a = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 1), dtype=torch.uint8, device=dev)
+    yout = torch.empty(BATCH, 2, 1, G, device=dev)
+    grad_y = torch.zeros(BATCH, 2, 1, G, device=dev)
+    adj_y0 = torch.empty(BATCH, 1, G, device=dev)
+    grads = torch.empty(BATCH, P, device=dev)
+    gsum = torch.empty(P, device=dev)
+    st_f = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
+    st_a = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
+    mid = _lib.METHOD_IDS[METHOD]
+    ptr = lambda x: ctypes.c_void_p(x.data_ptr())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    adj_ev = []
+
+    def step_resident(record):
+        for i in range(BATCH):
+            rc = lib.phx_solve_forward(ctx, G, H, 1, ptr(packed), ptr(y0_d[i]), tarr[i], 2, 1, 0, mid, 1e-7, 1e-9,
+                                       2 ** 31 - 1, ptr(yout[i]), ptr(ws_f), ws_f.numel(), ptr(st_f[i]), None, 0, sp)
+            _lib.check(rc, "solve_forward")
+        # d loss / d y(t1) for loss = mean((pred - target)^2) over the batch (train_insilico.py:132)
+        torch.sub(yout[:, 1], target_d, out=grad_y[:, 1])
+        grad_y[:, 1].mul_(2.0 / (BATCH * G))
+        for i in range(BATCH):
+            if record:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(stream)
+            rc = lib.phx_solve_adjoint(ctx, G, H, 1, ptr(packed), tarr[i], 2, 1, mid, 1e-7, 1e-9, 2 ** 31 - 1,
+                                       ptr(yout[i]), ptr(grad_y[i]), ptr(adj_y0[i]), ptr(grads[i]), ptr(ws_a),
+                                       ws_a.numel(), ptr(st_a[i]), None, 0, sp)
+            _lib.check(rc, "solve_adjoint")
+            if record:
+                e1.record(stream)
+                adj_ev.append((e0, e1))
+        torch.sum(grads, dim=0, out=gsum)                # autograd's accumulation of the per-sample .grad
+        if world > 1:
+            dist.all_reduce(gsum)
+
+    def timed(step_fn, steps):
+        total_ms = 0.0
+        for _ in range(steps):
+            flush.fill_(1)                               # evict L2 between timed iterations
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step_fn()
+            b.record(stream)
+            torch.cuda.synchronize()
+            total_ms += a.elapsed_time(b)
+        return total_ms
+
+    for _ in range(args.warmup):
+        step_resident(False)
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms_res = timed(lambda: step_resident(True), args.steps)
+    evals = 0
+    for i in range(BATCH):
+        evals += int(st_f[i, 3]) + int(st_a[i, 3])
+        if int(st_f[i, 0]) != 0 or int(st_a[i, 0]) != 0:
+            raise SystemExit("solver status non-zero: %s %s" % (st_f[i, :5].tolist(), st_a[i, :5].tolist()))
+    n_attempts = sum(int(st_a[i, 1]) + int(st_a[i, 2]) for i in range(BATCH)) / BATCH
+    n_vjp = sum(int(st_a[i, 3]) for i in range(BATCH)) / BATCH
+    adj_ms = sum(a.elapsed_time(b) for a, b in adj_ev) / len(adj_ev)
+
+    # ---- end-to-end leg: reference-facing Python API from pinned host buffers ------------------------------
+    y0_p, target_p = y0_h.pin_memory(), target_h.pin_memory()
+    t_cpu = [t_h[i].clone() for i in range(BATCH)]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e():
+        net.zero_grad(set_to_none=True)
+        preds = []
+        tgt = target_p.to(dev, non_blocking=True)
+        for i in range(BATCH):
+            yb = y0_p[i].to(dev, non_blocking=True)
+            preds.append(pb.odeint_adjoint(net, yb, t_cpu[i], method=METHOD)[1])
+        loss = torch.mean((torch.stack(preds) - tgt) ** 2)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_grads(net)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(args.warmup):
+        step_e2e()
+    torch.cuda.synchronize()
+    ms_e2e = timed(step_e2e, args.steps)
+    pb.check_errors()
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- reduce over ranks: time = max, work = sum -------------------------------------------------------
+    stats = torch.tensor([ms_res, ms_e2e, float(evals)], dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stats.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stats.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        ms_res, ms_e2e, evals_total = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        evals_total = float(evals)
+    work_per_step = G * evals_total                     # B = 1 per solve; evals already summed over the 17 samples
+    value = work_per_step / (ms_res / args.steps / 1e3)
+    e2e_value = work_per_step / (ms_e2e / args.steps / 1e3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        # algorithmic bytes of one adjoint launch: per RHS-VJP evaluation the
+        # weights twice + y, a in + y', a' out; per attempted step one 8P-byte read-modify-write of the parameter
+        # cotangents, plus the two P-long norm reads of the initial step and the dense-output pass at the end
+        alg = n_vjp * (32.0 * G * H + 16.0 * G) + (n_attempts + 2.0) * 8.0 * P
+        achieved = alg / (adj_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("phx_adj_kernel")
+        except Exception:
+            pass
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        cpu_sample(w, y0_h, target_h, t_h, 1)
+        ce, cs = cpu_sample(w, y0_h, target_h, t_h, 3)
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "breast 11165 genes x 200 neurons, batch 17 x (odeint_adjoint %s dt=0.0051 + "
+                                   "backward)" % METHOD, "genes": G, "neurons": H, "samples_per_step": BATCH,
+                       "rhs_evals_per_step": evals_total / world, "l2": "flushed between timed steps (256 MiB write)",
+                       "parallelism": "dp%d (samples sharded, 1 grad allreduce/step)" % world},
+            "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                    "h2d_bytes_per_step": 2 * BATCH * G * 4, "d2h_bytes_per_step": 4},
+            "gpu_launches": args.steps * BATCH * 2,
+            "roofline": {"bound": "hbm", "kernel": "phx_adj_kernel", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                         "launch_ms": adj_ms, "algorithmic_bytes": alg,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650"},
+            "cpu_baseline": {"value": G * ce / cs, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"},
+            "clocks": sampler.summary(),
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -115,6 +115,24 @@ int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, co
                       void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                       int steplog_cap, void* stream);
 
+/* ---- the same two solves for ANY number of rows B (streaming engine) ---------------------------------------- */
+/* phx_solve_forward / phx_solve_adjoint keep the whole solve in one persistent cooperative launch and need the rows
+ * to fit on chip (B <= phx_resident_max_rows()).  These variants stream the [B][G] state through HBM and run the
+ * branch contractions as batched GEMM-shaped launches; they cover the batched callers of the reference
+ * (find_gene_influences.py:64-73 with B=60, the 4096-row synthetic sweep).  Identical arguments and semantics; with
+ * method = PHX_DOPRI5 the call synchronises `stream` once per attempted step (host-side step controller). */
+size_t phx_stream_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint);
+int phx_stream_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y0,
+                             const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol,
+                             double atol, int64_t max_num_steps, float* y_out, void* workspace,
+                             size_t workspace_bytes, phx_status* status, double* steplog, int steplog_cap,
+                             void* stream);
+int phx_stream_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
+                             int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                             const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
+                             void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                             int steplog_cap, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -123,7 +123,7 @@ int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, cons
         phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
         return PHX_ERR_WORKSPACE;
     }
-    return phx_rhs_forward_launch(G, H, B, phx_packed_view(packed, G, H), y, f, decay, (float*)workspace,
+    return phx_rhs_forward_launch(G, H, B, phx_packed_view(packed, G, H), y, f, decay, 1.f, (float*)workspace,
                                   (cudaStream_t)stream);
 }
 
@@ -136,7 +136,7 @@ int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const fl
         return PHX_ERR_WORKSPACE;
     }
     return phx_rhs_vjp_launch(G, H, B, phx_packed_view(packed, G, H), y, g, decay, ybar, grads_flat, accumulate,
-                              (float*)workspace, (cudaStream_t)stream);
+                              nullptr, 1.f, (float*)workspace, (cudaStream_t)stream);
 }
 
 size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint) {

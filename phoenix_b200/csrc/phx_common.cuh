@@ -105,10 +105,11 @@ size_t phx_resident_workspace_floats(int nCTA, int G, int H, int B, int T, int a
 int phx_resident_launch(const ResParams& p, const ResLaunchPlan& plan, cudaStream_t stream);
 
 // host helpers implemented in phx_rhs.cu
-int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float* ws,
-                           cudaStream_t stream);
+int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
+                           float* ws, cudaStream_t stream);
 int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
-                       float* ybar, float* grads_flat, int accumulate, float* ws, cudaStream_t stream);
+                       float* ybar, float* grads_flat, int accumulate, float* f_out, float fscale, float* ws,
+                       cudaStream_t stream);
 size_t phx_rhs_workspace_floats(int G, int H, int B);
 
 void phx_set_error(const char* fmt, ...);

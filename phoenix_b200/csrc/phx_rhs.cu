@@ -155,11 +155,11 @@ struct EpiSP {  // SP[b][col0+n] = acc + bias ; exp on prods half ; pads -> 0
         SP[(size_t)b * K2 + k] = v;
     }
 };
-struct EpiF {  // f = decay ? relum*(J - y) : J
-    float* f; const float* y; const float* relum; int G; int decay;
+struct EpiF {  // f = fscale * (decay ? relum*(J - y) : J)
+    float* f; const float* y; const float* relum; int G; int decay; float fscale;
     __device__ void operator()(int b, int g, float acc) const {
         size_t i = (size_t)b * G + g;
-        f[i] = decay ? relum[g] * (acc - y[i]) : acc;
+        f[i] = fscale * (decay ? relum[g] * (acc - y[i]) : acc);
     }
 };
 struct EpiGS {  // GS[b][k] = acc (sums half) or acc * Pr (prods half)
@@ -212,6 +212,12 @@ __global__ void colsum_bias_kernel(const float* GS, int B, int K2, int Hp, int H
     float* dst = (k < H) ? (bs_bar + k) : (bp_bar + (k - H));
     *dst = accumulate ? *dst + t : t;
 }
+// f_out = fscale * relum * (J - y) from the un-decayed J
+__global__ void decay_kernel(const float* J, const float* y, const float* relum, int G, size_t n, float fscale,
+                             float* f_out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        f_out[i] = fscale * (relum[i % G] * (J[i] - y[i]));
+}
 __global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const float* y, const float* maskm, int B,
                                    int G, float* m_bar, int accumulate, int decay) {
     int gg = blockIdx.x * blockDim.x + threadIdx.x;
@@ -246,14 +252,14 @@ static void rhs_sp(int G, int H, int B, const PhxPacked& w, const float* y, floa
     }
 }
 
-int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float* ws,
-                           cudaStream_t st) {
+int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
+                           float* ws, cudaStream_t st) {
     const int K2 = phx_K2(H);
     float* SP = ws;
     rhs_sp(G, H, B, w, y, SP, st);
     LoadRowMajorA la{SP, K2, 0};
     LoadWcol lb{reinterpret_cast<const float*>(w.WA), K2, 0};
-    EpiF ep{f, y, w.relum, G, decay};
+    EpiF ep{f, y, w.relum, G, decay, fscale};
     sgemm(B, G, K2, la, lb, ep, st);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -264,7 +270,8 @@ int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float*
 }
 
 int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
-                       float* ybar, float* grads, int accumulate, float* ws, cudaStream_t st) {
+                       float* ybar, float* grads, int accumulate, float* f_out, float fscale, float* ws,
+                       cudaStream_t st) {
     const int Hp = phx_Hp(H), K2 = 2 * Hp;
     float* SP = ws;
     float* GS = ws + (size_t)B * K2;
@@ -293,6 +300,19 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
             sgemm(B, G, Hp, la, lb, ep, st);
         }
     }
+    const bool needJ = (f_out != nullptr) || (grads && decay);
+    if (needJ) {   // un-decayed joint, for the multiplier cotangent and/or the RHS value itself
+        LoadRowMajorA la{SP, K2, 0};
+        LoadWcol lb{WA, K2, 0};
+        EpiF ep{J, y, w.relum, G, 0, 1.f};
+        sgemm(B, G, K2, la, lb, ep, st);
+        if (f_out) {
+            size_t n = (size_t)B * G;
+            int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+            if (decay) decay_kernel<<<blocks, 256, 0, st>>>(J, y, w.relum, G, n, fscale, f_out);
+            else cudaMemcpyAsync(f_out, J, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        }
+    }
     if (grads) {
         const PhxGradOff off = phx_grad_offsets(G, H);
         {   // Wa_bar[g][k] = sum_b gJ[b][g] SP[b][k]
@@ -315,12 +335,6 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
         }
         colsum_bias_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(GS, B, K2, Hp, H, grads + off.bs, grads + off.bp,
                                                                 accumulate);
-        if (decay) {   // J (no decay) for the multiplier cotangent
-            LoadRowMajorA la{SP, K2, 0};
-            LoadWcol lb{WA, K2, 0};
-            EpiF ep{J, y, w.relum, G, 0};
-            sgemm(B, G, K2, la, lb, ep, st);
-        }
         colsum_mult_kernel<<<(G + 127) / 128, 128, 0, st>>>(g, J, y, w.maskm, B, G, grads + off.m, accumulate,
                                                             decay);
     }

@@ -1,20 +1,613 @@
-// Streaming engine (any B): placeholder entry points until the host-driven solver lands.
+// Streaming engine: the same solvers as the resident kernels for ANY number of rows B (gene-influence scan B=60,
+// synthetic sweep B=4096, batched adjoint), driven from the host.  The state is too large to live on chip, so each RK
+// stage is: one fused elementwise combine over the state -> the batched RHS / RHS-VJP contractions of phx_rhs.cu.
+// Fixed-grid methods stay fully asynchronous; dopri5 reads ONE small record (the error sums) back per step attempt
+// for the controller, negligible next to the B*G*H contractions of a step at these sizes.
+//
+// The adjoint treats (y, adj_y, adj_params) as three flat segments with identical elementwise arithmetic
+// (adjoint.py:86-151); at large B the parameter-cotangent stage derivatives are genuine rank-B contractions
+// (gJ^T SP etc., K = B) and are materialised per stage like the reference does.
+#include <math.h>
+#include <string.h>
+#include <vector>
 #include "phx_common.cuh"
 
+namespace {
+
+constexpr int EB = 256;        // elementwise block
+constexpr int MAXBLK = 1184;   // 8 x 148
+
+const double H_BETA[6][6] = {
+    {1.0 / 5, 0, 0, 0, 0, 0},
+    {3.0 / 40, 9.0 / 40, 0, 0, 0, 0},
+    {44.0 / 45, -56.0 / 15, 32.0 / 9, 0, 0, 0},
+    {19372.0 / 6561, -25360.0 / 2187, 64448.0 / 6561, -212.0 / 729, 0, 0},
+    {9017.0 / 3168, -355.0 / 33, 46732.0 / 5247, 49.0 / 176, -5103.0 / 18656, 0},
+    {35.0 / 384, 0, 500.0 / 1113, 125.0 / 192, -2187.0 / 6784, 11.0 / 84}};
+const double H_CERR[7] = {35.0 / 384 - 1951.0 / 21600, 0, 500.0 / 1113 - 22642.0 / 50085, 125.0 / 192 - 451.0 / 720,
+                          -2187.0 / 6784 - -12231.0 / 42400, 11.0 / 84 - 649.0 / 6300, -1.0 / 60.0};
+const double H_CMID[7] = {6025192743.0 / 30085553152.0 / 2, 0, 51252292925.0 / 65400821598.0 / 2,
+                          -2691868925.0 / 45128329728.0 / 2, 187940372067.0 / 1594534317056.0 / 2,
+                          -1776094331.0 / 19743644256.0 / 2, 11237099.0 / 235043384.0 / 2};
+
+struct KSet {
+    int nk;
+    const float* k[7];
+    float c[7];
+};
+
+__device__ __forceinline__ float ksum(const KSet& a, size_t i) {
+    float v = a.k[0][i] * a.c[0];
+    for (int j = 1; j < a.nk; ++j) v = fmaf(a.k[j][i], a.c[j], v);
+    return v;
+}
+
+// out = x0 + sum_j c_j k_j           (rk_common.py:66)
+__global__ void combine_kernel(float* out, const float* x0, KSet a, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        out[i] = x0[i] + ksum(a, i);
+}
+
+// fixed-grid formulas, exactly as written in fixed_grid.py / rk_common.py:96-103
+enum { FX_EULER_END = 0, FX_MID_IN = 1, FX_RK4_IN2 = 2, FX_RK4_IN3 = 3, FX_RK4_IN4 = 4, FX_RK4_END = 5 };
+__global__ void fixed_kernel(int mode, float* out, const float* x0, const float* k1, const float* k2, const float* k3,
+                             const float* k4, float dt, size_t n) {
+    const float third = (float)(1.0 / 3.0);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float x = x0[i], r;
+        switch (mode) {
+            case FX_EULER_END: r = x + dt * k1[i]; break;
+            case FX_MID_IN: r = x + k1[i] * dt; break;  // dt carries half_dt here
+            case FX_RK4_IN2: r = x + dt * k1[i] * third; break;
+            case FX_RK4_IN3: r = x + dt * (k2[i] - k1[i] * third); break;
+            case FX_RK4_IN4: r = x + dt * (k1[i] - k2[i] + k3[i]); break;
+            default: r = x + (k1[i] + 3.f * (k2[i] + k3[i]) + k4[i]) * dt * 0.125f; break;
+        }
+        out[i] = r;
+    }
+}
+
+template <int NV>
+__device__ void block_partials(double (&v)[NV], double* partial) {
+    __shared__ double sh[EB / 32][NV];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+#pragma unroll
+    for (int q = 0; q < NV; ++q) {
+        double s = v[q];
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0) sh[warp][q] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+        double s = 0;
+        for (int w = 0; w < EB / 32; ++w) s += sh[w][threadIdx.x];
+        partial[(size_t)blockIdx.x * NV + threadIdx.x] = s;
+    }
+}
+
+// sums for Hairer's initial step (misc.py:63-66): [0]=sum (x0/scale)^2, [1]=sum (k0/scale)^2, [2]=#non-finite
+__global__ void init01_kernel(const float* x0, const float* k0, float rtol, float atol, size_t n, double* partial) {
+    double v[3] = {0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float x = x0[i];
+        float scale = atol + fabsf(x) * rtol;
+        float r0 = x / scale, r1 = k0[i] / scale;
+        v[0] += (double)(r0 * r0);
+        v[1] += (double)(r1 * r1);
+        if (!isfinite(x)) v[2] += 1.0;
+    }
+    block_partials<3>(v, partial);
+}
+// [0] = sum ((k1-k0)/scale)^2   (misc.py:76)
+__global__ void initd2_kernel(const float* x0, const float* k0, const float* k1, float rtol, float atol, size_t n,
+                              double* partial) {
+    double v[3] = {0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float scale = atol + fabsf(x0[i]) * rtol;
+        float r = (k1[i] - k0[i]) / scale;
+        v[0] += (double)(r * r);
+    }
+    block_partials<3>(v, partial);
+}
+// [0] = sum (err/tol)^2, [1] = #non-finite in x1   (misc.py:89-91)
+__global__ void err_kernel(const float* x0, const float* x1, KSet a, float rtol, float atol, size_t n,
+                           double* partial) {
+    double v[3] = {0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float e = ksum(a, i);
+        float xa = x0[i], xb = x1[i];
+        float tol = atol + rtol * fmaxf(fabsf(xa), fabsf(xb));
+        float r = e / tol;
+        v[0] += (double)(r * r);
+        if (!isfinite(xb)) v[1] += 1.0;
+    }
+    block_partials<3>(v, partial);
+}
+// out[seg*3 + q] = sum over blocks, fixed order
+__global__ void final_reduce_kernel(const double* partial, int nblocks, double* out) {
+    int q = threadIdx.x;
+    if (q < 3) {
+        double s = 0;
+        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 3 + q];
+        out[q] = s;
+    }
+}
+// quartic dense output at x (interp.py:1-47)
+__global__ void interp_kernel(float* out, const float* x0, const float* x1, KSet mid, const float* kf, const float* kl,
+                              float dt, float xs0, float xs1, float xs2, float xs3, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float y0 = x0[i], y1 = x1[i], f0 = kf[i], f1 = kl[i];
+        float ymid = y0 + ksum(mid, i);
+        float a = 2.f * dt * (f1 - f0) - 8.f * (y1 + y0) + 16.f * ymid;
+        float b = dt * (5.f * f0 - 3.f * f1) + 18.f * y0 + 14.f * y1 - 32.f * ymid;
+        float c = dt * (f1 - 4.f * f0) - 11.f * y0 - 5.f * y1 + 16.f * ymid;
+        float d = dt * f0;
+        float total = y0 + xs0 * d;
+        total = total + xs1 * c;
+        total = total + xs2 * b;
+        total = total + xs3 * a;
+        out[i] = total;
+    }
+}
+__global__ void add_kernel(float* x, const float* y, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        x[i] = x[i] + y[i];
+}
+
+int nblk(size_t n) {
+    size_t b = (n + EB - 1) / EB;
+    return (int)(b < (size_t)MAXBLK ? (b ? b : 1) : MAXBLK);
+}
+
+struct Seg {
+    size_t n;
+    float* x0;
+    float* x1;
+    float* xs;   // stage input (null for the parameter segment: the dynamics do not depend on it)
+    float* k[7];
+    double count;
+};
+
+double next_dt_host(double dt, float ratio) {
+    if (ratio == 0.f) return dt * 10.0;
+    double dfactor = (ratio < 1.f) ? 1.0 : 0.2;
+    double r = (double)ratio;
+    if (isnan(r)) return nan("");
+    double f = 0.9 / pow(r, 0.2);
+    f = fmax(f, dfactor);
+    f = fmin(10.0, f);
+    return dt * f;
+}
+
+struct Stream {
+    phx_ctx* ctx;
+    int G, H, B, T, method, t_is_f32, adjoint;
+    float rtol_f, atol_f, fsign;
+    long long max_steps;
+    PhxPacked w;
+    cudaStream_t st;
+    std::vector<Seg> segs;
+    float* rhs_ws;
+    double* partial;   // [MAXBLK][3]
+    double* sums_dev;  // [nseg][3]
+    double* sums_host; // pinned
+    phx_status status;
+    double* steplog;
+    int steplog_cap;
+    std::vector<double> log;
+
+    // stage derivative `slot` of every segment at the current stage inputs
+    int eval(int slot) {
+        if (!adjoint)
+            return phx_rhs_forward_launch(G, H, B, w, segs[0].xs, segs[0].k[slot], 1, fsign, rhs_ws, st);
+        // reverse time: ky = -f, ka = VJP_y(cotangent a), ktheta = VJP_theta(cotangent a)
+        return phx_rhs_vjp_launch(G, H, B, w, segs[0].xs, segs[1].xs, 1, segs[1].k[slot], segs[2].k[slot], 0,
+                                  segs[0].k[slot], -1.f, rhs_ws, st);
+    }
+    // reduce a 3-value kernel result for segment si into sums_dev[si]
+    void finish_sums(int si) { final_reduce_kernel<<<1, 32, 0, st>>>(partial, nblk(segs[si].n), sums_dev + 3 * si); }
+    int fetch_sums() {
+        cudaError_t e = cudaMemcpyAsync(sums_host, sums_dev, sizeof(double) * 3 * segs.size(), cudaMemcpyDeviceToHost,
+                                        st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            phx_set_error("stream engine sync: %s", cudaGetErrorString(e));
+            return PHX_ERR_CUDA;
+        }
+        return PHX_OK;
+    }
+    float block_norm(int q) {  // max over segments of sqrt(mean) in fp32 (misc.py:10-24)
+        float m = 0.f;
+        bool any_nan = false;
+        for (size_t si = 0; si < segs.size(); ++si) {
+            double s = sums_host[3 * si + q];
+            if (isnan(s)) any_nan = true;
+            m = fmaxf(m, sqrtf((float)(s / segs[si].count)));
+        }
+        return any_nan ? nanf("") : m;
+    }
+    void set_inputs(const KSet* per_seg) {
+        for (size_t si = 0; si < segs.size(); ++si) {
+            Seg& s = segs[si];
+            if (s.xs) combine_kernel<<<nblk(s.n), EB, 0, st>>>(s.xs, s.x0, per_seg[si], s.n);
+        }
+    }
+    KSet kset(int si, const int* slots, const float* coef, int nk) {
+        KSet a;
+        a.nk = nk;
+        for (int j = 0; j < nk; ++j) {
+            a.k[j] = segs[si].k[slots[j]];
+            a.c[j] = coef[j];
+        }
+        for (int j = nk; j < 7; ++j) {
+            a.k[j] = nullptr;
+            a.c[j] = 0.f;
+        }
+        return a;
+    }
+    void copy_to_inputs() {
+        for (auto& s : segs)
+            if (s.xs) cudaMemcpyAsync(s.xs, s.x0, s.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    }
+
+    // ---- one fixed-grid step of size dtf on all segments (x0 updated in place) ----
+    int fixed_step(float dtf) {
+        int rc;
+        copy_to_inputs();
+        if ((rc = eval(0)) != PHX_OK) return rc;
+        auto fx = [&](int mode, Seg& s, float* out, float dt) {
+            fixed_kernel<<<nblk(s.n), EB, 0, st>>>(mode, out, s.x0, s.k[0], s.k[1], s.k[2], s.k[3], dt, s.n);
+        };
+        if (method == PHX_EULER) {
+            for (auto& s : segs) fx(FX_EULER_END, s, s.x0, dtf);
+            status.n_rhs += 1;
+        } else if (method == PHX_MIDPOINT) {
+            for (auto& s : segs)
+                if (s.xs) fx(FX_MID_IN, s, s.xs, 0.5f * dtf);
+            if ((rc = eval(1)) != PHX_OK) return rc;
+            for (auto& s : segs)
+                fixed_kernel<<<nblk(s.n), EB, 0, st>>>(FX_EULER_END, s.x0, s.x0, s.k[1], nullptr, nullptr, nullptr, dtf,
+                                                       s.n);
+            status.n_rhs += 2;
+        } else {
+            for (auto& s : segs)
+                if (s.xs) fx(FX_RK4_IN2, s, s.xs, dtf);
+            if ((rc = eval(1)) != PHX_OK) return rc;
+            for (auto& s : segs)
+                if (s.xs) fx(FX_RK4_IN3, s, s.xs, dtf);
+            if ((rc = eval(2)) != PHX_OK) return rc;
+            for (auto& s : segs)
+                if (s.xs) fx(FX_RK4_IN4, s, s.xs, dtf);
+            if ((rc = eval(3)) != PHX_OK) return rc;
+            for (auto& s : segs) fx(FX_RK4_END, s, s.x0, dtf);
+            status.n_rhs += 4;
+        }
+        return PHX_OK;
+    }
+
+    // ---- dopri5 from t_start until every time in outs[] (increasing, > t_start) has been emitted ----
+    // emit(j, xs[4], slots, dtf) writes the dense output for outs[j].
+    template <typename Emit>
+    int dopri5(double t_start, const double* outs, int nout, Emit emit) {
+        int rc;
+        const size_t ns = segs.size();
+        int sl[7] = {0, 1, 2, 3, 4, 5, 6};
+        copy_to_inputs();
+        if ((rc = eval(0)) != PHX_OK) return rc;
+        for (size_t si = 0; si < ns; ++si) {
+            Seg& s = segs[si];
+            init01_kernel<<<nblk(s.n), EB, 0, st>>>(s.x0, s.k[0], rtol_f, atol_f, s.n, partial);
+            finish_sums((int)si);
+        }
+        if ((rc = fetch_sums()) != PHX_OK) return rc;
+        float d0 = block_norm(0), d1 = block_norm(1);
+        bool nonfinite = false;
+        for (size_t si = 0; si < ns; ++si) nonfinite = nonfinite || sums_host[3 * si + 2] > 0.0;
+        float h0 = (d0 < 1e-5f || d1 < 1e-5f) ? 1e-6f : 0.01f * d0 / d1;
+        {
+            std::vector<KSet> ks(ns);
+            int s0[1] = {0};
+            float c0[1] = {h0};
+            for (size_t si = 0; si < ns; ++si) ks[si] = kset((int)si, s0, c0, 1);
+            set_inputs(ks.data());
+        }
+        if ((rc = eval(1)) != PHX_OK) return rc;
+        for (size_t si = 0; si < ns; ++si) {
+            Seg& s = segs[si];
+            initd2_kernel<<<nblk(s.n), EB, 0, st>>>(s.x0, s.k[0], s.k[1], rtol_f, atol_f, s.n, partial);
+            finish_sums((int)si);
+        }
+        if ((rc = fetch_sums()) != PHX_OK) return rc;
+        float d2 = block_norm(0) / h0;
+        float h1 = (d1 <= 1e-15f && d2 <= 1e-15f) ? fmaxf(1e-6f, h0 * 1e-3f) : powf(0.01f / fmaxf(d1, d2), 0.2f);
+        double dt = (double)fminf(100.f * h0, h1);
+        status.n_rhs += 2;
+        double tcur = t_start, tprev = t_start;
+        int next_out = 0;
+        long long nsteps = 0;
+        while (next_out < nout) {
+            if (nsteps >= max_steps) return fail(PHX_ST_MAX_STEPS, tcur, dt);
+            if (!(tcur + dt > tcur)) return fail(PHX_ST_DT_UNDERFLOW, tcur, dt);
+            if (nonfinite) return fail(PHX_ST_NONFINITE, tcur, dt);
+            const float dtf = (float)dt;
+            float cb[6][6], cerr[7], cmid[7];
+            for (int i = 0; i < 6; ++i)
+                for (int j = 0; j <= i; ++j) cb[i][j] = (float)H_BETA[i][j] * dtf;
+            for (int j = 0; j < 7; ++j) {
+                cerr[j] = dtf * (float)H_CERR[j];
+                cmid[j] = dtf * (float)H_CMID[j];
+            }
+            for (int stg = 1; stg <= 6; ++stg) {
+                // stage input from beta[stg-1]; the last one is y1 and is written to x1 as well
+                for (size_t si = 0; si < ns; ++si) {
+                    Seg& s = segs[si];
+                    KSet a = kset((int)si, sl, cb[stg - 1], stg);
+                    if (stg == 6) {
+                        combine_kernel<<<nblk(s.n), EB, 0, st>>>(s.x1, s.x0, a, s.n);
+                        if (s.xs) cudaMemcpyAsync(s.xs, s.x1, s.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
+                    } else if (s.xs) {
+                        combine_kernel<<<nblk(s.n), EB, 0, st>>>(s.xs, s.x0, a, s.n);
+                    }
+                }
+                if ((rc = eval(sl[stg])) != PHX_OK) return rc;
+            }
+            for (size_t si = 0; si < ns; ++si) {
+                Seg& s = segs[si];
+                KSet a = kset((int)si, sl, cerr, 7);
+                err_kernel<<<nblk(s.n), EB, 0, st>>>(s.x0, s.x1, a, rtol_f, atol_f, s.n, partial);
+                finish_sums((int)si);
+            }
+            if ((rc = fetch_sums()) != PHX_OK) return rc;
+            float ratio = block_norm(0);
+            bool accept = ratio <= 1.f;
+            if ((int)log.size() / 3 < steplog_cap) {
+                log.push_back(tcur);
+                log.push_back(dt);
+                log.push_back(accept ? 1.0 : 0.0);
+            }
+            status.n_rhs += 6;
+            tprev = tcur;
+            ++nsteps;
+            double dt_used = dt;
+            dt = next_dt_host(dt, ratio);
+            if (!accept) {
+                status.n_rejected++;
+                continue;
+            }
+            status.n_accepted++;
+            tcur = tcur + dt_used;
+            nonfinite = false;
+            for (size_t si = 0; si < ns; ++si) nonfinite = nonfinite || sums_host[3 * si + 1] > 0.0;
+            while (next_out < nout && outs[next_out] <= tcur) {
+                double x = (outs[next_out] - tprev) / (tcur - tprev);
+                float xs[4];
+                double xp = x;
+                xs[0] = (float)xp; xp *= x; xs[1] = (float)xp; xp *= x; xs[2] = (float)xp; xp *= x; xs[3] = (float)xp;
+                emit(next_out, xs, sl, dtf, cmid);
+                ++next_out;
+                nsteps = 0;
+            }
+            for (auto& s : segs) std::swap(s.x0, s.x1);
+            std::swap(sl[0], sl[6]);
+        }
+        return PHX_OK;
+    }
+    void interp_seg(int si, float* out, const float* xs, const int* sl, float dtf, const float* cmid) {
+        Seg& s = segs[si];
+        KSet mid = kset(si, sl, cmid, 7);
+        interp_kernel<<<nblk(s.n), EB, 0, st>>>(out, s.x0, s.x1, mid, s.k[sl[0]], s.k[sl[6]], dtf, xs[0], xs[1], xs[2],
+                                                xs[3], s.n);
+    }
+    int fail(int code, double t, double dt) {
+        status.code = code;
+        status.t_fail = t;
+        status.dt_fail = dt;
+        return PHX_OK;  // a solver assertion is reported through the status record, like the resident kernels
+    }
+};
+
+size_t stream_ws_floats(int G, int H, int B, int T, int adjoint, size_t* o_rhs, size_t* o_partial, size_t* o_sums,
+                        size_t* o_seg) {
+    size_t off = 0;
+    auto take = [&](size_t nfloats) {
+        size_t o = off;
+        off += (nfloats + 3) & ~size_t(3);
+        return o;
+    };
+    size_t partial = take(2 * (size_t)MAXBLK * 3);
+    size_t sums = take(2 * 3 * 3 + 2);
+    size_t rhs = take(phx_rhs_workspace_floats(G, H, B));
+    size_t BG = (size_t)B * G;
+    size_t seg = take(adjoint ? 2 * 10 * BG + 8 * phx_grad_offsets(G, H).total + 64 : 10 * BG + 16);
+    if (o_rhs) *o_rhs = rhs;
+    if (o_partial) *o_partial = partial;
+    if (o_sums) *o_sums = sums;
+    if (o_seg) *o_seg = seg;
+    return off;
+}
+
+void write_back(Stream& S, phx_status* status_out) {
+    S.status.n_logged = (int)(S.log.size() / 3);
+    cudaPointerAttributes at;
+    bool dev_status = false, dev_log = false;
+    if (status_out && cudaPointerGetAttributes(&at, status_out) == cudaSuccess) dev_status = at.type == cudaMemoryTypeDevice;
+    if (S.steplog && cudaPointerGetAttributes(&at, S.steplog) == cudaSuccess) dev_log = at.type == cudaMemoryTypeDevice;
+    cudaGetLastError();
+    cudaStreamSynchronize(S.st);
+    if (S.steplog && !S.log.empty()) {
+        if (dev_log) cudaMemcpy(S.steplog, S.log.data(), S.log.size() * sizeof(double), cudaMemcpyHostToDevice);
+        else memcpy(S.steplog, S.log.data(), S.log.size() * sizeof(double));
+    }
+    if (status_out) {
+        if (dev_status) cudaMemcpy(status_out, &S.status, sizeof(phx_status), cudaMemcpyHostToDevice);
+        else *status_out = S.status;
+    }
+}
+
+int setup(Stream& S, phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T, int t_is_f32,
+          int method, double rtol, double atol, int64_t max_steps, int adjoint, void* workspace, size_t ws_bytes,
+          double* steplog, int steplog_cap, cudaStream_t st, float** seg_base) {
+    if (!ctx || G < 1 || H < 1 || B < 1 || !packed || !t_host || !workspace || T < 2) {
+        phx_set_error("stream solve: invalid argument");
+        return PHX_ERR_INVALID;
+    }
+    for (int i = 1; i < T; ++i)
+        if (!(t_host[i] > t_host[i - 1])) {
+            phx_set_error("t must be strictly increasing at the C boundary");
+            return PHX_ERR_INVALID;
+        }
+    if (method < PHX_EULER || method > PHX_DOPRI5) {
+        phx_set_error("unknown method id %d", method);
+        return PHX_ERR_INVALID;
+    }
+    size_t o_rhs, o_partial, o_sums, o_seg;
+    size_t need = stream_ws_floats(G, H, B, T, adjoint, &o_rhs, &o_partial, &o_sums, &o_seg) * sizeof(float);
+    if (ws_bytes < need) {
+        phx_set_error("stream workspace too small: %zu < %zu", ws_bytes, need);
+        return PHX_ERR_WORKSPACE;
+    }
+    float* ws = (float*)workspace;
+    S.ctx = ctx; S.G = G; S.H = H; S.B = B; S.T = T; S.method = method; S.t_is_f32 = t_is_f32; S.adjoint = adjoint;
+    S.rtol_f = (float)rtol; S.atol_f = (float)atol; S.fsign = 1.f; S.max_steps = (long long)max_steps;
+    S.w = phx_packed_view(packed, G, H);
+    S.st = st;
+    S.rhs_ws = ws + o_rhs;
+    S.partial = (double*)(ws + o_partial);
+    S.sums_dev = (double*)(ws + o_sums);
+    S.steplog = steplog;
+    S.steplog_cap = steplog ? steplog_cap : 0;
+    memset(&S.status, 0, sizeof(S.status));
+    static thread_local double* pinned = nullptr;
+    if (!pinned && cudaMallocHost((void**)&pinned, sizeof(double) * 16) != cudaSuccess) {
+        phx_set_error("cudaMallocHost failed");
+        return PHX_ERR_CUDA;
+    }
+    S.sums_host = pinned;
+    *seg_base = ws + o_seg;
+    return PHX_OK;
+}
+
+float fixed_dt(const double* t, int i, int t_is_f32) {
+    return t_is_f32 ? ((float)t[i + 1] - (float)t[i]) : (float)(t[i + 1] - t[i]);
+}
+
+}  // namespace
+
 extern "C" {
-size_t phx_stream_workspace_bytes(const phx_ctx*, int, int, int, int, int) {
-    phx_set_error("streaming engine not built yet");
-    return 0;
+
+size_t phx_stream_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint) {
+    if (!ctx || G < 1 || H < 1 || B < 1 || T < 2) return 0;
+    return stream_ws_floats(G, H, B, T, adjoint, nullptr, nullptr, nullptr, nullptr) * sizeof(float);
 }
-int phx_stream_solve_forward(phx_ctx*, int, int, int, const float*, const float*, const double*, int, int, int, int,
-                             double, double, int64_t, float*, void*, size_t, phx_status*, double*, int, void*) {
-    phx_set_error("streaming engine not built yet");
-    return PHX_ERR_UNSUPPORTED;
+
+int phx_stream_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y0,
+                             const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol,
+                             double atol, int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
+                             phx_status* status, double* steplog, int steplog_cap, void* stream) {
+    Stream S;
+    float* base;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y0 || !y_out) {
+        phx_set_error("null y0 / y_out");
+        return PHX_ERR_INVALID;
+    }
+    int rc = setup(S, ctx, G, H, B, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 0, workspace,
+                   workspace_bytes, steplog, steplog_cap, st, &base);
+    if (rc != PHX_OK) return rc;
+    S.fsign = reversed ? -1.f : 1.f;
+    const size_t BG = (size_t)B * G;
+    Seg y;
+    y.n = BG; y.count = (double)BG;
+    y.x0 = base; y.x1 = base + BG; y.xs = base + 2 * BG;
+    for (int i = 0; i < 7; ++i) y.k[i] = base + (3 + i) * BG;
+    S.segs.push_back(y);
+    cudaMemcpyAsync(y.x0, y0, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(y_out, y0, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (method != PHX_DOPRI5) {
+        for (int i = 0; i + 1 < T && rc == PHX_OK; ++i) {
+            rc = S.fixed_step(fixed_dt(t_host, i, t_is_f32));
+            cudaMemcpyAsync(y_out + (size_t)(i + 1) * BG, S.segs[0].x0, BG * sizeof(float), cudaMemcpyDeviceToDevice,
+                            st);
+        }
+    } else {
+        rc = S.dopri5(t_host[0], t_host + 1, T - 1,
+                      [&](int j, const float* xs, const int* sl, float dtf, const float* cmid) {
+                          S.interp_seg(0, y_out + (size_t)(j + 1) * BG, xs, sl, dtf, cmid);
+                      });
+    }
+    if (rc != PHX_OK) return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("stream forward: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    write_back(S, status);
+    return PHX_OK;
 }
-int phx_stream_solve_adjoint(phx_ctx*, int, int, int, const float*, const double*, int, int, int, double, double,
-                             int64_t, const float*, const float*, float*, float*, void*, size_t, phx_status*, double*,
-                             int, void*) {
-    phx_set_error("streaming engine not built yet");
-    return PHX_ERR_UNSUPPORTED;
+
+int phx_stream_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
+                             int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                             const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
+                             void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                             int steplog_cap, void* stream) {
+    Stream S;
+    float* base;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!y_saved || !grad_y || !adj_y0 || !grads_flat) {
+        phx_set_error("null y_saved / grad_y / adj_y0 / grads_flat");
+        return PHX_ERR_INVALID;
+    }
+    int rc = setup(S, ctx, G, H, B, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 1, workspace,
+                   workspace_bytes, steplog, steplog_cap, st, &base);
+    if (rc != PHX_OK) return rc;
+    const size_t BG = (size_t)B * G, P = phx_grad_offsets(G, H).total;
+    Seg y, a, th;
+    y.n = a.n = BG; y.count = a.count = (double)BG;
+    y.x0 = base; y.x1 = base + BG; y.xs = base + 2 * BG;
+    for (int i = 0; i < 7; ++i) y.k[i] = base + (3 + i) * BG;
+    float* ab = base + 10 * BG;
+    a.x0 = ab; a.x1 = ab + BG; a.xs = ab + 2 * BG;
+    for (int i = 0; i < 7; ++i) a.k[i] = ab + (3 + i) * BG;
+    float* tb = ab + 10 * BG;
+    tb += (4 - ((size_t)(tb - (float*)workspace) & 3)) & 3;
+    th.n = P; th.count = (double)P;
+    th.x0 = grads_flat; th.x1 = tb; th.xs = nullptr;
+    for (int i = 0; i < 7; ++i) th.k[i] = tb + (size_t)(1 + i) * P;
+    S.segs.push_back(y);
+    S.segs.push_back(a);
+    S.segs.push_back(th);
+    cudaMemsetAsync(grads_flat, 0, P * sizeof(float), st);
+    cudaMemcpyAsync(S.segs[1].x0, grad_y + (size_t)(T - 1) * BG, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    for (int iv = T - 1; iv >= 1 && rc == PHX_OK && S.status.code == PHX_ST_OK; --iv) {
+        cudaMemcpyAsync(S.segs[0].x0, y_saved + (size_t)iv * BG, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
+        if (method != PHX_DOPRI5) {
+            rc = S.fixed_step(fixed_dt(t_host, iv - 1, t_is_f32));
+        } else {
+            double t_end = -t_host[iv - 1];
+            rc = S.dopri5(-t_host[iv], &t_end, 1,
+                          [&](int, const float* xs, const int* sl, float dtf, const float* cmid) {
+                              // dense output at t_end for adj_y and adj_params, written into x1 so that the swap
+                              // after the step leaves it in x0; y is replaced by the saved state anyway
+                              // (in place: every element is read before it is overwritten)
+                              S.interp_seg(1, S.segs[1].x1, xs, sl, dtf, cmid);
+                              S.interp_seg(2, S.segs[2].x1, xs, sl, dtf, cmid);
+                          });
+        }
+        if (rc != PHX_OK) break;
+        Seg& as = S.segs[1];
+        add_kernel<<<nblk(BG), EB, 0, st>>>(as.x0, grad_y + (size_t)(iv - 1) * BG, BG);
+    }
+    if (rc != PHX_OK) return rc;
+    cudaMemcpyAsync(adj_y0, S.segs[1].x0, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    if (S.segs[2].x0 != grads_flat)
+        cudaMemcpyAsync(grads_flat, S.segs[2].x0, P * sizeof(float), cudaMemcpyDeviceToDevice, st);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("stream adjoint: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    write_back(S, status);
+    return PHX_OK;
 }
-}
+
+}  // extern "C"

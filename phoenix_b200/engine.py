@@ -17,8 +17,21 @@ from . import _lib
 SYNC_ERRORS = False
 STEP_LOGGING = False
 STEPLOG_CAP = 4096
+FORCE_ENGINE = None  # None | "resident" | "stream"  (tests compare the two engines on the same inputs)
 
-_state = threading.local()
+class _State:
+    """Process-wide bookkeeping (NOT thread-local: autograd runs backward() on its own worker thread)."""
+
+    def __init__(self):
+        self.lock = threading.RLock()
+        self.pending = []       # [(status_tensor, what)]
+        self.free_status = []
+        self.last_log = None
+        self.last_status = None
+        self.workspaces = {}
+
+
+_state = _State()
 
 
 def set_sync_errors(flag):
@@ -33,12 +46,6 @@ def set_step_logging(flag):
 
 
 def _tls():
-    if not hasattr(_state, "pending"):
-        _state.pending = []       # [(status_tensor, what)]
-        _state.free_status = []
-        _state.last_log = None
-        _state.last_status = None
-        _state.workspaces = {}
     return _state
 
 
@@ -261,10 +268,12 @@ def _t_array(t_list):
 
 def _pick_engine(lib, dev, G, H, B, T, adjoint):
     """Resident (one persistent cooperative launch) when the rows fit on chip, else the streaming engine."""
-    if B <= lib.phx_resident_max_rows(int(adjoint)):
+    if FORCE_ENGINE != "stream" and B <= lib.phx_resident_max_rows(int(adjoint)):
         nb = lib.phx_solve_workspace_bytes(_lib.ctx(dev), G, H, B, T, int(adjoint))
         if nb > 0:
             return "resident", nb
+    if FORCE_ENGINE == "resident":
+        raise NotImplementedError("resident engine cannot take G=%d H=%d B=%d: %s" % (G, H, B, _lib.last_error()))
     nb = lib.phx_stream_workspace_bytes(_lib.ctx(dev), G, H, B, T, int(adjoint))
     if nb == 0:
         raise NotImplementedError("phoenix_b200: no kernel for G=%d H=%d B=%d (%s)" % (G, H, B, _lib.last_error()))

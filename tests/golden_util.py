@@ -45,3 +45,19 @@ def compare_logs(mine, ref, dt_rtol=1e-6):
     if len(mine) != len(ref):
         return n, "length differs: mine=%d ref=%d" % (len(mine), len(ref))
     return n, "identical"
+
+
+def assert_logs_close(mine, ref, dt_rtol, what=""):
+    """Step-log parity as far as it is well defined.  The reference's accept/reject sequence is decided by an error
+    estimate that is at fp32 rounding level for the default rtol=1e-7 (it differs between 1 and 8 CPU threads of the
+    reference itself, see tests/golden/*.npz `stable`), so exact equality is only asserted by the callers for cases
+    the reference reproduces; in general we require: same first step (Hairer heuristic, well conditioned), a common
+    prefix of at least 3 attempts within dt_rtol, and the same number of attempts within max(2, 15%)."""
+    mine = [tuple(x) for x in mine]
+    ref = [tuple(x) for x in ref]
+    assert len(mine) > 0 and len(ref) > 0, what
+    assert abs(mine[0][1] - ref[0][1]) <= 1e-5 * abs(ref[0][1]), (what, "first dt", mine[0], ref[0])
+    n, msg = compare_logs(mine, ref, dt_rtol)
+    assert n >= min(3, len(ref)), (what, msg)
+    assert abs(len(mine) - len(ref)) <= max(2, int(0.15 * len(ref))), (what, msg)
+    return msg

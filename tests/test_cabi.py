@@ -1,0 +1,38 @@
+"""CPU: the C-ABI library loads and exports every symbol include/phoenix_b200.h declares (no compute calls)."""
+import ctypes
+import os
+import re
+
+from phoenix_b200 import _lib
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(REPO, "include", "phoenix_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(phx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_expected_entry_points():
+    syms = declared_symbols()
+    for must in ("phx_pack_weights", "phx_rhs_forward", "phx_rhs_vjp", "phx_solve_forward", "phx_solve_adjoint",
+                 "phx_stream_solve_forward", "phx_stream_solve_adjoint", "phx_ctx_create"):
+        assert must in syms
+    assert sorted(_lib.EXPORTS) == syms
+
+
+def test_library_loads_and_exports_every_declared_symbol():
+    lib = _lib.load()
+    raw = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared_symbols():
+        assert hasattr(raw, name), name
+    assert lib.phx_resident_max_rows(0) >= 1 and lib.phx_resident_max_rows(1) >= 1
+    # pure host helpers: sizes follow the documented layout
+    G, H = 350, 40
+    assert lib.phx_packed_bytes(G, H) == 4 * (2 * G * 80 + 80 + 2 * 352)
+    assert lib.phx_rhs_workspace_bytes(G, H, 7) >= 4 * (2 * 7 * 80 + 7 * G)
+
+
+def test_status_struct_matches_header():
+    assert ctypes.sizeof(_lib.PhxStatus) == 40

@@ -1,0 +1,322 @@
+"""GPU parity tests: the CUDA path (through the Python mirror -> C ABI -> kernels) against
+  (1) the committed golden vectors produced by the reference itself (tests/golden/*.npz),
+  (2) the CPU oracle on seeded inputs at the BASELINE shapes (yeast 3551x120, breast 11165x200),
+  (3) size-independent properties at full size.
+
+Tolerances (fp32 everywhere; stated in north_star as ~1e-5 for fixed-step solvers):
+  * RHS / VJP and euler / midpoint / rk4 solves, losses and gradients: relative L2 <= 1e-5 (observed ~1e-7);
+  * dopri5 at the reference default rtol=1e-7 / atol=1e-9: y <= 1e-5, gradients <= 5e-5.  The accept/reject sequence
+    at that tolerance is decided by fp32 rounding noise in the error estimate: the reference does not reproduce its
+    own sequence between 1 and 8 CPU threads (golden field `stable`, `self_grad_rel` up to 1e-5), so step logs are
+    compared with `assert_logs_close` (same first step, common prefix, same length within 15 %), and accuracy is
+    additionally checked against a float64 solve of the oracle: our error may not exceed 3x the reference's own.
+  * dopri5 with loose tolerances (rtol 1e-3..1e-4): the controller semantics are pinned above the noise floor.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import assert_logs_close, load, manifest, rel_l2, weights_of
+from oracle import phoenix_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+RHS = [m["name"] for m in manifest("rhs")]
+SOLVE = manifest("solve")
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import phoenix_b200 as pb
+    pb.set_sync_errors(True)
+    pb.set_step_logging(True)
+    yield pb
+    pb.set_step_logging(False)
+    pb.set_sync_errors(False)
+
+
+def make_net(pb, w):
+    net = pb.ODENet("cuda", w.G, neurons=w.H)
+    with torch.no_grad():
+        for p, src in zip(net.parameters(), w.as_list()):
+            p.copy_(src)
+    return net
+
+
+def grads_of(net):
+    return [p.grad.detach().cpu() for p in net.parameters()]
+
+
+@pytest.mark.parametrize("name", RHS)
+def test_rhs_and_vjp_golden(pb, name):
+    d = load(name)
+    net = make_net(pb, weights_of(d))
+    for tag, fn in (("decay", net.forward), ("prior", net.prior_only_forward)):
+        net.zero_grad()
+        y = torch.from_numpy(d["y"]).cuda().requires_grad_(True)
+        f = fn(None, y)
+        f.backward(torch.from_numpy(d["g"]).cuda())
+        assert rel_l2(f.detach().cpu(), d["f_" + tag]) < 1e-5
+        assert rel_l2(y.grad.cpu(), d["ybar_" + tag]) < 1e-5
+        for i, p in enumerate(net.parameters()):
+            ref = d["pbar%d_%s" % (i, tag)]
+            if p.grad is None:
+                assert not ref.any()
+                continue
+            if not ref.any():
+                assert not p.grad.any()
+            else:
+                assert rel_l2(p.grad.cpu(), ref) < 1e-5, (name, tag, i)
+
+
+def _run_case(pb, m, d, engine_name=None):
+    pb.engine.FORCE_ENGINE = engine_name
+    try:
+        net = make_net(pb, weights_of(d))
+        y0 = torch.from_numpy(d["y0"]).cuda().requires_grad_(bool(m["adjoint"]))
+        t = torch.from_numpy(d["t"])
+        rtol, atol = float(d["rtol"]), float(d["atol"])
+        if m["adjoint"]:
+            y = pb.odeint_adjoint(net, y0, t, rtol=rtol, atol=atol, method=m["method"])
+        else:
+            with torch.no_grad():
+                y = pb.odeint(net, y0, t, rtol=rtol, atol=atol, method=m["method"])
+        flog = pb.last_step_log()
+        out = {"y": y.detach().cpu(), "flog": flog}
+        if m["adjoint"]:
+            target = torch.from_numpy(d["target"]).cuda()
+            loss = torch.mean((y[1:] - target) ** 2)
+            loss.backward()
+            out.update(loss=loss.item(), blog=pb.last_step_log(), adj_y0=y0.grad.cpu(), grads=grads_of(net))
+        return out
+    finally:
+        pb.engine.FORCE_ENGINE = None
+
+
+def _check_case(m, d, out):
+    loose = float(d["rtol"]) > 1e-6
+    dop = m["method"] == "dopri5"
+    ytol = 1e-5 if not dop else (5e-3 if loose else 1e-5)
+    gtol = 1e-5 if not dop else (5e-3 if loose else 5e-5)
+    assert rel_l2(out["y"], d["y"]) < ytol
+    if dop:
+        assert_logs_close(out["flog"], d["flog"], 5e-2, m["name"] + " fwd")
+    if m["adjoint"]:
+        assert abs(out["loss"] - float(d["loss"])) <= 10 * ytol * abs(float(d["loss"]))
+        assert rel_l2(out["adj_y0"], d["adj_y0"]) < gtol
+        for i, g in enumerate(out["grads"]):
+            assert rel_l2(g, d["grad%d" % i]) < gtol, (m["name"], i, rel_l2(g, d["grad%d" % i]))
+        if dop:
+            assert_logs_close(out["blog"], d["blog"], 5e-2, m["name"] + " bwd")
+
+
+@pytest.mark.parametrize("m", SOLVE, ids=[m["name"] for m in SOLVE])
+def test_solve_and_adjoint_golden(pb, m):
+    d = load(m["name"])
+    _check_case(m, d, _run_case(pb, m, d))
+
+
+@pytest.mark.parametrize("m", [m for m in SOLVE if m["B"] <= 3], ids=[m["name"] for m in SOLVE if m["B"] <= 3])
+def test_streaming_engine_golden(pb, m):
+    """The any-B engine on the small goldens (the default dispatch sends these to the resident kernels)."""
+    d = load(m["name"])
+    _check_case(m, d, _run_case(pb, m, d, "stream"))
+
+
+@pytest.mark.parametrize("name", ["solve_dopri5_g350_h40_b1_dense", "solve_dopri5_g129_h33_b5_t4",
+                                  "solve_dopri5_g37_h5_b1"])
+def test_dopri5_accuracy_against_fp64_truth(pb, name):
+    """Our dopri5 result must be as close to the exact solution as the reference's own (3x margin)."""
+    m = [x for x in SOLVE if x["name"] == name][0]
+    d = load(name)
+    w = weights_of(d)
+    w64 = O.Weights(*[p.double() for p in w.as_list()])
+    y0, t = torch.from_numpy(d["y0"]).double(), torch.from_numpy(d["t"]).double()
+    ytrue, _ = O.odeint(w64, y0, t, method="dopri5", rtol=1e-11, atol=1e-13)
+    target = torch.from_numpy(d["target"]).double()
+    gy = torch.zeros_like(ytrue)
+    gy[1:] = 2.0 * (ytrue[1:] - target) / target.numel()
+    _, gtrue, _ = O.adjoint_backward(w64, t, ytrue, gy, method="dopri5", rtol=1e-11, atol=1e-13)
+    out = _run_case(pb, m, d)
+    assert rel_l2(out["y"], ytrue) <= 3 * rel_l2(d["y"], ytrue) + 2e-7
+    for i, g in enumerate(out["grads"]):
+        ref_err = rel_l2(d["grad%d" % i], gtrue[i])
+        assert rel_l2(g, gtrue[i]) <= 3 * ref_err + 5e-6, (name, i, rel_l2(g, gtrue[i]), ref_err)
+
+
+def _oracle_case(G, H, B, method, times, seed, dense=True, rtol=1e-7, atol=1e-9):
+    w = O.make_weights(G, H, seed, dense=dense)
+    gen = torch.Generator().manual_seed(seed + 1)
+    shape = (1, G) if B == 1 else (B, 1, G)
+    y0 = torch.rand(*shape, generator=gen)
+    t = torch.tensor(times, dtype=torch.float32)
+    target = torch.rand(len(times) - 1, *shape, generator=gen)
+    y, flog = O.odeint(w, y0, t, method=method, rtol=rtol, atol=atol)
+    gy = torch.zeros_like(y)
+    gy[1:] = 2.0 * (y[1:] - target) / target.numel()
+    ady, grads, blog = O.adjoint_backward(w, t, y, gy, method=method, rtol=rtol, atol=atol)
+    return w, y0, t, target, y, ady, grads, flog, blog
+
+
+@pytest.mark.parametrize("G,H,method,times", [
+    (3551, 120, "rk4", [0.0, 5.0]),            # Pramila yeast shape, config_yeast.cfg
+    (3551, 120, "dopri5", [0.0, 0.5]),
+    (11165, 200, "rk4", [0.0, 0.0051]),        # breast-cancer shape, 178-point pseudotime spacing
+    (11165, 200, "dopri5", [0.0, 0.0051]),
+    (11165, 40, "euler", [0.0, 0.0051, 0.0102]),
+])
+def test_baseline_shapes_against_oracle(pb, G, H, method, times):
+    w, y0, t, target, y_ref, ady_ref, g_ref, flog, blog = _oracle_case(G, H, 1, method, times, 900 + H)
+    net = make_net(pb, w)
+    y0g = y0.cuda().requires_grad_(True)
+    y = pb.odeint_adjoint(net, y0g, t, method=method)
+    mine_f = pb.last_step_log()
+    loss = torch.mean((y[1:] - target.cuda()) ** 2)
+    loss.backward()
+    mine_b = pb.last_step_log()
+    dop = method == "dopri5"
+    assert rel_l2(y.detach().cpu(), y_ref) < 1e-5
+    gtol = 5e-5 if dop else 1e-5
+    assert rel_l2(y0g.grad.cpu(), ady_ref) < gtol
+    for i, (a, b) in enumerate(zip(grads_of(net), g_ref)):
+        assert rel_l2(a, b) < gtol, (G, H, method, i, rel_l2(a, b))
+    if dop:
+        assert_logs_close(mine_f, flog.steps, 5e-2, "fwd")
+        assert_logs_close(mine_b, blog.steps, 5e-2, "bwd")
+
+
+def test_bitwise_determinism(pb):
+    w = O.make_weights(690, 40, 77, dense=True)
+    net = make_net(pb, w)
+    y0 = torch.rand(1, 690, generator=torch.Generator().manual_seed(3)).cuda()
+    t = torch.tensor([0.0, 2.0])
+    runs = []
+    for _ in range(2):
+        net.zero_grad()
+        y0g = y0.clone().requires_grad_(True)
+        y = pb.odeint_adjoint(net, y0g, t, method="dopri5")
+        (y[1] ** 2).mean().backward()
+        runs.append([y.detach().clone(), y0g.grad.clone()] + [p.grad.clone() for p in net.parameters()])
+    for a, b in zip(*runs):
+        assert torch.equal(a, b)
+
+
+def test_batched_fixed_step_equals_per_row(pb):
+    """Fixed-grid rows are independent (no global norm): a B=4 resident solve equals four B=1 solves bit for bit."""
+    w = O.make_weights(350, 40, 78, dense=True)
+    net = make_net(pb, w)
+    y0 = torch.rand(4, 1, 350, generator=torch.Generator().manual_seed(4)).cuda()
+    t = torch.tensor([0.0, 1.0, 3.0])
+    with torch.no_grad():
+        yb = pb.odeint(net, y0, t, method="rk4")
+        for b in range(4):
+            yr = pb.odeint(net, y0[b], t, method="rk4")
+            assert torch.equal(yb[:, b], yr)
+
+
+def test_engines_agree_batched(pb):
+    """Resident and streaming engines on the same B=4 batch (global RMS norm over the batch, misc.py:10-11)."""
+    w = O.make_weights(350, 40, 79, dense=True)
+    net = make_net(pb, w)
+    y0 = torch.rand(4, 1, 350, generator=torch.Generator().manual_seed(5)).cuda()
+    t = torch.tensor([0.0, 0.7, 1.3], dtype=torch.float64)
+    res = {}
+    for eng in ("resident", "stream"):
+        pb.engine.FORCE_ENGINE = eng
+        try:
+            net.zero_grad()
+            y0g = y0.clone().requires_grad_(True)
+            y = pb.odeint_adjoint(net, y0g, t, method="dopri5", rtol=1e-5, atol=1e-7)
+            (y[1:] ** 2).mean().backward()
+            res[eng] = [y.detach().cpu(), y0g.grad.cpu()] + grads_of(net)
+        finally:
+            pb.engine.FORCE_ENGINE = None
+    for a, b in zip(res["resident"], res["stream"]):
+        assert rel_l2(a, b) < 1e-4
+
+
+def test_time_reversal_property_full_size(pb):
+    """Integrating forward then backward in time returns to the start (rk4, O(dt^5) defect) at the breast shape."""
+    G, H = 11165, 200
+    w = O.make_weights(G, H, 80, dense=False)
+    net = make_net(pb, w)
+    y0 = torch.rand(1, G, generator=torch.Generator().manual_seed(6)).cuda()
+    with torch.no_grad():
+        y1 = pb.odeint(net, y0, torch.tensor([0.0, 0.05]), method="rk4")[1]
+        yb = pb.odeint(net, y1, torch.tensor([0.05, 0.0]), method="rk4")[1]
+    assert rel_l2(yb.cpu(), y0.cpu()) < 1e-6
+    assert rel_l2(y1.cpu(), y0.cpu()) > 1e-5      # the state did move
+
+
+def test_adjoint_gradient_matches_directional_finite_difference(pb):
+    G, H = 3551, 120
+    w = O.make_weights(G, H, 81, dense=True)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(7)
+    y0 = torch.rand(1, G, generator=gen).cuda()
+    v = torch.randn(1, G, generator=gen).cuda()
+    v = v / v.norm()
+    t = torch.tensor([0.0, 1.0])
+    y0g = y0.clone().requires_grad_(True)
+    y = pb.odeint_adjoint(net, y0g, t, method="rk4")
+    loss = (y[1].double() ** 2).sum()
+    loss.backward()
+    analytic = float((y0g.grad.double() * v.double()).sum())
+    eps = 1e-2
+    with torch.no_grad():
+        lp = (pb.odeint(net, y0 + eps * v, t, method="rk4")[1].double() ** 2).sum()
+        lm = (pb.odeint(net, y0 - eps * v, t, method="rk4")[1].double() ** 2).sum()
+    fd = float((lp - lm) / (2 * eps))
+    assert abs(fd - analytic) <= 2e-3 * abs(analytic) + 1e-6
+
+
+def test_prior_batch_10000_rows(pb):
+    """The prior-loss call of train_insilico.py:134: 10 000 rows through prior_only_forward and its backward."""
+    G, H, K = 350, 40, 10000
+    w = O.make_weights(G, H, 82, dense=True)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(8)
+    x = torch.rand(K, 1, G, generator=gen) - 0.5
+    prior = torch.randn(K, 1, G, generator=gen) * 0.1
+    J = net.prior_only_forward(None, x.cuda())
+    loss = torch.mean((J - prior.cuda()) ** 2)
+    loss.backward()
+    J_ref = O.rhs(w, x, decay=False)
+    g = 2.0 * (J_ref - prior) / J_ref.numel()
+    _, _, pbar = O.rhs_vjp(w, x, g, decay=False)
+    assert rel_l2(J.detach().cpu(), J_ref) < 1e-5
+    for i, (p, ref) in enumerate(zip(net.parameters(), pbar)):
+        if i == 0:
+            assert p.grad is None or not p.grad.any()      # multipliers do not enter prior_only_forward
+        else:
+            assert rel_l2(p.grad.cpu(), ref) < 2e-5, (i, rel_l2(p.grad.cpu(), ref))
+
+
+def test_solver_assertions_surface_like_the_reference(pb):
+    w = O.make_weights(64, 8, 83, dense=True)
+    net = make_net(pb, w)
+    y0 = torch.rand(1, 64).cuda()
+    t = torch.tensor([0.0, 5.0])
+    with pytest.raises(AssertionError, match="max_num_steps exceeded"):
+        pb.odeint(net, y0, t, method="dopri5", options={"max_num_steps": 2})
+    bad = y0.clone()
+    bad[0, 3] = float("inf")
+    with pytest.raises(AssertionError):
+        pb.odeint(net, bad, t, method="dopri5")
+    # the library is still usable afterwards
+    with torch.no_grad():
+        y = pb.odeint(net, y0, t, method="rk4")
+    assert torch.isfinite(y).all()
+
+
+def test_ragged_and_edge_shapes(pb):
+    """G not a multiple of 4, H not a multiple of 4, a single gene per CTA, many output times."""
+    for G, H, B in ((5, 3, 1), (37, 5, 2), (129, 33, 1), (1001, 100, 1)):
+        w = O.make_weights(G, H, 84 + G, dense=True, neg_mult_frac=0.2)
+        net = make_net(pb, w)
+        y0 = torch.rand(B, G, generator=torch.Generator().manual_seed(G))
+        t = torch.linspace(0, 1, 7)
+        y_ref, _ = O.odeint(w, y0, t, method="rk4")
+        with torch.no_grad():
+            y = pb.odeint(net, y0.cuda(), t, method="rk4")
+        assert rel_l2(y.cpu(), y_ref) < 1e-5, (G, H, B)

@@ -1,0 +1,108 @@
+"""CPU: host-side mirror of the reference interface — argument normalisation, error behaviour, module surface,
+checkpoint format.  No kernels run here."""
+import inspect
+import os
+import pickle
+
+import pytest
+import torch
+
+import phoenix_b200 as pb
+from phoenix_b200 import engine, parallel
+from phoenix_b200.torchdiffeq import _api
+
+
+def small_net():
+    torch.manual_seed(0)
+    return pb.ODENet("cpu", 30, neurons=8)
+
+
+def test_module_surface_matches_reference():
+    net = small_net()
+    names = [n for n, _ in net.named_parameters()]
+    assert names == ["gene_multipliers", "net_prods.linear_out.weight", "net_prods.linear_out.bias",
+                     "net_sums.linear_out.weight", "net_sums.linear_out.bias", "net_alpha_combine.linear_out.weight"]
+    assert net.gene_multipliers.shape == (1, 30)
+    assert net.net_sums.linear_out.weight.shape == (8, 30)
+    assert net.net_alpha_combine.linear_out.weight.shape == (30, 16)
+    assert net.net_alpha_combine.linear_out.bias is None
+    assert net.ndim == 30 and net.explicit_time is False
+    assert "final" in inspect.getsource(pb.ODENet.forward)     # train_insilico.py:228 writes this to network.txt
+    assert isinstance(net.__str__(), str)
+    # init distribution of odenet.py:61-75: 95 % zeros per column, multipliers in [0, 1)
+    W = net.net_sums.linear_out.weight
+    assert (W == 0).float().mean() >= 0.85
+    assert float(net.gene_multipliers.min()) >= 0 and float(net.gene_multipliers.max()) < 1
+    assert [p is q for p, q in zip(engine.net_params(net), net.parameters())] == [True] * 6
+
+
+def test_no_cpu_fallback():
+    net = small_net()
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        net(None, torch.rand(1, 30))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pb.odeint_adjoint(net, torch.rand(1, 30), torch.tensor([0.0, 1.0]), method="rk4")
+
+
+def test_argument_errors_match_reference():
+    net = small_net()
+    y0, t = torch.rand(1, 30), torch.tensor([0.0, 1.0])
+    with pytest.raises(ValueError, match='Invalid method "foo"'):
+        pb.odeint(net, y0, t, method="foo")
+    with pytest.raises(NotImplementedError):
+        pb.odeint(net, y0, t, method="dopri8")
+    with pytest.raises(TypeError, match="floating point"):
+        pb.odeint(net, torch.zeros(1, 30, dtype=torch.long), t)
+    with pytest.raises(AssertionError, match="strictly increasing or decreasing"):
+        pb.odeint(net, y0, torch.tensor([0.0, 1.0, 0.5]))
+    with pytest.raises(AssertionError, match="one dimensional"):
+        pb.odeint(net, y0, torch.zeros(2, 2))
+    with pytest.raises(ValueError, match="func must be an instance of nn.Module"):
+        pb.odeint_adjoint(lambda t, y: y, y0, t)
+    with pytest.raises(TypeError, match="ODENet right-hand sides only"):
+        pb.odeint(torch.nn.Linear(30, 30), y0, t)
+
+
+def test_normalise_time_handling():
+    net = small_net()
+    y0 = torch.rand(1, 30)
+    tl, f32, rev, rtol, atol, method, mx = _api._normalise(net, y0, torch.tensor([3.0, 2.0, 0.5]), 1e-7, 1e-9, None,
+                                                          None)
+    assert tl == [-3.0, -2.0, -0.5] and rev and f32 and method == "dopri5" and mx == 2 ** 31 - 1
+    tl, f32, rev, *_ = _api._normalise(net, y0, torch.tensor([0.0, 0.1], dtype=torch.float64), 1e-7, 1e-9, "rk4",
+                                       {"max_num_steps": 5})
+    assert not f32 and not rev and tl == [0.0, 0.1]
+
+
+def test_flat_grad_layout_matches_reference_parameter_order():
+    G, H = 7, 3
+    P = 4 * G * H + 2 * H + G
+    flat = torch.arange(P, dtype=torch.float32)
+    views = engine.split_flat_grads(flat, G, H)
+    assert [tuple(v.shape) for v in views] == [(1, G), (H, G), (H,), (H, G), (H,), (G, 2 * H)]
+    assert torch.equal(torch.cat([v.reshape(-1) for v in views]), flat)
+
+
+def test_checkpoint_round_trip(tmp_path):
+    net = small_net()
+    fp = os.path.join(str(tmp_path), "model.pt")
+    net.save(fp)
+    for suffix in ("_prods", "_sums", "_alpha_comb", "_gene_multipliers"):
+        assert os.path.exists(os.path.join(str(tmp_path), "model" + suffix + ".pt"))
+    other = pb.ODENet("cpu", 30, neurons=8)
+    other.load(fp)
+    for a, b in zip(net.parameters(), other.parameters()):
+        assert torch.equal(a, b)
+    # the pickles name the activation classes through their module path, like the reference's `odenet.SoftsignMod`
+    blob = pickle.dumps(net.net_sums)
+    assert b"SoftsignMod" in blob
+
+
+def test_shard_range_is_a_partition():
+    for n in (0, 1, 7, 17, 4096):
+        for w in (1, 2, 3, 8):
+            spans = [parallel.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
