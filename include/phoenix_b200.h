@@ -72,6 +72,11 @@ const char* phx_last_error(void);
 /* number of SMs the persistent kernels will use on this device, and the largest B the resident solver accepts */
 int phx_ctx_num_sms(const phx_ctx* ctx);
 int phx_resident_max_rows(int adjoint);
+/* Diagnostics (no reference counterpart): while `slots` (a device array of phx_profile_slots() int64, zeroed by the
+ * caller) is set, CTA 0 of every resident solve adds the SM-clock cycles it spends in each phase of the kernel
+ * (phase ids: PT_* in csrc/phx_resident.cuh).  NULL switches the timer off. */
+int phx_ctx_set_profile(phx_ctx* ctx, void* slots);
+int phx_profile_slots(void);
 
 /* ---- weights --------------------------------------------------------------------------------------------- */
 /* Bytes of the packed (kernel-layout) copy of the six parameters for an ODENet(ndim=G, neurons=H). */

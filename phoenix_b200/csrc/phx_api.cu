@@ -18,6 +18,7 @@ struct phx_ctx {
     int device;
     int num_sms;
     int coop;
+    long long* prof;
 };
 
 namespace {
@@ -81,6 +82,7 @@ int phx_ctx_create(int device, phx_ctx** out) {
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
     c->coop = prop.cooperativeLaunch;
+    c->prof = nullptr;
     if (!c->coop) {
         delete c;
         phx_set_error("device %d does not support cooperative launch", device);
@@ -93,6 +95,13 @@ int phx_ctx_create(int device, phx_ctx** out) {
 void phx_ctx_destroy(phx_ctx* ctx) { delete ctx; }
 
 int phx_ctx_num_sms(const phx_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+
+int phx_ctx_set_profile(phx_ctx* ctx, void* slots) {
+    if (!ctx) return PHX_ERR_INVALID;
+    ctx->prof = (long long*)slots;
+    return PHX_OK;
+}
+int phx_profile_slots(void) { return PHX_PROF_SLOTS; }
 
 int phx_resident_max_rows(int adjoint) { return adjoint ? PHX_MAX_B_ADJ : PHX_MAX_B_FWD; }
 
@@ -189,6 +198,7 @@ static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, 
     p->st = ws + o_st; p->part = ws + o_part; p->redout = ws + o_red; p->partd = (double*)(ws + o_partd);
     p->theta1 = adjoint ? ws + o_th : nullptr;
     p->status = status; p->steplog = steplog; p->steplog_cap = steplog ? steplog_cap : 0;
+    p->prof = ctx->prof;
     cudaError_t e = cudaMemcpyAsync((void*)p->t, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) {
         phx_set_error("cudaMemcpyAsync(t): %s", cudaGetErrorString(e));

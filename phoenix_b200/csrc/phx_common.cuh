@@ -90,7 +90,9 @@ struct ResParams {
     phx_status* status;
     double* steplog;
     int steplog_cap;
+    long long* prof;       // optional [PHX_PROF_SLOTS] phase-timer accumulators (phx_ctx_set_profile), else nullptr
 };
+#define PHX_PROF_SLOTS 32
 
 struct ResLaunchPlan {
     int nCTA, gpc, NV;

@@ -67,6 +67,31 @@ struct Ctrl {
     int slot[7];
 };
 
+// Optional in-kernel phase timer (diagnostics; phx_ctx_set_profile): thread 0 of CTA 0 accumulates SM-clock deltas
+// per phase into p.prof[slot].  With p.prof == nullptr every tick is one predictable branch.
+enum {
+    PT_SETUP = 0, PT_PHASE_A, PT_ALLRED1, PT_FINALIZE, PT_PHASE_B, PT_ALLRED2, PT_GSP, PT_PHASE_C, PT_EPILOGUE,
+    PT_COMBINE, PT_PP_D01, PT_PP_D2, PT_PP_STEP, PT_PP_INTERP, PT_PP_COPY, PT_NORMS, PT_CTRL, PT_TOTAL, PT_COUNT
+};
+struct Prof {
+    long long* buf;
+    long long last, start;
+    __device__ __forceinline__ void init(long long* b) {
+        buf = (blockIdx.x == 0 && threadIdx.x == 0) ? b : nullptr;
+        last = start = buf ? clock64() : 0;
+    }
+    __device__ __forceinline__ void tick(int slot) {
+        if (buf) {
+            long long t = clock64();
+            buf[slot] += t - last;
+            last = t;
+        }
+    }
+    __device__ __forceinline__ void finish() {
+        if (buf) buf[PT_TOTAL] += clock64() - start;
+    }
+};
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -409,22 +434,34 @@ __device__ void finalize_sp(const ResParams& p, const Smem& s) {
 
 // One RHS evaluation at the stage input whose activations are in s.acts / s.actl; leaves joint(y) in s.jb.
 template <int NV, int BT>
-__device__ void eval_fwd(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc) {
+__device__ void eval_fwd(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc, Prof& pf) {
+    pf.tick(PT_COMBINE);
     for (int b0 = 0; b0 < p.B; b0 += BT) phaseA<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    pf.tick(PT_PHASE_A);
     grid_allreduce_f(grid, p, s.sp, p.B * p.K2);
+    pf.tick(PT_ALLRED1);
     finalize_sp(p, s);
+    pf.tick(PT_FINALIZE);
     for (int b0 = 0; b0 < p.B; b0 += BT) phaseB<NV, BT, false>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    pf.tick(PT_PHASE_B);
 }
 
 // RHS + VJP evaluation at the stage input (ysb, asb) with activations / gj already in smem.  Leaves jb, ub, vb and
 // stores this stage's branch factors in slot `slot` of pSP / pG.
 template <int NV, int BT>
-__device__ void eval_adj(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc, int slot) {
+__device__ void eval_adj(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc, int slot,
+                         Prof& pf) {
+    pf.tick(PT_COMBINE);
     for (int b0 = 0; b0 < p.B; b0 += BT) phaseA<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    pf.tick(PT_PHASE_A);
     grid_allreduce_f(grid, p, s.sp, p.B * p.K2);
+    pf.tick(PT_ALLRED1);
     finalize_sp(p, s);
+    pf.tick(PT_FINALIZE);
     for (int b0 = 0; b0 < p.B; b0 += BT) phaseB<NV, BT, true>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    pf.tick(PT_PHASE_B);
     grid_allreduce_f(grid, p, s.gsp, p.B * p.K2);
+    pf.tick(PT_ALLRED2);
     const int n = p.B * p.K2;
     for (int i = threadIdx.x; i < n; i += THREADS) {
         int k = i % p.K2;
@@ -436,7 +473,9 @@ __device__ void eval_adj(cg::grid_group& grid, const ResParams& p, const Smem& s
         s.pG[slot * n + i] = gv;
     }
     __syncthreads();
+    pf.tick(PT_GSP);
     for (int b0 = 0; b0 < p.B; b0 += BT) phaseC<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
+    pf.tick(PT_PHASE_C);
 }
 
 __device__ __forceinline__ float* slot_ptr(const ResParams& p, int slot) {
@@ -547,6 +586,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
     float* Y = slot_ptr(p, 0);
     float* Y1 = slot_ptr(p, 1);
     int dpar = 0;
+    Prof pf;
+    pf.init(p.prof);
 
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
@@ -582,7 +623,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         for (int i = 0; i + 1 < p.T; ++i) {
             const float dtf = p.t_is_f32 ? ((float)p.t[i + 1] - (float)p.t[i]) : (float)(p.t[i + 1] - p.t[i]);
             float* yo = p.yout + (size_t)(i + 1) * BG;
-            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
             if (p.method == PHX_EULER) {
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float y = s.ysb[li];
@@ -600,7 +641,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
                     set_stage_input(li, y + f * half);
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float f = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
                     float y1 = Y[gi] + dtf * f;
@@ -616,21 +657,21 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
                     set_stage_input(li, y + dtf * k1 * third);
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float k2 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
                     K(1)[gi] = k2;
                     set_stage_input(li, Y[gi] + dtf * (k2 - K(0)[gi] * third));
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float k3 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
                     K(2)[gi] = k3;
                     set_stage_input(li, Y[gi] + dtf * (K(0)[gi] - K(1)[gi] + k3));
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float k4 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
                     float dy = (K(0)[gi] + 3.f * (K(1)[gi] + K(2)[gi]) + k4) * dtf * 0.125f;
@@ -648,13 +689,15 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
             c->tcur = p.t[p.T - 1];
         }
         __syncthreads();
+        pf.tick(PT_CTRL);
+        pf.finish();
         write_status(p, c, PHX_ST_OK);
         return;
     }
 
     // ---- dopri5 (rk_common.py:111-228) ----
     // f0 and the initial step (misc.py:47-86)
-    eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+    eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
     {
         double acc[3] = {0, 0, 0};
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
@@ -669,6 +712,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         });
         block_sum_d<3>(acc, s.dred, c->dsum);
         grid_allreduce_d(grid, p, c->dsum, 3, dpar);
+        pf.tick(PT_NORMS);
         if (threadIdx.x == 0) {
             float d0 = sqrtf((float)(c->dsum[0] / Nel));
             float d1 = sqrtf((float)(c->dsum[1] / Nel));
@@ -682,7 +726,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
             set_stage_input(li, Y[gi] + h0 * K(0)[gi]);
         });
         __syncthreads();
-        eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+        eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
         double acc2[1] = {0};
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
             float f1 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
@@ -692,6 +736,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         });
         block_sum_d<1>(acc2, s.dred, c->dsum);
         grid_allreduce_d(grid, p, c->dsum, 1, dpar);
+        pf.tick(PT_NORMS);
         if (threadIdx.x == 0) {
             float d2 = sqrtf((float)(c->dsum[0] / Nel)) / c->h0;
             c->dt = init_dt(c->h0, c->d1, d2);
@@ -732,7 +777,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         }
         double acc[2] = {0, 0};
         for (int st = 1; st <= 6; ++st) {
-            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc);
+            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
             for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                 float ys = s.ysb[li];
                 float f = p.fsign * (p.w.relum[g] * (s.jb[li] - ys));
@@ -758,6 +803,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         }
         block_sum_d<2>(acc, s.dred, c->dsum);
         grid_allreduce_d(grid, p, c->dsum, 2, dpar);
+        pf.tick(PT_NORMS);
         if (threadIdx.x == 0) {
             float ratio = sqrtf((float)(c->dsum[0] / Nel));
             int accept = ratio <= 1.f;
@@ -805,6 +851,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         }
     }
     __syncthreads();
+    pf.tick(PT_CTRL);
+    pf.finish();
     write_status(p, c, code);
 }
 
@@ -990,6 +1038,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
     auto KY = [&](int i) { return slot_ptr(p, 4 + i); };
     auto KA = [&](int i) { return slot_ptr(p, 11 + i); };
     int dpar = 0;
+    Prof pf;
+    pf.init(p.prof);
     int cur = 0;  // which theta buffer holds the current value
     float* theta[2] = {p.theta0, p.theta1};
 
@@ -1014,6 +1064,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
     // after eval_adj: stage derivatives of the y and a blocks (reverse time: ky = -f, ka = VJP_y with cotangent a)
     // and this stage's per-gene factors into slot `slot`
     auto stage_epilogue = [&](int slot) {
+        pf.tick(PT_PHASE_C);
         float* ky = KY(slot);
         float* ka = KA(slot);
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
@@ -1039,6 +1090,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
             s.pM[slot * p.gpc + j] = t * p.w.maskm[g_lo + j];
         }
         __syncthreads();
+        pf.tick(PT_EPILOGUE);
     };
 
     int code = PHX_ST_OK;
@@ -1065,54 +1117,60 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
             pa.dtf = dtf;
             pa.s0 = 0; pa.s1 = 1; pa.s2 = 2; pa.s3 = 3;
             double d0 = 0, d1 = 0;
-            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0);
+            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0, pf);
             stage_epilogue(0);
             if (p.method == PHX_EULER) {
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     A[gi] = A[gi] + dtf * KA(0)[gi];
                 });
                 pa.mask = 1u;
+                pf.tick(PT_COMBINE);
                 ppass<PP_EULER>(p, s, g_lo, n_loc, pa, d0, d1);
+                pf.tick(PT_PP_STEP);
             } else if (p.method == PHX_MIDPOINT) {
                 const float half = 0.5f * dtf;
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     set_stage_input(li, g, Y[gi] + KY(0)[gi] * half, A[gi] + KA(0)[gi] * half);
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1);
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1, pf);
                 stage_epilogue(1);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     A[gi] = A[gi] + dtf * KA(1)[gi];
                 });
                 pa.mask = 2u;
+                pf.tick(PT_COMBINE);
                 ppass<PP_MIDPOINT>(p, s, g_lo, n_loc, pa, d0, d1);
+                pf.tick(PT_PP_STEP);
             } else {
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     set_stage_input(li, g, Y[gi] + dtf * KY(0)[gi] * third, A[gi] + dtf * KA(0)[gi] * third);
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1);
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1, pf);
                 stage_epilogue(1);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     set_stage_input(li, g, Y[gi] + dtf * (KY(1)[gi] - KY(0)[gi] * third),
                                     A[gi] + dtf * (KA(1)[gi] - KA(0)[gi] * third));
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 2);
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 2, pf);
                 stage_epilogue(2);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     set_stage_input(li, g, Y[gi] + dtf * (KY(0)[gi] - KY(1)[gi] + KY(2)[gi]),
                                     A[gi] + dtf * (KA(0)[gi] - KA(1)[gi] + KA(2)[gi]));
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 3);
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 3, pf);
                 stage_epilogue(3);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float dy = (KA(0)[gi] + 3.f * (KA(1)[gi] + KA(2)[gi]) + KA(3)[gi]) * dtf * 0.125f;
                     A[gi] = A[gi] + dy;
                 });
                 pa.mask = 15u;
+                pf.tick(PT_COMBINE);
                 ppass<PP_RK4>(p, s, g_lo, n_loc, pa, d0, d1);
+                pf.tick(PT_PP_STEP);
             }
             if (threadIdx.x == 0) {
                 int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
@@ -1131,7 +1189,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
             }
             __syncthreads();
             // f0 and Hairer's initial step under the mixed norm max(RMS_y, RMS_a, RMS_theta)
-            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0);
+            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0, pf);
             stage_epilogue(0);
             {
                 double acc[7] = {0, 0, 0, 0, 0, 0, 0};
@@ -1150,9 +1208,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 pa.dst = nullptr;
                 pa.mask = 1u;
                 pa.s0 = 0;
+                pf.tick(PT_COMBINE);
                 ppass<PP_D01>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
+                pf.tick(PT_PP_D01);
                 block_sum_d<7>(acc, s.dred, c->dsum);
                 grid_allreduce_d(grid, p, c->dsum, 7, dpar);
+                pf.tick(PT_NORMS);
                 if (threadIdx.x == 0) {
                     float d0 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
                                      sqrtf((float)(c->dsum[2] / Pel)));
@@ -1168,7 +1229,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                     set_stage_input(li, g, Y[gi] + h0 * KY(0)[gi], A[gi] + h0 * KA(0)[gi]);
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1);
+                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1, pf);
                 stage_epilogue(1);
                 double acc2[3] = {0, 0, 0};
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
@@ -1181,9 +1242,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 pa.s0 = 0;
                 pa.s1 = 1;
                 double dummy = 0;
+                pf.tick(PT_COMBINE);
                 ppass<PP_D2>(p, s, g_lo, n_loc, pa, acc2[2], dummy);
+                pf.tick(PT_PP_D2);
                 block_sum_d<3>(acc2, s.dred, c->dsum);
                 grid_allreduce_d(grid, p, c->dsum, 3, dpar);
+                pf.tick(PT_NORMS);
                 if (threadIdx.x == 0) {
                     float d2 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
                                      sqrtf((float)(c->dsum[2] / Pel))) / c->h0;
@@ -1219,7 +1283,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 }
                 double acc[4] = {0, 0, 0, 0};
                 for (int st = 1; st <= 6; ++st) {
-                    eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, sl[st]);
+                    eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, sl[st], pf);
                     stage_epilogue(sl[st]);
                     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                         if (st < 6) {
@@ -1265,9 +1329,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 }
                 pa.slot_first = sl[0];
                 pa.slot_last = sl[6];
+                pf.tick(PT_COMBINE);
                 ppass<PP_STEP>(p, s, g_lo, n_loc, pa, acc[2], acc[3]);
+                pf.tick(PT_PP_STEP);
                 block_sum_d<4>(acc, s.dred, c->dsum);
                 grid_allreduce_d(grid, p, c->dsum, 4, dpar);
+                pf.tick(PT_NORMS);
                 if (threadIdx.x == 0) {
                     float ratio = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
                                         sqrtf((float)(c->dsum[2] / Pel)));
@@ -1303,7 +1370,9 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                         });
                         for (int q = 0; q < 4; ++q) pa.xs[q] = c->xs[q];
                         double d0 = 0, d1 = 0;
+                        pf.tick(PT_COMBINE);
                         ppass<PP_INTERP>(p, s, g_lo, n_loc, pa, d0, d1);
+                        pf.tick(PT_PP_INTERP);
                         cur ^= 1;
                         done = true;
                     } else {
@@ -1338,9 +1407,13 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
         double d0 = 0, d1 = 0;
         const float zero[7] = {0, 0, 0, 0, 0, 0, 0};
         (void)zero;
+        pf.tick(PT_COMBINE);
         ppass<PP_COPY>(p, s, g_lo, n_loc, pa, d0, d1);
+        pf.tick(PT_PP_COPY);
     }
     __syncthreads();
+    pf.tick(PT_CTRL);
+    pf.finish();
     write_status(p, c, code);
 }
 

@@ -67,15 +67,17 @@ def main():
             target = torch.from_numpy(d["target"]).cuda()
             t0 = time.time()
             if m["adjoint"]:
-                y = pb.odeint_adjoint(net, y0, t, method=m["method"])
+                y = pb.odeint_adjoint(net, y0, t, rtol=float(d["rtol"]), atol=float(d["atol"]), method=m["method"])
             else:
                 with torch.no_grad():
-                    y = pb.odeint(net, y0, t, method=m["method"])
+                    y = pb.odeint(net, y0, t, rtol=float(d["rtol"]), atol=float(d["atol"]), method=m["method"])
             flog = pb.last_step_log()
             st = pb.last_status()
             msg = ["SOLVE", m["name"], "y %.1e" % rel_l2(y.detach().cpu(), d["y"]), "st", st]
             if m["method"] == "dopri5":
-                msg += ["flog:", compare_logs(flog, d["flog"])[1], "stable=%d" % int(d["stable"])]
+                msg += ["flog:", compare_logs(flog, d["flog"])[1], "stable=%d" % int(d["stable"]),
+                        "dts mine", " ".join("%.4g" % r[1] for r in flog[:6]), "ref",
+                        " ".join("%.4g" % r[1] for r in d["flog"][:6])]
             say(*msg)
             if m["adjoint"]:
                 loss = torch.mean((y[1:] - target) ** 2)
