@@ -165,6 +165,8 @@ def run_ours(args):
     tarr = [(ctypes.c_double * 2)(*x) for x in tl]
     ws_f = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 0), dtype=torch.uint8, device=dev)
     ws_a = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 1), dtype=torch.uint8, device=dev)
+    for ws in (ws_f, ws_a):   # one-time zeroing of the inter-CTA exchange area (include/phoenix_b200.h)
+        _lib.check(lib.phx_solve_workspace_init(ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp), "workspace_init")
     yout = torch.empty(BATCH, 2, 1, G, device=dev)
     grad_y = torch.zeros(BATCH, 2, 1, G, device=dev)
     adj_y0 = torch.empty(BATCH, 1, G, device=dev)

@@ -100,6 +100,12 @@ size_t phx_rhs_workspace_bytes(int G, int H, int B);
 
 /* ---- odeint (torchdiffeq/_impl/odeint.py:25-69) ---------------------------------------------------------- */
 size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint);
+/* The first phx_solve_workspace_init_bytes() bytes of a resident-solver workspace hold the inter-CTA exchange area
+ * (tagged slots carrying a per-workspace epoch from launch to launch).  Call phx_solve_workspace_init ONCE after
+ * allocating a workspace (it zeroes that area on `stream`); afterwards the same workspace serves any sequence of
+ * phx_solve_forward / phx_solve_adjoint calls of any shape, as long as calls sharing it are ordered on one stream. */
+size_t phx_solve_workspace_init_bytes(void);
+int phx_solve_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
 /* y_out[T][B][G] = solution at the T increasing times t_host (float64; t_is_f32 != 0 says the caller's tensor was
  * float32, which changes how fixed-grid dt is rounded, solvers.py:84-86).  reversed != 0: the caller's t was
  * decreasing and has been negated, so the kernel integrates -f (misc.py:159-162,210-212).  Reference defaults: rtol 1e-7,

@@ -18,7 +18,8 @@ EXPORTS = [
     "phx_ctx_create", "phx_ctx_destroy", "phx_last_error", "phx_ctx_num_sms", "phx_resident_max_rows",
     "phx_ctx_set_profile", "phx_profile_slots",
     "phx_packed_bytes", "phx_pack_weights", "phx_rhs_forward", "phx_rhs_vjp", "phx_rhs_workspace_bytes",
-    "phx_solve_workspace_bytes", "phx_solve_forward", "phx_solve_adjoint",
+    "phx_solve_workspace_bytes", "phx_solve_workspace_init_bytes", "phx_solve_workspace_init", "phx_solve_forward",
+    "phx_solve_adjoint",
     "phx_stream_workspace_bytes", "phx_stream_solve_forward", "phx_stream_solve_adjoint",
 ]
 
@@ -69,6 +70,10 @@ def _declare(lib):
     lib.phx_rhs_vjp.restype = c_int
     lib.phx_solve_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int]
     lib.phx_solve_workspace_bytes.restype = c_size_t
+    lib.phx_solve_workspace_init_bytes.argtypes = []
+    lib.phx_solve_workspace_init_bytes.restype = c_size_t
+    lib.phx_solve_workspace_init.argtypes = [c_void_p, c_size_t, c_void_p]
+    lib.phx_solve_workspace_init.restype = c_int
     fwd = [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, ctypes.POINTER(c_double), c_int, c_int, c_int,
            c_int, c_double, c_double, c_int64, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]
     adj = [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_double), c_int, c_int, c_int, c_double,

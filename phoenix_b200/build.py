@@ -26,7 +26,7 @@ NVCC_FLAGS = [
 
 # (object name, source, extra defines)
 UNITS = [("phx_api", "phx_api.cu", []), ("phx_plan", "phx_plan.cu", []), ("phx_rhs", "phx_rhs.cu", []),
-         ("phx_stream", "phx_stream.cu", [])]
+         ("phx_stream", "phx_stream.cu", []), ("phx_microbench", "phx_microbench.cu", [])]
 for kind in (0, 1):
     for nv in (1, 2, 4):
         UNITS.append(("phx_res_%s_nv%d" % ("adj" if kind else "fwd", nv), "phx_resident_inst.cu",

@@ -1,5 +1,6 @@
 // extern "C" entry points of libphoenix_b200.so (declared in include/phoenix_b200.h).
 #include <stdarg.h>
+#include <stdint.h>
 #include <stdio.h>
 #include <string.h>
 #include <vector>
@@ -152,8 +153,23 @@ size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T,
     if (!ctx) return 0;
     ResLaunchPlan plan;
     if (phx_resident_plan(ctx->num_sms, G, H, B, adjoint, &plan) != PHX_OK) return 0;
-    return phx_resident_workspace_floats(plan.nCTA, G, H, B, T, adjoint, nullptr, nullptr, nullptr, nullptr, nullptr,
-                                         nullptr) * sizeof(float);
+    return phx_resident_workspace_floats(G, H, B, T, adjoint, nullptr, nullptr) * sizeof(float);
+}
+
+size_t phx_solve_workspace_init_bytes(void) { return phx_ll_words() * sizeof(unsigned long long); }
+
+int phx_solve_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+    const size_t need = phx_solve_workspace_init_bytes();
+    if (!workspace || workspace_bytes < need) {
+        phx_set_error("workspace_init: workspace smaller than the %zu-byte exchange area", need);
+        return PHX_ERR_WORKSPACE;
+    }
+    cudaError_t e = cudaMemsetAsync(workspace, 0, need, (cudaStream_t)stream);
+    if (e != cudaSuccess) {
+        phx_set_error("cudaMemsetAsync(workspace): %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
 }
 
 static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
@@ -178,11 +194,14 @@ static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, 
         phx_set_error("unknown method id %d", method);
         return PHX_ERR_INVALID;
     }
+    if (((uintptr_t)workspace & 15) || ((uintptr_t)packed & 15)) {
+        phx_set_error("workspace and packed weights must be 16-byte aligned");
+        return PHX_ERR_INVALID;
+    }
     int rc = phx_resident_plan(ctx->num_sms, G, H, B, adjoint, plan);
     if (rc != PHX_OK) return rc;
-    size_t o_st, o_part, o_red, o_partd, o_t, o_th;
-    size_t need = phx_resident_workspace_floats(plan->nCTA, G, H, B, T, adjoint, &o_st, &o_part, &o_red, &o_partd,
-                                                &o_t, &o_th) * sizeof(float);
+    size_t o_t, o_th;
+    size_t need = phx_resident_workspace_floats(G, H, B, T, adjoint, &o_t, &o_th) * sizeof(float);
     if (workspace_bytes < need) {
         phx_set_error("solve workspace too small: %zu < %zu", workspace_bytes, need);
         return PHX_ERR_WORKSPACE;
@@ -191,14 +210,20 @@ static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, 
     memset(p, 0, sizeof(*p));
     p->G = G; p->H = H; p->Hp = phx_Hp(H); p->K2 = 2 * p->Hp; p->K2q = p->K2 / 4; p->B = B; p->T = T;
     p->method = method; p->gpc = plan->gpc; p->t_is_f32 = t_is_f32; p->adjoint = adjoint;
+    p->ring_rows = plan->ring_rows; p->ring_stages = plan->ring_stages;
+    p->so = plan->so;
     p->rtol_f = (float)rtol; p->atol_f = (float)atol; p->fsign = 1.f;
     p->max_steps = (long long)max_num_steps;
     p->w = phx_packed_view(packed, G, H);
+    p->ll = phx_ll_view(workspace);
     p->t = (const double*)(ws + o_t);
-    p->st = ws + o_st; p->part = ws + o_part; p->redout = ws + o_red; p->partd = (double*)(ws + o_partd);
     p->theta1 = adjoint ? ws + o_th : nullptr;
     p->status = status; p->steplog = steplog; p->steplog_cap = steplog ? steplog_cap : 0;
     p->prof = ctx->prof;
+    if (T <= PHX_T_INLINE) {
+        for (int i = 0; i < T; ++i) p->t_small[i] = t_host[i];  // travels with the kernel parameters
+        return PHX_OK;
+    }
     cudaError_t e = cudaMemcpyAsync((void*)p->t, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, stream);
     if (e != cudaSuccess) {
         phx_set_error("cudaMemcpyAsync(t): %s", cudaGetErrorString(e));
@@ -244,12 +269,7 @@ int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, co
     p.ysaved = y_saved;
     p.grad_y = grad_y;
     p.adj_y0 = adj_y0;
-    p.theta0 = grads_flat;
-    cudaError_t e = cudaMemsetAsync(grads_flat, 0, phx_grad_offsets(G, H).total * sizeof(float), (cudaStream_t)stream);
-    if (e != cudaSuccess) {
-        phx_set_error("cudaMemsetAsync(grads): %s", cudaGetErrorString(e));
-        return PHX_ERR_CUDA;
-    }
+    p.theta0 = grads_flat;  // written once by the kernel (never read while still zero): no memset needed
     return phx_resident_launch(p, plan, (cudaStream_t)stream);
 }
 

@@ -65,14 +65,103 @@ static inline __host__ __device__ PhxGradOff phx_grad_offsets(int G, int H) {
     return o;
 }
 
+// ---- inter-CTA exchange area ("LL" = low-latency tagged slots), at the START of every resident-solver workspace -----
+// Each slot is one naturally aligned 64-bit word {fp32 payload, 32-bit epoch tag} written with a single relaxed
+// gpu-scope store and polled with relaxed gpu-scope loads until the tag matches: the payload arrives with its flag, so
+// an exchange costs one L2 round trip and needs no fences or atomics.  Tags are a per-workspace monotonically
+// increasing epoch (word 0 of the area carries it from launch to launch), so the area has to be zero exactly once,
+// when the workspace is allocated (phx_solve_workspace_init).
+#define PHX_LL_MAXC 160                      /* CTAs (>= SM count of any sm_100 part)                    */
+#define PHX_LL_NMAX 4096                     /* longest all-reduced vector: max rows (8) x max K2 (512)  */
+#define PHX_LL_YMAX 16384                    /* one-phase exchange: nCTA * n <= YMAX                     */
+#define PHX_LL_DMAX 16                       /* scalar (norm) exchange: floats per CTA                   */
+struct PhxLL {
+    unsigned long long* epoch;   // [1] (+7 pad)
+    unsigned long long* xpart;   // [MAXC][NMAX]   two-phase all-reduce: per-CTA partials
+    unsigned long long* xres;    // [NMAX]         two-phase all-reduce: reduced vector
+    unsigned long long* ypart;   // [2][YMAX]      one-phase all-reduce (small grids), double-buffered
+    unsigned long long* dpart;   // [2][MAXC][DMAX] scalar sums (error norms), double-buffered
+};
+static inline __host__ __device__ size_t phx_ll_words() {
+    return 8 + (size_t)PHX_LL_MAXC * PHX_LL_NMAX + PHX_LL_NMAX + 2 * (size_t)PHX_LL_YMAX +
+           2 * (size_t)PHX_LL_MAXC * PHX_LL_DMAX;
+}
+static inline __host__ __device__ PhxLL phx_ll_view(void* base) {
+    PhxLL v;
+    unsigned long long* p = reinterpret_cast<unsigned long long*>(base);
+    v.epoch = p; p += 8;
+    v.xpart = p; p += (size_t)PHX_LL_MAXC * PHX_LL_NMAX;
+    v.xres = p; p += PHX_LL_NMAX;
+    v.ypart = p; p += 2 * (size_t)PHX_LL_YMAX;
+    v.dpart = p;
+    return v;
+}
+
+// Byte offsets of the resident kernels' shared-memory views (0xffffffff: not present), computed by phx_smem_layout.
+struct SmemOff {
+    unsigned ring, bar, ctrl, dred, gram, dstage, ystage, bias, relum, maskm, sp, gsp, red, st;
+    unsigned acts, actl, ysb, jb, acts2, actl2, ysb2, asb, gjb, ub, vb, mt;
+    unsigned FG, FSP, FS, FL, FGJ, FM;
+};
+#define PHX_CTRL_BYTES 1024  /* >= sizeof(Ctrl) in phx_resident.cuh (static_assert there) */
+
+static inline int phx_QB(int B) { return (7 * (B > 1 ? 4 : 1) + 3) & ~3; }
+static inline bool phx_use_y(int nCTA, int B, int K2) { return (size_t)nCTA * B * K2 <= 4096; }
+
+static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoint, int ring_rows, int ring_stages,
+                                     SmemOff* o) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += (bytes + 15) & ~size_t(15);
+        return (unsigned)at;
+    };
+    SmemOff t;
+    const unsigned none = 0xffffffffu;
+    const int QB = phx_QB(B);
+    const size_t bl = sizeof(float) * B * gpc;
+    t.ring = take(sizeof(float) * (size_t)ring_stages * ring_rows * K2);  // first: 128-byte aligned bulk-copy target
+    t.bar = take(sizeof(unsigned long long) * ring_stages);
+    t.ctrl = take(PHX_CTRL_BYTES);
+    t.dred = take(sizeof(double) * PHX_WARPS * 8);
+    t.gram = adjoint ? take(sizeof(double) * 128) : none;
+    t.dstage = take(sizeof(float) * nCTA * PHX_LL_DMAX);
+    t.ystage = phx_use_y(nCTA, B, K2) ? take(sizeof(float) * (size_t)nCTA * B * K2) : none;
+    t.bias = take(sizeof(float) * K2);
+    t.relum = take(sizeof(float) * gpc);
+    t.maskm = take(sizeof(float) * gpc);
+    t.sp = take(sizeof(float) * B * K2);
+    t.gsp = adjoint ? take(sizeof(float) * B * K2) : none;
+    t.red = take(sizeof(float) * PHX_WARPS * K2);
+    t.st = take((adjoint ? 18 : 9) * bl);
+    t.acts = take(bl); t.actl = take(bl); t.ysb = take(bl); t.jb = take(bl);
+    t.acts2 = t.actl2 = t.ysb2 = t.asb = t.gjb = t.ub = t.vb = t.mt = none;
+    t.FG = t.FSP = t.FS = t.FL = t.FGJ = t.FM = none;
+    if (adjoint) {
+        t.acts2 = take(bl); t.actl2 = take(bl); t.ysb2 = take(bl); t.asb = take(bl); t.gjb = take(bl);
+        t.ub = take(bl); t.vb = take(bl); t.mt = take(bl);
+        t.FG = take(sizeof(float) * K2 * QB);
+        t.FSP = take(sizeof(float) * K2 * QB);
+        t.FS = take(sizeof(float) * gpc * QB);
+        t.FL = take(sizeof(float) * gpc * QB);
+        t.FGJ = take(sizeof(float) * gpc * QB);
+        t.FM = take(sizeof(float) * gpc * 8);
+    }
+    if (o) *o = t;
+    return off;
+}
+
 // Parameters of the persistent ("resident") solver kernels.
 struct ResParams {
     int G, H, Hp, K2, K2q, B, T, method, gpc, t_is_f32, adjoint;
+    int ring_rows, ring_stages;   // weight-streaming ring: rows per chunk, chunks in flight
+    SmemOff so;
     float rtol_f, atol_f;
     float fsign;           // +1, or -1 when the caller's t was decreasing (f -> -f(-t, y), misc.py:159-162)
     long long max_steps;
     PhxPacked w;
-    const double* t;       // [T] device copy of the output times
+    const double* t;       // [T] device copy of the output times (only used when T > PHX_T_INLINE)
+    double t_small[16];    // the output times themselves when T <= PHX_T_INLINE (no host->device copy per call)
     // forward
     const float* y0;       // [B][G]
     float* yout;           // [T][B][G]
@@ -83,27 +172,24 @@ struct ResParams {
     float* theta0;         // [P] caller's flat grads (result lands here)
     float* theta1;         // [P] scratch twin
     // workspace
-    float* st;             // state slots [nslots][B][G]
-    float* part;           // [nCTA][B*K2] all-reduce partials
-    float* redout;         // [B*K2]
-    double* partd;         // [2][nCTA][8]
+    PhxLL ll;
     phx_status* status;
     double* steplog;
     int steplog_cap;
     long long* prof;       // optional [PHX_PROF_SLOTS] phase-timer accumulators (phx_ctx_set_profile), else nullptr
 };
 #define PHX_PROF_SLOTS 32
+#define PHX_T_INLINE 16
 
 struct ResLaunchPlan {
-    int nCTA, gpc, NV;
+    int nCTA, gpc, NV, ring_rows, ring_stages;
     size_t smem_bytes;
+    SmemOff so;
 };
 
 // host helpers implemented in phx_resident.cu
 int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPlan* plan);
-size_t phx_resident_workspace_floats(int nCTA, int G, int H, int B, int T, int adjoint, size_t* off_st,
-                                     size_t* off_part, size_t* off_redout, size_t* off_partd, size_t* off_t,
-                                     size_t* off_theta1);
+size_t phx_resident_workspace_floats(int G, int H, int B, int T, int adjoint, size_t* off_t, size_t* off_theta1);
 int phx_resident_launch(const ResParams& p, const ResLaunchPlan& plan, cudaStream_t stream);
 
 // host helpers implemented in phx_rhs.cu

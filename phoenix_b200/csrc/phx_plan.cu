@@ -1,5 +1,5 @@
 // Host-side planning of the resident solver launches (grid size, shared-memory and workspace layout).
-#include "phx_resident.cuh"
+#include "phx_common.cuh"
 
 int phx_launch_fwd_nv1(const ResParams&, const ResLaunchPlan&, cudaStream_t);
 int phx_launch_fwd_nv2(const ResParams&, const ResLaunchPlan&, cudaStream_t);
@@ -23,43 +23,52 @@ int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPl
                       adjoint ? PHX_MAX_B_ADJ : PHX_MAX_B_FWD, B);
         return PHX_ERR_UNSUPPORTED;
     }
-    // one CTA per SM; at least 16 genes (one per warp) per CTA so small problems use few CTAs (cheaper all-reduce)
+    if (num_sms > PHX_LL_MAXC) num_sms = PHX_LL_MAXC;
+    // one CTA per SM; at least 16 genes (one per warp) per CTA so small problems use few CTAs (cheaper exchanges)
     int gpc = (G + num_sms - 1) / num_sms;
     if (gpc < 16) gpc = 16;
     int nCTA = (G + gpc - 1) / gpc;
     plan->nCTA = nCTA;
     plan->gpc = gpc;
     plan->NV = NV;
-    plan->smem_bytes = smem_layout(B, K2, gpc, adjoint, nullptr, nullptr);
-    if (plan->smem_bytes > PHX_SMEM_LIMIT) {
-        phx_set_error("resident solver needs %zu B shared memory (> %d) for G=%d H=%d B=%d", plan->smem_bytes,
-                      PHX_SMEM_LIMIT, G, H, B);
+    // weight-streaming ring: chunks of whole rows (a multiple of the 16 warps), as many stages as shared memory
+    // allows up to 4 (or the whole slice); prefer >= 16 KB per chunk so few bulk copies are in flight per pass
+    const size_t row_bytes = (size_t)K2 * sizeof(float);
+    const int rows_cap = (gpc + PHX_WARPS - 1) / PHX_WARPS * PHX_WARPS;
+    int best_rows = 0, best_stages = 0;
+    for (int rows = PHX_WARPS * 4; rows >= PHX_WARPS && !best_rows; rows /= 2) {
+        int r = rows < rows_cap ? rows : rows_cap;
+        if (r * row_bytes > 32 * 1024 && r > PHX_WARPS) continue;
+        const int nch = (gpc + r - 1) / r;
+        for (int stages = (nch < 4 ? nch : 4); stages >= 1; --stages) {
+            if (stages == 1 && nch > 1) continue;  // needs double buffering to stream
+            if (phx_smem_layout(nCTA, B, K2, gpc, adjoint, r, stages, nullptr) <= PHX_SMEM_LIMIT) {
+                best_rows = r;
+                best_stages = stages;
+                break;
+            }
+        }
+    }
+    if (!best_rows) {
+        phx_set_error("resident solver does not fit in %d B shared memory for G=%d H=%d B=%d", PHX_SMEM_LIMIT, G, H, B);
         return PHX_ERR_UNSUPPORTED;
     }
+    plan->ring_rows = best_rows;
+    plan->ring_stages = best_stages;
+    plan->smem_bytes = phx_smem_layout(nCTA, B, K2, gpc, adjoint, best_rows, best_stages, &plan->so);
     return PHX_OK;
 }
 
-size_t phx_resident_workspace_floats(int nCTA, int G, int H, int B, int T, int adjoint, size_t* off_st,
-                                     size_t* off_part, size_t* off_redout, size_t* off_partd, size_t* off_t,
-                                     size_t* off_theta1) {
-    const size_t K2 = (size_t)phx_K2(H);
-    size_t off = 0;
+// workspace: [ LL exchange area (zeroed once by phx_solve_workspace_init) | t[T] doubles | theta twin (adjoint) ]
+size_t phx_resident_workspace_floats(int G, int H, int B, int T, int adjoint, size_t* off_t, size_t* off_theta1) {
+    size_t off = phx_ll_words() * 2;
     auto take = [&](size_t nfloats) {
         size_t o = off;
         off += (nfloats + 3) & ~size_t(3);
         return o;
     };
-    size_t nslots = adjoint ? 18 : 9;
     size_t o_t = take(2 * (size_t)T);  // doubles
-    size_t o_partd = take(2 * 2 * (size_t)nCTA * 8);
-    size_t o_st = take(nslots * (size_t)B * G);
-    size_t o_part = take((size_t)nCTA * B * K2);
-    size_t o_red = take((size_t)B * K2);
     size_t o_th = adjoint ? take(phx_grad_offsets(G, H).total) : 0;
-    if (off_st) *off_st = o_st;
-    if (off_part) *off_part = o_part;
-    if (off_redout) *off_redout = o_red;
-    if (off_partd) *off_partd = o_partd;
     if (off_t) *off_t = o_t;
     if (off_theta1) *off_theta1 = o_th;
     return off;

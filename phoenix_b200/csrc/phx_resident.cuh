@@ -3,28 +3,29 @@
 //
 // Decomposition (B200-first):
 //   * the G genes are split into contiguous slices, one CTA (one SM) per slice; the CTA owns every per-gene
-//     quantity of its slice: solver state, RK stage derivatives, Hill activations, and the rows W1[g][:], WA[g][:]
-//     of the packed weights (contiguous, streamed with 128-bit loads; L2-resident after the first stage because
-//     16GH bytes <= 64 MB << 126 MB L2);
-//   * an RHS evaluation is: phase A (branch pre-activations, reduce over the slice's genes) -> ONE grid-wide
-//     all-reduce of the K2-long branch vector -> phase B (combination row-dots, decay) -> the RK stage combine for
-//     the slice, all inside the same kernel, so the state never makes an HBM round trip between stages;
-//   * the adjoint adds a second all-reduce (gS|gLP) and phase C (state cotangent), and keeps the parameter
-//     cotangents FACTORISED per stage (rank-B outer-product factors in shared memory); they are folded into the
-//     P-long accumulator once per step together with their error-norm contribution (the reference instead carries
-//     seven P-long stage tensors through every stage, adjoint.py:86-151 + rk_common.py:62-76);
-//   * reductions are fixed-order (warp butterflies, ordered cross-warp / cross-CTA sums): results are run-to-run
-//     deterministic, which the dopri5 accept/reject sequence needs.
+//     quantity of its slice -- solver state, RK stage derivatives, Hill activations, all held in SHARED MEMORY for the
+//     whole solve -- and the rows W1[g][:], WA[g][:] of the packed weights, which are one contiguous block per CTA
+//     and are streamed through a ring of shared-memory stages by 1-D TMA bulk copies (cp.async.bulk + mbarrier),
+//     prefetched across the inter-CTA exchanges; after the first pass they come from L2 (16GH bytes << 126 MB);
+//   * an RHS evaluation is: pass A over W1 (branch pre-activations, reduced over the slice's genes) -> ONE
+//     grid-wide all-reduce of the K2-long branch vector -> pass B over WA (combination row-dots, decay) -> the RK
+//     stage combine for the slice, all inside the same kernel: the state never makes an HBM round trip;
+//   * the adjoint adds a second all-reduce (gS|gLP) and pass C over W1 (state cotangent), which is MERGED with
+//     pass A of the next stage (same rows), so a VJP evaluation streams each weight matrix once; the parameter
+//     cotangents stay FACTORISED per stage (rank-B outer-product factors in shared memory) and are folded into the
+//     P-long accumulator once per step together with their error-norm contribution; while the accumulator is known
+//     to be zero it is never read, and the last step of an interval writes the dense-output value directly (the
+//     reference carries seven P-long stage tensors through every stage, adjoint.py:86-151 + rk_common.py:62-76);
+//   * inter-CTA exchanges use tagged 64-bit slots ({fp32, epoch}, one relaxed store / polled relaxed loads, no
+//     fences, no atomics; PhxLL in phx_common.cuh) and are summed in a fixed order: results are run-to-run
+//     deterministic and identical in every CTA, which the device-side dopri5 controller relies on.
 //
 // Arithmetic mirrors the reference op by op where it is elementwise (compiled with -fmad=false, explicit fmaf only
 // inside dot products), fp32 state, float64 time-like scalars (rk_common.py:115-131).
-#include <cooperative_groups.h>
 #include <math.h>
 #include <stdio.h>
 #pragma once
 #include "phx_common.cuh"
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -62,7 +63,7 @@ struct Ctrl {
     float cmid[7];
     float xs[4];  // x, x^2, x^3, x^4 for the dense output (interp.py:40-47)
     float dtf, h0, d1;
-    int accept, stop, nonfinite_prev;
+    int accept, stop, nonfinite_prev, last;
     int n_acc, n_rej, n_rhs, n_log, n_steps_interval;
     int slot[7];
 };
@@ -73,24 +74,37 @@ enum {
     PT_SETUP = 0, PT_PHASE_A, PT_ALLRED1, PT_FINALIZE, PT_PHASE_B, PT_ALLRED2, PT_GSP, PT_PHASE_C, PT_EPILOGUE,
     PT_COMBINE, PT_PP_D01, PT_PP_D2, PT_PP_STEP, PT_PP_INTERP, PT_PP_COPY, PT_NORMS, PT_CTRL, PT_TOTAL, PT_COUNT
 };
+static_assert(sizeof(Ctrl) <= 512 && 512 + 8 * PT_COUNT <= PHX_CTRL_BYTES, "PHX_CTRL_BYTES too small");
 struct Prof {
-    long long* buf;
+    long long* gbuf;   // global accumulators (thread 0 of CTA 0 only, else nullptr)
+    long long* sbuf;   // shared-memory staging: ticks stay on chip, flushed once by finish()
     long long last, start;
-    __device__ __forceinline__ void init(long long* b) {
-        buf = (blockIdx.x == 0 && threadIdx.x == 0) ? b : nullptr;
-        last = start = buf ? clock64() : 0;
+    __device__ __forceinline__ void init(long long* g, long long* sm) {
+        gbuf = (blockIdx.x == 0 && threadIdx.x == 0) ? g : nullptr;
+        sbuf = sm;
+        if (gbuf) {
+            for (int i = 0; i < PT_COUNT; ++i) sbuf[i] = 0;
+            last = start = clock64();
+        }
     }
     __device__ __forceinline__ void tick(int slot) {
-        if (buf) {
+        if (gbuf) {
             long long t = clock64();
-            buf[slot] += t - last;
+            sbuf[slot] += t - last;
             last = t;
         }
     }
     __device__ __forceinline__ void finish() {
-        if (buf) buf[PT_TOTAL] += clock64() - start;
+        if (gbuf) {
+            sbuf[PT_TOTAL] += clock64() - start;
+            for (int i = 0; i < PT_COUNT; ++i) gbuf[i] += sbuf[i];
+        }
     }
 };
+
+__device__ __forceinline__ double tget(const ResParams& p, int i) {
+    return (p.T <= PHX_T_INLINE) ? p.t_small[i] : p.t[i];
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -110,11 +124,106 @@ __device__ __forceinline__ void hill(float y, float& s, float& l, float& den) {
     l = log1pf(s);
 }
 
-__device__ __forceinline__ float4 ld4(const float4* p) { return __ldg(p); }
+// ---- tagged-slot ("LL") inter-CTA exchange ----------------------------------------------------------------------------
+__device__ __forceinline__ void ll_put(unsigned long long* slot, float v, unsigned tag) {
+    unsigned long long w = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v);
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(w) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_ld(const unsigned long long* slot) {
+    unsigned long long w;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(w) : "l"(slot) : "memory");
+    return w;
+}
+__device__ __forceinline__ float ll_get(const unsigned long long* slot, unsigned tag) {
+    unsigned long long w = ll_ld(slot);
+    while ((unsigned)(w >> 32) != tag) w = ll_ld(slot);
+    return __uint_as_float((unsigned)w);
+}
 
-// ---- block / grid reductions ------------------------------------------------------------------------------------
+
+// ---- shared-memory carve-up ---------------------------------------------------------------------------------------
+// The byte offsets are computed on the host (phx_smem_layout, phx_common.cuh) and travel in the kernel parameters
+// (constant bank): the views below cost no registers.  Only the three buffers that swap roles between consecutive
+// stages of the adjoint keep their offsets in registers.
+extern __shared__ __align__(128) unsigned char smem_raw[];
+
+struct Xchg {
+    unsigned long long ep;  // epoch counter (uniform over the grid); tags are its low 32 bits, never 0
+    int ny, nd;             // one-phase / scalar exchanges done so far (double-buffer parity)
+    __device__ __forceinline__ unsigned next_tag() {
+        ++ep;
+        if ((unsigned)ep == 0u) ++ep;
+        return (unsigned)ep;
+    }
+};
+
+struct Ring {
+    unsigned par;             // per-stage parity of the next completion to wait for
+    const float4* pre_mat;    // matrix whose first chunks are already in flight (nullptr: none)
+};
+
+
+// Per-thread kernel context: shared-memory views + the (grid-uniform) exchange / ring / timer state.  Passed by
+// reference to the __noinline__ building blocks so that the solver loops stay small enough for the instruction cache.
+struct Smem {
+    const ResParams& p;
+    unsigned o_acts, o_actl, o_ysb, o_acts2, o_actl2, o_ysb2;
+    int g_lo, n_loc;
+    Xchg x;
+    Ring rg;
+    Prof pf;
+    __device__ __forceinline__ explicit Smem(const ResParams& pp)
+        : p(pp), o_acts(pp.so.acts), o_actl(pp.so.actl), o_ysb(pp.so.ysb), o_acts2(pp.so.acts2),
+          o_actl2(pp.so.actl2), o_ysb2(pp.so.ysb2) {
+        g_lo = blockIdx.x * pp.gpc;
+        n_loc = max(0, min(pp.gpc, pp.G - g_lo));
+    }
+    template <typename T>
+    __device__ __forceinline__ T* at(unsigned off) const { return reinterpret_cast<T*>(smem_raw + off); }
+    __device__ __forceinline__ Ctrl* ctrl() const { return at<Ctrl>(p.so.ctrl); }
+    __device__ __forceinline__ double* dred() const { return at<double>(p.so.dred); }      // [WARPS][8]
+    __device__ __forceinline__ double* gram() const { return at<double>(p.so.gram); }      // [2][64]   (adjoint)
+    __device__ __forceinline__ float* dstage() const { return at<float>(p.so.dstage); }    // [nCTA][PHX_LL_DMAX]
+    __device__ __forceinline__ float* ystage() const { return at<float>(p.so.ystage); }    // [nCTA*B*K2] if use_y
+    __device__ __forceinline__ float* bias() const { return at<float>(p.so.bias); }        // [K2]
+    __device__ __forceinline__ float* relum() const { return at<float>(p.so.relum); }      // [gpc]
+    __device__ __forceinline__ float* maskm() const { return at<float>(p.so.maskm); }      // [gpc]
+    __device__ __forceinline__ float* sp() const { return at<float>(p.so.sp); }            // [B][K2]  S | Pr
+    __device__ __forceinline__ float* gsp() const { return at<float>(p.so.gsp); }          // [B][K2]  gS | gLP
+    __device__ __forceinline__ float* red() const { return at<float>(p.so.red); }          // [WARPS][K2]
+    __device__ __forceinline__ float* st() const { return at<float>(p.so.st); }            // [nslots][B][gpc]
+    __device__ __forceinline__ float* jb() const { return at<float>(p.so.jb); }            // [B][gpc] ...
+    __device__ __forceinline__ float* asb() const { return at<float>(p.so.asb); }
+    __device__ __forceinline__ float* gjb() const { return at<float>(p.so.gjb); }
+    __device__ __forceinline__ float* ub() const { return at<float>(p.so.ub); }
+    __device__ __forceinline__ float* vb() const { return at<float>(p.so.vb); }
+    __device__ __forceinline__ float* mt() const { return at<float>(p.so.mt); }
+    __device__ __forceinline__ float* acts() const { return at<float>(o_acts); }
+    __device__ __forceinline__ float* actl() const { return at<float>(o_actl); }
+    __device__ __forceinline__ float* ysb() const { return at<float>(o_ysb); }
+    __device__ __forceinline__ float* acts2() const { return at<float>(o_acts2); }         // next stage's input
+    __device__ __forceinline__ float* actl2() const { return at<float>(o_actl2); }
+    __device__ __forceinline__ float* ysb2() const { return at<float>(o_ysb2); }
+    // per-stage parameter-cotangent factors, stage index innermost: [..][QB], QB = round_up(7 * BT, 4)
+    __device__ __forceinline__ float* FG() const { return at<float>(p.so.FG); }            // [K2][QB]  gS|gLP
+    __device__ __forceinline__ float* FSP() const { return at<float>(p.so.FSP); }          // [K2][QB]  S|Pr
+    __device__ __forceinline__ float* FS() const { return at<float>(p.so.FS); }            // [gpc][QB] s
+    __device__ __forceinline__ float* FL() const { return at<float>(p.so.FL); }            // [gpc][QB] l
+    __device__ __forceinline__ float* FGJ() const { return at<float>(p.so.FGJ); }          // [gpc][QB] gJ
+    __device__ __forceinline__ float* FM() const { return at<float>(p.so.FM); }            // [gpc][8]
+    __device__ __forceinline__ float4* ring() const { return at<float4>(p.so.ring); }      // [stages][rows][K2q]
+    __device__ __forceinline__ unsigned long long* bar() const { return at<unsigned long long>(p.so.bar); }
+    __device__ __forceinline__ void swap_stage_buffers() {
+        unsigned t;
+        t = o_ysb; o_ysb = o_ysb2; o_ysb2 = t;
+        t = o_acts; o_acts = o_acts2; o_acts2 = t;
+        t = o_actl; o_actl = o_actl2; o_actl2 = t;
+    }
+};
+
+// ---- block reductions and grid-wide exchanges -------------------------------------------------------------------------
 template <int N>
-__device__ void block_sum_d(double (&v)[N], double* dred, double* out) {
+__device__ __noinline__ void block_sum_d(double (&v)[N], double* dred, double* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -130,153 +239,232 @@ __device__ void block_sum_d(double (&v)[N], double* dred, double* out) {
     __syncthreads();
 }
 
-// sum over all CTAs of up to 8 doubles held in vals[] (smem); result replaces vals[] in every CTA.
-__device__ void grid_allreduce_d(cg::grid_group& grid, const ResParams& p, double* vals, int nd, int& parity) {
+// Sum over all CTAs of the nd (<= 8) doubles in vals[] (smem); the result replaces vals[] in every CTA.  Each double
+// travels as two fp32 slots (hi, lo = x - hi: 48 significant bits); every CTA adds the nCTA contributions in the same
+// order.
+__device__ __noinline__ void grid_sum_d(const ResParams& p, Smem& s, double* vals, int nd) {
+    Xchg& x = s.x;
     const int nC = gridDim.x;
     if (nC == 1) return;
-    double* buf = p.partd + (size_t)parity * nC * 8;
-    parity ^= 1;
-    if (threadIdx.x < nd) __stcg(buf + (size_t)blockIdx.x * 8 + threadIdx.x, vals[threadIdx.x]);
-    grid.sync();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (warp < nd) {
-        double s = 0;
-        for (int c = lane; c < nC; c += 32) s += __ldcg(buf + (size_t)c * 8 + warp);
-        s = warp_sum_d(s);
-        if (lane == 0) vals[warp] = s;
+    const unsigned tag = x.next_tag();
+    unsigned long long* base = p.ll.dpart + (size_t)(x.nd & 1) * PHX_LL_MAXC * PHX_LL_DMAX;
+    x.nd++;
+    if (threadIdx.x < 2 * nd) {
+        double v = vals[threadIdx.x >> 1];
+        float hi = (float)v;
+        float w = (threadIdx.x & 1) ? (float)(v - (double)hi) : hi;
+        if (!isfinite(hi)) w = hi;  // inf / nan: both halves carry it
+        ll_put(base + (size_t)blockIdx.x * PHX_LL_DMAX + threadIdx.x, w, tag);
+    }
+    const int per = 2 * nd, tot = nC * per;
+    for (int e = threadIdx.x; e < tot; e += THREADS) {
+        int c = e / per, i = e - c * per;
+        s.dstage()[c * PHX_LL_DMAX + i] = ll_get(base + (size_t)c * PHX_LL_DMAX + i, tag);
     }
     __syncthreads();
-}
-
-// sum over all CTAs of the n-float vector vec[] (smem); two-level, fixed order.
-__device__ void grid_allreduce_f(cg::grid_group& grid, const ResParams& p, float* vec, int n) {
-    const int nC = gridDim.x;
-    if (nC == 1) return;
-    float* mine = p.part + (size_t)blockIdx.x * n;
-    for (int i = threadIdx.x; i < n; i += THREADS) __stcg(mine + i, vec[i]);
-    grid.sync();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int i = blockIdx.x + nC * warp; i < n; i += nC * WARPS) {
-        float s = 0.f;
-        for (int c = lane; c < nC; c += 32) s += __ldcg(p.part + (size_t)c * n + i);
-        s = warp_sum(s);
-        if (lane == 0) __stcg(p.redout + i, s);
-    }
-    grid.sync();
-    for (int i = threadIdx.x; i < n; i += THREADS) vec[i] = __ldcg(p.redout + i);
-    __syncthreads();
-}
-
-// ---- shared-memory carve-up ---------------------------------------------------------------------------------------
-struct Smem {
-    Ctrl* ctrl;
-    double* dred;  // [WARPS][8]
-    float* sp;     // [B][K2]   S | Pr
-    float* gsp;    // [B][K2]   gS | gLP             (adjoint)
-    float* red;    // [WARPS][K2]
-    float *acts, *actl, *ysb, *jb;        // [B][gpc]
-    float *asb, *gjb, *ub, *vb, *mt;      // [B][gpc]  (adjoint)
-    float *pSP, *pG;                      // [7][B][K2] (adjoint, per-stage factors)
-    float *pS, *pL, *pGJ;                 // [7][B][gpc]
-    float* pM;                            // [7][gpc]
-};
-
-__host__ __device__ inline size_t smem_layout(int B, int K2, int gpc, int adjoint, Smem* s, unsigned char* base) {
-    size_t off = 0;
-    auto take = [&](size_t bytes) {
-        size_t o = off;
-        off += (bytes + 15) & ~size_t(15);
-        return o;
-    };
-    size_t o_ctrl = take(sizeof(Ctrl));
-    size_t o_dred = take(sizeof(double) * WARPS * 8);
-    size_t o_sp = take(sizeof(float) * B * K2);
-    size_t o_gsp = adjoint ? take(sizeof(float) * B * K2) : 0;
-    size_t o_red = take(sizeof(float) * WARPS * K2);
-    size_t bl = sizeof(float) * B * gpc;
-    size_t o_loc[9];
-    int nloc = adjoint ? 9 : 4;
-    for (int i = 0; i < nloc; ++i) o_loc[i] = take(bl);
-    size_t o_pSP = 0, o_pG = 0, o_pS = 0, o_pL = 0, o_pGJ = 0, o_pM = 0;
-    if (adjoint) {
-        o_pSP = take(sizeof(float) * 7 * B * K2);
-        o_pG = take(sizeof(float) * 7 * B * K2);
-        o_pS = take(7 * bl);
-        o_pL = take(7 * bl);
-        o_pGJ = take(7 * bl);
-        o_pM = take(sizeof(float) * 7 * gpc);
-    }
-    if (s) {
-        s->ctrl = reinterpret_cast<Ctrl*>(base + o_ctrl);
-        s->dred = reinterpret_cast<double*>(base + o_dred);
-        s->sp = reinterpret_cast<float*>(base + o_sp);
-        s->gsp = reinterpret_cast<float*>(base + o_gsp);
-        s->red = reinterpret_cast<float*>(base + o_red);
-        s->acts = reinterpret_cast<float*>(base + o_loc[0]);
-        s->actl = reinterpret_cast<float*>(base + o_loc[1]);
-        s->ysb = reinterpret_cast<float*>(base + o_loc[2]);
-        s->jb = reinterpret_cast<float*>(base + o_loc[3]);
-        if (adjoint) {
-            s->asb = reinterpret_cast<float*>(base + o_loc[4]);
-            s->gjb = reinterpret_cast<float*>(base + o_loc[5]);
-            s->ub = reinterpret_cast<float*>(base + o_loc[6]);
-            s->vb = reinterpret_cast<float*>(base + o_loc[7]);
-            s->mt = reinterpret_cast<float*>(base + o_loc[8]);
-            s->pSP = reinterpret_cast<float*>(base + o_pSP);
-            s->pG = reinterpret_cast<float*>(base + o_pG);
-            s->pS = reinterpret_cast<float*>(base + o_pS);
-            s->pL = reinterpret_cast<float*>(base + o_pL);
-            s->pGJ = reinterpret_cast<float*>(base + o_pGJ);
-            s->pM = reinterpret_cast<float*>(base + o_pM);
+    {   // one warp per value: lanes over CTAs (fixed assignment), fixed butterfly
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        if (warp < nd) {
+            double t = 0;
+            for (int c = lane; c < nC; c += 32) {
+                float hi = s.dstage()[c * PHX_LL_DMAX + 2 * warp], lo = s.dstage()[c * PHX_LL_DMAX + 2 * warp + 1];
+                t += isfinite(hi) ? ((double)hi + (double)lo) : (double)hi;
+            }
+            t = warp_sum_d(t);
+            if (lane == 0) vals[warp] = t;
         }
     }
-    return off;
+    __syncthreads();
 }
 
-// ---- the three weight passes ------------------------------------------------------------------------------------
-// Mapping common to all passes: a warp owns gene rows j = warp, warp+16, ... of the CTA's slice; lane l owns the
-// float4 columns q = l + 32 v (v < NV) of the K2-long row.
-
-// Phase A: partial[b][k] = sum_{g in slice} act[b][g] * W1[g][k], act = s for k < Hp, l for k >= Hp.
-// Result (this CTA's partial) is left in s.sp[b][:].
-template <int NV, int BT>
-__device__ void phaseA(const ResParams& p, const Smem& s, int g_lo, int n_loc, int b0, int nb) {
+// Sum over all CTAs of the n-float vector vec[] (smem, n a multiple of 4); the result replaces vec[] in every CTA.
+// Small grids: one phase (every CTA reads every partial).  Large grids: reduce-scatter by column quads (one warp per
+// quad, lanes over CTAs, fixed butterfly) then all-gather of the n results.
+__device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, float* vec, int n) {
+    Xchg& x = s.x;
+    const int nC = gridDim.x;
+    if (nC == 1) return;
+    const unsigned tag = x.next_tag();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K2q = p.K2q, Hq = p.Hp >> 2;
-    float4 acc[BT][NV];
+    if (p.so.ystage != 0xffffffffu) {
+        unsigned long long* base = p.ll.ypart + (size_t)(x.ny & 1) * PHX_LL_YMAX;
+        x.ny++;
+        for (int i = threadIdx.x; i < n; i += THREADS) ll_put(base + (size_t)blockIdx.x * n + i, vec[i], tag);
+        const int tot = nC * n;
+        for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * THREADS) {
+            unsigned long long w[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int e = e0 + u * THREADS;
+                if (e < tot) w[u] = ll_ld(base + e);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                int e = e0 + u * THREADS;
+                if (e < tot) {
+                    while ((unsigned)(w[u] >> 32) != tag) w[u] = ll_ld(base + e);
+                    s.ystage()[e] = __uint_as_float((unsigned)w[u]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            float t = 0.f;
+            for (int c = 0; c < nC; ++c) t += s.ystage()[c * n + i];
+            vec[i] = t;
+        }
+        __syncthreads();
+        return;
+    }
+    unsigned long long* mine = p.ll.xpart + (size_t)blockIdx.x * PHX_LL_NMAX;
+    for (int i = threadIdx.x; i < n; i += THREADS) ll_put(mine + i, vec[i], tag);
+    const int nq = n >> 2;
+    for (int q = blockIdx.x + nC * warp; q < nq; q += nC * WARPS) {
+        unsigned long long w[5][4];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            int c = lane + 32 * u;
+            if (c < nC) {
+                const unsigned long long* src = p.ll.xpart + (size_t)c * PHX_LL_NMAX + 4 * q;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) w[u][e] = ll_ld(src + e);
+            }
+        }
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            int c = lane + 32 * u;
+            if (c < nC) {
+                const unsigned long long* src = p.ll.xpart + (size_t)c * PHX_LL_NMAX + 4 * q;
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    while ((unsigned)(w[u][e] >> 32) != tag) w[u][e] = ll_ld(src + e);
+                a0 += __uint_as_float((unsigned)w[u][0]);
+                a1 += __uint_as_float((unsigned)w[u][1]);
+                a2 += __uint_as_float((unsigned)w[u][2]);
+                a3 += __uint_as_float((unsigned)w[u][3]);
+            }
+        }
+        a0 = warp_sum(a0);
+        a1 = warp_sum(a1);
+        a2 = warp_sum(a2);
+        a3 = warp_sum(a3);
+        if (lane < 4) ll_put(p.ll.xres + 4 * q + lane, lane == 0 ? a0 : (lane == 1 ? a1 : (lane == 2 ? a2 : a3)), tag);
+    }
+    for (int i = threadIdx.x; i < n; i += THREADS) vec[i] = ll_get(p.ll.xres + i, tag);
+    __syncthreads();
+}
+
+// ---- weight streaming: ring of shared-memory stages filled by 1-D TMA bulk copies --------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+
+
+__device__ __forceinline__ void ring_init(const ResParams& p, const Smem& s) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.ring_stages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s.bar() + i)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+}
+
+// thread 0 only: chunk c of the n_rows x K2q matrix `mat` -> stage c % S
+__device__ __forceinline__ void ring_issue(const ResParams& p, const Smem& s, const float4* mat, int n_rows, int c) {
+    const int st = c % p.ring_stages;
+    const int rows = min(p.ring_rows, n_rows - c * p.ring_rows);
+    const unsigned bytes = (unsigned)rows * p.K2q * 16u;
+    const unsigned bar = smem_u32(s.bar() + st);
+    const unsigned dst = smem_u32(s.ring() + (size_t)st * p.ring_rows * p.K2q);
+    const float4* src = mat + (size_t)c * p.ring_rows * p.K2q;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+// start the first chunks of the next pass (call right after a pass, before waiting on an exchange)
+__device__ __forceinline__ void ring_prefetch(const ResParams& p, Smem& s, const float4* mat, int n_rows) {
+    Ring& r = s.rg;
+    if (n_rows <= 0) return;
+    if (threadIdx.x == 0) {
+        const int nch = (n_rows + p.ring_rows - 1) / p.ring_rows;
+        for (int c = 0; c < min(nch, p.ring_stages); ++c) ring_issue(p, s, mat, n_rows, c);
+    }
+    r.pre_mat = mat;
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity);
+
+// wait for a prefetch nobody will consume (end of the kernel): no bulk copy may be in flight when the CTA exits
+__device__ __forceinline__ void ring_drain(const ResParams& p, Smem& s, int n_rows) {
+    Ring& r = s.rg;
+    if (r.pre_mat == nullptr || n_rows <= 0) return;
+    const int nch = (n_rows + p.ring_rows - 1) / p.ring_rows;
+    for (int c = 0; c < min(nch, p.ring_stages); ++c) {
+        mbar_wait(smem_u32(s.bar() + c), (r.par >> c) & 1u);
+        r.par ^= 1u << c;
+    }
+    r.pre_mat = nullptr;
+}
+
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+// One pass over this CTA's n_rows rows of `mat`: fn(j, row) is called by one warp (all lanes) per row j with the row
+// in shared memory.
+template <typename RowFn>
+__device__ __forceinline__ void stream_pass(const ResParams& p, Smem& s, const float4* mat, int n_rows, RowFn fn) {
+    Ring& r = s.rg;
+    if (n_rows <= 0) return;
+    const int warp = threadIdx.x >> 5;
+    const int R = p.ring_rows, S = p.ring_stages;
+    const int nch = (n_rows + R - 1) / R;
+    if (r.pre_mat != mat) ring_prefetch(p, s, mat, n_rows);
+    r.pre_mat = nullptr;
+    for (int c = 0; c < nch; ++c) {
+        const int st = c % S;
+        mbar_wait(smem_u32(s.bar() + st), (r.par >> st) & 1u);
+        r.par ^= 1u << st;
+        const int rows = min(R, n_rows - c * R);
+        const float4* base = s.ring() + (size_t)st * R * p.K2q;
+        for (int rr = warp; rr < rows; rr += WARPS) fn(c * R + rr, base + (size_t)rr * p.K2q);
+        __syncthreads();
+        if (threadIdx.x == 0 && c + S < nch) ring_issue(p, s, mat, n_rows, c + S);
+    }
+}
+
+// ---- the weight passes --------------------------------------------------------------------------------------------------
+// Mapping common to all passes: a warp owns one row at a time; lane l owns the float4 columns q = l + 32 v (v < NV) of
+// the K2-long row.  Column accumulators live in registers for the whole pass and are combined across warps in a fixed
+// order through s.red().
+template <int NV, int BT>
+__device__ __forceinline__ void acc_zero(float4 (&acc)[BT][NV]) {
 #pragma unroll
     for (int b = 0; b < BT; ++b)
 #pragma unroll
         for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int j = warp; j < n_loc; j += WARPS) {
-        const float4* row = p.w.W1 + (size_t)(g_lo + j) * K2q;
-        float4 w[NV];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            int q = lane + 32 * v;
-            w[v] = (q < K2q) ? ld4(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-            if (b < nb) {
-                float sv = s.acts[(b0 + b) * p.gpc + j], lv = s.actl[(b0 + b) * p.gpc + j];
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    int q = lane + 32 * v;
-                    float c = (q >= Hq) ? lv : sv;
-                    acc[b][v].x = fmaf(w[v].x, c, acc[b][v].x);
-                    acc[b][v].y = fmaf(w[v].y, c, acc[b][v].y);
-                    acc[b][v].z = fmaf(w[v].z, c, acc[b][v].z);
-                    acc[b][v].w = fmaf(w[v].w, c, acc[b][v].w);
-                }
-            }
-        }
-    }
-    float4* red4 = reinterpret_cast<float4*>(s.red);
+}
+
+template <int NV, int BT>
+__device__ __forceinline__ void acc_reduce(const ResParams& p, const Smem& s, float4 (&acc)[BT][NV], float* out, int b0, int nb) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K2q = p.K2q;
+    float4* red4 = reinterpret_cast<float4*>(s.red());
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
         if (b < nb) {
-            __syncthreads();
 #pragma unroll
             for (int v = 0; v < NV; ++v) {
                 int q = lane + 32 * v;
@@ -286,128 +474,157 @@ __device__ void phaseA(const ResParams& p, const Smem& s, int g_lo, int n_loc, i
             for (int k = threadIdx.x; k < p.K2; k += THREADS) {
                 float t = 0.f;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) t += s.red[w * p.K2 + k];
-                s.sp[(b0 + b) * p.K2 + k] = t;
+                for (int w = 0; w < WARPS; ++w) t += s.red()[w * p.K2 + k];
+                out[(b0 + b) * p.K2 + k] = t;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int NV>
+__device__ __forceinline__ void load_row(const float4* row, int K2q, float4 (&w)[NV]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        int q = lane + 32 * v;
+        w[v] = (q < K2q) ? row[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// acc[b][:] += c_b * w  with c_b = cs[b] on the sums half (q < Hq) and cl[b] on the prods half
+template <int NV, int BT>
+__device__ __forceinline__ void axpy_row(const float4 (&w)[NV], float4 (&acc)[BT][NV], const float* cs, const float* cl,
+                                         int stride, int j, int nb, int Hq) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < BT; ++b) {
+        if (b < nb) {
+            float sv = cs[b * stride + j], lv = cl[b * stride + j];
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                int q = lane + 32 * v;
+                float c = (q >= Hq) ? lv : sv;
+                acc[b][v].x = fmaf(w[v].x, c, acc[b][v].x);
+                acc[b][v].y = fmaf(w[v].y, c, acc[b][v].y);
+                acc[b][v].z = fmaf(w[v].z, c, acc[b][v].z);
+                acc[b][v].w = fmaf(w[v].w, c, acc[b][v].w);
             }
         }
     }
-    __syncthreads();
 }
 
-// Phase B: jb[b][j] = sum_k WA[g][k] * sp[b][k]; adjoint additionally partial gsp[b][k] = sum_g gj[b][g] WA[g][k].
-template <int NV, int BT, bool ADJ>
-__device__ void phaseB(const ResParams& p, const Smem& s, int g_lo, int n_loc, int b0, int nb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int K2q = p.K2q;
-    const float4* sp4 = reinterpret_cast<const float4*>(s.sp);
-    float4 acc[ADJ ? BT : 1][NV];
-    if (ADJ) {
-#pragma unroll
-        for (int b = 0; b < BT; ++b)
-#pragma unroll
-            for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+// Pass A: sp[b][k] (this CTA's partial) = sum_{g in slice} act[b][g] * W1[g][k], act = s for k < Hp, l for k >= Hp.
+template <int NV, int BT>
+__device__ __forceinline__ void passA(const ResParams& p, Smem& s) {
+    const int Hq = p.Hp >> 2;
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    const float *acts = s.acts(), *actl = s.actl();
+    for (int b0 = 0; b0 < p.B; b0 += BT) {
+        const int nb = min(BT, p.B - b0);
+        float4 acc[BT][NV];
+        acc_zero<NV, BT>(acc);
+        stream_pass(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc, [&](int j, const float4* row) {
+            float4 w[NV];
+            load_row<NV>(row, p.K2q, w);
+            axpy_row<NV, BT>(w, acc, acts + b0 * p.gpc, actl + b0 * p.gpc, p.gpc, j, nb, Hq);
+        });
+        acc_reduce<NV, BT>(p, s, acc, s.sp(), b0, nb);
     }
-    for (int j = warp; j < n_loc; j += WARPS) {
-        const float4* row = p.w.WA + (size_t)(g_lo + j) * K2q;
-        float4 w[NV];
+}
+
+// Pass B: jb[b][j] = sum_k WA[g][k] * sp[b][k]; adjoint additionally partial gsp[b][k] = sum_g gj[b][g] WA[g][k].
+template <int NV, int BT, bool ADJ>
+__device__ __forceinline__ void passB(const ResParams& p, Smem& s) {
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    const int lane = threadIdx.x & 31;
+    const int K2q = p.K2q;
+    const float4* sp4 = reinterpret_cast<const float4*>(s.sp());
+    for (int b0 = 0; b0 < p.B; b0 += BT) {
+        const int nb = min(BT, p.B - b0);
+        float4 acc[BT][NV];
+        if (ADJ) acc_zero<NV, BT>(acc);
+        stream_pass(p, s, p.w.WA + (size_t)g_lo * K2q, n_loc, [&](int j, const float4* row) {
+            float4 w[NV];
+            load_row<NV>(row, K2q, w);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            int q = lane + 32 * v;
-            w[v] = (q < K2q) ? ld4(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-            if (b < nb) {
-                float d = 0.f;
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    int q = lane + 32 * v;
-                    if (q < K2q) {
-                        float4 x = sp4[(b0 + b) * K2q + q];
-                        d = fmaf(w[v].x, x.x, d);
-                        d = fmaf(w[v].y, x.y, d);
-                        d = fmaf(w[v].z, x.z, d);
-                        d = fmaf(w[v].w, x.w, d);
-                    }
-                }
-                d = warp_sum(d);
-                if (lane == 0) s.jb[(b0 + b) * p.gpc + j] = d;
-                if (ADJ) {
-                    float gj = s.gjb[(b0 + b) * p.gpc + j];
+            for (int b = 0; b < BT; ++b) {
+                if (b < nb) {
+                    float d = 0.f;
 #pragma unroll
                     for (int v = 0; v < NV; ++v) {
-                        acc[b][v].x = fmaf(w[v].x, gj, acc[b][v].x);
-                        acc[b][v].y = fmaf(w[v].y, gj, acc[b][v].y);
-                        acc[b][v].z = fmaf(w[v].z, gj, acc[b][v].z);
-                        acc[b][v].w = fmaf(w[v].w, gj, acc[b][v].w);
+                        int q = lane + 32 * v;
+                        if (q < K2q) {
+                            float4 x = sp4[(b0 + b) * K2q + q];
+                            d = fmaf(w[v].x, x.x, d);
+                            d = fmaf(w[v].y, x.y, d);
+                            d = fmaf(w[v].z, x.z, d);
+                            d = fmaf(w[v].w, x.w, d);
+                        }
+                    }
+                    d = warp_sum(d);
+                    if (lane == 0) s.jb()[(b0 + b) * p.gpc + j] = d;
+                    if (ADJ) {
+                        float gj = s.gjb()[(b0 + b) * p.gpc + j];
+#pragma unroll
+                        for (int v = 0; v < NV; ++v) {
+                            acc[b][v].x = fmaf(w[v].x, gj, acc[b][v].x);
+                            acc[b][v].y = fmaf(w[v].y, gj, acc[b][v].y);
+                            acc[b][v].z = fmaf(w[v].z, gj, acc[b][v].z);
+                            acc[b][v].w = fmaf(w[v].w, gj, acc[b][v].w);
+                        }
                     }
                 }
             }
-        }
-    }
-    if (ADJ) {
-        float4* red4 = reinterpret_cast<float4*>(s.red);
-#pragma unroll
-        for (int b = 0; b < BT; ++b) {
-            if (b < nb) {
-                __syncthreads();
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    int q = lane + 32 * v;
-                    if (q < K2q) red4[warp * K2q + q] = acc[b][v];
-                }
-                __syncthreads();
-                for (int k = threadIdx.x; k < p.K2; k += THREADS) {
-                    float t = 0.f;
-#pragma unroll
-                    for (int w = 0; w < WARPS; ++w) t += s.red[w * p.K2 + k];
-                    s.gsp[(b0 + b) * p.K2 + k] = t;
-                }
-            }
-        }
+        });
+        if (ADJ) acc_reduce<NV, BT>(p, s, acc, s.gsp(), b0, nb);
     }
     __syncthreads();
 }
 
-// Phase C (adjoint): ub[b][j] = sum_{k<Hp} W1[g][k] gS[b][k],  vb[b][j] = sum_{k>=Hp} W1[g][k] gLP[b][k].
+// Pass C (adjoint): ub[b][j] = sum_{k<Hp} W1[g][k] gS[b][k],  vb[b][j] = sum_{k>=Hp} W1[g][k] gLP[b][k];
+// with do_a also pass A of the NEXT stage input (activations acts2 / actl2) over the same rows -> s.sp().
 template <int NV, int BT>
-__device__ void phaseC(const ResParams& p, const Smem& s, int g_lo, int n_loc, int b0, int nb) {
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+__device__ __forceinline__ void passCA(const ResParams& p, Smem& s, bool do_a) {
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    const int lane = threadIdx.x & 31;
     const int K2q = p.K2q, Hq = p.Hp >> 2;
-    const float4* g4 = reinterpret_cast<const float4*>(s.gsp);
-    for (int j = warp; j < n_loc; j += WARPS) {
-        const float4* row = p.w.W1 + (size_t)(g_lo + j) * K2q;
-        float4 w[NV];
+    const float4* g4 = reinterpret_cast<const float4*>(s.gsp());
+    for (int b0 = 0; b0 < p.B; b0 += BT) {
+        const int nb = min(BT, p.B - b0);
+        float4 acc[BT][NV];
+        acc_zero<NV, BT>(acc);
+        stream_pass(p, s, p.w.W1 + (size_t)g_lo * K2q, n_loc, [&](int j, const float4* row) {
+            float4 w[NV];
+            load_row<NV>(row, K2q, w);
 #pragma unroll
-        for (int v = 0; v < NV; ++v) {
-            int q = lane + 32 * v;
-            w[v] = (q < K2q) ? ld4(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
+            for (int b = 0; b < BT; ++b) {
+                if (b < nb) {
+                    float du = 0.f, dv = 0.f;
 #pragma unroll
-        for (int b = 0; b < BT; ++b) {
-            if (b < nb) {
-                float du = 0.f, dv = 0.f;
-#pragma unroll
-                for (int v = 0; v < NV; ++v) {
-                    int q = lane + 32 * v;
-                    if (q < K2q) {
-                        float4 x = g4[(b0 + b) * K2q + q];
-                        float t = 0.f;
-                        t = fmaf(w[v].x, x.x, t);
-                        t = fmaf(w[v].y, x.y, t);
-                        t = fmaf(w[v].z, x.z, t);
-                        t = fmaf(w[v].w, x.w, t);
-                        if (q >= Hq) dv += t; else du += t;
+                    for (int v = 0; v < NV; ++v) {
+                        int q = lane + 32 * v;
+                        if (q < K2q) {
+                            float4 x = g4[(b0 + b) * K2q + q];
+                            float t = 0.f;
+                            t = fmaf(w[v].x, x.x, t);
+                            t = fmaf(w[v].y, x.y, t);
+                            t = fmaf(w[v].z, x.z, t);
+                            t = fmaf(w[v].w, x.w, t);
+                            if (q >= Hq) dv += t; else du += t;
+                        }
+                    }
+                    du = warp_sum(du);
+                    dv = warp_sum(dv);
+                    if (lane == 0) {
+                        s.ub()[(b0 + b) * p.gpc + j] = du;
+                        s.vb()[(b0 + b) * p.gpc + j] = dv;
                     }
                 }
-                du = warp_sum(du);
-                dv = warp_sum(dv);
-                if (lane == 0) {
-                    s.ub[(b0 + b) * p.gpc + j] = du;
-                    s.vb[(b0 + b) * p.gpc + j] = dv;
-                }
             }
-        }
+            if (do_a) axpy_row<NV, BT>(w, acc, s.acts2() + b0 * p.gpc, s.actl2() + b0 * p.gpc, p.gpc, j, nb, Hq);
+        });
+        if (do_a) acc_reduce<NV, BT>(p, s, acc, s.sp(), b0, nb);
     }
     __syncthreads();
 }
@@ -422,64 +639,14 @@ __device__ __forceinline__ void for_local(const ResParams& p, int g_lo, int n_lo
 }
 
 // branch vector after the all-reduce: add bias, exponentiate the prods half (odenet.py:86-87); padded columns -> 0
-__device__ void finalize_sp(const ResParams& p, const Smem& s) {
+__device__ __forceinline__ void finalize_sp(const ResParams& p, const Smem& s) {
     for (int i = threadIdx.x; i < p.B * p.K2; i += THREADS) {
         int k = i % p.K2;
-        float v = s.sp[i] + p.w.bias[k];
+        float v = s.sp()[i] + s.bias()[k];
         if (k >= p.Hp) v = (k - p.Hp < p.H) ? expf(v) : 0.f;
-        s.sp[i] = v;
+        s.sp()[i] = v;
     }
     __syncthreads();
-}
-
-// One RHS evaluation at the stage input whose activations are in s.acts / s.actl; leaves joint(y) in s.jb.
-template <int NV, int BT>
-__device__ void eval_fwd(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc, Prof& pf) {
-    pf.tick(PT_COMBINE);
-    for (int b0 = 0; b0 < p.B; b0 += BT) phaseA<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
-    pf.tick(PT_PHASE_A);
-    grid_allreduce_f(grid, p, s.sp, p.B * p.K2);
-    pf.tick(PT_ALLRED1);
-    finalize_sp(p, s);
-    pf.tick(PT_FINALIZE);
-    for (int b0 = 0; b0 < p.B; b0 += BT) phaseB<NV, BT, false>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
-    pf.tick(PT_PHASE_B);
-}
-
-// RHS + VJP evaluation at the stage input (ysb, asb) with activations / gj already in smem.  Leaves jb, ub, vb and
-// stores this stage's branch factors in slot `slot` of pSP / pG.
-template <int NV, int BT>
-__device__ void eval_adj(cg::grid_group& grid, const ResParams& p, const Smem& s, int g_lo, int n_loc, int slot,
-                         Prof& pf) {
-    pf.tick(PT_COMBINE);
-    for (int b0 = 0; b0 < p.B; b0 += BT) phaseA<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
-    pf.tick(PT_PHASE_A);
-    grid_allreduce_f(grid, p, s.sp, p.B * p.K2);
-    pf.tick(PT_ALLRED1);
-    finalize_sp(p, s);
-    pf.tick(PT_FINALIZE);
-    for (int b0 = 0; b0 < p.B; b0 += BT) phaseB<NV, BT, true>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
-    pf.tick(PT_PHASE_B);
-    grid_allreduce_f(grid, p, s.gsp, p.B * p.K2);
-    pf.tick(PT_ALLRED2);
-    const int n = p.B * p.K2;
-    for (int i = threadIdx.x; i < n; i += THREADS) {
-        int k = i % p.K2;
-        float spv = s.sp[i];
-        float gv = s.gsp[i];
-        if (k >= p.Hp) gv = gv * spv;  // gLP = gPr * Pr (exp backward)
-        s.gsp[i] = gv;
-        s.pSP[slot * n + i] = spv;
-        s.pG[slot * n + i] = gv;
-    }
-    __syncthreads();
-    pf.tick(PT_GSP);
-    for (int b0 = 0; b0 < p.B; b0 += BT) phaseC<NV, BT>(p, s, g_lo, n_loc, b0, min(BT, p.B - b0));
-    pf.tick(PT_PHASE_C);
-}
-
-__device__ __forceinline__ float* slot_ptr(const ResParams& p, int slot) {
-    return p.st + (size_t)slot * p.B * p.G;
 }
 
 // controller pieces (thread 0 only) --------------------------------------------------------------------------------
@@ -529,8 +696,8 @@ __device__ void log_step(const ResParams& p, Ctrl* c, double t0, double dt, int 
     c->n_log++;
 }
 
-__device__ void set_interp_x(Ctrl* c, double t) {
-    double x = (t - c->tprev) / (c->tcur - c->tprev);
+__device__ void set_interp_x(Ctrl* c, double t, double t0, double t1) {
+    double x = (t - t0) / (t1 - t0);
     double xp = x;
     c->xs[0] = (float)xp;
     xp = xp * x;
@@ -569,114 +736,144 @@ __device__ void write_status(const ResParams& p, const Ctrl* c, int code) {
     }
 }
 
+// common prologue: shared-memory views, epoch, constant per-gene / per-column vectors
+__device__ __forceinline__ void prologue(const ResParams& p, Smem& s) {
+    Xchg& x = s.x;
+    Ring& ring = s.rg;
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    s.pf.init(p.prof, reinterpret_cast<long long*>(smem_raw + p.so.ctrl + 512));
+    x.ep = __ldcg(p.ll.epoch);
+    x.ny = x.nd = 0;
+    ring.par = 0;
+    ring.pre_mat = nullptr;
+    for (int k = threadIdx.x; k < p.K2; k += THREADS) s.bias()[k] = p.w.bias[k];
+    for (int j = threadIdx.x; j < n_loc; j += THREADS) {
+        s.relum()[j] = p.w.relum[g_lo + j];
+        s.maskm()[j] = p.w.maskm[g_lo + j];
+    }
+    ring_init(p, s);
+}
+
+__device__ __forceinline__ void epilogue_epoch(const ResParams& p, const Smem& s) {
+    const Xchg& x = s.x;
+    // every CTA has read the launch's starting epoch before CTA 0 can get here (it took part in >= 1 exchange)
+    if (blockIdx.x == 0 && threadIdx.x == 0) *p.ll.epoch = x.ep;
+}
+
+// One forward RHS evaluation at the stage input (acts / actl / ysb); leaves joint(y) in s.jb().
+template <int NV, int BT>
+__device__ __noinline__ void fwd_eval(const ResParams& __restrict__ p, Smem& __restrict__ s) {
+    Prof& pf = s.pf;
+    pf.tick(PT_COMBINE);
+    passA<NV, BT>(p, s);
+    ring_prefetch(p, s, p.w.WA + (size_t)s.g_lo * p.K2q, s.n_loc);
+    pf.tick(PT_PHASE_A);
+    grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
+    pf.tick(PT_ALLRED1);
+    finalize_sp(p, s);
+    pf.tick(PT_FINALIZE);
+    passB<NV, BT, false>(p, s);
+    ring_prefetch(p, s, p.w.W1 + (size_t)s.g_lo * p.K2q, s.n_loc);
+    pf.tick(PT_PHASE_B);
+}
+
 // =====================================================================================================================
 // Forward solve
 // =====================================================================================================================
 template <int NV, int BT>
-__global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem s;
-    smem_layout(p.B, p.K2, p.gpc, 0, &s, smem_raw);
-    Ctrl* c = s.ctrl;
-    const int g_lo = blockIdx.x * p.gpc;
-    const int n_loc = max(0, min(p.gpc, p.G - g_lo));
+__global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_constant__ ResParams p) {
+    Smem s(p);
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    prologue(p, s);
+    Prof& pf = s.pf;
+    Ctrl* c = s.ctrl();
     const size_t BG = (size_t)p.B * p.G;
+    const int BL = p.B * p.gpc;
     const double Nel = (double)p.B * (double)p.G;
-    float* Y = slot_ptr(p, 0);
-    float* Y1 = slot_ptr(p, 1);
-    int dpar = 0;
-    Prof pf;
-    pf.init(p.prof);
+    float* Y = s.st();
+    float* Y1 = s.st() + BL;
+    auto K = [&](int i) { return s.st() + (2 + i) * BL; };
 
+    ring_prefetch(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc);
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
         c->stop = 0;
-        c->tcur = p.t[0];
+        c->tcur = tget(p, 0);
         c->dt = 0;
         for (int i = 0; i < 7; ++i) c->slot[i] = i;
     }
+    auto set_stage_input = [&](int li, float ys) {
+        s.ysb()[li] = ys;
+        float sv, lv, den;
+        hill(ys, sv, lv, den);
+        s.acts()[li] = sv;
+        s.actl()[li] = lv;
+    };
     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
         float y = p.y0[gi];
-        Y[gi] = y;
+        Y[li] = y;
         p.yout[gi] = y;
-        s.ysb[li] = y;
-        float sv, lv, den;
-        hill(y, sv, lv, den);
-        s.acts[li] = sv;
-        s.actl[li] = lv;
+        set_stage_input(li, y);
     });
     __syncthreads();
 
-    auto K = [&](int i) { return slot_ptr(p, 2 + i); };
-    auto set_stage_input = [&](int li, float ys) {
-        s.ysb[li] = ys;
-        float sv, lv, den;
-        hill(ys, sv, lv, den);
-        s.acts[li] = sv;
-        s.actl[li] = lv;
-    };
+    auto eval = [&]() { fwd_eval<NV, BT>(p, s); };
+    auto fval = [&](int j, int li) { return p.fsign * (s.relum()[j] * (s.jb()[li] - s.ysb()[li])); };
 
     if (p.method != PHX_DOPRI5) {
         // ---- fixed grid: one step per output interval (solvers.py:48-50, 77-95) ----
         const float third = (float)(1.0 / 3.0);
         for (int i = 0; i + 1 < p.T; ++i) {
-            const float dtf = p.t_is_f32 ? ((float)p.t[i + 1] - (float)p.t[i]) : (float)(p.t[i + 1] - p.t[i]);
+            const float dtf = p.t_is_f32 ? ((float)tget(p, i + 1) - (float)tget(p, i)) : (float)(tget(p, i + 1) - tget(p, i));
             float* yo = p.yout + (size_t)(i + 1) * BG;
-            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+            eval();
             if (p.method == PHX_EULER) {
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y = s.ysb[li];
-                    float f = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
-                    float y1 = y + dtf * f;
-                    Y[gi] = y1;
+                    float y1 = s.ysb()[li] + dtf * fval(j, li);
+                    Y[li] = y1;
                     yo[gi] = y1;
                     set_stage_input(li, y1);
                 });
             } else if (p.method == PHX_MIDPOINT) {
                 const float half = 0.5f * dtf;
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y = s.ysb[li];
-                    float f = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
-                    set_stage_input(li, y + f * half);
+                    set_stage_input(li, s.ysb()[li] + fval(j, li) * half);
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+                eval();
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float f = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
-                    float y1 = Y[gi] + dtf * f;
-                    Y[gi] = y1;
+                    float y1 = Y[li] + dtf * fval(j, li);
+                    Y[li] = y1;
                     yo[gi] = y1;
                     set_stage_input(li, y1);
                 });
             } else {  // 3/8-rule RK4 (rk_common.py:96-103)
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y = s.ysb[li];
-                    float k1 = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
-                    K(0)[gi] = k1;
-                    set_stage_input(li, y + dtf * k1 * third);
+                    float k1 = fval(j, li);
+                    K(0)[li] = k1;
+                    set_stage_input(li, s.ysb()[li] + dtf * k1 * third);
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+                eval();
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k2 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
-                    K(1)[gi] = k2;
-                    set_stage_input(li, Y[gi] + dtf * (k2 - K(0)[gi] * third));
+                    float k2 = fval(j, li);
+                    K(1)[li] = k2;
+                    set_stage_input(li, Y[li] + dtf * (k2 - K(0)[li] * third));
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+                eval();
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k3 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
-                    K(2)[gi] = k3;
-                    set_stage_input(li, Y[gi] + dtf * (K(0)[gi] - K(1)[gi] + k3));
+                    float k3 = fval(j, li);
+                    K(2)[li] = k3;
+                    set_stage_input(li, Y[li] + dtf * (K(0)[li] - K(1)[li] + k3));
                 });
                 __syncthreads();
-                eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+                eval();
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k4 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
-                    float dy = (K(0)[gi] + 3.f * (K(1)[gi] + K(2)[gi]) + k4) * dtf * 0.125f;
-                    float y1 = Y[gi] + dy;
-                    Y[gi] = y1;
+                    float k4 = fval(j, li);
+                    float dy = (K(0)[li] + 3.f * (K(1)[li] + K(2)[li]) + k4) * dtf * 0.125f;
+                    float y1 = Y[li] + dy;
+                    Y[li] = y1;
                     yo[gi] = y1;
                     set_stage_input(li, y1);
                 });
@@ -686,32 +883,34 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         if (threadIdx.x == 0) {
             int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
             c->n_rhs = per * (p.T - 1);
-            c->tcur = p.t[p.T - 1];
+            c->tcur = tget(p, p.T - 1);
         }
         __syncthreads();
+        ring_drain(p, s, n_loc);
         pf.tick(PT_CTRL);
         pf.finish();
+        epilogue_epoch(p, s);
         write_status(p, c, PHX_ST_OK);
         return;
     }
 
     // ---- dopri5 (rk_common.py:111-228) ----
     // f0 and the initial step (misc.py:47-86)
-    eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+    eval();
     {
         double acc[3] = {0, 0, 0};
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            float y = s.ysb[li];
-            float f0 = p.fsign * (p.w.relum[g] * (s.jb[li] - y));
-            K(0)[gi] = f0;
+            float y = s.ysb()[li];
+            float f0 = fval(j, li);
+            K(0)[li] = f0;
             float scale = p.atol_f + fabsf(y) * p.rtol_f;
             float r0 = y / scale, r1 = f0 / scale;
             acc[0] += (double)(r0 * r0);
             acc[1] += (double)(r1 * r1);
             if (!isfinite(y)) acc[2] += 1.0;
         });
-        block_sum_d<3>(acc, s.dred, c->dsum);
-        grid_allreduce_d(grid, p, c->dsum, 3, dpar);
+        block_sum_d<3>(acc, s.dred(), c->dsum);
+        grid_sum_d(p, s, c->dsum, 3);
         pf.tick(PT_NORMS);
         if (threadIdx.x == 0) {
             float d0 = sqrtf((float)(c->dsum[0] / Nel));
@@ -723,19 +922,19 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         __syncthreads();
         const float h0 = c->h0;
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            set_stage_input(li, Y[gi] + h0 * K(0)[gi]);
+            set_stage_input(li, Y[li] + h0 * K(0)[li]);
         });
         __syncthreads();
-        eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+        eval();
         double acc2[1] = {0};
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            float f1 = p.fsign * (p.w.relum[g] * (s.jb[li] - s.ysb[li]));
-            float scale = p.atol_f + fabsf(Y[gi]) * p.rtol_f;
-            float r = (f1 - K(0)[gi]) / scale;
+            float f1 = fval(j, li);
+            float scale = p.atol_f + fabsf(Y[li]) * p.rtol_f;
+            float r = (f1 - K(0)[li]) / scale;
             acc2[0] += (double)(r * r);
         });
-        block_sum_d<1>(acc2, s.dred, c->dsum);
-        grid_allreduce_d(grid, p, c->dsum, 1, dpar);
+        block_sum_d<1>(acc2, s.dred(), c->dsum);
+        grid_sum_d(p, s, c->dsum, 1);
         pf.tick(PT_NORMS);
         if (threadIdx.x == 0) {
             float d2 = sqrtf((float)(c->dsum[0] / Nel)) / c->h0;
@@ -771,29 +970,29 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
             const float c00 = c->cb[0][0];
             const float* K0 = K(sl[0]);
             for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                set_stage_input(li, Y[gi] + K0[gi] * c00);
+                set_stage_input(li, Y[li] + K0[li] * c00);
             });
             __syncthreads();
         }
         double acc[2] = {0, 0};
         for (int st = 1; st <= 6; ++st) {
-            eval_fwd<NV, BT>(grid, p, s, g_lo, n_loc, pf);
+            eval();
             for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                float ys = s.ysb[li];
-                float f = p.fsign * (p.w.relum[g] * (s.jb[li] - ys));
-                K(sl[st])[gi] = f;
+                float ys = s.ysb()[li];
+                float f = fval(j, li);
+                K(sl[st])[li] = f;
                 if (st < 6) {
-                    float a = K(sl[0])[gi] * c->cb[st][0];
-                    for (int q = 1; q < st; ++q) a = fmaf(K(sl[q])[gi], c->cb[st][q], a);
+                    float a = K(sl[0])[li] * c->cb[st][0];
+                    for (int q = 1; q < st; ++q) a = fmaf(K(sl[q])[li], c->cb[st][q], a);
                     a = fmaf(f, c->cb[st][st], a);
-                    float yn = Y[gi] + a;
-                    if (st == 5) Y1[gi] = yn;
+                    float yn = Y[li] + a;
+                    if (st == 5) Y1[li] = yn;
                     set_stage_input(li, yn);
                 } else {
-                    float e = K(sl[0])[gi] * c->cerr[0];
-                    for (int q = 1; q < 6; ++q) e = fmaf(K(sl[q])[gi], c->cerr[q], e);
+                    float e = K(sl[0])[li] * c->cerr[0];
+                    for (int q = 1; q < 6; ++q) e = fmaf(K(sl[q])[li], c->cerr[q], e);
                     e = fmaf(f, c->cerr[6], e);
-                    float tol = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[gi]), fabsf(ys));
+                    float tol = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[li]), fabsf(ys));
                     float r = e / tol;
                     acc[0] += (double)(r * r);
                     if (!isfinite(ys)) acc[1] += 1.0;
@@ -801,8 +1000,9 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
             });
             __syncthreads();
         }
-        block_sum_d<2>(acc, s.dred, c->dsum);
-        grid_allreduce_d(grid, p, c->dsum, 2, dpar);
+        pf.tick(PT_COMBINE);
+        block_sum_d<2>(acc, s.dred(), c->dsum);
+        grid_sum_d(p, s, c->dsum, 2);
         pf.tick(PT_NORMS);
         if (threadIdx.x == 0) {
             float ratio = sqrtf((float)(c->dsum[0] / Nel));
@@ -825,23 +1025,23 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
         __syncthreads();
         if (c->accept) {
             // emit every pending output inside (tprev, tcur] from the quartic interpolant (rk_common.py:157)
-            while (next_out < p.T && p.t[next_out] <= c->tcur) {
-                if (threadIdx.x == 0) set_interp_x(c, p.t[next_out]);
+            while (next_out < p.T && tget(p, next_out) <= c->tcur) {
+                if (threadIdx.x == 0) set_interp_x(c, tget(p, next_out), c->tprev, c->tcur);
                 __syncthreads();
                 float* yo = p.yout + (size_t)next_out * BG;
                 const float dtf = c->dtf;
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y0 = Y[gi], y1 = Y1[gi];
-                    float m = K(sl[0])[gi] * c->cmid[0];
-                    for (int q = 1; q < 7; ++q) m = fmaf(K(sl[q])[gi], c->cmid[q], m);
+                    float y0 = Y[li], y1 = Y1[li];
+                    float m = K(sl[0])[li] * c->cmid[0];
+                    for (int q = 1; q < 7; ++q) m = fmaf(K(sl[q])[li], c->cmid[q], m);
                     float ymid = y0 + m;
-                    yo[gi] = interp_eval(y0, y1, ymid, K(sl[0])[gi], K(sl[6])[gi], dtf, c->xs);
+                    yo[gi] = interp_eval(y0, y1, ymid, K(sl[0])[li], K(sl[6])[li], dtf, c->xs);
                 });
                 __syncthreads();
                 ++next_out;
                 if (threadIdx.x == 0) c->n_steps_interval = 0;
             }
-            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { Y[gi] = Y1[gi]; });
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { Y[li] = Y1[li]; });
             if (threadIdx.x == 0) {
                 int t0 = c->slot[0];
                 c->slot[0] = c->slot[6];
@@ -849,24 +1049,34 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(ResParams p) {
             }
             __syncthreads();
         }
+        pf.tick(PT_CTRL);
     }
     __syncthreads();
+    ring_drain(p, s, n_loc);
     pf.tick(PT_CTRL);
     pf.finish();
+    epilogue_epoch(p, s);
     write_status(p, c, code);
 }
 
 // =====================================================================================================================
 // Adjoint sweep
 // =====================================================================================================================
-enum { PP_D01 = 0, PP_D2 = 1, PP_STEP = 2, PP_INTERP = 3, PP_EULER = 4, PP_MIDPOINT = 5, PP_RK4 = 6, PP_COPY = 7 };
+// Parameter-cotangent ("theta") passes.  The stage derivative of a theta element in physical slot q is the rank-B
+// outer product of that stage's factors:
+//   m[g]      : FM[g][q]
+//   Wp[h][g]  : sum_b gLP[q][b][h] * l[q][b][g]        bp[h] : sum_b gLP[q][b][h]
+//   Ws[h][g]  : sum_b gS [q][b][h] * s[q][b][g]        bs[h] : sum_b gS [q][b][h]
+//   Wa[g][k]  : sum_b gJ [q][b][g] * SP[q][b][k]
+enum { PP_D01 = 0, PP_D2 = 1, PP_STEP = 2, PP_FIXED = 3, PP_COPY = 4 };
 
 struct PPArgs {
-    const float* src;  // theta at step start
-    float* dst;        // where the pass writes (may alias src for the in-place fixed-grid modes)
-    unsigned mask;     // physical stage slots whose derivative is needed
-    int s0, s1, s2, s3;  // slots referenced by name (D01: s0; D2: s0,s1; EULER: s0; MIDPOINT: s1; RK4: s0..s3)
-    float coef_sol[7];   // indexed by PHYSICAL slot
+    const float* src;   // theta at step start; nullptr while theta is known to be identically zero
+    float* dst;         // where the pass writes (may alias src: every element is read before it is written)
+    int s0, s1;         // D01: s0; D2: s0, s1
+    int method;         // PP_FIXED: PHX_EULER / MIDPOINT / RK4 (slots 0..3)
+    int last;           // PP_STEP: this step, if accepted, ends the interval -> write the dense output at t_end
+    float coef_sol[7];  // indexed by PHYSICAL slot
     float coef_err[7];
     float coef_mid[7];
     int slot_first, slot_last;
@@ -875,223 +1085,396 @@ struct PPArgs {
 };
 
 template <int MODE>
-__device__ __forceinline__ void theta_elem(const ResParams& p, const PPArgs& a, size_t idx, const float (&k)[7],
-                                           double& acc0, double& acc1) {
+__device__ __forceinline__ void theta_elem(const float atol_f, const float rtol_f, const PPArgs& a, size_t idx,
+                                           const float (&k)[7], double& acc0, double& acc1) {
     if (MODE == PP_COPY) {
         a.dst[idx] = a.src[idx];
         return;
     }
-    float th0 = a.src[idx];
+    const float th0 = a.src ? a.src[idx] : 0.f;
     if (MODE == PP_D01) {
-        float scale = p.atol_f + fabsf(th0) * p.rtol_f;
-        float r0 = th0 / scale, r1 = k[a.s0] / scale;
+        float scale = atol_f + fabsf(th0) * rtol_f;
+        float r0 = th0 / scale, r1 = k[0] / scale;
         acc0 += (double)(r0 * r0);
         acc1 += (double)(r1 * r1);
     } else if (MODE == PP_D2) {
-        float scale = p.atol_f + fabsf(th0) * p.rtol_f;
-        float r = (k[a.s1] - k[a.s0]) / scale;
+        float scale = atol_f + fabsf(th0) * rtol_f;
+        float r = (k[1] - k[0]) / scale;
         acc0 += (double)(r * r);
-    } else if (MODE == PP_STEP || MODE == PP_INTERP) {
-        float inc = 0.f, e = 0.f, md = 0.f;
-        bool first = true;
+    } else if (MODE == PP_STEP) {
+        float inc = k[0] * a.coef_sol[0], e = k[0] * a.coef_err[0];
 #pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            if (first) {
-                inc = k[q] * a.coef_sol[q];
-                e = k[q] * a.coef_err[q];
-                md = k[q] * a.coef_mid[q];
-                first = false;
-            } else {
-                inc = fmaf(k[q], a.coef_sol[q], inc);
-                e = fmaf(k[q], a.coef_err[q], e);
-                md = fmaf(k[q], a.coef_mid[q], md);
-            }
+        for (int q = 1; q < 7; ++q) {
+            inc = fmaf(k[q], a.coef_sol[q], inc);
+            e = fmaf(k[q], a.coef_err[q], e);
         }
         float th1 = th0 + inc;
-        if (MODE == PP_STEP) {
-            float tol = p.atol_f + p.rtol_f * fmaxf(fabsf(th0), fabsf(th1));
-            float r = e / tol;
-            acc0 += (double)(r * r);
-            if (!isfinite(th1)) acc1 += 1.0;
-            a.dst[idx] = th1;
+        float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
+        float r = e / tol;
+        acc0 += (double)(r * r);
+        if (!isfinite(th1)) acc1 += 1.0;
+        if (a.last) {
+            float md = k[0] * a.coef_mid[0];
+            float kf = 0.f, kl = 0.f;
+#pragma unroll
+            for (int q = 0; q < 7; ++q) {
+                if (q > 0) md = fmaf(k[q], a.coef_mid[q], md);
+                kf = (q == a.slot_first) ? k[q] : kf;
+                kl = (q == a.slot_last) ? k[q] : kl;
+            }
+            a.dst[idx] = interp_eval(th0, th1, th0 + md, kf, kl, a.dtf, a.xs);
         } else {
-            float ymid = th0 + md;
-            a.dst[idx] = interp_eval(th0, th1, ymid, k[a.slot_first], k[a.slot_last], a.dtf, a.xs);
+            a.dst[idx] = th1;
         }
-    } else if (MODE == PP_EULER) {
-        a.dst[idx] = th0 + a.dtf * k[a.s0];
-    } else if (MODE == PP_MIDPOINT) {
-        a.dst[idx] = th0 + a.dtf * k[a.s1];
-    } else if (MODE == PP_RK4) {
-        float dy = (k[a.s0] + 3.f * (k[a.s1] + k[a.s2]) + k[a.s3]) * a.dtf * 0.125f;
-        a.dst[idx] = th0 + dy;
+    } else if (MODE == PP_FIXED) {
+        float r;
+        if (a.method == PHX_EULER) r = th0 + a.dtf * k[0];
+        else if (a.method == PHX_MIDPOINT) r = th0 + a.dtf * k[1];
+        else r = th0 + (k[0] + 3.f * (k[1] + k[2]) + k[3]) * a.dtf * 0.125f;
+        a.dst[idx] = r;
     }
 }
 
-// calls f(r, c) for every (r < R, c < C) with c fastest across threads
-template <typename F>
-__device__ __forceinline__ void tile2d(int R, int C, F f) {
-    if (C >= THREADS) {
-        for (int r = 0; r < R; ++r)
-            for (int c = threadIdx.x; c < C; c += THREADS) f(r, c);
-    } else {
-        const int RY = THREADS / C;
-        const int ry = threadIdx.x / C, cx = threadIdx.x - ry * C;
-        if (ry < RY)
-            for (int r = ry; r < R; r += RY) f(r, cx);
-    }
-}
-
-// One pass over this CTA's share of the P-long parameter-cotangent vector.  Stage derivative of an element in
-// physical slot q is the rank-B outer product of that stage's factors:
-//   m[g]      : pM[q][g]
-//   Wp[h][g]  : sum_b gLP[q][b][h] * l[q][b][g]        bp[h] : sum_b gLP[q][b][h]
-//   Ws[h][g]  : sum_b gS [q][b][h] * s[q][b][g]        bs[h] : sum_b gS [q][b][h]
-//   Wa[g][k]  : sum_b gJ [q][b][g] * SP[q][b][k]
+// which factor slots a mode needs, as k[0..NK): D01 {s0}, D2 {s0, s1}, STEP all seven physical slots, FIXED 0..3
 template <int MODE>
-__device__ void ppass(const ResParams& p, const Smem& s, int g_lo, int n_loc, const PPArgs& a, double& acc0,
-                      double& acc1) {
+struct PPSlots {
+    static constexpr int NK = (MODE == PP_D01) ? 1 : (MODE == PP_D2 ? 2 : (MODE == PP_STEP ? 7 : (MODE == PP_FIXED ? 4 : 0)));
+};
+template <int MODE>
+__device__ __forceinline__ int pp_slot(const PPArgs& a, int i) {
+    if (MODE == PP_D01) return a.s0;
+    if (MODE == PP_D2) return i == 0 ? a.s0 : a.s1;
+    return i;
+}
+
+// One R x C outer-product block of theta: element (r, c) at gbase + r * ld + c, factors U[r][QB] (smem, broadcast
+// loads) and V[vcol(c)][QB] (held in registers by the thread that owns column c).
+template <int MODE, int BT, typename VCol>
+__device__ __forceinline__ void pp_block(const float atol_f, const float rtol_f, const PPArgs& a, int R, int C,
+                                         const float* U, const float* V, VCol vcol, size_t gbase, size_t ld,
+                                         double& acc0, double& acc1) {
+    constexpr int NK = PPSlots<MODE>::NK;
+    constexpr int NKA = NK > 0 ? NK : 1;
+    constexpr int QB = (7 * BT + 3) & ~3;
+    if (C <= 0 || R <= 0) return;
+    for (int c0 = 0; c0 < C; c0 += THREADS) {
+        const int Cw = min(C - c0, THREADS);
+        const int RG = THREADS / Cw;
+        const int ry = threadIdx.x / Cw, cx = threadIdx.x - ry * Cw;
+        if (ry >= RG) continue;
+        float v[NKA][BT];
+        int uo[NKA];
+        const float* vp = V + (size_t)vcol(c0 + cx) * QB;
+#pragma unroll
+        for (int i = 0; i < NKA; ++i) {
+            uo[i] = pp_slot<MODE>(a, i) * BT;
+#pragma unroll
+            for (int b = 0; b < BT; ++b) v[i][b] = vp[uo[i] + b];
+        }
+        for (int r = ry; r < R; r += RG) {
+            float k[7];
+            const float* up = U + (size_t)r * QB;
+            if (MODE == PP_STEP) {
+                float u[QB];
+#pragma unroll
+                for (int i = 0; i < QB / 4; ++i) {
+                    float4 t = reinterpret_cast<const float4*>(up)[i];
+                    u[4 * i] = t.x; u[4 * i + 1] = t.y; u[4 * i + 2] = t.z; u[4 * i + 3] = t.w;
+                }
+#pragma unroll
+                for (int q = 0; q < 7; ++q) {
+                    float t = 0.f;
+#pragma unroll
+                    for (int b = 0; b < BT; ++b) t = fmaf(u[q * BT + b], v[q < NKA ? q : 0][b], t);
+                    k[q] = t;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 7; ++i) {
+                    float t = 0.f;
+                    if (i < NK) {
+#pragma unroll
+                        for (int b = 0; b < BT; ++b) t = fmaf(up[uo[i < NKA ? i : 0] + b], v[i < NKA ? i : 0][b], t);
+                    }
+                    k[i] = t;
+                }
+            }
+            theta_elem<MODE>(atol_f, rtol_f, a, gbase + (size_t)r * ld + c0 + cx, k, acc0, acc1);
+        }
+    }
+}
+
+// One pass over this CTA's share of the P-long parameter-cotangent vector.
+template <int MODE, int BT>
+__device__ __noinline__ void ppass(const ResParams& __restrict__ p, const Smem& s, int g_lo, int n_loc,
+                                   const PPArgs& a_in, double& acc0_out, double& acc1_out) {
+    // private copies: the stores to theta may not force reloads of the coefficients (they cannot alias a local)
+    const PPArgs a = a_in;
+    double acc0 = 0, acc1 = 0;
+    struct Fin {
+        double &o0, &o1, &a0, &a1;
+        __device__ ~Fin() { o0 += a0; o1 += a1; }
+    } fin{acc0_out, acc1_out, acc0, acc1};
+    constexpr int NK = PPSlots<MODE>::NK;
+    constexpr int QB = (7 * BT + 3) & ~3;
     const PhxGradOff off = phx_grad_offsets(p.G, p.H);
-    const int B = p.B, K2 = p.K2, Hp = p.Hp, H = p.H, G = p.G, gpc = p.gpc;
-    const unsigned mask = (MODE == PP_COPY) ? 0u : a.mask;
+    const int Hp = p.Hp, H = p.H, G = p.G;
+    const float atol_f = p.atol_f, rtol_f = p.rtol_f;
+    if (MODE == PP_COPY) {
+        float k[7] = {0, 0, 0, 0, 0, 0, 0};
+        for (int j = threadIdx.x; j < n_loc; j += THREADS) theta_elem<MODE>(atol_f, rtol_f, a, off.m + g_lo + j, k, acc0, acc1);
+        for (int h = 0; h < H; ++h)
+            for (int j = threadIdx.x; j < n_loc; j += THREADS) {
+                theta_elem<MODE>(atol_f, rtol_f, a, off.Wp + (size_t)h * G + g_lo + j, k, acc0, acc1);
+                theta_elem<MODE>(atol_f, rtol_f, a, off.Ws + (size_t)h * G + g_lo + j, k, acc0, acc1);
+            }
+        for (size_t e = threadIdx.x; e < (size_t)n_loc * 2 * H; e += THREADS)
+            theta_elem<MODE>(atol_f, rtol_f, a, off.Wa + (size_t)g_lo * 2 * H + e, k, acc0, acc1);
+        if (blockIdx.x == 0)
+            for (int h = threadIdx.x; h < H; h += THREADS) {
+                theta_elem<MODE>(atol_f, rtol_f, a, off.bp + h, k, acc0, acc1);
+                theta_elem<MODE>(atol_f, rtol_f, a, off.bs + h, k, acc0, acc1);
+            }
+        return;
+    }
     // m
     for (int j = threadIdx.x; j < n_loc; j += THREADS) {
         float k[7];
 #pragma unroll
-        for (int q = 0; q < 7; ++q) k[q] = (mask >> q & 1u) ? s.pM[q * gpc + j] : 0.f;
-        theta_elem<MODE>(p, a, off.m + g_lo + j, k, acc0, acc1);
+        for (int i = 0; i < 7; ++i) k[i] = (i < NK) ? s.FM()[j * 8 + pp_slot<MODE>(a, i)] : 0.f;
+        theta_elem<MODE>(atol_f, rtol_f, a, off.m + g_lo + j, k, acc0, acc1);
     }
-    // Wp, Ws : rows h, this CTA's gene columns
-    tile2d(H, n_loc, [&](int h, int j) {
-        float kp[7], ks[7];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            float tp = 0.f, ts = 0.f;
-            if (mask >> q & 1u) {
-                for (int b = 0; b < B; ++b) {
-                    const float* g = s.pG + (size_t)(q * B + b) * K2;
-                    tp = fmaf(g[Hp + h], s.pL[(q * B + b) * gpc + j], tp);
-                    ts = fmaf(g[h], s.pS[(q * B + b) * gpc + j], ts);
-                }
-            }
-            kp[q] = tp;
-            ks[q] = ts;
-        }
-        theta_elem<MODE>(p, a, off.Wp + (size_t)h * G + g_lo + j, kp, acc0, acc1);
-        theta_elem<MODE>(p, a, off.Ws + (size_t)h * G + g_lo + j, ks, acc0, acc1);
-    });
-    // Wa : this CTA's gene rows, 2H columns
-    tile2d(n_loc, 2 * H, [&](int j, int kk) {
-        const int kcol = (kk < H) ? kk : (Hp + kk - H);
-        float k[7];
-#pragma unroll
-        for (int q = 0; q < 7; ++q) {
-            float t = 0.f;
-            if (mask >> q & 1u) {
-                for (int b = 0; b < B; ++b)
-                    t = fmaf(s.pGJ[(q * B + b) * gpc + j], s.pSP[(size_t)(q * B + b) * K2 + kcol], t);
-            }
-            k[q] = t;
-        }
-        theta_elem<MODE>(p, a, off.Wa + (size_t)(g_lo + j) * 2 * H + kk, k, acc0, acc1);
-    });
+    auto ident = [](int c) { return c; };
+    // Wp, Ws : rows h (factors FG), this CTA's gene columns (factors FL / FS)
+    pp_block<MODE, BT>(atol_f, rtol_f, a, H, n_loc, s.FG() + (size_t)Hp * QB, s.FL(), ident, off.Wp + g_lo, (size_t)G, acc0, acc1);
+    pp_block<MODE, BT>(atol_f, rtol_f, a, H, n_loc, s.FG(), s.FS(), ident, off.Ws + g_lo, (size_t)G, acc0, acc1);
+    // Wa : this CTA's gene rows (factors FGJ), 2H columns (factors FSP, skipping the padded columns)
+    pp_block<MODE, BT>(atol_f, rtol_f, a, n_loc, 2 * H, s.FGJ(), s.FSP(), [&](int kk) { return kk < H ? kk : Hp + kk - H; },
+                       off.Wa + (size_t)g_lo * 2 * H, (size_t)2 * H, acc0, acc1);
     // biases : CTA 0
     if (blockIdx.x == 0) {
-        for (int h = threadIdx.x; h < H; h += THREADS) {
-            float kp[7], ks[7];
+        for (int h = threadIdx.x; h < 2 * H; h += THREADS) {
+            const bool prod = h >= H;
+            const float* up = s.FG() + (size_t)(prod ? Hp + h - H : h) * QB;
+            float k[7];
 #pragma unroll
-            for (int q = 0; q < 7; ++q) {
-                float tp = 0.f, ts = 0.f;
-                if (mask >> q & 1u) {
-                    for (int b = 0; b < B; ++b) {
-                        const float* g = s.pG + (size_t)(q * B + b) * K2;
-                        tp += g[Hp + h];
-                        ts += g[h];
-                    }
+            for (int i = 0; i < 7; ++i) {
+                float t = 0.f;
+                if (i < NK) {
+                    int o = pp_slot<MODE>(a, i) * BT;
+                    for (int b = 0; b < BT; ++b) t += up[o + b];
                 }
-                kp[q] = tp;
-                ks[q] = ts;
+                k[i] = t;
             }
-            theta_elem<MODE>(p, a, off.bp + h, kp, acc0, acc1);
-            theta_elem<MODE>(p, a, off.bs + h, ks, acc0, acc1);
+            theta_elem<MODE>(atol_f, rtol_f, a, (prod ? off.bp + (h - H) : off.bs + h), k, acc0, acc1);
         }
     }
 }
 
+// sum over (r, c) of (sum_m sgn_m U[r][idx_m] V[c][idx_m])^2 through the two M x M Gram matrices (theta == 0 norms:
+// no pass over memory).  All threads return the same value.
+__device__ __noinline__ double gram_sq(const Smem& s, const float* U, int R, const float* V, int C, int QB, const int* idx,
+                          const float* sgn, int M) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MM = M * M;
+    __syncthreads();
+    for (int pr = warp; pr < 2 * MM; pr += WARPS) {
+        const int which = pr / MM, m = (pr % MM) / M, m2 = pr % M;
+        const float* X = which ? V : U;
+        const int n = which ? C : R;
+        double t = 0;
+        for (int r = lane; r < n; r += 32) t += (double)X[(size_t)r * QB + idx[m]] * (double)X[(size_t)r * QB + idx[m2]];
+        t = warp_sum_d(t);
+        if (lane == 0) s.gram()[pr] = t;
+    }
+    __syncthreads();
+    double tot = 0;
+    for (int m = 0; m < M; ++m)
+        for (int m2 = 0; m2 < M; ++m2)
+            tot += (double)(sgn[m] * sgn[m2]) * s.gram()[m * M + m2] * s.gram()[MM + m * M + m2];
+    return tot;
+}
+
+// this thread's share of the sum over this CTA's theta elements of (k / atol)^2 with k = k[s1] - k[s0]
+// (s0 < 0: k = k[s1]); valid while theta == 0 (scale = atol, misc.py:63).
+template <int BT>
+__device__ __noinline__ double theta_zero_norm(const ResParams& p, const Smem& s, int n_loc, int s1, int s0) {
+    constexpr int QB = (7 * BT + 3) & ~3;
+    int idx[8];
+    float sgn[8];
+    int M = 0;
+    for (int b = 0; b < BT; ++b) { idx[M] = s1 * BT + b; sgn[M] = 1.f; ++M; }
+    if (s0 >= 0)
+        for (int b = 0; b < BT; ++b) { idx[M] = s0 * BT + b; sgn[M] = -1.f; ++M; }
+    const int Hp = p.Hp;
+    double tot = 0;
+    // Wp, Ws (padded branch columns hold zeros), Wa
+    tot += gram_sq(s, s.FG() + (size_t)Hp * QB, Hp, s.FL(), n_loc, QB, idx, sgn, M);
+    tot += gram_sq(s, s.FG(), Hp, s.FS(), n_loc, QB, idx, sgn, M);
+    tot += gram_sq(s, s.FGJ(), n_loc, s.FSP(), p.K2, QB, idx, sgn, M);
+    // m (per gene) and, on CTA 0, the biases: direct
+    double loc = 0;
+    for (int j = threadIdx.x; j < n_loc; j += THREADS) {
+        float k = s.FM()[j * 8 + s1] - (s0 >= 0 ? s.FM()[j * 8 + s0] : 0.f);
+        loc += (double)k * (double)k;
+    }
+    if (blockIdx.x == 0) {
+        for (int h = threadIdx.x; h < p.K2; h += THREADS) {
+            float k1 = 0.f, k0 = 0.f;
+            for (int b = 0; b < BT; ++b) {
+                k1 += s.FG()[(size_t)h * QB + s1 * BT + b];
+                if (s0 >= 0) k0 += s.FG()[(size_t)h * QB + s0 * BT + b];
+            }
+            float k = k1 - k0;
+            loc += (double)k * (double)k;
+        }
+    }
+    double mine = loc + (threadIdx.x == 0 ? tot : 0.0);
+    return mine / ((double)p.atol_f * (double)p.atol_f);
+}
+
+// First half of one RHS + VJP evaluation at the current stage input: passes A (unless a_done: it was merged into the
+// previous evaluation's pass C) and B with their two all-reduces; leaves ky = -f in KY(slot), the stage's theta
+// factors in column `slot` of the factor tables, gS|gLP in s.gsp().
 template <int NV, int BT>
-__global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
-    cg::grid_group grid = cg::this_grid();
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    Smem s;
-    smem_layout(p.B, p.K2, p.gpc, 1, &s, smem_raw);
-    Ctrl* c = s.ctrl;
-    const int g_lo = blockIdx.x * p.gpc;
-    const int n_loc = max(0, min(p.gpc, p.G - g_lo));
+__device__ __noinline__ void adj_eval1(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool a_done) {
+    constexpr int QB = (7 * BT + 3) & ~3;
+    Prof& pf = s.pf;
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    const float4* WAc = p.w.WA + (size_t)g_lo * p.K2q;
+    float* KYs = s.st() + (4 + slot) * p.B * p.gpc;
+    pf.tick(PT_COMBINE);
+    if (!a_done) passA<NV, BT>(p, s);
+    if (s.rg.pre_mat != WAc) ring_prefetch(p, s, WAc, n_loc);
+    pf.tick(PT_PHASE_A);
+    grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
+    pf.tick(PT_ALLRED1);
+    finalize_sp(p, s);
+    pf.tick(PT_FINALIZE);
+    passB<NV, BT, true>(p, s);
+    ring_prefetch(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc);
+    pf.tick(PT_PHASE_B);
+    grid_allreduce_f(p, s, s.gsp(), p.B * p.K2);
+    pf.tick(PT_ALLRED2);
+    {
+        const int n = p.B * p.K2;
+        for (int i = threadIdx.x; i < n; i += THREADS) {
+            int b = i / p.K2, k = i - b * p.K2;
+            float spv = s.sp()[i];
+            float gv = s.gsp()[i];
+            if (k >= p.Hp) gv = gv * spv;  // gLP = gPr * Pr (exp backward)
+            s.gsp()[i] = gv;
+            s.FSP()[k * QB + slot * BT + b] = spv;
+            s.FG()[k * QB + slot * BT + b] = gv;
+        }
+    }
+    // reverse time: ky = -f; the next stage's y input only needs ky, so the caller can form its activations now
+    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+        float y = s.ysb()[li];
+        float jm = s.jb()[li] - y;
+        KYs[li] = -(s.relum()[j] * jm);
+        s.mt()[li] = s.asb()[li] * jm;
+        s.FS()[j * QB + slot * BT + b] = s.acts()[li];
+        s.FL()[j * QB + slot * BT + b] = s.actl()[li];
+        s.FGJ()[j * QB + slot * BT + b] = s.gjb()[li];
+    });
+    __syncthreads();
+}
+
+// Second half: pass C (merged with pass A of the next stage input in ysb2 / acts2 / actl2 when has_next), then
+// ka = VJP_y with cotangent a into KA(slot); with has_next the stage buffers swap roles.
+template <int NV, int BT>
+__device__ __noinline__ void adj_eval2(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool has_next) {
+    Prof& pf = s.pf;
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    float* KAs = s.st() + (11 + slot) * p.B * p.gpc;
+    for (int j = threadIdx.x; j < n_loc; j += THREADS) {
+        float t = 0.f;
+        for (int b = 0; b < p.B; ++b) t += s.mt()[b * p.gpc + j];
+        s.FM()[j * 8 + slot] = t * s.maskm()[j];
+    }
+    __syncthreads();
+    pf.tick(PT_GSP);
+    passCA<NV, BT>(p, s, has_next);
+    if (has_next) ring_prefetch(p, s, p.w.WA + (size_t)g_lo * p.K2q, n_loc);  // the next evaluation starts at pass B
+    pf.tick(PT_PHASE_C);
+    // soft-sign / log1p backward, minus the decay path
+    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+        float y = s.ysb()[li];
+        float sv = s.acts()[li];
+        float z = y - 0.5f;
+        float den = 1.0f + fabsf(z);
+        float yb = (s.ub()[li] + s.vb()[li] / (1.0f + sv)) / (den * den);
+        KAs[li] = yb - s.gjb()[li];
+    });
+    __syncthreads();
+    if (has_next) s.swap_stage_buffers();
+    pf.tick(PT_EPILOGUE);
+}
+
+template <int NV, int BT>
+__global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_constant__ ResParams p) {
+    constexpr int QB = (7 * BT + 3) & ~3;
+    Smem s(p);
+    const int g_lo = s.g_lo, n_loc = s.n_loc;
+    prologue(p, s);
+    Prof& pf = s.pf;
+    Ctrl* c = s.ctrl();
     const size_t BG = (size_t)p.B * p.G;
+    const int BL = p.B * p.gpc;
     const double Nel = (double)p.B * (double)p.G;
     const PhxGradOff goff = phx_grad_offsets(p.G, p.H);
     const double Pel = (double)goff.total;
-    float* Y = slot_ptr(p, 0);
-    float* A = slot_ptr(p, 1);
-    float* Y1 = slot_ptr(p, 2);
-    float* A1 = slot_ptr(p, 3);
-    auto KY = [&](int i) { return slot_ptr(p, 4 + i); };
-    auto KA = [&](int i) { return slot_ptr(p, 11 + i); };
-    int dpar = 0;
-    Prof pf;
-    pf.init(p.prof);
-    int cur = 0;  // which theta buffer holds the current value
+    float* Y = s.st();
+    float* A = s.st() + BL;
+    float* Y1 = s.st() + 2 * BL;
+    float* A1 = s.st() + 3 * BL;
+    auto KY = [&](int i) { return s.st() + (4 + i) * BL; };
+    auto KA = [&](int i) { return s.st() + (11 + i) * BL; };
+    int cur = 0;             // which theta buffer holds the current value (meaningful once !theta_zero)
+    bool theta_zero = true;  // the accumulator has not been written yet: it is identically zero and never read
     float* theta[2] = {p.theta0, p.theta1};
 
+    ring_prefetch(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc);
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
         c->stop = 0;
         c->tcur = 0;
         c->dt = 0;
     }
+    // zero the factor tables once (padded entries are read by the float4 loads of the theta passes)
+    for (int i = threadIdx.x; i < p.K2 * QB; i += THREADS) { s.FG()[i] = 0.f; s.FSP()[i] = 0.f; }
+    for (int i = threadIdx.x; i < p.gpc * QB; i += THREADS) { s.FS()[i] = 0.f; s.FL()[i] = 0.f; s.FGJ()[i] = 0.f; }
+    for (int i = threadIdx.x; i < p.gpc * 8; i += THREADS) s.FM()[i] = 0.f;
     __syncthreads();
 
     // stage input (y, a) -> smem activations and gJ = a * relu(m)
-    auto set_stage_input = [&](int li, int g, float ys, float as) {
-        s.ysb[li] = ys;
-        s.asb[li] = as;
+    auto set_y_input = [&](float* ysb, float* acts, float* actl, int li, float ys) {
+        ysb[li] = ys;
         float sv, lv, den;
         hill(ys, sv, lv, den);
-        s.acts[li] = sv;
-        s.actl[li] = lv;
-        s.gjb[li] = as * p.w.relum[g];
+        acts[li] = sv;
+        actl[li] = lv;
     };
-    // after eval_adj: stage derivatives of the y and a blocks (reverse time: ky = -f, ka = VJP_y with cotangent a)
-    // and this stage's per-gene factors into slot `slot`
-    auto stage_epilogue = [&](int slot) {
-        pf.tick(PT_PHASE_C);
-        float* ky = KY(slot);
-        float* ka = KA(slot);
-        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            float y = s.ysb[li], av = s.asb[li];
-            float jm = s.jb[li] - y;
-            float f = p.w.relum[g] * jm;
-            float sv = s.acts[li];
-            float z = y - 0.5f;
-            float den = 1.0f + fabsf(z);
-            float yb = (s.ub[li] + s.vb[li] / (1.0f + sv)) / (den * den);
-            yb = yb - s.gjb[li];
-            ky[gi] = -f;
-            ka[gi] = yb;
-            s.mt[li] = av * jm;
-            s.pS[slot * p.B * p.gpc + li] = sv;
-            s.pL[slot * p.B * p.gpc + li] = s.actl[li];
-            s.pGJ[slot * p.B * p.gpc + li] = s.gjb[li];
-        });
-        __syncthreads();
-        for (int j = threadIdx.x; j < n_loc; j += THREADS) {
-            float t = 0.f;
-            for (int b = 0; b < p.B; ++b) t += s.mt[b * p.gpc + j];
-            s.pM[slot * p.gpc + j] = t * p.w.maskm[g_lo + j];
+    auto set_a_input = [&](int li, int j, float as) {
+        s.asb()[li] = as;
+        s.gjb()[li] = as * s.relum()[j];
+    };
+
+    // One RHS + VJP evaluation at the current stage input; stage derivatives land in KY(slot) / KA(slot), the theta
+    // factors in column `slot` of the factor tables.  a_done: pass A of this input already ran (merged into the
+    // previous evaluation's pass C).  With has_next, y_next(li) is called per element once KY(slot) is known and
+    // returns the NEXT stage's y input, whose pass A is merged into this evaluation's pass C.
+    auto eval = [&](int slot, bool a_done, bool has_next, auto y_next) {
+        adj_eval1<NV, BT>(p, s, slot, a_done);
+        if (has_next) {
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                set_y_input(s.ysb2(), s.acts2(), s.actl2(), li, y_next(li));
+            });
         }
-        __syncthreads();
-        pf.tick(PT_EPILOGUE);
+        adj_eval2<NV, BT>(p, s, slot, has_next);
     };
+    auto no_next = [](int) { return 0.f; };
 
     int code = PHX_ST_OK;
     for (int iv = p.T - 1; iv >= 1 && code == PHX_ST_OK; --iv) {
@@ -1100,78 +1483,66 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
         const bool first_iv = (iv == p.T - 1);
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
             float y = ysv[gi];
-            float av = first_iv ? gy[gi] : A[gi];
-            Y[gi] = y;
-            A[gi] = av;
-            set_stage_input(li, g, y, av);
+            float av = first_iv ? gy[gi] : A[li];
+            Y[li] = y;
+            A[li] = av;
+            set_y_input(s.ysb(), s.acts(), s.actl(), li, y);
+            set_a_input(li, j, av);
         });
         __syncthreads();
-        const double t_start = -p.t[iv], t_end = -p.t[iv - 1];
+        const double t_start = -tget(p, iv), t_end = -tget(p, iv - 1);
 
         if (p.method != PHX_DOPRI5) {
-            const float dtf = p.t_is_f32 ? ((float)p.t[iv] - (float)p.t[iv - 1]) : (float)(p.t[iv] - p.t[iv - 1]);
+            const float dtf = p.t_is_f32 ? ((float)tget(p, iv) - (float)tget(p, iv - 1)) : (float)(tget(p, iv) - tget(p, iv - 1));
             const float third = (float)(1.0 / 3.0);
             PPArgs pa;
-            pa.src = theta[0];
+            pa.src = theta_zero ? nullptr : theta[0];
             pa.dst = theta[0];
             pa.dtf = dtf;
-            pa.s0 = 0; pa.s1 = 1; pa.s2 = 2; pa.s3 = 3;
+            pa.method = p.method;
             double d0 = 0, d1 = 0;
-            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0, pf);
-            stage_epilogue(0);
             if (p.method == PHX_EULER) {
+                eval(0, false, false, no_next);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    A[gi] = A[gi] + dtf * KA(0)[gi];
+                    A[li] = A[li] + dtf * KA(0)[li];
                 });
-                pa.mask = 1u;
-                pf.tick(PT_COMBINE);
-                ppass<PP_EULER>(p, s, g_lo, n_loc, pa, d0, d1);
-                pf.tick(PT_PP_STEP);
             } else if (p.method == PHX_MIDPOINT) {
                 const float half = 0.5f * dtf;
+                eval(0, false, true, [&](int li) { return Y[li] + KY(0)[li] * half; });
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_stage_input(li, g, Y[gi] + KY(0)[gi] * half, A[gi] + KA(0)[gi] * half);
+                    set_a_input(li, j, A[li] + KA(0)[li] * half);
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1, pf);
-                stage_epilogue(1);
+                eval(1, true, false, no_next);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    A[gi] = A[gi] + dtf * KA(1)[gi];
+                    A[li] = A[li] + dtf * KA(1)[li];
                 });
-                pa.mask = 2u;
-                pf.tick(PT_COMBINE);
-                ppass<PP_MIDPOINT>(p, s, g_lo, n_loc, pa, d0, d1);
-                pf.tick(PT_PP_STEP);
             } else {
+                eval(0, false, true, [&](int li) { return Y[li] + dtf * KY(0)[li] * third; });
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_stage_input(li, g, Y[gi] + dtf * KY(0)[gi] * third, A[gi] + dtf * KA(0)[gi] * third);
+                    set_a_input(li, j, A[li] + dtf * KA(0)[li] * third);
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1, pf);
-                stage_epilogue(1);
+                eval(1, true, true, [&](int li) { return Y[li] + dtf * (KY(1)[li] - KY(0)[li] * third); });
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_stage_input(li, g, Y[gi] + dtf * (KY(1)[gi] - KY(0)[gi] * third),
-                                    A[gi] + dtf * (KA(1)[gi] - KA(0)[gi] * third));
+                    set_a_input(li, j, A[li] + dtf * (KA(1)[li] - KA(0)[li] * third));
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 2, pf);
-                stage_epilogue(2);
+                eval(2, true, true, [&](int li) { return Y[li] + dtf * (KY(0)[li] - KY(1)[li] + KY(2)[li]); });
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_stage_input(li, g, Y[gi] + dtf * (KY(0)[gi] - KY(1)[gi] + KY(2)[gi]),
-                                    A[gi] + dtf * (KA(0)[gi] - KA(1)[gi] + KA(2)[gi]));
+                    set_a_input(li, j, A[li] + dtf * (KA(0)[li] - KA(1)[li] + KA(2)[li]));
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 3, pf);
-                stage_epilogue(3);
+                eval(3, true, false, no_next);
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float dy = (KA(0)[gi] + 3.f * (KA(1)[gi] + KA(2)[gi]) + KA(3)[gi]) * dtf * 0.125f;
-                    A[gi] = A[gi] + dy;
+                    float dy = (KA(0)[li] + 3.f * (KA(1)[li] + KA(2)[li]) + KA(3)[li]) * dtf * 0.125f;
+                    A[li] = A[li] + dy;
                 });
-                pa.mask = 15u;
-                pf.tick(PT_COMBINE);
-                ppass<PP_RK4>(p, s, g_lo, n_loc, pa, d0, d1);
-                pf.tick(PT_PP_STEP);
             }
+            pf.tick(PT_COMBINE);
+            ppass<PP_FIXED, BT>(p, s, g_lo, n_loc, pa, d0, d1);
+            pf.tick(PT_PP_STEP);
+            theta_zero = false;
             if (threadIdx.x == 0) {
                 int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
                 c->n_rhs += per;
@@ -1189,30 +1560,30 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
             }
             __syncthreads();
             // f0 and Hairer's initial step under the mixed norm max(RMS_y, RMS_a, RMS_theta)
-            eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 0, pf);
-            stage_epilogue(0);
+            eval(0, false, false, no_next);
             {
                 double acc[7] = {0, 0, 0, 0, 0, 0, 0};
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y = Y[gi], av = A[gi];
+                    float y = Y[li], av = A[li];
                     float sy = p.atol_f + fabsf(y) * p.rtol_f, sa = p.atol_f + fabsf(av) * p.rtol_f;
                     float r;
                     r = y / sy; acc[0] += (double)(r * r);
                     r = av / sa; acc[1] += (double)(r * r);
-                    r = KY(0)[gi] / sy; acc[3] += (double)(r * r);
-                    r = KA(0)[gi] / sa; acc[4] += (double)(r * r);
+                    r = KY(0)[li] / sy; acc[3] += (double)(r * r);
+                    r = KA(0)[li] / sa; acc[4] += (double)(r * r);
                     if (!isfinite(y) || !isfinite(av)) acc[6] += 1.0;
                 });
                 PPArgs pa;
-                pa.src = theta[cur];
+                pa.src = theta_zero ? nullptr : theta[cur];
                 pa.dst = nullptr;
-                pa.mask = 1u;
                 pa.s0 = 0;
+                pa.s1 = 1;
                 pf.tick(PT_COMBINE);
-                ppass<PP_D01>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
+                if (theta_zero) acc[5] += theta_zero_norm<BT>(p, s, n_loc, 0, -1);
+                else ppass<PP_D01, BT>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
                 pf.tick(PT_PP_D01);
-                block_sum_d<7>(acc, s.dred, c->dsum);
-                grid_allreduce_d(grid, p, c->dsum, 7, dpar);
+                block_sum_d<7>(acc, s.dred(), c->dsum);
+                grid_sum_d(p, s, c->dsum, 7);
                 pf.tick(PT_NORMS);
                 if (threadIdx.x == 0) {
                     float d0 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
@@ -1226,27 +1597,25 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 __syncthreads();
                 const float h0 = c->h0;
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_stage_input(li, g, Y[gi] + h0 * KY(0)[gi], A[gi] + h0 * KA(0)[gi]);
+                    set_y_input(s.ysb(), s.acts(), s.actl(), li, Y[li] + h0 * KY(0)[li]);
+                    set_a_input(li, j, A[li] + h0 * KA(0)[li]);
                 });
                 __syncthreads();
-                eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, 1, pf);
-                stage_epilogue(1);
+                eval(1, false, false, no_next);
                 double acc2[3] = {0, 0, 0};
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float sy = p.atol_f + fabsf(Y[gi]) * p.rtol_f, sa = p.atol_f + fabsf(A[gi]) * p.rtol_f;
+                    float sy = p.atol_f + fabsf(Y[li]) * p.rtol_f, sa = p.atol_f + fabsf(A[li]) * p.rtol_f;
                     float r;
-                    r = (KY(1)[gi] - KY(0)[gi]) / sy; acc2[0] += (double)(r * r);
-                    r = (KA(1)[gi] - KA(0)[gi]) / sa; acc2[1] += (double)(r * r);
+                    r = (KY(1)[li] - KY(0)[li]) / sy; acc2[0] += (double)(r * r);
+                    r = (KA(1)[li] - KA(0)[li]) / sa; acc2[1] += (double)(r * r);
                 });
-                pa.mask = 3u;
-                pa.s0 = 0;
-                pa.s1 = 1;
                 double dummy = 0;
                 pf.tick(PT_COMBINE);
-                ppass<PP_D2>(p, s, g_lo, n_loc, pa, acc2[2], dummy);
+                if (theta_zero) acc2[2] += theta_zero_norm<BT>(p, s, n_loc, 1, 0);
+                else ppass<PP_D2, BT>(p, s, g_lo, n_loc, pa, acc2[2], dummy);
                 pf.tick(PT_PP_D2);
-                block_sum_d<3>(acc2, s.dred, c->dsum);
-                grid_allreduce_d(grid, p, c->dsum, 3, dpar);
+                block_sum_d<3>(acc2, s.dred(), c->dsum);
+                grid_sum_d(p, s, c->dsum, 3);
                 pf.tick(PT_NORMS);
                 if (threadIdx.x == 0) {
                     float d2 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
@@ -1264,7 +1633,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                     else if (!(c->tcur + c->dt > c->tcur)) st = PHX_ST_DT_UNDERFLOW;
                     else if (c->nonfinite_prev) st = PHX_ST_NONFINITE;
                     c->stop = st;
-                    if (!st) set_step_coeffs(c);
+                    if (!st) {
+                        set_step_coeffs(c);
+                        // this step, if accepted, reaches t_end: same comparison as rk_common.py:153 after the step
+                        c->last = !(c->t_end > c->tcur + c->dt);
+                        if (c->last) set_interp_x(c, c->t_end, c->tcur, c->tcur + c->dt);
+                    }
                 }
                 __syncthreads();
                 if (c->stop) {
@@ -1277,38 +1651,38 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 {
                     const float c00 = c->cb[0][0];
                     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                        set_stage_input(li, g, Y[gi] + KY(sl[0])[gi] * c00, A[gi] + KA(sl[0])[gi] * c00);
+                        set_y_input(s.ysb(), s.acts(), s.actl(), li, Y[li] + KY(sl[0])[li] * c00);
+                        set_a_input(li, j, A[li] + KA(sl[0])[li] * c00);
                     });
                     __syncthreads();
                 }
                 double acc[4] = {0, 0, 0, 0};
                 for (int st = 1; st <= 6; ++st) {
-                    eval_adj<NV, BT>(grid, p, s, g_lo, n_loc, sl[st], pf);
-                    stage_epilogue(sl[st]);
+                    // next stage's y input from ky of stages 0..st (the newest one just computed inside eval)
+                    eval(sl[st], st > 1, st < 6, [&](int li) {
+                        float ay = KY(sl[0])[li] * c->cb[st][0];
+                        for (int q = 1; q <= st; ++q) ay = fmaf(KY(sl[q])[li], c->cb[st][q], ay);
+                        float yn = Y[li] + ay;
+                        if (st == 5) Y1[li] = yn;
+                        return yn;
+                    });
                     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                         if (st < 6) {
-                            float ay = KY(sl[0])[gi] * c->cb[st][0];
-                            float aa = KA(sl[0])[gi] * c->cb[st][0];
-                            for (int q = 1; q <= st; ++q) {
-                                ay = fmaf(KY(sl[q])[gi], c->cb[st][q], ay);
-                                aa = fmaf(KA(sl[q])[gi], c->cb[st][q], aa);
-                            }
-                            float yn = Y[gi] + ay, an = A[gi] + aa;
-                            if (st == 5) {
-                                Y1[gi] = yn;
-                                A1[gi] = an;
-                            }
-                            set_stage_input(li, g, yn, an);
+                            float aa = KA(sl[0])[li] * c->cb[st][0];
+                            for (int q = 1; q <= st; ++q) aa = fmaf(KA(sl[q])[li], c->cb[st][q], aa);
+                            float an = A[li] + aa;
+                            if (st == 5) A1[li] = an;
+                            set_a_input(li, j, an);
                         } else {
-                            float ey = KY(sl[0])[gi] * c->cerr[0];
-                            float ea = KA(sl[0])[gi] * c->cerr[0];
+                            float ey = KY(sl[0])[li] * c->cerr[0];
+                            float ea = KA(sl[0])[li] * c->cerr[0];
                             for (int q = 1; q < 7; ++q) {
-                                ey = fmaf(KY(sl[q])[gi], c->cerr[q], ey);
-                                ea = fmaf(KA(sl[q])[gi], c->cerr[q], ea);
+                                ey = fmaf(KY(sl[q])[li], c->cerr[q], ey);
+                                ea = fmaf(KA(sl[q])[li], c->cerr[q], ea);
                             }
-                            float y1 = s.ysb[li], a1 = s.asb[li];
-                            float ty = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[gi]), fabsf(y1));
-                            float ta = p.atol_f + p.rtol_f * fmaxf(fabsf(A[gi]), fabsf(a1));
+                            float y1 = s.ysb()[li], a1 = s.asb()[li];
+                            float ty = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[li]), fabsf(y1));
+                            float ta = p.atol_f + p.rtol_f * fmaxf(fabsf(A[li]), fabsf(a1));
                             float r;
                             r = ey / ty; acc[0] += (double)(r * r);
                             r = ea / ta; acc[1] += (double)(r * r);
@@ -1318,10 +1692,10 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                     __syncthreads();
                 }
                 PPArgs pa;
-                pa.src = theta[cur];
-                pa.dst = theta[cur ^ 1];
-                pa.mask = 127u;
+                pa.src = theta_zero ? nullptr : theta[cur];
+                pa.dst = theta_zero ? theta[0] : theta[cur ^ 1];
                 pa.dtf = c->dtf;
+                pa.last = c->last;
                 for (int q = 0; q < 7; ++q) {
                     pa.coef_sol[sl[q]] = (q < 6) ? c->cb[5][q] : 0.f;
                     pa.coef_err[sl[q]] = c->cerr[q];
@@ -1329,11 +1703,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                 }
                 pa.slot_first = sl[0];
                 pa.slot_last = sl[6];
+                for (int q = 0; q < 4; ++q) pa.xs[q] = c->xs[q];
                 pf.tick(PT_COMBINE);
-                ppass<PP_STEP>(p, s, g_lo, n_loc, pa, acc[2], acc[3]);
+                ppass<PP_STEP, BT>(p, s, g_lo, n_loc, pa, acc[2], acc[3]);
                 pf.tick(PT_PP_STEP);
-                block_sum_d<4>(acc, s.dred, c->dsum);
-                grid_allreduce_d(grid, p, c->dsum, 4, dpar);
+                block_sum_d<4>(acc, s.dred(), c->dsum);
+                grid_sum_d(p, s, c->dsum, 4);
                 pf.tick(PT_NORMS);
                 if (threadIdx.x == 0) {
                     float ratio = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
@@ -1355,32 +1730,25 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                     c->accept = accept;
                     c->n_rhs += 6;
                     c->n_steps_interval++;
-                    if (accept && !(c->t_end > c->tcur)) set_interp_x(c, c->t_end);
                 }
                 __syncthreads();
                 if (c->accept) {
-                    if (!(c->t_end > c->tcur)) {
-                        // last step of the interval: dense output at t_end for adj_y and adj_params
+                    if (theta_zero) { cur = 0; theta_zero = false; } else cur ^= 1;
+                    if (c->last) {
+                        // last step of the interval: dense output at t_end for adj_y (adj_params: done in the pass)
                         const float dtf = c->dtf;
                         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                            float a0 = A[gi], a1 = A1[gi];
-                            float m = KA(sl[0])[gi] * c->cmid[0];
-                            for (int q = 1; q < 7; ++q) m = fmaf(KA(sl[q])[gi], c->cmid[q], m);
-                            A[gi] = interp_eval(a0, a1, a0 + m, KA(sl[0])[gi], KA(sl[6])[gi], dtf, c->xs);
+                            float a0 = A[li], a1 = A1[li];
+                            float m = KA(sl[0])[li] * c->cmid[0];
+                            for (int q = 1; q < 7; ++q) m = fmaf(KA(sl[q])[li], c->cmid[q], m);
+                            A[li] = interp_eval(a0, a1, a0 + m, KA(sl[0])[li], KA(sl[6])[li], dtf, c->xs);
                         });
-                        for (int q = 0; q < 4; ++q) pa.xs[q] = c->xs[q];
-                        double d0 = 0, d1 = 0;
-                        pf.tick(PT_COMBINE);
-                        ppass<PP_INTERP>(p, s, g_lo, n_loc, pa, d0, d1);
-                        pf.tick(PT_PP_INTERP);
-                        cur ^= 1;
                         done = true;
                     } else {
                         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                            Y[gi] = Y1[gi];
-                            A[gi] = A1[gi];
+                            Y[li] = Y1[li];
+                            A[li] = A1[li];
                         });
-                        cur ^= 1;
                         if (threadIdx.x == 0) {
                             int t0 = c->slot[0];
                             c->slot[0] = c->slot[6];
@@ -1389,31 +1757,37 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(ResParams p) {
                     }
                     __syncthreads();
                 }
+                pf.tick(PT_CTRL);
             }
         }
         // interval done: adj_y picks up the loss gradient at t[iv-1] (adjoint.py:152-154)
         if (code == PHX_ST_OK) {
             const float* gprev = p.grad_y + (size_t)(iv - 1) * BG;
-            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { A[gi] = A[gi] + gprev[gi]; });
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { A[li] = A[li] + gprev[gi]; });
             __syncthreads();
         }
     }
-    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { p.adj_y0[gi] = A[gi]; });
-    if (cur != 0) {
+    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { p.adj_y0[gi] = A[li]; });
+    pf.tick(PT_COMBINE);
+    if (theta_zero) {
+        // nothing was ever written (a solver assertion fired before the first accepted step): report zeros
+        const size_t tot = goff.total;
+        for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < tot; i += (size_t)gridDim.x * THREADS)
+            theta[0][i] = 0.f;
+    } else if (cur != 0) {
+        // the last accepted step landed in the scratch twin
         PPArgs pa;
         pa.src = theta[1];
         pa.dst = theta[0];
-        pa.mask = 0;
         double d0 = 0, d1 = 0;
-        const float zero[7] = {0, 0, 0, 0, 0, 0, 0};
-        (void)zero;
-        pf.tick(PT_COMBINE);
-        ppass<PP_COPY>(p, s, g_lo, n_loc, pa, d0, d1);
-        pf.tick(PT_PP_COPY);
+        ppass<PP_COPY, BT>(p, s, g_lo, n_loc, pa, d0, d1);
     }
+    pf.tick(PT_PP_COPY);
     __syncthreads();
+    ring_drain(p, s, n_loc);
     pf.tick(PT_CTRL);
     pf.finish();
+    epilogue_epoch(p, s);
     write_status(p, c, code);
 }
 

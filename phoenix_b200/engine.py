@@ -71,6 +71,10 @@ def _workspace(dev, nbytes, tag):
     ws = tls.workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=torch.device("cuda", dev))
+        if tag == "solve":
+            # the resident solvers keep their inter-CTA exchange area at the start of the workspace: zero it once
+            lib = _lib.load()
+            _lib.check(lib.phx_solve_workspace_init(_ptr(ws), ws.numel(), _stream_ptr(dev)), "workspace_init")
         tls.workspaces[key] = ws
     return ws
 
@@ -291,7 +295,7 @@ def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, 
     T = len(t_list)
     lib = _lib.load()
     engine, nb = _pick_engine(lib, dev, G, H, B, T, False)
-    ws = _workspace(dev, nb, "solve")
+    ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     yout = torch.empty((T,) + tuple(y0c.shape), dtype=torch.float32, device=y0c.device)
     st = _new_status()
     log, cap = _steplog()
@@ -312,7 +316,7 @@ def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_sa
     B = ys[0].numel() // G
     lib = _lib.load()
     engine, nb = _pick_engine(lib, dev, G, H, B, T, True)
-    ws = _workspace(dev, nb, "solve")
+    ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     adj_y0 = torch.empty_like(ys[0])
     P = 4 * G * H + 2 * H + G
     grads = torch.empty(P, dtype=torch.float32, device=ys.device)

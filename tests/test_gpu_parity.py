@@ -208,7 +208,8 @@ def test_bitwise_determinism(pb):
 
 
 def test_batched_fixed_step_equals_per_row(pb):
-    """Fixed-grid rows are independent (no global norm): a B=4 resident solve equals four B=1 solves bit for bit."""
+    """Fixed-grid rows are independent (no global norm): a B=4 resident solve equals four B=1 solves up to the
+    summation order of the inter-CTA all-reduce (one-phase at B=1, reduce-scatter at B=4 for this grid)."""
     w = O.make_weights(350, 40, 78, dense=True)
     net = make_net(pb, w)
     y0 = torch.rand(4, 1, 350, generator=torch.Generator().manual_seed(4)).cuda()
@@ -217,7 +218,7 @@ def test_batched_fixed_step_equals_per_row(pb):
         yb = pb.odeint(net, y0, t, method="rk4")
         for b in range(4):
             yr = pb.odeint(net, y0[b], t, method="rk4")
-            assert torch.equal(yb[:, b], yr)
+            assert rel_l2(yb[:, b].cpu(), yr.cpu()) < 2e-6
 
 
 def test_engines_agree_batched(pb):
