@@ -75,6 +75,10 @@ int phx_resident_max_rows(int adjoint);
 /* Diagnostics (no reference counterpart): while `slots` (a device array of phx_profile_slots() int64, zeroed by the
  * caller) is set, CTA 0 of every resident solve adds the SM-clock cycles it spends in each phase of the kernel
  * (phase ids: PT_* in csrc/phx_resident.cuh).  NULL switches the timer off. */
+/* Host-only: how a resident solve of this shape would be laid out on a device with num_sms SMs (needs no GPU).
+ * out = {CTAs, genes per CTA, float4 columns per lane, W1 slice resident in shared memory?, WA slice resident?,
+ * ring rows per chunk, ring stages, dynamic shared memory bytes}.  PHX_ERR_UNSUPPORTED if the shape does not fit. */
+int phx_plan_describe(int num_sms, int G, int H, int B, int adjoint, int32_t out[8]);
 int phx_ctx_set_profile(phx_ctx* ctx, void* slots);
 int phx_profile_slots(void);
 

@@ -106,6 +106,16 @@ int phx_profile_slots(void) { return PHX_PROF_SLOTS; }
 
 int phx_resident_max_rows(int adjoint) { return adjoint ? PHX_MAX_B_ADJ : PHX_MAX_B_FWD; }
 
+int phx_plan_describe(int num_sms, int G, int H, int B, int adjoint, int32_t out[8]) {
+    ResLaunchPlan plan;
+    if (!out || !check_dims(G, H, B)) return PHX_ERR_INVALID;
+    int rc = phx_resident_plan(num_sms, G, H, B, adjoint, &plan);
+    if (rc != PHX_OK) return rc;
+    out[0] = plan.nCTA; out[1] = plan.gpc; out[2] = plan.NV; out[3] = plan.w1_res; out[4] = plan.wa_res;
+    out[5] = plan.ring_rows; out[6] = plan.ring_stages; out[7] = (int32_t)plan.smem_bytes;
+    return PHX_OK;
+}
+
 size_t phx_packed_bytes(int G, int H) { return phx_packed_floats(G, H) * sizeof(float); }
 
 int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* m, const float* Wp, const float* bp, const float* Ws,

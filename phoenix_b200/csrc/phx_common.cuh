@@ -75,41 +75,50 @@ static inline __host__ __device__ PhxGradOff phx_grad_offsets(int G, int H) {
 #define PHX_LL_NMAX 4096                     /* longest all-reduced vector: max rows (8) x max K2 (512)  */
 #define PHX_LL_YMAX 16384                    /* one-phase exchange: nCTA * n <= YMAX                     */
 #define PHX_LL_DMAX 16                       /* scalar (norm) exchange: floats per CTA                   */
+#define PHX_LL_RCOPIES 8                     /* replicas of every reduced result: CTA c polls copy c % R, so the
+                                                readers of one exchange spread over R x as many L2 slices */
 struct PhxLL {
     unsigned long long* epoch;   // [1] (+7 pad)
     unsigned long long* xpart;   // [MAXC][NMAX]   two-phase all-reduce: per-CTA partials
-    unsigned long long* xres;    // [NMAX]         two-phase all-reduce: reduced vector
+    unsigned long long* xres;    // [R][NMAX]      two-phase all-reduce: reduced vector, R replicas
     unsigned long long* ypart;   // [2][YMAX]      one-phase all-reduce (small grids), double-buffered
-    unsigned long long* dpart;   // [2][MAXC][DMAX] scalar sums (error norms), double-buffered
+    unsigned long long* dpart;   // [MAXC][DMAX]   scalar sums (error norms): per-CTA partials
+    unsigned long long* dres;    // [R][DMAX]      scalar sums: totals, R replicas
 };
 static inline __host__ __device__ size_t phx_ll_words() {
-    return 8 + (size_t)PHX_LL_MAXC * PHX_LL_NMAX + PHX_LL_NMAX + 2 * (size_t)PHX_LL_YMAX +
-           2 * (size_t)PHX_LL_MAXC * PHX_LL_DMAX;
+    return 8 + (size_t)PHX_LL_MAXC * PHX_LL_NMAX + (size_t)PHX_LL_RCOPIES * PHX_LL_NMAX + 2 * (size_t)PHX_LL_YMAX +
+           (size_t)PHX_LL_MAXC * PHX_LL_DMAX + (size_t)PHX_LL_RCOPIES * PHX_LL_DMAX;
 }
 static inline __host__ __device__ PhxLL phx_ll_view(void* base) {
     PhxLL v;
     unsigned long long* p = reinterpret_cast<unsigned long long*>(base);
     v.epoch = p; p += 8;
     v.xpart = p; p += (size_t)PHX_LL_MAXC * PHX_LL_NMAX;
-    v.xres = p; p += PHX_LL_NMAX;
+    v.xres = p; p += (size_t)PHX_LL_RCOPIES * PHX_LL_NMAX;
     v.ypart = p; p += 2 * (size_t)PHX_LL_YMAX;
-    v.dpart = p;
+    v.dpart = p; p += (size_t)PHX_LL_MAXC * PHX_LL_DMAX;
+    v.dres = p;
     return v;
 }
 
-// Byte offsets of the resident kernels' shared-memory views (0xffffffff: not present), computed by phx_smem_layout.
+// Byte offsets of the resident kernels' shared-memory views (PHX_NONE: not present), computed by phx_smem_layout.
+#define PHX_NONE 0xffffffffu
+#define PHX_RED_WARPS 8   /* slots of the cross-warp column-sum buffer (16 warps fold into 8, then 8 -> 1) */
 struct SmemOff {
-    unsigned ring, bar, ctrl, dred, gram, dstage, ystage, bias, relum, maskm, sp, gsp, red, st;
+    unsigned w1r, war;   // this CTA's gpc rows of W1 / WA when they stay resident in shared memory for the whole solve
+    unsigned ring, bar, resbar, ctrl, dred, gram, dst16, ystage, bias, relum, maskm, sp, xv, red, st;
     unsigned acts, actl, ysb, jb, acts2, actl2, ysb2, asb, gjb, ub, vb, mt;
     unsigned FG, FSP, FS, FL, FGJ, FM;
 };
 #define PHX_CTRL_BYTES 1024  /* >= sizeof(Ctrl) in phx_resident.cuh (static_assert there) */
 
 static inline int phx_QB(int B) { return (7 * (B > 1 ? 4 : 1) + 3) & ~3; }
-static inline bool phx_use_y(int nCTA, int B, int K2) { return (size_t)nCTA * B * K2 <= 4096; }
+static inline bool phx_use_y(int nCTA, int B, int K2, int adjoint) {
+    return (size_t)nCTA * B * K2 * (adjoint ? 2 : 1) <= 4096;
+}
 
-static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoint, int ring_rows, int ring_stages,
-                                     SmemOff* o) {
+static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoint, int w1_res, int wa_res,
+                                     int ring_rows, int ring_stages, SmemOff* o) {
     size_t off = 0;
     auto take = [&](size_t bytes) {
         size_t at = off;
@@ -117,22 +126,27 @@ static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoi
         return (unsigned)at;
     };
     SmemOff t;
-    const unsigned none = 0xffffffffu;
+    const unsigned none = PHX_NONE;
     const int QB = phx_QB(B);
     const size_t bl = sizeof(float) * B * gpc;
-    t.ring = take(sizeof(float) * (size_t)ring_stages * ring_rows * K2);  // first: 128-byte aligned bulk-copy target
-    t.bar = take(sizeof(unsigned long long) * ring_stages);
+    const size_t slice = sizeof(float) * (size_t)gpc * K2;
+    // bulk-copy targets first (128-byte aligned: every size below is a multiple of 32 bytes)
+    t.w1r = w1_res ? take(slice) : none;
+    t.war = wa_res ? take(slice) : none;
+    t.ring = ring_stages ? take(sizeof(float) * (size_t)ring_stages * ring_rows * K2) : none;
+    t.bar = take(sizeof(unsigned long long) * (ring_stages ? ring_stages : 1));
+    t.resbar = take(sizeof(unsigned long long));
     t.ctrl = take(PHX_CTRL_BYTES);
     t.dred = take(sizeof(double) * PHX_WARPS * 8);
     t.gram = adjoint ? take(sizeof(double) * 128) : none;
-    t.dstage = take(sizeof(float) * nCTA * PHX_LL_DMAX);
-    t.ystage = phx_use_y(nCTA, B, K2) ? take(sizeof(float) * (size_t)nCTA * B * K2) : none;
+    t.dst16 = take(sizeof(float) * PHX_LL_DMAX);
+    t.ystage = phx_use_y(nCTA, B, K2, adjoint) ? take(sizeof(float) * (size_t)nCTA * B * K2 * (adjoint ? 2 : 1)) : none;
     t.bias = take(sizeof(float) * K2);
     t.relum = take(sizeof(float) * gpc);
     t.maskm = take(sizeof(float) * gpc);
     t.sp = take(sizeof(float) * B * K2);
-    t.gsp = adjoint ? take(sizeof(float) * B * K2) : none;
-    t.red = take(sizeof(float) * PHX_WARPS * K2);
+    t.xv = adjoint ? take(sizeof(float) * 2 * B * K2) : none;   // [gS|gLP partial][next stage's S|P partial]
+    t.red = take(sizeof(float) * PHX_RED_WARPS * K2);
     t.st = take((adjoint ? 18 : 9) * bl);
     t.acts = take(bl); t.actl = take(bl); t.ysb = take(bl); t.jb = take(bl);
     t.acts2 = t.actl2 = t.ysb2 = t.asb = t.gjb = t.ub = t.vb = t.mt = none;
@@ -182,7 +196,7 @@ struct ResParams {
 #define PHX_T_INLINE 16
 
 struct ResLaunchPlan {
-    int nCTA, gpc, NV, ring_rows, ring_stages;
+    int nCTA, gpc, NV, ring_rows, ring_stages, w1_res, wa_res;
     size_t smem_bytes;
     SmemOff so;
 };

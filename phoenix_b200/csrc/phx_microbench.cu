@@ -39,19 +39,80 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) mb_sumd_kernel(const __grid_co
 
 // iters x one streamed pass over this CTA's rows of W1 (column accumulation only)
 template <int NV>
-__global__ void __launch_bounds__(PHX_THREADS, 1) mb_pass_kernel(const __grid_constant__ ResParams p, int iters,
-                                                                 float* out) {
+__global__ void __launch_bounds__(PHX_THREADS, 1) mb_pass_kernel(const __grid_constant__ ResParams p, int which,
+                                                                 int iters, float* out) {
     Smem s(p);
     s.rg.par = 0;
     s.rg.pre_mat = nullptr;
     ring_init(p, s);
+    resident_wait(p, s);
     for (int i = threadIdx.x; i < p.B * p.gpc; i += THREADS) { s.acts()[i] = 1.f; s.actl()[i] = 0.5f; }
+    for (int i = threadIdx.x; i < p.B * p.K2; i += THREADS) s.sp()[i] = 1.f;
     __syncthreads();
-    for (int it = 0; it < iters; ++it) passA<NV, 1>(p, s);
+    for (int it = 0; it < iters; ++it) {
+        if (which == MAT_W1) passA<NV, 1>(p, s, s.acts(), s.actl(), s.sp(), MAT_W1);
+        else passB<NV, 1, false>(p, s, MAT_WA);
+    }
+    ring_drain(p, s);
     if (threadIdx.x < p.K2) out[(size_t)blockIdx.x * p.K2 + threadIdx.x] = s.sp()[threadIdx.x];
 }
 
+// raw hop latency: CTA 0 and CTA `peer` bounce one tagged slot back and forth
+__global__ void mb_pingpong_kernel(unsigned long long* slots, int peer, int iters, long long* out) {
+    if (threadIdx.x != 0) return;
+    if (blockIdx.x != 0 && blockIdx.x != peer) return;
+    long long t0 = clock64();
+    for (int it = 1; it <= iters; ++it) {
+        if (blockIdx.x == 0) {
+            ll_put(slots, 1.f, (unsigned)it);
+            ll_get(slots + 64, (unsigned)it);
+        } else {
+            ll_get(slots, (unsigned)it);
+            ll_put(slots + 64, 1.f, (unsigned)it);
+        }
+    }
+    if (blockIdx.x == 0) out[0] = clock64() - t0;
+}
+
+// one-hop all-to-all flag barrier: every CTA posts one slot, warp 0 of every CTA polls all of them
+__global__ void mb_barrier_kernel(unsigned long long* slots, int iters, long long* out) {
+    const int nC = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long t0 = clock64();
+    for (int it = 1; it <= iters; ++it) {
+        unsigned long long* base = slots + (size_t)(it & 1) * 4096;
+        if (threadIdx.x == 0) ll_put(base + blockIdx.x * 16, 1.f, (unsigned)it);   // one 128-byte line per CTA
+        if (warp == 0)
+            for (int c = lane; c < nC; c += 32) ll_get(base + c * 16, (unsigned)it);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+
+// same, but all flags packed densely (8 bytes apart)
+__global__ void mb_barrier_dense_kernel(unsigned long long* slots, int iters, long long* out) {
+    const int nC = gridDim.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    long long t0 = clock64();
+    for (int it = 1; it <= iters; ++it) {
+        unsigned long long* base = slots + (size_t)(it & 1) * 4096;
+        if (threadIdx.x == 0) ll_put(base + blockIdx.x, 1.f, (unsigned)it);
+        if (warp == 0)
+            for (int c = lane; c < nC; c += 32) ll_get(base + c, (unsigned)it);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = clock64() - t0;
+}
+
 }  // namespace
+
+extern "C" int phx_microbench_sync(int what, int nCTA, int peer, int iters, void* slots, long long* out, void* stream) {
+    if (what == 0) mb_pingpong_kernel<<<nCTA, 32, 0, (cudaStream_t)stream>>>((unsigned long long*)slots, peer, iters, out);
+    else {
+        void* args[] = {&slots, &iters, &out};
+        cudaLaunchCooperativeKernel(what == 1 ? (const void*)mb_barrier_kernel : (const void*)mb_barrier_dense_kernel,
+                                    dim3(nCTA), dim3(128), args, 0, (cudaStream_t)stream);
+    }
+    return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
 
 extern "C" int phx_microbench(phx_ctx* ctx, int G, int H, int B, int what, int n, int iters, const float* packed,
                               void* workspace, size_t workspace_bytes, float* out, void* stream) {
@@ -65,7 +126,8 @@ extern "C" int phx_microbench(phx_ctx* ctx, int G, int H, int B, int what, int n
     p.w = phx_packed_view(packed, G, H);
     p.ll = phx_ll_view(workspace);
     void* args3[] = {&p, &n, &iters, &out};
-    void* args2[] = {&p, &iters, &out};
+    int which = (what == 2) ? MAT_W1 : MAT_WA;
+    void* args2[] = {&p, &which, &iters, &out};
     const void* fn;
     void** args;
     if (what == 0) { fn = (const void*)mb_allreduce_kernel; args = args3; }

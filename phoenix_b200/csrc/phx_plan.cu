@@ -31,31 +31,53 @@ int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPl
     plan->nCTA = nCTA;
     plan->gpc = gpc;
     plan->NV = NV;
-    // weight-streaming ring: chunks of whole rows (a multiple of the 16 warps), as many stages as shared memory
-    // allows up to 4 (or the whole slice); prefer >= 16 KB per chunk so few bulk copies are in flight per pass
+    // Where the CTA's two weight slices live.  Preference: both resident in shared memory for the whole solve (every
+    // pass is a shared-memory pass; all shipped configs up to the yeast shape) -> W1 resident (it is read twice per
+    // VJP evaluation) and WA streamed from L2 through the ring (the 11k-gene breast shape) -> both streamed.
+    // Ring geometry: chunks of whole rows, at most 32 KB per chunk, 2..4 chunks in flight; most row-stages wins.
     const size_t row_bytes = (size_t)K2 * sizeof(float);
-    const int rows_cap = (gpc + PHX_WARPS - 1) / PHX_WARPS * PHX_WARPS;
-    int best_rows = 0, best_stages = 0;
-    for (int rows = PHX_WARPS * 4; rows >= PHX_WARPS && !best_rows; rows /= 2) {
-        int r = rows < rows_cap ? rows : rows_cap;
-        if (r * row_bytes > 32 * 1024 && r > PHX_WARPS) continue;
-        const int nch = (gpc + r - 1) / r;
-        for (int stages = (nch < 4 ? nch : 4); stages >= 1; --stages) {
-            if (stages == 1 && nch > 1) continue;  // needs double buffering to stream
-            if (phx_smem_layout(nCTA, B, K2, gpc, adjoint, r, stages, nullptr) <= PHX_SMEM_LIMIT) {
-                best_rows = r;
-                best_stages = stages;
+    auto fits = [&](int w1r, int war, int rows, int stages) {
+        return phx_smem_layout(nCTA, B, K2, gpc, adjoint, w1r, war, rows, stages, nullptr) <= PHX_SMEM_LIMIT;
+    };
+    int w1r = 0, war = 0, best_rows = 0, best_stages = 0;
+    bool ok = false;
+    if (fits(1, 1, 0, 0)) {
+        w1r = war = 1;
+        ok = true;
+    }
+    for (int res = 1; res >= 0 && !ok; --res) {
+        const int rows_cap = (gpc + 7) / 8 * 8;
+        int best = 0;
+        for (int rows = 64; rows >= 8; rows /= 2) {
+            int r = rows < rows_cap ? rows : rows_cap;
+            if (r * row_bytes > 32 * 1024 && r > 8) continue;
+            const int nch = (gpc + r - 1) / r;
+            for (int stages = (nch < 4 ? nch : 4); stages >= 1; --stages) {
+                if (stages == 1 && nch > 1) continue;  // needs double buffering to stream
+                if (!fits(res, 0, r, stages)) continue;
+                if (r * stages > best) {
+                    best = r * stages;
+                    best_rows = r;
+                    best_stages = stages;
+                }
                 break;
             }
         }
+        if (best) {
+            w1r = res;
+            war = 0;
+            ok = true;
+        }
     }
-    if (!best_rows) {
+    if (!ok) {
         phx_set_error("resident solver does not fit in %d B shared memory for G=%d H=%d B=%d", PHX_SMEM_LIMIT, G, H, B);
         return PHX_ERR_UNSUPPORTED;
     }
+    plan->w1_res = w1r;
+    plan->wa_res = war;
     plan->ring_rows = best_rows;
     plan->ring_stages = best_stages;
-    plan->smem_bytes = phx_smem_layout(nCTA, B, K2, gpc, adjoint, best_rows, best_stages, &plan->so);
+    plan->smem_bytes = phx_smem_layout(nCTA, B, K2, gpc, adjoint, w1r, war, best_rows, best_stages, &plan->so);
     return PHX_OK;
 }
 

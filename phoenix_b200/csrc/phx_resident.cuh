@@ -74,6 +74,7 @@ enum {
     PT_SETUP = 0, PT_PHASE_A, PT_ALLRED1, PT_FINALIZE, PT_PHASE_B, PT_ALLRED2, PT_GSP, PT_PHASE_C, PT_EPILOGUE,
     PT_COMBINE, PT_PP_D01, PT_PP_D2, PT_PP_STEP, PT_PP_INTERP, PT_PP_COPY, PT_NORMS, PT_CTRL, PT_TOTAL, PT_COUNT
 };
+static_assert(PHX_LL_RCOPIES * 4 == 32, "replica posting assumes 8 replicas");
 static_assert(sizeof(Ctrl) <= 512 && 512 + 8 * PT_COUNT <= PHX_CTRL_BYTES, "PHX_CTRL_BYTES too small");
 struct Prof {
     long long* gbuf;   // global accumulators (thread 0 of CTA 0 only, else nullptr)
@@ -139,6 +140,22 @@ __device__ __forceinline__ float ll_get(const unsigned long long* slot, unsigned
     while ((unsigned)(w >> 32) != tag) w = ll_ld(slot);
     return __uint_as_float((unsigned)w);
 }
+// two adjacent slots in one 16-byte access (each 8-byte half is single-copy atomic and carries its own tag)
+__device__ __forceinline__ void ll_put2(unsigned long long* slot, float v0, float v1, unsigned tag) {
+    unsigned long long w0 = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v0);
+    unsigned long long w1 = ((unsigned long long)tag << 32) | (unsigned long long)__float_as_uint(v1);
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(slot), "l"(w0), "l"(w1) : "memory");
+}
+__device__ __forceinline__ void ll_ld2(const unsigned long long* slot, unsigned long long& w0, unsigned long long& w1) {
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(w0), "=l"(w1) : "l"(slot) : "memory");
+}
+__device__ __forceinline__ void ll_get2(const unsigned long long* slot, unsigned tag, float& v0, float& v1) {
+    unsigned long long w0, w1;
+    ll_ld2(slot, w0, w1);
+    while ((unsigned)(w0 >> 32) != tag || (unsigned)(w1 >> 32) != tag) ll_ld2(slot, w0, w1);
+    v0 = __uint_as_float((unsigned)w0);
+    v1 = __uint_as_float((unsigned)w1);
+}
 
 
 // ---- shared-memory carve-up ---------------------------------------------------------------------------------------
@@ -183,14 +200,18 @@ struct Smem {
     __device__ __forceinline__ Ctrl* ctrl() const { return at<Ctrl>(p.so.ctrl); }
     __device__ __forceinline__ double* dred() const { return at<double>(p.so.dred); }      // [WARPS][8]
     __device__ __forceinline__ double* gram() const { return at<double>(p.so.gram); }      // [2][64]   (adjoint)
-    __device__ __forceinline__ float* dstage() const { return at<float>(p.so.dstage); }    // [nCTA][PHX_LL_DMAX]
+    __device__ __forceinline__ float* dst16() const { return at<float>(p.so.dst16); }      // [PHX_LL_DMAX]
     __device__ __forceinline__ float* ystage() const { return at<float>(p.so.ystage); }    // [nCTA*B*K2] if use_y
     __device__ __forceinline__ float* bias() const { return at<float>(p.so.bias); }        // [K2]
     __device__ __forceinline__ float* relum() const { return at<float>(p.so.relum); }      // [gpc]
     __device__ __forceinline__ float* maskm() const { return at<float>(p.so.maskm); }      // [gpc]
     __device__ __forceinline__ float* sp() const { return at<float>(p.so.sp); }            // [B][K2]  S | Pr
-    __device__ __forceinline__ float* gsp() const { return at<float>(p.so.gsp); }          // [B][K2]  gS | gLP
-    __device__ __forceinline__ float* red() const { return at<float>(p.so.red); }          // [WARPS][K2]
+    __device__ __forceinline__ float* xv() const { return at<float>(p.so.xv); }            // [2][B][K2] exchange vector
+    __device__ __forceinline__ float* gsp() const { return at<float>(p.so.xv); }           // [B][K2]  gS | gLP  (= xv[0])
+    __device__ __forceinline__ float* spn() const { return at<float>(p.so.xv) + p.B * p.K2; }  // next S|P (= xv[1])
+    __device__ __forceinline__ float* red() const { return at<float>(p.so.red); }          // [PHX_RED_WARPS][K2]
+    __device__ __forceinline__ const float4* w1g() const { return p.w.W1 + (size_t)g_lo * p.K2q; }  // my rows, global
+    __device__ __forceinline__ const float4* wag() const { return p.w.WA + (size_t)g_lo * p.K2q; }
     __device__ __forceinline__ float* st() const { return at<float>(p.so.st); }            // [nslots][B][gpc]
     __device__ __forceinline__ float* jb() const { return at<float>(p.so.jb); }            // [B][gpc] ...
     __device__ __forceinline__ float* asb() const { return at<float>(p.so.asb); }
@@ -240,70 +261,88 @@ __device__ __noinline__ void block_sum_d(double (&v)[N], double* dred, double* o
 }
 
 // Sum over all CTAs of the nd (<= 8) doubles in vals[] (smem); the result replaces vals[] in every CTA.  Each double
-// travels as two fp32 slots (hi, lo = x - hi: 48 significant bits); every CTA adds the nCTA contributions in the same
-// order.
+// travels as two fp32 slots (hi, lo = x - hi: 48 significant bits).  Two hops: every CTA posts its partials, CTA 0
+// adds them in a fixed order (one warp per value, lanes over CTAs, fixed butterfly) and posts the totals in R
+// replicas, every CTA reads one replica: each hop is one L2 round trip and no slot is polled by more than nCTA / R
+// readers.
 __device__ __noinline__ void grid_sum_d(const ResParams& p, Smem& s, double* vals, int nd) {
     Xchg& x = s.x;
     const int nC = gridDim.x;
     if (nC == 1) return;
     const unsigned tag = x.next_tag();
-    unsigned long long* base = p.ll.dpart + (size_t)(x.nd & 1) * PHX_LL_MAXC * PHX_LL_DMAX;
-    x.nd++;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x < 2 * nd) {
         double v = vals[threadIdx.x >> 1];
         float hi = (float)v;
         float w = (threadIdx.x & 1) ? (float)(v - (double)hi) : hi;
         if (!isfinite(hi)) w = hi;  // inf / nan: both halves carry it
-        ll_put(base + (size_t)blockIdx.x * PHX_LL_DMAX + threadIdx.x, w, tag);
+        ll_put(p.ll.dpart + (size_t)blockIdx.x * PHX_LL_DMAX + threadIdx.x, w, tag);
     }
-    const int per = 2 * nd, tot = nC * per;
-    for (int e = threadIdx.x; e < tot; e += THREADS) {
-        int c = e / per, i = e - c * per;
-        s.dstage()[c * PHX_LL_DMAX + i] = ll_get(base + (size_t)c * PHX_LL_DMAX + i, tag);
-    }
-    __syncthreads();
-    {   // one warp per value: lanes over CTAs (fixed assignment), fixed butterfly
-        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        if (warp < nd) {
-            double t = 0;
-            for (int c = lane; c < nC; c += 32) {
-                float hi = s.dstage()[c * PHX_LL_DMAX + 2 * warp], lo = s.dstage()[c * PHX_LL_DMAX + 2 * warp + 1];
+    if (blockIdx.x == 0 && warp < nd) {
+        unsigned long long w0[5], w1[5];
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            int c = lane + 32 * u;
+            if (c < nC) ll_ld2(p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * warp, w0[u], w1[u]);
+        }
+        double t = 0;
+#pragma unroll
+        for (int u = 0; u < 5; ++u) {
+            int c = lane + 32 * u;
+            if (c < nC) {
+                const unsigned long long* src = p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * warp;
+                while ((unsigned)(w0[u] >> 32) != tag || (unsigned)(w1[u] >> 32) != tag) ll_ld2(src, w0[u], w1[u]);
+                float hi = __uint_as_float((unsigned)w0[u]), lo = __uint_as_float((unsigned)w1[u]);
                 t += isfinite(hi) ? ((double)hi + (double)lo) : (double)hi;
             }
-            t = warp_sum_d(t);
-            if (lane == 0) vals[warp] = t;
         }
+        t = warp_sum_d(t);
+        if (lane < PHX_LL_RCOPIES) {
+            float hi = (float)t;
+            float lo = isfinite(hi) ? (float)(t - (double)hi) : hi;
+            ll_put2(p.ll.dres + (size_t)lane * PHX_LL_DMAX + 2 * warp, hi, lo, tag);
+        }
+    }
+    if (threadIdx.x < 2 * nd)
+        s.dst16()[threadIdx.x] =
+            ll_get(p.ll.dres + (size_t)(blockIdx.x % PHX_LL_RCOPIES) * PHX_LL_DMAX + threadIdx.x, tag);
+    __syncthreads();
+    if (threadIdx.x < nd) {
+        float hi = s.dst16()[2 * threadIdx.x], lo = s.dst16()[2 * threadIdx.x + 1];
+        vals[threadIdx.x] = isfinite(hi) ? ((double)hi + (double)lo) : (double)hi;
     }
     __syncthreads();
 }
 
 // Sum over all CTAs of the n-float vector vec[] (smem, n a multiple of 4); the result replaces vec[] in every CTA.
 // Small grids: one phase (every CTA reads every partial).  Large grids: reduce-scatter by column quads (one warp per
-// quad, lanes over CTAs, fixed butterfly) then all-gather of the n results.
+// quad, lanes over CTAs, fixed butterfly), the reduced quads posted in R replicas, then all-gather from one replica.
 __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, float* vec, int n) {
     Xchg& x = s.x;
     const int nC = gridDim.x;
     if (nC == 1) return;
     const unsigned tag = x.next_tag();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (p.so.ystage != 0xffffffffu) {
+    if (p.so.ystage != PHX_NONE) {
         unsigned long long* base = p.ll.ypart + (size_t)(x.ny & 1) * PHX_LL_YMAX;
         x.ny++;
-        for (int i = threadIdx.x; i < n; i += THREADS) ll_put(base + (size_t)blockIdx.x * n + i, vec[i], tag);
+        for (int i = 2 * threadIdx.x; i < n; i += 2 * THREADS) ll_put2(base + (size_t)blockIdx.x * n + i, vec[i], vec[i + 1], tag);
         const int tot = nC * n;
-        for (int e0 = threadIdx.x; e0 < tot; e0 += 4 * THREADS) {
-            unsigned long long w[4];
+        for (int e0 = 2 * threadIdx.x; e0 < tot; e0 += 8 * THREADS) {
+            unsigned long long w[4][2];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                int e = e0 + u * THREADS;
-                if (e < tot) w[u] = ll_ld(base + e);
+                int e = e0 + u * 2 * THREADS;
+                if (e < tot) ll_ld2(base + e, w[u][0], w[u][1]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                int e = e0 + u * THREADS;
+                int e = e0 + u * 2 * THREADS;
                 if (e < tot) {
-                    while ((unsigned)(w[u] >> 32) != tag) w[u] = ll_ld(base + e);
-                    s.ystage()[e] = __uint_as_float((unsigned)w[u]);
+                    while ((unsigned)(w[u][0] >> 32) != tag || (unsigned)(w[u][1] >> 32) != tag)
+                        ll_ld2(base + e, w[u][0], w[u][1]);
+                    s.ystage()[e] = __uint_as_float((unsigned)w[u][0]);
+                    s.ystage()[e + 1] = __uint_as_float((unsigned)w[u][1]);
                 }
             }
         }
@@ -317,7 +356,7 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
         return;
     }
     unsigned long long* mine = p.ll.xpart + (size_t)blockIdx.x * PHX_LL_NMAX;
-    for (int i = threadIdx.x; i < n; i += THREADS) ll_put(mine + i, vec[i], tag);
+    for (int i = 2 * threadIdx.x; i < n; i += 2 * THREADS) ll_put2(mine + i, vec[i], vec[i + 1], tag);
     const int nq = n >> 2;
     for (int q = blockIdx.x + nC * warp; q < nq; q += nC * WARPS) {
         unsigned long long w[5][4];
@@ -326,8 +365,8 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
             int c = lane + 32 * u;
             if (c < nC) {
                 const unsigned long long* src = p.ll.xpart + (size_t)c * PHX_LL_NMAX + 4 * q;
-#pragma unroll
-                for (int e = 0; e < 4; ++e) w[u][e] = ll_ld(src + e);
+                ll_ld2(src, w[u][0], w[u][1]);
+                ll_ld2(src + 2, w[u][2], w[u][3]);
             }
         }
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -336,9 +375,9 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
             int c = lane + 32 * u;
             if (c < nC) {
                 const unsigned long long* src = p.ll.xpart + (size_t)c * PHX_LL_NMAX + 4 * q;
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    while ((unsigned)(w[u][e] >> 32) != tag) w[u][e] = ll_ld(src + e);
+                while ((unsigned)(w[u][0] >> 32) != tag || (unsigned)(w[u][1] >> 32) != tag) ll_ld2(src, w[u][0], w[u][1]);
+                while ((unsigned)(w[u][2] >> 32) != tag || (unsigned)(w[u][3] >> 32) != tag)
+                    ll_ld2(src + 2, w[u][2], w[u][3]);
                 a0 += __uint_as_float((unsigned)w[u][0]);
                 a1 += __uint_as_float((unsigned)w[u][1]);
                 a2 += __uint_as_float((unsigned)w[u][2]);
@@ -349,63 +388,22 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
         a1 = warp_sum(a1);
         a2 = warp_sum(a2);
         a3 = warp_sum(a3);
-        if (lane < 4) ll_put(p.ll.xres + 4 * q + lane, lane == 0 ? a0 : (lane == 1 ? a1 : (lane == 2 ? a2 : a3)), tag);
+        // lane l posts element (l & 3) of replica (l >> 2): 32 lanes = 8 replicas x 4 elements
+        const int e = lane & 3;
+        ll_put(p.ll.xres + (size_t)(lane >> 2) * PHX_LL_NMAX + 4 * q + e, e == 0 ? a0 : (e == 1 ? a1 : (e == 2 ? a2 : a3)),
+               tag);
     }
-    for (int i = threadIdx.x; i < n; i += THREADS) vec[i] = ll_get(p.ll.xres + i, tag);
+    const unsigned long long* res = p.ll.xres + (size_t)(blockIdx.x % PHX_LL_RCOPIES) * PHX_LL_NMAX;
+    for (int i = 2 * threadIdx.x; i < n; i += 2 * THREADS) ll_get2(res + i, tag, vec[i], vec[i + 1]);
     __syncthreads();
 }
 
-// ---- weight streaming: ring of shared-memory stages filled by 1-D TMA bulk copies --------------------------------------
+// ---- weight access: slices resident in shared memory, or a ring of stages filled by 1-D TMA bulk copies ---------------
+// A CTA's rows of W1 / WA are one contiguous block of global memory.  If the plan found room, a slice is copied into
+// shared memory ONCE (prologue) and every pass over it is a shared-memory pass; otherwise its passes stream the slice
+// from L2 through the ring (cp.async.bulk + mbarrier), the first chunks of the next streamed pass prefetched across
+// the inter-CTA exchange that precedes it.
 __device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
-
-
-__device__ __forceinline__ void ring_init(const ResParams& p, const Smem& s) {
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < p.ring_stages; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s.bar() + i)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-}
-
-// thread 0 only: chunk c of the n_rows x K2q matrix `mat` -> stage c % S
-__device__ __forceinline__ void ring_issue(const ResParams& p, const Smem& s, const float4* mat, int n_rows, int c) {
-    const int st = c % p.ring_stages;
-    const int rows = min(p.ring_rows, n_rows - c * p.ring_rows);
-    const unsigned bytes = (unsigned)rows * p.K2q * 16u;
-    const unsigned bar = smem_u32(s.bar() + st);
-    const unsigned dst = smem_u32(s.ring() + (size_t)st * p.ring_rows * p.K2q);
-    const float4* src = mat + (size_t)c * p.ring_rows * p.K2q;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-                 "l"(src), "r"(bytes), "r"(bar)
-                 : "memory");
-}
-
-// start the first chunks of the next pass (call right after a pass, before waiting on an exchange)
-__device__ __forceinline__ void ring_prefetch(const ResParams& p, Smem& s, const float4* mat, int n_rows) {
-    Ring& r = s.rg;
-    if (n_rows <= 0) return;
-    if (threadIdx.x == 0) {
-        const int nch = (n_rows + p.ring_rows - 1) / p.ring_rows;
-        for (int c = 0; c < min(nch, p.ring_stages); ++c) ring_issue(p, s, mat, n_rows, c);
-    }
-    r.pre_mat = mat;
-}
-
-__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity);
-
-// wait for a prefetch nobody will consume (end of the kernel): no bulk copy may be in flight when the CTA exits
-__device__ __forceinline__ void ring_drain(const ResParams& p, Smem& s, int n_rows) {
-    Ring& r = s.rg;
-    if (r.pre_mat == nullptr || n_rows <= 0) return;
-    const int nch = (n_rows + p.ring_rows - 1) / p.ring_rows;
-    for (int c = 0; c < min(nch, p.ring_stages); ++c) {
-        mbar_wait(smem_u32(s.bar() + c), (r.par >> c) & 1u);
-        r.par ^= 1u << c;
-    }
-    r.pre_mat = nullptr;
-}
 
 __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     unsigned done = 0;
@@ -422,16 +420,111 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
     }
 }
 
-// One pass over this CTA's n_rows rows of `mat`: fn(j, row) is called by one warp (all lanes) per row j with the row
-// in shared memory.
-template <typename RowFn>
-__device__ __forceinline__ void stream_pass(const ResParams& p, Smem& s, const float4* mat, int n_rows, RowFn fn) {
+__device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned bytes, unsigned bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+
+enum { MAT_W1 = 0, MAT_WA = 1, MAT_NONE = -1 };
+
+__device__ __forceinline__ bool mat_resident(const ResParams& p, int which) {
+    return (which == MAT_W1 ? p.so.w1r : p.so.war) != PHX_NONE;
+}
+__device__ __forceinline__ const float4* mat_global(const Smem& s, int which) { return which == MAT_W1 ? s.w1g() : s.wag(); }
+
+// barriers + the one-time copy of the resident slices (all threads wait for it before the first pass)
+__device__ __forceinline__ void ring_init(const ResParams& p, const Smem& s) {
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < p.ring_stages; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s.bar() + i)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s.at<unsigned long long>(p.so.resbar))));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const unsigned bytes = (unsigned)s.n_loc * p.K2q * 16u;
+        const unsigned nres = (p.so.w1r != PHX_NONE ? 1u : 0u) + (p.so.war != PHX_NONE ? 1u : 0u);
+        if (nres && bytes) {
+            const unsigned bar = smem_u32(s.at<unsigned long long>(p.so.resbar));
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes * nres) : "memory");
+            if (p.so.w1r != PHX_NONE) bulk_g2s(smem_u32(smem_raw + p.so.w1r), s.w1g(), bytes, bar);
+            if (p.so.war != PHX_NONE) bulk_g2s(smem_u32(smem_raw + p.so.war), s.wag(), bytes, bar);
+        }
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void resident_wait(const ResParams& p, const Smem& s) {
+    if ((p.so.w1r != PHX_NONE || p.so.war != PHX_NONE) && s.n_loc > 0)
+        mbar_wait(smem_u32(s.at<unsigned long long>(p.so.resbar)), 0u);
+}
+
+// thread 0 only: chunk c of the n_rows x K2q matrix `mat` -> stage c % S
+__device__ __forceinline__ void ring_issue(const ResParams& p, const Smem& s, const float4* mat, int n_rows, int c) {
+    const int st = c % p.ring_stages;
+    const int rows = min(p.ring_rows, n_rows - c * p.ring_rows);
+    const unsigned bytes = (unsigned)rows * p.K2q * 16u;
+    const unsigned bar = smem_u32(s.bar() + st);
+    const unsigned dst = smem_u32(s.ring() + (size_t)st * p.ring_rows * p.K2q);
+    const float4* src = mat + (size_t)c * p.ring_rows * p.K2q;
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    bulk_g2s(dst, src, bytes, bar);
+}
+
+// wait for a prefetch nobody will consume (end of the kernel, or a change of plan): no bulk copy may be in flight
+// when the CTA exits or when the ring is re-targeted
+__device__ __forceinline__ void ring_drain(const ResParams& p, Smem& s) {
     Ring& r = s.rg;
-    if (n_rows <= 0) return;
+    const int n_rows = s.n_loc;
+    if (r.pre_mat == nullptr || n_rows <= 0) return;
+    const int nch = (n_rows + p.ring_rows - 1) / p.ring_rows;
+    for (int c = 0; c < min(nch, p.ring_stages); ++c) {
+        mbar_wait(smem_u32(s.bar() + c), (r.par >> c) & 1u);
+        r.par ^= 1u << c;
+    }
+    r.pre_mat = nullptr;
+    __syncthreads();
+}
+
+// start the first chunks of the next STREAMED pass.  `hint` is the matrix the next pass in program order reads; when
+// it is resident the only other candidate is the next streamed one (at most one matrix streams in that case).
+__device__ __forceinline__ void ring_prefetch(const ResParams& p, Smem& s, int hint) {
+    Ring& r = s.rg;
+    if (hint == MAT_NONE || p.ring_stages == 0 || s.n_loc <= 0 || r.pre_mat != nullptr) return;
+    int which = hint;
+    if (mat_resident(p, which)) which = (hint == MAT_W1) ? MAT_WA : MAT_W1;
+    if (mat_resident(p, which)) return;
+    const float4* mat = mat_global(s, which);
+    if (threadIdx.x == 0) {
+        const int nch = (s.n_loc + p.ring_rows - 1) / p.ring_rows;
+        for (int c = 0; c < min(nch, p.ring_stages); ++c) ring_issue(p, s, mat, s.n_loc, c);
+    }
+    r.pre_mat = mat;
+}
+
+// One pass over this CTA's rows of W1 / WA: fn(j, row) is called by one warp (all lanes) per row j with the row in
+// shared memory.  `next`: the matrix the following pass reads (MAT_NONE: unknown), for the prefetch.
+// Ends with a block barrier.
+template <typename RowFn>
+__device__ __forceinline__ void mat_pass(const ResParams& p, Smem& s, int which, int next, RowFn fn) {
+    Ring& r = s.rg;
+    const int n_rows = s.n_loc;
     const int warp = threadIdx.x >> 5;
+    const unsigned roff = (which == MAT_W1) ? p.so.w1r : p.so.war;
+    if (roff != PHX_NONE) {
+        const float4* base = s.at<float4>(roff);
+        for (int rr = warp; rr < n_rows; rr += WARPS) fn(rr, base + (size_t)rr * p.K2q);
+        __syncthreads();
+        return;
+    }
+    if (n_rows <= 0) {
+        __syncthreads();
+        return;
+    }
+    const float4* mat = mat_global(s, which);
     const int R = p.ring_rows, S = p.ring_stages;
     const int nch = (n_rows + R - 1) / R;
-    if (r.pre_mat != mat) ring_prefetch(p, s, mat, n_rows);
+    if (r.pre_mat != mat) {
+        ring_drain(p, s);
+        ring_prefetch(p, s, which);
+    }
     r.pre_mat = nullptr;
     for (int c = 0; c < nch; ++c) {
         const int st = c % S;
@@ -443,6 +536,7 @@ __device__ __forceinline__ void stream_pass(const ResParams& p, Smem& s, const f
         __syncthreads();
         if (threadIdx.x == 0 && c + S < nch) ring_issue(p, s, mat, n_rows, c + S);
     }
+    ring_prefetch(p, s, next);
 }
 
 // ---- the weight passes --------------------------------------------------------------------------------------------------
@@ -457,24 +551,38 @@ __device__ __forceinline__ void acc_zero(float4 (&acc)[BT][NV]) {
         for (int v = 0; v < NV; ++v) acc[b][v] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+__device__ __forceinline__ float4 add4(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+
+// out[(b0+b)][k] = sum over the 16 warps of acc[b] (fixed order: warps w and w+8 first, then 0..7)
 template <int NV, int BT>
 __device__ __forceinline__ void acc_reduce(const ResParams& p, const Smem& s, float4 (&acc)[BT][NV], float* out, int b0, int nb) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K2q = p.K2q;
     float4* red4 = reinterpret_cast<float4*>(s.red());
+    static_assert(WARPS == 2 * PHX_RED_WARPS, "two-round fold");
 #pragma unroll
     for (int b = 0; b < BT; ++b) {
         if (b < nb) {
+            if (warp >= PHX_RED_WARPS) {
 #pragma unroll
-            for (int v = 0; v < NV; ++v) {
-                int q = lane + 32 * v;
-                if (q < K2q) red4[warp * K2q + q] = acc[b][v];
+                for (int v = 0; v < NV; ++v) {
+                    int q = lane + 32 * v;
+                    if (q < K2q) red4[(warp - PHX_RED_WARPS) * K2q + q] = acc[b][v];
+                }
+            }
+            __syncthreads();
+            if (warp < PHX_RED_WARPS) {
+#pragma unroll
+                for (int v = 0; v < NV; ++v) {
+                    int q = lane + 32 * v;
+                    if (q < K2q) red4[warp * K2q + q] = add4(acc[b][v], red4[warp * K2q + q]);
+                }
             }
             __syncthreads();
             for (int k = threadIdx.x; k < p.K2; k += THREADS) {
                 float t = 0.f;
 #pragma unroll
-                for (int w = 0; w < WARPS; ++w) t += s.red()[w * p.K2 + k];
+                for (int w = 0; w < PHX_RED_WARPS; ++w) t += s.red()[w * p.K2 + k];
                 out[(b0 + b) * p.K2 + k] = t;
             }
             __syncthreads();
@@ -514,29 +622,27 @@ __device__ __forceinline__ void axpy_row(const float4 (&w)[NV], float4 (&acc)[BT
     }
 }
 
-// Pass A: sp[b][k] (this CTA's partial) = sum_{g in slice} act[b][g] * W1[g][k], act = s for k < Hp, l for k >= Hp.
+// Pass A: out[b][k] (this CTA's partial) = sum_{g in slice} act[b][g] * W1[g][k], act = s for k < Hp, l for k >= Hp.
 template <int NV, int BT>
-__device__ __forceinline__ void passA(const ResParams& p, Smem& s) {
+__device__ __forceinline__ void passA(const ResParams& p, Smem& s, const float* acts, const float* actl, float* out,
+                                      int next) {
     const int Hq = p.Hp >> 2;
-    const int g_lo = s.g_lo, n_loc = s.n_loc;
-    const float *acts = s.acts(), *actl = s.actl();
     for (int b0 = 0; b0 < p.B; b0 += BT) {
         const int nb = min(BT, p.B - b0);
         float4 acc[BT][NV];
         acc_zero<NV, BT>(acc);
-        stream_pass(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc, [&](int j, const float4* row) {
+        mat_pass(p, s, MAT_W1, (b0 + BT < p.B) ? MAT_W1 : next, [&](int j, const float4* row) {
             float4 w[NV];
             load_row<NV>(row, p.K2q, w);
             axpy_row<NV, BT>(w, acc, acts + b0 * p.gpc, actl + b0 * p.gpc, p.gpc, j, nb, Hq);
         });
-        acc_reduce<NV, BT>(p, s, acc, s.sp(), b0, nb);
+        acc_reduce<NV, BT>(p, s, acc, out, b0, nb);
     }
 }
 
 // Pass B: jb[b][j] = sum_k WA[g][k] * sp[b][k]; adjoint additionally partial gsp[b][k] = sum_g gj[b][g] WA[g][k].
 template <int NV, int BT, bool ADJ>
-__device__ __forceinline__ void passB(const ResParams& p, Smem& s) {
-    const int g_lo = s.g_lo, n_loc = s.n_loc;
+__device__ __forceinline__ void passB(const ResParams& p, Smem& s, int next) {
     const int lane = threadIdx.x & 31;
     const int K2q = p.K2q;
     const float4* sp4 = reinterpret_cast<const float4*>(s.sp());
@@ -544,7 +650,7 @@ __device__ __forceinline__ void passB(const ResParams& p, Smem& s) {
         const int nb = min(BT, p.B - b0);
         float4 acc[BT][NV];
         if (ADJ) acc_zero<NV, BT>(acc);
-        stream_pass(p, s, p.w.WA + (size_t)g_lo * K2q, n_loc, [&](int j, const float4* row) {
+        mat_pass(p, s, MAT_WA, (b0 + BT < p.B) ? MAT_WA : next, [&](int j, const float4* row) {
             float4 w[NV];
             load_row<NV>(row, K2q, w);
 #pragma unroll
@@ -579,22 +685,17 @@ __device__ __forceinline__ void passB(const ResParams& p, Smem& s) {
         });
         if (ADJ) acc_reduce<NV, BT>(p, s, acc, s.gsp(), b0, nb);
     }
-    __syncthreads();
 }
 
-// Pass C (adjoint): ub[b][j] = sum_{k<Hp} W1[g][k] gS[b][k],  vb[b][j] = sum_{k>=Hp} W1[g][k] gLP[b][k];
-// with do_a also pass A of the NEXT stage input (activations acts2 / actl2) over the same rows -> s.sp().
+// Pass C (adjoint): ub[b][j] = sum_{k<Hp} W1[g][k] gS[b][k],  vb[b][j] = sum_{k>=Hp} W1[g][k] gLP[b][k].
 template <int NV, int BT>
-__device__ __forceinline__ void passCA(const ResParams& p, Smem& s, bool do_a) {
-    const int g_lo = s.g_lo, n_loc = s.n_loc;
+__device__ __forceinline__ void passC(const ResParams& p, Smem& s, int next) {
     const int lane = threadIdx.x & 31;
     const int K2q = p.K2q, Hq = p.Hp >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(s.gsp());
     for (int b0 = 0; b0 < p.B; b0 += BT) {
         const int nb = min(BT, p.B - b0);
-        float4 acc[BT][NV];
-        acc_zero<NV, BT>(acc);
-        stream_pass(p, s, p.w.W1 + (size_t)g_lo * K2q, n_loc, [&](int j, const float4* row) {
+        mat_pass(p, s, MAT_W1, (b0 + BT < p.B) ? MAT_W1 : next, [&](int j, const float4* row) {
             float4 w[NV];
             load_row<NV>(row, K2q, w);
 #pragma unroll
@@ -622,11 +723,8 @@ __device__ __forceinline__ void passCA(const ResParams& p, Smem& s, bool do_a) {
                     }
                 }
             }
-            if (do_a) axpy_row<NV, BT>(w, acc, s.acts2() + b0 * p.gpc, s.actl2() + b0 * p.gpc, p.gpc, j, nb, Hq);
         });
-        if (do_a) acc_reduce<NV, BT>(p, s, acc, s.sp(), b0, nb);
     }
-    __syncthreads();
 }
 
 template <typename F>
@@ -639,12 +737,12 @@ __device__ __forceinline__ void for_local(const ResParams& p, int g_lo, int n_lo
 }
 
 // branch vector after the all-reduce: add bias, exponentiate the prods half (odenet.py:86-87); padded columns -> 0
-__device__ __forceinline__ void finalize_sp(const ResParams& p, const Smem& s) {
+__device__ __forceinline__ void finalize_sp(const ResParams& p, const Smem& s, const float* src, float* dst) {
     for (int i = threadIdx.x; i < p.B * p.K2; i += THREADS) {
         int k = i % p.K2;
-        float v = s.sp()[i] + s.bias()[k];
+        float v = src[i] + s.bias()[k];
         if (k >= p.Hp) v = (k - p.Hp < p.H) ? expf(v) : 0.f;
-        s.sp()[i] = v;
+        dst[i] = v;
     }
     __syncthreads();
 }
@@ -752,6 +850,8 @@ __device__ __forceinline__ void prologue(const ResParams& p, Smem& s) {
         s.maskm()[j] = p.w.maskm[g_lo + j];
     }
     ring_init(p, s);
+    ring_prefetch(p, s, MAT_W1);
+    resident_wait(p, s);
 }
 
 __device__ __forceinline__ void epilogue_epoch(const ResParams& p, const Smem& s) {
@@ -765,15 +865,13 @@ template <int NV, int BT>
 __device__ __noinline__ void fwd_eval(const ResParams& __restrict__ p, Smem& __restrict__ s) {
     Prof& pf = s.pf;
     pf.tick(PT_COMBINE);
-    passA<NV, BT>(p, s);
-    ring_prefetch(p, s, p.w.WA + (size_t)s.g_lo * p.K2q, s.n_loc);
+    passA<NV, BT>(p, s, s.acts(), s.actl(), s.sp(), MAT_WA);
     pf.tick(PT_PHASE_A);
     grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
     pf.tick(PT_ALLRED1);
-    finalize_sp(p, s);
+    finalize_sp(p, s, s.sp(), s.sp());
     pf.tick(PT_FINALIZE);
-    passB<NV, BT, false>(p, s);
-    ring_prefetch(p, s, p.w.W1 + (size_t)s.g_lo * p.K2q, s.n_loc);
+    passB<NV, BT, false>(p, s, MAT_W1);
     pf.tick(PT_PHASE_B);
 }
 
@@ -794,7 +892,6 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     float* Y1 = s.st() + BL;
     auto K = [&](int i) { return s.st() + (2 + i) * BL; };
 
-    ring_prefetch(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc);
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
         c->stop = 0;
@@ -886,7 +983,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
             c->tcur = tget(p, p.T - 1);
         }
         __syncthreads();
-        ring_drain(p, s, n_loc);
+        ring_drain(p, s);
         pf.tick(PT_CTRL);
         pf.finish();
         epilogue_epoch(p, s);
@@ -1052,7 +1149,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
         pf.tick(PT_CTRL);
     }
     __syncthreads();
-    ring_drain(p, s, n_loc);
+    ring_drain(p, s);
     pf.tick(PT_CTRL);
     pf.finish();
     epilogue_epoch(p, s);
@@ -1333,41 +1430,27 @@ __device__ __noinline__ double theta_zero_norm(const ResParams& p, const Smem& s
     return mine / ((double)p.atol_f * (double)p.atol_f);
 }
 
-// First half of one RHS + VJP evaluation at the current stage input: passes A (unless a_done: it was merged into the
-// previous evaluation's pass C) and B with their two all-reduces; leaves ky = -f in KY(slot), the stage's theta
-// factors in column `slot` of the factor tables, gS|gLP in s.gsp().
+// First half of one RHS + VJP evaluation at the current stage input: (unless sp_ready: the branch vector of this input
+// was all-reduced together with the previous evaluation's gS|gLP) pass A + its all-reduce; then pass B; leaves
+// ky = -f in KY(slot), the stage's local theta factors in column `slot` of the factor tables and this CTA's partial
+// gS|gP in s.gsp().
 template <int NV, int BT>
-__device__ __noinline__ void adj_eval1(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool a_done) {
+__device__ __noinline__ void adj_eval1(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool sp_ready) {
     constexpr int QB = (7 * BT + 3) & ~3;
     Prof& pf = s.pf;
     const int g_lo = s.g_lo, n_loc = s.n_loc;
-    const float4* WAc = p.w.WA + (size_t)g_lo * p.K2q;
     float* KYs = s.st() + (4 + slot) * p.B * p.gpc;
     pf.tick(PT_COMBINE);
-    if (!a_done) passA<NV, BT>(p, s);
-    if (s.rg.pre_mat != WAc) ring_prefetch(p, s, WAc, n_loc);
-    pf.tick(PT_PHASE_A);
-    grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
-    pf.tick(PT_ALLRED1);
-    finalize_sp(p, s);
-    pf.tick(PT_FINALIZE);
-    passB<NV, BT, true>(p, s);
-    ring_prefetch(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc);
-    pf.tick(PT_PHASE_B);
-    grid_allreduce_f(p, s, s.gsp(), p.B * p.K2);
-    pf.tick(PT_ALLRED2);
-    {
-        const int n = p.B * p.K2;
-        for (int i = threadIdx.x; i < n; i += THREADS) {
-            int b = i / p.K2, k = i - b * p.K2;
-            float spv = s.sp()[i];
-            float gv = s.gsp()[i];
-            if (k >= p.Hp) gv = gv * spv;  // gLP = gPr * Pr (exp backward)
-            s.gsp()[i] = gv;
-            s.FSP()[k * QB + slot * BT + b] = spv;
-            s.FG()[k * QB + slot * BT + b] = gv;
-        }
+    if (!sp_ready) {
+        passA<NV, BT>(p, s, s.acts(), s.actl(), s.sp(), MAT_WA);
+        pf.tick(PT_PHASE_A);
+        grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
+        pf.tick(PT_ALLRED1);
+        finalize_sp(p, s, s.sp(), s.sp());
+        pf.tick(PT_FINALIZE);
     }
+    passB<NV, BT, true>(p, s, MAT_W1);
+    pf.tick(PT_PHASE_B);
     // reverse time: ky = -f; the next stage's y input only needs ky, so the caller can form its activations now
     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
         float y = s.ysb()[li];
@@ -1381,12 +1464,15 @@ __device__ __noinline__ void adj_eval1(const ResParams& __restrict__ p, Smem& __
     __syncthreads();
 }
 
-// Second half: pass C (merged with pass A of the next stage input in ysb2 / acts2 / actl2 when has_next), then
-// ka = VJP_y with cotangent a into KA(slot); with has_next the stage buffers swap roles.
+// Second half: (with has_next) pass A of the NEXT stage input (ysb2 / acts2 / actl2) -> ONE all-reduce of
+// [gS|gP of this stage, S|P pre-activations of the next] -> pass C -> ka = VJP_y with cotangent a into KA(slot);
+// with has_next the stage buffers swap roles and s.sp() holds the next stage's finalised branch vector.
 template <int NV, int BT>
 __device__ __noinline__ void adj_eval2(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool has_next) {
+    constexpr int QB = (7 * BT + 3) & ~3;
     Prof& pf = s.pf;
     const int g_lo = s.g_lo, n_loc = s.n_loc;
+    const int n = p.B * p.K2;
     float* KAs = s.st() + (11 + slot) * p.B * p.gpc;
     for (int j = threadIdx.x; j < n_loc; j += THREADS) {
         float t = 0.f;
@@ -1395,8 +1481,22 @@ __device__ __noinline__ void adj_eval2(const ResParams& __restrict__ p, Smem& __
     }
     __syncthreads();
     pf.tick(PT_GSP);
-    passCA<NV, BT>(p, s, has_next);
-    if (has_next) ring_prefetch(p, s, p.w.WA + (size_t)g_lo * p.K2q, n_loc);  // the next evaluation starts at pass B
+    if (has_next) passA<NV, BT>(p, s, s.acts2(), s.actl2(), s.spn(), MAT_W1);
+    pf.tick(PT_PHASE_A);
+    grid_allreduce_f(p, s, s.xv(), has_next ? 2 * n : n);
+    pf.tick(PT_ALLRED2);
+    for (int i = threadIdx.x; i < n; i += THREADS) {
+        int b = i / p.K2, k = i - b * p.K2;
+        float spv = s.sp()[i];
+        float gv = s.gsp()[i];
+        if (k >= p.Hp) gv = gv * spv;  // gLP = gPr * Pr (exp backward)
+        s.gsp()[i] = gv;
+        s.FSP()[k * QB + slot * BT + b] = spv;
+        s.FG()[k * QB + slot * BT + b] = gv;
+    }
+    __syncthreads();
+    pf.tick(PT_FINALIZE);
+    passC<NV, BT>(p, s, has_next ? MAT_WA : MAT_W1);
     pf.tick(PT_PHASE_C);
     // soft-sign / log1p backward, minus the decay path
     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
@@ -1407,7 +1507,8 @@ __device__ __noinline__ void adj_eval2(const ResParams& __restrict__ p, Smem& __
         float yb = (s.ub()[li] + s.vb()[li] / (1.0f + sv)) / (den * den);
         KAs[li] = yb - s.gjb()[li];
     });
-    __syncthreads();
+    if (has_next) finalize_sp(p, s, s.spn(), s.sp());
+    else __syncthreads();
     if (has_next) s.swap_stage_buffers();
     pf.tick(PT_EPILOGUE);
 }
@@ -1435,7 +1536,6 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
     bool theta_zero = true;  // the accumulator has not been written yet: it is identically zero and never read
     float* theta[2] = {p.theta0, p.theta1};
 
-    ring_prefetch(p, s, p.w.W1 + (size_t)g_lo * p.K2q, n_loc);
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
         c->stop = 0;
@@ -1463,8 +1563,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
 
     // One RHS + VJP evaluation at the current stage input; stage derivatives land in KY(slot) / KA(slot), the theta
     // factors in column `slot` of the factor tables.  a_done: pass A of this input already ran (merged into the
-    // previous evaluation's pass C).  With has_next, y_next(li) is called per element once KY(slot) is known and
-    // returns the NEXT stage's y input, whose pass A is merged into this evaluation's pass C.
+    // previous evaluation's exchange).  With has_next, y_next(li) is called per element once KY(slot) is known and
+    // returns the NEXT stage's y input, whose pass A runs before this evaluation's (single) all-reduce.
     auto eval = [&](int slot, bool a_done, bool has_next, auto y_next) {
         adj_eval1<NV, BT>(p, s, slot, a_done);
         if (has_next) {
@@ -1784,7 +1884,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
     }
     pf.tick(PT_PP_COPY);
     __syncthreads();
-    ring_drain(p, s, n_loc);
+    ring_drain(p, s);
     pf.tick(PT_CTRL);
     pf.finish();
     epilogue_epoch(p, s);
