@@ -133,8 +133,9 @@ static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoi
     // bulk-copy targets first (128-byte aligned: every size below is a multiple of 32 bytes)
     t.w1r = w1_res ? take(slice) : none;
     t.war = wa_res ? take(slice) : none;
-    t.ring = ring_stages ? take(sizeof(float) * (size_t)ring_stages * ring_rows * K2) : none;
-    t.bar = take(sizeof(unsigned long long) * (ring_stages ? ring_stages : 1));
+    // per-warp ring: PHX_WARPS x ring_stages row-sized slots, one mbarrier each
+    t.ring = ring_stages ? take(sizeof(float) * (size_t)ring_stages * PHX_WARPS * K2) : none;
+    t.bar = take(sizeof(unsigned long long) * (ring_stages ? ring_stages * PHX_WARPS : 1));
     t.resbar = take(sizeof(unsigned long long));
     t.ctrl = take(PHX_CTRL_BYTES);
     t.dred = take(sizeof(double) * PHX_WARPS * 8);
@@ -146,7 +147,9 @@ static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoi
     t.maskm = take(sizeof(float) * gpc);
     t.sp = take(sizeof(float) * B * K2);
     t.xv = adjoint ? take(sizeof(float) * 2 * B * K2) : none;   // [gS|gLP partial][next stage's S|P partial]
-    t.red = take(sizeof(float) * PHX_RED_WARPS * K2);
+    // cross-warp column-sum buffer: aliases the ring when there is one (no bulk copy is ever in flight during a
+    // reduction: see the prefetch rules in phx_resident.cuh)
+    t.red = ring_stages ? t.ring : take(sizeof(float) * PHX_RED_WARPS * K2);
     t.st = take((adjoint ? 18 : 9) * bl);
     t.acts = take(bl); t.actl = take(bl); t.ysb = take(bl); t.jb = take(bl);
     t.acts2 = t.actl2 = t.ysb2 = t.asb = t.gjb = t.ub = t.vb = t.mt = none;

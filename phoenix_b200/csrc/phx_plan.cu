@@ -34,38 +34,23 @@ int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPl
     // Where the CTA's two weight slices live.  Preference: both resident in shared memory for the whole solve (every
     // pass is a shared-memory pass; all shipped configs up to the yeast shape) -> W1 resident (it is read twice per
     // VJP evaluation) and WA streamed from L2 through the ring (the 11k-gene breast shape) -> both streamed.
-    // Ring geometry: chunks of whole rows, at most 32 KB per chunk, 2..4 chunks in flight; most row-stages wins.
-    const size_t row_bytes = (size_t)K2 * sizeof(float);
-    auto fits = [&](int w1r, int war, int rows, int stages) {
-        return phx_smem_layout(nCTA, B, K2, gpc, adjoint, w1r, war, rows, stages, nullptr) <= PHX_SMEM_LIMIT;
+    // Ring geometry: every warp owns a private ring of S row-sized slots (S = 4..1, as many as fit).
+    auto fits = [&](int w1r, int war, int stages) {
+        return phx_smem_layout(nCTA, B, K2, gpc, adjoint, w1r, war, PHX_WARPS, stages, nullptr) <= PHX_SMEM_LIMIT;
     };
     int w1r = 0, war = 0, best_rows = 0, best_stages = 0;
     bool ok = false;
-    if (fits(1, 1, 0, 0)) {
+    if (fits(1, 1, 0)) {
         w1r = war = 1;
         ok = true;
     }
     for (int res = 1; res >= 0 && !ok; --res) {
-        const int rows_cap = (gpc + 7) / 8 * 8;
-        int best = 0;
-        for (int rows = 64; rows >= 8; rows /= 2) {
-            int r = rows < rows_cap ? rows : rows_cap;
-            if (r * row_bytes > 32 * 1024 && r > 8) continue;
-            const int nch = (gpc + r - 1) / r;
-            for (int stages = (nch < 4 ? nch : 4); stages >= 1; --stages) {
-                if (stages == 1 && nch > 1) continue;  // needs double buffering to stream
-                if (!fits(res, 0, r, stages)) continue;
-                if (r * stages > best) {
-                    best = r * stages;
-                    best_rows = r;
-                    best_stages = stages;
-                }
-                break;
-            }
-        }
-        if (best) {
+        for (int stages = 4; stages >= 1 && !ok; --stages) {
+            if (!fits(res, 0, stages)) continue;
             w1r = res;
             war = 0;
+            best_rows = PHX_WARPS;
+            best_stages = stages;
             ok = true;
         }
     }

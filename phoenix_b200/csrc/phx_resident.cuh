@@ -175,8 +175,8 @@ struct Xchg {
 };
 
 struct Ring {
-    unsigned par;             // per-stage parity of the next completion to wait for
-    const float4* pre_mat;    // matrix whose first chunks are already in flight (nullptr: none)
+    unsigned par;   // this warp's per-slot parity of the next completion to wait for
+    int pre;        // matrix (MAT_*) whose first rows are already in flight in this warp's slots, or -1
 };
 
 
@@ -280,18 +280,23 @@ __device__ __noinline__ void grid_sum_d(const ResParams& p, Smem& s, double* val
     }
     if (blockIdx.x == 0 && warp < nd) {
         unsigned long long w0[5], w1[5];
+        unsigned need = 0;
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-            int c = lane + 32 * u;
-            if (c < nC) ll_ld2(p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * warp, w0[u], w1[u]);
+        for (int u = 0; u < 5; ++u)
+            if (lane + 32 * u < nC) need |= 1u << u;
+        while (need) {   // every pending slot is (re)polled in the same round trip
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+                if (need & (1u << u)) ll_ld2(p.ll.dpart + (size_t)(lane + 32 * u) * PHX_LL_DMAX + 2 * warp, w0[u], w1[u]);
+#pragma unroll
+            for (int u = 0; u < 5; ++u)
+                if ((need & (1u << u)) && (unsigned)(w0[u] >> 32) == tag && (unsigned)(w1[u] >> 32) == tag) need &= ~(1u << u);
         }
         double t = 0;
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
             int c = lane + 32 * u;
             if (c < nC) {
-                const unsigned long long* src = p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * warp;
-                while ((unsigned)(w0[u] >> 32) != tag || (unsigned)(w1[u] >> 32) != tag) ll_ld2(src, w0[u], w1[u]);
                 float hi = __uint_as_float((unsigned)w0[u]), lo = __uint_as_float((unsigned)w1[u]);
                 t += isfinite(hi) ? ((double)hi + (double)lo) : (double)hi;
             }
@@ -330,20 +335,21 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
         const int tot = nC * n;
         for (int e0 = 2 * threadIdx.x; e0 < tot; e0 += 8 * THREADS) {
             unsigned long long w[4][2];
+            unsigned need = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int e = e0 + u * 2 * THREADS;
-                if (e < tot) ll_ld2(base + e, w[u][0], w[u][1]);
-            }
+            for (int u = 0; u < 4; ++u)
+                if (e0 + u * 2 * THREADS < tot) need |= 1u << u;
+            while (need) {   // every pending pair is (re)polled in the same round trip
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                int e = e0 + u * 2 * THREADS;
-                if (e < tot) {
-                    while ((unsigned)(w[u][0] >> 32) != tag || (unsigned)(w[u][1] >> 32) != tag)
-                        ll_ld2(base + e, w[u][0], w[u][1]);
-                    s.ystage()[e] = __uint_as_float((unsigned)w[u][0]);
-                    s.ystage()[e + 1] = __uint_as_float((unsigned)w[u][1]);
-                }
+                for (int u = 0; u < 4; ++u)
+                    if (need & (1u << u)) ll_ld2(base + e0 + u * 2 * THREADS, w[u][0], w[u][1]);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if ((need & (1u << u)) && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag) {
+                        need &= ~(1u << u);
+                        s.ystage()[e0 + u * 2 * THREADS] = __uint_as_float((unsigned)w[u][0]);
+                        s.ystage()[e0 + u * 2 * THREADS + 1] = __uint_as_float((unsigned)w[u][1]);
+                    }
             }
         }
         __syncthreads();
@@ -360,24 +366,29 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
     const int nq = n >> 2;
     for (int q = blockIdx.x + nC * warp; q < nq; q += nC * WARPS) {
         unsigned long long w[5][4];
+        const unsigned long long* src0 = p.ll.xpart + (size_t)lane * PHX_LL_NMAX + 4 * q;
+        unsigned need = 0;
 #pragma unroll
-        for (int u = 0; u < 5; ++u) {
-            int c = lane + 32 * u;
-            if (c < nC) {
-                const unsigned long long* src = p.ll.xpart + (size_t)c * PHX_LL_NMAX + 4 * q;
-                ll_ld2(src, w[u][0], w[u][1]);
-                ll_ld2(src + 2, w[u][2], w[u][3]);
+        for (int u = 0; u < 5; ++u)
+            if (lane + 32 * u < nC) need |= 3u << (2 * u);
+        while (need) {   // every pending pair is (re)polled in the same round trip
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                if (need & (1u << (2 * u))) ll_ld2(src0 + (size_t)32 * u * PHX_LL_NMAX, w[u][0], w[u][1]);
+                if (need & (2u << (2 * u))) ll_ld2(src0 + (size_t)32 * u * PHX_LL_NMAX + 2, w[u][2], w[u][3]);
+            }
+#pragma unroll
+            for (int u = 0; u < 5; ++u) {
+                if ((need & (1u << (2 * u))) && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag)
+                    need &= ~(1u << (2 * u));
+                if ((need & (2u << (2 * u))) && (unsigned)(w[u][2] >> 32) == tag && (unsigned)(w[u][3] >> 32) == tag)
+                    need &= ~(2u << (2 * u));
             }
         }
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
-            int c = lane + 32 * u;
-            if (c < nC) {
-                const unsigned long long* src = p.ll.xpart + (size_t)c * PHX_LL_NMAX + 4 * q;
-                while ((unsigned)(w[u][0] >> 32) != tag || (unsigned)(w[u][1] >> 32) != tag) ll_ld2(src, w[u][0], w[u][1]);
-                while ((unsigned)(w[u][2] >> 32) != tag || (unsigned)(w[u][3] >> 32) != tag)
-                    ll_ld2(src + 2, w[u][2], w[u][3]);
+            if (lane + 32 * u < nC) {
                 a0 += __uint_as_float((unsigned)w[u][0]);
                 a1 += __uint_as_float((unsigned)w[u][1]);
                 a2 += __uint_as_float((unsigned)w[u][2]);
@@ -388,10 +399,10 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
         a1 = warp_sum(a1);
         a2 = warp_sum(a2);
         a3 = warp_sum(a3);
-        // lane l posts element (l & 3) of replica (l >> 2): 32 lanes = 8 replicas x 4 elements
-        const int e = lane & 3;
-        ll_put(p.ll.xres + (size_t)(lane >> 2) * PHX_LL_NMAX + 4 * q + e, e == 0 ? a0 : (e == 1 ? a1 : (e == 2 ? a2 : a3)),
-               tag);
+        // lanes 0..15 post: replica (l >> 1), half (l & 1) of the quad, 16 bytes each
+        if (lane < 2 * PHX_LL_RCOPIES)
+            ll_put2(p.ll.xres + (size_t)(lane >> 1) * PHX_LL_NMAX + 4 * q + 2 * (lane & 1), (lane & 1) ? a2 : a0,
+                    (lane & 1) ? a3 : a1, tag);
     }
     const unsigned long long* res = p.ll.xres + (size_t)(blockIdx.x % PHX_LL_RCOPIES) * PHX_LL_NMAX;
     for (int i = 2 * threadIdx.x; i < n; i += 2 * THREADS) ll_get2(res + i, tag, vec[i], vec[i + 1]);
@@ -436,7 +447,7 @@ __device__ __forceinline__ const float4* mat_global(const Smem& s, int which) { 
 // barriers + the one-time copy of the resident slices (all threads wait for it before the first pass)
 __device__ __forceinline__ void ring_init(const ResParams& p, const Smem& s) {
     if (threadIdx.x == 0) {
-        for (int i = 0; i < p.ring_stages; ++i)
+        for (int i = 0; i < p.ring_stages * WARPS; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s.bar() + i)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(s.at<unsigned long long>(p.so.resbar))));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -456,87 +467,133 @@ __device__ __forceinline__ void resident_wait(const ResParams& p, const Smem& s)
         mbar_wait(smem_u32(s.at<unsigned long long>(p.so.resbar)), 0u);
 }
 
-// thread 0 only: chunk c of the n_rows x K2q matrix `mat` -> stage c % S
-__device__ __forceinline__ void ring_issue(const ResParams& p, const Smem& s, const float4* mat, int n_rows, int c) {
-    const int st = c % p.ring_stages;
-    const int rows = min(p.ring_rows, n_rows - c * p.ring_rows);
-    const unsigned bytes = (unsigned)rows * p.K2q * 16u;
-    const unsigned bar = smem_u32(s.bar() + st);
-    const unsigned dst = smem_u32(s.ring() + (size_t)st * p.ring_rows * p.K2q);
-    const float4* src = mat + (size_t)c * p.ring_rows * p.K2q;
+// Streaming is PER WARP: warp w owns rows w, w + 16, ... of the CTA's slice and a private ring of S row-sized slots
+// with one mbarrier each; its lane 0 issues the bulk copies, so a pass needs no block-wide synchronisation and the
+// warps drift freely against each other.
+__device__ __forceinline__ int warp_rows(const Smem& s) {
+    const int warp = threadIdx.x >> 5;
+    return (s.n_loc > warp) ? (s.n_loc - warp + WARPS - 1) / WARPS : 0;
+}
+// lane 0 only: row i of this warp (row index warp + 16 i of the slice) -> slot i % S
+__device__ __forceinline__ void ring_issue(const ResParams& p, const Smem& s, const float4* mat, int i) {
+    const int warp = threadIdx.x >> 5;
+    const int slot = warp * p.ring_stages + i % p.ring_stages;
+    const unsigned bytes = (unsigned)p.K2q * 16u;
+    const unsigned bar = smem_u32(s.bar() + slot);
+    const unsigned dst = smem_u32(s.ring() + (size_t)slot * p.K2q);
+    const float4* src = mat + (size_t)(warp + WARPS * i) * p.K2q;
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
     bulk_g2s(dst, src, bytes, bar);
 }
 
 // wait for a prefetch nobody will consume (end of the kernel, or a change of plan): no bulk copy may be in flight
-// when the CTA exits or when the ring is re-targeted
+// when the CTA exits or when the slots are re-targeted
 __device__ __forceinline__ void ring_drain(const ResParams& p, Smem& s) {
     Ring& r = s.rg;
-    const int n_rows = s.n_loc;
-    if (r.pre_mat == nullptr || n_rows <= 0) return;
-    const int nch = (n_rows + p.ring_rows - 1) / p.ring_rows;
-    for (int c = 0; c < min(nch, p.ring_stages); ++c) {
-        mbar_wait(smem_u32(s.bar() + c), (r.par >> c) & 1u);
-        r.par ^= 1u << c;
+    if (r.pre < 0) return;
+    const int warp = threadIdx.x >> 5;
+    const int nw = warp_rows(s);
+    for (int i = 0; i < min(nw, p.ring_stages); ++i) {
+        mbar_wait(smem_u32(s.bar() + warp * p.ring_stages + i), (r.par >> i) & 1u);
+        r.par ^= 1u << i;
     }
-    r.pre_mat = nullptr;
-    __syncthreads();
+    r.pre = -1;
 }
 
-// start the first chunks of the next STREAMED pass.  `hint` is the matrix the next pass in program order reads; when
-// it is resident the only other candidate is the next streamed one (at most one matrix streams in that case).
-__device__ __forceinline__ void ring_prefetch(const ResParams& p, Smem& s, int hint) {
+// Start the first rows of the next pass over `which` if that matrix streams (no-op when it is resident).  The ring
+// slots double as the cross-warp reduction buffer, so call this only (a) after a block barrier that follows the last
+// generic-proxy use of the slots and (b) when no reduction happens before the prefetched rows are consumed.
+__device__ __forceinline__ void ring_prefetch(const ResParams& p, Smem& s, int which) {
     Ring& r = s.rg;
-    if (hint == MAT_NONE || p.ring_stages == 0 || s.n_loc <= 0 || r.pre_mat != nullptr) return;
-    int which = hint;
-    if (mat_resident(p, which)) which = (hint == MAT_W1) ? MAT_WA : MAT_W1;
-    if (mat_resident(p, which)) return;
-    const float4* mat = mat_global(s, which);
-    if (threadIdx.x == 0) {
-        const int nch = (s.n_loc + p.ring_rows - 1) / p.ring_rows;
-        for (int c = 0; c < min(nch, p.ring_stages); ++c) ring_issue(p, s, mat, s.n_loc, c);
+    if (which == MAT_NONE || p.ring_stages == 0 || r.pre >= 0 || mat_resident(p, which)) return;
+    if ((threadIdx.x & 31) == 0) {
+        const int nw = warp_rows(s);
+        const float4* mat = mat_global(s, which);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int i = 0; i < min(nw, p.ring_stages); ++i) ring_issue(p, s, mat, i);
     }
-    r.pre_mat = mat;
+    r.pre = which;
 }
 
 // One pass over this CTA's rows of W1 / WA: fn(j, row) is called by one warp (all lanes) per row j with the row in
-// shared memory.  `next`: the matrix the following pass reads (MAT_NONE: unknown), for the prefetch.
+// shared memory; fn must have consumed the row (into registers and through at least one use) when it returns.
 // Ends with a block barrier.
 template <typename RowFn>
-__device__ __forceinline__ void mat_pass(const ResParams& p, Smem& s, int which, int next, RowFn fn) {
+__device__ __forceinline__ void mat_pass(const ResParams& p, Smem& s, int which, RowFn fn) {
     Ring& r = s.rg;
-    const int n_rows = s.n_loc;
-    const int warp = threadIdx.x >> 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned roff = (which == MAT_W1) ? p.so.w1r : p.so.war;
     if (roff != PHX_NONE) {
         const float4* base = s.at<float4>(roff);
-        for (int rr = warp; rr < n_rows; rr += WARPS) fn(rr, base + (size_t)rr * p.K2q);
-        __syncthreads();
-        return;
-    }
-    if (n_rows <= 0) {
+        for (int rr = warp; rr < s.n_loc; rr += WARPS) fn(rr, base + (size_t)rr * p.K2q);
         __syncthreads();
         return;
     }
     const float4* mat = mat_global(s, which);
-    const int R = p.ring_rows, S = p.ring_stages;
-    const int nch = (n_rows + R - 1) / R;
-    if (r.pre_mat != mat) {
+    const int S = p.ring_stages;
+    const int nw = warp_rows(s);
+    if (r.pre != which) {
         ring_drain(p, s);
         ring_prefetch(p, s, which);
     }
-    r.pre_mat = nullptr;
-    for (int c = 0; c < nch; ++c) {
-        const int st = c % S;
-        mbar_wait(smem_u32(s.bar() + st), (r.par >> st) & 1u);
-        r.par ^= 1u << st;
-        const int rows = min(R, n_rows - c * R);
-        const float4* base = s.ring() + (size_t)st * R * p.K2q;
-        for (int rr = warp; rr < rows; rr += WARPS) fn(c * R + rr, base + (size_t)rr * p.K2q);
-        __syncthreads();
-        if (threadIdx.x == 0 && c + S < nch) ring_issue(p, s, mat, n_rows, c + S);
+    r.pre = -1;
+    for (int i = 0; i < nw; ++i) {
+        const int sl = i % S;
+        mbar_wait(smem_u32(s.bar() + warp * S + sl), (r.par >> sl) & 1u);
+        r.par ^= 1u << sl;
+        fn(warp + WARPS * i, s.ring() + (size_t)(warp * S + sl) * p.K2q);
+        __syncwarp();
+        if (lane == 0 && i + S < nw) ring_issue(p, s, mat, i + S);
     }
-    ring_prefetch(p, s, next);
+    __syncthreads();
+}
+
+// Grouped variant: a warp's rows are taken RG at a time.  row_fn(r, j, row) consumes row j (slot r of the group) --
+// typically per-lane partial dot products kept in registers -- and group_fn(g0, ng) then finishes the ng rows
+// j = warp + 16 (g0 + r) together: one interleaved butterfly for all their dot products, the per-element algebra on
+// one lane per element, and whatever needs the results.  The latency chain of a pass is paid once per group instead
+// of once per row.
+template <int RG, typename RowFn, typename GroupFn>
+__device__ __forceinline__ void mat_pass_grouped(const ResParams& p, Smem& s, int which, RowFn row_fn, GroupFn group_fn) {
+    Ring& r = s.rg;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const unsigned roff = (which == MAT_W1) ? p.so.w1r : p.so.war;
+    const int nw = warp_rows(s);
+    if (roff != PHX_NONE) {
+        const float4* base = s.at<float4>(roff);
+        for (int g0 = 0; g0 < nw; g0 += RG) {
+            const int ng = min(RG, nw - g0);
+#pragma unroll
+            for (int q = 0; q < RG; ++q)
+                if (q < ng) row_fn(q, warp + WARPS * (g0 + q), base + (size_t)(warp + WARPS * (g0 + q)) * p.K2q);
+            group_fn(g0, ng);
+        }
+        __syncthreads();
+        return;
+    }
+    const float4* mat = mat_global(s, which);
+    const int S = p.ring_stages;
+    if (r.pre != which) {
+        ring_drain(p, s);
+        ring_prefetch(p, s, which);
+    }
+    r.pre = -1;
+    for (int g0 = 0; g0 < nw; g0 += RG) {
+        const int ng = min(RG, nw - g0);
+#pragma unroll
+        for (int q = 0; q < RG; ++q) {
+            if (q < ng) {
+                const int i = g0 + q, sl = i % S;
+                mbar_wait(smem_u32(s.bar() + warp * S + sl), (r.par >> sl) & 1u);
+                r.par ^= 1u << sl;
+                row_fn(q, warp + WARPS * i, s.ring() + (size_t)(warp * S + sl) * p.K2q);
+                __syncwarp();
+                if (lane == 0 && i + S < nw) ring_issue(p, s, mat, i + S);
+            }
+        }
+        group_fn(g0, ng);
+    }
+    __syncthreads();
 }
 
 // ---- the weight passes --------------------------------------------------------------------------------------------------
@@ -631,100 +688,324 @@ __device__ __forceinline__ void passA(const ResParams& p, Smem& s, const float* 
         const int nb = min(BT, p.B - b0);
         float4 acc[BT][NV];
         acc_zero<NV, BT>(acc);
-        mat_pass(p, s, MAT_W1, (b0 + BT < p.B) ? MAT_W1 : next, [&](int j, const float4* row) {
+        mat_pass(p, s, MAT_W1, [&](int j, const float4* row) {
             float4 w[NV];
             load_row<NV>(row, p.K2q, w);
             axpy_row<NV, BT>(w, acc, acts + b0 * p.gpc, actl + b0 * p.gpc, p.gpc, j, nb, Hq);
         });
         acc_reduce<NV, BT>(p, s, acc, out, b0, nb);
     }
+    ring_prefetch(p, s, next);
 }
 
-// Pass B: jb[b][j] = sum_k WA[g][k] * sp[b][k]; adjoint additionally partial gsp[b][k] = sum_g gj[b][g] WA[g][k].
-template <int NV, int BT, bool ADJ>
-__device__ __forceinline__ void passB(const ResParams& p, Smem& s, int next) {
+// rows of the batch handled per fused pass (register budget: accumulators are PB x NV float4 each)
+template <int NV, int BT> struct PassRows {
+    static constexpr int FWD = (BT < 8 / NV) ? BT : (8 / NV > 1 ? 8 / NV : 1);
+    static constexpr int ADJ = (BT < 4 / NV) ? BT : (4 / NV > 1 ? 4 / NV : 1);
+};
+
+__device__ __forceinline__ float dot4(const float4& w, const float4& x) {
+    float t = w.x * x.x;
+    t = fmaf(w.y, x.y, t);
+    t = fmaf(w.z, x.z, t);
+    t = fmaf(w.w, x.w, t);
+    return t;
+}
+
+// per-lane partial of sum_k w[k] * x[k] (x in shared memory)
+template <int NV>
+__device__ __forceinline__ float row_dot_partial(const float4 (&w)[NV], const float4* x4, int K2q) {
     const int lane = threadIdx.x & 31;
-    const int K2q = p.K2q;
-    const float4* sp4 = reinterpret_cast<const float4*>(s.sp());
-    for (int b0 = 0; b0 < p.B; b0 += BT) {
-        const int nb = min(BT, p.B - b0);
-        float4 acc[BT][NV];
-        if (ADJ) acc_zero<NV, BT>(acc);
-        mat_pass(p, s, MAT_WA, (b0 + BT < p.B) ? MAT_WA : next, [&](int j, const float4* row) {
-            float4 w[NV];
-            load_row<NV>(row, K2q, w);
+    float t0 = 0.f, t1 = 0.f;
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                if (b < nb) {
-                    float d = 0.f;
+    for (int v = 0; v < NV; ++v) {
+        int q = lane + 32 * v;
+        if (q < K2q) {
+            if (v & 1) t1 += dot4(w[v], x4[q]); else t0 += dot4(w[v], x4[q]);
+        }
+    }
+    return t0 + t1;
+}
+
+// all lanes end up with the warp-wide sums of the N per-lane values (N independent butterflies, interleaved)
+template <int N>
+__device__ __forceinline__ void warp_sum_n(float (&d)[N]) {
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        int q = lane + 32 * v;
-                        if (q < K2q) {
-                            float4 x = sp4[(b0 + b) * K2q + q];
-                            d = fmaf(w[v].x, x.x, d);
-                            d = fmaf(w[v].y, x.y, d);
-                            d = fmaf(w[v].z, x.z, d);
-                            d = fmaf(w[v].w, x.w, d);
-                        }
-                    }
-                    d = warp_sum(d);
-                    if (lane == 0) s.jb()[(b0 + b) * p.gpc + j] = d;
-                    if (ADJ) {
-                        float gj = s.gjb()[(b0 + b) * p.gpc + j];
+    for (int o = 16; o > 0; o >>= 1)
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            acc[b][v].x = fmaf(w[v].x, gj, acc[b][v].x);
-                            acc[b][v].y = fmaf(w[v].y, gj, acc[b][v].y);
-                            acc[b][v].z = fmaf(w[v].z, gj, acc[b][v].z);
-                            acc[b][v].w = fmaf(w[v].w, gj, acc[b][v].w);
-                        }
-                    }
-                }
+        for (int i = 0; i < N; ++i) d[i] += __shfl_xor_sync(0xffffffffu, d[i], o);
+}
+template <int N>
+__device__ __forceinline__ float pick_lane(const float (&d)[N]) {
+    const int lane = threadIdx.x & 31;
+    float v = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) v = (lane == i) ? d[i] : v;
+    return v;
+}
+
+// acc[b][:] += c[b] * w  (one coefficient per row of the batch)
+template <int NV, int PB>
+__device__ __forceinline__ void axpy1(const float4 (&w)[NV], float4 (&acc)[PB][NV], const float (&c)[PB], int nb) {
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+        if (b < nb) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                acc[b][v].x = fmaf(w[v].x, c[b], acc[b][v].x);
+                acc[b][v].y = fmaf(w[v].y, c[b], acc[b][v].y);
+                acc[b][v].z = fmaf(w[v].z, c[b], acc[b][v].z);
+                acc[b][v].w = fmaf(w[v].w, c[b], acc[b][v].w);
             }
-        });
-        if (ADJ) acc_reduce<NV, BT>(p, s, acc, s.gsp(), b0, nb);
+        }
+    }
+}
+// acc[b][:] += (cs[b] on the sums half, cl[b] on the prods half) * w
+template <int NV, int PB>
+__device__ __forceinline__ void axpy2(const float4 (&w)[NV], float4 (&acc)[PB][NV], const float (&cs)[PB],
+                                      const float (&cl)[PB], int nb, int Hq) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < PB; ++b) {
+        if (b < nb) {
+#pragma unroll
+            for (int v = 0; v < NV; ++v) {
+                int q = lane + 32 * v;
+                float c = (q >= Hq) ? cl[b] : cs[b];
+                acc[b][v].x = fmaf(w[v].x, c, acc[b][v].x);
+                acc[b][v].y = fmaf(w[v].y, c, acc[b][v].y);
+                acc[b][v].z = fmaf(w[v].z, c, acc[b][v].z);
+                acc[b][v].w = fmaf(w[v].w, c, acc[b][v].w);
+            }
+        }
     }
 }
 
-// Pass C (adjoint): ub[b][j] = sum_{k<Hp} W1[g][k] gS[b][k],  vb[b][j] = sum_{k>=Hp} W1[g][k] gLP[b][k].
-template <int NV, int BT>
-__device__ __forceinline__ void passC(const ResParams& p, Smem& s, int next) {
-    const int lane = threadIdx.x & 31;
+// Fused forward pass over WA: for every local gene row j and batch row b
+//     J = WA[g][:] . sp[b][:]              f = fsign * relu(m)[g] * (J - y_stage)          (odenet.py:88-90)
+//     y_next = post(b, j, li, f, true)     (the caller's RK stage algebra, run by ONE lane per element)
+// and, with do_next, the Hill activations of y_next become the next stage input (ysb / acts / actl) and -- when the W1
+// slice is resident -- are contracted with W1[g][:] on the spot, so that pass A of the NEXT evaluation costs no extra
+// pass: its partial branch vector lands in s.sp().  With a streamed W1 the contraction is a separate pass A.
+template <int NV, int BT, typename Post>
+__device__ __forceinline__ void fwd_passBA(const ResParams& p, Smem& s, bool do_next, Post post) {
+    constexpr int PB = PassRows<NV, BT>::FWD;
+    constexpr int RG = 8 / PB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K2q = p.K2q, Hq = p.Hp >> 2;
+    const bool fuse = do_next && p.so.w1r != PHX_NONE;
+    const float4* sp4 = reinterpret_cast<const float4*>(s.sp());
+    const float4* w1res = s.at<float4>(p.so.w1r);
+    float4 acc[PB][NV];
+    for (int b0 = 0; b0 < p.B; b0 += PB) {
+        const int nb = min(PB, p.B - b0);
+        acc_zero<NV, PB>(acc);
+        float d[RG * PB] = {};
+        mat_pass_grouped<RG>(
+            p, s, MAT_WA,
+            [&](int r, int j, const float4* row) {
+                float4 w[NV];
+                load_row<NV>(row, K2q, w);
+#pragma unroll
+                for (int b = 0; b < PB; ++b)
+                    d[r * PB + b] = (b < nb) ? row_dot_partial<NV>(w, sp4 + (size_t)(b0 + b) * K2q, K2q) : 0.f;
+            },
+            [&](int g0, int ng) {
+                warp_sum_n<RG * PB>(d);
+                const float mine = pick_lane<RG * PB>(d);
+                float sv = 0.f, lv = 0.f;
+                {
+                    const int r = lane / PB, b = lane - r * PB;
+                    if (r < ng && b < nb) {
+                        const int j = warp + WARPS * (g0 + r);
+                        const int li = (b0 + b) * p.gpc + j;
+                        const float f = p.fsign * (s.relum()[j] * (mine - s.ysb()[li]));
+                        const float yn = post(b0 + b, j, li, f, true);
+                        if (do_next) {
+                            float den;
+                            hill(yn, sv, lv, den);
+                            s.ysb()[li] = yn;
+                            s.acts()[li] = sv;
+                            s.actl()[li] = lv;
+                        }
+                    }
+                }
+                if (fuse) {
+#pragma unroll
+                    for (int r = 0; r < RG; ++r) {
+                        if (r < ng) {
+                            float cs[PB], cl[PB];
+#pragma unroll
+                            for (int b = 0; b < PB; ++b) {
+                                cs[b] = __shfl_sync(0xffffffffu, sv, r * PB + b);
+                                cl[b] = __shfl_sync(0xffffffffu, lv, r * PB + b);
+                            }
+                            float4 w[NV];
+                            load_row<NV>(w1res + (size_t)(warp + WARPS * (g0 + r)) * K2q, K2q, w);
+                            axpy2<NV, PB>(w, acc, cs, cl, nb, Hq);
+                        }
+                    }
+                }
+            });
+        if (fuse) acc_reduce<NV, PB>(p, s, acc, s.sp(), b0, nb);   // sp is dead once every row-dot of the pass is done
+    }
+    // what streams next (the ring slots double as the reduction buffer: only prefetch what is consumed before the
+    // next reduction): fused -> the next evaluation's WA pass; not fused -> pass A over W1; last stage -> the next
+    // step's stand-alone pass A over W1
+    if (do_next && !fuse) passA<NV, BT>(p, s, s.acts(), s.actl(), s.sp(), MAT_WA);
+    else ring_prefetch(p, s, fuse ? MAT_WA : MAT_W1);
+}
+
+// Fused adjoint pass 1 over WA at the current stage input (ysb / acts / actl, cotangent asb, gj = a relu(m) in gjb):
+//     J = WA[g][:] . sp[b][:]        ky = -relu(m) (J - y)       gSP partial += gj[b][g] * WA[g][:]  -> s.gsp()
+//     theta factors of this stage (FS, FL, FGJ, FM) into column `slot`
+//     with has_next: y_next = ynext(b, j, li, ky) -> ysb2 / acts2 / actl2 and (resident W1) its pass A -> s.spn()
+template <int NV, int BT, typename YNext>
+__device__ __forceinline__ void adj_pass1(const ResParams& p, Smem& s, int slot, bool has_next, YNext ynext) {
+    constexpr int PB = PassRows<NV, BT>::ADJ;
+    constexpr int RG = 8 / PB;
+    constexpr int QB = (7 * BT + 3) & ~3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int K2q = p.K2q, Hq = p.Hp >> 2;
+    const bool fuse = has_next && p.so.w1r != PHX_NONE;
+    const float4* sp4 = reinterpret_cast<const float4*>(s.sp());
+    const float4* w1res = s.at<float4>(p.so.w1r);
+    float* KYs = s.st() + (4 + slot) * p.B * p.gpc;
+    float4 accg[PB][NV], acca[PB][NV];
+    for (int b0 = 0; b0 < p.B; b0 += PB) {
+        const int nb = min(PB, p.B - b0);
+        acc_zero<NV, PB>(accg);
+        acc_zero<NV, PB>(acca);
+        float d[RG * PB] = {};
+        mat_pass_grouped<RG>(
+            p, s, MAT_WA,
+            [&](int r, int j, const float4* row) {
+                float4 w[NV];
+                load_row<NV>(row, K2q, w);
+                float gj[PB];
+#pragma unroll
+                for (int b = 0; b < PB; ++b) {
+                    d[r * PB + b] = (b < nb) ? row_dot_partial<NV>(w, sp4 + (size_t)(b0 + b) * K2q, K2q) : 0.f;
+                    gj[b] = (b < nb) ? s.gjb()[(b0 + b) * p.gpc + j] : 0.f;
+                }
+                axpy1<NV, PB>(w, accg, gj, nb);
+            },
+            [&](int g0, int ng) {
+                warp_sum_n<RG * PB>(d);
+                const float mine = pick_lane<RG * PB>(d);
+                float sv = 0.f, lv = 0.f, mt = 0.f;
+                const int r = lane / PB, b = lane - r * PB;
+                const int j = warp + WARPS * (g0 + r);
+                const bool active = r < ng && b < nb;
+                if (active) {
+                    const int li = (b0 + b) * p.gpc + j;
+                    const float jm = mine - s.ysb()[li];
+                    const float ky = -(s.relum()[j] * jm);
+                    mt = s.asb()[li] * jm;
+                    KYs[li] = ky;
+                    s.FS()[j * QB + slot * BT + b0 + b] = s.acts()[li];
+                    s.FL()[j * QB + slot * BT + b0 + b] = s.actl()[li];
+                    s.FGJ()[j * QB + slot * BT + b0 + b] = s.gjb()[li];
+                    if (has_next) {
+                        const float yn = ynext(b0 + b, j, li, ky);
+                        float den;
+                        hill(yn, sv, lv, den);
+                        s.ysb2()[li] = yn;
+                        s.acts2()[li] = sv;
+                        s.actl2()[li] = lv;
+                    }
+                }
+                // multiplier cotangent of the row: sum over the batch rows (adjacent lanes), masked by m > 0
+#pragma unroll
+                for (int o = PB / 2; o > 0; o >>= 1) mt += __shfl_xor_sync(0xffffffffu, mt, o);
+                if (r < ng && b == 0) {
+                    const float prev = (b0 == 0) ? 0.f : s.FM()[j * 8 + slot];
+                    s.FM()[j * 8 + slot] = prev + mt * s.maskm()[j];
+                }
+                if (fuse) {
+#pragma unroll
+                    for (int q = 0; q < RG; ++q) {
+                        if (q < ng) {
+                            float cs[PB], cl[PB];
+#pragma unroll
+                            for (int bb = 0; bb < PB; ++bb) {
+                                cs[bb] = __shfl_sync(0xffffffffu, sv, q * PB + bb);
+                                cl[bb] = __shfl_sync(0xffffffffu, lv, q * PB + bb);
+                            }
+                            float4 w[NV];
+                            load_row<NV>(w1res + (size_t)(warp + WARPS * (g0 + q)) * K2q, K2q, w);
+                            axpy2<NV, PB>(w, acca, cs, cl, nb, Hq);
+                        }
+                    }
+                }
+            });
+        acc_reduce<NV, PB>(p, s, accg, s.gsp(), b0, nb);
+        if (fuse) acc_reduce<NV, PB>(p, s, acca, s.spn(), b0, nb);
+    }
+    // next streamed pass: pass A (not fused) or pass 2 over W1; with W1 resident the next evaluation's WA pass (pass 2
+    // does no cross-warp reduction, so the ring slots stay untouched until then)
+    if (has_next && !fuse) passA<NV, BT>(p, s, s.acts2(), s.actl2(), s.spn(), MAT_W1);
+    else ring_prefetch(p, s, (has_next && mat_resident(p, MAT_W1)) ? MAT_WA : MAT_W1);
+}
+
+// Fused adjoint pass 2 over W1 (after the exchange; s.gsp() = gS | gLP):
+//     u = W1[g][:Hp] . gS     v = W1[g][Hp:] . gLP      ka = (u + v / (1 + s)) / (1 + |y - .5|)^2 - gj   -> KA(slot)
+//     a_next = anext(b, j, li, ka, true); with has_next it becomes the next stage's cotangent input (asb, gjb)
+template <int NV, int BT, typename ANext>
+__device__ __forceinline__ void adj_pass2(const ResParams& p, Smem& s, int slot, bool has_next, ANext anext) {
+    constexpr int PB = PassRows<NV, BT>::ADJ;
+    constexpr int RG = 8 / PB;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int K2q = p.K2q, Hq = p.Hp >> 2;
     const float4* g4 = reinterpret_cast<const float4*>(s.gsp());
-    for (int b0 = 0; b0 < p.B; b0 += BT) {
-        const int nb = min(BT, p.B - b0);
-        mat_pass(p, s, MAT_W1, (b0 + BT < p.B) ? MAT_W1 : next, [&](int j, const float4* row) {
-            float4 w[NV];
-            load_row<NV>(row, K2q, w);
+    float* KAs = s.st() + (11 + slot) * p.B * p.gpc;
+    for (int b0 = 0; b0 < p.B; b0 += PB) {
+        const int nb = min(PB, p.B - b0);
+        float du[RG * PB] = {}, dv[RG * PB] = {};
+        mat_pass_grouped<RG>(
+            p, s, MAT_W1,
+            [&](int r, int j, const float4* row) {
+                float4 w[NV];
+                load_row<NV>(row, K2q, w);
 #pragma unroll
-            for (int b = 0; b < BT; ++b) {
-                if (b < nb) {
-                    float du = 0.f, dv = 0.f;
+                for (int b = 0; b < PB; ++b) {
+                    float tu = 0.f, tv = 0.f;
+                    if (b < nb) {
 #pragma unroll
-                    for (int v = 0; v < NV; ++v) {
-                        int q = lane + 32 * v;
-                        if (q < K2q) {
-                            float4 x = g4[(b0 + b) * K2q + q];
-                            float t = 0.f;
-                            t = fmaf(w[v].x, x.x, t);
-                            t = fmaf(w[v].y, x.y, t);
-                            t = fmaf(w[v].z, x.z, t);
-                            t = fmaf(w[v].w, x.w, t);
-                            if (q >= Hq) dv += t; else du += t;
+                        for (int v = 0; v < NV; ++v) {
+                            int q = lane + 32 * v;
+                            if (q < K2q) {
+                                float t = dot4(w[v], g4[(b0 + b) * K2q + q]);
+                                if (q >= Hq) tv += t; else tu += t;
+                            }
                         }
                     }
-                    du = warp_sum(du);
-                    dv = warp_sum(dv);
-                    if (lane == 0) {
-                        s.ub()[(b0 + b) * p.gpc + j] = du;
-                        s.vb()[(b0 + b) * p.gpc + j] = dv;
+                    du[r * PB + b] = tu;
+                    dv[r * PB + b] = tv;
+                }
+            },
+            [&](int g0, int ng) {
+                warp_sum_n<RG * PB>(du);
+                warp_sum_n<RG * PB>(dv);
+                const float u = pick_lane<RG * PB>(du), v = pick_lane<RG * PB>(dv);
+                const int r = lane / PB, b = lane - r * PB;
+                if (r < ng && b < nb) {
+                    const int j = warp + WARPS * (g0 + r);
+                    const int li = (b0 + b) * p.gpc + j;
+                    const float z = s.ysb()[li] - 0.5f;
+                    const float den = 1.0f + fabsf(z);
+                    const float yb = (u + v / (1.0f + s.acts()[li])) / (den * den);
+                    const float ka = yb - s.gjb()[li];
+                    KAs[li] = ka;
+                    const float an = anext(b0 + b, j, li, ka, true);
+                    if (has_next) {
+                        s.asb()[li] = an;
+                        s.gjb()[li] = an * s.relum()[j];
                     }
                 }
-            }
-        });
+            });
     }
+    ring_prefetch(p, s, has_next ? MAT_WA : MAT_W1);
 }
 
 template <typename F>
@@ -843,7 +1124,7 @@ __device__ __forceinline__ void prologue(const ResParams& p, Smem& s) {
     x.ep = __ldcg(p.ll.epoch);
     x.ny = x.nd = 0;
     ring.par = 0;
-    ring.pre_mat = nullptr;
+    ring.pre = -1;
     for (int k = threadIdx.x; k < p.K2; k += THREADS) s.bias()[k] = p.w.bias[k];
     for (int j = threadIdx.x; j < n_loc; j += THREADS) {
         s.relum()[j] = p.w.relum[g_lo + j];
@@ -860,9 +1141,9 @@ __device__ __forceinline__ void epilogue_epoch(const ResParams& p, const Smem& s
     if (blockIdx.x == 0 && threadIdx.x == 0) *p.ll.epoch = x.ep;
 }
 
-// One forward RHS evaluation at the stage input (acts / actl / ysb); leaves joint(y) in s.jb().
+// Stand-alone pass A at the stage input (acts / actl) + its exchange: leaves the finalised branch vector in s.sp().
 template <int NV, int BT>
-__device__ __noinline__ void fwd_eval(const ResParams& __restrict__ p, Smem& __restrict__ s) {
+__device__ __noinline__ void eval_A(const ResParams& __restrict__ p, Smem& __restrict__ s) {
     Prof& pf = s.pf;
     pf.tick(PT_COMBINE);
     passA<NV, BT>(p, s, s.acts(), s.actl(), s.sp(), MAT_WA);
@@ -871,8 +1152,21 @@ __device__ __noinline__ void fwd_eval(const ResParams& __restrict__ p, Smem& __r
     pf.tick(PT_ALLRED1);
     finalize_sp(p, s, s.sp(), s.sp());
     pf.tick(PT_FINALIZE);
-    passB<NV, BT, false>(p, s, MAT_W1);
+}
+
+// The rest of a forward evaluation: fused pass B (+ the caller's stage algebra + pass A of the next stage input) and,
+// with do_next, the exchange that completes the next stage's branch vector.
+template <int NV, int BT, typename Post>
+__device__ __forceinline__ void eval_B(const ResParams& __restrict__ p, Smem& __restrict__ s, bool do_next, Post post) {
+    Prof& pf = s.pf;
+    fwd_passBA<NV, BT>(p, s, do_next, post);
     pf.tick(PT_PHASE_B);
+    if (do_next) {
+        grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
+        pf.tick(PT_ALLRED1);
+        finalize_sp(p, s, s.sp(), s.sp());
+        pf.tick(PT_FINALIZE);
+    }
 }
 
 // =====================================================================================================================
@@ -914,68 +1208,39 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     });
     __syncthreads();
 
-    auto eval = [&]() { fwd_eval<NV, BT>(p, s); };
-    auto fval = [&](int j, int li) { return p.fsign * (s.relum()[j] * (s.jb()[li] - s.ysb()[li])); };
-
     if (p.method != PHX_DOPRI5) {
         // ---- fixed grid: one step per output interval (solvers.py:48-50, 77-95) ----
         const float third = (float)(1.0 / 3.0);
+        eval_A<NV, BT>(p, s);
         for (int i = 0; i + 1 < p.T; ++i) {
             const float dtf = p.t_is_f32 ? ((float)tget(p, i + 1) - (float)tget(p, i)) : (float)(tget(p, i + 1) - tget(p, i));
             float* yo = p.yout + (size_t)(i + 1) * BG;
-            eval();
-            if (p.method == PHX_EULER) {
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y1 = s.ysb()[li] + dtf * fval(j, li);
-                    Y[li] = y1;
-                    yo[gi] = y1;
-                    set_stage_input(li, y1);
-                });
-            } else if (p.method == PHX_MIDPOINT) {
-                const float half = 0.5f * dtf;
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_stage_input(li, s.ysb()[li] + fval(j, li) * half);
-                });
-                __syncthreads();
-                eval();
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y1 = Y[li] + dtf * fval(j, li);
-                    Y[li] = y1;
-                    yo[gi] = y1;
-                    set_stage_input(li, y1);
-                });
-            } else {  // 3/8-rule RK4 (rk_common.py:96-103)
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k1 = fval(j, li);
-                    K(0)[li] = k1;
-                    set_stage_input(li, s.ysb()[li] + dtf * k1 * third);
-                });
-                __syncthreads();
-                eval();
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k2 = fval(j, li);
-                    K(1)[li] = k2;
-                    set_stage_input(li, Y[li] + dtf * (k2 - K(0)[li] * third));
-                });
-                __syncthreads();
-                eval();
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k3 = fval(j, li);
-                    K(2)[li] = k3;
-                    set_stage_input(li, Y[li] + dtf * (K(0)[li] - K(1)[li] + k3));
-                });
-                __syncthreads();
-                eval();
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float k4 = fval(j, li);
-                    float dy = (K(0)[li] + 3.f * (K(1)[li] + K(2)[li]) + k4) * dtf * 0.125f;
-                    float y1 = Y[li] + dy;
-                    Y[li] = y1;
-                    yo[gi] = y1;
-                    set_stage_input(li, y1);
+            const bool more = i + 2 < p.T;   // another interval follows: its first pass A is fused into the last stage
+            // one call site for every stage of every fixed-grid method (the stage algebra switches at run time)
+            const int nst = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
+            const float half = 0.5f * dtf;
+            for (int st = 0; st < nst; ++st) {
+                const bool last = st + 1 == nst;
+                eval_B<NV, BT>(p, s, !last || more, [&](int b, int j, int li, float f, bool lead) {
+                    float yn;
+                    if (p.method == PHX_EULER) {
+                        yn = Y[li] + dtf * f;
+                    } else if (p.method == PHX_MIDPOINT) {
+                        yn = (st == 0) ? Y[li] + f * half : Y[li] + dtf * f;
+                    } else {  // 3/8-rule RK4 (rk_common.py:96-103)
+                        if (st == 0) yn = Y[li] + dtf * f * third;
+                        else if (st == 1) yn = Y[li] + dtf * (f - K(0)[li] * third);
+                        else if (st == 2) yn = Y[li] + dtf * (K(0)[li] - K(1)[li] + f);
+                        else yn = Y[li] + (K(0)[li] + 3.f * (K(1)[li] + K(2)[li]) + f) * dtf * 0.125f;
+                        if (lead && !last) K(st)[li] = f;
+                    }
+                    if (last && lead) {
+                        Y[li] = yn;
+                        yo[(size_t)b * p.G + g_lo + j] = yn;
+                    }
+                    return yn;
                 });
             }
-            __syncthreads();
         }
         if (threadIdx.x == 0) {
             int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
@@ -992,55 +1257,54 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     }
 
     // ---- dopri5 (rk_common.py:111-228) ----
-    // f0 and the initial step (misc.py:47-86)
-    eval();
-    {
+    // f0 and the initial step (misc.py:47-86): two evaluations through one call site
+    for (int which = 0; which < 2; ++which) {
         double acc[3] = {0, 0, 0};
-        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            float y = s.ysb()[li];
-            float f0 = fval(j, li);
-            K(0)[li] = f0;
-            float scale = p.atol_f + fabsf(y) * p.rtol_f;
-            float r0 = y / scale, r1 = f0 / scale;
-            acc[0] += (double)(r0 * r0);
-            acc[1] += (double)(r1 * r1);
-            if (!isfinite(y)) acc[2] += 1.0;
+        eval_A<NV, BT>(p, s);
+        eval_B<NV, BT>(p, s, false, [&](int b, int j, int li, float f, bool lead) {
+            if (lead) {
+                float y = Y[li];
+                float scale = p.atol_f + fabsf(y) * p.rtol_f;
+                if (which == 0) {
+                    K(0)[li] = f;
+                    float r0 = y / scale, r1 = f / scale;
+                    acc[0] += (double)(r0 * r0);
+                    acc[1] += (double)(r1 * r1);
+                    if (!isfinite(y)) acc[2] += 1.0;
+                } else {
+                    float r = (f - K(0)[li]) / scale;
+                    acc[0] += (double)(r * r);
+                }
+            }
+            return 0.f;
         });
         block_sum_d<3>(acc, s.dred(), c->dsum);
-        grid_sum_d(p, s, c->dsum, 3);
+        grid_sum_d(p, s, c->dsum, which == 0 ? 3 : 1);
         pf.tick(PT_NORMS);
-        if (threadIdx.x == 0) {
-            float d0 = sqrtf((float)(c->dsum[0] / Nel));
-            float d1 = sqrtf((float)(c->dsum[1] / Nel));
-            c->d1 = d1;
-            c->h0 = init_h0(d0, d1);
-            c->nonfinite_prev = c->dsum[2] > 0.0;
+        if (which == 0) {
+            if (threadIdx.x == 0) {
+                float d0 = sqrtf((float)(c->dsum[0] / Nel));
+                float d1 = sqrtf((float)(c->dsum[1] / Nel));
+                c->d1 = d1;
+                c->h0 = init_h0(d0, d1);
+                c->nonfinite_prev = c->dsum[2] > 0.0;
+            }
+            __syncthreads();
+            const float h0 = c->h0;
+            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                set_stage_input(li, Y[li] + h0 * K(0)[li]);
+            });
+            __syncthreads();
+        } else {
+            if (threadIdx.x == 0) {
+                float d2 = sqrtf((float)(c->dsum[0] / Nel)) / c->h0;
+                c->dt = init_dt(c->h0, c->d1, d2);
+                c->tprev = c->tcur;
+                c->n_rhs = 2;
+                c->n_steps_interval = 0;
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const float h0 = c->h0;
-        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            set_stage_input(li, Y[li] + h0 * K(0)[li]);
-        });
-        __syncthreads();
-        eval();
-        double acc2[1] = {0};
-        for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-            float f1 = fval(j, li);
-            float scale = p.atol_f + fabsf(Y[li]) * p.rtol_f;
-            float r = (f1 - K(0)[li]) / scale;
-            acc2[0] += (double)(r * r);
-        });
-        block_sum_d<1>(acc2, s.dred(), c->dsum);
-        grid_sum_d(p, s, c->dsum, 1);
-        pf.tick(PT_NORMS);
-        if (threadIdx.x == 0) {
-            float d2 = sqrtf((float)(c->dsum[0] / Nel)) / c->h0;
-            c->dt = init_dt(c->h0, c->d1, d2);
-            c->tprev = c->tcur;
-            c->n_rhs = 2;
-            c->n_steps_interval = 0;
-        }
-        __syncthreads();
     }
 
     int next_out = 1;
@@ -1071,21 +1335,21 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
             });
             __syncthreads();
         }
+        eval_A<NV, BT>(p, s);
         double acc[2] = {0, 0};
         for (int st = 1; st <= 6; ++st) {
-            eval();
-            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                float ys = s.ysb()[li];
-                float f = fval(j, li);
-                K(sl[st])[li] = f;
+            eval_B<NV, BT>(p, s, st < 6, [&](int b, int j, int li, float f, bool lead) {
+                if (lead) K(sl[st])[li] = f;
                 if (st < 6) {
                     float a = K(sl[0])[li] * c->cb[st][0];
                     for (int q = 1; q < st; ++q) a = fmaf(K(sl[q])[li], c->cb[st][q], a);
                     a = fmaf(f, c->cb[st][st], a);
                     float yn = Y[li] + a;
-                    if (st == 5) Y1[li] = yn;
-                    set_stage_input(li, yn);
-                } else {
+                    if (st == 5 && lead) Y1[li] = yn;
+                    return yn;
+                }
+                if (lead) {
+                    float ys = s.ysb()[li];
                     float e = K(sl[0])[li] * c->cerr[0];
                     for (int q = 1; q < 6; ++q) e = fmaf(K(sl[q])[li], c->cerr[q], e);
                     e = fmaf(f, c->cerr[6], e);
@@ -1094,8 +1358,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
                     acc[0] += (double)(r * r);
                     if (!isfinite(ys)) acc[1] += 1.0;
                 }
+                return 0.f;
             });
-            __syncthreads();
         }
         pf.tick(PT_COMBINE);
         block_sum_d<2>(acc, s.dred(), c->dsum);
@@ -1430,87 +1694,46 @@ __device__ __noinline__ double theta_zero_norm(const ResParams& p, const Smem& s
     return mine / ((double)p.atol_f * (double)p.atol_f);
 }
 
-// First half of one RHS + VJP evaluation at the current stage input: (unless sp_ready: the branch vector of this input
-// was all-reduced together with the previous evaluation's gS|gLP) pass A + its all-reduce; then pass B; leaves
-// ky = -f in KY(slot), the stage's local theta factors in column `slot` of the factor tables and this CTA's partial
-// gS|gP in s.gsp().
-template <int NV, int BT>
-__device__ __noinline__ void adj_eval1(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool sp_ready) {
+// One RHS + VJP evaluation at the current stage input (ysb / acts / actl, cotangent asb / gjb); stage derivatives land
+// in KY(slot) / KA(slot), the theta factors in column `slot` of the factor tables.
+//   sp_ready: the branch vector of this input is already in s.sp() (it was all-reduced together with the previous
+//             evaluation's gS|gP); otherwise a stand-alone pass A + exchange runs first.
+//   has_next: ynext(b, j, li, ky) returns the NEXT stage's y input per element; its pass A is fused into pass 1 and its
+//             branch vector shares this evaluation's single all-reduce.  anext(b, j, li, ka, lead) returns the next
+//             stage's cotangent input (and is where the caller does its per-element stage algebra).
+template <int NV, int BT, typename YNext, typename ANext>
+__device__ __forceinline__ void adj_eval(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool sp_ready,
+                                         bool has_next, YNext ynext, ANext anext) {
     constexpr int QB = (7 * BT + 3) & ~3;
     Prof& pf = s.pf;
-    const int g_lo = s.g_lo, n_loc = s.n_loc;
-    float* KYs = s.st() + (4 + slot) * p.B * p.gpc;
-    pf.tick(PT_COMBINE);
-    if (!sp_ready) {
-        passA<NV, BT>(p, s, s.acts(), s.actl(), s.sp(), MAT_WA);
-        pf.tick(PT_PHASE_A);
-        grid_allreduce_f(p, s, s.sp(), p.B * p.K2);
-        pf.tick(PT_ALLRED1);
-        finalize_sp(p, s, s.sp(), s.sp());
-        pf.tick(PT_FINALIZE);
-    }
-    passB<NV, BT, true>(p, s, MAT_W1);
-    pf.tick(PT_PHASE_B);
-    // reverse time: ky = -f; the next stage's y input only needs ky, so the caller can form its activations now
-    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-        float y = s.ysb()[li];
-        float jm = s.jb()[li] - y;
-        KYs[li] = -(s.relum()[j] * jm);
-        s.mt()[li] = s.asb()[li] * jm;
-        s.FS()[j * QB + slot * BT + b] = s.acts()[li];
-        s.FL()[j * QB + slot * BT + b] = s.actl()[li];
-        s.FGJ()[j * QB + slot * BT + b] = s.gjb()[li];
-    });
-    __syncthreads();
-}
-
-// Second half: (with has_next) pass A of the NEXT stage input (ysb2 / acts2 / actl2) -> ONE all-reduce of
-// [gS|gP of this stage, S|P pre-activations of the next] -> pass C -> ka = VJP_y with cotangent a into KA(slot);
-// with has_next the stage buffers swap roles and s.sp() holds the next stage's finalised branch vector.
-template <int NV, int BT>
-__device__ __noinline__ void adj_eval2(const ResParams& __restrict__ p, Smem& __restrict__ s, int slot, bool has_next) {
-    constexpr int QB = (7 * BT + 3) & ~3;
-    Prof& pf = s.pf;
-    const int g_lo = s.g_lo, n_loc = s.n_loc;
     const int n = p.B * p.K2;
-    float* KAs = s.st() + (11 + slot) * p.B * p.gpc;
-    for (int j = threadIdx.x; j < n_loc; j += THREADS) {
-        float t = 0.f;
-        for (int b = 0; b < p.B; ++b) t += s.mt()[b * p.gpc + j];
-        s.FM()[j * 8 + slot] = t * s.maskm()[j];
-    }
-    __syncthreads();
-    pf.tick(PT_GSP);
-    if (has_next) passA<NV, BT>(p, s, s.acts2(), s.actl2(), s.spn(), MAT_W1);
-    pf.tick(PT_PHASE_A);
+    if (!sp_ready) eval_A<NV, BT>(p, s);
+    pf.tick(PT_COMBINE);
+    adj_pass1<NV, BT>(p, s, slot, has_next, ynext);
+    pf.tick(PT_PHASE_B);
     grid_allreduce_f(p, s, s.xv(), has_next ? 2 * n : n);
     pf.tick(PT_ALLRED2);
+    // gLP = gPr * Pr (exp backward); record the stage's K2-long theta factors; the next stage's branch vector replaces
+    // this one (bias, exp) -- every index is handled by one thread, reads before writes
     for (int i = threadIdx.x; i < n; i += THREADS) {
-        int b = i / p.K2, k = i - b * p.K2;
-        float spv = s.sp()[i];
+        const int b = i / p.K2, k = i - b * p.K2;
+        const float spv = s.sp()[i];
         float gv = s.gsp()[i];
-        if (k >= p.Hp) gv = gv * spv;  // gLP = gPr * Pr (exp backward)
+        if (k >= p.Hp) gv = gv * spv;
         s.gsp()[i] = gv;
         s.FSP()[k * QB + slot * BT + b] = spv;
         s.FG()[k * QB + slot * BT + b] = gv;
+        if (has_next) {
+            float v = s.spn()[i] + s.bias()[k];
+            if (k >= p.Hp) v = (k - p.Hp < p.H) ? expf(v) : 0.f;
+            s.sp()[i] = v;
+        }
     }
     __syncthreads();
     pf.tick(PT_FINALIZE);
-    passC<NV, BT>(p, s, has_next ? MAT_WA : MAT_W1);
-    pf.tick(PT_PHASE_C);
-    // soft-sign / log1p backward, minus the decay path
-    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-        float y = s.ysb()[li];
-        float sv = s.acts()[li];
-        float z = y - 0.5f;
-        float den = 1.0f + fabsf(z);
-        float yb = (s.ub()[li] + s.vb()[li] / (1.0f + sv)) / (den * den);
-        KAs[li] = yb - s.gjb()[li];
-    });
-    if (has_next) finalize_sp(p, s, s.spn(), s.sp());
-    else __syncthreads();
+    adj_pass2<NV, BT>(p, s, slot, has_next, anext);
     if (has_next) s.swap_stage_buffers();
-    pf.tick(PT_EPILOGUE);
+    pf.tick(PT_PHASE_C);
 }
 
 template <int NV, int BT>
@@ -1561,20 +1784,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
         s.gjb()[li] = as * s.relum()[j];
     };
 
-    // One RHS + VJP evaluation at the current stage input; stage derivatives land in KY(slot) / KA(slot), the theta
-    // factors in column `slot` of the factor tables.  a_done: pass A of this input already ran (merged into the
-    // previous evaluation's exchange).  With has_next, y_next(li) is called per element once KY(slot) is known and
-    // returns the NEXT stage's y input, whose pass A runs before this evaluation's (single) all-reduce.
-    auto eval = [&](int slot, bool a_done, bool has_next, auto y_next) {
-        adj_eval1<NV, BT>(p, s, slot, a_done);
-        if (has_next) {
-            for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                set_y_input(s.ysb2(), s.acts2(), s.actl2(), li, y_next(li));
-            });
-        }
-        adj_eval2<NV, BT>(p, s, slot, has_next);
-    };
-    auto no_next = [](int) { return 0.f; };
+    auto no_y = [](int, int, int, float) { return 0.f; };
+    auto no_a = [](int, int, int, float, bool) { return 0.f; };
 
     int code = PHX_ST_OK;
     for (int iv = p.T - 1; iv >= 1 && code == PHX_ST_OK; --iv) {
@@ -1601,44 +1812,36 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
             pa.dtf = dtf;
             pa.method = p.method;
             double d0 = 0, d1 = 0;
-            if (p.method == PHX_EULER) {
-                eval(0, false, false, no_next);
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    A[li] = A[li] + dtf * KA(0)[li];
-                });
-            } else if (p.method == PHX_MIDPOINT) {
-                const float half = 0.5f * dtf;
-                eval(0, false, true, [&](int li) { return Y[li] + KY(0)[li] * half; });
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_a_input(li, j, A[li] + KA(0)[li] * half);
-                });
-                __syncthreads();
-                eval(1, true, false, no_next);
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    A[li] = A[li] + dtf * KA(1)[li];
-                });
-            } else {
-                eval(0, false, true, [&](int li) { return Y[li] + dtf * KY(0)[li] * third; });
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_a_input(li, j, A[li] + dtf * KA(0)[li] * third);
-                });
-                __syncthreads();
-                eval(1, true, true, [&](int li) { return Y[li] + dtf * (KY(1)[li] - KY(0)[li] * third); });
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_a_input(li, j, A[li] + dtf * (KA(1)[li] - KA(0)[li] * third));
-                });
-                __syncthreads();
-                eval(2, true, true, [&](int li) { return Y[li] + dtf * (KY(0)[li] - KY(1)[li] + KY(2)[li]); });
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_a_input(li, j, A[li] + dtf * (KA(0)[li] - KA(1)[li] + KA(2)[li]));
-                });
-                __syncthreads();
-                eval(3, true, false, no_next);
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float dy = (KA(0)[li] + 3.f * (KA(1)[li] + KA(2)[li]) + KA(3)[li]) * dtf * 0.125f;
-                    A[li] = A[li] + dy;
-                });
+            // one call site for every stage of every fixed-grid method (stage algebra switches at run time)
+            const int nst = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
+            const float half = 0.5f * dtf;
+            for (int st = 0; st < nst; ++st) {
+                const bool last = st + 1 == nst;
+                adj_eval<NV, BT>(
+                    p, s, st, st > 0, !last,
+                    [&](int b, int j, int li, float ky) {
+                        if (p.method == PHX_MIDPOINT) return Y[li] + ky * half;
+                        if (st == 0) return Y[li] + dtf * ky * third;
+                        if (st == 1) return Y[li] + dtf * (ky - KY(0)[li] * third);
+                        return Y[li] + dtf * (KY(0)[li] - KY(1)[li] + ky);
+                    },
+                    [&](int b, int j, int li, float ka, bool lead) {
+                        float an;
+                        if (p.method == PHX_EULER) {
+                            an = A[li] + dtf * ka;
+                        } else if (p.method == PHX_MIDPOINT) {
+                            an = (st == 0) ? A[li] + ka * half : A[li] + dtf * ka;
+                        } else {
+                            if (st == 0) an = A[li] + dtf * ka * third;
+                            else if (st == 1) an = A[li] + dtf * (ka - KA(0)[li] * third);
+                            else if (st == 2) an = A[li] + dtf * (KA(0)[li] - KA(1)[li] + ka);
+                            else an = A[li] + (KA(0)[li] + 3.f * (KA(1)[li] + KA(2)[li]) + ka) * dtf * 0.125f;
+                        }
+                        if (last && lead) A[li] = an;
+                        return an;
+                    });
             }
+            __syncthreads();
             pf.tick(PT_COMBINE);
             ppass<PP_FIXED, BT>(p, s, g_lo, n_loc, pa, d0, d1);
             pf.tick(PT_PP_STEP);
@@ -1659,71 +1862,74 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                 for (int i = 0; i < 7; ++i) c->slot[i] = i;
             }
             __syncthreads();
-            // f0 and Hairer's initial step under the mixed norm max(RMS_y, RMS_a, RMS_theta)
-            eval(0, false, false, no_next);
-            {
+            // f0 and Hairer's initial step under the mixed norm max(RMS_y, RMS_a, RMS_theta): two evaluations through
+            // one call site
+            for (int which = 0; which < 2; ++which) {
                 double acc[7] = {0, 0, 0, 0, 0, 0, 0};
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float y = Y[li], av = A[li];
-                    float sy = p.atol_f + fabsf(y) * p.rtol_f, sa = p.atol_f + fabsf(av) * p.rtol_f;
-                    float r;
-                    r = y / sy; acc[0] += (double)(r * r);
-                    r = av / sa; acc[1] += (double)(r * r);
-                    r = KY(0)[li] / sy; acc[3] += (double)(r * r);
-                    r = KA(0)[li] / sa; acc[4] += (double)(r * r);
-                    if (!isfinite(y) || !isfinite(av)) acc[6] += 1.0;
+                adj_eval<NV, BT>(p, s, which, false, false, no_y, [&](int b, int j, int li, float ka, bool lead) {
+                    if (lead) {
+                        float y = Y[li], av = A[li];
+                        float sy = p.atol_f + fabsf(y) * p.rtol_f, sa = p.atol_f + fabsf(av) * p.rtol_f;
+                        float r;
+                        if (which == 0) {
+                            r = y / sy; acc[0] += (double)(r * r);
+                            r = av / sa; acc[1] += (double)(r * r);
+                            r = KY(0)[li] / sy; acc[3] += (double)(r * r);
+                            r = ka / sa; acc[4] += (double)(r * r);
+                            if (!isfinite(y) || !isfinite(av)) acc[6] += 1.0;
+                        } else {
+                            r = (KY(1)[li] - KY(0)[li]) / sy; acc[0] += (double)(r * r);
+                            r = (ka - KA(0)[li]) / sa; acc[1] += (double)(r * r);
+                        }
+                    }
+                    return 0.f;
                 });
+                __syncthreads();
                 PPArgs pa;
                 pa.src = theta_zero ? nullptr : theta[cur];
                 pa.dst = nullptr;
                 pa.s0 = 0;
                 pa.s1 = 1;
                 pf.tick(PT_COMBINE);
-                if (theta_zero) acc[5] += theta_zero_norm<BT>(p, s, n_loc, 0, -1);
-                else ppass<PP_D01, BT>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
-                pf.tick(PT_PP_D01);
-                block_sum_d<7>(acc, s.dred(), c->dsum);
-                grid_sum_d(p, s, c->dsum, 7);
-                pf.tick(PT_NORMS);
-                if (threadIdx.x == 0) {
-                    float d0 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
-                                     sqrtf((float)(c->dsum[2] / Pel)));
-                    float d1 = fmaxf(fmaxf(sqrtf((float)(c->dsum[3] / Nel)), sqrtf((float)(c->dsum[4] / Nel))),
-                                     sqrtf((float)(c->dsum[5] / Pel)));
-                    c->d1 = d1;
-                    c->h0 = init_h0(d0, d1);
-                    c->nonfinite_prev = c->dsum[6] > 0.0;
+                if (which == 0) {
+                    if (theta_zero) acc[5] += theta_zero_norm<BT>(p, s, n_loc, 0, -1);
+                    else ppass<PP_D01, BT>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
+                    pf.tick(PT_PP_D01);
+                    block_sum_d<7>(acc, s.dred(), c->dsum);
+                    grid_sum_d(p, s, c->dsum, 7);
+                    pf.tick(PT_NORMS);
+                    if (threadIdx.x == 0) {
+                        float d0 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
+                                         sqrtf((float)(c->dsum[2] / Pel)));
+                        float d1 = fmaxf(fmaxf(sqrtf((float)(c->dsum[3] / Nel)), sqrtf((float)(c->dsum[4] / Nel))),
+                                         sqrtf((float)(c->dsum[5] / Pel)));
+                        c->d1 = d1;
+                        c->h0 = init_h0(d0, d1);
+                        c->nonfinite_prev = c->dsum[6] > 0.0;
+                    }
+                    __syncthreads();
+                    const float h0 = c->h0;
+                    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
+                        set_y_input(s.ysb(), s.acts(), s.actl(), li, Y[li] + h0 * KY(0)[li]);
+                        set_a_input(li, j, A[li] + h0 * KA(0)[li]);
+                    });
+                    __syncthreads();
+                } else {
+                    double dummy = 0;
+                    if (theta_zero) acc[2] += theta_zero_norm<BT>(p, s, n_loc, 1, 0);
+                    else ppass<PP_D2, BT>(p, s, g_lo, n_loc, pa, acc[2], dummy);
+                    pf.tick(PT_PP_D2);
+                    block_sum_d<7>(acc, s.dred(), c->dsum);
+                    grid_sum_d(p, s, c->dsum, 3);
+                    pf.tick(PT_NORMS);
+                    if (threadIdx.x == 0) {
+                        float d2 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
+                                         sqrtf((float)(c->dsum[2] / Pel))) / c->h0;
+                        c->dt = init_dt(c->h0, c->d1, d2);
+                        c->n_rhs += 2;
+                    }
+                    __syncthreads();
                 }
-                __syncthreads();
-                const float h0 = c->h0;
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    set_y_input(s.ysb(), s.acts(), s.actl(), li, Y[li] + h0 * KY(0)[li]);
-                    set_a_input(li, j, A[li] + h0 * KA(0)[li]);
-                });
-                __syncthreads();
-                eval(1, false, false, no_next);
-                double acc2[3] = {0, 0, 0};
-                for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                    float sy = p.atol_f + fabsf(Y[li]) * p.rtol_f, sa = p.atol_f + fabsf(A[li]) * p.rtol_f;
-                    float r;
-                    r = (KY(1)[li] - KY(0)[li]) / sy; acc2[0] += (double)(r * r);
-                    r = (KA(1)[li] - KA(0)[li]) / sa; acc2[1] += (double)(r * r);
-                });
-                double dummy = 0;
-                pf.tick(PT_COMBINE);
-                if (theta_zero) acc2[2] += theta_zero_norm<BT>(p, s, n_loc, 1, 0);
-                else ppass<PP_D2, BT>(p, s, g_lo, n_loc, pa, acc2[2], dummy);
-                pf.tick(PT_PP_D2);
-                block_sum_d<3>(acc2, s.dred(), c->dsum);
-                grid_sum_d(p, s, c->dsum, 3);
-                pf.tick(PT_NORMS);
-                if (threadIdx.x == 0) {
-                    float d2 = fmaxf(fmaxf(sqrtf((float)(c->dsum[0] / Nel)), sqrtf((float)(c->dsum[1] / Nel))),
-                                     sqrtf((float)(c->dsum[2] / Pel))) / c->h0;
-                    c->dt = init_dt(c->h0, c->d1, d2);
-                    c->n_rhs += 2;
-                }
-                __syncthreads();
             }
             bool done = false;
             while (!done) {
@@ -1758,39 +1964,47 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                 }
                 double acc[4] = {0, 0, 0, 0};
                 for (int st = 1; st <= 6; ++st) {
-                    // next stage's y input from ky of stages 0..st (the newest one just computed inside eval)
-                    eval(sl[st], st > 1, st < 6, [&](int li) {
-                        float ay = KY(sl[0])[li] * c->cb[st][0];
-                        for (int q = 1; q <= st; ++q) ay = fmaf(KY(sl[q])[li], c->cb[st][q], ay);
-                        float yn = Y[li] + ay;
-                        if (st == 5) Y1[li] = yn;
-                        return yn;
-                    });
-                    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-                        if (st < 6) {
-                            float aa = KA(sl[0])[li] * c->cb[st][0];
-                            for (int q = 1; q <= st; ++q) aa = fmaf(KA(sl[q])[li], c->cb[st][q], aa);
-                            float an = A[li] + aa;
-                            if (st == 5) A1[li] = an;
-                            set_a_input(li, j, an);
-                        } else {
-                            float ey = KY(sl[0])[li] * c->cerr[0];
-                            float ea = KA(sl[0])[li] * c->cerr[0];
-                            for (int q = 1; q < 7; ++q) {
-                                ey = fmaf(KY(sl[q])[li], c->cerr[q], ey);
-                                ea = fmaf(KA(sl[q])[li], c->cerr[q], ea);
+                    adj_eval<NV, BT>(
+                        p, s, sl[st], st > 1, st < 6,
+                        // next stage's y input from ky of stages 0..st (the newest one still in a register)
+                        [&](int b, int j, int li, float ky) {
+                            float ay = KY(sl[0])[li] * c->cb[st][0];
+                            for (int q = 1; q < st; ++q) ay = fmaf(KY(sl[q])[li], c->cb[st][q], ay);
+                            ay = fmaf(ky, c->cb[st][st], ay);
+                            float yn = Y[li] + ay;
+                            if (st == 5) Y1[li] = yn;
+                            return yn;
+                        },
+                        [&](int b, int j, int li, float ka, bool lead) {
+                            if (st < 6) {
+                                float aa = KA(sl[0])[li] * c->cb[st][0];
+                                for (int q = 1; q < st; ++q) aa = fmaf(KA(sl[q])[li], c->cb[st][q], aa);
+                                aa = fmaf(ka, c->cb[st][st], aa);
+                                float an = A[li] + aa;
+                                if (st == 5 && lead) A1[li] = an;
+                                return an;
                             }
-                            float y1 = s.ysb()[li], a1 = s.asb()[li];
-                            float ty = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[li]), fabsf(y1));
-                            float ta = p.atol_f + p.rtol_f * fmaxf(fabsf(A[li]), fabsf(a1));
-                            float r;
-                            r = ey / ty; acc[0] += (double)(r * r);
-                            r = ea / ta; acc[1] += (double)(r * r);
-                            if (!isfinite(y1) || !isfinite(a1)) acc[3] += 1.0;
-                        }
-                    });
-                    __syncthreads();
+                            if (lead) {
+                                float ey = KY(sl[0])[li] * c->cerr[0];
+                                float ea = KA(sl[0])[li] * c->cerr[0];
+                                for (int q = 1; q < 6; ++q) {
+                                    ey = fmaf(KY(sl[q])[li], c->cerr[q], ey);
+                                    ea = fmaf(KA(sl[q])[li], c->cerr[q], ea);
+                                }
+                                ey = fmaf(KY(sl[6])[li], c->cerr[6], ey);
+                                ea = fmaf(ka, c->cerr[6], ea);
+                                float y1 = s.ysb()[li], a1 = s.asb()[li];
+                                float ty = p.atol_f + p.rtol_f * fmaxf(fabsf(Y[li]), fabsf(y1));
+                                float ta = p.atol_f + p.rtol_f * fmaxf(fabsf(A[li]), fabsf(a1));
+                                float r;
+                                r = ey / ty; acc[0] += (double)(r * r);
+                                r = ea / ta; acc[1] += (double)(r * r);
+                                if (!isfinite(y1) || !isfinite(a1)) acc[3] += 1.0;
+                            }
+                            return 0.f;
+                        });
                 }
+                __syncthreads();
                 PPArgs pa;
                 pa.src = theta_zero ? nullptr : theta[cur];
                 pa.dst = theta_zero ? theta[0] : theta[cur ^ 1];

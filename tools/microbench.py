@@ -27,7 +27,7 @@ def main():
         out = torch.zeros(200 * 1024, device="cuda")
         K2 = 2 * ((H + 3) // 4 * 4)
         sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-        for what, name, n in ((0, "allreduce_f n=K2", K2), (1, "grid_sum_d nd=4", 4), (2, "pass over W1", 0), (3, "pass over WA", 0)):
+        for what, name, n in ((0, "allreduce_f n=K2", K2), (1, "grid_sum_d nd=4", 4), (2, "pass over W1", 0), (3, "fused pass B", 0), (4, "fused pass B+A", 0)):
             iters = 200
             res = []
             for rep in range(3):
