@@ -106,9 +106,11 @@ static inline __host__ __device__ PhxLL phx_ll_view(void* base) {
 #define PHX_RED_WARPS 8   /* slots of the cross-warp column-sum buffer (16 warps fold into 8, then 8 -> 1) */
 struct SmemOff {
     unsigned w1r, war;   // this CTA's gpc rows of W1 / WA when they stay resident in shared memory for the whole solve
+    unsigned watm;       // != PHX_NONE: the WA slice is parked in TENSOR MEMORY (value = smem word that receives the
+                         // tcgen05.alloc base address); each warp keeps its own rows in its own TMEM lanes / columns
     unsigned ring, bar, resbar, ctrl, dred, gram, dst16, ystage, bias, relum, maskm, sp, xv, red, st;
     unsigned acts, actl, ysb, jb, acts2, actl2, ysb2, asb, gjb, ub, vb, mt;
-    unsigned FG, FSP, FS, FL, FGJ, FM;
+    unsigned FG, FSP, FS, FL, FGJ, FM, ppa;
 };
 #define PHX_CTRL_BYTES 1024  /* >= sizeof(Ctrl) in phx_resident.cuh (static_assert there) */
 
@@ -117,6 +119,7 @@ static inline bool phx_use_y(int nCTA, int B, int K2, int adjoint) {
     return (size_t)nCTA * B * K2 * (adjoint ? 2 : 1) <= 4096;
 }
 
+// wa_res: 0 = WA streams through the ring, 1 = resident in shared memory, 2 = resident in tensor memory
 static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoint, int w1_res, int wa_res,
                                      int ring_rows, int ring_stages, SmemOff* o) {
     size_t off = 0;
@@ -132,7 +135,8 @@ static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoi
     const size_t slice = sizeof(float) * (size_t)gpc * K2;
     // bulk-copy targets first (128-byte aligned: every size below is a multiple of 32 bytes)
     t.w1r = w1_res ? take(slice) : none;
-    t.war = wa_res ? take(slice) : none;
+    t.war = wa_res == 1 ? take(slice) : none;
+    t.watm = wa_res == 2 ? take(16) : none;
     // per-warp ring: PHX_WARPS x ring_stages row-sized slots, one mbarrier each
     t.ring = ring_stages ? take(sizeof(float) * (size_t)ring_stages * PHX_WARPS * K2) : none;
     t.bar = take(sizeof(unsigned long long) * (ring_stages ? ring_stages * PHX_WARPS : 1));
@@ -153,7 +157,7 @@ static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoi
     t.st = take((adjoint ? 18 : 9) * bl);
     t.acts = take(bl); t.actl = take(bl); t.ysb = take(bl); t.jb = take(bl);
     t.acts2 = t.actl2 = t.ysb2 = t.asb = t.gjb = t.ub = t.vb = t.mt = none;
-    t.FG = t.FSP = t.FS = t.FL = t.FGJ = t.FM = none;
+    t.FG = t.FSP = t.FS = t.FL = t.FGJ = t.FM = t.ppa = none;
     if (adjoint) {
         t.acts2 = take(bl); t.actl2 = take(bl); t.ysb2 = take(bl); t.asb = take(bl); t.gjb = take(bl);
         t.ub = take(bl); t.vb = take(bl); t.mt = take(bl);
@@ -163,6 +167,7 @@ static inline size_t phx_smem_layout(int nCTA, int B, int K2, int gpc, int adjoi
         t.FL = take(sizeof(float) * gpc * QB);
         t.FGJ = take(sizeof(float) * gpc * QB);
         t.FM = take(sizeof(float) * gpc * 8);
+        t.ppa = take(256);   // PPArgs of the theta passes (phx_resident.cuh)
     }
     if (o) *o = t;
     return off;

@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) mb_pass_kernel(const __grid_co
     s.rg.pre = -1;
     ring_init(p, s);
     resident_wait(p, s);
+    s.tmem = tmem_setup<NV>(p, s);
     for (int i = threadIdx.x; i < p.B * p.gpc; i += THREADS) { s.acts()[i] = 1.f; s.actl()[i] = 0.5f; }
     for (int i = threadIdx.x; i < p.B * p.K2; i += THREADS) s.sp()[i] = 1.f;
     __syncthreads();
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) mb_pass_kernel(const __grid_co
         else fwd_passBA<NV, 1>(p, s, which == 3, [](int, int, int, float f, bool) { return f; });
     }
     ring_drain(p, s);
+    tmem_release(p, s.tmem);
     if (threadIdx.x < p.K2) out[(size_t)blockIdx.x * p.K2 + threadIdx.x] = s.sp()[threadIdx.x];
 }
 

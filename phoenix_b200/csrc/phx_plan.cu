@@ -1,4 +1,5 @@
 // Host-side planning of the resident solver launches (grid size, shared-memory and workspace layout).
+#include <stdlib.h>
 #include "phx_common.cuh"
 
 int phx_launch_fwd_nv1(const ResParams&, const ResLaunchPlan&, cudaStream_t);
@@ -43,6 +44,27 @@ int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPl
     if (fits(1, 1, 0)) {
         w1r = war = 1;
         ok = true;
+    }
+    // Tensor memory as a second on-chip weight store: 512 columns x 128 lanes x 32 bit per SM.  A warp can only touch
+    // the 32 lanes of its quarter (warp % 4), the four warps of a quarter split the 512 columns, and a row costs
+    // 4 NV columns per lane (the lane's own float4 columns of the row): 32 / NV rows per warp.
+    const int rows_per_warp = (gpc + PHX_WARPS - 1) / PHX_WARPS;
+    const bool tmem_ok = rows_per_warp * 4 * NV <= 128 && !getenv("PHX_NO_TMEM");
+    if (!ok && tmem_ok) {
+        if (fits(1, 2, 0)) {
+            w1r = 1;
+            war = 2;
+            ok = true;
+        } else {
+            for (int stages = 4; stages >= 1 && !ok; --stages) {
+                if (!fits(0, 2, stages)) continue;
+                w1r = 0;
+                war = 2;
+                best_rows = PHX_WARPS;
+                best_stages = stages;
+                ok = true;
+            }
+        }
     }
     for (int res = 1; res >= 0 && !ok; --res) {
         for (int stages = 4; stages >= 1 && !ok; --stages) {

@@ -186,6 +186,7 @@ struct Smem {
     const ResParams& p;
     unsigned o_acts, o_actl, o_ysb, o_acts2, o_actl2, o_ysb2;
     int g_lo, n_loc;
+    uint32_t tmem;   // tensor-memory base address of the parked WA slice (0: not used)
     Xchg x;
     Ring rg;
     Prof pf;
@@ -194,6 +195,7 @@ struct Smem {
           o_actl2(pp.so.actl2), o_ysb2(pp.so.ysb2) {
         g_lo = blockIdx.x * pp.gpc;
         n_loc = max(0, min(pp.gpc, pp.G - g_lo));
+        tmem = 0u;
     }
     template <typename T>
     __device__ __forceinline__ T* at(unsigned off) const { return reinterpret_cast<T*>(smem_raw + off); }
@@ -244,7 +246,7 @@ struct Smem {
 
 // ---- block reductions and grid-wide exchanges -------------------------------------------------------------------------
 template <int N>
-__device__ __noinline__ void block_sum_d(double (&v)[N], double* dred, double* out) {
+__device__ __forceinline__ void block_sum_d(double (&v)[N], double* dred, double* out) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 #pragma unroll
     for (int i = 0; i < N; ++i) {
@@ -265,7 +267,7 @@ __device__ __noinline__ void block_sum_d(double (&v)[N], double* dred, double* o
 // adds them in a fixed order (one warp per value, lanes over CTAs, fixed butterfly) and posts the totals in R
 // replicas, every CTA reads one replica: each hop is one L2 round trip and no slot is polled by more than nCTA / R
 // readers.
-__device__ __noinline__ void grid_sum_d(const ResParams& p, Smem& s, double* vals, int nd) {
+__device__ __forceinline__ void grid_sum_d(const ResParams& p, Smem& s, double* vals, int nd) {
     Xchg& x = s.x;
     const int nC = gridDim.x;
     if (nC == 1) return;
@@ -279,24 +281,24 @@ __device__ __noinline__ void grid_sum_d(const ResParams& p, Smem& s, double* val
         ll_put(p.ll.dpart + (size_t)blockIdx.x * PHX_LL_DMAX + threadIdx.x, w, tag);
     }
     if (blockIdx.x == 0 && warp < nd) {
+        // every round (re)polls all five CTAs of the lane in one round trip; lanes past the grid re-read the last CTA
+        // (unconditional loads keep the slots in registers)
         unsigned long long w0[5], w1[5];
-        unsigned need = 0;
+        bool ok;
+        do {
+            ok = true;
 #pragma unroll
-        for (int u = 0; u < 5; ++u)
-            if (lane + 32 * u < nC) need |= 1u << u;
-        while (need) {   // every pending slot is (re)polled in the same round trip
+            for (int u = 0; u < 5; ++u) {
+                const int c = min(lane + 32 * u, nC - 1);
+                ll_ld2(p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * warp, w0[u], w1[u]);
+            }
 #pragma unroll
-            for (int u = 0; u < 5; ++u)
-                if (need & (1u << u)) ll_ld2(p.ll.dpart + (size_t)(lane + 32 * u) * PHX_LL_DMAX + 2 * warp, w0[u], w1[u]);
-#pragma unroll
-            for (int u = 0; u < 5; ++u)
-                if ((need & (1u << u)) && (unsigned)(w0[u] >> 32) == tag && (unsigned)(w1[u] >> 32) == tag) need &= ~(1u << u);
-        }
+            for (int u = 0; u < 5; ++u) ok = ok && (unsigned)(w0[u] >> 32) == tag && (unsigned)(w1[u] >> 32) == tag;
+        } while (!ok);
         double t = 0;
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
-            int c = lane + 32 * u;
-            if (c < nC) {
+            if (lane + 32 * u < nC) {
                 float hi = __uint_as_float((unsigned)w0[u]), lo = __uint_as_float((unsigned)w1[u]);
                 t += isfinite(hi) ? ((double)hi + (double)lo) : (double)hi;
             }
@@ -335,21 +337,21 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
         const int tot = nC * n;
         for (int e0 = 2 * threadIdx.x; e0 < tot; e0 += 8 * THREADS) {
             unsigned long long w[4][2];
-            unsigned need = 0;
+            bool ok;
+            do {   // all four pairs are (re)polled in the same round trip (past the end: the last pair again)
+                ok = true;
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (e0 + u * 2 * THREADS < tot) need |= 1u << u;
-            while (need) {   // every pending pair is (re)polled in the same round trip
+                for (int u = 0; u < 4; ++u) ll_ld2(base + min(e0 + u * 2 * THREADS, tot - 2), w[u][0], w[u][1]);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if (need & (1u << u)) ll_ld2(base + e0 + u * 2 * THREADS, w[u][0], w[u][1]);
+                for (int u = 0; u < 4; ++u) ok = ok && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag;
+            } while (!ok);
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    if ((need & (1u << u)) && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag) {
-                        need &= ~(1u << u);
-                        s.ystage()[e0 + u * 2 * THREADS] = __uint_as_float((unsigned)w[u][0]);
-                        s.ystage()[e0 + u * 2 * THREADS + 1] = __uint_as_float((unsigned)w[u][1]);
-                    }
+            for (int u = 0; u < 4; ++u) {
+                const int e = e0 + u * 2 * THREADS;
+                if (e < tot) {
+                    s.ystage()[e] = __uint_as_float((unsigned)w[u][0]);
+                    s.ystage()[e + 1] = __uint_as_float((unsigned)w[u][1]);
+                }
             }
         }
         __syncthreads();
@@ -365,26 +367,22 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
     for (int i = 2 * threadIdx.x; i < n; i += 2 * THREADS) ll_put2(mine + i, vec[i], vec[i + 1], tag);
     const int nq = n >> 2;
     for (int q = blockIdx.x + nC * warp; q < nq; q += nC * WARPS) {
+        // every round (re)polls all five CTAs of the lane in one round trip; lanes past the grid re-read the last CTA
         unsigned long long w[5][4];
-        const unsigned long long* src0 = p.ll.xpart + (size_t)lane * PHX_LL_NMAX + 4 * q;
-        unsigned need = 0;
-#pragma unroll
-        for (int u = 0; u < 5; ++u)
-            if (lane + 32 * u < nC) need |= 3u << (2 * u);
-        while (need) {   // every pending pair is (re)polled in the same round trip
+        bool ok;
+        do {
+            ok = true;
 #pragma unroll
             for (int u = 0; u < 5; ++u) {
-                if (need & (1u << (2 * u))) ll_ld2(src0 + (size_t)32 * u * PHX_LL_NMAX, w[u][0], w[u][1]);
-                if (need & (2u << (2 * u))) ll_ld2(src0 + (size_t)32 * u * PHX_LL_NMAX + 2, w[u][2], w[u][3]);
+                const unsigned long long* src = p.ll.xpart + (size_t)min(lane + 32 * u, nC - 1) * PHX_LL_NMAX + 4 * q;
+                ll_ld2(src, w[u][0], w[u][1]);
+                ll_ld2(src + 2, w[u][2], w[u][3]);
             }
 #pragma unroll
-            for (int u = 0; u < 5; ++u) {
-                if ((need & (1u << (2 * u))) && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag)
-                    need &= ~(1u << (2 * u));
-                if ((need & (2u << (2 * u))) && (unsigned)(w[u][2] >> 32) == tag && (unsigned)(w[u][3] >> 32) == tag)
-                    need &= ~(2u << (2 * u));
-            }
-        }
+            for (int u = 0; u < 5; ++u)
+                ok = ok && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag &&
+                     (unsigned)(w[u][2] >> 32) == tag && (unsigned)(w[u][3] >> 32) == tag;
+        } while (!ok);
         float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll
         for (int u = 0; u < 5; ++u) {
@@ -440,9 +438,132 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
 enum { MAT_W1 = 0, MAT_WA = 1, MAT_NONE = -1 };
 
 __device__ __forceinline__ bool mat_resident(const ResParams& p, int which) {
-    return (which == MAT_W1 ? p.so.w1r : p.so.war) != PHX_NONE;
+    return (which == MAT_W1 ? p.so.w1r : p.so.war) != PHX_NONE || (which == MAT_WA && p.so.watm != PHX_NONE);
 }
 __device__ __forceinline__ const float4* mat_global(const Smem& s, int which) { return which == MAT_W1 ? s.w1g() : s.wag(); }
+
+// ---- tensor memory as a weight store ---------------------------------------------------------------------------------
+// TMEM (256 KB per SM: 128 lanes x 512 columns x 32 bit) normally holds tcgen05.mma accumulators; the B = 1 solves do
+// GEMV-shaped work that never touches the tensor cores, so the whole TMEM is free and serves as a second on-chip home
+// for weights next to shared memory: the CTA's WA slice is written there once (tcgen05.st) and every pass reads its
+// rows back with tcgen05.ld (LDTM) straight into the registers of the lanes that own the columns -- no L2 traffic, no
+// shared-memory bandwidth.  Warp w may only touch lanes 32 (w % 4) .. + 31; the four warps of a quarter take 128
+// columns each; row i of the warp occupies columns 4 NV i .. of every lane (the lane's float4 columns l + 32 v).
+template <int NV>
+__device__ __forceinline__ void tmem_ld_row(uint32_t taddr, float4 (&w)[NV]) {
+    uint32_t u[4 * NV];
+    if constexpr (NV == 1) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3])
+                     : "r"(taddr));
+    } else if constexpr (NV == 2) {
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                     : "r"(taddr));
+    } else {
+        static_assert(NV == 4, "NV must be 1, 2 or 4");
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+            : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+              "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+            : "r"(taddr));
+    }
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+        w[v] = make_float4(__uint_as_float(u[4 * v]), __uint_as_float(u[4 * v + 1]), __uint_as_float(u[4 * v + 2]),
+                           __uint_as_float(u[4 * v + 3]));
+}
+template <int NV>
+__device__ __forceinline__ void tmem_st_row(uint32_t taddr, const float4 (&w)[NV]) {
+    uint32_t u[4 * NV];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        u[4 * v] = __float_as_uint(w[v].x);
+        u[4 * v + 1] = __float_as_uint(w[v].y);
+        u[4 * v + 2] = __float_as_uint(w[v].z);
+        u[4 * v + 3] = __float_as_uint(w[v].w);
+    }
+    if constexpr (NV == 1) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(taddr), "r"(u[0]), "r"(u[1]),
+                     "r"(u[2]), "r"(u[3])
+                     : "memory");
+    } else if constexpr (NV == 2) {
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr), "r"(u[0]),
+                     "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7])
+                     : "memory");
+    } else {
+        asm volatile(
+            "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+                taddr),
+            "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+            "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+            : "memory");
+    }
+}
+// TMEM address of row i of this warp
+template <int NV>
+__device__ __forceinline__ uint32_t tmem_row_addr(uint32_t base, int i) {
+    const int warp = threadIdx.x >> 5;
+    return base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * 128 + i * 4 * NV);
+}
+
+// allocate all 512 columns (one CTA per SM) and park this CTA's WA rows; every warp fills its own rows
+template <int NV>
+__device__ __forceinline__ uint32_t tmem_setup(const ResParams& p, const Smem& s) {
+    if (p.so.watm == PHX_NONE) return 0u;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t* slot = s.at<uint32_t>(p.so.watm);
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(512u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t base = *slot;
+    const int nw = (s.n_loc > warp) ? (s.n_loc - warp + WARPS - 1) / WARPS : 0;
+    const float4* mat = s.wag();
+    for (int i = 0; i < nw; ++i) {
+        const float4* row = mat + (size_t)(warp + WARPS * i) * p.K2q;
+        float4 w[NV];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            int q = lane + 32 * v;
+            w[v] = (q < p.K2q) ? __ldg(row + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        tmem_st_row<NV>(tmem_row_addr<NV>(base, i), w);
+    }
+    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    return base;
+}
+__device__ __forceinline__ void tmem_release(const ResParams& p, uint32_t base) {
+    if (p.so.watm == PHX_NONE) return;
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if ((threadIdx.x >> 5) == 0)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
+}
+
+// where a pass finds a row: shared memory (resident slice or ring slot) or tensor memory
+struct RowSrc {
+    const float4* sm;
+    uint32_t tm;
+};
+template <int NV>
+__device__ __forceinline__ void load_row_src(const RowSrc& src, int K2q, float4 (&w)[NV]) {
+    if (src.sm) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            int q = lane + 32 * v;
+            w[v] = (q < K2q) ? src.sm[q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    } else {
+        tmem_ld_row<NV>(src.tm, w);
+    }
+}
 
 // barriers + the one-time copy of the resident slices (all threads wait for it before the first pass)
 __device__ __forceinline__ void ring_init(const ResParams& p, const Smem& s) {
@@ -553,19 +674,26 @@ __device__ __forceinline__ void mat_pass(const ResParams& p, Smem& s, int which,
 // j = warp + 16 (g0 + r) together: one interleaved butterfly for all their dot products, the per-element algebra on
 // one lane per element, and whatever needs the results.  The latency chain of a pass is paid once per group instead
 // of once per row.
-template <int RG, typename RowFn, typename GroupFn>
+template <int NV, int RG, typename RowFn, typename GroupFn>
 __device__ __forceinline__ void mat_pass_grouped(const ResParams& p, Smem& s, int which, RowFn row_fn, GroupFn group_fn) {
     Ring& r = s.rg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const unsigned roff = (which == MAT_W1) ? p.so.w1r : p.so.war;
     const int nw = warp_rows(s);
-    if (roff != PHX_NONE) {
-        const float4* base = s.at<float4>(roff);
+    const bool in_tmem = which == MAT_WA && p.so.watm != PHX_NONE;
+    if (roff != PHX_NONE || in_tmem) {
+        const float4* base = in_tmem ? nullptr : s.at<float4>(roff);
         for (int g0 = 0; g0 < nw; g0 += RG) {
             const int ng = min(RG, nw - g0);
 #pragma unroll
-            for (int q = 0; q < RG; ++q)
-                if (q < ng) row_fn(q, warp + WARPS * (g0 + q), base + (size_t)(warp + WARPS * (g0 + q)) * p.K2q);
+            for (int q = 0; q < RG; ++q) {
+                if (q < ng) {
+                    RowSrc src;
+                    src.sm = in_tmem ? nullptr : base + (size_t)(warp + WARPS * (g0 + q)) * p.K2q;
+                    src.tm = in_tmem ? tmem_row_addr<NV>(s.tmem, g0 + q) : 0u;
+                    row_fn(q, warp + WARPS * (g0 + q), src);
+                }
+            }
             group_fn(g0, ng);
         }
         __syncthreads();
@@ -586,7 +714,10 @@ __device__ __forceinline__ void mat_pass_grouped(const ResParams& p, Smem& s, in
                 const int i = g0 + q, sl = i % S;
                 mbar_wait(smem_u32(s.bar() + warp * S + sl), (r.par >> sl) & 1u);
                 r.par ^= 1u << sl;
-                row_fn(q, warp + WARPS * i, s.ring() + (size_t)(warp * S + sl) * p.K2q);
+                RowSrc src;
+                src.sm = s.ring() + (size_t)(warp * S + sl) * p.K2q;
+                src.tm = 0u;
+                row_fn(q, warp + WARPS * i, src);
                 __syncwarp();
                 if (lane == 0 && i + S < nw) ring_issue(p, s, mat, i + S);
             }
@@ -801,11 +932,11 @@ __device__ __forceinline__ void fwd_passBA(const ResParams& p, Smem& s, bool do_
         const int nb = min(PB, p.B - b0);
         acc_zero<NV, PB>(acc);
         float d[RG * PB] = {};
-        mat_pass_grouped<RG>(
+        mat_pass_grouped<NV, RG>(
             p, s, MAT_WA,
-            [&](int r, int j, const float4* row) {
+            [&](int r, int j, const RowSrc& row) {
                 float4 w[NV];
-                load_row<NV>(row, K2q, w);
+                load_row_src<NV>(row, K2q, w);
 #pragma unroll
                 for (int b = 0; b < PB; ++b)
                     d[r * PB + b] = (b < nb) ? row_dot_partial<NV>(w, sp4 + (size_t)(b0 + b) * K2q, K2q) : 0.f;
@@ -877,11 +1008,11 @@ __device__ __forceinline__ void adj_pass1(const ResParams& p, Smem& s, int slot,
         acc_zero<NV, PB>(accg);
         acc_zero<NV, PB>(acca);
         float d[RG * PB] = {};
-        mat_pass_grouped<RG>(
+        mat_pass_grouped<NV, RG>(
             p, s, MAT_WA,
-            [&](int r, int j, const float4* row) {
+            [&](int r, int j, const RowSrc& row) {
                 float4 w[NV];
-                load_row<NV>(row, K2q, w);
+                load_row_src<NV>(row, K2q, w);
                 float gj[PB];
 #pragma unroll
                 for (int b = 0; b < PB; ++b) {
@@ -962,11 +1093,11 @@ __device__ __forceinline__ void adj_pass2(const ResParams& p, Smem& s, int slot,
     for (int b0 = 0; b0 < p.B; b0 += PB) {
         const int nb = min(PB, p.B - b0);
         float du[RG * PB] = {}, dv[RG * PB] = {};
-        mat_pass_grouped<RG>(
+        mat_pass_grouped<NV, RG>(
             p, s, MAT_W1,
-            [&](int r, int j, const float4* row) {
+            [&](int r, int j, const RowSrc& row) {
                 float4 w[NV];
-                load_row<NV>(row, K2q, w);
+                load_row_src<NV>(row, K2q, w);
 #pragma unroll
                 for (int b = 0; b < PB; ++b) {
                     float tu = 0.f, tv = 0.f;
@@ -1143,7 +1274,7 @@ __device__ __forceinline__ void epilogue_epoch(const ResParams& p, const Smem& s
 
 // Stand-alone pass A at the stage input (acts / actl) + its exchange: leaves the finalised branch vector in s.sp().
 template <int NV, int BT>
-__device__ __noinline__ void eval_A(const ResParams& __restrict__ p, Smem& __restrict__ s) {
+__device__ __forceinline__ void eval_A(const ResParams& __restrict__ p, Smem& __restrict__ s) {
     Prof& pf = s.pf;
     pf.tick(PT_COMBINE);
     passA<NV, BT>(p, s, s.acts(), s.actl(), s.sp(), MAT_WA);
@@ -1177,6 +1308,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     Smem s(p);
     const int g_lo = s.g_lo, n_loc = s.n_loc;
     prologue(p, s);
+    s.tmem = tmem_setup<NV>(p, s);
     Prof& pf = s.pf;
     Ctrl* c = s.ctrl();
     const size_t BG = (size_t)p.B * p.G;
@@ -1251,7 +1383,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
         ring_drain(p, s);
         pf.tick(PT_CTRL);
         pf.finish();
-        epilogue_epoch(p, s);
+        tmem_release(p, s.tmem);
+    epilogue_epoch(p, s);
         write_status(p, c, PHX_ST_OK);
         return;
     }
@@ -1324,9 +1457,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
             code = c->stop;
             break;
         }
-        int sl[7];
-#pragma unroll
-        for (int i = 0; i < 7; ++i) sl[i] = c->slot[i];
+        const int* sl = c->slot;   // FSAL slot permutation, read from shared memory (a dynamically indexed local array
+                                   // would live in local memory)
         {
             const float c00 = c->cb[0][0];
             const float* K0 = K(sl[0]);
@@ -1416,6 +1548,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     ring_drain(p, s);
     pf.tick(PT_CTRL);
     pf.finish();
+    tmem_release(p, s.tmem);
     epilogue_epoch(p, s);
     write_status(p, c, code);
 }
@@ -1566,16 +1699,19 @@ __device__ __forceinline__ void pp_block(const float atol_f, const float rtol_f,
 }
 
 // One pass over this CTA's share of the P-long parameter-cotangent vector.
+struct PPSums {
+    double a0, a1;
+};
+// (returns its two partial sums BY VALUE and builds its own shared-memory view: nothing of the caller's per-thread
+// state may have its address taken, or it would live in local memory for the whole kernel)
+static_assert(sizeof(PPArgs) <= 256, "PPArgs must fit its shared-memory slot");
 template <int MODE, int BT>
-__device__ __noinline__ void ppass(const ResParams& __restrict__ p, const Smem& s, int g_lo, int n_loc,
-                                   const PPArgs& a_in, double& acc0_out, double& acc1_out) {
-    // private copies: the stores to theta may not force reloads of the coefficients (they cannot alias a local)
-    const PPArgs a = a_in;
+__device__ __noinline__ PPSums ppass(const ResParams& __restrict__ p, int g_lo, int n_loc) {
+    const Smem s(p);
+    // the arguments travel through shared memory (written by thread 0, block barrier before the call); private copy:
+    // the stores to theta may not force reloads of the coefficients
+    const PPArgs a = *s.at<PPArgs>(p.so.ppa);
     double acc0 = 0, acc1 = 0;
-    struct Fin {
-        double &o0, &o1, &a0, &a1;
-        __device__ ~Fin() { o0 += a0; o1 += a1; }
-    } fin{acc0_out, acc1_out, acc0, acc1};
     constexpr int NK = PPSlots<MODE>::NK;
     constexpr int QB = (7 * BT + 3) & ~3;
     const PhxGradOff off = phx_grad_offsets(p.G, p.H);
@@ -1596,7 +1732,7 @@ __device__ __noinline__ void ppass(const ResParams& __restrict__ p, const Smem& 
                 theta_elem<MODE>(atol_f, rtol_f, a, off.bp + h, k, acc0, acc1);
                 theta_elem<MODE>(atol_f, rtol_f, a, off.bs + h, k, acc0, acc1);
             }
-        return;
+        return PPSums{acc0, acc1};
     }
     // m
     for (int j = threadIdx.x; j < n_loc; j += THREADS) {
@@ -1630,6 +1766,7 @@ __device__ __noinline__ void ppass(const ResParams& __restrict__ p, const Smem& 
             theta_elem<MODE>(atol_f, rtol_f, a, (prod ? off.bp + (h - H) : off.bs + h), k, acc0, acc1);
         }
     }
+    return PPSums{acc0, acc1};
 }
 
 // sum over (r, c) of (sum_m sgn_m U[r][idx_m] V[c][idx_m])^2 through the two M x M Gram matrices (theta == 0 norms:
@@ -1659,7 +1796,8 @@ __device__ __noinline__ double gram_sq(const Smem& s, const float* U, int R, con
 // this thread's share of the sum over this CTA's theta elements of (k / atol)^2 with k = k[s1] - k[s0]
 // (s0 < 0: k = k[s1]); valid while theta == 0 (scale = atol, misc.py:63).
 template <int BT>
-__device__ __noinline__ double theta_zero_norm(const ResParams& p, const Smem& s, int n_loc, int s1, int s0) {
+__device__ __noinline__ double theta_zero_norm(const ResParams& p, int n_loc, int s1, int s0) {
+    const Smem s(p);
     constexpr int QB = (7 * BT + 3) & ~3;
     int idx[8];
     float sgn[8];
@@ -1742,6 +1880,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
     Smem s(p);
     const int g_lo = s.g_lo, n_loc = s.n_loc;
     prologue(p, s);
+    s.tmem = tmem_setup<NV>(p, s);
     Prof& pf = s.pf;
     Ctrl* c = s.ctrl();
     const size_t BG = (size_t)p.B * p.G;
@@ -1757,7 +1896,6 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
     auto KA = [&](int i) { return s.st() + (11 + i) * BL; };
     int cur = 0;             // which theta buffer holds the current value (meaningful once !theta_zero)
     bool theta_zero = true;  // the accumulator has not been written yet: it is identically zero and never read
-    float* theta[2] = {p.theta0, p.theta1};
 
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
@@ -1806,12 +1944,13 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
         if (p.method != PHX_DOPRI5) {
             const float dtf = p.t_is_f32 ? ((float)tget(p, iv) - (float)tget(p, iv - 1)) : (float)(tget(p, iv) - tget(p, iv - 1));
             const float third = (float)(1.0 / 3.0);
-            PPArgs pa;
-            pa.src = theta_zero ? nullptr : theta[0];
-            pa.dst = theta[0];
-            pa.dtf = dtf;
-            pa.method = p.method;
-            double d0 = 0, d1 = 0;
+            if (threadIdx.x == 0) {
+                PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
+                pa.src = theta_zero ? nullptr : p.theta0;
+                pa.dst = p.theta0;
+                pa.dtf = dtf;
+                pa.method = p.method;
+            }
             // one call site for every stage of every fixed-grid method (stage algebra switches at run time)
             const int nst = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
             const float half = 0.5f * dtf;
@@ -1843,7 +1982,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
             }
             __syncthreads();
             pf.tick(PT_COMBINE);
-            ppass<PP_FIXED, BT>(p, s, g_lo, n_loc, pa, d0, d1);
+            ppass<PP_FIXED, BT>(p, g_lo, n_loc);
             pf.tick(PT_PP_STEP);
             theta_zero = false;
             if (threadIdx.x == 0) {
@@ -1884,16 +2023,22 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                     }
                     return 0.f;
                 });
+                if (threadIdx.x == 0) {
+                    PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
+                    pa.src = theta_zero ? nullptr : (cur ? p.theta1 : p.theta0);
+                    pa.dst = nullptr;
+                    pa.s0 = 0;
+                    pa.s1 = 1;
+                }
                 __syncthreads();
-                PPArgs pa;
-                pa.src = theta_zero ? nullptr : theta[cur];
-                pa.dst = nullptr;
-                pa.s0 = 0;
-                pa.s1 = 1;
                 pf.tick(PT_COMBINE);
                 if (which == 0) {
-                    if (theta_zero) acc[5] += theta_zero_norm<BT>(p, s, n_loc, 0, -1);
-                    else ppass<PP_D01, BT>(p, s, g_lo, n_loc, pa, acc[2], acc[5]);
+                    if (theta_zero) acc[5] += theta_zero_norm<BT>(p, n_loc, 0, -1);
+                    else {
+                        PPSums ps = ppass<PP_D01, BT>(p, g_lo, n_loc);
+                        acc[2] += ps.a0;
+                        acc[5] += ps.a1;
+                    }
                     pf.tick(PT_PP_D01);
                     block_sum_d<7>(acc, s.dred(), c->dsum);
                     grid_sum_d(p, s, c->dsum, 7);
@@ -1915,9 +2060,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                     });
                     __syncthreads();
                 } else {
-                    double dummy = 0;
-                    if (theta_zero) acc[2] += theta_zero_norm<BT>(p, s, n_loc, 1, 0);
-                    else ppass<PP_D2, BT>(p, s, g_lo, n_loc, pa, acc[2], dummy);
+                    if (theta_zero) acc[2] += theta_zero_norm<BT>(p, n_loc, 1, 0);
+                    else acc[2] += ppass<PP_D2, BT>(p, g_lo, n_loc).a0;
                     pf.tick(PT_PP_D2);
                     block_sum_d<7>(acc, s.dred(), c->dsum);
                     grid_sum_d(p, s, c->dsum, 3);
@@ -1951,9 +2095,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                     code = c->stop;
                     break;
                 }
-                int sl[7];
-#pragma unroll
-                for (int i = 0; i < 7; ++i) sl[i] = c->slot[i];
+                const int* sl = c->slot;   // FSAL slot permutation, read from shared memory
                 {
                     const float c00 = c->cb[0][0];
                     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
@@ -2004,22 +2146,28 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                             return 0.f;
                         });
                 }
-                __syncthreads();
-                PPArgs pa;
-                pa.src = theta_zero ? nullptr : theta[cur];
-                pa.dst = theta_zero ? theta[0] : theta[cur ^ 1];
-                pa.dtf = c->dtf;
-                pa.last = c->last;
-                for (int q = 0; q < 7; ++q) {
-                    pa.coef_sol[sl[q]] = (q < 6) ? c->cb[5][q] : 0.f;
-                    pa.coef_err[sl[q]] = c->cerr[q];
-                    pa.coef_mid[sl[q]] = c->cmid[q];
+                if (threadIdx.x == 0) {
+                    PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
+                    pa.src = theta_zero ? nullptr : (cur ? p.theta1 : p.theta0);
+                    pa.dst = theta_zero ? p.theta0 : (cur ? p.theta0 : p.theta1);
+                    pa.dtf = c->dtf;
+                    pa.last = c->last;
+                    for (int q = 0; q < 7; ++q) {
+                        pa.coef_sol[sl[q]] = (q < 6) ? c->cb[5][q] : 0.f;
+                        pa.coef_err[sl[q]] = c->cerr[q];
+                        pa.coef_mid[sl[q]] = c->cmid[q];
+                    }
+                    pa.slot_first = sl[0];
+                    pa.slot_last = sl[6];
+                    for (int q = 0; q < 4; ++q) pa.xs[q] = c->xs[q];
                 }
-                pa.slot_first = sl[0];
-                pa.slot_last = sl[6];
-                for (int q = 0; q < 4; ++q) pa.xs[q] = c->xs[q];
+                __syncthreads();
                 pf.tick(PT_COMBINE);
-                ppass<PP_STEP, BT>(p, s, g_lo, n_loc, pa, acc[2], acc[3]);
+                {
+                    PPSums ps = ppass<PP_STEP, BT>(p, g_lo, n_loc);
+                    acc[2] += ps.a0;
+                    acc[3] += ps.a1;
+                }
                 pf.tick(PT_PP_STEP);
                 block_sum_d<4>(acc, s.dred(), c->dsum);
                 grid_sum_d(p, s, c->dsum, 4);
@@ -2087,20 +2235,23 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
         // nothing was ever written (a solver assertion fired before the first accepted step): report zeros
         const size_t tot = goff.total;
         for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < tot; i += (size_t)gridDim.x * THREADS)
-            theta[0][i] = 0.f;
+            p.theta0[i] = 0.f;
     } else if (cur != 0) {
         // the last accepted step landed in the scratch twin
-        PPArgs pa;
-        pa.src = theta[1];
-        pa.dst = theta[0];
-        double d0 = 0, d1 = 0;
-        ppass<PP_COPY, BT>(p, s, g_lo, n_loc, pa, d0, d1);
+        if (threadIdx.x == 0) {
+            PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
+            pa.src = p.theta1;
+            pa.dst = p.theta0;
+        }
+        __syncthreads();
+        ppass<PP_COPY, BT>(p, g_lo, n_loc);
     }
     pf.tick(PT_PP_COPY);
     __syncthreads();
     ring_drain(p, s);
     pf.tick(PT_CTRL);
     pf.finish();
+    tmem_release(p, s.tmem);
     epilogue_epoch(p, s);
     write_status(p, c, code);
 }
