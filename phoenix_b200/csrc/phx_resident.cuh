@@ -858,6 +858,29 @@ __device__ __forceinline__ float row_dot_partial(const float4 (&w)[NV], const fl
     return t0 + t1;
 }
 
+// the lane's own float4 columns of PB K2-long vectors (x[b][:], shared memory) into registers: the passes dot every
+// row with the same vectors, so they are loaded once per pass instead of once per row
+template <int NV, int PB>
+__device__ __forceinline__ void hoist_vec(const float4* x4, int K2q, int nb, float4 (&x)[PB][NV]) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int b = 0; b < PB; ++b)
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+            int q = lane + 32 * v;
+            x[b][v] = (b < nb && q < K2q) ? x4[b * K2q + q] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+}
+template <int NV>
+__device__ __forceinline__ float row_dot_reg(const float4 (&w)[NV], const float4 (&x)[NV]) {
+    float t0 = 0.f, t1 = 0.f;
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+        if (v & 1) t1 += dot4(w[v], x[v]); else t0 += dot4(w[v], x[v]);
+    }
+    return t0 + t1;
+}
+
 // all lanes end up with the warp-wide sums of the N per-lane values (N independent butterflies, interleaved)
 template <int N>
 __device__ __forceinline__ void warp_sum_n(float (&d)[N]) {
@@ -932,14 +955,15 @@ __device__ __forceinline__ void fwd_passBA(const ResParams& p, Smem& s, bool do_
         const int nb = min(PB, p.B - b0);
         acc_zero<NV, PB>(acc);
         float d[RG * PB] = {};
+        float4 x[PB][NV];
+        hoist_vec<NV, PB>(sp4 + (size_t)b0 * K2q, K2q, nb, x);
         mat_pass_grouped<NV, RG>(
             p, s, MAT_WA,
             [&](int r, int j, const RowSrc& row) {
                 float4 w[NV];
                 load_row_src<NV>(row, K2q, w);
 #pragma unroll
-                for (int b = 0; b < PB; ++b)
-                    d[r * PB + b] = (b < nb) ? row_dot_partial<NV>(w, sp4 + (size_t)(b0 + b) * K2q, K2q) : 0.f;
+                for (int b = 0; b < PB; ++b) d[r * PB + b] = row_dot_reg<NV>(w, x[b]);
             },
             [&](int g0, int ng) {
                 warp_sum_n<RG * PB>(d);
@@ -1008,6 +1032,8 @@ __device__ __forceinline__ void adj_pass1(const ResParams& p, Smem& s, int slot,
         acc_zero<NV, PB>(accg);
         acc_zero<NV, PB>(acca);
         float d[RG * PB] = {};
+        float4 x[PB][NV];
+        hoist_vec<NV, PB>(sp4 + (size_t)b0 * K2q, K2q, nb, x);
         mat_pass_grouped<NV, RG>(
             p, s, MAT_WA,
             [&](int r, int j, const RowSrc& row) {
@@ -1016,7 +1042,7 @@ __device__ __forceinline__ void adj_pass1(const ResParams& p, Smem& s, int slot,
                 float gj[PB];
 #pragma unroll
                 for (int b = 0; b < PB; ++b) {
-                    d[r * PB + b] = (b < nb) ? row_dot_partial<NV>(w, sp4 + (size_t)(b0 + b) * K2q, K2q) : 0.f;
+                    d[r * PB + b] = row_dot_reg<NV>(w, x[b]);
                     gj[b] = (b < nb) ? s.gjb()[(b0 + b) * p.gpc + j] : 0.f;
                 }
                 axpy1<NV, PB>(w, accg, gj, nb);
@@ -1093,6 +1119,8 @@ __device__ __forceinline__ void adj_pass2(const ResParams& p, Smem& s, int slot,
     for (int b0 = 0; b0 < p.B; b0 += PB) {
         const int nb = min(PB, p.B - b0);
         float du[RG * PB] = {}, dv[RG * PB] = {};
+        float4 x[PB][NV];
+        hoist_vec<NV, PB>(g4 + (size_t)b0 * K2q, K2q, nb, x);
         mat_pass_grouped<NV, RG>(
             p, s, MAT_W1,
             [&](int r, int j, const RowSrc& row) {
@@ -1101,15 +1129,10 @@ __device__ __forceinline__ void adj_pass2(const ResParams& p, Smem& s, int slot,
 #pragma unroll
                 for (int b = 0; b < PB; ++b) {
                     float tu = 0.f, tv = 0.f;
-                    if (b < nb) {
 #pragma unroll
-                        for (int v = 0; v < NV; ++v) {
-                            int q = lane + 32 * v;
-                            if (q < K2q) {
-                                float t = dot4(w[v], g4[(b0 + b) * K2q + q]);
-                                if (q >= Hq) tv += t; else tu += t;
-                            }
-                        }
+                    for (int v = 0; v < NV; ++v) {
+                        const float t = dot4(w[v], x[b][v]);   // zero beyond the row / the batch
+                        if (lane + 32 * v >= Hq) tv += t; else tu += t;
                     }
                     du[r * PB + b] = tu;
                     dv[r * PB + b] = tv;
@@ -1629,6 +1652,42 @@ __device__ __forceinline__ void theta_elem(const float atol_f, const float rtol_
     }
 }
 
+// PP_STEP for one theta element with the seven stage derivatives produced on the fly by kq(q) (q = physical slot):
+// no k[] array exists, so nothing can be demoted to local memory (a select chain over an array is turned into a
+// dynamically indexed load by the optimiser).  Same operation order as the reference's k.matmul(dt * c).
+template <typename KQ>
+__device__ __forceinline__ float theta_step_val(const float atol_f, const float rtol_f, const PPArgs& a, const float th0, KQ kq,
+                                                double& acc0, double& acc1) {
+    float inc = 0.f, e = 0.f, md = 0.f, kf = 0.f, kl = 0.f;
+#pragma unroll
+    for (int q = 0; q < 7; ++q) {
+        const float t = kq(q);
+        if (q == 0) {
+            inc = t * a.coef_sol[0];
+            e = t * a.coef_err[0];
+            md = t * a.coef_mid[0];
+        } else {
+            inc = fmaf(t, a.coef_sol[q], inc);
+            e = fmaf(t, a.coef_err[q], e);
+            md = fmaf(t, a.coef_mid[q], md);
+        }
+        kf = (q == a.slot_first) ? t : kf;
+        kl = (q == a.slot_last) ? t : kl;
+    }
+    const float th1 = th0 + inc;
+    const float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
+    const float r = e / tol;
+    acc0 += (double)(r * r);
+    if (!isfinite(th1)) acc1 += 1.0;
+    return a.last ? interp_eval(th0, th1, th0 + md, kf, kl, a.dtf, a.xs) : th1;
+}
+template <typename KQ>
+__device__ __forceinline__ void theta_step(const float atol_f, const float rtol_f, const PPArgs& a, size_t idx, KQ kq,
+                                           double& acc0, double& acc1) {
+    const float th0 = a.src ? a.src[idx] : 0.f;
+    a.dst[idx] = theta_step_val(atol_f, rtol_f, a, th0, kq, acc0, acc1);
+}
+
 // which factor slots a mode needs, as k[0..NK): D01 {s0}, D2 {s0, s1}, STEP all seven physical slots, FIXED 0..3
 template <int MODE>
 struct PPSlots {
@@ -1665,33 +1724,61 @@ __device__ __forceinline__ void pp_block(const float atol_f, const float rtol_f,
 #pragma unroll
             for (int b = 0; b < BT; ++b) v[i][b] = vp[uo[i] + b];
         }
-        for (int r = ry; r < R; r += RG) {
-            float k[7];
-            const float* up = U + (size_t)r * QB;
-            if (MODE == PP_STEP) {
-                float u[QB];
+        if constexpr (MODE == PP_STEP) {
+            // two rows per iteration: the per-element chain (7-term combinations, a division, the quartic) is long
+            // and the rows are independent, so interleaving them doubles the instruction-level parallelism
+            for (int r = ry; r < R; r += 2 * RG) {
+                const int r2 = r + RG;
+                const bool two = r2 < R;
+                const float* upA = U + (size_t)r * QB;
+                const float* upB = U + (size_t)(two ? r2 : r) * QB;
+                float uA[QB], uB[QB];
 #pragma unroll
                 for (int i = 0; i < QB / 4; ++i) {
-                    float4 t = reinterpret_cast<const float4*>(up)[i];
-                    u[4 * i] = t.x; u[4 * i + 1] = t.y; u[4 * i + 2] = t.z; u[4 * i + 3] = t.w;
+                    float4 t = reinterpret_cast<const float4*>(upA)[i];
+                    uA[4 * i] = t.x; uA[4 * i + 1] = t.y; uA[4 * i + 2] = t.z; uA[4 * i + 3] = t.w;
+                    t = reinterpret_cast<const float4*>(upB)[i];
+                    uB[4 * i] = t.x; uB[4 * i + 1] = t.y; uB[4 * i + 2] = t.z; uB[4 * i + 3] = t.w;
                 }
+                const size_t iA = gbase + (size_t)r * ld + c0 + cx, iB = gbase + (size_t)(two ? r2 : r) * ld + c0 + cx;
+                const float thA = a.src ? a.src[iA] : 0.f, thB = a.src ? a.src[iB] : 0.f;
+                double b0 = 0, b1 = 0;
+                const float oA = theta_step_val(atol_f, rtol_f, a, thA,
+                                                [&](int q) {
+                                                    float t = 0.f;
 #pragma unroll
-                for (int q = 0; q < 7; ++q) {
-                    float t = 0.f;
+                                                    for (int b = 0; b < BT; ++b) t = fmaf(uA[q * BT + b], v[q < NKA ? q : 0][b], t);
+                                                    return t;
+                                                },
+                                                acc0, acc1);
+                const float oB = theta_step_val(atol_f, rtol_f, a, thB,
+                                                [&](int q) {
+                                                    float t = 0.f;
 #pragma unroll
-                    for (int b = 0; b < BT; ++b) t = fmaf(u[q * BT + b], v[q < NKA ? q : 0][b], t);
-                    k[q] = t;
+                                                    for (int b = 0; b < BT; ++b) t = fmaf(uB[q * BT + b], v[q < NKA ? q : 0][b], t);
+                                                    return t;
+                                                },
+                                                b0, b1);
+                a.dst[iA] = oA;
+                if (two) {
+                    a.dst[iB] = oB;
+                    acc0 += b0;
+                    acc1 += b1;
                 }
-            } else {
+            }
+            continue;
+        }
+        for (int r = ry; r < R; r += RG) {
+            const float* up = U + (size_t)r * QB;
+            float k[7];
 #pragma unroll
-                for (int i = 0; i < 7; ++i) {
-                    float t = 0.f;
-                    if (i < NK) {
+            for (int i = 0; i < 7; ++i) {
+                float t = 0.f;
+                if (i < NK) {
 #pragma unroll
-                        for (int b = 0; b < BT; ++b) t = fmaf(up[uo[i < NKA ? i : 0] + b], v[i < NKA ? i : 0][b], t);
-                    }
-                    k[i] = t;
+                    for (int b = 0; b < BT; ++b) t = fmaf(up[uo[i < NKA ? i : 0] + b], v[i < NKA ? i : 0][b], t);
                 }
+                k[i] = t;
             }
             theta_elem<MODE>(atol_f, rtol_f, a, gbase + (size_t)r * ld + c0 + cx, k, acc0, acc1);
         }
@@ -1736,10 +1823,14 @@ __device__ __noinline__ PPSums ppass(const ResParams& __restrict__ p, int g_lo, 
     }
     // m
     for (int j = threadIdx.x; j < n_loc; j += THREADS) {
-        float k[7];
+        if constexpr (MODE == PP_STEP) {
+            theta_step(atol_f, rtol_f, a, off.m + g_lo + j, [&](int q) { return s.FM()[j * 8 + q]; }, acc0, acc1);
+        } else {
+            float k[7];
 #pragma unroll
-        for (int i = 0; i < 7; ++i) k[i] = (i < NK) ? s.FM()[j * 8 + pp_slot<MODE>(a, i)] : 0.f;
-        theta_elem<MODE>(atol_f, rtol_f, a, off.m + g_lo + j, k, acc0, acc1);
+            for (int i = 0; i < 7; ++i) k[i] = (i < NK) ? s.FM()[j * 8 + pp_slot<MODE>(a, i)] : 0.f;
+            theta_elem<MODE>(atol_f, rtol_f, a, off.m + g_lo + j, k, acc0, acc1);
+        }
     }
     auto ident = [](int c) { return c; };
     // Wp, Ws : rows h (factors FG), this CTA's gene columns (factors FL / FS)
@@ -1753,6 +1844,16 @@ __device__ __noinline__ PPSums ppass(const ResParams& __restrict__ p, int g_lo, 
         for (int h = threadIdx.x; h < 2 * H; h += THREADS) {
             const bool prod = h >= H;
             const float* up = s.FG() + (size_t)(prod ? Hp + h - H : h) * QB;
+            if constexpr (MODE == PP_STEP) {
+                theta_step(atol_f, rtol_f, a, (prod ? off.bp + (h - H) : off.bs + h),
+                           [&](int q) {
+                               float t = 0.f;
+                               for (int b = 0; b < BT; ++b) t += up[q * BT + b];
+                               return t;
+                           },
+                           acc0, acc1);
+                continue;
+            }
             float k[7];
 #pragma unroll
             for (int i = 0; i < 7; ++i) {

@@ -135,8 +135,9 @@ def _new_status():
         st = tls.free_status.pop()
     else:
         st = torch.empty(ctypes.sizeof(_lib.PhxStatus) // 4, dtype=torch.int32).pin_memory()
-    st.zero_()
-    st[0] = _lib.ST_RUNNING
+    # reset through ctypes (no torch dispatch on the per-sample path)
+    ctypes.memset(st.data_ptr(), 0, ctypes.sizeof(_lib.PhxStatus))
+    _lib.PhxStatus.from_address(st.data_ptr()).code = _lib.ST_RUNNING
     return st
 
 

@@ -42,16 +42,15 @@ def _normalise(func, y0, t, rtol, atol, method, options):
         raise TypeError('`{}` must be a floating point Tensor but is a {}'.format('t', t.type()))
     if t.requires_grad:
         raise NotImplementedError("gradients with respect to t are not computed on the B200 path")
-    if t.device != y0.device:
-        # same coercion as misc.py:236-239, minus the copy: the times are consumed on the host
-        pass
+    # the times are consumed on the host (float32 values are promoted exactly, like solvers.py:26); plain Python from
+    # here on: this runs once per sample of every training step
     t_is_f32 = t.dtype != torch.float64
-    tl = t.detach().to('cpu', torch.float64)
+    tl = t.tolist()
     reversed_time = False
-    if len(tl) > 1 and bool((tl[1:] < tl[:-1]).all()):
-        tl = -tl
+    if len(tl) > 1 and all(b < a for a, b in zip(tl, tl[1:])):
+        tl = [-x for x in tl]
         reversed_time = True
-    assert bool((tl[1:] > tl[:-1]).all()), '{} must be strictly increasing or decreasing'.format('t')
+    assert all(b > a for a, b in zip(tl, tl[1:])), '{} must be strictly increasing or decreasing'.format('t')
     if torch.is_tensor(rtol):
         assert not rtol.requires_grad, "rtol cannot require gradient"
         rtol = float(rtol)
@@ -63,7 +62,7 @@ def _normalise(func, y0, t, rtol, atol, method, options):
                         "no generic / CPU fallback".format(type(func).__name__))
     if y0.dtype != torch.float32:
         raise TypeError("the B200 path keeps the state in float32 like the reference (got {})".format(y0.dtype))
-    return tl.tolist(), t_is_f32, reversed_time, float(rtol), float(atol), method, max_num_steps
+    return tl, t_is_f32, reversed_time, float(rtol), float(atol), method, max_num_steps
 
 
 def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
@@ -122,9 +121,14 @@ def odeint_adjoint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None,
         adjoint_method = method
     if adjoint_options is None:
         adjoint_options = {k: v for k, v in options.items() if k != "norm"} if options is not None else {}
+    same = (adjoint_rtol is rtol and adjoint_atol is atol and adjoint_method is method and not adjoint_options
+            and not options)
     tl, t_is_f32, rev, rtol, atol, method, max_steps = _normalise(func, y0, t, rtol, atol, method, options)
-    _, _, _, a_rtol, a_atol, a_method, a_max = _normalise(func, y0, t, adjoint_rtol, adjoint_atol, adjoint_method,
-                                                          adjoint_options)
+    if same:
+        a_rtol, a_atol, a_method, a_max = rtol, atol, method, max_steps
+    else:
+        _, _, _, a_rtol, a_atol, a_method, a_max = _normalise(func, y0, t, adjoint_rtol, adjoint_atol, adjoint_method,
+                                                              adjoint_options)
     if rev:
         raise NotImplementedError("odeint_adjoint with decreasing t is not part of the PHOENIX path")
     params = engine.net_params(func)

@@ -106,3 +106,36 @@ def test_shard_range_is_a_partition():
             assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
             sizes = [hi - lo for lo, hi in spans]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_resident_plan_places_the_weight_slices():
+    """phx_plan_describe (host only): where the two weight slices of a CTA live for the BASELINE shapes."""
+    import ctypes
+    from phoenix_b200 import _lib
+    lib = _lib.load()
+
+    def plan(G, H, B, adjoint):
+        out = (ctypes.c_int32 * 8)()
+        rc = lib.phx_plan_describe(148, G, H, B, adjoint, out)
+        return rc, dict(zip(("ctas", "gpc", "nv", "w1", "wa", "ring_rows", "ring_stages", "smem"), list(out)))
+
+    for adjoint in (0, 1):
+        # SIM350 / SIM690 / yeast: both slices resident in shared memory, no ring
+        for G, H in ((350, 40), (690, 40), (3551, 120)):
+            rc, p = plan(G, H, 1, adjoint)
+            assert rc == 0 and (p["w1"], p["wa"], p["ring_stages"]) == (1, 1, 0), (G, H, p)
+        # breast 11165 x 200: W1 in shared memory, WA parked in tensor memory (wa == 2), nothing streams
+        rc, p = plan(11165, 200, 1, adjoint)
+        assert rc == 0 and (p["w1"], p["wa"], p["ring_stages"]) == (1, 2, 0), p
+        assert p["ctas"] == 147 and p["gpc"] == 76 and p["nv"] == 4
+        assert p["smem"] <= 227 * 1024
+        # 20000 x 200: 9 rows per warp exceed the 8-row tensor-memory share -> both slices stream through the ring
+        rc, p = plan(20000, 200, 1, adjoint)
+        assert rc == 0 and (p["w1"], p["wa"]) == (0, 0) and p["ring_stages"] >= 1, p
+    # more rows than the resident kernels take, or too many neurons: refused (the engine then streams)
+    assert plan(350, 40, 9, 0)[0] != 0
+    assert plan(350, 40, 5, 1)[0] != 0
+    assert plan(350, 300, 1, 0)[0] != 0
+    # tiny problems use few CTAs (cheap exchanges): at least 16 genes per CTA
+    rc, p = plan(37, 5, 1, 0)
+    assert rc == 0 and p["ctas"] == 3 and p["gpc"] == 16
