@@ -82,11 +82,24 @@ int phx_plan_describe(int num_sms, int G, int H, int B, int adjoint, int32_t out
 int phx_ctx_set_profile(phx_ctx* ctx, void* slots);
 int phx_profile_slots(void);
 
+/* ---- precision of the batched contractions ------------------------------------------------------------------ */
+/* Calls with B >= phx_tc_min_rows() rows (the 10 000-row prior batch train_insilico.py:134,209; the batched sweeps)
+ * are dense contractions and run on the tcgen05 tensor cores.  PHX_PREC_3XTF32 (default) keeps fp32 parity with the
+ * reference's ATen fp32 matmuls by splitting every operand into two TF32 terms (three MMAs per product);
+ * PHX_PREC_TF32 is the single-pass TF32 mode (relative error ~1e-3, reported separately); PHX_PREC_FP32 forces the
+ * fp32 CUDA-core contractions.  Calls with fewer rows are GEMV-bound and never use the tensor cores. */
+enum { PHX_PREC_FP32 = 0, PHX_PREC_TF32 = 1, PHX_PREC_3XTF32 = 3 };
+int phx_ctx_set_precision(phx_ctx* ctx, int precision);
+int phx_ctx_get_precision(const phx_ctx* ctx);
+int phx_tc_min_rows(void);
+
 /* ---- weights --------------------------------------------------------------------------------------------- */
 /* Bytes of the packed (kernel-layout) copy of the six parameters for an ODENet(ndim=G, neurons=H). */
 size_t phx_packed_bytes(int G, int H);
 /* Re-lay the six reference parameter tensors (odenet.py:49-61) into the kernel layout:
- * W1[G][K2] = [Ws^T | Wp^T], WA[G][K2] = Wa (halves padded to a multiple of 4), bias[K2], relu(m)[G], (m>0)[G]. */
+ * W1[G][K2] = [Ws^T | Wp^T], WA[G][K2] = Wa (halves padded to a multiple of 4), bias[K2], relu(m)[G], (m>0)[G].
+ * The tail of the buffer holds the tensor-core operand images; they are rebuilt on `stream` by the first large-B call
+ * that follows a phx_pack_weights of the same buffer, so all calls sharing a packed buffer must share a stream. */
 int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* gene_multipliers, const float* Wp, const float* bp,
                      const float* Ws, const float* bs, const float* Wa, float* packed, void* stream);
 

@@ -5,9 +5,9 @@
 hand-written CUDA kernels behind the C ABI of ``include/phoenix_b200.h`` (libphoenix_b200.so).  No CPU fallback.
 """
 from . import engine
-from .engine import check_errors, last_status, last_step_log, set_step_logging, set_sync_errors
+from .engine import check_errors, last_status, last_step_log, set_precision, set_step_logging, set_sync_errors
 from .odenet import ODENet, LogShiftedSoftSignMod, SoftsignMod
 from .torchdiffeq import odeint, odeint_adjoint
 
 __all__ = ["ODENet", "SoftsignMod", "LogShiftedSoftSignMod", "odeint", "odeint_adjoint", "engine", "check_errors",
-           "last_status", "last_step_log", "set_step_logging", "set_sync_errors"]
+           "last_status", "last_step_log", "set_precision", "set_step_logging", "set_sync_errors"]

@@ -12,11 +12,13 @@ LIB_PATH = os.path.join(_HERE, "libphoenix_b200.so")
 
 PHX_OK = 0
 METHOD_IDS = {"euler": 0, "midpoint": 1, "rk4": 2, "dopri5": 3}
+PREC_FP32, PREC_TF32, PREC_3XTF32 = 0, 1, 3
 ST_OK, ST_DT_UNDERFLOW, ST_NONFINITE, ST_MAX_STEPS, ST_RUNNING = 0, 1, 2, 3, 99
 
 EXPORTS = [
     "phx_ctx_create", "phx_ctx_destroy", "phx_last_error", "phx_ctx_num_sms", "phx_resident_max_rows",
     "phx_ctx_set_profile", "phx_profile_slots", "phx_plan_describe",
+    "phx_ctx_set_precision", "phx_ctx_get_precision", "phx_tc_min_rows",
     "phx_packed_bytes", "phx_pack_weights", "phx_rhs_forward", "phx_rhs_vjp", "phx_rhs_workspace_bytes",
     "phx_solve_workspace_bytes", "phx_solve_workspace_init_bytes", "phx_solve_workspace_init", "phx_solve_forward",
     "phx_solve_adjoint",
@@ -58,6 +60,12 @@ def _declare(lib):
     lib.phx_plan_describe.restype = c_int
     lib.phx_profile_slots.argtypes = []
     lib.phx_profile_slots.restype = c_int
+    lib.phx_ctx_set_precision.argtypes = [c_void_p, c_int]
+    lib.phx_ctx_set_precision.restype = c_int
+    lib.phx_ctx_get_precision.argtypes = [c_void_p]
+    lib.phx_ctx_get_precision.restype = c_int
+    lib.phx_tc_min_rows.argtypes = []
+    lib.phx_tc_min_rows.restype = c_int
     lib.phx_packed_bytes.argtypes = [c_int, c_int]
     lib.phx_packed_bytes.restype = c_size_t
     lib.phx_pack_weights.argtypes = [c_void_p, c_int, c_int] + [c_void_p] * 7 + [c_void_p]

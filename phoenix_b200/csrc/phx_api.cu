@@ -2,7 +2,10 @@
 #include <stdarg.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <mutex>
+#include <unordered_map>
 #include <vector>
 #include "phx_common.cuh"
 
@@ -20,6 +23,9 @@ struct phx_ctx {
     int num_sms;
     int coop;
     long long* prof;
+    int precision;                                   // PHX_PREC_*
+    std::mutex mu;
+    std::unordered_map<const float*, int> tc_valid;  // packed buffer -> its tensor-core images are current
 };
 
 namespace {
@@ -62,6 +68,28 @@ bool check_dims(int G, int H, int B) {
 
 }  // namespace
 
+int phx_tc_prepare(phx_ctx* ctx, int G, int H, int B, const float* packed, PhxPacked* view, cudaStream_t stream) {
+    *view = phx_packed_view(packed, G, H);
+    if (!ctx || ctx->precision == PHX_PREC_FP32 || !phx_tc_shape_ok(H, B)) return PHX_OK;
+    if ((uintptr_t)packed & 127) {
+        phx_set_error("packed weights must be 128-byte aligned for the tensor-core path");
+        return PHX_ERR_INVALID;
+    }
+    bool stale;
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        auto it = ctx->tc_valid.find(packed);
+        stale = (it == ctx->tc_valid.end()) || it->second == 0;
+        ctx->tc_valid[packed] = 1;
+    }
+    if (stale) {
+        int rc = phx_tc_pack_launch(G, H, *view, stream);
+        if (rc != PHX_OK) return rc;
+    }
+    view->tc = ctx->precision == PHX_PREC_TF32 ? 1 : 3;
+    return PHX_OK;
+}
+
 extern "C" {
 
 const char* phx_last_error(void) { return g_err; }
@@ -84,6 +112,8 @@ int phx_ctx_create(int device, phx_ctx** out) {
     c->num_sms = prop.multiProcessorCount;
     c->coop = prop.cooperativeLaunch;
     c->prof = nullptr;
+    c->precision = PHX_PREC_3XTF32;
+    if (const char* e = getenv("PHX_PRECISION")) c->precision = atoi(e);
     if (!c->coop) {
         delete c;
         phx_set_error("device %d does not support cooperative launch", device);
@@ -116,6 +146,17 @@ int phx_plan_describe(int num_sms, int G, int H, int B, int adjoint, int32_t out
     return PHX_OK;
 }
 
+int phx_ctx_set_precision(phx_ctx* ctx, int precision) {
+    if (!ctx || (precision != PHX_PREC_FP32 && precision != PHX_PREC_3XTF32 && precision != PHX_PREC_TF32)) {
+        phx_set_error("set_precision: unknown mode %d", precision);
+        return PHX_ERR_INVALID;
+    }
+    ctx->precision = precision;
+    return PHX_OK;
+}
+int phx_ctx_get_precision(const phx_ctx* ctx) { return ctx ? ctx->precision : PHX_ERR_INVALID; }
+int phx_tc_min_rows(void) { return PHX_TC_MIN_ROWS; }
+
 size_t phx_packed_bytes(int G, int H) { return phx_packed_floats(G, H) * sizeof(float); }
 
 int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* m, const float* Wp, const float* bp, const float* Ws,
@@ -126,6 +167,10 @@ int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* m, const float* Wp
     pack_kernel<<<ctx->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(
         G, H, Hp, K2, m, Wp, bp, Ws, bs, Wa, (float*)v.W1, (float*)v.WA, (float*)v.bias, (float*)v.relum,
         (float*)v.maskm);
+    {
+        std::lock_guard<std::mutex> lk(ctx->mu);
+        ctx->tc_valid[packed] = 0;   // the tensor-core operand images are rebuilt lazily by the first large-B call
+    }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         phx_set_error("pack_weights launch: %s", cudaGetErrorString(e));
@@ -143,8 +188,10 @@ int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, cons
         phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
         return PHX_ERR_WORKSPACE;
     }
-    return phx_rhs_forward_launch(G, H, B, phx_packed_view(packed, G, H), y, f, decay, 1.f, (float*)workspace,
-                                  (cudaStream_t)stream);
+    PhxPacked w;
+    int rc = phx_tc_prepare(ctx, G, H, B, packed, &w, (cudaStream_t)stream);
+    if (rc != PHX_OK) return rc;
+    return phx_rhs_forward_launch(G, H, B, w, y, f, decay, 1.f, (float*)workspace, (cudaStream_t)stream);
 }
 
 int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, const float* g, int decay,
@@ -155,8 +202,11 @@ int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const fl
         phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
         return PHX_ERR_WORKSPACE;
     }
-    return phx_rhs_vjp_launch(G, H, B, phx_packed_view(packed, G, H), y, g, decay, ybar, grads_flat, accumulate,
-                              nullptr, 1.f, (float*)workspace, (cudaStream_t)stream);
+    PhxPacked w;
+    int rc = phx_tc_prepare(ctx, G, H, B, packed, &w, (cudaStream_t)stream);
+    if (rc != PHX_OK) return rc;
+    return phx_rhs_vjp_launch(G, H, B, w, y, g, decay, ybar, grads_flat, accumulate, nullptr, 1.f, (float*)workspace,
+                              (cudaStream_t)stream);
 }
 
 size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint) {

@@ -24,6 +24,7 @@
 static inline __host__ __device__ int phx_round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline __host__ __device__ int phx_Hp(int H) { return phx_round_up(H, 4); }
 static inline __host__ __device__ int phx_K2(int H) { return 2 * phx_Hp(H); }
+#include "phx_tc.cuh"
 
 struct PhxPacked {
     const float4* W1;
@@ -31,11 +32,20 @@ struct PhxPacked {
     const float* bias;
     const float* relum;
     const float* maskm;
+    // tensor-core operand images (phx_tc.cuh), the tail of the packed buffer; valid only once tc_pack has run on it
+    const float* w1img;
+    const float* waimg;
+    int tc;   // 0: fp32 CUDA-core contractions; 3: 3xTF32 tcgen05; 1: single-pass TF32 tcgen05 (set by the entry points)
 };
 
-static inline __host__ __device__ size_t phx_packed_floats(int G, int H) {
+// base part (W1, WA, bias, relum, maskm) rounded up to 128 bytes so that the tensor-core images that follow are aligned
+static inline __host__ __device__ size_t phx_packed_base_floats(int G, int H) {
     size_t K2 = (size_t)phx_K2(H);
-    return 2 * (size_t)G * K2 + K2 + 2 * (size_t)phx_round_up(G, 4);
+    size_t n = 2 * (size_t)G * K2 + K2 + 2 * (size_t)phx_round_up(G, 4);
+    return (n + 31) & ~(size_t)31;
+}
+static inline __host__ __device__ size_t phx_packed_floats(int G, int H) {
+    return phx_packed_base_floats(G, H) + phx_tc_w1img_floats(G, H) + phx_tc_waimg_floats(G, H);
 }
 
 static inline __host__ __device__ PhxPacked phx_packed_view(const float* base, int G, int H) {
@@ -46,6 +56,9 @@ static inline __host__ __device__ PhxPacked phx_packed_view(const float* base, i
     v.bias = base + 2 * (size_t)G * K2;
     v.relum = v.bias + K2;
     v.maskm = v.relum + phx_round_up(G, 4);
+    v.w1img = base + phx_packed_base_floats(G, H);
+    v.waimg = v.w1img + phx_tc_w1img_floats(G, H);
+    v.tc = 0;
     return v;
 }
 
@@ -221,5 +234,14 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
                        float* ybar, float* grads_flat, int accumulate, float* f_out, float fscale, float* ws,
                        cudaStream_t stream);
 size_t phx_rhs_workspace_floats(int G, int H, int B);
+
+// tensor-core path (phx_tc.cu).  phx_tc_prepare (phx_api.cu) decides per call whether the contractions of a B-row call
+// run on tcgen05 (ctx precision, shape), (re)builds the operand images in the tail of `packed` if phx_pack_weights has
+// run since they were last built, and returns the view with .tc set.
+struct phx_ctx;
+int phx_tc_prepare(phx_ctx* ctx, int G, int H, int B, const float* packed, PhxPacked* view, cudaStream_t stream);
+int phx_tc_pack_launch(int G, int H, const PhxPacked& w, cudaStream_t stream);
+int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay,
+                              float fscale, float* SP, float* tcws, cudaStream_t stream);
 
 void phx_set_error(const char* fmt, ...);

@@ -235,10 +235,14 @@ __global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const
 
 }  // namespace
 
+static size_t rhs_base_floats(int G, int H, int B) {
+    size_t K2 = (size_t)phx_K2(H);
+    return 2 * (size_t)B * K2 + (size_t)B * G + 16;
+}
 size_t phx_rhs_workspace_floats(int G, int H, int B) {
     size_t K2 = (size_t)phx_K2(H);
-    // SP, GS : [B][K2] each ; J : [B][G]
-    return 2 * (size_t)B * K2 + (size_t)B * G + 16;
+    // SP, GS : [B][K2] each ; J : [B][G] ; scratch of the tensor-core path (K-split partials, [S|P] operand image)
+    return rhs_base_floats(G, H, B) + (phx_tc_shape_ok(H, B) ? phx_tc_scratch_floats(G, H, B) : 0);
 }
 
 static void rhs_sp(int G, int H, int B, const PhxPacked& w, const float* y, float* SP, cudaStream_t st) {
@@ -256,6 +260,8 @@ int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float*
                            float* ws, cudaStream_t st) {
     const int K2 = phx_K2(H);
     float* SP = ws;
+    if (w.tc && phx_tc_shape_ok(H, B))   // tcgen05 path: both contractions on the tensor cores
+        return phx_tc_rhs_forward_launch(G, H, B, w, y, f, decay, fscale, SP, ws + rhs_base_floats(G, H, B), st);
     rhs_sp(G, H, B, w, y, SP, st);
     LoadRowMajorA la{SP, K2, 0};
     LoadWcol lb{reinterpret_cast<const float*>(w.WA), K2, 0};
@@ -278,7 +284,12 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
     float* J = GS + (size_t)B * K2;
     const float* W1 = reinterpret_cast<const float*>(w.W1);
     const float* WA = reinterpret_cast<const float*>(w.WA);
-    rhs_sp(G, H, B, w, y, SP, st);
+    if (w.tc && phx_tc_shape_ok(H, B)) {   // branch contraction on the tensor cores; cotangent GEMMs below stay fp32
+        int rc = phx_tc_rhs_forward_launch(G, H, B, w, y, nullptr, 0, 1.f, SP, ws + rhs_base_floats(G, H, B), st);
+        if (rc != PHX_OK) return rc;
+    } else {
+        rhs_sp(G, H, B, w, y, SP, st);
+    }
     // GS = gJ WA, prods half scaled by Pr
     {
         LoadGJ la{g, w.relum, G, decay};

@@ -469,7 +469,8 @@ int setup(Stream& S, phx_ctx* ctx, int G, int H, int B, const float* packed, con
     float* ws = (float*)workspace;
     S.ctx = ctx; S.G = G; S.H = H; S.B = B; S.T = T; S.method = method; S.t_is_f32 = t_is_f32; S.adjoint = adjoint;
     S.rtol_f = (float)rtol; S.atol_f = (float)atol; S.fsign = 1.f; S.max_steps = (long long)max_steps;
-    S.w = phx_packed_view(packed, G, H);
+    int rc_tc = phx_tc_prepare(ctx, G, H, B, packed, &S.w, st);
+    if (rc_tc != PHX_OK) return rc_tc;
     S.st = st;
     S.rhs_ws = ws + o_rhs;
     S.partial = (double*)(ws + o_partial);

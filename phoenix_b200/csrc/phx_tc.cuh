@@ -1,0 +1,68 @@
+// Tensor-core (tcgen05 / TMEM) path of the batched RHS: shared layout definitions.
+//
+// When the trajectory batch makes the branch contractions real dense GEMMs (B >= PHX_TC_MIN_ROWS rows: the 10 000-row
+// prior batch of train_insilico.py:134, the 4 096-row synthetic sweep), they run on the 5th-generation tensor cores as
+// TF32 MMAs with fp32 accumulators in tensor memory.  fp32 parity with the reference (odenet.py:85-91 evaluated by ATen
+// in fp32) is kept by the 3xTF32 split: every operand x is stored as hi = rna_tf32(x), lo = rna_tf32(x - hi) and a
+// product is accumulated as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (PHX_PREC_3XTF32).  PHX_PREC_TF32 issues only hi*hi and is
+// reported separately with its own tolerance.
+//
+// Operand images.  tcgen05.mma reads its operands from shared memory through matrix descriptors; we use the K-major
+// NO-SWIZZLE canonical layout, whose unit is the 8-row x 16-byte "core matrix" stored as 128 contiguous bytes:
+//     tile of R rows x 16 floats (one k-block):  float offset(r, k) = (((k/4) * (R/8) + r/8) * 8 + r%8) * 4 + k%4
+//     descriptor: leading byte offset (K-adjacent core matrices) = (R/8)*128, stride byte offset (row groups) = 128.
+// The constant operands (weights) are re-laid into exactly this image once per weight update (tc_pack_kernel), k-block
+// by k-block and hi|lo side by side, so one k-block of an operand is ONE contiguous chunk of global memory and is
+// fetched with a single 1-D TMA bulk copy (cp.async.bulk + mbarrier complete_tx) -- no tensor maps, no swizzle.
+//     w1img [KB1][branch 2][hi|lo][Hn x 16]   branch contraction S|P = act(y) W1      (N = Hn hidden units, K = genes)
+//     waimg [GT][KB2][hi|lo][128 x 16]        joint contraction J = [S|P] WA^T         (M = genes, K = 2*Hn)
+//     spimg [BT][KB2][hi|lo][256 x 16]        [S|P] rows, written by the K-split reduction kernel (N = batch rows)
+// Hn = round_up(H, 16) (UMMA N granularity at M = 128); pads are zero in every image.
+#pragma once
+// (included from phx_common.cuh after phx_round_up)
+
+#define PHX_TC_BK 16
+#define PHX_TC_MIN_ROWS 128
+#define PHX_TC_MAX_HN 256
+#define PHX_TC_SMS 148
+#define PHX_TC_MAX_KSPLIT 64
+
+static inline __host__ __device__ int phx_tc_Hn(int H) { return phx_round_up(H, 16); }
+static inline __host__ __device__ int phx_tc_KB1(int G) { return (G + PHX_TC_BK - 1) / PHX_TC_BK; }
+static inline __host__ __device__ int phx_tc_KB2(int H) { return 2 * phx_tc_Hn(H) / PHX_TC_BK; }
+static inline __host__ __device__ int phx_tc_GT(int G) { return (G + 127) / 128; }
+static inline __host__ __device__ int phx_tc_BT(int B) { return (B + 255) / 256; }
+static inline bool phx_tc_shape_ok(int H, int B) { return B >= PHX_TC_MIN_ROWS && phx_tc_Hn(H) <= PHX_TC_MAX_HN; }
+
+static inline __host__ __device__ size_t phx_tc_w1img_floats(int G, int H) {
+    return (size_t)phx_tc_KB1(G) * 4 * phx_tc_Hn(H) * PHX_TC_BK;
+}
+static inline __host__ __device__ size_t phx_tc_waimg_floats(int G, int H) {
+    return (size_t)phx_tc_GT(G) * phx_tc_KB2(H) * 2 * 128 * PHX_TC_BK;
+}
+static inline __host__ __device__ size_t phx_tc_spimg_floats(int H, int B) {
+    return (size_t)phx_tc_BT(B) * phx_tc_KB2(H) * 2 * 256 * PHX_TC_BK;
+}
+// float offset of element (r, k) inside an R-row x 16-float tile image
+static inline __host__ __device__ int phx_tc_tile_off(int R, int r, int k) {
+    return ((((k >> 2) * (R >> 3) + (r >> 3)) * 8 + (r & 7)) << 2) + (k & 3);
+}
+
+// K-split of the branch contraction: how many CTAs share one 128-row tile, and k-blocks per split
+static inline void phx_tc_ksplit(int G, int B, int* ks, int* kb_per_split) {
+    const int mtiles = (B + 127) / 128, KB1 = phx_tc_KB1(G);
+    int want = PHX_TC_SMS / mtiles;
+    if (want < 1) want = 1;
+    if (want > PHX_TC_MAX_KSPLIT) want = PHX_TC_MAX_KSPLIT;
+    int per = (KB1 + want - 1) / want;
+    if (per < 4) per = KB1 < 4 ? KB1 : 4;
+    *kb_per_split = per;
+    *ks = (KB1 + per - 1) / per;
+}
+// scratch of the tensor-core RHS in floats (K-split partial sums + [S|P] operand image), 128-byte aligned inside
+static inline size_t phx_tc_scratch_floats(int G, int H, int B) {
+    int ks, per;
+    phx_tc_ksplit(G, B, &ks, &per);
+    const size_t Bpad = (size_t)phx_round_up(B, 128);
+    return (size_t)ks * Bpad * 2 * phx_tc_Hn(H) + phx_tc_spimg_floats(H, B) + 64;
+}

@@ -45,6 +45,19 @@ def set_step_logging(flag):
     STEP_LOGGING = bool(flag)
 
 
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "3xtf32": _lib.PREC_3XTF32}
+
+
+def set_precision(mode, device=None):
+    """Arithmetic of the dense (B >= 128 rows) contractions: '3xtf32' (default; tcgen05 tensor cores with the
+    three-term TF32 split, fp32 parity), 'tf32' (single-pass TF32, ~1e-3 relative error) or 'fp32' (CUDA cores).
+    Smaller batches are GEMV-bound and always run in fp32 on the CUDA cores."""
+    if mode not in _PRECISIONS:
+        raise ValueError("precision must be one of %s" % sorted(_PRECISIONS))
+    dev = torch.cuda.current_device() if device is None else torch.device(device).index
+    _lib.check(_lib.load().phx_ctx_set_precision(_lib.ctx(dev), _PRECISIONS[mode]), "set_precision")
+
+
 def _tls():
     return _state
 
