@@ -17,6 +17,7 @@
 //
 // Every accumulation order is fixed (MMA issue order, K-split reduction order) => results are run-to-run identical.
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include "phx_common.cuh"
 
@@ -106,6 +107,17 @@ __device__ __forceinline__ void tmem_ld16(unsigned taddr, float (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(u[i]);
 }
 
+__device__ __forceinline__ void tmem_ld8(unsigned taddr, float (&v)[8]) {
+    unsigned u[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(u[i]);
+}
+
 __device__ __forceinline__ float tf32_rna(float x) {
     unsigned u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
@@ -155,173 +167,313 @@ __global__ void tc_pack_kernel(int G, int H, int Hp, int K2, int Hn, const float
     }
 }
 
-__device__ __forceinline__ void hill(float y, float& s, float& l) {
+__device__ __forceinline__ void hill(float y, float& s, float& l, int want_l) {
     float z = y - 0.5f;
     float den = 1.0f + fabsf(z);
-    s = z / den;
-    l = log1pf(s);
+    s = __fdividef(z, den);   // den in [1, inf): no range issue; <= 2 ulp, far inside the 3xTF32 error budget
+    l = want_l ? log1pf(s) : 0.f;
 }
 
 // ---- kernel 1: branch contraction ----------------------------------------------------------------------------------------
+// Accumulation chains.  The tensor core adds each MMA result into the fp32 accumulator with truncation, so the error of
+// a long chain grows linearly with its length (measured: ~6e-8 per accumulating MMA, 1.5e-4 at 1 900 MMAs, against 1e-5
+// for a plain fp32 FMA loop).  To keep fp32 parity a CTA accumulates at most `chunk` k-blocks (6 MMAs each) in one
+// tensor-memory accumulator, then its warps add that chunk sum into a RUNNING SUM with round-to-nearest fp32 adds.  The
+// running sum lives in tensor memory too (tcgen05.ld / add / tcgen05.st), which is why a CTA owns ONE branch: chunk
+// accumulator (Hn columns) + running sum (Hn columns) fit the 512 columns for every Hn <= 256.  The soft-sign CTAs
+// need ~1/2 the ALU work per k-block of the log1p CTAs, so they get K ranges twice as long (phx_tc_branch_plan).
 struct BranchParams {
-    int G, B, Bpad, Hn, KB1, kb_per_split, stages, nterms;
-    unsigned a_lbo, a_sbo, b_lbo, b_sbo;   // descriptor fields
-    unsigned a_kadv, b_kadv;               // byte advance of the start address per K = 8 MMA (two core matrices)
+    int G, B, Bpad, Hn, KB1, chunk, stages, nterms, dbg;
+    int mtiles, ks_p, per_p, ks_s, per_s;   // work split: blocks [0, mtiles*ks_p) are prods-branch CTAs, the rest sums
+    unsigned a_lbo, a_sbo, b_lbo, b_sbo;    // descriptor fields
+    unsigned a_kadv, b_kadv;                // byte advance of the start address per K = 8 MMA (two core matrices)
     const float* y;       // [B][G]
     const float* w1img;
-    float* spart;         // [ks][Bpad][2*Hn]
+    float* spart;         // [slot][Bpad][2*Hn]; sums branch uses slots < ks_s, prods branch slots < ks_p
+    unsigned long long* prof;   // optional cycle counters (PHX_TC_PROF): see tools/tc_check.py
 };
-constexpr int K1_THREADS = 320;
-constexpr unsigned K1_A_TILE = 128 * BK * 4;   // bytes of one 128 x 16 tile
-constexpr unsigned K1_A_BYTES = 4 * K1_A_TILE; // s_hi, s_lo, l_hi, l_lo
+constexpr int K1_PWARPS = 16;                      // producer warps
+constexpr int K1_DWARPS = 4;                       // drain warps (one per TMEM lane quarter)
+constexpr int K1_W_BULK = K1_PWARPS;               // warp roles
+constexpr int K1_W_MMA = K1_PWARPS + 1;
+constexpr int K1_W_DRAIN = K1_PWARPS + 2;          // 18..21: (warp & 3) covers the four lane quarters
+constexpr int K1_THREADS = (K1_PWARPS + 2 + K1_DWARPS) * 32;
+constexpr int K1_PF = 4;                           // k-blocks of y in flight per thread (HBM latency)
+constexpr unsigned K1_A_TILE = 128 * BK * 4;       // bytes of one 128 x 16 tile
+constexpr unsigned K1_A_BYTES = 2 * K1_A_TILE;     // hi, lo
+
+__device__ __forceinline__ void tmem_ld16_nowait(unsigned taddr, unsigned (&u)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(u[0]), "=r"(u[1]), "=r"(u[2]), "=r"(u[3]), "=r"(u[4]), "=r"(u[5]), "=r"(u[6]), "=r"(u[7]), "=r"(u[8]),
+          "=r"(u[9]), "=r"(u[10]), "=r"(u[11]), "=r"(u[12]), "=r"(u[13]), "=r"(u[14]), "=r"(u[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st16(unsigned taddr, const unsigned (&u)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(
+            taddr),
+        "r"(u[0]), "r"(u[1]), "r"(u[2]), "r"(u[3]), "r"(u[4]), "r"(u[5]), "r"(u[6]), "r"(u[7]), "r"(u[8]), "r"(u[9]),
+        "r"(u[10]), "r"(u[11]), "r"(u[12]), "r"(u[13]), "r"(u[14]), "r"(u[15])
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+    unsigned pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "elect.sync _|p, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+// descriptor of the tile at shared address `saddr` given the constant high part (offsets, version)
+__device__ __forceinline__ uint64_t desc_at(uint64_t hi_part, unsigned saddr) {
+    return hi_part | (uint64_t)((saddr >> 4) & 0x3fffu);
+}
 
 __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int m0 = blockIdx.x * 128, ks = blockIdx.y;
-    const int kb0 = ks * p.kb_per_split;
-    const int nkb = min(p.KB1, kb0 + p.kb_per_split) - kb0;   // >= 1 by construction (phx_tc_ksplit)
+    // work item: branch, 128-row tile, K range (a whole number of chunks)
+    int blk = blockIdx.x;
+    const int np = p.mtiles * p.ks_p;
+    const int br = blk < np ? 1 : 0;
+    if (!br) blk -= np;
+    const int ks = blk / p.mtiles, per = br ? p.per_p : p.per_s;
+    const int m0 = (blk % p.mtiles) * 128;
+    const int kb0 = ks * per;
+    const int nkb = min(p.KB1, kb0 + per) - kb0;   // >= 1 by construction (phx_tc_branch_plan)
+    const int nchunks = (nkb + p.chunk - 1) / p.chunk;
     const int S = p.stages, Hn = p.Hn;
     const unsigned b_tile = (unsigned)Hn * BK * 4;
-    const unsigned b_bytes = 4 * b_tile;
+    const unsigned b_bytes = 2 * b_tile;
     const unsigned stage_bytes = K1_A_BYTES + b_bytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)S * stage_bytes);
-    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + S), done = smem_u32(bars + 2 * S);
-    unsigned* slot = reinterpret_cast<unsigned*>(bars + 2 * S + 1);
+    const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + S), done = smem_u32(bars + 2 * S),
+                   drained = smem_u32(bars + 2 * S + 1);
+    unsigned* slot = reinterpret_cast<unsigned*>(bars + 2 * S + 2);
     const unsigned stage0 = smem_u32(smem);
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, 9);    // 8 producer warps + the bulk-copy issuer (expect_tx)
-            mbar_init(empty0 + 8 * s, 1);   // tcgen05.commit
+            mbar_init(full0 + 8 * s, K1_PWARPS + 1);   // producer warps + the bulk-copy issuer (expect_tx)
+            mbar_init(empty0 + 8 * s, 1);              // tcgen05.commit
         }
         mbar_init(done, 1);
+        mbar_init(drained, K1_DWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 8) tmem_alloc512(smem_u32(slot));
+    if (warp == K1_W_BULK) tmem_alloc512(smem_u32(slot));
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const unsigned tmem = *slot;
+    const unsigned tmem = *slot;   // chunk accumulator: columns [0, Hn); running sum: columns [256, 256 + Hn)
 
-    if (warp < 8) {
-        // ---- producers: Hill activations of this CTA's 128 x 16 slab of y, hi/lo split, core-matrix layout ----
-        const int rl = warp * 16 + (lane & 7), kc = lane >> 3;   // rows rl and rl + 8, k-chunk kc (4 floats)
-        float cur[8], nxt[8];
-        auto load = [&](int kb, float (&v)[8]) {
+    if (warp < K1_PWARPS) {
+        // ---- producers: Hill activation of this CTA's 128 x 16 slab of y, hi/lo split, core-matrix layout ----
+        const int rl = warp * 8 + (lane & 7), kc = lane >> 3;   // row rl, k-chunk kc (4 floats)
+        const int row = m0 + rl;
+        const float* src = p.y + (size_t)row * p.G;
+        const bool rok = row < p.B;
+        const unsigned a_off = (unsigned)(((kc * 16 + (rl >> 3)) * 8 + (rl & 7)) * 16);
+        // y is read in super-blocks of K1_PF k-blocks: all loads of the NEXT super-block (K1_PF x 64 contiguous bytes
+        // of this thread's row, requested back to back with a 256-byte L2 prefetch hint so that DRAM sees whole
+        // bursts of one page) are in flight while the current super-block is converted and handed to the MMAs.
+        float cur[K1_PF][4], nxt[K1_PF][4];
+        auto load = [&](int i, float (&v)[K1_PF][4]) {   // k-blocks kb0 + i .. kb0 + i + K1_PF - 1
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int row = m0 + rl + 8 * it;
-                const float* src = p.y + (size_t)row * p.G;
+            for (int u = 0; u < K1_PF; ++u) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    const int g = kb * BK + kc * 4 + j;
-                    v[it * 4 + j] = (row < p.B && g < p.G) ? __ldg(src + g) : 0.5f;   // s(0.5) = l(0.5) = 0
+                    const int g = (kb0 + i + u) * BK + kc * 4 + j;
+                    float t = 0.5f;   // s(0.5) = l(0.5) = 0
+                    if (rok && i + u < nkb && g < p.G && !(p.dbg & 16))
+                        asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
+                    v[u][j] = t;
                 }
             }
         };
-        load(kb0, cur);
-        for (int i = 0; i < nkb; ++i) {
-            const int s = i % S;
-            const unsigned ph = (unsigned)(i / S) & 1u;
-            if (i + 1 < nkb) load(kb0 + i + 1, nxt);
-            float4 t[2][4];
+        load(0, cur);
+        long long t_empty = 0, t0 = clock64();
+        int s = 0;           // ring slot of k-block i
+        unsigned ph = 0;     // its phase parity
+        for (int i0 = 0; i0 < nkb; i0 += K1_PF) {
+            if (i0 + K1_PF < nkb) load(i0 + K1_PF, nxt);
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                float sv[4], lv[4], shi[4], slo[4], lhi[4], llo[4];
+            for (int u = 0; u < K1_PF; ++u) {
+                const int i = i0 + u;
+                if (i < nkb) {
+                    float hi[4], lo[4];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    hill(cur[it * 4 + j], sv[j], lv[j]);
-                    split_tf32(sv[j], shi[j], slo[j]);
-                    split_tf32(lv[j], lhi[j], llo[j]);
+                    for (int j = 0; j < 4; ++j) {
+                        float sv, lv;
+                        hill(cur[u][j], sv, lv, br && !(p.dbg & 2));
+                        split_tf32(br ? lv : sv, hi[j], lo[j]);
+                    }
+                    const long long tw = p.prof ? clock64() : 0;
+                    if (lane == 0) mbar_wait(empty0 + 8 * s, ph ^ 1u);   // one poller per warp
+                    __syncwarp();
+                    if (p.prof) t_empty += clock64() - tw;
+                    unsigned char* a = smem + (size_t)s * stage_bytes + a_off;
+                    *reinterpret_cast<float4*>(a) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+                    *reinterpret_cast<float4*>(a + K1_A_TILE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+                    if (!(p.dbg & 32)) fence_async_smem();   // generic-proxy writes -> visible to the async-proxy reads
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(full0 + 8 * s);
+                    if (++s == S) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
                 }
-                t[it][0] = make_float4(shi[0], shi[1], shi[2], shi[3]);
-                t[it][1] = make_float4(slo[0], slo[1], slo[2], slo[3]);
-                t[it][2] = make_float4(lhi[0], lhi[1], lhi[2], lhi[3]);
-                t[it][3] = make_float4(llo[0], llo[1], llo[2], llo[3]);
             }
-            mbar_wait(empty0 + 8 * s, ph ^ 1u);
-            unsigned char* a = smem + (size_t)s * stage_bytes;
 #pragma unroll
-            for (int it = 0; it < 2; ++it) {
-                const int r = rl + 8 * it;
-                const unsigned off = (unsigned)(((kc * 16 + (r >> 3)) * 8 + (r & 7)) * 16);
+            for (int u = 0; u < K1_PF; ++u)
 #pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(a + q * K1_A_TILE + off) = t[it][q];
-            }
-            fence_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
-            __syncwarp();
-            if (lane == 0) mbar_arrive(full0 + 8 * s);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+                for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
         }
-        // ---- epilogue: accumulators -> K-split partial sums ----
-        mbar_wait(done, 0u);
-        tc_fence_after();
-        const int q = warp & 3, br = warp >> 2;
-        const int row = m0 + q * 32 + lane;
-        float* dst = p.spart + ((size_t)ks * p.Bpad + row) * (2 * Hn) + br * Hn;
-        for (int c0 = 0; c0 < Hn; c0 += 16) {
-            float v[16];
-            tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(br * 256 + c0), v);
-#pragma unroll
-            for (int j = 0; j < 16; j += 4)
-                *reinterpret_cast<float4*>(dst + c0 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.prof && tid == 0) {
+            unsigned long long* q = p.prof + 8 * br + 4;
+            atomicAdd(q + 0, (unsigned long long)(clock64() - t0));
+            atomicAdd(q + 1, (unsigned long long)t_empty);
         }
-    } else if (warp == 8) {
+    } else if (warp == K1_W_BULK) {
         if (lane == 0) {
+            int s = 0;
+            unsigned ph = 0;
             for (int i = 0; i < nkb; ++i) {
-                const int s = i % S;
-                const unsigned ph = (unsigned)(i / S) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                mbar_expect_tx(full0 + 8 * s, b_bytes);
-                bulk_g2s(stage0 + s * stage_bytes + K1_A_BYTES, p.w1img + (size_t)(kb0 + i) * 4 * Hn * BK, b_bytes,
-                         full0 + 8 * s);
+                if (p.dbg & 8) {   // timing experiment: no operand copy
+                    mbar_arrive(full0 + 8 * s);
+                } else {
+                    mbar_expect_tx(full0 + 8 * s, b_bytes);
+                    bulk_g2s(stage0 + s * stage_bytes + K1_A_BYTES,
+                             p.w1img + ((size_t)(kb0 + i) * 4 + 2 * br) * Hn * BK, b_bytes, full0 + 8 * s);
+                }
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
-    } else {
-        if (lane == 0) {
-            const unsigned idesc = idesc_tf32(128, Hn);
-            for (int i = 0; i < nkb; ++i) {
-                const int s = i % S;
-                const unsigned ph = (unsigned)(i / S) & 1u;
-                mbar_wait(full0 + 8 * s, ph);
-                tc_fence_after();
-                const unsigned a_base = stage0 + s * stage_bytes, b_base = a_base + K1_A_BYTES;
+    } else if (warp == K1_W_MMA) {
+        // ---- MMA issuer: the whole warp runs the loop (uniform control flow, descriptors in uniform registers); one
+        // elected lane issues the tcgen05 instructions ----
+        const unsigned idesc = idesc_tf32(128, Hn);
+        const uint64_t a_hi_part = smem_desc(0, p.a_lbo, p.a_sbo), b_hi_part = smem_desc(0, p.b_lbo, p.b_sbo);
+        int s = 0, c = 0, ic = 0;
+        unsigned ph = 0;
+        long long t_full = 0, t_drained = 0, t0 = clock64();
+        for (int i = 0; i < nkb; ++i) {
+            if (ic == 0 && c > 0) {   // the previous chunk's sum must have left the chunk accumulator
+                const long long tw = p.prof ? clock64() : 0;
+                mbar_wait(drained, (unsigned)(c - 1) & 1u);
+                if (p.prof) t_drained += clock64() - tw;
+            }
+            const long long tw = p.prof ? clock64() : 0;
+            mbar_wait(full0 + 8 * s, ph);
+            if (p.prof) t_full += clock64() - tw;
+            tc_fence_after();
+            const unsigned a_base = stage0 + s * stage_bytes, b_base = a_base + K1_A_BYTES;
+            if (elect_one()) {
 #pragma unroll
                 for (int k8 = 0; k8 < BK / 8; ++k8) {
-#pragma unroll
-                    for (int br = 0; br < 2; ++br) {
-                        const uint64_t a_hi = smem_desc(a_base + (2 * br) * K1_A_TILE + k8 * p.a_kadv, p.a_lbo, p.a_sbo);
-                        const uint64_t a_lo =
-                            smem_desc(a_base + (2 * br + 1) * K1_A_TILE + k8 * p.a_kadv, p.a_lbo, p.a_sbo);
-                        const uint64_t b_hi = smem_desc(b_base + (2 * br) * b_tile + k8 * p.b_kadv, p.b_lbo, p.b_sbo);
-                        const uint64_t b_lo =
-                            smem_desc(b_base + (2 * br + 1) * b_tile + k8 * p.b_kadv, p.b_lbo, p.b_sbo);
-                        const unsigned d = tmem + (unsigned)(br * 256);
-                        const unsigned acc = (i > 0 || k8 > 0) ? 1u : 0u;
-                        if (p.nterms == 3) {
-                            mma_tf32(d, a_lo, b_hi, idesc, acc);
-                            mma_tf32(d, a_hi, b_lo, idesc, 1u);
-                            mma_tf32(d, a_hi, b_hi, idesc, 1u);
-                        } else {
-                            mma_tf32(d, a_hi, b_hi, idesc, acc);
-                        }
+                    const uint64_t a_hi = desc_at(a_hi_part, a_base + k8 * p.a_kadv);
+                    const uint64_t a_lo = desc_at(a_hi_part, a_base + K1_A_TILE + k8 * p.a_kadv);
+                    const uint64_t b_hi = desc_at(b_hi_part, b_base + k8 * p.b_kadv);
+                    const uint64_t b_lo = desc_at(b_hi_part, b_base + b_tile + k8 * p.b_kadv);
+                    const unsigned acc = (ic > 0 || k8 > 0) ? 1u : 0u;
+                    if (p.dbg & 4) continue;   // timing experiment: no MMAs
+                    if (p.nterms == 3) {
+                        mma_tf32(tmem, a_lo, b_hi, idesc, acc);
+                        mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
+                        mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
+                    } else {
+                        mma_tf32(tmem, a_hi, b_hi, idesc, acc);
                     }
                 }
                 mma_commit(empty0 + 8 * s);
+                if (ic == p.chunk - 1 || i == nkb - 1) mma_commit(done);
             }
-            mma_commit(done);
+            __syncwarp();
+            if (++s == S) {
+                s = 0;
+                ph ^= 1u;
+            }
+            if (++ic == p.chunk) {
+                ic = 0;
+                ++c;
+            }
         }
+        if (p.prof && lane == 0) {
+            unsigned long long* q = p.prof + 8 * br;
+            atomicAdd(q + 0, (unsigned long long)(clock64() - t0));
+            atomicAdd(q + 1, (unsigned long long)t_full);
+            atomicAdd(q + 2, (unsigned long long)t_drained);
+            atomicAdd(q + 3, (unsigned long long)nkb);
+        }
+    } else {
+        // ---- drain warps: running sum += chunk sum (round-to-nearest fp32 adds), all inside tensor memory; the last
+        // chunk's result goes to this CTA's partial-sum slot ----
+        const int q = warp & 3;
+        const unsigned trow = tmem + ((unsigned)(q * 32) << 16);
+        float* dst = p.spart + ((size_t)ks * p.Bpad + (m0 + q * 32 + lane)) * (2 * Hn) + br * Hn;
+        long long t_drain = 0;
+        for (int c = 0; c < nchunks; ++c) {
+            if (lane == 0) mbar_wait(done, (unsigned)c & 1u);
+            __syncwarp();
+            const long long tw = p.prof ? clock64() : 0;
+            tc_fence_after();
+            const bool last = c == nchunks - 1;
+            for (int c0 = 0; c0 < Hn; c0 += 32) {
+                // two 16-column groups in flight per round trip to tensor memory
+                const bool two = c0 + 16 < Hn;
+                unsigned v0[16], v1[16], r0[16], r1[16];
+                tmem_ld16_nowait(trow + c0, v0);
+                if (two) tmem_ld16_nowait(trow + c0 + 16, v1);
+                if (c > 0) {
+                    tmem_ld16_nowait(trow + 256 + c0, r0);
+                    if (two) tmem_ld16_nowait(trow + 256 + c0 + 16, r1);
+                }
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c > 0) {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        v0[j] = __float_as_uint(__uint_as_float(r0[j]) + __uint_as_float(v0[j]));
+                        if (two) v1[j] = __float_as_uint(__uint_as_float(r1[j]) + __uint_as_float(v1[j]));
+                    }
+                }
+                if (last) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        *reinterpret_cast<uint4*>(dst + c0 + j) = make_uint4(v0[j], v0[j + 1], v0[j + 2], v0[j + 3]);
+                        if (two)
+                            *reinterpret_cast<uint4*>(dst + c0 + 16 + j) =
+                                make_uint4(v1[j], v1[j + 1], v1[j + 2], v1[j + 3]);
+                    }
+                } else {
+                    tmem_st16(trow + 256 + c0, v0);
+                    if (two) tmem_st16(trow + 256 + c0 + 16, v1);
+                }
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(drained);
+            if (p.prof) t_drain += clock64() - tw;
+        }
+        if (p.prof && warp == K1_W_DRAIN && lane == 0) atomicAdd(p.prof + 8 * br + 6, (unsigned long long)t_drain);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 8) tmem_free512(tmem);
+    if (warp == K1_W_BULK) tmem_free512(tmem);
 }
 
 // ---- K-split reduction + bias + exp + operand image of [S|P] ------------------------------------------------------------
 // one thread per (batch row b in [0, BT*256), 4 consecutive Hn-numbered columns)
-__global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K2, int ks, const float* __restrict__ spart,
+__global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K2, int ks_s, int ks_p, const float* __restrict__ spart,
                                    const float* __restrict__ bias, float* __restrict__ SP, float* __restrict__ spimg) {
     const int BT = phx_tc_BT(B), KB2 = 2 * Hn / BK, C4 = 2 * Hn / 4;
     const size_t total = (size_t)BT * 256 * C4;
@@ -331,7 +483,8 @@ __global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K
         const int c = c4 * 4, br = c / Hn, n0 = c % Hn;
         float v[4] = {0.f, 0.f, 0.f, 0.f};
         if (b < B) {
-            for (int s = 0; s < ks; ++s) {
+            const int nslots = br ? ks_p : ks_s;
+            for (int s = 0; s < nslots; ++s) {
                 const float4 t = *reinterpret_cast<const float4*>(spart + ((size_t)s * Bpad + b) * (2 * Hn) + c);
                 v[0] += t.x; v[1] += t.y; v[2] += t.z; v[3] += t.w;
             }
@@ -370,7 +523,7 @@ struct JointParams {
     const float* relum;   // [G]
     float* f;             // [B][G]
 };
-constexpr int K2_THREADS = 192;
+constexpr int K2_THREADS = 320;   // bulk-copy issuer, MMA issuer, 8 epilogue warps
 constexpr int K2_STAGES = 4;
 constexpr unsigned K2_A_TILE = 128 * BK * 4, K2_B_TILE = 256 * BK * 4;
 constexpr unsigned K2_STAGE_BYTES = 2 * K2_A_TILE + 2 * K2_B_TILE;   // 48 KB
@@ -393,7 +546,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
         }
         for (int b = 0; b < 2; ++b) {
             mbar_init(tfull0 + 8 * b, 1);
-            mbar_init(tempty0 + 8 * b, 4);   // one arrive per epilogue warp
+            mbar_init(tempty0 + 8 * b, 8);   // one arrive per epilogue warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -457,8 +610,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             }
         }
     } else {
-        // ---- epilogue warps 2..5: lane quarter q = warp % 4 of the accumulator = 32 consecutive genes ----
-        const int q = warp & 3;
+        // ---- epilogue warps 2..9: lane quarter q = warp % 4 of the accumulator = 32 consecutive genes; the two warps
+        // of a quarter take 128 batch rows (accumulator columns) each.  y does not depend on the MMAs, so the loads of
+        // the next 16 columns are always in flight while the current 16 are combined and stored.
+        const int q = warp & 3, half = (warp - 2) >> 2;
         int j = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
             const int gt = t / p.BT, bt = t % p.BT;
@@ -467,25 +622,30 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             const int g = gt * 128 + q * 32 + lane;
             const bool gok = g < p.G;
             const float rm = (gok && p.decay) ? p.relum[g] : 1.f;
-            mbar_wait(tfull0 + 8 * buf, tph);
-            tc_fence_after();
-            const int b0 = bt * 256;
-            for (int c0 = 0; c0 < 256 && b0 + c0 < p.B; c0 += 16) {
-                float v[16], yv[16];
-                tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * 256 + c0), v);
-                if (p.decay) {
-#pragma unroll
-                    for (int jj = 0; jj < 16; ++jj) {
-                        const int row = b0 + c0 + jj;
-                        yv[jj] = (gok && row < p.B) ? p.y[(size_t)row * p.G + g] : 0.f;
-                    }
-                }
+            const int b0 = bt * 256 + half * 128;
+            const int ncol = min(128, p.B - b0);   // valid batch rows of this warp's half (may be <= 0)
+            float yv[16], yn[16];
+            auto loady = [&](int c0, float (&dst)[16]) {
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     const int row = b0 + c0 + jj;
-                    if (gok && row < p.B) {
+                    dst[jj] = (p.decay && gok && c0 + jj < ncol) ? __ldg(p.y + (size_t)row * p.G + g) : 0.f;
+                }
+            };
+            loady(0, yn);
+            mbar_wait(tfull0 + 8 * buf, tph);
+            tc_fence_after();
+            for (int c0 = 0; c0 < ncol; c0 += 16) {
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) yv[jj] = yn[jj];
+                if (c0 + 16 < ncol) loady(c0 + 16, yn);
+                float v[16];
+                tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * 256 + half * 128 + c0), v);
+#pragma unroll
+                for (int jj = 0; jj < 16; ++jj) {
+                    if (gok && c0 + jj < ncol) {
                         const float r = p.decay ? rm * (v[jj] - yv[jj]) : v[jj];
-                        p.f[(size_t)row * p.G + g] = p.fscale * r;
+                        p.f[(size_t)(b0 + c0 + jj) * p.G + g] = p.fscale * r;
                     }
                 }
             }
@@ -497,6 +657,21 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_free512(tmem);
+}
+
+// PHX_TC_PROF=1: 16 device counters, printed (and reset) by phx_tc_prof_dump()
+unsigned long long* g_prof = nullptr;
+unsigned long long* phx_tc_prof_buffer() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("PHX_TC_PROF");
+        on = (e && atoi(e)) ? 1 : 0;
+        if (on) {
+            cudaMalloc((void**)&g_prof, 16 * sizeof(unsigned long long));
+            cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long));
+        }
+    }
+    return g_prof;
 }
 
 int debug_flags() {
@@ -528,16 +703,16 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
                               float fscale, float* SP, float* tcws, cudaStream_t st) {
     const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H);
     const int Bpad = phx_round_up(B, 128);
-    int ks, per;
-    phx_tc_ksplit(G, B, &ks, &per);
+    const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
     float* base = reinterpret_cast<float*>(((uintptr_t)tcws + 127) & ~(uintptr_t)127);
     float* spart = base;
-    float* spimg = spart + (size_t)ks * Bpad * 2 * Hn;
+    float* spimg = spart + (size_t)pl.slots * Bpad * 2 * Hn;
     const int dbg = debug_flags();
     const int nterms = (w.tc == 1) ? 1 : 3;
 
     BranchParams bp;
-    bp.G = G; bp.B = B; bp.Bpad = Bpad; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(G); bp.kb_per_split = per; bp.nterms = nterms;
+    bp.G = G; bp.B = B; bp.Bpad = Bpad; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(G); bp.chunk = phx_tc_chunk(); bp.nterms = nterms; bp.dbg = dbg;
+    bp.mtiles = pl.mtiles; bp.ks_p = pl.ks_p; bp.per_p = pl.per_p; bp.ks_s = pl.ks_s; bp.per_s = pl.per_s;
     bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hn / 8) * 128; bp.b_sbo = 128;
     bp.a_kadv = 2 * bp.a_lbo; bp.b_kadv = 2 * bp.b_lbo;
     if (dbg & 1) {   // diagnostic: swapped meaning of the two descriptor offsets
@@ -545,10 +720,15 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
         t = bp.b_lbo; bp.b_lbo = bp.b_sbo; bp.b_sbo = t;
     }
     bp.y = y; bp.w1img = w.w1img; bp.spart = spart;
-    const size_t stage1 = K1_A_BYTES + (size_t)4 * Hn * BK * 4;
+    bp.prof = phx_tc_prof_buffer();
+    const size_t stage1 = K1_A_BYTES + (size_t)2 * Hn * BK * 4;
     int S1 = (int)((PHX_SMEM_LIMIT - 256) / stage1);
-    if (S1 > 4) S1 = 4;
-    if (S1 < 2) {
+    if (S1 > 6) S1 = 6;
+    if (const char* e = getenv("PHX_TC_STAGES")) {   // experiment
+        int v = atoi(e);
+        if (v >= 1 && v < S1) S1 = v;
+    }
+    if (S1 < 1) {
         phx_set_error("tc branch kernel: stage of %zu bytes does not fit twice", stage1);
         return PHX_ERR_UNSUPPORTED;
     }
@@ -560,14 +740,14 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
         cudaFuncSetAttribute(tc_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
         attr_done = true;
     }
-    tc_branch_kernel<<<dim3(Bpad / 128, ks), K1_THREADS, smem1, st>>>(bp);
+    tc_branch_kernel<<<pl.mtiles * (pl.ks_p + pl.ks_s), K1_THREADS, smem1, st>>>(bp);
 
     const int BT = phx_tc_BT(B);
     {
         const size_t total = (size_t)BT * 256 * (2 * Hn / 4);
         int blocks = (int)((total + 255) / 256);
         if (blocks > PHX_TC_SMS * 16) blocks = PHX_TC_SMS * 16;
-        tc_spfinish_kernel<<<blocks, 256, 0, st>>>(B, Bpad, H, Hp, Hn, K2, ks, spart, w.bias, SP, spimg);
+        tc_spfinish_kernel<<<blocks, 256, 0, st>>>(B, Bpad, H, Hp, Hn, K2, pl.ks_s, pl.ks_p, spart, w.bias, SP, spimg);
     }
     if (f) {
         JointParams jp;
@@ -590,4 +770,18 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
         return PHX_ERR_CUDA;
     }
     return PHX_OK;
+}
+
+extern "C" void phx_tc_prof_dump(void) {
+    if (!g_prof) return;
+    unsigned long long h[16];
+    cudaMemcpy(h, g_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    cudaMemset(g_prof, 0, sizeof(h));
+    for (int br = 0; br < 2; ++br) {
+        const unsigned long long* q = h + 8 * br;
+        const double n = q[3] ? (double)q[3] : 1.0;
+        printf("tc_branch %s: k-blocks %llu | MMA thread cycles/k-block: total %.0f wait_full %.0f wait_drained %.0f | "
+               "producer warp 0: total %.0f wait_empty %.0f drain %.0f\n",
+               br ? "prods" : "sums", q[3], q[0] / n, q[1] / n, q[2] / n, q[4] / n, q[5] / n, q[6] / n);
+    }
 }

@@ -19,6 +19,7 @@
 //     spimg [BT][KB2][hi|lo][256 x 16]        [S|P] rows, written by the K-split reduction kernel (N = batch rows)
 // Hn = round_up(H, 16) (UMMA N granularity at M = 128); pads are zero in every image.
 #pragma once
+#include <stdlib.h>
 // (included from phx_common.cuh after phx_round_up)
 
 #define PHX_TC_BK 16
@@ -48,21 +49,45 @@ static inline __host__ __device__ int phx_tc_tile_off(int R, int r, int k) {
     return ((((k >> 2) * (R >> 3) + (r >> 3)) * 8 + (r & 7)) << 2) + (k & 3);
 }
 
-// K-split of the branch contraction: how many CTAs share one 128-row tile, and k-blocks per split
-static inline void phx_tc_ksplit(int G, int B, int* ks, int* kb_per_split) {
-    const int mtiles = (B + 127) / 128, KB1 = phx_tc_KB1(G);
-    int want = PHX_TC_SMS / mtiles;
-    if (want < 1) want = 1;
-    if (want > PHX_TC_MAX_KSPLIT) want = PHX_TC_MAX_KSPLIT;
-    int per = (KB1 + want - 1) / want;
-    if (per < 4) per = KB1 < 4 ? KB1 : 4;
-    *kb_per_split = per;
-    *ks = (KB1 + per - 1) / per;
+// Accumulation-chain limit of the branch contraction: k-blocks summed inside tensor memory before the chunk sum is
+// drained to its own partial-sum slot (phx_tc.cu, "Accumulation chains").  16 k-blocks = 96 accumulating MMAs.
+static inline int phx_tc_chunk() {
+    static int chunk = 0;
+    if (!chunk) {
+        const char* e = getenv("PHX_TC_CHUNK");
+        int v = e ? atoi(e) : 16;
+        chunk = v > 0 ? v : 16;
+    }
+    return chunk;
 }
-// scratch of the tensor-core RHS in floats (K-split partial sums + [S|P] operand image), 128-byte aligned inside
+// Work split of the branch contraction (tc_branch_kernel): every CTA owns one branch, one 128-row tile and a K range
+// of whole chunks.  Aim at two CTAs per SM in total (the hardware scheduler balances them; the log1p CTAs are launched
+// first).  Measured on B200 a log1p CTA needs ~1.2x the time of a soft-sign CTA per k-block (both are bound by the
+// shared-memory traffic of the 3xTF32 operand reads), so the soft-sign branch gets 4/9 of the K-splits.
+struct PhxTcBranchPlan {
+    int mtiles, ks_p, per_p, ks_s, per_s, slots;
+};
+static inline PhxTcBranchPlan phx_tc_branch_plan(int G, int B) {
+    PhxTcBranchPlan pl;
+    const int KB1 = phx_tc_KB1(G), chunk = phx_tc_chunk();
+    const int nch = (KB1 + chunk - 1) / chunk;   // chunks along K
+    pl.mtiles = (B + 127) / 128;
+    int ks_total = (2 * PHX_TC_SMS) / pl.mtiles;
+    if (ks_total < 2) ks_total = 2;
+    int ks_p = (ks_total * 5 + 4) / 9, ks_s = ks_total - ks_p;
+    if (ks_s < 1) ks_s = 1;
+    if (ks_p > nch) ks_p = nch;
+    if (ks_s > nch) ks_s = nch;
+    pl.per_p = (nch + ks_p - 1) / ks_p * chunk;
+    pl.per_s = (nch + ks_s - 1) / ks_s * chunk;
+    pl.ks_p = (KB1 + pl.per_p - 1) / pl.per_p;
+    pl.ks_s = (KB1 + pl.per_s - 1) / pl.per_s;
+    pl.slots = pl.ks_p > pl.ks_s ? pl.ks_p : pl.ks_s;
+    return pl;
+}
+// scratch of the tensor-core RHS in floats (partial-sum slots + [S|P] operand image), 128-byte aligned inside
 static inline size_t phx_tc_scratch_floats(int G, int H, int B) {
-    int ks, per;
-    phx_tc_ksplit(G, B, &ks, &per);
+    const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
     const size_t Bpad = (size_t)phx_round_up(B, 128);
-    return (size_t)ks * Bpad * 2 * phx_tc_Hn(H) + phx_tc_spimg_floats(H, B) + 64;
+    return (size_t)pl.slots * Bpad * 2 * phx_tc_Hn(H) + phx_tc_spimg_floats(H, B) + 64;
 }

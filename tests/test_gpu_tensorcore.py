@@ -1,0 +1,172 @@
+"""GPU parity tests of the tcgen05 (tensor-core) batched RHS: calls with B >= 128 rows run the branch and joint
+contractions as 3xTF32 MMAs with TMEM accumulators (csrc/phx_tc.cu).
+
+Tolerances:
+  * '3xtf32' (default): same bar as the fp32 CUDA-core path, relative L2 <= 1e-5 against the fp32 oracle
+    (observed 3e-7 .. 9e-6 up to 20 000 genes; the accumulation chain inside tensor memory is capped at 96 MMAs because
+    the tensor core adds with truncation);
+  * 'tf32' (single pass, reported separately): relative L2 <= 2e-3 (observed 2e-4 .. 6e-4);
+  * 'fp32': the CUDA-core contractions, <= 1e-5.
+"""
+import pytest
+import torch
+
+from golden_util import rel_l2
+from oracle import phoenix_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import phoenix_b200 as pb
+    pb.set_sync_errors(True)
+    yield pb
+    pb.set_precision("3xtf32")
+    pb.set_sync_errors(False)
+
+
+def make_net(pb, w):
+    net = pb.ODENet("cuda", w.G, neurons=w.H)
+    with torch.no_grad():
+        for p, src in zip(net.parameters(), w.as_list()):
+            p.copy_(src)
+    return net
+
+
+SHAPES = [(350, 40, 300), (37, 5, 128), (1001, 100, 257), (690, 40, 1000), (3551, 120, 256)]
+
+
+@pytest.mark.parametrize("G,H,B", SHAPES)
+def test_tc_rhs_matches_oracle(pb, G, H, B):
+    """ODENet.forward and prior_only_forward (odenet.py:85-98) on ragged shapes: G, H, B not multiples of any tile."""
+    w = O.make_weights(G, H, 300 + G, dense=True, neg_mult_frac=0.2)
+    net = make_net(pb, w)
+    y = torch.rand(B, 1, G, generator=torch.Generator().manual_seed(B)) * 1.5 - 0.25
+    pb.set_precision("3xtf32")
+    with torch.no_grad():
+        f = net(None, y.cuda())
+        J = net.prior_only_forward(None, y.cuda())
+    assert rel_l2(f.cpu(), O.rhs(w, y)) < 1e-5
+    assert rel_l2(J.cpu(), O.rhs(w, y, decay=False)) < 1e-5
+
+
+def test_tc_precision_modes(pb):
+    G, H, B = 1001, 100, 384
+    w = O.make_weights(G, H, 17, dense=True)
+    net = make_net(pb, w)
+    y = torch.rand(B, G, generator=torch.Generator().manual_seed(3))
+    ref = O.rhs(w, y)
+    err = {}
+    try:
+        for mode in ("fp32", "3xtf32", "tf32"):
+            pb.set_precision(mode)
+            with torch.no_grad():
+                err[mode] = rel_l2(net(None, y.cuda()).cpu(), ref)
+    finally:
+        pb.set_precision("3xtf32")
+    assert err["fp32"] < 1e-5 and err["3xtf32"] < 1e-5
+    assert 1e-6 < err["tf32"] < 2e-3          # the single-pass mode really is a different arithmetic
+    with pytest.raises(ValueError):
+        pb.set_precision("bf16")
+
+
+def test_tc_below_threshold_uses_fp32_path(pb):
+    """B < 128 rows never touches the tensor cores: identical bits in every precision mode."""
+    G, H, B = 350, 40, 127
+    w = O.make_weights(G, H, 18, dense=True)
+    net = make_net(pb, w)
+    y = torch.rand(B, G, generator=torch.Generator().manual_seed(4)).cuda()
+    outs = []
+    try:
+        for mode in ("fp32", "3xtf32", "tf32"):
+            pb.set_precision(mode)
+            with torch.no_grad():
+                outs.append(net(None, y).clone())
+    finally:
+        pb.set_precision("3xtf32")
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_tc_operand_images_follow_weight_updates(pb):
+    """The operand images are rebuilt lazily after phx_pack_weights: an in-place optimiser-style update must be seen."""
+    G, H, B = 350, 40, 256
+    w = O.make_weights(G, H, 19, dense=True)
+    net = make_net(pb, w)
+    y = torch.rand(B, G, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        f0 = net(None, y.cuda()).cpu()
+        for p in net.parameters():
+            p.mul_(0.5)
+        f1 = net(None, y.cuda()).cpu()
+    w2 = O.make_weights(G, H, 19, dense=True)
+    for t in w2.as_list():
+        t.mul_(0.5)
+    assert rel_l2(f0, O.rhs(w, y)) < 1e-5
+    assert rel_l2(f1, O.rhs(w2, y)) < 1e-5
+
+
+def test_tc_bitwise_determinism_and_exact_scaling(pb):
+    """Fixed MMA issue order and fixed K-split reduction order => run-to-run identical bits; and because the hi/lo TF32
+    split commutes with powers of two, doubling Wa doubles prior_only_forward exactly (size-independent property)."""
+    G, H, B = 3551, 120, 640
+    w = O.make_weights(G, H, 20, dense=True)
+    net = make_net(pb, w)
+    y = torch.rand(B, G, generator=torch.Generator().manual_seed(6)).cuda()
+    with torch.no_grad():
+        a = net.prior_only_forward(None, y).clone()
+        b = net.prior_only_forward(None, y).clone()
+        net.net_alpha_combine.linear_out.weight.mul_(2.0)
+        c = net.prior_only_forward(None, y).clone()
+    assert torch.equal(a, b)
+    assert torch.equal(c, 2.0 * a)
+
+
+def test_tc_vjp_and_batched_solves(pb):
+    """VJP (branch contraction on tensor cores, cotangent contractions fp32) and the streaming solvers on B = 256."""
+    G, H, B = 350, 40, 256
+    w = O.make_weights(G, H, 21, dense=True, neg_mult_frac=0.1)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(7)
+    y = torch.rand(B, G, generator=gen)
+    g = torch.randn(B, G, generator=gen)
+    yg = y.cuda().requires_grad_(True)
+    net(None, yg).backward(g.cuda())
+    _, ybar, pbar = O.rhs_vjp(w, y, g, decay=True)
+    assert rel_l2(yg.grad.cpu(), ybar) < 1e-5
+    for p, ref in zip(net.parameters(), pbar):
+        assert rel_l2(p.grad.cpu(), ref) < 2e-5
+    t = torch.tensor([0.0, 0.5, 1.0])
+    with torch.no_grad():
+        yr = pb.odeint(net, y.cuda(), t, method="rk4")
+        yd = pb.odeint(net, y.cuda(), t, method="dopri5", rtol=1e-5, atol=1e-7)
+    y_ref, _ = O.odeint(w, y, t, method="rk4")
+    yd_ref, _ = O.odeint(w, y, t, method="dopri5", rtol=1e-5, atol=1e-7)
+    assert rel_l2(yr.cpu(), y_ref) < 1e-5
+    assert rel_l2(yd.cpu(), yd_ref) < 2e-5
+
+
+def test_tc_full_size_sweep_shape_against_float64_rows(pb):
+    """BASELINE config 5 shape (20 000 genes x 4 096 trajectories, H = 200): the full batch runs on the tensor cores;
+    256 of its rows are checked against a float64 evaluation of odenet.py:85-91 on the GPU."""
+    G, H, B = 20000, 200, 4096
+    torch.manual_seed(22)
+    net = pb.ODENet("cuda", G, neurons=H)
+    with torch.no_grad():
+        for p in net.parameters():
+            if p.dim() == 2 and p.shape[0] != 1:
+                p.copy_(torch.randn_like(p) * 0.02)
+    y = torch.rand(B, G, device="cuda")
+    with torch.no_grad():
+        f = net(None, y)
+        rows = torch.arange(0, B, 16, device="cuda")
+        yd = y[rows].double()
+        z = yd - 0.5
+        s = z / (1 + z.abs())
+        l = torch.log1p(s)
+        S = s @ net.net_sums.linear_out.weight.double().t() + net.net_sums.linear_out.bias.double()
+        P = torch.exp(l @ net.net_prods.linear_out.weight.double().t() + net.net_prods.linear_out.bias.double())
+        J = torch.cat([S, P], -1) @ net.net_alpha_combine.linear_out.weight.double().t()
+        ref = torch.relu(net.gene_multipliers.double()) * (J - yd)
+    assert torch.isfinite(f).all()
+    assert rel_l2(f[rows].cpu(), ref.cpu()) < 1e-5

@@ -68,6 +68,10 @@ def main():
                 ms = min(ev[i].elapsed_time(ev[i + 1]) for i in range(a.reps))
             print(json.dumps({"G": G, "H": H, "B": B, "mode": mode, "rel_l2": err, "max_abs": mx, "ms": ms,
                               "fp32_equiv_tflops": flops / ms / 1e9}), flush=True)
+            if os.environ.get("PHX_TC_PROF"):
+                from phoenix_b200 import _lib
+                _lib.load().phx_tc_prof_dump()
+                sys.stdout.flush()
         pb.set_precision("3xtf32")
 
 
