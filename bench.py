@@ -132,6 +132,38 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows)}
 
 
+def tensor_leg(pb, dev):
+    """ODENet.forward on the synthetic-sweep shape (BASELINE config 5: 20 000 genes x 4 096 trajectories, H = 200):
+    the dense branch / joint contractions on tcgen05 (3xTF32, fp32 parity).  achieved = ALGORITHMIC flops
+    8*B*G*H per RHS evaluation / device time; operands (y 328 MB, weights 64 MB, f 328 MB) exceed L2."""
+    Gs, Hs, Bs, reps = 20000, 200, 4096, 10
+    gen = torch.Generator(device=dev).manual_seed(5)
+    net = pb.ODENet(dev, Gs, neurons=Hs)
+    y = torch.rand(Bs, Gs, device=dev, generator=gen)
+    out = {}
+    with torch.no_grad():
+        for mode in ("3xtf32", "tf32"):
+            pb.set_precision(mode)
+            for _ in range(3):
+                net(None, y)
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(reps + 1)]
+            ev[0].record()
+            for i in range(reps):
+                net(None, y)
+                ev[i + 1].record()
+            torch.cuda.synchronize()
+            out[mode] = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(reps)) / reps
+    pb.set_precision("3xtf32")
+    flops = 8.0 * Bs * Gs * Hs
+    del net, y
+    torch.cuda.empty_cache()
+    return {"kernel": "tc_branch_kernel + tc_spfinish_kernel + tc_joint_kernel",
+            "workload": "ODENet.forward, 20000 genes x 200 neurons x 4096 rows (3 launches per RHS evaluation)",
+            "achieved": flops / (out["3xtf32"] * 1e-3) / 1e12, "launch_ms": out["3xtf32"],
+            "algorithmic_flops": flops, "executed_mma_flops": 3.0 * flops,
+            "tf32_single_pass_ms": out["tf32"], "dtype": "tf32 x3 (fp32 parity)"}
+
+
 def run_ours(args):
     import torch.distributed as dist
     import phoenix_b200 as pb
@@ -258,6 +290,11 @@ def run_ours(args):
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
+    # ---- tensor-core leg (rank 0, N = 1 only; bounded): the batched RHS of BASELINE config 5 ---------------------
+    tensor = None
+    if rank == 0 and world == 1 and not int(os.environ.get("PHX_BENCH_SKIP_TENSOR", "0")):
+        tensor = tensor_leg(pb, dev)
+
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------------
     stats = torch.tensor([ms_res, ms_e2e, float(evals)], dtype=torch.float64, device=dev)
     if world > 1:
@@ -312,6 +349,14 @@ def run_ours(args):
                              "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"},
             "clocks": sampler.summary(),
         }
+        if tensor is not None:
+            bf16 = float(peaks.get("bf16_tflops", 1590.0))
+            tpeak = bf16 / 2.0                            # TF32 dense = half the bf16 rate (B200_PROFILING.md)
+            line["roofline_tensor"] = dict(tensor, bound="tensor", peak=tpeak, unit="TFLOP/s",
+                                           frac=tensor["achieved"] / tpeak,
+                                           frac_of_3xtf32_ceiling=tensor["achieved"] / (tpeak / 3.0),
+                                           peak_source=("MEASURED_PEAKS.json bf16_tflops / 2" if peaks
+                                                        else "fallback 1590 / 2"))
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

@@ -12,7 +12,8 @@ tag = sys.argv[1]
 out_dir = os.path.join(REPO, "profiles")
 os.makedirs(out_dir, exist_ok=True)
 
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEYS = ["gpu__time_duration.sum", "sm__inst_executed_pipe_tensor.sum", "lts__t_bytes.sum", "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
         "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
         "sm__warps_active.avg.pct_of_peak_sustained_active", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
@@ -33,19 +34,21 @@ if os.path.exists(lp):
         a[1] += v
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, "%s_launches.txt" % tag), "w") as fh:
-        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, python bench.py --steps 2 --warmup 3\n")
+        fh.write("# ncu --metrics gpu__time_duration.sum --clock-control none, %s\n" %
+                 (sys.argv[2] if len(sys.argv) > 2 else "python bench.py --steps 2 --warmup 3"))
         fh.write("# per-launch times are cold-cache and serialised: compare SHARES\n")
         for n, (c, t) in sorted(agg.items(), key=lambda x: -x[1][1]):
             fh.write("%-72s n=%4d total_us=%11.1f avg_us=%9.1f share=%5.1f%%\n" % (n, c, t, t / c, 100 * t / tot))
     print(open(os.path.join(out_dir, "%s_launches.txt" % tag)).read())
 
-rp = os.path.join(REPO, "gpurun_out", "prof_%s.ncu-rep" % tag)
-if os.path.exists(rp):
+import glob
+for rp in sorted(glob.glob(os.path.join(REPO, "gpurun_out", "prof_%s*.ncu-rep" % tag))):
+    sub = os.path.basename(rp)[len("prof_"):-len(".ncu-rep")]
     raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     traffic = {}
-    with open(os.path.join(out_dir, "%s_ncu_full.txt" % tag), "w") as fh:
+    with open(os.path.join(out_dir, "%s_ncu_full.txt" % sub), "w") as fh:
         fh.write("# ncu --set full --clock-control none --import-source on (selected raw metrics per captured launch)\n")
         for r in rows[2:]:
             name = r[hdr.index("Kernel Name")]
@@ -63,10 +66,10 @@ if os.path.exists(rp):
             if "dram__bytes_read.sum" in vals:
                 key = name.split("(")[0].split("::")[-1].split("<")[0].strip()
                 traffic.setdefault(key, []).append(to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"))
-    print(open(os.path.join(out_dir, "%s_ncu_full.txt" % tag)).read())
+    print(open(os.path.join(out_dir, "%s_ncu_full.txt" % sub)).read())
     tj = os.path.join(out_dir, "traffic.json")
     cur = json.load(open(tj)) if os.path.exists(tj) else {}
     for k, v in traffic.items():
         cur[k] = sum(v) / len(v)
-    cur["_source"] = "profiles/%s_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch)" % tag
+    cur["_source"] = "profiles/*_ncu_full.txt (dram__bytes_read.sum + dram__bytes_write.sum per launch)"
     json.dump(cur, open(tj, "w"), indent=1)
