@@ -35,6 +35,8 @@ struct PhxPacked {
     // tensor-core operand images (phx_tc.cuh), the tail of the packed buffer; valid only once tc_pack has run on it
     const float* w1img;
     const float* waimg;
+    const float* watimg;
+    const float* w1kimg;
     int tc;   // 0: fp32 CUDA-core contractions; 3: 3xTF32 tcgen05; 1: single-pass TF32 tcgen05 (set by the entry points)
 };
 
@@ -45,7 +47,7 @@ static inline __host__ __device__ size_t phx_packed_base_floats(int G, int H) {
     return (n + 31) & ~(size_t)31;
 }
 static inline __host__ __device__ size_t phx_packed_floats(int G, int H) {
-    return phx_packed_base_floats(G, H) + phx_tc_w1img_floats(G, H) + phx_tc_waimg_floats(G, H);
+    return phx_packed_base_floats(G, H) + 2 * (phx_tc_w1img_floats(G, H) + phx_tc_waimg_floats(G, H));
 }
 
 static inline __host__ __device__ PhxPacked phx_packed_view(const float* base, int G, int H) {
@@ -58,6 +60,8 @@ static inline __host__ __device__ PhxPacked phx_packed_view(const float* base, i
     v.maskm = v.relum + phx_round_up(G, 4);
     v.w1img = base + phx_packed_base_floats(G, H);
     v.waimg = v.w1img + phx_tc_w1img_floats(G, H);
+    v.watimg = v.waimg + phx_tc_waimg_floats(G, H);
+    v.w1kimg = v.watimg + phx_tc_w1img_floats(G, H);
     v.tc = 0;
     return v;
 }
@@ -243,5 +247,9 @@ int phx_tc_prepare(phx_ctx* ctx, int G, int H, int B, const float* packed, PhxPa
 int phx_tc_pack_launch(int G, int H, const PhxPacked& w, cudaStream_t stream);
 int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay,
                               float fscale, float* SP, float* tcws, cudaStream_t stream);
+// after phx_tc_rhs_forward_launch on the same scratch: GS = (g relu(m)) WA (prods half scaled by Pr) and, if ybar != 0,
+// ybar = (GS_s Ws + (GS_p Wp)/(1+s)) / (1+|y-.5|)^2 - g relu(m); if J != 0 also the un-decayed joint J = [S|P] WA^T
+int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
+                            float* ybar, const float* SP, float* GS, float* J, float* tcws, cudaStream_t stream);
 
 void phx_set_error(const char* fmt, ...);

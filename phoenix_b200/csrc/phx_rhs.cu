@@ -284,45 +284,51 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
     float* J = GS + (size_t)B * K2;
     const float* W1 = reinterpret_cast<const float*>(w.W1);
     const float* WA = reinterpret_cast<const float*>(w.WA);
-    if (w.tc && phx_tc_shape_ok(H, B)) {   // branch contraction on the tensor cores; cotangent GEMMs below stay fp32
-        int rc = phx_tc_rhs_forward_launch(G, H, B, w, y, nullptr, 0, 1.f, SP, ws + rhs_base_floats(G, H, B), st);
+    const bool tc = w.tc && phx_tc_shape_ok(H, B);
+    const bool needJ = (f_out != nullptr) || (grads && decay);
+    if (tc) {
+        // tensor cores: [S|P], gSP, the state cotangent and the un-decayed joint (phx_tc.cu); the K = B parameter
+        // contractions below stay on the fp32 path
+        float* tcws = ws + rhs_base_floats(G, H, B);
+        int rc = phx_tc_rhs_forward_launch(G, H, B, w, y, nullptr, 0, 1.f, SP, tcws, st);
+        if (rc != PHX_OK) return rc;
+        rc = phx_tc_vjp_state_launch(G, H, B, w, y, g, decay, ybar, SP, GS, needJ ? J : nullptr, tcws, st);
         if (rc != PHX_OK) return rc;
     } else {
         rhs_sp(G, H, B, w, y, SP, st);
-    }
-    // GS = gJ WA, prods half scaled by Pr
-    {
-        LoadGJ la{g, w.relum, G, decay};
-        LoadWrow lb{WA, K2, 0};
-        EpiGS ep{GS, SP, K2, Hp};
-        sgemm(B, K2, G, la, lb, ep, st);
-    }
-    if (ybar) {
-        {   // u = GS_s Ws
-            LoadRowMajorA la{GS, K2, 0};
-            LoadWcol lb{W1, K2, 0};
-            EpiStore ep{ybar, G};
-            sgemm(B, G, Hp, la, lb, ep, st);
+        // GS = gJ WA, prods half scaled by Pr
+        {
+            LoadGJ la{g, w.relum, G, decay};
+            LoadWrow lb{WA, K2, 0};
+            EpiGS ep{GS, SP, K2, Hp};
+            sgemm(B, K2, G, la, lb, ep, st);
         }
-        {   // v = GS_p Wp, combine
-            LoadRowMajorA la{GS, K2, Hp};
-            LoadWcol lb{W1, K2, Hp};
-            EpiYbar ep{ybar, y, g, w.relum, G, decay};
-            sgemm(B, G, Hp, la, lb, ep, st);
+        if (ybar) {
+            {   // u = GS_s Ws
+                LoadRowMajorA la{GS, K2, 0};
+                LoadWcol lb{W1, K2, 0};
+                EpiStore ep{ybar, G};
+                sgemm(B, G, Hp, la, lb, ep, st);
+            }
+            {   // v = GS_p Wp, combine
+                LoadRowMajorA la{GS, K2, Hp};
+                LoadWcol lb{W1, K2, Hp};
+                EpiYbar ep{ybar, y, g, w.relum, G, decay};
+                sgemm(B, G, Hp, la, lb, ep, st);
+            }
+        }
+        if (needJ) {   // un-decayed joint, for the multiplier cotangent and/or the RHS value itself
+            LoadRowMajorA la{SP, K2, 0};
+            LoadWcol lb{WA, K2, 0};
+            EpiF ep{J, y, w.relum, G, 0, 1.f};
+            sgemm(B, G, K2, la, lb, ep, st);
         }
     }
-    const bool needJ = (f_out != nullptr) || (grads && decay);
-    if (needJ) {   // un-decayed joint, for the multiplier cotangent and/or the RHS value itself
-        LoadRowMajorA la{SP, K2, 0};
-        LoadWcol lb{WA, K2, 0};
-        EpiF ep{J, y, w.relum, G, 0, 1.f};
-        sgemm(B, G, K2, la, lb, ep, st);
-        if (f_out) {
-            size_t n = (size_t)B * G;
-            int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
-            if (decay) decay_kernel<<<blocks, 256, 0, st>>>(J, y, w.relum, G, n, fscale, f_out);
-            else cudaMemcpyAsync(f_out, J, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-        }
+    if (f_out) {
+        size_t n = (size_t)B * G;
+        int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
+        if (decay) decay_kernel<<<blocks, 256, 0, st>>>(J, y, w.relum, G, n, fscale, f_out);
+        else cudaMemcpyAsync(f_out, J, n * sizeof(float), cudaMemcpyDeviceToDevice, st);
     }
     if (grads) {
         const PhxGradOff off = phx_grad_offsets(G, H);

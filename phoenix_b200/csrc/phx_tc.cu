@@ -130,7 +130,8 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
 
 // ---- operand images of the weights -------------------------------------------------------------------------------------
 __global__ void tc_pack_kernel(int G, int H, int Hp, int K2, int Hn, const float* __restrict__ W1,
-                               const float* __restrict__ WA, float* __restrict__ w1img, float* __restrict__ waimg) {
+                               const float* __restrict__ WA, float* __restrict__ w1img, float* __restrict__ waimg,
+                               float* __restrict__ watimg, float* __restrict__ w1kimg) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t tid0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     // w1img: one thread per (gene g, branch, hidden unit n): reads of W1 rows are coalesced over n
@@ -140,14 +141,19 @@ __global__ void tc_pack_kernel(int G, int H, int Hp, int K2, int Hn, const float
         const int n = (int)(i % Hn);
         const int br = (int)((i / Hn) & 1);
         const int g = (int)(i / (2 * (size_t)Hn));
-        const float v = (g < G && n < H) ? W1[(size_t)g * K2 + br * Hp + n] : 0.f;
+        const bool ok = g < G && n < H;
+        const float v = ok ? W1[(size_t)g * K2 + br * Hp + n] : 0.f;
+        const float vt = ok ? WA[(size_t)g * K2 + br * Hp + n] : 0.f;
         float hi, lo;
         split_tf32(v, hi, lo);
         const int kb = g / BK, k = g % BK;
-        float* chunk = w1img + (size_t)kb * 4 * Hn * BK + (size_t)br * 2 * Hn * BK;
+        const size_t co = (size_t)kb * 4 * Hn * BK + (size_t)br * 2 * Hn * BK;
         const int off = phx_tc_tile_off(Hn, n, k);
-        chunk[off] = hi;
-        chunk[Hn * BK + off] = lo;
+        w1img[co + off] = hi;
+        w1img[co + Hn * BK + off] = lo;
+        split_tf32(vt, hi, lo);
+        watimg[co + off] = hi;
+        watimg[co + Hn * BK + off] = lo;
     }
     // waimg: one thread per (gene g, column c of [S|P] in Hn-padded numbering): reads of WA rows coalesced over c
     const int KB2 = 2 * Hn / BK, GT = phx_tc_GT(G);
@@ -156,14 +162,19 @@ __global__ void tc_pack_kernel(int G, int H, int Hp, int K2, int Hn, const float
         const int c = (int)(i % (2 * Hn));
         const int g = (int)(i / (2 * (size_t)Hn));
         const int br = c / Hn, n = c % Hn;
-        const float v = (g < G && n < H) ? WA[(size_t)g * K2 + br * Hp + n] : 0.f;
+        const bool ok = g < G && n < H;
+        const float v = ok ? WA[(size_t)g * K2 + br * Hp + n] : 0.f;
+        const float vk = ok ? W1[(size_t)g * K2 + br * Hp + n] : 0.f;
         float hi, lo;
         split_tf32(v, hi, lo);
         const int gt = g >> 7, r = g & 127, kb = c / BK, k = c % BK;
-        float* chunk = waimg + ((size_t)gt * KB2 + kb) * 2 * 128 * BK;
+        const size_t co = ((size_t)gt * KB2 + kb) * 2 * 128 * BK;
         const int off = phx_tc_tile_off(128, r, k);
-        chunk[off] = hi;
-        chunk[128 * BK + off] = lo;
+        waimg[co + off] = hi;
+        waimg[co + 128 * BK + off] = lo;
+        split_tf32(vk, hi, lo);
+        w1kimg[co + off] = hi;
+        w1kimg[co + 128 * BK + off] = lo;
     }
 }
 
@@ -184,6 +195,8 @@ __device__ __forceinline__ void hill(float y, float& s, float& l, int want_l) {
 // need ~1/2 the ALU work per k-block of the log1p CTAs, so they get K ranges twice as long (phx_tc_branch_plan).
 struct BranchParams {
     int G, B, Bpad, Hn, KB1, chunk, stages, nterms, dbg;
+    int mode;             // 0: A = Hill activation of y (soft-sign / log1p by branch); 1: A = y[b][g] * ascale[g] (cotangent)
+    const float* ascale;  // mode 1: per-gene factor relu(m) (or NULL)
     int mtiles, ks_p, per_p, ks_s, per_s;   // work split: blocks [0, mtiles*ks_p) are prods-branch CTAs, the rest sums
     unsigned a_lbo, a_sbo, b_lbo, b_sbo;    // descriptor fields
     unsigned a_kadv, b_kadv;                // byte advance of the start address per K = 8 MMA (two core matrices)
@@ -234,6 +247,7 @@ __device__ __forceinline__ uint64_t desc_at(uint64_t hi_part, unsigned saddr) {
     return hi_part | (uint64_t)((saddr >> 4) & 0x3fffu);
 }
 
+template <int MODE>
 __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -289,9 +303,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
                     const int g = (kb0 + i + u) * BK + kc * 4 + j;
-                    float t = 0.5f;   // s(0.5) = l(0.5) = 0
-                    if (rok && i + u < nkb && g < p.G && !(p.dbg & 16))
+                    float t = MODE ? 0.f : 0.5f;   // pads contribute zero: s(0.5) = l(0.5) = 0
+                    if (rok && i + u < nkb && g < p.G && !(p.dbg & 16)) {
                         asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
+                        if (MODE && p.ascale) t *= __ldg(p.ascale + g);
+                    }
                     v[u][j] = t;
                 }
             }
@@ -310,7 +326,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float sv, lv;
-                        hill(cur[u][j], sv, lv, br && !(p.dbg & 2));
+                        if (MODE) {
+                            sv = lv = cur[u][j];
+                        } else {
+                            hill(cur[u][j], sv, lv, br && !(p.dbg & 2));
+                        }
                         split_tf32(br ? lv : sv, hi[j], lo[j]);
                     }
                     const long long tw = p.prof ? clock64() : 0;
@@ -473,7 +493,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 
 // ---- K-split reduction + bias + exp + operand image of [S|P] ------------------------------------------------------------
 // one thread per (batch row b in [0, BT*256), 4 consecutive Hn-numbered columns)
-__global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K2, int ks_s, int ks_p, const float* __restrict__ spart,
+__global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K2, int ks_s, int ks_p, int mode, const float* __restrict__ spart,
                                    const float* __restrict__ bias, float* __restrict__ SP, float* __restrict__ spimg) {
     const int BT = phx_tc_BT(B), KB2 = 2 * Hn / BK, C4 = 2 * Hn / 4;
     const size_t total = (size_t)BT * 256 * C4;
@@ -492,8 +512,12 @@ __global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K
             for (int j = 0; j < 4; ++j) {
                 const int n = n0 + j;
                 if (n < H) {
-                    float x = v[j] + bias[br * Hp + n];
-                    v[j] = br ? expf(x) : x;
+                    if (mode == 0) {          // [S|P]: bias, exp on the prods half
+                        float x = v[j] + bias[br * Hp + n];
+                        v[j] = br ? expf(x) : x;
+                    } else if (br) {          // gSP: prods half scaled by Pr (bias = the plain [S|P] of this batch)
+                        v[j] = v[j] * bias[(size_t)b * K2 + Hp + n];
+                    }
                 } else {
                     v[j] = 0.f;
                 }
@@ -516,10 +540,14 @@ struct JointParams {
     int G, B, KB2, GT, BT, nterms, decay;
     unsigned a_lbo, a_sbo, b_lbo, b_sbo;   // descriptor fields
     unsigned a_kadv, b_kadv;               // byte advance of the start address per K = 8 MMA (two core matrices)
+    int kb_lo, kb_hi;     // k-blocks of the images used by this launch
+    int emode;            // epilogue: 0 f = fscale*(decay ? relu(m)*(acc - y) : acc); 1 f = acc; 2 state cotangent:
+                          //   f = (f + acc/(1+s(y))) / (1+|y-.5|)^2 - (decay ? g*relu(m) : 0)   (f holds u on entry)
     float fscale;
-    const float* waimg;
-    const float* spimg;
+    const float* waimg;   // A image: [GT][KB2][hi|lo][128 x 16]
+    const float* spimg;   // B image: [BT][KB2][hi|lo][256 x 16]
     const float* y;       // [B][G]
+    const float* g;       // [B][G] cotangent (emode 2 with decay)
     const float* relum;   // [G]
     float* f;             // [B][G]
 };
@@ -528,6 +556,7 @@ constexpr int K2_STAGES = 4;
 constexpr unsigned K2_A_TILE = 128 * BK * 4, K2_B_TILE = 256 * BK * 4;
 constexpr unsigned K2_STAGE_BYTES = 2 * K2_A_TILE + 2 * K2_B_TILE;   // 48 KB
 
+template <int EMODE>
 __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -561,7 +590,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             int it = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
                 const int gt = t / p.BT, bt = t % p.BT;
-                for (int kb = 0; kb < p.KB2; ++kb, ++it) {
+                for (int kb = p.kb_lo; kb < p.kb_hi; ++kb, ++it) {
                     const int s = it % S;
                     const unsigned ph = (unsigned)(it / S) & 1u;
                     mbar_wait(empty0 + 8 * s, ph ^ 1u);
@@ -583,7 +612,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
                 mbar_wait(tempty0 + 8 * buf, tph ^ 1u);   // epilogue has drained this accumulator
                 tc_fence_after();
                 const unsigned d = tmem + (unsigned)(buf * 256);
-                for (int kb = 0; kb < p.KB2; ++kb, ++it) {
+                for (int kb = p.kb_lo; kb < p.kb_hi; ++kb, ++it) {
                     const int s = it % S;
                     const unsigned ph = (unsigned)(it / S) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
@@ -595,7 +624,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
                         const uint64_t a_lo = smem_desc(a_base + K2_A_TILE + k8 * p.a_kadv, p.a_lbo, p.a_sbo);
                         const uint64_t b_hi = smem_desc(b_base + k8 * p.b_kadv, p.b_lbo, p.b_sbo);
                         const uint64_t b_lo = smem_desc(b_base + K2_B_TILE + k8 * p.b_kadv, p.b_lbo, p.b_sbo);
-                        const unsigned acc = (kb > 0 || k8 > 0) ? 1u : 0u;
+                        const unsigned acc = (kb > p.kb_lo || k8 > 0) ? 1u : 0u;
                         if (p.nterms == 3) {
                             mma_tf32(d, a_lo, b_hi, idesc, acc);
                             mma_tf32(d, a_hi, b_lo, idesc, 1u);
@@ -624,28 +653,49 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             const float rm = (gok && p.decay) ? p.relum[g] : 1.f;
             const int b0 = bt * 256 + half * 128;
             const int ncol = min(128, p.B - b0);   // valid batch rows of this warp's half (may be <= 0)
-            float yv[16], yn[16];
-            auto loady = [&](int c0, float (&dst)[16]) {
+            const bool need_y = EMODE == 2 || (EMODE == 0 && p.decay);
+            constexpr bool need_u = EMODE == 2;
+            const bool need_g = EMODE == 2 && p.decay;
+            float yv[16], yn[16], uv[16], un[16], gv[16], gn[16];
+            auto loadin = [&](int c0, float (&dy)[16], float (&du)[16], float (&dg)[16]) {
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
-                    const int row = b0 + c0 + jj;
-                    dst[jj] = (p.decay && gok && c0 + jj < ncol) ? __ldg(p.y + (size_t)row * p.G + g) : 0.f;
+                    const bool ok = gok && c0 + jj < ncol;
+                    const size_t idx = (size_t)(b0 + c0 + jj) * p.G + g;
+                    dy[jj] = (need_y && ok) ? __ldg(p.y + idx) : 0.f;
+                    du[jj] = (need_u && ok) ? p.f[idx] : 0.f;
+                    dg[jj] = (need_g && ok) ? __ldg(p.g + idx) : 0.f;
                 }
             };
-            loady(0, yn);
+            loadin(0, yn, un, gn);
             mbar_wait(tfull0 + 8 * buf, tph);
             tc_fence_after();
             for (int c0 = 0; c0 < ncol; c0 += 16) {
 #pragma unroll
-                for (int jj = 0; jj < 16; ++jj) yv[jj] = yn[jj];
-                if (c0 + 16 < ncol) loady(c0 + 16, yn);
+                for (int jj = 0; jj < 16; ++jj) {
+                    yv[jj] = yn[jj];
+                    uv[jj] = un[jj];
+                    gv[jj] = gn[jj];
+                }
+                if (c0 + 16 < ncol) loadin(c0 + 16, yn, un, gn);
                 float v[16];
                 tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * 256 + half * 128 + c0), v);
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     if (gok && c0 + jj < ncol) {
-                        const float r = p.decay ? rm * (v[jj] - yv[jj]) : v[jj];
-                        p.f[(size_t)(b0 + c0 + jj) * p.G + g] = p.fscale * r;
+                        float r;
+                        if (EMODE == 0) {
+                            r = p.fscale * (p.decay ? rm * (v[jj] - yv[jj]) : v[jj]);
+                        } else if (EMODE == 1) {
+                            r = v[jj];
+                        } else {
+                            const float z = yv[jj] - 0.5f;
+                            const float den = 1.0f + fabsf(z);
+                            const float sv = z / den;
+                            r = (uv[jj] + v[jj] / (1.0f + sv)) / (den * den);
+                            if (p.decay) r = r - gv[jj] * rm;
+                        }
+                        p.f[(size_t)(b0 + c0 + jj) * p.G + g] = r;
                     }
                 }
             }
@@ -689,7 +739,8 @@ int phx_tc_pack_launch(int G, int H, const PhxPacked& w, cudaStream_t st) {
     const int Hp = phx_Hp(H), Hn = phx_tc_Hn(H);
     tc_pack_kernel<<<PHX_TC_SMS * 8, 256, 0, st>>>(G, H, Hp, 2 * Hp, Hn, reinterpret_cast<const float*>(w.W1),
                                                     reinterpret_cast<const float*>(w.WA), const_cast<float*>(w.w1img),
-                                                    const_cast<float*>(w.waimg));
+                                                    const_cast<float*>(w.waimg), const_cast<float*>(w.watimg),
+                                                    const_cast<float*>(w.w1kimg));
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         phx_set_error("tc_pack launch: %s", cudaGetErrorString(e));
@@ -698,20 +749,51 @@ int phx_tc_pack_launch(int G, int H, const PhxPacked& w, cudaStream_t st) {
     return PHX_OK;
 }
 
-// SP (plain [B][K2], bias/exp applied) and f; tcws = scratch of phx_tc_scratch_floats(G, H, B) floats
-int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay,
-                              float fscale, float* SP, float* tcws, cudaStream_t st) {
-    const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H);
-    const int Bpad = phx_round_up(B, 128);
-    const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
-    float* base = reinterpret_cast<float*>(((uintptr_t)tcws + 127) & ~(uintptr_t)127);
-    float* spart = base;
-    float* spimg = spart + (size_t)pl.slots * Bpad * 2 * Hn;
-    const int dbg = debug_flags();
-    const int nterms = (w.tc == 1) ? 1 : 3;
+namespace {
 
+struct TcScratch {
+    float* spart;   // partial-sum slots of the branch-type contraction
+    float* spimg;   // operand image of [S|P]
+    float* gsimg;   // operand image of gSP
+};
+TcScratch carve(int G, int H, int B, float* tcws) {
+    const int Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
+    const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
+    TcScratch sc;
+    sc.spart = reinterpret_cast<float*>(((uintptr_t)tcws + 127) & ~(uintptr_t)127);
+    sc.spimg = sc.spart + (size_t)pl.slots * Bpad * 2 * Hn;
+    sc.gsimg = sc.spimg + phx_tc_spimg_floats(H, B);
+    return sc;
+}
+
+void set_attrs() {
+    static bool done = false;
+    if (done) return;
+    cudaFuncSetAttribute(tc_branch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_joint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_joint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_joint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    done = true;
+}
+
+// partial[B x 2Hn] = A(src) x image^T, then the finishing pass (mode 0: bias/exp -> [S|P]; mode 1: * Pr -> gSP)
+int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, const float* ascale, const float* bimg,
+                  const float* fin_aux, float* out_plain, float* out_img, float* spart, cudaStream_t st) {
+    const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
+    PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
+    if (mode == 1) {   // both halves cost the same: equal K ranges (never more slots than the RHS plan reserved)
+        const int chunk = phx_tc_chunk(), nch = (phx_tc_KB1(G) + chunk - 1) / chunk;
+        int ks = (pl.ks_p + pl.ks_s) / 2;
+        if (ks < 1) ks = 1;
+        const int per = (nch + ks - 1) / ks * chunk;
+        pl.per_p = pl.per_s = per;
+        pl.ks_p = pl.ks_s = (phx_tc_KB1(G) + per - 1) / per;
+    }
+    const int dbg = debug_flags();
     BranchParams bp;
-    bp.G = G; bp.B = B; bp.Bpad = Bpad; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(G); bp.chunk = phx_tc_chunk(); bp.nterms = nterms; bp.dbg = dbg;
+    bp.G = G; bp.B = B; bp.Bpad = Bpad; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(G); bp.chunk = phx_tc_chunk();
+    bp.nterms = nterms; bp.dbg = dbg; bp.mode = mode; bp.ascale = ascale;
     bp.mtiles = pl.mtiles; bp.ks_p = pl.ks_p; bp.per_p = pl.per_p; bp.ks_s = pl.ks_s; bp.per_s = pl.per_s;
     bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hn / 8) * 128; bp.b_sbo = 128;
     bp.a_kadv = 2 * bp.a_lbo; bp.b_kadv = 2 * bp.b_lbo;
@@ -719,7 +801,7 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
         unsigned t = bp.a_lbo; bp.a_lbo = bp.a_sbo; bp.a_sbo = t;
         t = bp.b_lbo; bp.b_lbo = bp.b_sbo; bp.b_sbo = t;
     }
-    bp.y = y; bp.w1img = w.w1img; bp.spart = spart;
+    bp.y = src; bp.w1img = bimg; bp.spart = spart;
     bp.prof = phx_tc_prof_buffer();
     const size_t stage1 = K1_A_BYTES + (size_t)2 * Hn * BK * 4;
     int S1 = (int)((PHX_SMEM_LIMIT - 256) / stage1);
@@ -729,47 +811,83 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
         if (v >= 1 && v < S1) S1 = v;
     }
     if (S1 < 1) {
-        phx_set_error("tc branch kernel: stage of %zu bytes does not fit twice", stage1);
+        phx_set_error("tc branch kernel: stage of %zu bytes does not fit", stage1);
         return PHX_ERR_UNSUPPORTED;
     }
     bp.stages = S1;
+    set_attrs();
+    const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
     const size_t smem1 = (size_t)S1 * stage1 + 256;
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaFuncSetAttribute(tc_branch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-        cudaFuncSetAttribute(tc_joint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-        attr_done = true;
-    }
-    tc_branch_kernel<<<pl.mtiles * (pl.ks_p + pl.ks_s), K1_THREADS, smem1, st>>>(bp);
+    if (mode == 0) tc_branch_kernel<0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+    else tc_branch_kernel<1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+    const size_t total = (size_t)phx_tc_BT(B) * 256 * (2 * Hn / 4);
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > PHX_TC_SMS * 16) blocks = PHX_TC_SMS * 16;
+    tc_spfinish_kernel<<<blocks, 256, 0, st>>>(B, Bpad, H, Hp, Hn, K2, pl.ks_s, pl.ks_p, mode, spart, fin_aux, out_plain,
+                                               out_img);
+    return PHX_OK;
+}
 
-    const int BT = phx_tc_BT(B);
-    {
-        const size_t total = (size_t)BT * 256 * (2 * Hn / 4);
-        int blocks = (int)((total + 255) / 256);
-        if (blocks > PHX_TC_SMS * 16) blocks = PHX_TC_SMS * 16;
-        tc_spfinish_kernel<<<blocks, 256, 0, st>>>(B, Bpad, H, Hp, Hn, K2, pl.ks_s, pl.ks_p, spart, w.bias, SP, spimg);
+// out^T tiles = Aimg[genes x k-blocks kb_lo..kb_hi) x Bimg[batch rows]^T with the epilogue `emode`
+void launch_joint(int G, int H, int B, int nterms, const float* aimg, const float* bimg, int kb_lo, int kb_hi, int emode,
+                  int decay, float fscale, const float* y, const float* g, const float* relum, float* out,
+                  cudaStream_t st) {
+    const int dbg = debug_flags();
+    JointParams jp;
+    jp.G = G; jp.B = B; jp.KB2 = phx_tc_KB2(H); jp.GT = phx_tc_GT(G); jp.BT = phx_tc_BT(B); jp.nterms = nterms;
+    jp.decay = decay; jp.fscale = fscale; jp.kb_lo = kb_lo; jp.kb_hi = kb_hi; jp.emode = emode;
+    jp.a_lbo = 16 * 128; jp.a_sbo = 128; jp.b_lbo = 32 * 128; jp.b_sbo = 128;
+    jp.a_kadv = 2 * jp.a_lbo; jp.b_kadv = 2 * jp.b_lbo;
+    if (dbg & 1) {
+        unsigned t = jp.a_lbo; jp.a_lbo = jp.a_sbo; jp.a_sbo = t;
+        t = jp.b_lbo; jp.b_lbo = jp.b_sbo; jp.b_sbo = t;
     }
-    if (f) {
-        JointParams jp;
-        jp.G = G; jp.B = B; jp.KB2 = phx_tc_KB2(H); jp.GT = phx_tc_GT(G); jp.BT = BT; jp.nterms = nterms;
-        jp.decay = decay; jp.fscale = fscale;
-        jp.a_lbo = 16 * 128; jp.a_sbo = 128; jp.b_lbo = 32 * 128; jp.b_sbo = 128;
-        jp.a_kadv = 2 * jp.a_lbo; jp.b_kadv = 2 * jp.b_lbo;
-        if (dbg & 1) {
-            unsigned t = jp.a_lbo; jp.a_lbo = jp.a_sbo; jp.a_sbo = t;
-            t = jp.b_lbo; jp.b_lbo = jp.b_sbo; jp.b_sbo = t;
-        }
-        jp.waimg = w.waimg; jp.spimg = spimg; jp.y = y; jp.relum = w.relum; jp.f = f;
-        const int ntiles = jp.GT * jp.BT;
-        const int grid = ntiles < PHX_TC_SMS ? ntiles : PHX_TC_SMS;
-        tc_joint_kernel<<<grid, K2_THREADS, (size_t)K2_STAGES * K2_STAGE_BYTES + 256, st>>>(jp);
-    }
+    jp.waimg = aimg; jp.spimg = bimg; jp.y = y; jp.g = g; jp.relum = relum; jp.f = out;
+    const int ntiles = jp.GT * jp.BT;
+    const int grid = ntiles < PHX_TC_SMS ? ntiles : PHX_TC_SMS;
+    set_attrs();
+    const size_t smem2 = (size_t)K2_STAGES * K2_STAGE_BYTES + 256;
+    if (emode == 0) tc_joint_kernel<0><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else if (emode == 1) tc_joint_kernel<1><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else tc_joint_kernel<2><<<grid, K2_THREADS, smem2, st>>>(jp);
+}
+
+int check_launch(const char* what) {
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        phx_set_error("tc rhs_forward launch: %s", cudaGetErrorString(e));
+        phx_set_error("%s launch: %s", what, cudaGetErrorString(e));
         return PHX_ERR_CUDA;
     }
     return PHX_OK;
+}
+
+}  // namespace
+
+// SP (plain [B][K2], bias/exp applied) and, if f != 0, f; tcws = scratch of phx_tc_scratch_floats(G, H, B) floats
+int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay,
+                              float fscale, float* SP, float* tcws, cudaStream_t st) {
+    const TcScratch sc = carve(G, H, B, tcws);
+    const int nterms = (w.tc == 1) ? 1 : 3;
+    int rc = launch_branch(0, G, H, B, nterms, y, nullptr, w.w1img, w.bias, SP, sc.spimg, sc.spart, st);
+    if (rc != PHX_OK) return rc;
+    if (f) launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 0, decay, fscale, y, nullptr, w.relum, f, st);
+    return check_launch("tc rhs_forward");
+}
+
+int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
+                            float* ybar, const float* SP, float* GS, float* J, float* tcws, cudaStream_t st) {
+    const TcScratch sc = carve(G, H, B, tcws);
+    const int nterms = (w.tc == 1) ? 1 : 3, KB2 = phx_tc_KB2(H);
+    // gSP = (g relu(m)) WA over the genes, prods half scaled by Pr  (exp / Linear backward, odenet.py:86-89)
+    int rc = launch_branch(1, G, H, B, nterms, g, decay ? w.relum : nullptr, w.watimg, SP, GS, sc.gsimg, sc.spart, st);
+    if (rc != PHX_OK) return rc;
+    if (ybar) {
+        // u = gS Ws (k-blocks of the sums half), then v = gP Wp and the soft-sign / log1p backward in the epilogue
+        launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, 0, KB2 / 2, 1, 0, 1.f, nullptr, nullptr, w.relum, ybar, st);
+        launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, KB2 / 2, KB2, 2, decay, 1.f, y, g, w.relum, ybar, st);
+    }
+    if (J) launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, KB2, 0, 0, 1.f, y, nullptr, w.relum, J, st);
+    return check_launch("tc vjp_state");
 }
 
 extern "C" void phx_tc_prof_dump(void) {

@@ -17,6 +17,9 @@
 //     w1img [KB1][branch 2][hi|lo][Hn x 16]   branch contraction S|P = act(y) W1      (N = Hn hidden units, K = genes)
 //     waimg [GT][KB2][hi|lo][128 x 16]        joint contraction J = [S|P] WA^T         (M = genes, K = 2*Hn)
 //     spimg [BT][KB2][hi|lo][256 x 16]        [S|P] rows, written by the K-split reduction kernel (N = batch rows)
+//     watimg = w1img layout built from WA     cotangent contraction gSP = gJ WA       (N = Hn columns of a half, K = genes)
+//     w1kimg = waimg layout built from W1     state cotangent u|v = gSP W1^T          (M = genes, K = Hn of one half)
+//     gsimg  = spimg layout holding gSP
 // Hn = round_up(H, 16) (UMMA N granularity at M = 128); pads are zero in every image.
 #pragma once
 #include <stdlib.h>
@@ -89,5 +92,5 @@ static inline PhxTcBranchPlan phx_tc_branch_plan(int G, int B) {
 static inline size_t phx_tc_scratch_floats(int G, int H, int B) {
     const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
     const size_t Bpad = (size_t)phx_round_up(B, 128);
-    return (size_t)pl.slots * Bpad * 2 * phx_tc_Hn(H) + phx_tc_spimg_floats(H, B) + 64;
+    return (size_t)pl.slots * Bpad * 2 * phx_tc_Hn(H) + 2 * phx_tc_spimg_floats(H, B) + 64;
 }

@@ -32,7 +32,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     G, H = 350, 40
     base = (2 * G * 80 + 80 + 2 * 352 + 31) // 32 * 32          # W1, WA, bias, relu(m), mask; 128-byte rounded
     Hn, KB1, GT = 48, (G + 15) // 16, (G + 127) // 128               # tensor-core operand images (phx_tc.cuh)
-    images = KB1 * 4 * Hn * 16 + GT * (2 * Hn // 16) * 2 * 128 * 16
+    images = 2 * (KB1 * 4 * Hn * 16 + GT * (2 * Hn // 16) * 2 * 128 * 16)   # forward pair + cotangent pair
     assert lib.phx_packed_bytes(G, H) == 4 * (base + images)
     assert lib.phx_tc_min_rows() == 128
     assert lib.phx_rhs_workspace_bytes(G, H, 256) > lib.phx_rhs_workspace_bytes(G, H, 127) * 2

@@ -39,6 +39,7 @@ def main():
                                                     "20000,200,4096"])
     ap.add_argument("--reps", type=int, default=5)
     ap.add_argument("--modes", nargs="*", default=["fp32", "3xtf32", "tf32"])
+    ap.add_argument("--vjp", action="store_true", help="also check / time forward + backward (state and parameter cotangents)")
     a = ap.parse_args()
     for sh in a.shapes:
         G, H, B = (int(v) for v in sh.split(","))
@@ -52,6 +53,27 @@ def main():
         with torch.no_grad():
             r = ref64(net, y)
         flops = 8.0 * B * G * H
+        if a.vjp:
+            gcot = torch.randn(B, G, device="cuda")
+            y64 = y.double().requires_grad_(True)
+            ps = [p_ for p_ in net.parameters()]
+            for p_ in ps:
+                p_.grad = None
+
+            class N64:  # float64 view of the parameters with autograd
+                pass
+            n64 = N64()
+            leaves = [p_.detach().double().requires_grad_(True) for p_ in ps]
+            m64, Wp64, bp64, Ws64, bs64, Wa64 = leaves
+            z = y64 - 0.5
+            s_ = z / (1 + z.abs())
+            l_ = torch.log1p(s_)
+            J64 = torch.cat([s_ @ Ws64.t() + bs64, torch.exp(l_ @ Wp64.t() + bp64)], -1) @ Wa64.t()
+            r64 = torch.relu(m64) * (J64 - y64)
+            r64.backward(gcot.double())
+            ref_ybar = y64.grad
+            ref_grads = [t.grad for t in leaves]
+            del J64, r64, z, s_, l_
         for mode in a.modes:
             pb.set_precision(mode)
             with torch.no_grad():
@@ -66,8 +88,28 @@ def main():
                     ev[i + 1].record()
                 torch.cuda.synchronize()
                 ms = min(ev[i].elapsed_time(ev[i + 1]) for i in range(a.reps))
-            print(json.dumps({"G": G, "H": H, "B": B, "mode": mode, "rel_l2": err, "max_abs": mx, "ms": ms,
-                              "fp32_equiv_tflops": flops / ms / 1e9}), flush=True)
+            rec = {"G": G, "H": H, "B": B, "mode": mode, "rel_l2": err, "max_abs": mx, "ms": ms,
+                   "fp32_equiv_tflops": flops / ms / 1e9}
+            if a.vjp:
+                def fb():
+                    for p_ in net.parameters():
+                        p_.grad = None
+                    yg = y.clone().requires_grad_(True)
+                    net(None, yg).backward(gcot)
+                    return yg
+                yg = fb()
+                torch.cuda.synchronize()
+                rel = lambda x, r_: float((x.double() - r_).norm() / r_.norm())
+                rec["ybar_rel_l2"] = rel(yg.grad, ref_ybar)
+                rec["grad_rel_l2"] = [rel(p_.grad, r_) for p_, r_ in zip(net.parameters(), ref_grads)]
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(a.reps):
+                    fb()
+                e1.record()
+                torch.cuda.synchronize()
+                rec["fwd_bwd_ms"] = e0.elapsed_time(e1) / a.reps
+            print(json.dumps(rec), flush=True)
             if os.environ.get("PHX_TC_PROF"):
                 from phoenix_b200 import _lib
                 _lib.load().phx_tc_prof_dump()
