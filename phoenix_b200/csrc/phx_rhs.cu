@@ -332,23 +332,29 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
     }
     if (grads) {
         const PhxGradOff off = phx_grad_offsets(G, H);
-        {   // Wa_bar[g][k] = sum_b gJ[b][g] SP[b][k]
-            LoadGJT la{g, w.relum, G, decay};
-            LoadRowMajorB lb{SP, K2, 0};
-            EpiGradWa ep{grads + off.Wa, H, Hp, accumulate};
-            sgemm(G, K2, B, la, lb, ep, st);
-        }
-        {   // Ws_bar[h][g] = sum_b GS[b][h] s[b][g]
-            LoadTransA la{GS, K2, 0};
-            LoadActB lb{y, G, 0};
-            EpiGrad ep{grads + off.Ws, G, accumulate};
-            sgemm(H, G, B, la, lb, ep, st);
-        }
-        {   // Wp_bar[h][g] = sum_b GS[b][Hp+h] l[b][g]
-            LoadTransA la{GS, K2, Hp};
-            LoadActB lb{y, G, 1};
-            EpiGrad ep{grads + off.Wp, G, accumulate};
-            sgemm(H, G, B, la, lb, ep, st);
+        if (tc) {
+            int rc = phx_tc_vjp_params_launch(G, H, B, w, y, g, decay, grads, accumulate,
+                                              ws + rhs_base_floats(G, H, B), st);
+            if (rc != PHX_OK) return rc;
+        } else {
+            {   // Wa_bar[g][k] = sum_b gJ[b][g] SP[b][k]
+                LoadGJT la{g, w.relum, G, decay};
+                LoadRowMajorB lb{SP, K2, 0};
+                EpiGradWa ep{grads + off.Wa, H, Hp, accumulate};
+                sgemm(G, K2, B, la, lb, ep, st);
+            }
+            {   // Ws_bar[h][g] = sum_b GS[b][h] s[b][g]
+                LoadTransA la{GS, K2, 0};
+                LoadActB lb{y, G, 0};
+                EpiGrad ep{grads + off.Ws, G, accumulate};
+                sgemm(H, G, B, la, lb, ep, st);
+            }
+            {   // Wp_bar[h][g] = sum_b GS[b][Hp+h] l[b][g]
+                LoadTransA la{GS, K2, Hp};
+                LoadActB lb{y, G, 1};
+                EpiGrad ep{grads + off.Wp, G, accumulate};
+                sgemm(H, G, B, la, lb, ep, st);
+            }
         }
         colsum_bias_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(GS, B, K2, Hp, H, grads + off.bs, grads + off.bp,
                                                                 accumulate);

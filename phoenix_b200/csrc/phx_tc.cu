@@ -194,7 +194,8 @@ __device__ __forceinline__ void hill(float y, float& s, float& l, int want_l) {
 // accumulator (Hn columns) + running sum (Hn columns) fit the 512 columns for every Hn <= 256.  The soft-sign CTAs
 // need ~1/2 the ALU work per k-block of the log1p CTAs, so they get K ranges twice as long (phx_tc_branch_plan).
 struct BranchParams {
-    int G, B, Bpad, Hn, KB1, chunk, stages, nterms, dbg;
+    int G, B, Bpad, Hn, KB1, chunk, stages, nterms, dbg;   // G = valid k, B = valid rows, Bpad = mtiles * 128
+    int ld;               // leading dimension of the source matrix
     int mode;             // 0: A = Hill activation of y (soft-sign / log1p by branch); 1: A = y[b][g] * ascale[g] (cotangent)
     const float* ascale;  // mode 1: per-gene factor relu(m) (or NULL)
     int mtiles, ks_p, per_p, ks_s, per_s;   // work split: blocks [0, mtiles*ks_p) are prods-branch CTAs, the rest sums
@@ -247,7 +248,10 @@ __device__ __forceinline__ uint64_t desc_at(uint64_t hi_part, unsigned saddr) {
     return hi_part | (uint64_t)((saddr >> 4) & 0x3fffu);
 }
 
-template <int MODE>
+// TRANS = 0: A(row, k) = src[row][k]  (rows = batch, k = genes).  TRANS = 1: A(row, k) = src[k][row] (rows = genes,
+// k = batch rows: the K = B parameter-cotangent contractions); lanes then run along the genes, so every load is a
+// coalesced 128-byte row segment and the transpose happens in registers (4 batch rows -> one 16-byte k chunk).
+template <int MODE, int TRANS>
 __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -288,9 +292,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 
     if (warp < K1_PWARPS) {
         // ---- producers: Hill activation of this CTA's 128 x 16 slab of y, hi/lo split, core-matrix layout ----
-        const int rl = warp * 8 + (lane & 7), kc = lane >> 3;   // row rl, k-chunk kc (4 floats)
+        const int rl = TRANS ? (warp & 3) * 32 + lane : warp * 8 + (lane & 7);   // row rl of the tile
+        const int kc = TRANS ? warp >> 2 : lane >> 3;                           // k-chunk kc (4 floats)
         const int row = m0 + rl;
-        const float* src = p.y + (size_t)row * p.G;
+        const float* src = TRANS ? p.y + row : p.y + (size_t)row * p.ld;
         const bool rok = row < p.B;
         const unsigned a_off = (unsigned)(((kc * 16 + (rl >> 3)) * 8 + (rl & 7)) * 16);
         // y is read in super-blocks of K1_PF k-blocks: all loads of the NEXT super-block (K1_PF x 64 contiguous bytes
@@ -305,8 +310,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     const int g = (kb0 + i + u) * BK + kc * 4 + j;
                     float t = MODE ? 0.f : 0.5f;   // pads contribute zero: s(0.5) = l(0.5) = 0
                     if (rok && i + u < nkb && g < p.G && !(p.dbg & 16)) {
-                        asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
-                        if (MODE && p.ascale) t *= __ldg(p.ascale + g);
+                        if (TRANS) t = __ldg(src + (size_t)g * p.ld);
+                        else asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
+                        if (MODE && p.ascale) t *= __ldg(p.ascale + (TRANS ? row : g));
                     }
                     v[u][j] = t;
                 }
@@ -494,7 +500,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 // ---- K-split reduction + bias + exp + operand image of [S|P] ------------------------------------------------------------
 // one thread per (batch row b in [0, BT*256), 4 consecutive Hn-numbered columns)
 __global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K2, int ks_s, int ks_p, int mode, const float* __restrict__ spart,
-                                   const float* __restrict__ bias, float* __restrict__ SP, float* __restrict__ spimg) {
+                                   const float* __restrict__ bias, float* __restrict__ SP, float* __restrict__ spimg,
+                                   float* __restrict__ timg) {
     const int BT = phx_tc_BT(B), KB2 = 2 * Hn / BK, C4 = 2 * Hn / 4;
     const size_t total = (size_t)BT * 256 * C4;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -532,6 +539,41 @@ __global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K
         const int off = phx_tc_tile_off(256, r, k);
         *reinterpret_cast<float4*>(chunk + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
         *reinterpret_cast<float4*>(chunk + 256 * BK + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        if (timg && b < ((B + BK - 1) / BK) * BK) {
+            // the same values as the B operand of the K = batch contractions: [b / 16][branch][hi|lo][Hn x 16]
+            float* tch = timg + ((size_t)(b / BK) * 4 + 2 * br) * Hn * BK;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = phx_tc_tile_off(Hn, n0 + j, b % BK);
+                tch[o] = hi[j];
+                tch[Hn * BK + o] = lo[j];
+            }
+        }
+    }
+}
+
+// parameter cotangents from the K-split partial sums part[slot][Gpad][2*Hn] of the K = batch contractions
+//   which = 0: Ws_bar[n][g] / Wp_bar[n][g]  <- part[.][g][br*Hn + n]      which = 1: Wa_bar[g][br*H + n]
+__global__ void tc_gradfinish_kernel(int which, int G, int Gpad, int H, int Hn, int ks_s, int ks_p,
+                                     const float* __restrict__ part, float* __restrict__ d0, float* __restrict__ d1,
+                                     int accumulate) {
+    const size_t total = (size_t)G * 2 * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        int g, br, n;
+        if (which == 0) {   // g fastest: coalesced stores into [H][G]
+            g = (int)(i % G);
+            const int c = (int)(i / G);
+            br = c / H; n = c % H;
+        } else {            // column fastest: coalesced loads and stores of [G][2H]
+            const int c = (int)(i % (2 * H));
+            g = (int)(i / (2 * H));
+            br = c / H; n = c % H;
+        }
+        const int nslots = br ? ks_p : ks_s;
+        float v = 0.f;
+        for (int s = 0; s < nslots; ++s) v += part[((size_t)s * Gpad + g) * (2 * Hn) + br * Hn + n];
+        float* dst = which == 0 ? (br ? d1 : d0) + (size_t)n * G + g : d0 + (size_t)g * 2 * H + br * H + n;
+        *dst = accumulate ? *dst + v : v;
     }
 }
 
@@ -752,9 +794,12 @@ int phx_tc_pack_launch(int G, int H, const PhxPacked& w, cudaStream_t st) {
 namespace {
 
 struct TcScratch {
-    float* spart;   // partial-sum slots of the branch-type contraction
-    float* spimg;   // operand image of [S|P]
-    float* gsimg;   // operand image of gSP
+    float* spart;    // partial-sum slots of the branch-type contraction
+    float* spimg;    // operand image of [S|P]
+    float* gsimg;    // operand image of gSP
+    float* sptimg;   // [S|P] as the B operand of the K = batch contractions
+    float* gstimg;   // gSP likewise
+    float* gslots;   // partial-sum slots of the K = batch contractions
 };
 TcScratch carve(int G, int H, int B, float* tcws) {
     const int Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
@@ -763,14 +808,19 @@ TcScratch carve(int G, int H, int B, float* tcws) {
     sc.spart = reinterpret_cast<float*>(((uintptr_t)tcws + 127) & ~(uintptr_t)127);
     sc.spimg = sc.spart + (size_t)pl.slots * Bpad * 2 * Hn;
     sc.gsimg = sc.spimg + phx_tc_spimg_floats(H, B);
+    sc.sptimg = sc.gsimg + phx_tc_spimg_floats(H, B);
+    sc.gstimg = sc.sptimg + phx_tc_timg_floats(H, B);
+    sc.gslots = sc.gstimg + phx_tc_timg_floats(H, B);
     return sc;
 }
 
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(tc_branch_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
@@ -778,21 +828,26 @@ void set_attrs() {
 }
 
 // partial[B x 2Hn] = A(src) x image^T, then the finishing pass (mode 0: bias/exp -> [S|P]; mode 1: * Pr -> gSP)
-int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, const float* ascale, const float* bimg,
-                  const float* fin_aux, float* out_plain, float* out_img, float* spart, cudaStream_t st) {
-    const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
-    PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
-    if (mode == 1) {   // both halves cost the same: equal K ranges (never more slots than the RHS plan reserved)
-        const int chunk = phx_tc_chunk(), nch = (phx_tc_KB1(G) + chunk - 1) / chunk;
+// the branch-type contraction itself: part[slot][Mpad][2*Hn] = A(src) x image^T.  trans = 0: M = batch rows, K = genes;
+// trans = 1: M = genes, K = batch rows.  Returns the plan used (slot counts per half) through *plan.
+int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, const float* src, const float* ascale,
+                      const float* bimg, float* spart, PhxTcBranchPlan* plan, cudaStream_t st) {
+    const int Hn = phx_tc_Hn(H);
+    const int Kdim = trans ? B : G, Mdim = trans ? G : B;
+    PhxTcBranchPlan pl = phx_tc_branch_plan(Kdim, Mdim);
+    if (mode == 1) {   // both halves cost the same: equal K ranges (never more slots than the plan reserved)
+        const int chunk = phx_tc_chunk(), nch = (phx_tc_KB1(Kdim) + chunk - 1) / chunk;
         int ks = (pl.ks_p + pl.ks_s) / 2;
         if (ks < 1) ks = 1;
         const int per = (nch + ks - 1) / ks * chunk;
         pl.per_p = pl.per_s = per;
-        pl.ks_p = pl.ks_s = (phx_tc_KB1(G) + per - 1) / per;
+        pl.ks_p = pl.ks_s = (phx_tc_KB1(Kdim) + per - 1) / per;
     }
+    *plan = pl;
     const int dbg = debug_flags();
     BranchParams bp;
-    bp.G = G; bp.B = B; bp.Bpad = Bpad; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(G); bp.chunk = phx_tc_chunk();
+    bp.G = Kdim; bp.B = Mdim; bp.Bpad = pl.mtiles * 128; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(Kdim); bp.chunk = phx_tc_chunk();
+    bp.ld = G;
     bp.nterms = nterms; bp.dbg = dbg; bp.mode = mode; bp.ascale = ascale;
     bp.mtiles = pl.mtiles; bp.ks_p = pl.ks_p; bp.per_p = pl.per_p; bp.ks_s = pl.ks_s; bp.per_s = pl.per_s;
     bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hn / 8) * 128; bp.b_sbo = 128;
@@ -818,13 +873,29 @@ int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, c
     set_attrs();
     const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
     const size_t smem1 = (size_t)S1 * stage1 + 256;
-    if (mode == 0) tc_branch_kernel<0><<<grid1, K1_THREADS, smem1, st>>>(bp);
-    else tc_branch_kernel<1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+    if (!trans) {
+        if (mode == 0) tc_branch_kernel<0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        else tc_branch_kernel<1, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+    } else {
+        if (mode == 0) tc_branch_kernel<0, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        else tc_branch_kernel<1, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+    }
+    return PHX_OK;
+}
+
+// partial[B x 2Hn] = A(src) x image^T, then the finishing pass (mode 0: bias/exp -> [S|P]; mode 1: * Pr -> gSP)
+int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, const float* ascale, const float* bimg,
+                  const float* fin_aux, float* out_plain, float* out_img, float* out_timg, float* spart,
+                  cudaStream_t st) {
+    const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
+    PhxTcBranchPlan pl;
+    int rc = launch_branch_mma(mode, 0, G, H, B, nterms, src, ascale, bimg, spart, &pl, st);
+    if (rc != PHX_OK) return rc;
     const size_t total = (size_t)phx_tc_BT(B) * 256 * (2 * Hn / 4);
     int blocks = (int)((total + 255) / 256);
     if (blocks > PHX_TC_SMS * 16) blocks = PHX_TC_SMS * 16;
     tc_spfinish_kernel<<<blocks, 256, 0, st>>>(B, Bpad, H, Hp, Hn, K2, pl.ks_s, pl.ks_p, mode, spart, fin_aux, out_plain,
-                                               out_img);
+                                               out_img, out_timg);
     return PHX_OK;
 }
 
@@ -868,7 +939,7 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
                               float fscale, float* SP, float* tcws, cudaStream_t st) {
     const TcScratch sc = carve(G, H, B, tcws);
     const int nterms = (w.tc == 1) ? 1 : 3;
-    int rc = launch_branch(0, G, H, B, nterms, y, nullptr, w.w1img, w.bias, SP, sc.spimg, sc.spart, st);
+    int rc = launch_branch(0, G, H, B, nterms, y, nullptr, w.w1img, w.bias, SP, sc.spimg, sc.sptimg, sc.spart, st);
     if (rc != PHX_OK) return rc;
     if (f) launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 0, decay, fscale, y, nullptr, w.relum, f, st);
     return check_launch("tc rhs_forward");
@@ -879,7 +950,8 @@ int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float
     const TcScratch sc = carve(G, H, B, tcws);
     const int nterms = (w.tc == 1) ? 1 : 3, KB2 = phx_tc_KB2(H);
     // gSP = (g relu(m)) WA over the genes, prods half scaled by Pr  (exp / Linear backward, odenet.py:86-89)
-    int rc = launch_branch(1, G, H, B, nterms, g, decay ? w.relum : nullptr, w.watimg, SP, GS, sc.gsimg, sc.spart, st);
+    int rc = launch_branch(1, G, H, B, nterms, g, decay ? w.relum : nullptr, w.watimg, SP, GS, sc.gsimg, sc.gstimg,
+                           sc.spart, st);
     if (rc != PHX_OK) return rc;
     if (ybar) {
         // u = gS Ws (k-blocks of the sums half), then v = gP Wp and the soft-sign / log1p backward in the epilogue
@@ -888,6 +960,29 @@ int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float
     }
     if (J) launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, KB2, 0, 0, 1.f, y, nullptr, w.relum, J, st);
     return check_launch("tc vjp_state");
+}
+
+// after phx_tc_rhs_forward_launch and phx_tc_vjp_state_launch on the same scratch: the K = batch contractions
+//   Wa_bar[g][k] = sum_b (g relu(m))[b][g] [S|P][b][k],  Ws_bar[h][g] = sum_b gS[b][h] s[b][g],  Wp_bar likewise with l
+// (Linear backward, odenet.py:86-89), written / accumulated into the flat gradient vector.
+int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
+                             float* grads, int accumulate, float* tcws, cudaStream_t st) {
+    const TcScratch sc = carve(G, H, B, tcws);
+    const int nterms = (w.tc == 1) ? 1 : 3, Hn = phx_tc_Hn(H);
+    const PhxGradOff off = phx_grad_offsets(G, H);
+    const size_t total = (size_t)G * 2 * H;
+    int blocks = (int)((total + 255) / 256);
+    if (blocks > PHX_TC_SMS * 16) blocks = PHX_TC_SMS * 16;
+    PhxTcBranchPlan pl;
+    int rc = launch_branch_mma(1, 1, G, H, B, nterms, g, decay ? w.relum : nullptr, sc.sptimg, sc.gslots, &pl, st);
+    if (rc != PHX_OK) return rc;
+    tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(1, G, pl.mtiles * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
+                                                 grads + off.Wa, nullptr, accumulate);
+    rc = launch_branch_mma(0, 1, G, H, B, nterms, y, nullptr, sc.gstimg, sc.gslots, &pl, st);
+    if (rc != PHX_OK) return rc;
+    tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(0, G, pl.mtiles * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
+                                                 grads + off.Ws, grads + off.Wp, accumulate);
+    return check_launch("tc vjp_params");
 }
 
 extern "C" void phx_tc_prof_dump(void) {

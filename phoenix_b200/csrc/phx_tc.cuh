@@ -47,6 +47,10 @@ static inline __host__ __device__ size_t phx_tc_waimg_floats(int G, int H) {
 static inline __host__ __device__ size_t phx_tc_spimg_floats(int H, int B) {
     return (size_t)phx_tc_BT(B) * phx_tc_KB2(H) * 2 * 256 * PHX_TC_BK;
 }
+// [S|P] / gSP as the B operand of the K = batch contractions: [ceil(B/16)][branch 2][hi|lo][Hn x 16]
+static inline __host__ __device__ size_t phx_tc_timg_floats(int H, int B) {
+    return (size_t)((B + PHX_TC_BK - 1) / PHX_TC_BK) * 4 * phx_tc_Hn(H) * PHX_TC_BK;
+}
 // float offset of element (r, k) inside an R-row x 16-float tile image
 static inline __host__ __device__ int phx_tc_tile_off(int R, int r, int k) {
     return ((((k >> 2) * (R >> 3) + (r >> 3)) * 8 + (r & 7)) << 2) + (k & 3);
@@ -92,5 +96,7 @@ static inline PhxTcBranchPlan phx_tc_branch_plan(int G, int B) {
 static inline size_t phx_tc_scratch_floats(int G, int H, int B) {
     const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
     const size_t Bpad = (size_t)phx_round_up(B, 128);
-    return (size_t)pl.slots * Bpad * 2 * phx_tc_Hn(H) + 2 * phx_tc_spimg_floats(H, B) + 64;
+    const PhxTcBranchPlan pg = phx_tc_branch_plan(B, G);   // K = batch contractions (parameter cotangents)
+    return (size_t)pl.slots * Bpad * 2 * phx_tc_Hn(H) + 2 * phx_tc_spimg_floats(H, B) + 2 * phx_tc_timg_floats(H, B) +
+           (size_t)pg.slots * pg.mtiles * 128 * 2 * phx_tc_Hn(H) + 64;
 }
