@@ -201,16 +201,33 @@ struct EpiGradWa {  // m = gene, n = packed column -> Wa_bar[g][2H] (skip pads)
     }
 };
 
-// column sums over the B rows (biases, multipliers): one thread per column, fixed order
+// column sums over the B rows (biases, multipliers).  Block = 32 columns x 32 row lanes: a warp reads 128 contiguous
+// bytes of one row, every row lane walks rows ty, ty+32, ... and the 32 lane totals are added in fixed order, so the
+// result is deterministic.
+constexpr int CS = 32;
+__device__ __forceinline__ float colsum_fold(float t, float (*sh)[CS + 1]) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    sh[ty][tx] = t;
+    __syncthreads();
+    float r = 0.f;
+    if (ty == 0)
+        for (int i = 0; i < CS; ++i) r += sh[i][tx];
+    return r;
+}
 __global__ void colsum_bias_kernel(const float* GS, int B, int K2, int Hp, int H, float* bs_bar, float* bp_bar,
                                    int accumulate) {
-    int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= 2 * H) return;
-    int col = (k < H) ? k : (Hp + k - H);
+    __shared__ float sh[CS][CS + 1];
+    const int k = blockIdx.x * CS + threadIdx.x;
+    const bool ok = k < 2 * H;
+    const int col = ok ? ((k < H) ? k : (Hp + k - H)) : 0;
     float t = 0.f;
-    for (int b = 0; b < B; ++b) t += GS[(size_t)b * K2 + col];
-    float* dst = (k < H) ? (bs_bar + k) : (bp_bar + (k - H));
-    *dst = accumulate ? *dst + t : t;
+    if (ok)
+        for (int b = threadIdx.y; b < B; b += CS) t += GS[(size_t)b * K2 + col];
+    t = colsum_fold(t, sh);
+    if (ok && threadIdx.y == 0) {
+        float* dst = (k < H) ? (bs_bar + k) : (bp_bar + (k - H));
+        *dst = accumulate ? *dst + t : t;
+    }
 }
 // f_out = fscale * relum * (J - y) from the un-decayed J
 __global__ void decay_kernel(const float* J, const float* y, const float* relum, int G, size_t n, float fscale,
@@ -220,17 +237,20 @@ __global__ void decay_kernel(const float* J, const float* y, const float* relum,
 }
 __global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const float* y, const float* maskm, int B,
                                    int G, float* m_bar, int accumulate, int decay) {
-    int gg = blockIdx.x * blockDim.x + threadIdx.x;
-    if (gg >= G) return;
+    __shared__ float sh[CS][CS + 1];
+    const int gg = blockIdx.x * CS + threadIdx.x;
+    const bool ok = gg < G;
     float t = 0.f;
-    if (decay) {
-        for (int b = 0; b < B; ++b) {
+    if (ok && decay)
+        for (int b = threadIdx.y; b < B; b += CS) {
             size_t i = (size_t)b * G + gg;
             t += g[i] * (f_nodecay[i] - y[i]);
         }
-        t *= maskm[gg];
+    t = colsum_fold(t, sh);
+    if (ok && threadIdx.y == 0) {
+        t = decay ? t * maskm[gg] : 0.f;
+        m_bar[gg] = accumulate ? m_bar[gg] + t : t;
     }
-    m_bar[gg] = accumulate ? m_bar[gg] + t : t;
 }
 
 }  // namespace
@@ -356,10 +376,10 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
                 sgemm(H, G, B, la, lb, ep, st);
             }
         }
-        colsum_bias_kernel<<<(2 * H + 127) / 128, 128, 0, st>>>(GS, B, K2, Hp, H, grads + off.bs, grads + off.bp,
-                                                                accumulate);
-        colsum_mult_kernel<<<(G + 127) / 128, 128, 0, st>>>(g, J, y, w.maskm, B, G, grads + off.m, accumulate,
-                                                            decay);
+        colsum_bias_kernel<<<(2 * H + CS - 1) / CS, dim3(CS, CS), 0, st>>>(GS, B, K2, Hp, H, grads + off.bs,
+                                                                           grads + off.bp, accumulate);
+        colsum_mult_kernel<<<(G + CS - 1) / CS, dim3(CS, CS), 0, st>>>(g, J, y, w.maskm, B, G, grads + off.m,
+                                                                       accumulate, decay);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -297,6 +297,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         const int row = m0 + rl;
         const float* src = TRANS ? p.y + row : p.y + (size_t)row * p.ld;
         const bool rok = row < p.B;
+        const float rscale = (MODE && TRANS && p.ascale && rok) ? __ldg(p.ascale + row) : 1.f;
         const unsigned a_off = (unsigned)(((kc * 16 + (rl >> 3)) * 8 + (rl & 7)) * 16);
         // y is read in super-blocks of K1_PF k-blocks: all loads of the NEXT super-block (K1_PF x 64 contiguous bytes
         // of this thread's row, requested back to back with a 256-byte L2 prefetch hint so that DRAM sees whole
@@ -312,7 +313,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     if (rok && i + u < nkb && g < p.G && !(p.dbg & 16)) {
                         if (TRANS) t = __ldg(src + (size_t)g * p.ld);
                         else asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
-                        if (MODE && p.ascale) t *= __ldg(p.ascale + (TRANS ? row : g));
                     }
                     v[u][j] = t;
                 }
@@ -333,7 +333,18 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     for (int j = 0; j < 4; ++j) {
                         float sv, lv;
                         if (MODE) {
-                            sv = lv = cur[u][j];
+                            // the per-gene factor is applied here, NOT where the load is issued: a use right behind
+                            // the load would wait for it and serialise the prefetch
+                            float sc = 1.f;
+                            if (p.ascale) {
+                                if (TRANS) {
+                                    sc = rscale;
+                                } else {
+                                    const int gi = (kb0 + i) * BK + kc * 4 + j;
+                                    sc = gi < p.G ? __ldg(p.ascale + gi) : 0.f;
+                                }
+                            }
+                            sv = lv = cur[u][j] * sc;
                         } else {
                             hill(cur[u][j], sv, lv, br && !(p.dbg & 2));
                         }
