@@ -154,14 +154,32 @@ def tensor_leg(pb, dev):
             torch.cuda.synchronize()
             out[mode] = sum(ev[i].elapsed_time(ev[i + 1]) for i in range(reps)) / reps
     pb.set_precision("3xtf32")
+    # forward + backward through autograd (ODENet.forward + the VJP for state and all six parameter cotangents):
+    # 8 (forward) + 24 (VJP: recompute, state cotangent, parameter cotangents) x B*G*H algorithmic flops
+    gcot = torch.randn(Bs, Gs, device=dev, generator=gen)
+    def fwd_bwd():
+        for p_ in net.parameters():
+            p_.grad = None
+        yg = y.detach().requires_grad_(True)
+        net(None, yg).backward(gcot)
+    for _ in range(2):
+        fwd_bwd()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        fwd_bwd()
+    e1.record()
+    torch.cuda.synchronize()
+    fb_ms = e0.elapsed_time(e1) / 5
     flops = 8.0 * Bs * Gs * Hs
-    del net, y
+    del net, y, gcot
     torch.cuda.empty_cache()
     return {"kernel": "tc_branch_kernel + tc_spfinish_kernel + tc_joint_kernel",
             "workload": "ODENet.forward, 20000 genes x 200 neurons x 4096 rows (3 launches per RHS evaluation)",
             "achieved": flops / (out["3xtf32"] * 1e-3) / 1e12, "launch_ms": out["3xtf32"],
             "algorithmic_flops": flops, "executed_mma_flops": 3.0 * flops,
-            "tf32_single_pass_ms": out["tf32"], "dtype": "tf32 x3 (fp32 parity)"}
+            "tf32_single_pass_ms": out["tf32"], "dtype": "tf32 x3 (fp32 parity)",
+            "fwd_bwd_ms": fb_ms, "fwd_bwd_achieved": 4.0 * flops / (fb_ms * 1e-3) / 1e12}
 
 
 def run_ours(args):

@@ -1,0 +1,73 @@
+"""BASELINE config 5 (synthetic scaling sweep): 20 000 genes x 4 096 trajectories in ONE batched odeint call,
+rk4 and dopri5, forward solve and forward + adjoint, on one B200 (streaming engine + tcgen05 contractions).
+
+    python tools/sweep_c5.py [--genes 20000] [--neurons 200] [--rows 4096] [--cpu-rows 8]
+
+Prints one JSON line per (method, leg): gene-steps/s = B * G * RHS evaluations / device time.  With --cpu-rows N the
+oracle (torch CPU port of the reference) is timed on N of the rows for the "vs host CPU" column.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import phoenix_b200 as pb  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--genes", type=int, default=20000)
+    ap.add_argument("--neurons", type=int, default=200)
+    ap.add_argument("--rows", type=int, default=4096)
+    ap.add_argument("--cpu-rows", type=int, default=0)
+    a = ap.parse_args()
+    G, H, B = a.genes, a.neurons, a.rows
+    torch.manual_seed(5)
+    net = pb.ODENet("cuda", G, neurons=H)
+    y0 = torch.rand(B, G, device="cuda")
+    pb.set_sync_errors(True)
+    for method, t, kw in (("rk4", torch.tensor([0.0, 0.1]), {}),
+                          ("dopri5", torch.tensor([0.0, 0.1]), {"rtol": 1e-5, "atol": 1e-7})):
+        for leg in ("forward", "forward+adjoint"):
+            def run():
+                if leg == "forward":
+                    with torch.no_grad():
+                        pb.odeint(net, y0, t, method=method, **kw)
+                    n = pb.last_status()["n_rhs"]
+                    return n
+                for p in net.parameters():
+                    p.grad = None
+                yg = y0.detach().requires_grad_(True)
+                y = pb.odeint_adjoint(net, yg, t, method=method, **kw)
+                nf = pb.last_status()["n_rhs"]
+                (y[1] ** 2).mean().backward()
+                return nf + pb.last_status()["n_rhs"]
+            run()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            evals = run()
+            e1.record()
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1)
+            print(json.dumps({"G": G, "H": H, "B": B, "method": method, "leg": leg, "rhs_evals": evals, "ms": ms,
+                              "gene_steps_per_s": B * G * evals / (ms * 1e-3)}), flush=True)
+    if a.cpu_rows:
+        from oracle import phoenix_oracle as O
+        torch.set_num_threads(os.cpu_count() or 1)
+        w = O.Weights(*[p.detach().cpu() for p in net.parameters()]) if hasattr(O, "Weights") else None
+        yc = y0[:a.cpu_rows].cpu()
+        O.odeint(w, yc, torch.tensor([0.0, 0.1]), method="rk4")
+        t0 = time.perf_counter()
+        _, log = O.odeint(w, yc, torch.tensor([0.0, 0.1]), method="rk4")
+        dt = time.perf_counter() - t0
+        print(json.dumps({"cpu_port": True, "rows": a.cpu_rows, "method": "rk4", "leg": "forward", "s": dt,
+                          "gene_steps_per_s": a.cpu_rows * G * 4 / dt, "cores": os.cpu_count()}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
