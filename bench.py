@@ -11,8 +11,10 @@ Synthetic expression values U[0,1), weights with the reference init distribution
 
 metric  gene-steps/s = B * G * (RHS evals forward + RHS-VJP evals adjoint) / time, evaluations counted by the solver.
 value   device-resident inputs, C-ABI calls (phx_solve_forward / phx_solve_adjoint) issued back to back.
-e2e     the same step through the reference-facing Python API (phoenix_b200.odeint_adjoint + backward) from pinned
-        HOST buffers, H2D of every sample and D2H of the loss inside the timed region.
+e2e     the same step through the public Python API from pinned HOST buffers, H2D of the samples and D2H of the loss
+        inside the timed region: phoenix_b200.odeint_adjoint_many (the per-sample loop of training_step as one call,
+        identical solves) + backward; the literal per-sample loop over phoenix_b200.odeint_adjoint is timed beside it
+        (e2e.per_sample_api_value).
 N > 1   weak scaling: every rank runs its own 17 samples, then ONE NCCL sum-allreduce of the flat gradient.
 """
 import argparse
@@ -287,7 +289,8 @@ def run_ours(args):
     t_cpu = [t_h[i].clone() for i in range(BATCH)]
     loss_host = torch.zeros(1).pin_memory()
 
-    def step_e2e():
+    def step_e2e_loop():
+        # the reference's training_step verbatim: one odeint call per sample (train_insilico.py:128-130)
         net.zero_grad(set_to_none=True)
         preds = []
         tgt = target_p.to(dev, non_blocking=True)
@@ -300,10 +303,24 @@ def run_ours(args):
             parallel.allreduce_grads(net)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
+    def step_e2e():
+        # the same step with the sample loop inside the library (odeint_adjoint_many: same solves, same results)
+        net.zero_grad(set_to_none=True)
+        tgt = target_p.to(dev, non_blocking=True)
+        yb = y0_p.to(dev, non_blocking=True)
+        pred = pb.odeint_adjoint_many(net, yb, t_h, method=METHOD)[:, 1]
+        loss = torch.mean((pred - tgt) ** 2)
+        loss.backward()
+        if world > 1:
+            parallel.allreduce_grads(net)
+        loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
+
     for _ in range(args.warmup):
         step_e2e()
+        step_e2e_loop()
     torch.cuda.synchronize()
     ms_e2e = timed(step_e2e, args.steps)
+    ms_e2e_loop = timed(step_e2e_loop, max(3, args.steps // 4)) / max(3, args.steps // 4) * args.steps
     pb.check_errors()
     sampler.stop_flag = True
     sampler.join(timeout=2)
@@ -314,13 +331,13 @@ def run_ours(args):
         tensor = tensor_leg(pb, dev)
 
     # ---- reduce over ranks: time = max, work = sum -------------------------------------------------------
-    stats = torch.tensor([ms_res, ms_e2e, float(evals)], dtype=torch.float64, device=dev)
+    stats = torch.tensor([ms_res, ms_e2e, float(evals), ms_e2e_loop], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stats.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stats.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        ms_res, ms_e2e, evals_total = float(mx[0]), float(mx[1]), float(sm[2])
+        ms_res, ms_e2e, evals_total, ms_e2e_loop = float(mx[0]), float(mx[1]), float(sm[2]), float(mx[3])
     else:
         evals_total = float(evals)
     work_per_step = G * evals_total                     # B = 1 per solve; evals already summed over the 17 samples
@@ -345,9 +362,13 @@ def run_ours(args):
         except Exception:
             pass
         cores = os.cpu_count() or 1
-        torch.set_num_threads(cores)
-        cpu_sample(w, y0_h, target_h, t_h, 1)
-        ce, cs = cpu_sample(w, y0_h, target_h, t_h, 3)
+        if world == 1:
+            torch.set_num_threads(cores)
+            cpu_sample(w, y0_h, target_h, t_h, 1)
+            ce, cs = cpu_sample(w, y0_h, target_h, t_h, 3)
+            cpu_value = G * ce / cs
+        else:
+            cpu_value = None   # measured at N = 1 only (torchrun pins the ranks to one OpenMP thread)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -357,14 +378,19 @@ def run_ours(args):
                        "rhs_evals_per_step": evals_total / world, "l2": "flushed between timed steps (256 MiB write)",
                        "parallelism": "dp%d (samples sharded, 1 grad allreduce/step)" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
-                    "h2d_bytes_per_step": 2 * BATCH * G * 4, "d2h_bytes_per_step": 4},
+                    "h2d_bytes_per_step": 2 * BATCH * G * 4, "d2h_bytes_per_step": 4,
+                    "api": "phoenix_b200.odeint_adjoint_many (sample loop of training_step inside the library) + "
+                           "loss.backward(), pinned host inputs",
+                    "per_sample_api_value": work_per_step / (ms_e2e_loop / args.steps / 1e3),
+                    "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130"},
             "gpu_launches": args.steps * BATCH * 2,
             "roofline": {"bound": "hbm", "kernel": "phx_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "launch_ms": adj_ms, "algorithmic_bytes": alg,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650"},
-            "cpu_baseline": {"value": G * ce / cs, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"},
+            "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"
+                                       if world == 1 else "measured at N=1 only"},
             "clocks": sampler.summary(),
         }
         if tensor is not None:

@@ -7,7 +7,7 @@ hand-written CUDA kernels behind the C ABI of ``include/phoenix_b200.h`` (libpho
 from . import engine
 from .engine import check_errors, last_status, last_step_log, set_precision, set_step_logging, set_sync_errors
 from .odenet import ODENet, LogShiftedSoftSignMod, SoftsignMod
-from .torchdiffeq import odeint, odeint_adjoint
+from .torchdiffeq import odeint, odeint_adjoint, odeint_adjoint_many
 
-__all__ = ["ODENet", "SoftsignMod", "LogShiftedSoftSignMod", "odeint", "odeint_adjoint", "engine", "check_errors",
+__all__ = ["ODENet", "SoftsignMod", "LogShiftedSoftSignMod", "odeint", "odeint_adjoint", "odeint_adjoint_many", "engine", "check_errors",
            "last_status", "last_step_log", "set_precision", "set_step_logging", "set_sync_errors"]

@@ -343,3 +343,83 @@ def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_sa
     _lib.check(rc, "solve_adjoint")
     _finish(st, "adjoint solve", dev)
     return adj_y0, split_flat_grads(grads, G, H)
+
+
+# ---- many independent problems per call (the per-sample loop of training_step) -----------------
+_MANY_CHUNK = 32   # samples whose [P]-long parameter cotangents are held at once before they are summed
+
+
+def _t_rows(t_rows):
+    return [(ctypes.c_double * len(r))(*r) for r in t_rows]
+
+
+def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_steps):
+    """y0 ``[N, *S, G]``: N independent problems, problem i integrated over its own times ``t_rows[i]`` (all of length
+    T).  Every problem is one resident launch with its own step controller -- exactly the reference's per-sample call
+    (train_insilico.py:128-130) -- but the weights are packed, the workspace fetched and the arguments marshalled once
+    for the whole set.  Returns ``[N, T, *S, G]``."""
+    packed, G, H, dev = packed_weights(net)
+    if y0.shape[-1] != G:
+        raise RuntimeError("last dimension of y0 (%d) must equal ndim (%d)" % (y0.shape[-1], G))
+    if _device_index(y0) != dev:
+        raise RuntimeError("y0 and the ODENet parameters must be on the same CUDA device")
+    y0c = y0.detach().contiguous()
+    N, T = len(t_rows), len(t_rows[0])
+    B = y0c[0].numel() // G
+    lib = _lib.load()
+    engine, nb = _pick_engine(lib, dev, G, H, B, T, False)
+    ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
+    yout = torch.empty((N, T) + tuple(y0c.shape[1:]), dtype=torch.float32, device=y0c.device)
+    fn = lib.phx_solve_forward if engine == "resident" else lib.phx_stream_solve_forward
+    ctx, sp, mid = _lib.ctx(dev), _stream_ptr(dev), _lib.METHOD_IDS[method]
+    pk, wsp, wsn = _ptr(packed), _ptr(ws), ws.numel()
+    ybase, obase = y0c.data_ptr(), yout.data_ptr()
+    ystride, ostride = y0c[0].numel() * 4, yout[0].numel() * 4
+    tarr = _t_rows(t_rows)
+    for i in range(N):
+        st = _new_status()
+        log, cap = _steplog()
+        rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
+                float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride), wsp, wsn,
+                _ptr(st), _ptr(log), cap, sp)
+        _lib.check(rc, "solve_forward")
+        _finish(st, "forward solve %d" % i, dev)
+    return yout
+
+
+def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps, y_saved, grad_y):
+    """Backward sweeps of N independent problems (``y_saved``, ``grad_y``: ``[N, T, *S, G]``): adj_y0 ``[N, *S, G]`` and
+    the six parameter cotangents summed over the problems (what autograd accumulates into ``.grad``)."""
+    packed, G, H, dev = packed_weights(net)
+    ys = y_saved.detach().contiguous()
+    gy = grad_y.detach().to(torch.float32).contiguous()
+    N, T = len(t_rows), len(t_rows[0])
+    B = ys[0, 0].numel() // G
+    lib = _lib.load()
+    engine, nb = _pick_engine(lib, dev, G, H, B, T, True)
+    ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
+    adj_y0 = torch.empty_like(ys[:, 0])
+    P = 4 * G * H + 2 * H + G
+    chunk = min(N, _MANY_CHUNK)
+    grads = torch.empty(chunk, P, dtype=torch.float32, device=ys.device)
+    total = None
+    fn = lib.phx_solve_adjoint if engine == "resident" else lib.phx_stream_solve_adjoint
+    ctx, sp, mid = _lib.ctx(dev), _stream_ptr(dev), _lib.METHOD_IDS[method]
+    pk, wsp, wsn = _ptr(packed), _ptr(ws), ws.numel()
+    stride = ys[0].numel() * 4
+    astride = adj_y0[0].numel() * 4
+    tarr = _t_rows(t_rows)
+    for lo in range(0, N, chunk):
+        hi = min(N, lo + chunk)
+        for i in range(lo, hi):
+            st = _new_status()
+            log, cap = _steplog()
+            rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
+                    ctypes.c_void_p(ys.data_ptr() + i * stride), ctypes.c_void_p(gy.data_ptr() + i * stride),
+                    ctypes.c_void_p(adj_y0.data_ptr() + i * astride),
+                    ctypes.c_void_p(grads.data_ptr() + (i - lo) * P * 4), wsp, wsn, _ptr(st), _ptr(log), cap, sp)
+            _lib.check(rc, "solve_adjoint")
+            _finish(st, "adjoint solve %d" % i, dev)
+        part = grads[:hi - lo].sum(dim=0)
+        total = part if total is None else total + part
+    return adj_y0, split_flat_grads(total, G, H)

@@ -134,3 +134,50 @@ def odeint_adjoint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None,
     params = engine.net_params(func)
     return OdeintAdjointMethod.apply(func, tl, t_is_f32, method, rtol, atol, max_steps,
                                      (a_method, a_rtol, a_atol, a_max), y0, *params)
+
+
+class OdeintAdjointManyMethod(torch.autograd.Function):
+    """N independent ``OdeintAdjointMethod`` problems behind one autograd node (engine.solve_*_many)."""
+
+    @staticmethod
+    def forward(ctx, func, t_rows, t_is_f32, method, rtol, atol, max_steps, adj, y0, *adjoint_params):
+        ctx.func, ctx.t_rows, ctx.t_is_f32, ctx.adj = func, t_rows, t_is_f32, adj
+        with torch.no_grad():
+            y = engine.solve_forward_many(func, y0, t_rows, t_is_f32, method, rtol, atol, max_steps)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, grad_y):
+        (y,) = ctx.saved_tensors
+        a_method, a_rtol, a_atol, a_max = ctx.adj
+        with torch.no_grad():
+            adj_y0, grads = engine.solve_adjoint_many(ctx.func, ctx.t_rows, ctx.t_is_f32, a_method, a_rtol, a_atol,
+                                                      a_max, y, grad_y)
+        out = [None] * 8 + [adj_y0 if ctx.needs_input_grad[8] else None]
+        for i, need in enumerate(ctx.needs_input_grad[9:]):
+            out.append(grads[i] if need else None)
+        return tuple(out)
+
+
+def odeint_adjoint_many(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
+    """The per-sample loop of the reference's ``training_step`` (train_insilico.py:128-130,
+    ``[odeint(odenet, batch_point, time_points, method=method)[1] for ...]``) as ONE call: ``y0`` is ``[N, *S, G]``
+    (N independent initial states), ``t`` is ``[N, T]`` (each sample's own times, increasing) and the result is
+    ``[N, T, *S, G]`` with ``result[i] == odeint_adjoint(func, y0[i], t[i], ...)`` bit for bit: every sample is still
+    its own solve with its own step controller (NOT the global-norm batched call).  Gradients flow to ``y0`` and to the
+    six ODENet parameters (summed over the samples) through one autograd node.  No reference counterpart: opt-in."""
+    assert torch.is_tensor(t) and t.ndimension() == 2, "t must be a [N, T] tensor of per-sample times"
+    assert torch.is_tensor(y0) and y0.shape[0] == t.shape[0], "y0 and t must hold the same number of samples"
+    if y0.shape[0] == 0:
+        raise ValueError("odeint_adjoint_many needs at least one sample")
+    t_is_f32 = t.dtype != torch.float64
+    rows = t.tolist()
+    tl0, _, rev, rtol_f, atol_f, method, max_steps = _normalise(func, y0[0], t[0], rtol, atol, method, options)
+    for r in rows:
+        assert all(b > a for a, b in zip(r, r[1:])), 't must be strictly increasing for every sample'
+    if rev:
+        raise NotImplementedError("odeint_adjoint_many with decreasing t is not part of the PHOENIX path")
+    params = engine.net_params(func)
+    return OdeintAdjointManyMethod.apply(func, rows, t_is_f32, method, rtol_f, atol_f, max_steps,
+                                         (method, rtol_f, atol_f, max_steps), y0, *params)

@@ -329,3 +329,31 @@ def test_ragged_and_edge_shapes(pb):
         with torch.no_grad():
             y = pb.odeint(net, y0.cuda(), t, method="rk4")
         assert rel_l2(y.cpu(), y_ref) < 1e-5, (G, H, B)
+
+
+def test_odeint_adjoint_many_equals_the_per_sample_loop(pb):
+    """SURVEY 8(f1): the sample loop of training_step inside the library.  Same solves => identical trajectories;
+    parameter cotangents are the per-sample ones summed (different summation tree => 1e-6)."""
+    G, H, N = 690, 40, 5
+    w = O.make_weights(G, H, 90, dense=True)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(11)
+    y0 = torch.rand(N, 1, G, generator=gen).cuda()
+    tau = torch.rand(N, generator=gen)
+    t = torch.stack([tau, tau + 0.5, tau + 1.25], dim=1)
+    target = torch.rand(N, 1, G, generator=gen).cuda()
+    for method in ("dopri5", "rk4"):
+        net.zero_grad()
+        ya = y0.clone().requires_grad_(True)
+        many = pb.odeint_adjoint_many(net, ya, t, method=method)
+        torch.mean((many[:, 2] - target) ** 2).backward()
+        g_many = [ya.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+        net.zero_grad()
+        yb = y0.clone().requires_grad_(True)
+        loop = torch.stack([pb.odeint_adjoint(net, yb[i], t[i], method=method) for i in range(N)])
+        torch.mean((loop[:, 2] - target) ** 2).backward()
+        g_loop = [yb.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+        assert torch.equal(many, loop)
+        assert torch.equal(g_many[0], g_loop[0])
+        for a, b in zip(g_many[1:], g_loop[1:]):
+            assert rel_l2(a.cpu(), b.cpu()) < 1e-6
