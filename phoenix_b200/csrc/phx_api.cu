@@ -155,7 +155,7 @@ int phx_ctx_set_precision(phx_ctx* ctx, int precision) {
     return PHX_OK;
 }
 int phx_ctx_get_precision(const phx_ctx* ctx) { return ctx ? ctx->precision : PHX_ERR_INVALID; }
-int phx_tc_min_rows(void) { return PHX_TC_MIN_ROWS; }
+int phx_tc_min_rows(void) { return phx_tc_min_rows_rt(); }
 
 size_t phx_packed_bytes(int G, int H) { return phx_packed_floats(G, H) * sizeof(float); }
 

@@ -1,7 +1,7 @@
 // Tensor-core (tcgen05 / TMEM) path of the batched RHS: shared layout definitions.
 //
-// When the trajectory batch makes the branch contractions real dense GEMMs (B >= PHX_TC_MIN_ROWS rows: the 10 000-row
-// prior batch of train_insilico.py:134, the 4 096-row synthetic sweep), they run on the 5th-generation tensor cores as
+// When a call carries more rows than the resident solver kernels take (B >= PHX_TC_MIN_ROWS: the 60-row gene-influence
+// scan, the 10 000-row prior batch of train_insilico.py:134, the 4 096-row synthetic sweep), the contractions run on the 5th-generation tensor cores as
 // TF32 MMAs with fp32 accumulators in tensor memory.  fp32 parity with the reference (odenet.py:85-91 evaluated by ATen
 // in fp32) is kept by the 3xTF32 split: every operand x is stored as hi = rna_tf32(x), lo = rna_tf32(x - hi) and a
 // product is accumulated as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (PHX_PREC_3XTF32).  PHX_PREC_TF32 issues only hi*hi and is
@@ -26,7 +26,8 @@
 // (included from phx_common.cuh after phx_round_up)
 
 #define PHX_TC_BK 16
-#define PHX_TC_MIN_ROWS 128
+#define PHX_TC_MIN_ROWS 5   /* more rows than the resident adjoint kernel takes: measured 40-55x faster than the
+                             fp32 SGEMM path already at 17-60 rows (128-row tiles mostly padding, still far ahead) */
 #define PHX_TC_MAX_HN 256
 #define PHX_TC_SMS 148
 #define PHX_TC_MAX_KSPLIT 64
@@ -36,7 +37,15 @@ static inline __host__ __device__ int phx_tc_KB1(int G) { return (G + PHX_TC_BK 
 static inline __host__ __device__ int phx_tc_KB2(int H) { return 2 * phx_tc_Hn(H) / PHX_TC_BK; }
 static inline __host__ __device__ int phx_tc_GT(int G) { return (G + 127) / 128; }
 static inline __host__ __device__ int phx_tc_BT(int B) { return (B + 255) / 256; }
-static inline bool phx_tc_shape_ok(int H, int B) { return B >= PHX_TC_MIN_ROWS && phx_tc_Hn(H) <= PHX_TC_MAX_HN; }
+static inline int phx_tc_min_rows_rt() {
+    static int v = 0;
+    if (!v) {
+        const char* e = getenv("PHX_TC_MIN_ROWS");   // experiments only
+        v = e && atoi(e) > 0 ? atoi(e) : PHX_TC_MIN_ROWS;
+    }
+    return v;
+}
+static inline bool phx_tc_shape_ok(int H, int B) { return B >= phx_tc_min_rows_rt() && phx_tc_Hn(H) <= PHX_TC_MAX_HN; }
 
 static inline __host__ __device__ size_t phx_tc_w1img_floats(int G, int H) {
     return (size_t)phx_tc_KB1(G) * 4 * phx_tc_Hn(H) * PHX_TC_BK;

@@ -49,7 +49,7 @@ _PRECISIONS = {"fp32": _lib.PREC_FP32, "tf32": _lib.PREC_TF32, "3xtf32": _lib.PR
 
 
 def set_precision(mode, device=None):
-    """Arithmetic of the dense (B >= 128 rows) contractions: '3xtf32' (default; tcgen05 tensor cores with the
+    """Arithmetic of the dense (B >= 5 rows) contractions: '3xtf32' (default; tcgen05 tensor cores with the
     three-term TF32 split, fp32 parity), 'tf32' (single-pass TF32, ~1e-3 relative error) or 'fp32' (CUDA cores).
     Smaller batches are GEMV-bound and always run in fp32 on the CUDA cores."""
     if mode not in _PRECISIONS:

@@ -1,5 +1,5 @@
-"""GPU parity tests of the tcgen05 (tensor-core) batched RHS: calls with B >= 128 rows run the branch and joint
-contractions as 3xTF32 MMAs with TMEM accumulators (csrc/phx_tc.cu).
+"""GPU parity tests of the tcgen05 (tensor-core) batched RHS: calls with B >= 5 rows run the branch and joint
+contractions as 3xTF32 MMAs (phx_tc_min_rows() = 5: everything the resident solver kernels do not take) with TMEM accumulators (csrc/phx_tc.cu).
 
 Tolerances:
   * '3xtf32' (default): same bar as the fp32 CUDA-core path, relative L2 <= 1e-5 against the fp32 oracle
@@ -34,7 +34,8 @@ def make_net(pb, w):
     return net
 
 
-SHAPES = [(350, 40, 300), (37, 5, 128), (1001, 100, 257), (690, 40, 1000), (3551, 120, 256)]
+SHAPES = [(350, 40, 300), (37, 5, 128), (1001, 100, 257), (690, 40, 1000), (3551, 120, 256), (129, 33, 5),
+          (350, 40, 17), (1001, 100, 60)]
 
 
 @pytest.mark.parametrize("G,H,B", SHAPES)
@@ -72,8 +73,8 @@ def test_tc_precision_modes(pb):
 
 
 def test_tc_below_threshold_uses_fp32_path(pb):
-    """B < 128 rows never touches the tensor cores: identical bits in every precision mode."""
-    G, H, B = 350, 40, 127
+    """B < phx_tc_min_rows() = 5 rows never touches the tensor cores: identical bits in every precision mode."""
+    G, H, B = 350, 40, 4
     w = O.make_weights(G, H, 18, dense=True)
     net = make_net(pb, w)
     y = torch.rand(B, G, generator=torch.Generator().manual_seed(4)).cuda()
