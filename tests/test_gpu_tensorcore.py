@@ -171,3 +171,14 @@ def test_tc_full_size_sweep_shape_against_float64_rows(pb):
         ref = torch.relu(net.gene_multipliers.double()) * (J - yd)
     assert torch.isfinite(f).all()
     assert rel_l2(f[rows].cpu(), ref.cpu()) < 1e-5
+
+
+def test_wide_hidden_layer_falls_back_to_fp32_contractions(pb):
+    """H > 256 does not fit the 512 tensor-memory columns (chunk accumulator + running sum): CUDA-core path, same bar."""
+    G, H, B = 97, 300, 40
+    w = O.make_weights(G, H, 23, dense=True)
+    net = make_net(pb, w)
+    y = torch.rand(B, G, generator=torch.Generator().manual_seed(9))
+    with torch.no_grad():
+        f = net(None, y.cuda())
+    assert rel_l2(f.cpu(), O.rhs(w, y)) < 1e-5

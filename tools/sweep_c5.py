@@ -2,6 +2,10 @@
 rk4 and dopri5, forward solve and forward + adjoint, on one B200 (streaming engine + tcgen05 contractions).
 
     python tools/sweep_c5.py [--genes 20000] [--neurons 200] [--rows 4096] [--cpu-rows 8]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sweep_c5.py ...
+
+Under torchrun the rows are sharded over the ranks (weak scaling: --rows is PER RANK), weights are broadcast from rank
+0, the adjoint leg ends with ONE NCCL sum-allreduce of the flat gradient, times are the max over ranks.
 
 Prints one JSON line per (method, leg): gene-steps/s = B * G * RHS evaluations / device time.  With --cpu-rows N the
 oracle (torch CPU port of the reference) is timed on N of the rows for the "vs host CPU" column.
@@ -26,8 +30,16 @@ def main():
     ap.add_argument("--cpu-rows", type=int, default=0)
     a = ap.parse_args()
     G, H, B = a.genes, a.neurons, a.rows
+    import torch.distributed as dist
+    from phoenix_b200 import parallel
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
     torch.manual_seed(5)
     net = pb.ODENet("cuda", G, neurons=H)
+    parallel.broadcast_parameters(net)
+    torch.manual_seed(100 + rank)
     y0 = torch.rand(B, G, device="cuda")
     pb.set_sync_errors(True)
     for method, t, kw in (("rk4", torch.tensor([0.0, 0.1]), {}),
@@ -45,18 +57,31 @@ def main():
                 y = pb.odeint_adjoint(net, yg, t, method=method, **kw)
                 nf = pb.last_status()["n_rhs"]
                 (y[1] ** 2).mean().backward()
-                return nf + pb.last_status()["n_rhs"]
+                nb = pb.last_status()["n_rhs"]
+                if world > 1:
+                    parallel.allreduce_grads(net)
+                return nf + nb
             run()
             torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
             evals = run()
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1)
-            print(json.dumps({"G": G, "H": H, "B": B, "method": method, "leg": leg, "rhs_evals": evals, "ms": ms,
-                              "gene_steps_per_s": B * G * evals / (ms * 1e-3)}), flush=True)
-    if a.cpu_rows:
+            work = float(B * G * evals)
+            if world > 1:
+                st = torch.tensor([ms, work], dtype=torch.float64, device="cuda")
+                mx = st.clone()
+                dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+                dist.all_reduce(st, op=dist.ReduceOp.SUM)
+                ms, work = float(mx[0]), float(st[1])
+            if rank == 0:
+                print(json.dumps({"n_gpus": world, "G": G, "H": H, "rows_per_gpu": B, "method": method, "leg": leg,
+                                  "rhs_evals": evals, "ms": ms, "gene_steps_per_s": work / (ms * 1e-3)}), flush=True)
+    if a.cpu_rows and rank == 0 and world == 1:
         from oracle import phoenix_oracle as O
         torch.set_num_threads(os.cpu_count() or 1)
         w = O.Weights(*[p.detach().cpu() for p in net.parameters()]) if hasattr(O, "Weights") else None
@@ -67,6 +92,9 @@ def main():
         dt = time.perf_counter() - t0
         print(json.dumps({"cpu_port": True, "rows": a.cpu_rows, "method": "rk4", "leg": "forward", "s": dt,
                           "gene_steps_per_s": a.cpu_rows * G * 4 / dt, "cores": os.cpu_count()}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
