@@ -108,8 +108,12 @@ int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* gene_multipliers, 
 int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, float* f, int decay,
                     void* workspace, size_t workspace_bytes, void* stream);
 /* VJP of the call above for cotangent g[B][G] (what torch.autograd computes through odenet.py:85-98):
- * ybar[B][G] (may be NULL) and the flat parameter cotangents grads_flat[P] (may be NULL); accumulate != 0 adds into
- * grads_flat instead of overwriting it. */
+ * ybar[B][G] (may be NULL) and the flat parameter cotangents grads_flat[P] (may be NULL); accumulate bit 0 adds into
+ * grads_flat instead of overwriting it.  accumulate bit 1 (PHX_VJP_REUSE_FORWARD = 2) is a promise by the caller that
+ * `workspace` has not been touched since a phx_rhs_forward call with the same packed weights, the same y and the same
+ * B ran on it: the branch contraction [S|P] it left there is reused instead of recomputed (what autograd's saved
+ * activations give the reference).  Ignored on the fp32 path. */
+#define PHX_VJP_REUSE_FORWARD 2
 int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, const float* g, int decay,
                 float* ybar, float* grads_flat, int accumulate, void* workspace, size_t workspace_bytes,
                 void* stream);

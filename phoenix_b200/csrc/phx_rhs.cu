@@ -296,9 +296,10 @@ int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float*
 }
 
 int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
-                       float* ybar, float* grads, int accumulate, float* f_out, float fscale, float* ws,
+                       float* ybar, float* grads, int accumulate_flags, float* f_out, float fscale, float* ws,
                        cudaStream_t st) {
     const int Hp = phx_Hp(H), K2 = 2 * Hp;
+    const int accumulate = accumulate_flags & 1;
     float* SP = ws;
     float* GS = ws + (size_t)B * K2;
     float* J = GS + (size_t)B * K2;
@@ -310,7 +311,9 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
         // tensor cores: [S|P], gSP, the state cotangent and the un-decayed joint (phx_tc.cu); the K = B parameter
         // contractions below stay on the fp32 path
         float* tcws = ws + rhs_base_floats(G, H, B);
-        int rc = phx_tc_rhs_forward_launch(G, H, B, w, y, nullptr, 0, 1.f, SP, tcws, st);
+        int rc = PHX_OK;
+        if (!(accumulate_flags & 2))   // bit 1: the workspace still holds [S|P] (+ images) of this (weights, y)
+            rc = phx_tc_rhs_forward_launch(G, H, B, w, y, nullptr, 0, 1.f, SP, tcws, st);
         if (rc != PHX_OK) return rc;
         rc = phx_tc_vjp_state_launch(G, H, B, w, y, g, decay, ybar, SP, GS, needJ ? J : nullptr, tcws, st);
         if (rc != PHX_OK) return rc;

@@ -55,6 +55,56 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst, const void* src, unsigned
                  "l"(src), "r"(bytes), "r"(bar)
                  : "memory");
 }
+// cluster-scope variants for the 2-CTA (cta_group::2) kernels
+__device__ __forceinline__ void mbar_wait_cluster(unsigned bar, unsigned parity) {
+    unsigned done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+__device__ __forceinline__ void mbar_arrive_remote(unsigned bar, unsigned cta) {   // same barrier offset in CTA `cta`
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(bar), "r"(cta));
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(r) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mma_tf32_pair(unsigned tmem_d, uint64_t adesc, uint64_t bdesc, unsigned idesc,
+                                              unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair(unsigned bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"((unsigned short)3)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc512_pair(unsigned slot_saddr) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(slot_saddr), "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_free512_pair(unsigned base) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(base), "r"(512u) : "memory");
+}
+
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -251,22 +301,32 @@ __device__ __forceinline__ uint64_t desc_at(uint64_t hi_part, unsigned saddr) {
 // TRANS = 0: A(row, k) = src[row][k]  (rows = batch, k = genes).  TRANS = 1: A(row, k) = src[k][row] (rows = genes,
 // k = batch rows: the K = B parameter-cotangent contractions); lanes then run along the genes, so every load is a
 // coalesced 128-byte row segment and the transpose happens in registers (4 batch rows -> one 16-byte k chunk).
-template <int MODE, int TRANS>
+// PAIR = 1: two CTAs of a cluster (the two SMs of a TPC) work on adjacent 128-row tiles of the same (branch, K range) and
+// their tensor cores execute ONE tcgen05.mma.cta_group::2 (M = 256) issued by the leader CTA: each CTA stages its own A
+// tile and only HALF of the B operand (rows [rank*Hn/2, +Hn/2) of the image), which cuts the shared-memory traffic per
+// k-block from ~107 KB to ~73 KB -- the bound of the single-CTA kernel.  Producer arrivals and the "B half landed"
+// signal of the peer CTA reach the leader's full barrier as remote (cluster-scope) arrives; slot release and chunk
+// completion come back to both CTAs by multicast tcgen05.commit.
+template <int MODE, int TRANS, int PAIR>
 __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // work item: branch, 128-row tile, K range (a whole number of chunks)
-    int blk = blockIdx.x;
-    const int np = p.mtiles * p.ks_p;
+    // work item: branch, 128-row tile (PAIR: tile pair), K range (a whole number of chunks)
+    int blk = PAIR ? blockIdx.x >> 1 : blockIdx.x;
+    const unsigned crank = PAIR ? (blockIdx.x & 1u) : 0u;   // rank in the (2,1,1) cluster
+    const bool leader = crank == 0;
+    const int mt = PAIR ? (p.mtiles + 1) / 2 : p.mtiles;
+    const int np = mt * p.ks_p;
     const int br = blk < np ? 1 : 0;
     if (!br) blk -= np;
-    const int ks = blk / p.mtiles, per = br ? p.per_p : p.per_s;
-    const int m0 = (blk % p.mtiles) * 128;
+    const int ks = blk / mt, per = br ? p.per_p : p.per_s;
+    const int m0 = (PAIR ? 2 * (blk % mt) + (int)crank : blk % mt) * 128;
     const int kb0 = ks * per;
     const int nkb = min(p.KB1, kb0 + per) - kb0;   // >= 1 by construction (phx_tc_branch_plan)
     const int nchunks = (nkb + p.chunk - 1) / p.chunk;
     const int S = p.stages, Hn = p.Hn;
-    const unsigned b_tile = (unsigned)Hn * BK * 4;
+    const int Hb = PAIR ? Hn >> 1 : Hn;                 // B rows staged by this CTA
+    const unsigned b_tile = (unsigned)Hb * BK * 4;
     const unsigned b_bytes = 2 * b_tile;
     const unsigned stage_bytes = K1_A_BYTES + b_bytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)S * stage_bytes);
@@ -277,16 +337,22 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
-            mbar_init(full0 + 8 * s, K1_PWARPS + 1);   // producer warps + the bulk-copy issuer (expect_tx)
-            mbar_init(empty0 + 8 * s, 1);              // tcgen05.commit
+            // single CTA: producer warps + the bulk-copy issuer (expect_tx).  Pair, leader: + the peer's producer warps
+            // and its "B half landed" relay; pair, peer: the barrier only tracks the peer's own bulk copy.
+            mbar_init(full0 + 8 * s, !PAIR ? K1_PWARPS + 1 : (leader ? 2 * K1_PWARPS + 2 : 1));
+            mbar_init(empty0 + 8 * s, 1);              // tcgen05.commit (multicast to both CTAs of a pair)
         }
         mbar_init(done, 1);
-        mbar_init(drained, K1_DWARPS);
+        mbar_init(drained, PAIR ? 2 * K1_DWARPS : K1_DWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == K1_W_BULK) tmem_alloc512(smem_u32(slot));
+    if (warp == K1_W_BULK) {
+        if (PAIR) tmem_alloc512_pair(smem_u32(slot));
+        else tmem_alloc512(smem_u32(slot));
+    }
     tc_fence_before();
     __syncthreads();
+    if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
     tc_fence_after();
     const unsigned tmem = *slot;   // chunk accumulator: columns [0, Hn); running sum: columns [256, 256 + Hn)
 
@@ -359,7 +425,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     *reinterpret_cast<float4*>(a + K1_A_TILE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
                     if (!(p.dbg & 32)) fence_async_smem();   // generic-proxy writes -> visible to the async-proxy reads
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(full0 + 8 * s);
+                    if (lane == 0) {
+                        if (PAIR && !leader) mbar_arrive_remote(full0 + 8 * s, 0u);
+                        else mbar_arrive(full0 + 8 * s);
+                    }
                     if (++s == S) {
                         s = 0;
                         ph ^= 1u;
@@ -384,10 +453,24 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (p.dbg & 8) {   // timing experiment: no operand copy
                     mbar_arrive(full0 + 8 * s);
-                } else {
+                } else if (!PAIR) {
                     mbar_expect_tx(full0 + 8 * s, b_bytes);
                     bulk_g2s(stage0 + s * stage_bytes + K1_A_BYTES,
                              p.w1img + ((size_t)(kb0 + i) * 4 + 2 * br) * Hn * BK, b_bytes, full0 + 8 * s);
+                } else {
+                    // this CTA's half of the rows: in the image the rows of one k-chunk are contiguous, so the half
+                    // tile is 2 (hi|lo) x 4 (k-chunks) pieces of Hn/16 core matrices
+                    mbar_expect_tx(full0 + 8 * s, b_bytes);
+                    const float* chunk = p.w1img + ((size_t)(kb0 + i) * 4 + 2 * br) * Hn * BK;
+                    const unsigned piece = (unsigned)(Hn >> 4) * 128u;
+                    const unsigned dst0 = stage0 + s * stage_bytes + K1_A_BYTES;
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl)
+#pragma unroll
+                        for (int kc4 = 0; kc4 < 4; ++kc4)
+                            bulk_g2s(dst0 + hl * b_tile + kc4 * piece,
+                                     chunk + (size_t)hl * Hn * BK + ((size_t)kc4 * (Hn >> 3) + crank * (Hn >> 4)) * 32,
+                                     piece, full0 + 8 * s);
                 }
                 if (++s == S) {
                     s = 0;
@@ -397,20 +480,36 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         }
     } else if (warp == K1_W_MMA) {
         // ---- MMA issuer: the whole warp runs the loop (uniform control flow, descriptors in uniform registers); one
-        // elected lane issues the tcgen05 instructions ----
-        const unsigned idesc = idesc_tf32(128, Hn);
+        // elected lane issues the tcgen05 instructions.  In a pair only the leader issues; the peer's warp relays
+        // "my half of B has landed" to the leader's full barrier. ----
+        const unsigned idesc = idesc_tf32(PAIR ? 256 : 128, Hn);
         const uint64_t a_hi_part = smem_desc(0, p.a_lbo, p.a_sbo), b_hi_part = smem_desc(0, p.b_lbo, p.b_sbo);
         int s = 0, c = 0, ic = 0;
         unsigned ph = 0;
         long long t_full = 0, t_drained = 0, t0 = clock64();
+        if (PAIR && !leader) {
+            for (int i = 0; i < nkb; ++i) {
+                if (lane == 0) {
+                    mbar_wait(full0 + 8 * s, ph);
+                    mbar_arrive_remote(full0 + 8 * s, 0u);
+                }
+                __syncwarp();
+                if (++s == S) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        } else
         for (int i = 0; i < nkb; ++i) {
-            if (ic == 0 && c > 0) {   // the previous chunk's sum must have left the chunk accumulator
+            if (ic == 0 && c > 0) {   // the previous chunk's sum must have left the chunk accumulator (both CTAs)
                 const long long tw = p.prof ? clock64() : 0;
-                mbar_wait(drained, (unsigned)(c - 1) & 1u);
+                if (PAIR) mbar_wait_cluster(drained, (unsigned)(c - 1) & 1u);
+                else mbar_wait(drained, (unsigned)(c - 1) & 1u);
                 if (p.prof) t_drained += clock64() - tw;
             }
             const long long tw = p.prof ? clock64() : 0;
-            mbar_wait(full0 + 8 * s, ph);
+            if (PAIR) mbar_wait_cluster(full0 + 8 * s, ph);
+            else mbar_wait(full0 + 8 * s, ph);
             if (p.prof) t_full += clock64() - tw;
             tc_fence_after();
             const unsigned a_base = stage0 + s * stage_bytes, b_base = a_base + K1_A_BYTES;
@@ -423,7 +522,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     const uint64_t b_lo = desc_at(b_hi_part, b_base + b_tile + k8 * p.b_kadv);
                     const unsigned acc = (ic > 0 || k8 > 0) ? 1u : 0u;
                     if (p.dbg & 4) continue;   // timing experiment: no MMAs
-                    if (p.nterms == 3) {
+                    if (PAIR) {
+                        if (p.nterms == 3) {
+                            mma_tf32_pair(tmem, a_lo, b_hi, idesc, acc);
+                            mma_tf32_pair(tmem, a_hi, b_lo, idesc, 1u);
+                            mma_tf32_pair(tmem, a_hi, b_hi, idesc, 1u);
+                        } else {
+                            mma_tf32_pair(tmem, a_hi, b_hi, idesc, acc);
+                        }
+                    } else if (p.nterms == 3) {
                         mma_tf32(tmem, a_lo, b_hi, idesc, acc);
                         mma_tf32(tmem, a_hi, b_lo, idesc, 1u);
                         mma_tf32(tmem, a_hi, b_hi, idesc, 1u);
@@ -431,8 +538,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                         mma_tf32(tmem, a_hi, b_hi, idesc, acc);
                     }
                 }
-                mma_commit(empty0 + 8 * s);
-                if (ic == p.chunk - 1 || i == nkb - 1) mma_commit(done);
+                if (PAIR) {
+                    mma_commit_pair(empty0 + 8 * s);
+                    if (ic == p.chunk - 1 || i == nkb - 1) mma_commit_pair(done);
+                } else {
+                    mma_commit(empty0 + 8 * s);
+                    if (ic == p.chunk - 1 || i == nkb - 1) mma_commit(done);
+                }
             }
             __syncwarp();
             if (++s == S) {
@@ -498,14 +610,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(drained);
+            if (lane == 0) {
+                if (PAIR && !leader) mbar_arrive_remote(drained, 0u);
+                else mbar_arrive(drained);
+            }
             if (p.prof) t_drain += clock64() - tw;
         }
         if (p.prof && warp == K1_W_DRAIN && lane == 0) atomicAdd(p.prof + 8 * br + 6, (unsigned long long)t_drain);
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == K1_W_BULK) tmem_free512(tmem);
+    if (PAIR) cluster_sync_all();   // the peer's shared memory and barriers stay alive until the leader is done
+    if (warp == K1_W_BULK) {
+        if (PAIR) tmem_free512_pair(tmem);
+        else tmem_free512(tmem);
+    }
 }
 
 // ---- K-split reduction + bias + exp + operand image of [S|P] ------------------------------------------------------------
@@ -777,6 +896,17 @@ unsigned long long* phx_tc_prof_buffer() {
     return g_prof;
 }
 
+// EXPERIMENTAL, off by default (PHX_TC_PAIR=1 or phx_tc_set_pair): the branch-type contractions as CTA pairs (tcgen05
+// cta_group::2).  Bit-identical results; measured SLOWER on B200 than the single-CTA kernel.
+int g_pair = -1;
+int pair_mode() {
+    if (g_pair < 0) {
+        const char* e = getenv("PHX_TC_PAIR");
+        g_pair = e ? atoi(e) : 0;
+    }
+    return g_pair;
+}
+
 int debug_flags() {
     static int flags = -1;
     if (flags < 0) {
@@ -813,7 +943,7 @@ struct TcScratch {
     float* gslots;   // partial-sum slots of the K = batch contractions
 };
 TcScratch carve(int G, int H, int B, float* tcws) {
-    const int Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
+    const int Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 256);
     const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
     TcScratch sc;
     sc.spart = reinterpret_cast<float*>(((uintptr_t)tcws + 127) & ~(uintptr_t)127);
@@ -828,10 +958,14 @@ TcScratch carve(int G, int H, int B, float* tcws) {
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(tc_branch_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
@@ -857,11 +991,13 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     *plan = pl;
     const int dbg = debug_flags();
     BranchParams bp;
-    bp.G = Kdim; bp.B = Mdim; bp.Bpad = pl.mtiles * 128; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(Kdim); bp.chunk = phx_tc_chunk();
+    const int pair = pair_mode();
+    bp.G = Kdim; bp.B = Mdim; bp.Bpad = phx_round_up(pl.mtiles, 2) * 128; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(Kdim); bp.chunk = phx_tc_chunk();
     bp.ld = G;
     bp.nterms = nterms; bp.dbg = dbg; bp.mode = mode; bp.ascale = ascale;
     bp.mtiles = pl.mtiles; bp.ks_p = pl.ks_p; bp.per_p = pl.per_p; bp.ks_s = pl.ks_s; bp.per_s = pl.per_s;
-    bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hn / 8) * 128; bp.b_sbo = 128;
+    const int Hb = pair ? Hn / 2 : Hn;   // B rows staged per CTA
+    bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hb / 8) * 128; bp.b_sbo = 128;
     bp.a_kadv = 2 * bp.a_lbo; bp.b_kadv = 2 * bp.b_lbo;
     if (dbg & 1) {   // diagnostic: swapped meaning of the two descriptor offsets
         unsigned t = bp.a_lbo; bp.a_lbo = bp.a_sbo; bp.a_sbo = t;
@@ -869,7 +1005,7 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     }
     bp.y = src; bp.w1img = bimg; bp.spart = spart;
     bp.prof = phx_tc_prof_buffer();
-    const size_t stage1 = K1_A_BYTES + (size_t)2 * Hn * BK * 4;
+    const size_t stage1 = K1_A_BYTES + (size_t)2 * Hb * BK * 4;
     int S1 = (int)((PHX_SMEM_LIMIT - 256) / stage1);
     if (S1 > 6) S1 = 6;
     if (const char* e = getenv("PHX_TC_STAGES")) {   // experiment
@@ -882,14 +1018,42 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     }
     bp.stages = S1;
     set_attrs();
-    const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
     const size_t smem1 = (size_t)S1 * stage1 + 256;
+    if (!pair) {
+        const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
+        if (!trans) {
+            if (mode == 0) tc_branch_kernel<0, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            else tc_branch_kernel<1, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        } else {
+            if (mode == 0) tc_branch_kernel<0, 1, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            else tc_branch_kernel<1, 1, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        }
+        return PHX_OK;
+    }
+    // CTA pairs: clusters of two along x
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * ((pl.mtiles + 1) / 2) * (pl.ks_p + pl.ks_s));
+    cfg.blockDim = dim3(K1_THREADS);
+    cfg.dynamicSmemBytes = smem1;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e;
     if (!trans) {
-        if (mode == 0) tc_branch_kernel<0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
-        else tc_branch_kernel<1, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        e = mode == 0 ? cudaLaunchKernelEx(&cfg, tc_branch_kernel<0, 0, 1>, bp)
+                      : cudaLaunchKernelEx(&cfg, tc_branch_kernel<1, 0, 1>, bp);
     } else {
-        if (mode == 0) tc_branch_kernel<0, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
-        else tc_branch_kernel<1, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        e = mode == 0 ? cudaLaunchKernelEx(&cfg, tc_branch_kernel<0, 1, 1>, bp)
+                      : cudaLaunchKernelEx(&cfg, tc_branch_kernel<1, 1, 1>, bp);
+    }
+    if (e != cudaSuccess) {
+        phx_set_error("tc branch pair launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
     }
     return PHX_OK;
 }
@@ -898,7 +1062,7 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
 int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, const float* ascale, const float* bimg,
                   const float* fin_aux, float* out_plain, float* out_img, float* out_timg, float* spart,
                   cudaStream_t st) {
-    const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 128);
+    const int Hp = phx_Hp(H), K2 = 2 * Hp, Hn = phx_tc_Hn(H), Bpad = phx_round_up(B, 256);
     PhxTcBranchPlan pl;
     int rc = launch_branch_mma(mode, 0, G, H, B, nterms, src, ascale, bimg, spart, &pl, st);
     if (rc != PHX_OK) return rc;
@@ -987,14 +1151,16 @@ int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const floa
     PhxTcBranchPlan pl;
     int rc = launch_branch_mma(1, 1, G, H, B, nterms, g, decay ? w.relum : nullptr, sc.sptimg, sc.gslots, &pl, st);
     if (rc != PHX_OK) return rc;
-    tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(1, G, pl.mtiles * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
+    tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(1, G, phx_round_up(pl.mtiles, 2) * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
                                                  grads + off.Wa, nullptr, accumulate);
     rc = launch_branch_mma(0, 1, G, H, B, nterms, y, nullptr, sc.gstimg, sc.gslots, &pl, st);
     if (rc != PHX_OK) return rc;
-    tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(0, G, pl.mtiles * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
+    tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(0, G, phx_round_up(pl.mtiles, 2) * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
                                                  grads + off.Ws, grads + off.Wp, accumulate);
     return check_launch("tc vjp_params");
 }
+
+extern "C" void phx_tc_set_pair(int on) { g_pair = on ? 1 : 0; }
 
 extern "C" void phx_tc_prof_dump(void) {
     if (!g_prof) return;

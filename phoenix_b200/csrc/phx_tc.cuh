@@ -104,8 +104,8 @@ static inline PhxTcBranchPlan phx_tc_branch_plan(int G, int B) {
 // scratch of the tensor-core RHS in floats (partial-sum slots + [S|P] operand image), 128-byte aligned inside
 static inline size_t phx_tc_scratch_floats(int G, int H, int B) {
     const PhxTcBranchPlan pl = phx_tc_branch_plan(G, B);
-    const size_t Bpad = (size_t)phx_round_up(B, 128);
+    const size_t Bpad = (size_t)phx_round_up(B, 256);   // 128-row tiles, paired
     const PhxTcBranchPlan pg = phx_tc_branch_plan(B, G);   // K = batch contractions (parameter cotangents)
     return (size_t)pl.slots * Bpad * 2 * phx_tc_Hn(H) + 2 * phx_tc_spimg_floats(H, B) + 2 * phx_tc_timg_floats(H, B) +
-           (size_t)pg.slots * pg.mtiles * 128 * 2 * phx_tc_Hn(H) + 64;
+           (size_t)pg.slots * phx_round_up(pg.mtiles, 2) * 128 * 2 * phx_tc_Hn(H) + 64;
 }

@@ -32,6 +32,7 @@ class _State:
 
 
 _state = _State()
+_last_rhs = {}   # rhs workspace data_ptr -> signature of the phx_rhs_forward call whose [S|P] it still holds
 
 
 def set_sync_errors(flag):
@@ -84,6 +85,8 @@ def _workspace(dev, nbytes, tag):
     ws = tls.workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=torch.device("cuda", dev))
+        if tag == "rhs":
+            _last_rhs.clear()   # a new buffer holds nothing (and a freed one may come back at the same address)
         if tag == "solve":
             # the resident solvers keep their inter-CTA exchange area at the start of the workspace: zero it once
             lib = _lib.load()
@@ -235,6 +238,13 @@ def _steplog():
 
 
 # ---- RHS -----------------------------------------------------------------------------------------------------------------
+def _rhs_signature(net, packed, y2, B):
+    key = _pack_cache.get(net)
+    prec = _lib.load().phx_ctx_get_precision(_lib.ctx(_device_index(y2)))
+    return (packed.data_ptr(), key[0] if key is not None else None, y2.data_ptr(), y2._version, tuple(y2.shape), B,
+            prec)
+
+
 def rhs_forward(net, y, decay):
     packed, G, H, dev = packed_weights(net)
     if y.shape[-1] != G:
@@ -247,6 +257,8 @@ def rhs_forward(net, y, decay):
     ws = _workspace(dev, nb, "rhs")
     _lib.check(lib.phx_rhs_forward(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(f), int(decay), _ptr(ws),
                                    ws.numel(), _stream_ptr(dev)), "rhs_forward")
+    with _state.lock:
+        _last_rhs[ws.data_ptr()] = _rhs_signature(net, packed, y2, B)
     return f
 
 
@@ -261,8 +273,12 @@ def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True):
     grads = torch.empty(P, dtype=torch.float32, device=y2.device) if need_grads else None
     nb = lib.phx_rhs_workspace_bytes(G, H, B)
     ws = _workspace(dev, nb, "rhs")
+    # the workspace still holds [S|P] of the forward call on exactly these weights and this y (training_step: prior
+    # forward, then composed_loss.backward()): tell the library not to recompute it
+    with _state.lock:
+        reuse = _last_rhs.pop(ws.data_ptr(), None) == _rhs_signature(net, packed, y2, B)
     _lib.check(lib.phx_rhs_vjp(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(g2), int(decay), _ptr(ybar),
-                               _ptr(grads), 0, _ptr(ws), ws.numel(), _stream_ptr(dev)), "rhs_vjp")
+                               _ptr(grads), 2 if reuse else 0, _ptr(ws), ws.numel(), _stream_ptr(dev)), "rhs_vjp")
     return ybar, (split_flat_grads(grads, G, H) if need_grads else None)
 
 

@@ -182,3 +182,58 @@ def test_wide_hidden_layer_falls_back_to_fp32_contractions(pb):
     with torch.no_grad():
         f = net(None, y.cuda())
     assert rel_l2(f.cpu(), O.rhs(w, y)) < 1e-5
+
+
+def test_vjp_reuses_forward_activations_only_when_they_are_still_there(pb):
+    """engine.rhs_vjp skips the [S|P] recomputation when the workspace still holds the forward of the same (weights, y);
+    an intervening forward on other data, or a weight update, must invalidate that."""
+    G, H, B = 350, 40, 200
+    w = O.make_weights(G, H, 24, dense=True)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(10)
+    y1, y2 = torch.rand(B, G, generator=gen), torch.rand(B, G, generator=gen)
+    g = torch.randn(B, G, generator=gen)
+    _, ybar_ref, pbar_ref = O.rhs_vjp(w, y1, g, decay=True)
+
+    def check(yg):
+        assert rel_l2(yg.grad.cpu(), ybar_ref) < 1e-5
+        for p, ref in zip(net.parameters(), pbar_ref):
+            assert rel_l2(p.grad.cpu(), ref) < 2e-5
+
+    # plain forward -> backward (reuse path)
+    net.zero_grad()
+    a = y1.cuda().requires_grad_(True)
+    net(None, a).backward(g.cuda())
+    check(a)
+    # another forward in between overwrites the workspace: the first graph's backward must recompute
+    net.zero_grad()
+    a = y1.cuda().requires_grad_(True)
+    fa = net(None, a)
+    with torch.no_grad():
+        net(None, y2.cuda())
+    fa.backward(g.cuda())
+    check(a)
+    # two graphs alive at once, backward in creation order
+    net.zero_grad()
+    a, b = y1.cuda().requires_grad_(True), y2.cuda().requires_grad_(True)
+    fa, fb = net(None, a), net(None, b)
+    fa.backward(g.cuda())
+    check(a)
+
+
+def test_cta_pair_variant_is_bit_identical(pb):
+    """Experimental cta_group::2 form of the branch-type contractions (off by default): same accumulation order."""
+    from phoenix_b200 import _lib
+    G, H, B = 1001, 100, 300
+    w = O.make_weights(G, H, 25, dense=True)
+    net = make_net(pb, w)
+    y = torch.rand(B, G, generator=torch.Generator().manual_seed(12)).cuda()
+    lib = _lib.load()
+    with torch.no_grad():
+        f0 = net(None, y).clone()
+        lib.phx_tc_set_pair(1)
+        try:
+            f1 = net(None, y).clone()
+        finally:
+            lib.phx_tc_set_pair(0)
+    assert torch.equal(f0, f1)
