@@ -110,11 +110,13 @@ __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence:
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 
 // shared-memory matrix descriptor, K-major, no swizzle (cute::UMMA::SmemDescriptor bit layout; version 1 = sm_100)
-__device__ __forceinline__ uint64_t smem_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes) {
+__device__ __forceinline__ uint64_t smem_desc(unsigned saddr, unsigned lbo_bytes, unsigned sbo_bytes,
+                                              unsigned layout_type = 0) {
     uint64_t d = (uint64_t)((saddr >> 4) & 0x3fffu);
     d |= (uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16;
     d |= (uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32;
     d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout_type & 7u) << 61;   // 0 no swizzle, 2 SWIZZLE_128B, 4 SWIZZLE_64B, 6 SWIZZLE_32B
     return d;
 }
 // instruction descriptor: D fp32, A/B tf32, both K-major, M x N  (cute::UMMA::InstrDescriptor bit layout)
@@ -198,7 +200,7 @@ __global__ void tc_pack_kernel(int G, int H, int Hp, int K2, int Hn, const float
         split_tf32(v, hi, lo);
         const int kb = g / BK, k = g % BK;
         const size_t co = (size_t)kb * 4 * Hn * BK + (size_t)br * 2 * Hn * BK;
-        const int off = phx_tc_tile_off(Hn, n, k);
+        const int off = phx_tc_btile_off(Hn, n, k);
         w1img[co + off] = hi;
         w1img[co + Hn * BK + off] = lo;
         split_tf32(vt, hi, lo);
@@ -309,7 +311,7 @@ __device__ __forceinline__ uint64_t desc_at(uint64_t hi_part, unsigned saddr) {
 // completion come back to both CTAs by multicast tcgen05.commit.
 template <int MODE, int TRANS, int PAIR>
 __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p) {
-    extern __shared__ __align__(128) unsigned char smem[];
+    extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // work item: branch, 128-row tile (PAIR: tile pair), K range (a whole number of chunks)
     int blk = PAIR ? blockIdx.x >> 1 : blockIdx.x;
@@ -364,7 +366,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         const float* src = TRANS ? p.y + row : p.y + (size_t)row * p.ld;
         const bool rok = row < p.B;
         const float rscale = (MODE && TRANS && p.ascale && rok) ? __ldg(p.ascale + row) : 1.f;
-        const unsigned a_off = (unsigned)(((kc * 16 + (rl >> 3)) * 8 + (rl & 7)) * 16);
+        const unsigned a_off = (unsigned)phx_tc_btile_off(128, rl, kc * 4) * 4u;
         // y is read in super-blocks of K1_PF k-blocks: all loads of the NEXT super-block (K1_PF x 64 contiguous bytes
         // of this thread's row, requested back to back with a 256-byte L2 prefetch hint so that DRAM sees whole
         // bursts of one page) are in flight while the current super-block is converted and handed to the MMAs.
@@ -462,8 +464,15 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     // tile is 2 (hi|lo) x 4 (k-chunks) pieces of Hn/16 core matrices
                     mbar_expect_tx(full0 + 8 * s, b_bytes);
                     const float* chunk = p.w1img + ((size_t)(kb0 + i) * 4 + 2 * br) * Hn * BK;
-                    const unsigned piece = (unsigned)(Hn >> 4) * 128u;
                     const unsigned dst0 = stage0 + s * stage_bytes + K1_A_BYTES;
+#if PHX_TC_BRANCH_SW64
+                    // rows are 64 contiguous bytes: this CTA's half of a tile is one contiguous piece
+#pragma unroll
+                    for (int hl = 0; hl < 2; ++hl)
+                        bulk_g2s(dst0 + hl * b_tile, chunk + (size_t)hl * Hn * BK + (size_t)crank * Hb * BK, b_tile,
+                                 full0 + 8 * s);
+#else
+                    const unsigned piece = (unsigned)(Hn >> 4) * 128u;
 #pragma unroll
                     for (int hl = 0; hl < 2; ++hl)
 #pragma unroll
@@ -471,6 +480,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                             bulk_g2s(dst0 + hl * b_tile + kc4 * piece,
                                      chunk + (size_t)hl * Hn * BK + ((size_t)kc4 * (Hn >> 3) + crank * (Hn >> 4)) * 32,
                                      piece, full0 + 8 * s);
+#endif
                 }
                 if (++s == S) {
                     s = 0;
@@ -483,7 +493,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         // elected lane issues the tcgen05 instructions.  In a pair only the leader issues; the peer's warp relays
         // "my half of B has landed" to the leader's full barrier. ----
         const unsigned idesc = idesc_tf32(PAIR ? 256 : 128, Hn);
-        const uint64_t a_hi_part = smem_desc(0, p.a_lbo, p.a_sbo), b_hi_part = smem_desc(0, p.b_lbo, p.b_sbo);
+        const unsigned lt = PHX_TC_BRANCH_SW64 ? 4u : 0u;
+        const uint64_t a_hi_part = smem_desc(0, p.a_lbo, p.a_sbo, lt), b_hi_part = smem_desc(0, p.b_lbo, p.b_sbo, lt);
         int s = 0, c = 0, ic = 0;
         unsigned ph = 0;
         long long t_full = 0, t_drained = 0, t0 = clock64();
@@ -674,7 +685,7 @@ __global__ void tc_spfinish_kernel(int B, int Bpad, int H, int Hp, int Hn, int K
             float* tch = timg + ((size_t)(b / BK) * 4 + 2 * br) * Hn * BK;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int o = phx_tc_tile_off(Hn, n0 + j, b % BK);
+                const int o = phx_tc_btile_off(Hn, n0 + j, b % BK);
                 tch[o] = hi[j];
                 tch[Hn * BK + o] = lo[j];
             }
@@ -997,8 +1008,13 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     bp.nterms = nterms; bp.dbg = dbg; bp.mode = mode; bp.ascale = ascale;
     bp.mtiles = pl.mtiles; bp.ks_p = pl.ks_p; bp.per_p = pl.per_p; bp.ks_s = pl.ks_s; bp.per_s = pl.per_s;
     const int Hb = pair ? Hn / 2 : Hn;   // B rows staged per CTA
+#if PHX_TC_BRANCH_SW64
+    bp.a_lbo = 16; bp.a_sbo = 512; bp.b_lbo = 16; bp.b_sbo = 512;   // 8-row x 64-byte atoms; LBO unused when swizzled
+    bp.a_kadv = 32; bp.b_kadv = 32;                                  // K = 8 floats further inside the 64-byte row
+#else
     bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hb / 8) * 128; bp.b_sbo = 128;
     bp.a_kadv = 2 * bp.a_lbo; bp.b_kadv = 2 * bp.b_lbo;
+#endif
     if (dbg & 1) {   // diagnostic: swapped meaning of the two descriptor offsets
         unsigned t = bp.a_lbo; bp.a_lbo = bp.a_sbo; bp.a_sbo = t;
         t = bp.b_lbo; bp.b_lbo = bp.b_sbo; bp.b_sbo = t;

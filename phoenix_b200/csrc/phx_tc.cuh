@@ -64,6 +64,20 @@ static inline __host__ __device__ size_t phx_tc_timg_floats(int H, int B) {
 static inline __host__ __device__ int phx_tc_tile_off(int R, int r, int k) {
     return ((((k >> 2) * (R >> 3) + (r >> 3)) * 8 + (r & 7)) << 2) + (k & 3);
 }
+// Operands of the branch-type kernel (tc_branch_kernel): -DPHX_TC_BRANCH_SW64=1 selects the K-major SWIZZLE_64B
+// canonical layout instead (rows of 16 floats = 64 bytes, 8-row x 64-byte atoms, the 16-byte chunk index XORed with
+// bits 1-2 of the row).  Measured on B200: identical results and identical speed (0.79 ms per RHS evaluation at
+// 20 000 x 200 x 4 096 either way), so the default stays the no-swizzle core-matrix layout above.
+#ifndef PHX_TC_BRANCH_SW64
+#define PHX_TC_BRANCH_SW64 0
+#endif
+static inline __host__ __device__ int phx_tc_btile_off(int R, int r, int k) {
+#if PHX_TC_BRANCH_SW64
+    return r * 16 + ((((k >> 2) ^ ((r >> 1) & 3))) << 2) + (k & 3);
+#else
+    return phx_tc_tile_off(R, r, k);
+#endif
+}
 
 // Accumulation-chain limit of the branch contraction: k-blocks summed inside tensor memory before the chunk sum is
 // drained to its own partial-sum slot (phx_tc.cu, "Accumulation chains").  16 k-blocks = 96 accumulating MMAs.
