@@ -1,19 +1,27 @@
-// Tensor-core path of the batched RHS (ODENet.forward / prior_only_forward, odenet.py:85-98) for B >= 128 rows:
-// hand-written tcgen05.mma (kind::tf32, 3xTF32 split for fp32 parity) with accumulators in tensor memory, operands
-// staged by 1-D TMA bulk copies and -- for the Hill activations -- by producer warps that compute them on the fly.
-// Layouts: phx_tc.cuh.  Three launches per RHS evaluation:
+// Tensor-core path of the batched RHS and of its VJP (ODENet.forward / prior_only_forward, odenet.py:85-98, and what
+// torch.autograd computes through them) for every call beyond the resident solver kernels' capacity (B >= 5 rows):
+// hand-written tcgen05.mma (kind::tf32, 3xTF32 split for fp32 parity) with accumulators in tensor memory, operands staged
+// by 1-D TMA bulk copies and -- for everything derived from y or from the cotangent -- by producer warps that compute
+// it on the fly.  Layouts: phx_tc.cuh.  Two MMA kernels, each in a few compile-time modes, plus small finishing passes:
 //
-//   tc_branch_kernel   [S|P]partial = act(y) W1        M = 128 batch rows per CTA, N = 2 x Hn (both branches, so each
-//                      y element's soft-sign / log1p is computed exactly once), K = a slice of the genes (K-split so
-//                      that ~148 CTAs are busy).  Warps 0-7 load y, evaluate s(y), l(y), split hi/lo and write the four
-//                      A tiles of a stage; warp 8 streams the matching w1img chunk with cp.async.bulk; warp 9 issues
-//                      the MMAs; warps 0-7 then read the accumulators back (tcgen05.ld) and store the partial sums.
-//   tc_spfinish_kernel sums the K-split partials in fixed order, adds the bias, exponentiates the prods half, writes the
-//                      plain [B][K2] copy (VJP / parity) and the hi|lo operand image of the next contraction.
-//   tc_joint_kernel    f^T tile = WA [S|P]^T           persistent, M = 128 genes, N = 256 batch rows, K = 2*Hn, double-
-//                      buffered TMEM accumulators; both operands arrive by bulk copy (warp 0), warp 1 issues MMAs,
-//                      warps 2-5 run the epilogue f = fscale * relu(m) * (J - y) straight out of tensor memory: lanes
-//                      are genes, so every global access of the epilogue is a coalesced 128-byte row segment.
+//   tc_branch_kernel<MODE, TRANS, PAIR>   "A(src) x image^T", M = 128 rows per CTA, N = Hn columns of ONE half
+//       (sums | prods) of the 2*Hn-wide result, K split over CTAs, accumulation in chunks of 16 k-blocks folded into a
+//       tensor-memory running sum by drain warps (see "Accumulation chains" below).  704 threads: 16 producer warps,
+//       1 bulk-copy warp, 1 MMA-issue warp (uniform control flow + elect.sync), 4 drain warps.
+//         <0,0>  [S|P] partial  = act(y) W1          rows = batch, k = genes, A = soft-sign / log1p of y by half
+//         <1,0>  gSP partial    = (g relu(m)) WA     rows = batch, k = genes, A = cotangent x per-gene factor
+//         <1,1>  Wa_bar partial = (g relu(m))^T [S|P]   rows = genes, k = batch rows (transposed loads: lanes along genes)
+//         <0,1>  Ws_bar | Wp_bar partial = act(y)^T gSP  rows = genes, k = batch rows
+//       PAIR = 1 is the experimental cta_group::2 form (off by default).
+//   tc_spfinish_kernel    fixed-order sum of the K-split partials; mode 0: + bias, exp on the prods half -> [S|P];
+//       mode 1: prods half x Pr -> gSP; writes the plain [B][K2] copy and the hi|lo operand images of the consumers.
+//   tc_gradfinish_kernel  the same for the parameter cotangents, scattered into the flat gradient vector.
+//   tc_joint_kernel<EMODE>   "image_A x image_B^T" with both operands by bulk copy: persistent, M = 128 genes,
+//       N = 256 batch rows, 4-stage ring, double-buffered TMEM accumulators, 8 epilogue warps working straight out of
+//       tensor memory (lanes are genes => every global access of the epilogue is a coalesced 128-byte row segment).
+//         <0>  f = fscale * relu(m) * ([S|P] WA^T - y)   (or the un-decayed joint)        odenet.py:89-90
+//         <1>  u = gS Ws                                    (k-blocks of the sums half)
+//         <2>  ybar = (u + (gP Wp)/(1+s)) / (1+|y-.5|)^2 - g relu(m)    soft-sign / log1p backward in the epilogue
 //
 // Every accumulation order is fixed (MMA issue order, K-split reduction order) => results are run-to-run identical.
 #include <stdint.h>
