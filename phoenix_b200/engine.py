@@ -369,6 +369,44 @@ def _t_rows(t_rows):
     return [(ctypes.c_double * len(r))(*r) for r in t_rows]
 
 
+_MANY_MAX_STREAMS = 8
+_side_streams = {}
+
+
+def _concurrency(lib, dev, G, H, B, adjoint, engine, n_problems):
+    """How many of the independent solves can run side by side: a resident solve of a small model occupies only
+    ceil(G / 16) of the SMs (22 CTAs at 350 genes, 44 at 690), so several persistent launches fit on the GPU at once --
+    each on its own stream with its own workspace.  Genome-scale models fill the GPU by themselves (1)."""
+    if engine != "resident" or n_problems < 2:
+        return []
+    out = (ctypes.c_int32 * 8)()
+    num_sms = lib.phx_ctx_num_sms(_lib.ctx(dev))
+    if lib.phx_plan_describe(num_sms, G, H, B, int(adjoint), out) != _lib.PHX_OK:
+        return []
+    k = min(num_sms // max(1, out[0]), _MANY_MAX_STREAMS, n_problems)
+    if k < 2:
+        return []
+    pool = _side_streams.setdefault(dev, [])
+    while len(pool) < k:
+        pool.append(torch.cuda.Stream(device=dev))
+    return pool[:k]
+
+
+def _fan_out(dev, streams):
+    ev = torch.cuda.Event()
+    ev.record(torch.cuda.current_stream(dev))
+    for st in streams:
+        st.wait_event(ev)
+
+
+def _fan_in(dev, streams):
+    main = torch.cuda.current_stream(dev)
+    for st in streams:
+        ev = torch.cuda.Event()
+        ev.record(st)
+        main.wait_event(ev)
+
+
 def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_steps):
     """y0 ``[N, *S, G]``: N independent problems, problem i integrated over its own times ``t_rows[i]`` (all of length
     T).  Every problem is one resident launch with its own step controller -- exactly the reference's per-sample call
@@ -392,14 +430,28 @@ def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_st
     ybase, obase = y0c.data_ptr(), yout.data_ptr()
     ystride, ostride = y0c[0].numel() * 4, yout[0].numel() * 4
     tarr = _t_rows(t_rows)
+    streams = _concurrency(lib, dev, G, H, B, False, engine, N)
+    if streams:
+        _fan_out(dev, streams)
     for i in range(N):
         st = _new_status()
         log, cap = _steplog()
+        if streams:
+            with torch.cuda.stream(streams[i % len(streams)]):
+                wsi = _workspace(dev, nb, "solve")
+                rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
+                        float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride),
+                        _ptr(wsi), wsi.numel(), _ptr(st), _ptr(log), cap, _stream_ptr(dev))
+                _lib.check(rc, "solve_forward")
+                _finish(st, "forward solve %d" % i, dev)
+            continue
         rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
                 float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride), wsp, wsn,
                 _ptr(st), _ptr(log), cap, sp)
         _lib.check(rc, "solve_forward")
         _finish(st, "forward solve %d" % i, dev)
+    if streams:
+        _fan_in(dev, streams)
     return yout
 
 
@@ -425,17 +477,32 @@ def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps,
     stride = ys[0].numel() * 4
     astride = adj_y0[0].numel() * 4
     tarr = _t_rows(t_rows)
+    streams = _concurrency(lib, dev, G, H, B, True, engine, N)
     for lo in range(0, N, chunk):
         hi = min(N, lo + chunk)
+        if streams:
+            _fan_out(dev, streams)
         for i in range(lo, hi):
             st = _new_status()
             log, cap = _steplog()
-            rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
-                    ctypes.c_void_p(ys.data_ptr() + i * stride), ctypes.c_void_p(gy.data_ptr() + i * stride),
+            args = (ctypes.c_void_p(ys.data_ptr() + i * stride), ctypes.c_void_p(gy.data_ptr() + i * stride),
                     ctypes.c_void_p(adj_y0.data_ptr() + i * astride),
-                    ctypes.c_void_p(grads.data_ptr() + (i - lo) * P * 4), wsp, wsn, _ptr(st), _ptr(log), cap, sp)
+                    ctypes.c_void_p(grads.data_ptr() + (i - lo) * P * 4))
+            if streams:
+                with torch.cuda.stream(streams[i % len(streams)]):
+                    wsi = _workspace(dev, nb, "solve")
+                    rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol),
+                            int(max_num_steps), *args, _ptr(wsi), wsi.numel(), _ptr(st), _ptr(log), cap,
+                            _stream_ptr(dev))
+                    _lib.check(rc, "solve_adjoint")
+                    _finish(st, "adjoint solve %d" % i, dev)
+                continue
+            rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
+                    *args, wsp, wsn, _ptr(st), _ptr(log), cap, sp)
             _lib.check(rc, "solve_adjoint")
             _finish(st, "adjoint solve %d" % i, dev)
+        if streams:
+            _fan_in(dev, streams)
         part = grads[:hi - lo].sum(dim=0)
         total = part if total is None else total + part
     return adj_y0, split_flat_grads(total, G, H)
