@@ -136,6 +136,8 @@ def test_resident_plan_places_the_weight_slices():
     assert plan(350, 40, 9, 0)[0] != 0
     assert plan(350, 40, 5, 1)[0] != 0
     assert plan(350, 300, 1, 0)[0] != 0
-    # tiny problems use few CTAs (cheap exchanges): at least 16 genes per CTA
+    # small problems use few CTAs (cheap exchanges, room for concurrent solves): >= 16 genes per CTA, 32 from 256 genes
     rc, p = plan(37, 5, 1, 0)
     assert rc == 0 and p["ctas"] == 3 and p["gpc"] == 16
+    rc, p = plan(690, 40, 1, 1)
+    assert rc == 0 and p["ctas"] == 22 and p["gpc"] == 32
