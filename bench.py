@@ -10,7 +10,8 @@ ODENet(ndim=11165, neurons=200); one step = one training-step batch of the hot p
 Synthetic expression values U[0,1), weights with the reference init distribution (odenet.py:61-75).
 
 metric  gene-steps/s = B * G * (RHS evals forward + RHS-VJP evals adjoint) / time, evaluations counted by the solver.
-value   device-resident inputs, C-ABI calls (phx_solve_forward / phx_solve_adjoint) issued back to back.
+value   device-resident inputs, C-ABI calls (phx_solve_forward_many / phx_solve_adjoint_many, 8 samples per persistent
+        launch, every sample its own solve) issued back to back.
 e2e     the same step through the public Python API from pinned HOST buffers, H2D of the samples and D2H of the loss
         inside the timed region: phoenix_b200.odeint_adjoint_many (the per-sample loop of training_step as one call,
         identical solves) + backward; the literal per-sample loop over phoenix_b200.odeint_adjoint is timed beside it
@@ -231,25 +232,32 @@ def run_ours(args):
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     adj_ev = []
 
+    # the 17 independent samples go through the multi-problem entry points 8 at a time (N * T <= 16 output times per
+    # launch): every sample is its own solve with its own step controller, the weights are staged on chip once per launch
+    PER = 8
+    chunks = [(lo, min(PER, BATCH - lo)) for lo in range(0, BATCH, PER)]
+    tflat = {lo: (ctypes.c_double * (2 * n))(*[x for i in range(lo, lo + n) for x in tl[i]]) for lo, n in chunks}
+
     def step_resident(record):
-        for i in range(BATCH):
-            rc = lib.phx_solve_forward(ctx, G, H, 1, ptr(packed), ptr(y0_d[i]), tarr[i], 2, 1, 0, mid, 1e-7, 1e-9,
-                                       2 ** 31 - 1, ptr(yout[i]), ptr(ws_f), ws_f.numel(), ptr(st_f[i]), None, 0, sp)
-            _lib.check(rc, "solve_forward")
+        for lo, n in chunks:
+            rc = lib.phx_solve_forward_many(ctx, G, H, 1, n, ptr(packed), ptr(y0_d[lo]), tflat[lo], 2, 1, mid, 1e-7,
+                                            1e-9, 2 ** 31 - 1, ptr(yout[lo]), ptr(ws_f), ws_f.numel(), ptr(st_f[lo]),
+                                            sp)
+            _lib.check(rc, "solve_forward_many")
         # d loss / d y(t1) for loss = mean((pred - target)^2) over the batch (train_insilico.py:132)
         torch.sub(yout[:, 1], target_d, out=grad_y[:, 1])
         grad_y[:, 1].mul_(2.0 / (BATCH * G))
-        for i in range(BATCH):
+        for lo, n in chunks:
             if record:
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record(stream)
-            rc = lib.phx_solve_adjoint(ctx, G, H, 1, ptr(packed), tarr[i], 2, 1, mid, 1e-7, 1e-9, 2 ** 31 - 1,
-                                       ptr(yout[i]), ptr(grad_y[i]), ptr(adj_y0[i]), ptr(grads[i]), ptr(ws_a),
-                                       ws_a.numel(), ptr(st_a[i]), None, 0, sp)
-            _lib.check(rc, "solve_adjoint")
+            rc = lib.phx_solve_adjoint_many(ctx, G, H, 1, n, ptr(packed), tflat[lo], 2, 1, mid, 1e-7, 1e-9,
+                                            2 ** 31 - 1, ptr(yout[lo]), ptr(grad_y[lo]), ptr(adj_y0[lo]),
+                                            ptr(grads[lo]), ptr(ws_a), ws_a.numel(), ptr(st_a[lo]), sp)
+            _lib.check(rc, "solve_adjoint_many")
             if record:
                 e1.record(stream)
-                adj_ev.append((e0, e1))
+                adj_ev.append((e0, e1, n))
         torch.sum(grads, dim=0, out=gsum)                # autograd's accumulation of the per-sample .grad
         if world > 1:
             dist.all_reduce(gsum)
@@ -282,7 +290,7 @@ def run_ours(args):
             raise SystemExit("solver status non-zero: %s %s" % (st_f[i, :5].tolist(), st_a[i, :5].tolist()))
     n_attempts = sum(int(st_a[i, 1]) + int(st_a[i, 2]) for i in range(BATCH)) / BATCH
     n_vjp = sum(int(st_a[i, 3]) for i in range(BATCH)) / BATCH
-    adj_ms = sum(a.elapsed_time(b) for a, b in adj_ev) / len(adj_ev)
+    adj_ms = sum(a.elapsed_time(b) for a, b, _ in adj_ev) / sum(n for _, _, n in adj_ev)   # per problem
 
     # ---- end-to-end leg: reference-facing Python API from pinned host buffers ------------------------------
     y0_p, target_p = y0_h.pin_memory(), target_h.pin_memory()
@@ -383,10 +391,11 @@ def run_ours(args):
                            "loss.backward(), pinned host inputs",
                     "per_sample_api_value": work_per_step / (ms_e2e_loop / args.steps / 1e3),
                     "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130"},
-            "gpu_launches": args.steps * BATCH * 2,
+            "gpu_launches": args.steps * len(chunks) * 2,
             "roofline": {"bound": "hbm", "kernel": "phx_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "launch_ms": adj_ms, "algorithmic_bytes": alg,
+                         "per": "one sample's adjoint sweep (a launch holds up to 8)",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650"},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"

@@ -147,6 +147,21 @@ int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, co
                       void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                       int steplog_cap, void* stream);
 
+/* ---- N independent problems per launch (the per-sample loop of training_step, train_insilico.py:128-130) -------- */
+/* Problem i: initial state y0 + i*B*G, its own T increasing times t_host[i*T .. i*T+T), outputs y_out + i*T*B*G, its own
+ * step controller and its own status[i] (an array of N records).  The solves run one after the other inside ONE
+ * persistent launch, so the weights are staged on chip once for all of them; results are bit-identical to N calls of
+ * phx_solve_forward / phx_solve_adjoint.  Limits: the rows fit the resident kernels and N * T <= 16.
+ * Adjoint: y_saved / grad_y are [N][T][B][G], adj_y0 [N][B][G], grads_flat [N][P] (one cotangent vector per problem). */
+int phx_solve_forward_many(phx_ctx* ctx, int G, int H, int B, int N, const float* packed, const float* y0,
+                           const double* t_host, int T, int t_is_f32, int method, double rtol, double atol,
+                           int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
+                           phx_status* status, void* stream);
+int phx_solve_adjoint_many(phx_ctx* ctx, int G, int H, int B, int N, const float* packed, const double* t_host, int T,
+                           int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
+                           void* workspace, size_t workspace_bytes, phx_status* status, void* stream);
+
 /* ---- the same two solves for ANY number of rows B (streaming engine) ---------------------------------------- */
 /* phx_solve_forward / phx_solve_adjoint keep the whole solve in one persistent cooperative launch and need the rows
  * to fit on chip (B <= phx_resident_max_rows()).  These variants stream the [B][G] state through HBM and run the

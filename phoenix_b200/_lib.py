@@ -21,7 +21,7 @@ EXPORTS = [
     "phx_ctx_set_precision", "phx_ctx_get_precision", "phx_tc_min_rows",
     "phx_packed_bytes", "phx_pack_weights", "phx_rhs_forward", "phx_rhs_vjp", "phx_rhs_workspace_bytes",
     "phx_solve_workspace_bytes", "phx_solve_workspace_init_bytes", "phx_solve_workspace_init", "phx_solve_forward",
-    "phx_solve_adjoint",
+    "phx_solve_adjoint", "phx_solve_forward_many", "phx_solve_adjoint_many",
     "phx_stream_workspace_bytes", "phx_stream_solve_forward", "phx_stream_solve_adjoint",
 ]
 
@@ -93,6 +93,14 @@ def _declare(lib):
     lib.phx_solve_forward.restype = c_int
     lib.phx_solve_adjoint.argtypes = adj
     lib.phx_solve_adjoint.restype = c_int
+    lib.phx_solve_forward_many.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
+                                           ctypes.POINTER(c_double), c_int, c_int, c_int, c_double, c_double, c_int64,
+                                           c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.phx_solve_forward_many.restype = c_int
+    lib.phx_solve_adjoint_many.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_double), c_int,
+                                           c_int, c_int, c_double, c_double, c_int64, c_void_p, c_void_p, c_void_p,
+                                           c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.phx_solve_adjoint_many.restype = c_int
     lib.phx_stream_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int]
     lib.phx_stream_workspace_bytes.restype = c_size_t
     lib.phx_stream_solve_forward.argtypes = fwd

@@ -235,7 +235,7 @@ int phx_solve_workspace_init(void* workspace, size_t workspace_bytes, void* stre
 static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, const double* t_host, int T,
                         int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps, int adjoint,
                         void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
-                        int steplog_cap, cudaStream_t stream, ResParams* p, ResLaunchPlan* plan) {
+                        int steplog_cap, cudaStream_t stream, ResParams* p, ResLaunchPlan* plan, int nprob = 1) {
     if (!ctx || !check_dims(G, H, B) || !packed || !t_host || !workspace) {
         if (g_err[0] == 0) phx_set_error("null argument");
         return PHX_ERR_INVALID;
@@ -244,12 +244,18 @@ static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, 
         phx_set_error("t must hold at least two time points (got %d)", T);
         return PHX_ERR_INVALID;
     }
-    for (int i = 1; i < T; ++i) {
-        if (!(t_host[i] > t_host[i - 1])) {
-            phx_set_error("t must be strictly increasing at the C boundary (the Python shim negates decreasing t)");
-            return PHX_ERR_INVALID;
-        }
+    if (nprob < 1 || (nprob > 1 && nprob * T > PHX_T_INLINE)) {
+        phx_set_error("a multi-problem launch takes 1 <= N and N * T <= %d output times (got N=%d, T=%d)", PHX_T_INLINE,
+                      nprob, T);
+        return PHX_ERR_INVALID;
     }
+    for (int q = 0; q < nprob; ++q)
+        for (int i = 1; i < T; ++i) {
+            if (!(t_host[q * T + i] > t_host[q * T + i - 1])) {
+                phx_set_error("t must be strictly increasing at the C boundary (the Python shim negates decreasing t)");
+                return PHX_ERR_INVALID;
+            }
+        }
     if (method < PHX_EULER || method > PHX_DOPRI5) {
         phx_set_error("unknown method id %d", method);
         return PHX_ERR_INVALID;
@@ -280,8 +286,9 @@ static int solve_common(phx_ctx* ctx, int G, int H, int B, const float* packed, 
     p->theta1 = adjoint ? ws + o_th : nullptr;
     p->status = status; p->steplog = steplog; p->steplog_cap = steplog ? steplog_cap : 0;
     p->prof = ctx->prof;
-    if (T <= PHX_T_INLINE) {
-        for (int i = 0; i < T; ++i) p->t_small[i] = t_host[i];  // travels with the kernel parameters
+    p->nprob = nprob;
+    if (T * nprob <= PHX_T_INLINE) {
+        for (int i = 0; i < T * nprob; ++i) p->t_small[i] = t_host[i];  // travels with the kernel parameters
         return PHX_OK;
     }
     cudaError_t e = cudaMemcpyAsync((void*)p->t, t_host, sizeof(double) * T, cudaMemcpyHostToDevice, stream);
@@ -330,6 +337,52 @@ int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, co
     p.grad_y = grad_y;
     p.adj_y0 = adj_y0;
     p.theta0 = grads_flat;  // written once by the kernel (never read while still zero): no memset needed
+    return phx_resident_launch(p, plan, (cudaStream_t)stream);
+}
+
+/* ---- several independent problems per launch -------------------------------------------- */
+int phx_solve_forward_many(phx_ctx* ctx, int G, int H, int B, int N, const float* packed, const float* y0,
+                           const double* t_host, int T, int t_is_f32, int method, double rtol, double atol,
+                           int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
+                           phx_status* status, void* stream) {
+    g_err[0] = 0;
+    if (!y0 || !y_out) {
+        phx_set_error("null y0 / y_out");
+        return PHX_ERR_INVALID;
+    }
+    ResParams p;
+    ResLaunchPlan plan;
+    int rc = solve_common(ctx, G, H, B, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 0, workspace,
+                          workspace_bytes, status, nullptr, 0, (cudaStream_t)stream, &p, &plan, N);
+    if (rc != PHX_OK) return rc;
+    p.y0 = y0;
+    p.yout = y_out;
+    p.y0_stride = (long long)B * G;
+    p.yout_stride = (long long)T * B * G;
+    return phx_resident_launch(p, plan, (cudaStream_t)stream);
+}
+
+int phx_solve_adjoint_many(phx_ctx* ctx, int G, int H, int B, int N, const float* packed, const double* t_host, int T,
+                           int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
+                           void* workspace, size_t workspace_bytes, phx_status* status, void* stream) {
+    g_err[0] = 0;
+    if (!y_saved || !grad_y || !adj_y0 || !grads_flat) {
+        phx_set_error("null y_saved / grad_y / adj_y0 / grads_flat");
+        return PHX_ERR_INVALID;
+    }
+    ResParams p;
+    ResLaunchPlan plan;
+    int rc = solve_common(ctx, G, H, B, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 1, workspace,
+                          workspace_bytes, status, nullptr, 0, (cudaStream_t)stream, &p, &plan, N);
+    if (rc != PHX_OK) return rc;
+    p.ysaved = y_saved;
+    p.grad_y = grad_y;
+    p.adj_y0 = adj_y0;
+    p.theta0 = grads_flat;
+    p.yout_stride = (long long)T * B * G;
+    p.adj_stride = (long long)B * G;
+    p.theta_stride = (long long)phx_grad_offsets(G, H).total;
     return phx_resident_launch(p, plan, (cudaStream_t)stream);
 }
 

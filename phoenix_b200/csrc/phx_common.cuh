@@ -210,6 +210,10 @@ struct ResParams {
     float* adj_y0;         // [B][G]
     float* theta0;         // [P] caller's flat grads (result lands here)
     float* theta1;         // [P] scratch twin
+    // several independent problems per launch (phx_solve_*_many): problem i reads / writes base + i * stride (floats),
+    // its output times are t_small[i*T .. i*T+T) and its status record is status[i]; nprob == 1 for the plain calls
+    int nprob;
+    long long y0_stride, yout_stride, adj_stride, theta_stride;
     // workspace
     PhxLL ll;
     phx_status* status;

@@ -103,8 +103,8 @@ struct Prof {
     }
 };
 
-__device__ __forceinline__ double tget(const ResParams& p, int i) {
-    return (p.T <= PHX_T_INLINE) ? p.t_small[i] : p.t[i];
+__device__ __forceinline__ double tget(const ResParams& p, int pi, int i) {
+    return (p.T * p.nprob <= PHX_T_INLINE) ? p.t_small[pi * p.T + i] : p.t[pi * p.T + i];
 }
 
 __device__ __forceinline__ float warp_sum(float v) {
@@ -1255,17 +1255,18 @@ __device__ __forceinline__ float interp_eval(float y0, float y1, float ymid, flo
     return total;
 }
 
-__device__ void write_status(const ResParams& p, const Ctrl* c, int code) {
+__device__ void write_status(const ResParams& p, int pi, const Ctrl* c, int code) {
     if (blockIdx.x == 0 && threadIdx.x == 0 && p.status) {
-        p.status->n_accepted = c->n_acc;
-        p.status->n_rejected = c->n_rej;
-        p.status->n_rhs = c->n_rhs;
-        p.status->n_logged = min(c->n_log, p.steplog_cap);
-        p.status->reserved = 0;
-        p.status->t_fail = c->tcur;
-        p.status->dt_fail = c->dt;
+        phx_status* st = p.status + pi;
+        st->n_accepted = c->n_acc;
+        st->n_rejected = c->n_rej;
+        st->n_rhs = c->n_rhs;
+        st->n_logged = min(c->n_log, p.steplog_cap);
+        st->reserved = 0;
+        st->t_fail = c->tcur;
+        st->dt_fail = c->dt;
         __threadfence_system();
-        p.status->code = code;
+        st->code = code;
     }
 }
 
@@ -1341,10 +1342,14 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     float* Y1 = s.st() + BL;
     auto K = [&](int i) { return s.st() + (2 + i) * BL; };
 
+    // independent problems, one after the other: the weights stay on chip (shared / tensor memory) across them
+    for (int pi = 0; pi < p.nprob; ++pi) {
+    const float* y0p = p.y0 + (size_t)pi * p.y0_stride;
+    float* youtp = p.yout + (size_t)pi * p.yout_stride;
     if (threadIdx.x == 0) {
         c->n_acc = c->n_rej = c->n_rhs = c->n_log = 0;
         c->stop = 0;
-        c->tcur = tget(p, 0);
+        c->tcur = tget(p, pi, 0);
         c->dt = 0;
         for (int i = 0; i < 7; ++i) c->slot[i] = i;
     }
@@ -1356,9 +1361,9 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
         s.actl()[li] = lv;
     };
     for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
-        float y = p.y0[gi];
+        float y = y0p[gi];
         Y[li] = y;
-        p.yout[gi] = y;
+        youtp[gi] = y;
         set_stage_input(li, y);
     });
     __syncthreads();
@@ -1368,8 +1373,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
         const float third = (float)(1.0 / 3.0);
         eval_A<NV, BT>(p, s);
         for (int i = 0; i + 1 < p.T; ++i) {
-            const float dtf = p.t_is_f32 ? ((float)tget(p, i + 1) - (float)tget(p, i)) : (float)(tget(p, i + 1) - tget(p, i));
-            float* yo = p.yout + (size_t)(i + 1) * BG;
+            const float dtf = p.t_is_f32 ? ((float)tget(p, pi, i + 1) - (float)tget(p, pi, i)) : (float)(tget(p, pi, i + 1) - tget(p, pi, i));
+            float* yo = youtp + (size_t)(i + 1) * BG;
             const bool more = i + 2 < p.T;   // another interval follows: its first pass A is fused into the last stage
             // one call site for every stage of every fixed-grid method (the stage algebra switches at run time)
             const int nst = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
@@ -1400,16 +1405,14 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
         if (threadIdx.x == 0) {
             int per = (p.method == PHX_EULER) ? 1 : (p.method == PHX_MIDPOINT ? 2 : 4);
             c->n_rhs = per * (p.T - 1);
-            c->tcur = tget(p, p.T - 1);
+            c->tcur = tget(p, pi, p.T - 1);
         }
         __syncthreads();
         ring_drain(p, s);
         pf.tick(PT_CTRL);
-        pf.finish();
-        tmem_release(p, s.tmem);
-    epilogue_epoch(p, s);
-        write_status(p, c, PHX_ST_OK);
-        return;
+        write_status(p, pi, c, PHX_ST_OK);
+        __syncthreads();
+        continue;
     }
 
     // ---- dopri5 (rk_common.py:111-228) ----
@@ -1541,10 +1544,10 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
         __syncthreads();
         if (c->accept) {
             // emit every pending output inside (tprev, tcur] from the quartic interpolant (rk_common.py:157)
-            while (next_out < p.T && tget(p, next_out) <= c->tcur) {
-                if (threadIdx.x == 0) set_interp_x(c, tget(p, next_out), c->tprev, c->tcur);
+            while (next_out < p.T && tget(p, pi, next_out) <= c->tcur) {
+                if (threadIdx.x == 0) set_interp_x(c, tget(p, pi, next_out), c->tprev, c->tcur);
                 __syncthreads();
-                float* yo = p.yout + (size_t)next_out * BG;
+                float* yo = youtp + (size_t)next_out * BG;
                 const float dtf = c->dtf;
                 for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
                     float y0 = Y[li], y1 = Y1[li];
@@ -1570,10 +1573,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_fwd_kernel(const __grid_co
     __syncthreads();
     ring_drain(p, s);
     pf.tick(PT_CTRL);
+    write_status(p, pi, c, code);
+    __syncthreads();
+    }   // problems
     pf.finish();
     tmem_release(p, s.tmem);
     epilogue_epoch(p, s);
-    write_status(p, c, code);
 }
 
 // =====================================================================================================================
@@ -1995,6 +2000,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
     float* A1 = s.st() + 3 * BL;
     auto KY = [&](int i) { return s.st() + (4 + i) * BL; };
     auto KA = [&](int i) { return s.st() + (11 + i) * BL; };
+    // independent problems, one after the other: the weights stay on chip (shared / tensor memory) across them
+    for (int pi = 0; pi < p.nprob; ++pi) {
+    const float* ysavedp = p.ysaved + (size_t)pi * p.yout_stride;
+    const float* gradyp = p.grad_y + (size_t)pi * p.yout_stride;
+    float* adjy0p = p.adj_y0 + (size_t)pi * p.adj_stride;
+    float* theta0p = p.theta0 + (size_t)pi * p.theta_stride;
     int cur = 0;             // which theta buffer holds the current value (meaningful once !theta_zero)
     bool theta_zero = true;  // the accumulator has not been written yet: it is identically zero and never read
 
@@ -2028,8 +2039,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
 
     int code = PHX_ST_OK;
     for (int iv = p.T - 1; iv >= 1 && code == PHX_ST_OK; --iv) {
-        const float* ysv = p.ysaved + (size_t)iv * BG;
-        const float* gy = p.grad_y + (size_t)iv * BG;
+        const float* ysv = ysavedp + (size_t)iv * BG;
+        const float* gy = gradyp + (size_t)iv * BG;
         const bool first_iv = (iv == p.T - 1);
         for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) {
             float y = ysv[gi];
@@ -2040,15 +2051,15 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
             set_a_input(li, j, av);
         });
         __syncthreads();
-        const double t_start = -tget(p, iv), t_end = -tget(p, iv - 1);
+        const double t_start = -tget(p, pi, iv), t_end = -tget(p, pi, iv - 1);
 
         if (p.method != PHX_DOPRI5) {
-            const float dtf = p.t_is_f32 ? ((float)tget(p, iv) - (float)tget(p, iv - 1)) : (float)(tget(p, iv) - tget(p, iv - 1));
+            const float dtf = p.t_is_f32 ? ((float)tget(p, pi, iv) - (float)tget(p, pi, iv - 1)) : (float)(tget(p, pi, iv) - tget(p, pi, iv - 1));
             const float third = (float)(1.0 / 3.0);
             if (threadIdx.x == 0) {
                 PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
-                pa.src = theta_zero ? nullptr : p.theta0;
-                pa.dst = p.theta0;
+                pa.src = theta_zero ? nullptr : theta0p;
+                pa.dst = theta0p;
                 pa.dtf = dtf;
                 pa.method = p.method;
             }
@@ -2126,7 +2137,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                 });
                 if (threadIdx.x == 0) {
                     PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
-                    pa.src = theta_zero ? nullptr : (cur ? p.theta1 : p.theta0);
+                    pa.src = theta_zero ? nullptr : (cur ? p.theta1 : theta0p);
                     pa.dst = nullptr;
                     pa.s0 = 0;
                     pa.s1 = 1;
@@ -2249,8 +2260,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
                 }
                 if (threadIdx.x == 0) {
                     PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
-                    pa.src = theta_zero ? nullptr : (cur ? p.theta1 : p.theta0);
-                    pa.dst = theta_zero ? p.theta0 : (cur ? p.theta0 : p.theta1);
+                    pa.src = theta_zero ? nullptr : (cur ? p.theta1 : theta0p);
+                    pa.dst = theta_zero ? theta0p : (cur ? theta0p : p.theta1);
                     pa.dtf = c->dtf;
                     pa.last = c->last;
                     for (int q = 0; q < 7; ++q) {
@@ -2325,24 +2336,24 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
         }
         // interval done: adj_y picks up the loss gradient at t[iv-1] (adjoint.py:152-154)
         if (code == PHX_ST_OK) {
-            const float* gprev = p.grad_y + (size_t)(iv - 1) * BG;
+            const float* gprev = gradyp + (size_t)(iv - 1) * BG;
             for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { A[li] = A[li] + gprev[gi]; });
             __syncthreads();
         }
     }
-    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { p.adj_y0[gi] = A[li]; });
+    for_local(p, g_lo, n_loc, [&](int b, int j, int g, size_t gi, int li) { adjy0p[gi] = A[li]; });
     pf.tick(PT_COMBINE);
     if (theta_zero) {
         // nothing was ever written (a solver assertion fired before the first accepted step): report zeros
         const size_t tot = goff.total;
         for (size_t i = (size_t)blockIdx.x * THREADS + threadIdx.x; i < tot; i += (size_t)gridDim.x * THREADS)
-            p.theta0[i] = 0.f;
+            theta0p[i] = 0.f;
     } else if (cur != 0) {
         // the last accepted step landed in the scratch twin
         if (threadIdx.x == 0) {
             PPArgs& pa = *s.at<PPArgs>(p.so.ppa);
             pa.src = p.theta1;
-            pa.dst = p.theta0;
+            pa.dst = theta0p;
         }
         __syncthreads();
         ppass<PP_COPY, BT>(p, g_lo, n_loc);
@@ -2351,10 +2362,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_adj_kernel(const __grid_co
     __syncthreads();
     ring_drain(p, s);
     pf.tick(PT_CTRL);
+    write_status(p, pi, c, code);
+    __syncthreads();
+    }   // problems
     pf.finish();
     tmem_release(p, s.tmem);
     epilogue_epoch(p, s);
-    write_status(p, c, code);
 }
 
 }  // namespace

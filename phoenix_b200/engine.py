@@ -369,6 +369,20 @@ def _t_rows(t_rows):
     return [(ctypes.c_double * len(r))(*r) for r in t_rows]
 
 
+def _problems_per_launch(T):
+    return max(1, 16 // T)   # PHX_T_INLINE output times travel with the kernel parameters
+
+
+def _new_status_block(n):
+    """n contiguous pinned status records (one per problem of a multi-problem launch), all marked RUNNING."""
+    words = ctypes.sizeof(_lib.PhxStatus) // 4
+    st = torch.empty(n, words, dtype=torch.int32).pin_memory()
+    ctypes.memset(st.data_ptr(), 0, n * ctypes.sizeof(_lib.PhxStatus))
+    for i in range(n):
+        _lib.PhxStatus.from_address(st.data_ptr() + i * ctypes.sizeof(_lib.PhxStatus)).code = _lib.ST_RUNNING
+    return st
+
+
 _MANY_MAX_STREAMS = 8
 _side_streams = {}
 
@@ -433,6 +447,21 @@ def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_st
     streams = _concurrency(lib, dev, G, H, B, False, engine, N)
     if streams:
         _fan_out(dev, streams)
+    per = _problems_per_launch(T) if (engine == "resident" and not streams and not STEP_LOGGING) else 1
+    if per > 1:
+        # genome-scale model: a solve fills the GPU, so the problems go through ONE persistent launch a few at a time
+        # and the weights are staged on chip once per launch instead of once per problem
+        for lo in range(0, N, per):
+            n = min(per, N - lo)
+            stn = _new_status_block(n)
+            flat_t = (ctypes.c_double * (n * T))(*[x for r in t_rows[lo:lo + n] for x in r])
+            rc = lib.phx_solve_forward_many(ctx, G, H, B, n, pk, ctypes.c_void_p(ybase + lo * ystride), flat_t, T,
+                                            int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
+                                            ctypes.c_void_p(obase + lo * ostride), wsp, wsn, _ptr(stn), sp)
+            _lib.check(rc, "solve_forward_many")
+            for i in range(n):
+                _finish(stn[i], "forward solve %d" % (lo + i), dev)
+        return yout
     for i in range(N):
         st = _new_status()
         log, cap = _steplog()
@@ -478,8 +507,25 @@ def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps,
     astride = adj_y0[0].numel() * 4
     tarr = _t_rows(t_rows)
     streams = _concurrency(lib, dev, G, H, B, True, engine, N)
+    per = _problems_per_launch(T) if (engine == "resident" and not streams and not STEP_LOGGING) else 1
     for lo in range(0, N, chunk):
         hi = min(N, lo + chunk)
+        if per > 1:
+            for l2 in range(lo, hi, per):
+                n = min(per, hi - l2)
+                stn = _new_status_block(n)
+                flat_t = (ctypes.c_double * (n * T))(*[x for r in t_rows[l2:l2 + n] for x in r])
+                rc = lib.phx_solve_adjoint_many(
+                    ctx, G, H, B, n, pk, flat_t, T, int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
+                    ctypes.c_void_p(ys.data_ptr() + l2 * stride), ctypes.c_void_p(gy.data_ptr() + l2 * stride),
+                    ctypes.c_void_p(adj_y0.data_ptr() + l2 * astride),
+                    ctypes.c_void_p(grads.data_ptr() + (l2 - lo) * P * 4), wsp, wsn, _ptr(stn), sp)
+                _lib.check(rc, "solve_adjoint_many")
+                for i in range(n):
+                    _finish(stn[i], "adjoint solve %d" % (l2 + i), dev)
+            part = grads[:hi - lo].sum(dim=0)
+            total = part if total is None else total + part
+            continue
         if streams:
             _fan_out(dev, streams)
         for i in range(lo, hi):

@@ -331,10 +331,12 @@ def test_ragged_and_edge_shapes(pb):
         assert rel_l2(y.cpu(), y_ref) < 1e-5, (G, H, B)
 
 
-def test_odeint_adjoint_many_equals_the_per_sample_loop(pb):
+@pytest.mark.parametrize("G,H,N", [(690, 40, 5), (3551, 120, 7)])
+def test_odeint_adjoint_many_equals_the_per_sample_loop(pb, G, H, N):
     """SURVEY 8(f1): the sample loop of training_step inside the library.  Same solves => identical trajectories;
-    parameter cotangents are the per-sample ones summed (different summation tree => 1e-6)."""
-    G, H, N = 690, 40, 5
+    parameter cotangents are the per-sample ones summed (different summation tree => 1e-6).  690 genes: the solves
+    run side by side on separate streams; 3 551 genes (a solve fills the GPU): several problems per persistent launch
+    (phx_solve_forward_many / phx_solve_adjoint_many, 5 + 2 problems at T = 3)."""
     w = O.make_weights(G, H, 90, dense=True)
     net = make_net(pb, w)
     gen = torch.Generator().manual_seed(11)
