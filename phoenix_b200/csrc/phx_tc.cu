@@ -254,7 +254,7 @@ __device__ __forceinline__ void hill(float y, float& s, float& l, int want_l) {
 // accumulator (Hn columns) + running sum (Hn columns) fit the 512 columns for every Hn <= 256.  The soft-sign CTAs
 // need ~1/2 the ALU work per k-block of the log1p CTAs, so they get K ranges twice as long (phx_tc_branch_plan).
 struct BranchParams {
-    int G, B, Bpad, Hn, KB1, chunk, stages, nterms, dbg;   // G = valid k, B = valid rows, Bpad = mtiles * 128
+    int G, B, Bpad, Hn, KB1, chunk, stages, nterms;   // G = valid k, B = valid rows, Bpad = mtiles * 128
     int ld;               // leading dimension of the source matrix
     int mode;             // 0: A = Hill activation of y (soft-sign / log1p by branch); 1: A = y[b][g] * ascale[g] (cotangent)
     const float* ascale;  // mode 1: per-gene factor relu(m) (or NULL)
@@ -386,7 +386,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 for (int j = 0; j < 4; ++j) {
                     const int g = (kb0 + i + u) * BK + kc * 4 + j;
                     float t = MODE ? 0.f : 0.5f;   // pads contribute zero: s(0.5) = l(0.5) = 0
-                    if (rok && i + u < nkb && g < p.G && !(p.dbg & 16)) {
+                    if (rok && i + u < nkb && g < p.G) {
                         if (TRANS) t = __ldg(src + (size_t)g * p.ld);
                         else asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
                     }
@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                             }
                             sv = lv = cur[u][j] * sc;
                         } else {
-                            hill(cur[u][j], sv, lv, br && !(p.dbg & 2));
+                            hill(cur[u][j], sv, lv, br);
                         }
                         split_tf32(br ? lv : sv, hi[j], lo[j]);
                     }
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     unsigned char* a = smem + (size_t)s * stage_bytes + a_off;
                     *reinterpret_cast<float4*>(a) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<float4*>(a + K1_A_TILE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-                    if (!(p.dbg & 32)) fence_async_smem();   // generic-proxy writes -> visible to the async-proxy reads
+                    fence_async_smem();   // generic-proxy writes -> visible to the tensor core's async-proxy reads
                     __syncwarp();
                     if (lane == 0) {
                         if (PAIR && !leader) mbar_arrive_remote(full0 + 8 * s, 0u);
@@ -461,9 +461,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             unsigned ph = 0;
             for (int i = 0; i < nkb; ++i) {
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
-                if (p.dbg & 8) {   // timing experiment: no operand copy
-                    mbar_arrive(full0 + 8 * s);
-                } else if (!PAIR) {
+                if (!PAIR) {
                     mbar_expect_tx(full0 + 8 * s, b_bytes);
                     bulk_g2s(stage0 + s * stage_bytes + K1_A_BYTES,
                              p.w1img + ((size_t)(kb0 + i) * 4 + 2 * br) * Hn * BK, b_bytes, full0 + 8 * s);
@@ -540,7 +538,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     const uint64_t b_hi = desc_at(b_hi_part, b_base + k8 * p.b_kadv);
                     const uint64_t b_lo = desc_at(b_hi_part, b_base + b_tile + k8 * p.b_kadv);
                     const unsigned acc = (ic > 0 || k8 > 0) ? 1u : 0u;
-                    if (p.dbg & 4) continue;   // timing experiment: no MMAs
                     if (PAIR) {
                         if (p.nterms == 3) {
                             mma_tf32_pair(tmem, a_lo, b_hi, idesc, acc);
@@ -733,7 +730,8 @@ struct JointParams {
     unsigned a_kadv, b_kadv;               // byte advance of the start address per K = 8 MMA (two core matrices)
     int kb_lo, kb_hi;     // k-blocks of the images used by this launch
     int emode;            // epilogue: 0 f = fscale*(decay ? relu(m)*(acc - y) : acc); 1 f = acc; 2 state cotangent:
-                          //   f = (f + acc/(1+s(y))) / (1+|y-.5|)^2 - (decay ? g*relu(m) : 0)   (f holds u on entry)
+                          //   f = (f + acc/(1+s(y))) / (1+|y-.5|)^2 - (decay ? g*relu(m) : 0)   (f holds u on entry);
+                          // 3 the same with u and v accumulated side by side (k-blocks below / above the middle)
     float fscale;
     const float* waimg;   // A image: [GT][KB2][hi|lo][128 x 16]
     const float* spimg;   // B image: [BT][KB2][hi|lo][256 x 16]
@@ -798,12 +796,17 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             const unsigned idesc = idesc_tf32(128, 256);
             int it = 0, j = 0;
             for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
-                const int buf = j & 1;
-                const unsigned tph = (unsigned)(j >> 1) & 1u;
+                // EMODE 3 (fused u|v pass): both halves of tensor memory hold ONE tile (u in columns 0..255, v in
+                // 256..511), so there is no second buffer and the MMAs of a tile wait for the previous epilogue
+                const int buf = EMODE == 3 ? 0 : (j & 1);
+                const unsigned tph = EMODE == 3 ? (unsigned)j & 1u : (unsigned)(j >> 1) & 1u;
                 mbar_wait(tempty0 + 8 * buf, tph ^ 1u);   // epilogue has drained this accumulator
                 tc_fence_after();
-                const unsigned d = tmem + (unsigned)(buf * 256);
+                const int kb_mid = (p.kb_lo + p.kb_hi) >> 1;
                 for (int kb = p.kb_lo; kb < p.kb_hi; ++kb, ++it) {
+                    const bool second = EMODE == 3 && kb >= kb_mid;
+                    const unsigned d = tmem + (unsigned)(EMODE == 3 ? (second ? 256 : 0) : buf * 256);
+                    const int kb_first = second ? kb_mid : p.kb_lo;
                     const int s = it % S;
                     const unsigned ph = (unsigned)(it / S) & 1u;
                     mbar_wait(full0 + 8 * s, ph);
@@ -815,7 +818,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
                         const uint64_t a_lo = smem_desc(a_base + K2_A_TILE + k8 * p.a_kadv, p.a_lbo, p.a_sbo);
                         const uint64_t b_hi = smem_desc(b_base + k8 * p.b_kadv, p.b_lbo, p.b_sbo);
                         const uint64_t b_lo = smem_desc(b_base + K2_B_TILE + k8 * p.b_kadv, p.b_lbo, p.b_sbo);
-                        const unsigned acc = (kb > p.kb_lo || k8 > 0) ? 1u : 0u;
+                        const unsigned acc = (kb > kb_first || k8 > 0) ? 1u : 0u;
                         if (p.nterms == 3) {
                             mma_tf32(d, a_lo, b_hi, idesc, acc);
                             mma_tf32(d, a_hi, b_lo, idesc, 1u);
@@ -837,16 +840,16 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
         int j = 0;
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
             const int gt = t / p.BT, bt = t % p.BT;
-            const int buf = j & 1;
-            const unsigned tph = (unsigned)(j >> 1) & 1u;
+            const int buf = EMODE == 3 ? 0 : (j & 1);
+            const unsigned tph = EMODE == 3 ? (unsigned)j & 1u : (unsigned)(j >> 1) & 1u;
             const int g = gt * 128 + q * 32 + lane;
             const bool gok = g < p.G;
             const float rm = (gok && p.decay) ? p.relum[g] : 1.f;
             const int b0 = bt * 256 + half * 128;
             const int ncol = min(128, p.B - b0);   // valid batch rows of this warp's half (may be <= 0)
-            const bool need_y = EMODE == 2 || (EMODE == 0 && p.decay);
+            const bool need_y = EMODE >= 2 || (EMODE == 0 && p.decay);
             constexpr bool need_u = EMODE == 2;
-            const bool need_g = EMODE == 2 && p.decay;
+            const bool need_g = EMODE >= 2 && p.decay;
             float yv[16], yn[16], uv[16], un[16], gv[16], gn[16];
             auto loadin = [&](int c0, float (&dy)[16], float (&du)[16], float (&dg)[16]) {
 #pragma unroll
@@ -871,6 +874,11 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
                 if (c0 + 16 < ncol) loadin(c0 + 16, yn, un, gn);
                 float v[16];
                 tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * 256 + half * 128 + c0), v);
+                if (EMODE == 3) {   // u from the first half of tensor memory, v from the second
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) uv[jj] = v[jj];
+                    tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(256 + half * 128 + c0), v);
+                }
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     if (gok && c0 + jj < ncol) {
@@ -915,6 +923,16 @@ unsigned long long* phx_tc_prof_buffer() {
     return g_prof;
 }
 
+// PHX_TC_UV_FUSED=0 selects the two-pass form of the state cotangent (u stored, then v + epilogue)
+int uv_fused() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PHX_TC_UV_FUSED");
+        v = e ? atoi(e) : 0;
+    }
+    return v;
+}
+
 // EXPERIMENTAL, off by default (PHX_TC_PAIR=1 or phx_tc_set_pair): the branch-type contractions as CTA pairs (tcgen05
 // cta_group::2).  Bit-identical results; measured SLOWER on B200 than the single-CTA kernel.
 int g_pair = -1;
@@ -924,15 +942,6 @@ int pair_mode() {
         g_pair = e ? atoi(e) : 0;
     }
     return g_pair;
-}
-
-int debug_flags() {
-    static int flags = -1;
-    if (flags < 0) {
-        const char* e = getenv("PHX_TC_DEBUG");
-        flags = e ? atoi(e) : 0;
-    }
-    return flags;
 }
 
 }  // namespace
@@ -988,6 +997,7 @@ void set_attrs() {
     cudaFuncSetAttribute(tc_joint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_joint_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     done = true;
 }
 
@@ -1008,12 +1018,11 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
         pl.ks_p = pl.ks_s = (phx_tc_KB1(Kdim) + per - 1) / per;
     }
     *plan = pl;
-    const int dbg = debug_flags();
     BranchParams bp;
     const int pair = pair_mode();
     bp.G = Kdim; bp.B = Mdim; bp.Bpad = phx_round_up(pl.mtiles, 2) * 128; bp.Hn = Hn; bp.KB1 = phx_tc_KB1(Kdim); bp.chunk = phx_tc_chunk();
     bp.ld = G;
-    bp.nterms = nterms; bp.dbg = dbg; bp.mode = mode; bp.ascale = ascale;
+    bp.nterms = nterms; bp.mode = mode; bp.ascale = ascale;
     bp.mtiles = pl.mtiles; bp.ks_p = pl.ks_p; bp.per_p = pl.per_p; bp.ks_s = pl.ks_s; bp.per_s = pl.per_s;
     const int Hb = pair ? Hn / 2 : Hn;   // B rows staged per CTA
 #if PHX_TC_BRANCH_SW64
@@ -1023,10 +1032,6 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     bp.a_lbo = 16 * 128; bp.a_sbo = 128; bp.b_lbo = (unsigned)(Hb / 8) * 128; bp.b_sbo = 128;
     bp.a_kadv = 2 * bp.a_lbo; bp.b_kadv = 2 * bp.b_lbo;
 #endif
-    if (dbg & 1) {   // diagnostic: swapped meaning of the two descriptor offsets
-        unsigned t = bp.a_lbo; bp.a_lbo = bp.a_sbo; bp.a_sbo = t;
-        t = bp.b_lbo; bp.b_lbo = bp.b_sbo; bp.b_sbo = t;
-    }
     bp.y = src; bp.w1img = bimg; bp.spart = spart;
     bp.prof = phx_tc_prof_buffer();
     const size_t stage1 = K1_A_BYTES + (size_t)2 * Hb * BK * 4;
@@ -1102,16 +1107,11 @@ int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, c
 void launch_joint(int G, int H, int B, int nterms, const float* aimg, const float* bimg, int kb_lo, int kb_hi, int emode,
                   int decay, float fscale, const float* y, const float* g, const float* relum, float* out,
                   cudaStream_t st) {
-    const int dbg = debug_flags();
     JointParams jp;
     jp.G = G; jp.B = B; jp.KB2 = phx_tc_KB2(H); jp.GT = phx_tc_GT(G); jp.BT = phx_tc_BT(B); jp.nterms = nterms;
     jp.decay = decay; jp.fscale = fscale; jp.kb_lo = kb_lo; jp.kb_hi = kb_hi; jp.emode = emode;
     jp.a_lbo = 16 * 128; jp.a_sbo = 128; jp.b_lbo = 32 * 128; jp.b_sbo = 128;
     jp.a_kadv = 2 * jp.a_lbo; jp.b_kadv = 2 * jp.b_lbo;
-    if (dbg & 1) {
-        unsigned t = jp.a_lbo; jp.a_lbo = jp.a_sbo; jp.a_sbo = t;
-        t = jp.b_lbo; jp.b_lbo = jp.b_sbo; jp.b_sbo = t;
-    }
     jp.waimg = aimg; jp.spimg = bimg; jp.y = y; jp.g = g; jp.relum = relum; jp.f = out;
     const int ntiles = jp.GT * jp.BT;
     const int grid = ntiles < PHX_TC_SMS ? ntiles : PHX_TC_SMS;
@@ -1119,7 +1119,8 @@ void launch_joint(int G, int H, int B, int nterms, const float* aimg, const floa
     const size_t smem2 = (size_t)K2_STAGES * K2_STAGE_BYTES + 256;
     if (emode == 0) tc_joint_kernel<0><<<grid, K2_THREADS, smem2, st>>>(jp);
     else if (emode == 1) tc_joint_kernel<1><<<grid, K2_THREADS, smem2, st>>>(jp);
-    else tc_joint_kernel<2><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else if (emode == 2) tc_joint_kernel<2><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else tc_joint_kernel<3><<<grid, K2_THREADS, smem2, st>>>(jp);
 }
 
 int check_launch(const char* what) {
@@ -1153,9 +1154,14 @@ int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float
                            sc.spart, st);
     if (rc != PHX_OK) return rc;
     if (ybar) {
-        // u = gS Ws (k-blocks of the sums half), then v = gP Wp and the soft-sign / log1p backward in the epilogue
-        launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, 0, KB2 / 2, 1, 0, 1.f, nullptr, nullptr, w.relum, ybar, st);
-        launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, KB2 / 2, KB2, 2, decay, 1.f, y, g, w.relum, ybar, st);
+        // u = gS Ws (k-blocks of the sums half) and v = gP Wp (prods half) in the two halves of tensor memory, the
+        // soft-sign / log1p backward in the epilogue.  (Two-pass form: EMODE 1 stores u, EMODE 2 finishes.)
+        if (uv_fused()) {
+            launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, 0, KB2, 3, decay, 1.f, y, g, w.relum, ybar, st);
+        } else {
+            launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, 0, KB2 / 2, 1, 0, 1.f, nullptr, nullptr, w.relum, ybar, st);
+            launch_joint(G, H, B, nterms, w.w1kimg, sc.gsimg, KB2 / 2, KB2, 2, decay, 1.f, y, g, w.relum, ybar, st);
+        }
     }
     if (J) launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, KB2, 0, 0, 1.f, y, nullptr, w.relum, J, st);
     return check_launch("tc vjp_state");

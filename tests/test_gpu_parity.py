@@ -359,3 +359,35 @@ def test_odeint_adjoint_many_equals_the_per_sample_loop(pb, G, H, N):
         assert torch.equal(g_many[0], g_loop[0])
         for a, b in zip(g_many[1:], g_loop[1:]):
             assert rel_l2(a.cpu(), b.cpu()) < 1e-6
+
+
+def test_multi_problem_entry_points_check_their_limits(pb):
+    """phx_solve_forward_many: N * T output times must fit the kernel parameters (16); the rows must fit the resident
+    kernels; a decreasing time row is refused like in the single-problem call."""
+    import ctypes
+    from phoenix_b200 import _lib, engine
+    w = O.make_weights(350, 40, 91, dense=True)
+    net = make_net(pb, w)
+    lib = _lib.load()
+    packed, G, H, dev = engine.packed_weights(net)
+    ctx = _lib.ctx(dev)
+    y0 = torch.rand(9, 1, G).cuda()
+    yout = torch.empty(9, 2, 1, G).cuda()
+    ws = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 0), dtype=torch.uint8, device="cuda")
+    lib.phx_solve_workspace_init(ctypes.c_void_p(ws.data_ptr()), ws.numel(), None)
+    st = torch.zeros(9, 10, dtype=torch.int32).pin_memory()
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())
+
+    def call(n, times):
+        tarr = (ctypes.c_double * len(times))(*times)
+        return lib.phx_solve_forward_many(ctx, G, H, 1, n, ptr(packed), ptr(y0), tarr, 2, 1, 2, 1e-7, 1e-9, 2 ** 31 - 1,
+                                          ptr(yout), ptr(ws), ws.numel(), ptr(st), None)
+
+    assert call(9, [0.0, 1.0] * 9) != 0 and "16" in _lib.last_error()          # 9 * 2 > 16 output times
+    assert call(2, [0.0, 1.0, 1.0, 0.5]) != 0                                   # second problem's times decrease
+    assert call(8, [0.0, 0.5] * 8) == 0
+    torch.cuda.synchronize()
+    with torch.no_grad():
+        ref = pb.odeint(net, y0[3], torch.tensor([0.0, 0.5]), method="rk4")
+    assert torch.equal(yout[3], ref)
+    assert all(int(st[i, 0]) == 0 and int(st[i, 3]) == 4 for i in range(8))     # code OK, 4 RHS evaluations each
