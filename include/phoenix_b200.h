@@ -92,6 +92,10 @@ enum { PHX_PREC_FP32 = 0, PHX_PREC_TF32 = 1, PHX_PREC_3XTF32 = 3 };
 int phx_ctx_set_precision(phx_ctx* ctx, int precision);
 int phx_ctx_get_precision(const phx_ctx* ctx);
 int phx_tc_min_rows(void);
+/* Host-only: how a branch-type tensor-core contraction with K k-elements (genes, or batch rows for the parameter
+ * cotangents) and M rows is split over CTAs.  out = {128-row tiles, K-splits of the prods half, k-blocks per split,
+ * K-splits of the sums half, k-blocks per split, partial-sum slots}; a k-block is 16 k-elements. */
+int phx_tc_plan_describe(int K, int M, int32_t out[6]);
 
 /* ---- weights --------------------------------------------------------------------------------------------- */
 /* Bytes of the packed (kernel-layout) copy of the six parameters for an ODENet(ndim=G, neurons=H). */

@@ -157,6 +157,13 @@ int phx_ctx_set_precision(phx_ctx* ctx, int precision) {
 int phx_ctx_get_precision(const phx_ctx* ctx) { return ctx ? ctx->precision : PHX_ERR_INVALID; }
 int phx_tc_min_rows(void) { return phx_tc_min_rows_rt(); }
 
+int phx_tc_plan_describe(int K, int M, int32_t out[6]) {
+    if (!out || K < 1 || M < 1) return PHX_ERR_INVALID;
+    const PhxTcBranchPlan pl = phx_tc_branch_plan(K, M);
+    out[0] = pl.mtiles; out[1] = pl.ks_p; out[2] = pl.per_p; out[3] = pl.ks_s; out[4] = pl.per_s; out[5] = pl.slots;
+    return PHX_OK;
+}
+
 size_t phx_packed_bytes(int G, int H) { return phx_packed_floats(G, H) * sizeof(float); }
 
 int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* m, const float* Wp, const float* bp, const float* Ws,

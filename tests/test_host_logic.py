@@ -141,3 +141,25 @@ def test_resident_plan_places_the_weight_slices():
     assert rc == 0 and p["ctas"] == 3 and p["gpc"] == 16
     rc, p = plan(690, 40, 1, 1)
     assert rc == 0 and p["ctas"] == 22 and p["gpc"] == 32
+
+
+def test_tensor_core_work_split_covers_k_exactly():
+    """phx_tc_plan_describe (host only): every K-split is a whole number of 16-k-block chunks, the splits of each half
+    cover all k-blocks with no empty split, the partial-sum slots bound both halves, and the grid stays near two CTAs
+    per SM (148 SMs) unless the row tiles alone exceed that."""
+    import ctypes
+    from phoenix_b200 import _lib
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 6)()
+    for K in (1, 15, 16, 17, 350, 690, 3551, 4096, 10000, 11165, 20000):
+        for M in (1, 5, 60, 128, 129, 1024, 4096, 10000, 11165, 20000):
+            assert lib.phx_tc_plan_describe(K, M, out) == 0
+            mtiles, ks_p, per_p, ks_s, per_s, slots = list(out)
+            kb = (K + 15) // 16
+            assert mtiles == (M + 127) // 128
+            for ks, per in ((ks_p, per_p), (ks_s, per_s)):
+                assert per % 16 == 0 and per >= 16
+                assert ks >= 1 and ks * per >= kb and (ks - 1) * per < kb, (K, M, ks, per, kb)
+            assert slots == max(ks_p, ks_s)
+            assert mtiles * (ks_p + ks_s) <= max(2 * 148 + 2 * mtiles, 2 * mtiles), (K, M, list(out))
+    assert lib.phx_tc_plan_describe(0, 5, out) != 0
