@@ -96,23 +96,21 @@ def _workspace(dev, nbytes, tag):
 
 
 # ---- packed weights ------------------------------------------------------------------------------------------------
-_PARAM_GETTERS = (
-    lambda n: n.gene_multipliers,
-    lambda n: n.net_prods.linear_out.weight,
-    lambda n: n.net_prods.linear_out.bias,
-    lambda n: n.net_sums.linear_out.weight,
-    lambda n: n.net_sums.linear_out.bias,
-    lambda n: n.net_alpha_combine.linear_out.weight,
-)
+def _lin(net, name):
+    # nn.Module keeps parameters / submodules in dicts and only reaches them through the slow __getattr__ fallback;
+    # this runs twice per sample of every training step, so go to the dicts directly
+    return net._modules[name]._modules["linear_out"]._parameters
 
 
 def net_params(net):
     """The six parameters in the reference's ``ODENet.parameters()`` order (adjoint.py:185,207-220)."""
-    return [g(net) for g in _PARAM_GETTERS]
+    prods, sums = _lin(net, "net_prods"), _lin(net, "net_sums")
+    return [net._parameters["gene_multipliers"], prods["weight"], prods["bias"], sums["weight"], sums["bias"],
+            _lin(net, "net_alpha_combine")["weight"]]
 
 
 def net_dims(net):
-    W = net.net_sums.linear_out.weight
+    W = _lin(net, "net_sums")["weight"]
     return int(W.shape[1]), int(W.shape[0])
 
 
@@ -122,6 +120,13 @@ _pack_cache = weakref.WeakKeyDictionary()
 def packed_weights(net):
     """Kernel-layout copy of the parameters, rebuilt only when a parameter changed (``_version`` / storage)."""
     params = net_params(net)
+    ent = _pack_cache.get(net)
+    if ent is not None:
+        # fast path (every call between two optimiser steps): same storages, same versions, same stream
+        dev = ent[3]
+        key = tuple((p.data_ptr(), p._version) for p in params) + (torch.cuda.current_stream(dev).cuda_stream,)
+        if ent[0] == key:
+            return ent[1], ent[2][0], ent[2][1], dev
     G, H = net_dims(net)
     dev = _device_index(params[0])
     for p in params:
@@ -130,9 +135,6 @@ def packed_weights(net):
         if _device_index(p) != dev:
             raise RuntimeError("all ODENet parameters must live on the same CUDA device")
     key = tuple((p.data_ptr(), p._version) for p in params) + (torch.cuda.current_stream(dev).cuda_stream,)
-    ent = _pack_cache.get(net)
-    if ent is not None and ent[0] == key:
-        return ent[1], G, H, dev
     lib = _lib.load()
     nbytes = lib.phx_packed_bytes(G, H)
     buf = ent[1] if ent is not None and ent[1].numel() * 4 == nbytes and ent[1].device.index == dev else \
@@ -140,7 +142,7 @@ def packed_weights(net):
     ps = [p.detach().contiguous() for p in params]
     _lib.check(lib.phx_pack_weights(_lib.ctx(dev), G, H, *[_ptr(p) for p in ps], _ptr(buf), _stream_ptr(dev)),
                "pack_weights")
-    _pack_cache[net] = (key, buf)
+    _pack_cache[net] = (key, buf, (G, H), dev)
     return buf, G, H, dev
 
 
