@@ -9,6 +9,7 @@
 // (gJ^T SP etc., K = B) and are materialised per stage like the reference does.
 #include <math.h>
 #include <string.h>
+#include <stdint.h>
 #include <vector>
 #include "phx_common.cuh"
 
@@ -41,29 +42,64 @@ __device__ __forceinline__ float ksum(const KSet& a, size_t i) {
     for (int j = 1; j < a.nk; ++j) v = fmaf(a.k[j][i], a.c[j], v);
     return v;
 }
+// the same for four consecutive elements (i a multiple of 4, 16-byte aligned arrays): one 128-bit load per array
+__device__ __forceinline__ float4 ksum4(const KSet& a, size_t i) {
+    float4 k = *reinterpret_cast<const float4*>(a.k[0] + i);
+    float4 v = make_float4(k.x * a.c[0], k.y * a.c[0], k.z * a.c[0], k.w * a.c[0]);
+    for (int j = 1; j < a.nk; ++j) {
+        k = *reinterpret_cast<const float4*>(a.k[j] + i);
+        v.x = fmaf(k.x, a.c[j], v.x);
+        v.y = fmaf(k.y, a.c[j], v.y);
+        v.z = fmaf(k.z, a.c[j], v.z);
+        v.w = fmaf(k.w, a.c[j], v.w);
+    }
+    return v;
+}
+__device__ __forceinline__ float4 ld4(const float* p, size_t i) { return *reinterpret_cast<const float4*>(p + i); }
 
-// out = x0 + sum_j c_j k_j           (rk_common.py:66)
+// out = x0 + sum_j c_j k_j           (rk_common.py:66).  V = 4: n is a multiple of 4 and every array is 16-byte aligned
+template <int V>
 __global__ void combine_kernel(float* out, const float* x0, KSet a, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        out[i] = x0[i] + ksum(a, i);
+    const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        if (V == 4) {
+            const float4 x = ld4(x0, i), k = ksum4(a, i);
+            *reinterpret_cast<float4*>(out + i) = make_float4(x.x + k.x, x.y + k.y, x.z + k.z, x.w + k.w);
+        } else {
+            out[i] = x0[i] + ksum(a, i);
+        }
+    }
 }
 
 // fixed-grid formulas, exactly as written in fixed_grid.py / rk_common.py:96-103
 enum { FX_EULER_END = 0, FX_MID_IN = 1, FX_RK4_IN2 = 2, FX_RK4_IN3 = 3, FX_RK4_IN4 = 4, FX_RK4_END = 5 };
+__device__ __forceinline__ float fixed_one(int mode, float x, float a1, float a2, float a3, float a4, float dt) {
+    const float third = (float)(1.0 / 3.0);
+    switch (mode) {
+        case FX_EULER_END: return x + dt * a1;
+        case FX_MID_IN: return x + a1 * dt;  // dt carries half_dt here
+        case FX_RK4_IN2: return x + dt * a1 * third;
+        case FX_RK4_IN3: return x + dt * (a2 - a1 * third);
+        case FX_RK4_IN4: return x + dt * (a1 - a2 + a3);
+        default: return x + (a1 + 3.f * (a2 + a3) + a4) * dt * 0.125f;
+    }
+}
+template <int V>
 __global__ void fixed_kernel(int mode, float* out, const float* x0, const float* k1, const float* k2, const float* k3,
                              const float* k4, float dt, size_t n) {
-    const float third = (float)(1.0 / 3.0);
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float x = x0[i], r;
-        switch (mode) {
-            case FX_EULER_END: r = x + dt * k1[i]; break;
-            case FX_MID_IN: r = x + k1[i] * dt; break;  // dt carries half_dt here
-            case FX_RK4_IN2: r = x + dt * k1[i] * third; break;
-            case FX_RK4_IN3: r = x + dt * (k2[i] - k1[i] * third); break;
-            case FX_RK4_IN4: r = x + dt * (k1[i] - k2[i] + k3[i]); break;
-            default: r = x + (k1[i] + 3.f * (k2[i] + k3[i]) + k4[i]) * dt * 0.125f; break;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+    const bool u2 = mode >= FX_RK4_IN3, u3 = mode >= FX_RK4_IN4, u4 = mode == FX_RK4_END;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        if (V == 4) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 x = ld4(x0, i), a1 = ld4(k1, i), a2 = u2 ? ld4(k2, i) : z, a3 = u3 ? ld4(k3, i) : z,
+                         a4 = u4 ? ld4(k4, i) : z;
+            *reinterpret_cast<float4*>(out + i) =
+                make_float4(fixed_one(mode, x.x, a1.x, a2.x, a3.x, a4.x, dt), fixed_one(mode, x.y, a1.y, a2.y, a3.y, a4.y, dt),
+                            fixed_one(mode, x.z, a1.z, a2.z, a3.z, a4.z, dt), fixed_one(mode, x.w, a1.w, a2.w, a3.w, a4.w, dt));
+        } else {
+            out[i] = fixed_one(mode, x0[i], k1[i], u2 ? k2[i] : 0.f, u3 ? k3[i] : 0.f, u4 ? k4[i] : 0.f, dt);
         }
-        out[i] = r;
     }
 }
 
@@ -110,16 +146,33 @@ __global__ void initd2_kernel(const float* x0, const float* k0, const float* k1,
     block_partials<3>(v, partial);
 }
 // [0] = sum (err/tol)^2, [1] = #non-finite in x1   (misc.py:89-91)
+template <int V>
 __global__ void err_kernel(const float* x0, const float* x1, KSet a, float rtol, float atol, size_t n,
                            double* partial) {
     double v[3] = {0, 0, 0};
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float e = ksum(a, i);
-        float xa = x0[i], xb = x1[i];
-        float tol = atol + rtol * fmaxf(fabsf(xa), fabsf(xb));
-        float r = e / tol;
-        v[0] += (double)(r * r);
-        if (!isfinite(xb)) v[1] += 1.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        float e[4], xa[4], xb[4];
+        if (V == 4) {
+            const float4 e4 = ksum4(a, i), a4 = ld4(x0, i), b4 = ld4(x1, i);
+            e[0] = e4.x; e[1] = e4.y; e[2] = e4.z; e[3] = e4.w;
+            xa[0] = a4.x; xa[1] = a4.y; xa[2] = a4.z; xa[3] = a4.w;
+            xb[0] = b4.x; xb[1] = b4.y; xb[2] = b4.z; xb[3] = b4.w;
+        } else {
+            e[0] = ksum(a, i); xa[0] = x0[i]; xb[0] = x1[i];
+        }
+        float s = 0.f;   // squares of (at most) four neighbours in fp32, then into the double running sum
+        bool bad = false;
+#pragma unroll
+        for (int q = 0; q < V; ++q) {
+            const float tol = atol + rtol * fmaxf(fabsf(xa[q]), fabsf(xb[q]));
+            const float r = e[q] / tol;
+            s += r * r;
+            bad = bad || !isfinite(xb[q]);
+            if (V == 4 && !isfinite(xb[q])) v[1] += 1.0;
+        }
+        v[0] += (double)s;
+        if (V == 1 && bad) v[1] += 1.0;
     }
     block_partials<3>(v, partial);
 }
@@ -133,25 +186,46 @@ __global__ void final_reduce_kernel(const double* partial, int nblocks, double* 
     }
 }
 // quartic dense output at x (interp.py:1-47)
+__device__ __forceinline__ float interp_one(float y0, float y1, float f0, float f1, float ks, float dt, float xs0,
+                                            float xs1, float xs2, float xs3) {
+    float ymid = y0 + ks;
+    float a = 2.f * dt * (f1 - f0) - 8.f * (y1 + y0) + 16.f * ymid;
+    float b = dt * (5.f * f0 - 3.f * f1) + 18.f * y0 + 14.f * y1 - 32.f * ymid;
+    float c = dt * (f1 - 4.f * f0) - 11.f * y0 - 5.f * y1 + 16.f * ymid;
+    float d = dt * f0;
+    float total = y0 + xs0 * d;
+    total = total + xs1 * c;
+    total = total + xs2 * b;
+    total = total + xs3 * a;
+    return total;
+}
+template <int V>
 __global__ void interp_kernel(float* out, const float* x0, const float* x1, KSet mid, const float* kf, const float* kl,
                               float dt, float xs0, float xs1, float xs2, float xs3, size_t n) {
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
-        float y0 = x0[i], y1 = x1[i], f0 = kf[i], f1 = kl[i];
-        float ymid = y0 + ksum(mid, i);
-        float a = 2.f * dt * (f1 - f0) - 8.f * (y1 + y0) + 16.f * ymid;
-        float b = dt * (5.f * f0 - 3.f * f1) + 18.f * y0 + 14.f * y1 - 32.f * ymid;
-        float c = dt * (f1 - 4.f * f0) - 11.f * y0 - 5.f * y1 + 16.f * ymid;
-        float d = dt * f0;
-        float total = y0 + xs0 * d;
-        total = total + xs1 * c;
-        total = total + xs2 * b;
-        total = total + xs3 * a;
-        out[i] = total;
+    const size_t stride = (size_t)gridDim.x * blockDim.x * V;
+    for (size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V; i < n; i += stride) {
+        if (V == 4) {
+            const float4 a = ld4(x0, i), b = ld4(x1, i), f0 = ld4(kf, i), f1 = ld4(kl, i), m = ksum4(mid, i);
+            *reinterpret_cast<float4*>(out + i) =
+                make_float4(interp_one(a.x, b.x, f0.x, f1.x, m.x, dt, xs0, xs1, xs2, xs3),
+                            interp_one(a.y, b.y, f0.y, f1.y, m.y, dt, xs0, xs1, xs2, xs3),
+                            interp_one(a.z, b.z, f0.z, f1.z, m.z, dt, xs0, xs1, xs2, xs3),
+                            interp_one(a.w, b.w, f0.w, f1.w, m.w, dt, xs0, xs1, xs2, xs3));
+        } else {
+            out[i] = interp_one(x0[i], x1[i], kf[i], kl[i], ksum(mid, i), dt, xs0, xs1, xs2, xs3);
+        }
     }
 }
 __global__ void add_kernel(float* x, const float* y, size_t n) {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         x[i] = x[i] + y[i];
+}
+
+inline bool al16(const void* p) { return p == nullptr || ((uintptr_t)p & 15) == 0; }
+inline bool kset_al16(const KSet& a) {
+    for (int j = 0; j < a.nk; ++j)
+        if (!al16(a.k[j])) return false;
+    return true;
 }
 
 int nblk(size_t n) {
@@ -205,7 +279,21 @@ struct Stream {
                                   segs[0].k[slot], -1.f, rhs_ws, st);
     }
     // reduce a 3-value kernel result for segment si into sums_dev[si]
-    void finish_sums(int si) { final_reduce_kernel<<<1, 32, 0, st>>>(partial, nblk(segs[si].n), sums_dev + 3 * si); }
+    // reduce the per-block partials of the LAST 3-value kernel launched for segment si (`blocks` = its grid size)
+    void finish_sums(int si, int blocks = -1) {
+        final_reduce_kernel<<<1, 32, 0, st>>>(partial, blocks < 0 ? nblk(segs[si].n) : blocks, sums_dev + 3 * si);
+    }
+    void combine(float* out, const float* x0, const KSet& a, size_t n) {
+        if (n % 4 == 0 && al16(out) && al16(x0) && kset_al16(a)) combine_kernel<4><<<nblk(n / 4), EB, 0, st>>>(out, x0, a, n);
+        else combine_kernel<1><<<nblk(n), EB, 0, st>>>(out, x0, a, n);
+    }
+    void fixed(int mode, float* out, const float* x0, const float* k1, const float* k2, const float* k3, const float* k4,
+               float dt, size_t n) {
+        if (n % 4 == 0 && al16(out) && al16(x0) && al16(k1) && al16(k2) && al16(k3) && al16(k4))
+            fixed_kernel<4><<<nblk(n / 4), EB, 0, st>>>(mode, out, x0, k1, k2, k3, k4, dt, n);
+        else
+            fixed_kernel<1><<<nblk(n), EB, 0, st>>>(mode, out, x0, k1, k2, k3, k4, dt, n);
+    }
     int fetch_sums() {
         cudaError_t e = cudaMemcpyAsync(sums_host, sums_dev, sizeof(double) * 3 * segs.size(), cudaMemcpyDeviceToHost,
                                         st);
@@ -229,7 +317,7 @@ struct Stream {
     void set_inputs(const KSet* per_seg) {
         for (size_t si = 0; si < segs.size(); ++si) {
             Seg& s = segs[si];
-            if (s.xs) combine_kernel<<<nblk(s.n), EB, 0, st>>>(s.xs, s.x0, per_seg[si], s.n);
+            if (s.xs) combine(s.xs, s.x0, per_seg[si], s.n);
         }
     }
     KSet kset(int si, const int* slots, const float* coef, int nk) {
@@ -256,7 +344,7 @@ struct Stream {
         copy_to_inputs();
         if ((rc = eval(0)) != PHX_OK) return rc;
         auto fx = [&](int mode, Seg& s, float* out, float dt) {
-            fixed_kernel<<<nblk(s.n), EB, 0, st>>>(mode, out, s.x0, s.k[0], s.k[1], s.k[2], s.k[3], dt, s.n);
+            fixed(mode, out, s.x0, s.k[0], s.k[1], s.k[2], s.k[3], dt, s.n);
         };
         if (method == PHX_EULER) {
             for (auto& s : segs) fx(FX_EULER_END, s, s.x0, dtf);
@@ -266,8 +354,7 @@ struct Stream {
                 if (s.xs) fx(FX_MID_IN, s, s.xs, 0.5f * dtf);
             if ((rc = eval(1)) != PHX_OK) return rc;
             for (auto& s : segs)
-                fixed_kernel<<<nblk(s.n), EB, 0, st>>>(FX_EULER_END, s.x0, s.x0, s.k[1], nullptr, nullptr, nullptr, dtf,
-                                                       s.n);
+                fixed(FX_EULER_END, s.x0, s.x0, s.k[1], nullptr, nullptr, nullptr, dtf, s.n);
             status.n_rhs += 2;
         } else {
             for (auto& s : segs)
@@ -343,10 +430,10 @@ struct Stream {
                     Seg& s = segs[si];
                     KSet a = kset((int)si, sl, cb[stg - 1], stg);
                     if (stg == 6) {
-                        combine_kernel<<<nblk(s.n), EB, 0, st>>>(s.x1, s.x0, a, s.n);
+                        combine(s.x1, s.x0, a, s.n);
                         if (s.xs) cudaMemcpyAsync(s.xs, s.x1, s.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
                     } else if (s.xs) {
-                        combine_kernel<<<nblk(s.n), EB, 0, st>>>(s.xs, s.x0, a, s.n);
+                        combine(s.xs, s.x0, a, s.n);
                     }
                 }
                 if ((rc = eval(sl[stg])) != PHX_OK) return rc;
@@ -354,8 +441,13 @@ struct Stream {
             for (size_t si = 0; si < ns; ++si) {
                 Seg& s = segs[si];
                 KSet a = kset((int)si, sl, cerr, 7);
-                err_kernel<<<nblk(s.n), EB, 0, st>>>(s.x0, s.x1, a, rtol_f, atol_f, s.n, partial);
-                finish_sums((int)si);
+                if (s.n % 4 == 0 && al16(s.x0) && al16(s.x1) && kset_al16(a)) {
+                    err_kernel<4><<<nblk(s.n / 4), EB, 0, st>>>(s.x0, s.x1, a, rtol_f, atol_f, s.n, partial);
+                    finish_sums((int)si, nblk(s.n / 4));
+                } else {
+                    err_kernel<1><<<nblk(s.n), EB, 0, st>>>(s.x0, s.x1, a, rtol_f, atol_f, s.n, partial);
+                    finish_sums((int)si);
+                }
             }
             if ((rc = fetch_sums()) != PHX_OK) return rc;
             float ratio = block_norm(0);
@@ -395,8 +487,12 @@ struct Stream {
     void interp_seg(int si, float* out, const float* xs, const int* sl, float dtf, const float* cmid) {
         Seg& s = segs[si];
         KSet mid = kset(si, sl, cmid, 7);
-        interp_kernel<<<nblk(s.n), EB, 0, st>>>(out, s.x0, s.x1, mid, s.k[sl[0]], s.k[sl[6]], dtf, xs[0], xs[1], xs[2],
-                                                xs[3], s.n);
+        if (s.n % 4 == 0 && al16(out) && al16(s.x0) && al16(s.x1) && kset_al16(mid))
+            interp_kernel<4><<<nblk(s.n / 4), EB, 0, st>>>(out, s.x0, s.x1, mid, s.k[sl[0]], s.k[sl[6]], dtf, xs[0], xs[1],
+                                                           xs[2], xs[3], s.n);
+        else
+            interp_kernel<1><<<nblk(s.n), EB, 0, st>>>(out, s.x0, s.x1, mid, s.k[sl[0]], s.k[sl[6]], dtf, xs[0], xs[1],
+                                                       xs[2], xs[3], s.n);
     }
     int fail(int code, double t, double dt) {
         status.code = code;
