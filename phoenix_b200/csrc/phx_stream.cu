@@ -176,13 +176,15 @@ __global__ void err_kernel(const float* x0, const float* x1, KSet a, float rtol,
     }
     block_partials<3>(v, partial);
 }
-// out[seg*3 + q] = sum over blocks, fixed order
+// out[seg*3 + q] = sum over blocks, fixed order: lane l adds blocks l, l+32, ... then a fixed butterfly (one warp)
 __global__ void final_reduce_kernel(const double* partial, int nblocks, double* out) {
-    int q = threadIdx.x;
-    if (q < 3) {
-        double s = 0;
-        for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * 3 + q];
-        out[q] = s;
+    const int lane = threadIdx.x;
+    double s[3] = {0, 0, 0};
+    for (int b = lane; b < nblocks; b += 32)
+        for (int q = 0; q < 3; ++q) s[q] += partial[(size_t)b * 3 + q];
+    for (int q = 0; q < 3; ++q) {
+        for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+        if (lane == 0) out[q] = s[q];
     }
 }
 // quartic dense output at x (interp.py:1-47)
