@@ -39,9 +39,31 @@ UNIT = "gene-steps/s"
 P = 4 * G * H + 2 * H + G
 
 
+def synthetic_weights(seed, dense):
+    """The six parameters in the reference's order (gene_multipliers, Wp, bp, Ws, bs, Wa) with its init distribution
+    (odenet.py:61-75): matrices nn.init.sparse_(sparsity=0.95, std=0.05) -- per column 95 % zeros -- or dense
+    N(0, 0.05^2) ("trained-like"), nn.Linear default biases, multipliers U[0,1).  Input generation only; the product arm
+    never touches oracle/."""
+    import math
+    gen = torch.Generator().manual_seed(seed)
+
+    def mat(rows, cols):
+        w = torch.randn(rows, cols, generator=gen) * 0.05
+        if not dense:
+            keep = torch.rand(rows, cols, generator=gen).argsort(dim=0) >= int(math.ceil(0.95 * rows))
+            w = w * keep
+        return w.contiguous()
+
+    Ws, Wp, Wa = mat(H, G), mat(H, G), mat(G, 2 * H)
+    bound = 1.0 / math.sqrt(G)
+    bs = (torch.rand(H, generator=gen) * 2 - 1) * bound
+    bp = (torch.rand(H, generator=gen) * 2 - 1) * bound
+    m = torch.rand(1, G, generator=gen)
+    return [m, Wp, bp, Ws, bs, Wa]
+
+
 def workload(seed, device):
-    from oracle.phoenix_oracle import make_weights  # deterministic input generator only (no compute)
-    w = make_weights(G, H, 1003, dense=bool(int(os.environ.get("PHX_BENCH_DENSE", "0"))))
+    w = synthetic_weights(1003, bool(int(os.environ.get("PHX_BENCH_DENSE", "0"))))
     gen = torch.Generator().manual_seed(seed)
     y0 = torch.rand(BATCH, 1, G, generator=gen)
     target = torch.rand(BATCH, 1, G, generator=gen)
@@ -54,7 +76,9 @@ def workload(seed, device):
 # reference arm / cpu baseline: the oracle port of the reference's torch-CPU path, all host threads
 # ------------------------------------------------------------------------------------------------------------------
 def cpu_sample(w, y0, target, t, n_samples):
-    from oracle import phoenix_oracle as O
+    from oracle import phoenix_oracle as O   # the ONLY use of oracle/ in this file: the CPU baseline / reference arm
+    if not isinstance(w, O.Weights):
+        w = O.Weights(*w)
     evals = 0
     t0 = time.perf_counter()
     for i in range(n_samples):
@@ -203,7 +227,7 @@ def run_ours(args):
     w, y0_h, target_h, t_h = workload(2000 + rank, "cpu")
     net = pb.ODENet(dev, G, neurons=H)
     with torch.no_grad():
-        for p, src in zip(net.parameters(), w.as_list()):
+        for p, src in zip(net.parameters(), w):
             p.copy_(src)
     parallel.broadcast_parameters(net)
     lib = _lib.load()
