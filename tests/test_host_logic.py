@@ -63,6 +63,25 @@ def test_argument_errors_match_reference():
         pb.odeint(torch.nn.Linear(30, 30), y0, t)
 
 
+def test_odeint_adjoint_many_argument_checks():
+    """The opt-in many-samples entry: shape checks on the host, and no CPU fallback either."""
+    net = small_net()
+    y0 = torch.rand(3, 1, 30)
+    t = torch.tensor([[0.0, 1.0], [0.5, 1.5], [0.2, 0.3]])
+    with pytest.raises(AssertionError, match="per-sample times"):
+        pb.odeint_adjoint_many(net, y0, t[0])
+    with pytest.raises(AssertionError, match="same number of samples"):
+        pb.odeint_adjoint_many(net, y0, t[:2])
+    with pytest.raises(AssertionError, match="strictly increasing"):
+        pb.odeint_adjoint_many(net, y0, torch.tensor([[0.0, 1.0], [0.5, 1.5], [0.3, 0.2]]))
+    with pytest.raises(ValueError, match='Invalid method "foo"'):
+        pb.odeint_adjoint_many(net, y0, t, method="foo")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        pb.odeint_adjoint_many(net, y0, t, method="rk4")
+    assert pb.engine._problems_per_launch(2) == 8 and pb.engine._problems_per_launch(3) == 5
+    assert pb.engine._problems_per_launch(17) == 1
+
+
 def test_normalise_time_handling():
     net = small_net()
     y0 = torch.rand(1, 30)
