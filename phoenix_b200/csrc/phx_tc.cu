@@ -375,35 +375,80 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         const bool rok = row < p.B;
         const float rscale = (MODE && TRANS && p.ascale && rok) ? __ldg(p.ascale + row) : 1.f;
         const unsigned a_off = (unsigned)phx_tc_btile_off(128, rl, kc * 4) * 4u;
-        // y is read in super-blocks of K1_PF k-blocks: all loads of the NEXT super-block (K1_PF x 64 contiguous bytes
-        // of this thread's row, requested back to back with a 256-byte L2 prefetch hint so that DRAM sees whole
-        // bursts of one page) are in flight while the current super-block is converted and handed to the MMAs.
+        // y is read in super-blocks of K1_PF k-blocks, the loads of the NEXT super-block in flight while the current one is
+        // converted and handed to the MMAs.
+        //   TRANS = 1: lanes run along the genes, each load instruction of a warp is one contiguous 128-byte piece.
+        //   TRANS = 0: a thread's own elements (row lane%8, 4 floats of a 64-byte k-block piece) would make every load
+        //   instruction touch 8 rows x 2 sectors -- measured, the L1 wavefronts of those loads were what the producers
+        //   waited for.  Instead the warp loads its 8 rows COALESCED (lane = float index inside the row's 256-byte
+        //   super-block piece, two instructions per row) and redistributes through a private shared-memory staging
+        //   buffer (double buffered, rows padded to 68 floats: conflict-free 128-bit reads), __syncwarp only.
         float cur[K1_PF][4], nxt[K1_PF][4];
+        constexpr int SBF = K1_PF * BK;          // floats of one row in a super-block (64)
+        constexpr int SROW = SBF + 4;            // padded row stride of the staging buffer
+        float* stg = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + 256) + (size_t)warp * 2 * 8 * SROW;
+        const float padv = MODE ? 0.f : 0.5f;    // pads contribute zero: s(0.5) = l(0.5) = 0
         auto load = [&](int i, float (&v)[K1_PF][4]) {   // k-blocks kb0 + i .. kb0 + i + K1_PF - 1
+            if (TRANS) {
 #pragma unroll
-            for (int u = 0; u < K1_PF; ++u) {
+                for (int u = 0; u < K1_PF; ++u) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int g = (kb0 + i + u) * BK + kc * 4 + j;
-                    float t = MODE ? 0.f : 0.5f;   // pads contribute zero: s(0.5) = l(0.5) = 0
-                    if (rok && i + u < nkb && g < p.G) {
-                        if (TRANS) t = __ldg(src + (size_t)g * p.ld);
-                        else asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(src + g));
+                    for (int j = 0; j < 4; ++j) {
+                        const int g = (kb0 + i + u) * BK + kc * 4 + j;
+                        v[u][j] = (rok && i + u < nkb && g < p.G) ? __ldg(src + (size_t)g * p.ld) : padv;
                     }
-                    v[u][j] = t;
+                }
+            } else {
+                // v[rr/2][(rr%2)*2 + h] = element (lane + 32 h) of row rr of this warp
+                const int kvalid = min(p.G - (kb0 + i) * BK, (nkb - i) * BK);   // valid floats of the piece
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int row8 = m0 + warp * 8 + rr;
+                    const float* rp = p.y + (size_t)row8 * p.ld + (size_t)(kb0 + i) * BK;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int e = lane + 32 * h;
+                        float t = padv;
+                        if (row8 < p.B && e < kvalid)
+                            asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];" : "=f"(t) : "l"(rp + e));
+                        v[rr >> 1][(rr & 1) * 2 + h] = t;
+                    }
                 }
             }
         };
-        load(0, cur);
+        auto stage_put = [&](int buf, const float (&v)[K1_PF][4]) {   // TRANS = 0: registers -> staging buffer
+            float* d = stg + buf * 8 * SROW;
+#pragma unroll
+            for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) d[rr * SROW + lane + 32 * h] = v[rr >> 1][(rr & 1) * 2 + h];
+        };
         long long t_empty = 0, t0 = clock64();
         int s = 0;           // ring slot of k-block i
         unsigned ph = 0;     // its phase parity
+        int sbuf = 0;
+        if (TRANS) {
+            load(0, cur);
+        } else {
+            load(0, nxt);
+            stage_put(0, nxt);
+            __syncwarp();
+        }
         for (int i0 = 0; i0 < nkb; i0 += K1_PF) {
             if (i0 + K1_PF < nkb) load(i0 + K1_PF, nxt);
 #pragma unroll
             for (int u = 0; u < K1_PF; ++u) {
                 const int i = i0 + u;
                 if (i < nkb) {
+                    float xin[4];
+                    if (TRANS) {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) xin[j] = cur[u][j];
+                    } else {
+                        const float4 t =
+                            *reinterpret_cast<const float4*>(stg + sbuf * 8 * SROW + (lane & 7) * SROW + u * BK + kc * 4);
+                        xin[0] = t.x; xin[1] = t.y; xin[2] = t.z; xin[3] = t.w;
+                    }
                     float hi[4], lo[4];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -420,9 +465,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                                     sc = gi < p.G ? __ldg(p.ascale + gi) : 0.f;
                                 }
                             }
-                            sv = lv = cur[u][j] * sc;
+                            sv = lv = xin[j] * sc;
                         } else {
-                            hill(cur[u][j], sv, lv, br);
+                            hill(xin[j], sv, lv, br);
                         }
                         split_tf32(br ? lv : sv, hi[j], lo[j]);
                     }
@@ -445,10 +490,16 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     }
                 }
             }
+            if (TRANS) {
 #pragma unroll
-            for (int u = 0; u < K1_PF; ++u)
+                for (int u = 0; u < K1_PF; ++u)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
+                    for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
+            } else if (i0 + K1_PF < nkb) {
+                sbuf ^= 1;
+                stage_put(sbuf, nxt);   // the other buffer: last read one super-block ago (ordered by the __syncwarp)
+                __syncwarp();
+            }
         }
         if (p.prof && tid == 0) {
             unsigned long long* q = p.prof + 8 * br + 4;
@@ -1035,7 +1086,8 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     bp.y = src; bp.w1img = bimg; bp.spart = spart;
     bp.prof = phx_tc_prof_buffer();
     const size_t stage1 = K1_A_BYTES + (size_t)2 * Hb * BK * 4;
-    int S1 = (int)((PHX_SMEM_LIMIT - 256) / stage1);
+    const size_t staging = trans ? 0 : (size_t)K1_PWARPS * 2 * 8 * (K1_PF * BK + 4) * sizeof(float);
+    int S1 = (int)((PHX_SMEM_LIMIT - 256 - staging) / stage1);
     if (S1 > 6) S1 = 6;
     if (const char* e = getenv("PHX_TC_STAGES")) {   // experiment
         int v = atoi(e);
@@ -1047,7 +1099,7 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     }
     bp.stages = S1;
     set_attrs();
-    const size_t smem1 = (size_t)S1 * stage1 + 256;
+    const size_t smem1 = (size_t)S1 * stage1 + 256 + staging;
     if (!pair) {
         const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
         if (!trans) {
