@@ -237,3 +237,25 @@ def test_cta_pair_variant_is_bit_identical(pb):
         finally:
             lib.phx_tc_set_pair(0)
     assert torch.equal(f0, f1)
+
+
+@pytest.mark.parametrize("G,H,B,decay", [(129, 33, 5, True), (1001, 100, 257, True), (350, 40, 1000, False),
+                                         (37, 5, 130, True)])
+def test_tc_vjp_ragged_shapes(pb, G, H, B, decay):
+    """State and parameter cotangents on tcgen05 (gSP, u|v passes, the K = batch contractions with transposed loads) at
+    shapes where nothing is a multiple of a tile: genes % 128, rows % 16, hidden % 16 all non-zero."""
+    w = O.make_weights(G, H, 500 + G, dense=True, neg_mult_frac=0.2)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(G + B)
+    y = torch.rand(B, G, generator=gen) * 1.4 - 0.2
+    g = torch.randn(B, G, generator=gen)
+    yg = y.cuda().requires_grad_(True)
+    fn = net.forward if decay else net.prior_only_forward
+    fn(None, yg).backward(g.cuda())
+    _, ybar, pbar = O.rhs_vjp(w, y, g, decay=decay)
+    assert rel_l2(yg.grad.cpu(), ybar) < 1e-5
+    for i, (p, ref) in enumerate(zip(net.parameters(), pbar)):
+        if i == 0 and not decay:
+            assert p.grad is None or not p.grad.any()
+        else:
+            assert rel_l2(p.grad.cpu(), ref) < 2e-5, (i, rel_l2(p.grad.cpu(), ref))
