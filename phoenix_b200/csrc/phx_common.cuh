@@ -255,6 +255,8 @@ int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const flo
 // ybar = (GS_s Ws + (GS_p Wp)/(1+s)) / (1+|y-.5|)^2 - g relu(m); if J != 0 also the un-decayed joint J = [S|P] WA^T
 int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
                             float* ybar, const float* SP, float* GS, float* J, float* tcws, cudaStream_t stream);
+int phx_tc_joint_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
+                        float* tcws, cudaStream_t stream);
 int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
                              float* grads_flat, int accumulate, float* tcws, cudaStream_t stream);
 

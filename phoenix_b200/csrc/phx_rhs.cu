@@ -235,8 +235,12 @@ __global__ void decay_kernel(const float* J, const float* y, const float* relum,
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         f_out[i] = fscale * (relum[i % G] * (J[i] - y[i]));
 }
+// m_bar[g] = mask[g] * sum_b g[b][g] * (J - y)[b][g].  from_f != 0: `f_nodecay` is the finished RHS value
+// f = fscale * relu(m) * (J - y) instead of J, and (J - y) is recovered per gene after the column sum
+// (mask[g] != 0  <=>  relu(m)[g] > 0).
 __global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const float* y, const float* maskm, int B,
-                                   int G, float* m_bar, int accumulate, int decay) {
+                                   int G, float* m_bar, int accumulate, int decay, int from_f, const float* relum,
+                                   float fscale) {
     __shared__ float sh[CS][CS + 1];
     const int gg = blockIdx.x * CS + threadIdx.x;
     const bool ok = gg < G;
@@ -244,11 +248,12 @@ __global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const
     if (ok && decay)
         for (int b = threadIdx.y; b < B; b += CS) {
             size_t i = (size_t)b * G + gg;
-            t += g[i] * (f_nodecay[i] - y[i]);
+            t += from_f ? g[i] * f_nodecay[i] : g[i] * (f_nodecay[i] - y[i]);
         }
     t = colsum_fold(t, sh);
     if (ok && threadIdx.y == 0) {
-        t = decay ? t * maskm[gg] : 0.f;
+        if (!decay || maskm[gg] == 0.f) t = 0.f;
+        else if (from_f) t = t / (fscale * relum[gg]);
         m_bar[gg] = accumulate ? m_bar[gg] + t : t;
     }
 }
@@ -307,6 +312,7 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
     const float* WA = reinterpret_cast<const float*>(w.WA);
     const bool tc = w.tc && phx_tc_shape_ok(H, B);
     const bool needJ = (f_out != nullptr) || (grads && decay);
+    bool direct_f = false;
     if (tc) {
         // tensor cores: [S|P], gSP, the state cotangent and the un-decayed joint (phx_tc.cu); the K = B parameter
         // contractions below stay on the fp32 path
@@ -315,8 +321,15 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
         if (!(accumulate_flags & 2))   // bit 1: the workspace still holds [S|P] (+ images) of this (weights, y)
             rc = phx_tc_rhs_forward_launch(G, H, B, w, y, nullptr, 0, 1.f, SP, tcws, st);
         if (rc != PHX_OK) return rc;
-        rc = phx_tc_vjp_state_launch(G, H, B, w, y, g, decay, ybar, SP, GS, needJ ? J : nullptr, tcws, st);
+        // with the decay term and an RHS output requested (the streaming adjoint) the joint kernel writes f itself and
+        // the multiplier cotangent is recovered from it: no un-decayed J, no separate decay pass
+        direct_f = f_out != nullptr && decay;
+        rc = phx_tc_vjp_state_launch(G, H, B, w, y, g, decay, ybar, SP, GS, (needJ && !direct_f) ? J : nullptr, tcws, st);
         if (rc != PHX_OK) return rc;
+        if (direct_f) {
+            rc = phx_tc_joint_launch(G, H, B, w, y, f_out, 1, fscale, tcws, st);
+            if (rc != PHX_OK) return rc;
+        }
     } else {
         rhs_sp(G, H, B, w, y, SP, st);
         // GS = gJ WA, prods half scaled by Pr
@@ -347,7 +360,7 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
             sgemm(B, G, K2, la, lb, ep, st);
         }
     }
-    if (f_out) {
+    if (f_out && !direct_f) {
         size_t n = (size_t)B * G;
         int blocks = (int)((n + 255) / 256 < 4096 ? (n + 255) / 256 : 4096);
         if (decay) decay_kernel<<<blocks, 256, 0, st>>>(J, y, w.relum, G, n, fscale, f_out);
@@ -381,8 +394,9 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
         }
         colsum_bias_kernel<<<(2 * H + CS - 1) / CS, dim3(CS, CS), 0, st>>>(GS, B, K2, Hp, H, grads + off.bs,
                                                                            grads + off.bp, accumulate);
-        colsum_mult_kernel<<<(G + CS - 1) / CS, dim3(CS, CS), 0, st>>>(g, J, y, w.maskm, B, G, grads + off.m,
-                                                                       accumulate, decay);
+        colsum_mult_kernel<<<(G + CS - 1) / CS, dim3(CS, CS), 0, st>>>(g, direct_f ? f_out : J, y, w.maskm, B, G,
+                                                                       grads + off.m, accumulate, decay, direct_f,
+                                                                       w.relum, fscale);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

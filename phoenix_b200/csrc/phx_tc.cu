@@ -1219,6 +1219,15 @@ int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float
     return check_launch("tc vjp_state");
 }
 
+// after phx_tc_rhs_forward_launch on the same scratch: f = fscale * (decay ? relu(m) * (J - y) : J) from the [S|P] image
+int phx_tc_joint_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
+                        float* tcws, cudaStream_t st) {
+    const TcScratch sc = carve(G, H, B, tcws);
+    launch_joint(G, H, B, (w.tc == 1) ? 1 : 3, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 0, decay, fscale, y, nullptr, w.relum,
+                 f, st);
+    return check_launch("tc joint");
+}
+
 // after phx_tc_rhs_forward_launch and phx_tc_vjp_state_launch on the same scratch: the K = batch contractions
 //   Wa_bar[g][k] = sum_b (g relu(m))[b][g] [S|P][b][k],  Ws_bar[h][g] = sum_b gS[b][h] s[b][g],  Wp_bar likewise with l
 // (Linear backward, odenet.py:86-89), written / accumulated into the flat gradient vector.
