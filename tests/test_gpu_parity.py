@@ -391,3 +391,23 @@ def test_multi_problem_entry_points_check_their_limits(pb):
         ref = pb.odeint(net, y0[3], torch.tensor([0.0, 0.5]), method="rk4")
     assert torch.equal(yout[3], ref)
     assert all(int(st[i, 0]) == 0 and int(st[i, 3]) == 4 for i in range(8))     # code OK, 4 RHS evaluations each
+
+
+def test_many_reports_a_failing_problem_and_finishes_the_others(pb):
+    """A solver assertion in one problem of a multi-problem launch (non-finite state, rk_common.py:176) is reported for
+    that problem only; the library stays usable and the other problems of the launch are solved."""
+    G, H, N = 3551, 120, 4
+    w = O.make_weights(G, H, 92, dense=True)
+    net = make_net(pb, w)
+    y0 = torch.rand(N, 1, G, generator=torch.Generator().manual_seed(13)).cuda()
+    t = torch.tensor([[0.0, 0.3]] * N)
+    bad = y0.clone()
+    bad[2, 0, 7] = float("inf")
+    with pytest.raises(AssertionError):
+        with torch.no_grad():
+            pb.odeint_adjoint_many(net, bad, t, method="dopri5")
+    pb.check_errors()            # nothing left pending
+    with torch.no_grad():
+        good = pb.odeint_adjoint_many(net, y0, t, method="dopri5")
+        ref = pb.odeint(net, y0[3], t[3], method="dopri5")
+    assert torch.isfinite(good).all() and torch.equal(good[3], ref)
