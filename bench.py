@@ -419,7 +419,8 @@ def run_ours(args):
             "roofline": {"bound": "hbm", "kernel": "phx_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "launch_ms": adj_ms, "algorithmic_bytes": alg,
-                         "per": "one sample's adjoint sweep (a launch holds up to 8)",
+                         "per": "one sample's adjoint sweep (a launch holds up to 8); achieved, launch_ms, "
+                                "algorithmic_bytes and traffic are all per sample",
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650"},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"
