@@ -383,10 +383,10 @@ def run_ours(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        # algorithmic bytes of one adjoint launch: per RHS-VJP evaluation the
-        # weights twice + y, a in + y', a' out; per attempted step one 8P-byte read-modify-write of the parameter
-        # cotangents, plus the two P-long norm reads of the initial step and the dense-output pass at the end
-        alg = n_vjp * (32.0 * G * H + 16.0 * G) + (n_attempts + 2.0) * 8.0 * P
+        # algorithmic bytes of one sample's adjoint sweep, exactly SURVEY.md 8(d): per RHS-VJP evaluation the weights
+        # twice + y, a in + y', a' out (32GH + 16G bytes); per attempted step ONE 8P-byte read-modify-write of the
+        # parameter cotangents.  Nothing else is counted.
+        alg = n_vjp * (32.0 * G * H + 16.0 * G) + n_attempts * 8.0 * P
         achieved = alg / (adj_ms * 1e-3) / 1e9
         traffic = None
         try:

@@ -155,7 +155,7 @@ int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, co
 /* Problem i: initial state y0 + i*B*G, its own T increasing times t_host[i*T .. i*T+T), outputs y_out + i*T*B*G, its own
  * step controller and its own status[i] (an array of N records).  The solves run one after the other inside ONE
  * persistent launch, so the weights are staged on chip once for all of them; results are bit-identical to N calls of
- * phx_solve_forward / phx_solve_adjoint.  Limits: the rows fit the resident kernels and N * T <= 16.
+ * phx_solve_forward / phx_solve_adjoint.  Limits: the rows fit the resident kernels and N * T <= 64.
  * Adjoint: y_saved / grad_y are [N][T][B][G], adj_y0 [N][B][G], grads_flat [N][P] (one cotangent vector per problem). */
 int phx_solve_forward_many(phx_ctx* ctx, int G, int H, int B, int N, const float* packed, const float* y0,
                            const double* t_host, int T, int t_is_f32, int method, double rtol, double atol,
@@ -183,6 +183,37 @@ int phx_stream_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* pac
                              const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
                              void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                              int steplog_cap, void* stream);
+
+/* ---- the sample loop of training_step as rows of ONE launch (train_insilico.py:128-130) ------------------------------- */
+/* N independent ONE-ROW problems (y0 [N][G], each with its own T increasing times t_host[i*T .. i*T+T), its own dopri5 step
+ * controller and its own status[i]) advance in lock-step, phx_rows_supported() of them at a time as the rows of one
+ * pass: the RHS is autonomous, so every weight-slice pass and every inter-CTA exchange serves all rows.  A problem's results
+ * are bit-identical whether it runs alone or beside others.  phx_rows_supported returns the rows per pass (0: the model's
+ * weight slices do not fit on chip -- use phx_solve_forward / phx_solve_adjoint).
+ * steplog (may be NULL): [N][steplog_cap][3] float64 rows of (t0, dt, accepted), one block per problem. */
+int phx_rows_supported(const phx_ctx* ctx, int G, int H, int adjoint);
+/* Host-only: out = {CTAs, genes per CTA, quad-warps, gene groups, genes per group, WA slice in shared (1) / tensor (2)
+ * memory, rows per pass, W1 row stride (float4), tensor-memory columns used, dynamic shared memory bytes}. */
+int phx_rows_plan_describe(int num_sms, int G, int H, int adjoint, int32_t out[10]);
+size_t phx_rows_workspace_bytes(const phx_ctx* ctx, int G, int H, int N, int T, int adjoint);
+/* y_out [N][T][G].  The workspace starts with the exchange area of phx_solve_workspace_init (same rules). */
+int phx_solve_forward_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const float* y0,
+                           const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol, double atol,
+                           int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
+                           phx_status* status, double* steplog, int steplog_cap, void* stream);
+/* OdeintAdjointMethod.backward (adjoint.py:32-162) of the N problems: y_saved / grad_y [N][T][G], adj_y0 [N][G], and the
+ * parameter cotangents SUMMED over the problems (what autograd accumulates into .grad) in the PACKED layout --
+ * W1bar[G][K2] | WAbar[G][K2] | biasbar[K2] | mbar[G], the layout of phx_pack_weights, phx_packed_grad_bytes() bytes,
+ * 16-byte aligned; accumulate != 0 adds to grads_packed_sum.  phx_unpack_grads converts to the reference's flat order
+ * (gene_multipliers, Wp, bp, Ws, bs, Wa), optionally accumulating into grads_flat. */
+int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const double* t_host, int T,
+                           int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_sum,
+                           int accumulate, void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                           int steplog_cap, void* stream);
+size_t phx_packed_grad_bytes(int G, int H);
+int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, float* grads_flat, int accumulate,
+                     void* stream);
 
 #ifdef __cplusplus
 }

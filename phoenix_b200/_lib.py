@@ -23,6 +23,8 @@ EXPORTS = [
     "phx_solve_workspace_bytes", "phx_solve_workspace_init_bytes", "phx_solve_workspace_init", "phx_solve_forward",
     "phx_solve_adjoint", "phx_solve_forward_many", "phx_solve_adjoint_many",
     "phx_stream_workspace_bytes", "phx_stream_solve_forward", "phx_stream_solve_adjoint",
+    "phx_rows_supported", "phx_rows_plan_describe", "phx_rows_workspace_bytes", "phx_solve_forward_rows",
+    "phx_solve_adjoint_rows", "phx_unpack_grads", "phx_packed_grad_bytes",
 ]
 
 
@@ -109,6 +111,26 @@ def _declare(lib):
     lib.phx_stream_solve_forward.restype = c_int
     lib.phx_stream_solve_adjoint.argtypes = adj
     lib.phx_stream_solve_adjoint.restype = c_int
+    lib.phx_rows_supported.argtypes = [c_void_p, c_int, c_int, c_int]
+    lib.phx_rows_supported.restype = c_int
+    lib.phx_rows_plan_describe.argtypes = [c_int] * 4 + [ctypes.POINTER(ctypes.c_int32)]
+    lib.phx_rows_plan_describe.restype = c_int
+    lib.phx_rows_workspace_bytes.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_int]
+    lib.phx_rows_workspace_bytes.restype = c_size_t
+    # (ctx, G, H, N, packed, y0, t, T, t_is_f32, reversed, method, rtol, atol, max_steps, y_out, ws, ws_bytes, status,
+    #  steplog, steplog_cap, stream)
+    lib.phx_solve_forward_rows.argtypes = fwd
+    lib.phx_solve_forward_rows.restype = c_int
+    # (ctx, G, H, N, packed, t, T, t_is_f32, method, rtol, atol, max_steps, y_saved, grad_y, adj_y0, grads_packed_sum,
+    #  accumulate, ws, ws_bytes, status, steplog, steplog_cap, stream)
+    lib.phx_solve_adjoint_rows.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_double), c_int, c_int,
+                                           c_int, c_double, c_double, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                           c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]
+    lib.phx_solve_adjoint_rows.restype = c_int
+    lib.phx_unpack_grads.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
+    lib.phx_unpack_grads.restype = c_int
+    lib.phx_packed_grad_bytes.argtypes = [c_int, c_int]
+    lib.phx_packed_grad_bytes.restype = c_size_t
 
 
 def load():

@@ -17,6 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libphoenix_b200.so")
 HEADERS = [os.path.join(CSRC, "phx_common.cuh"), os.path.join(CSRC, "phx_resident.cuh"), os.path.join(CSRC, "phx_tc.cuh"),
+           os.path.join(CSRC, "phx_rows.cuh"),
            os.path.join(HERE, "..", "include", "phoenix_b200.h")]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -28,6 +29,7 @@ NVCC_FLAGS = [
 UNITS = [("phx_api", "phx_api.cu", []), ("phx_plan", "phx_plan.cu", []), ("phx_rhs", "phx_rhs.cu", []),
          ("phx_stream", "phx_stream.cu", []), ("phx_microbench", "phx_microbench.cu", []), ("phx_tc", "phx_tc.cu", [])]
 for kind in (0, 1):
+    UNITS.append(("phx_rows_%s" % ("adj" if kind else "fwd"), "phx_rows_inst.cu", ["-DPHX_KIND_ADJ=%d" % kind]))
     for nv in (1, 2, 4):
         UNITS.append(("phx_res_%s_nv%d" % ("adj" if kind else "fwd", nv), "phx_resident_inst.cu",
                       ["-DPHX_KIND_ADJ=%d" % kind, "-DPHX_NV=%d" % nv]))

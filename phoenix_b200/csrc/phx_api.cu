@@ -58,6 +58,49 @@ __global__ void pack_kernel(int G, int H, int Hp, int K2, const float* __restric
     }
 }
 
+
+// packed-layout cotangents (phx_packed_grad_offsets) -> the reference's flat order (phx_grad_offsets).  The two branch
+// matrices are transposed ([G][K2] gene-major -> [H][G]) through a 32 x 33 shared-memory tile so that both the reads
+// (along k) and the writes (along g) are coalesced.
+__global__ void unpack_w1_kernel(int G, int H, int Hp, int K2, const float* __restrict__ w1bar, float* __restrict__ Ws,
+                                 float* __restrict__ Wp, int accumulate) {
+    __shared__ float tile[32][33];
+    const int g0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int g = g0 + r, k = k0 + threadIdx.x;
+        tile[r][threadIdx.x] = (g < G && k < K2) ? w1bar[(size_t)g * K2 + k] : 0.f;
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int k = k0 + r, g = g0 + threadIdx.x;
+        if (g >= G || k >= K2) continue;
+        const int half = k >= Hp, h = half ? k - Hp : k;
+        if (h >= H) continue;
+        float* dst = (half ? Wp : Ws) + (size_t)h * G + g;
+        const float v = tile[threadIdx.x][r];
+        *dst = accumulate ? *dst + v : v;
+    }
+}
+__global__ void unpack_rest_kernel(int G, int H, int Hp, int K2, const float* __restrict__ wabar,
+                                   const float* __restrict__ biasbar, const float* __restrict__ mbar,
+                                   float* __restrict__ Wa, float* __restrict__ bs, float* __restrict__ bp,
+                                   float* __restrict__ m, int accumulate) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t n = (size_t)G * 2 * H;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const size_t g = i / (2 * H);
+        const int kk = (int)(i - g * 2 * H);
+        const float v = wabar[g * K2 + (kk < H ? kk : Hp + kk - H)];
+        Wa[i] = accumulate ? Wa[i] + v : v;
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)H; i += stride) {
+        bs[i] = accumulate ? bs[i] + biasbar[i] : biasbar[i];
+        bp[i] = accumulate ? bp[i] + biasbar[Hp + i] : biasbar[Hp + i];
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)G; i += stride)
+        m[i] = accumulate ? m[i] + mbar[i] : mbar[i];
+}
+
 bool check_dims(int G, int H, int B) {
     if (G < 1 || H < 1 || B < 1) {
         phx_set_error("invalid dims G=%d H=%d B=%d", G, H, B);
@@ -391,6 +434,169 @@ int phx_solve_adjoint_many(phx_ctx* ctx, int G, int H, int B, int N, const float
     p.adj_stride = (long long)B * G;
     p.theta_stride = (long long)phx_grad_offsets(G, H).total;
     return phx_resident_launch(p, plan, (cudaStream_t)stream);
+}
+
+
+/* ---- rows kernels: N independent one-row problems in lock-step (phx_rows.cuh) ------------------------------------------- */
+static int rows_common(phx_ctx* ctx, int G, int H, int N, const float* packed, const double* t_host, int T, int t_is_f32,
+                       int method, double rtol, double atol, int64_t max_num_steps, int adjoint, void* workspace,
+                       size_t workspace_bytes, phx_status* status, double* steplog, int steplog_cap, cudaStream_t stream,
+                       ResParams* p, RowsPlan* plan, size_t* off_theta) {
+    if (!ctx || !check_dims(G, H, 1) || !packed || !t_host || !workspace || N < 1) {
+        if (g_err[0] == 0) phx_set_error("null argument");
+        return PHX_ERR_INVALID;
+    }
+    if (T < 2) {
+        phx_set_error("t must hold at least two time points (got %d)", T);
+        return PHX_ERR_INVALID;
+    }
+    for (int q = 0; q < N; ++q)
+        for (int i = 1; i < T; ++i)
+            if (!(t_host[q * T + i] > t_host[q * T + i - 1])) {
+                phx_set_error("t must be strictly increasing at the C boundary (the Python shim negates decreasing t)");
+                return PHX_ERR_INVALID;
+            }
+    if (method < PHX_EULER || method > PHX_DOPRI5) {
+        phx_set_error("unknown method id %d", method);
+        return PHX_ERR_INVALID;
+    }
+    if (((uintptr_t)workspace & 127) || ((uintptr_t)packed & 15)) {
+        phx_set_error("workspace must be 128-byte and packed weights 16-byte aligned");
+        return PHX_ERR_INVALID;
+    }
+    int rc = phx_rows_plan(ctx->num_sms, G, H, adjoint, plan);
+    if (rc != PHX_OK) return rc;
+    size_t o_t;
+    const size_t need = phx_rows_workspace_floats(G, H, N, T, plan->rows, adjoint, &o_t, off_theta) * sizeof(float);
+    if (workspace_bytes < need) {
+        phx_set_error("rows workspace too small: %zu < %zu", workspace_bytes, need);
+        return PHX_ERR_WORKSPACE;
+    }
+    float* ws = (float*)workspace;
+    memset(p, 0, sizeof(*p));
+    p->G = G; p->H = H; p->Hp = phx_Hp(H); p->K2 = 2 * p->Hp; p->K2q = p->K2 / 4; p->B = 1; p->T = T;
+    p->method = method; p->gpc = plan->gpc; p->t_is_f32 = t_is_f32; p->adjoint = adjoint;
+    p->ring_rows = plan->w1_stride_q;   // rows kernels: W1 row stride in shared memory (float4 units)
+    p->ring_stages = 0;
+    p->so = plan->so;
+    p->rtol_f = (float)rtol; p->atol_f = (float)atol; p->fsign = 1.f;
+    p->max_steps = (long long)max_num_steps;
+    p->w = phx_packed_view(packed, G, H);
+    p->ll = phx_ll_view(workspace);
+    p->t = (const double*)(ws + o_t);
+    p->status = status; p->steplog = steplog; p->steplog_cap = steplog ? steplog_cap : 0;
+    p->prof = ctx->prof;
+    p->nprob = 1;
+    p->rows = plan->rows; p->ntot = N; p->nqw = plan->nqw; p->ngg = plan->ngg; p->gpg = plan->gpg;
+    p->tm_wa = plan->tm_wa; p->tm_fac = plan->tm_fac;
+    p->y0_stride = G; p->yout_stride = (long long)T * G; p->adj_stride = G;
+    p->ppk = (long long)phx_packed_grad_offsets(G, H).total;
+    if ((size_t)T * N <= PHX_T_INLINE) {
+        for (int i = 0; i < T * N; ++i) p->t_small[i] = t_host[i];
+        return PHX_OK;
+    }
+    cudaError_t e = cudaMemcpyAsync((void*)p->t, t_host, sizeof(double) * T * N, cudaMemcpyHostToDevice, stream);
+    if (e != cudaSuccess) {
+        phx_set_error("cudaMemcpyAsync(t): %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+int phx_rows_supported(const phx_ctx* ctx, int G, int H, int adjoint) {
+    if (!ctx) return 0;
+    RowsPlan plan;
+    return phx_rows_plan(ctx->num_sms, G, H, adjoint, &plan) == PHX_OK ? plan.rows : 0;
+}
+
+int phx_rows_plan_describe(int num_sms, int G, int H, int adjoint, int32_t out[10]) {
+    RowsPlan plan;
+    if (!out || !check_dims(G, H, 1)) return PHX_ERR_INVALID;
+    int rc = phx_rows_plan(num_sms, G, H, adjoint, &plan);
+    if (rc != PHX_OK) return rc;
+    out[0] = plan.nCTA; out[1] = plan.gpc; out[2] = plan.nqw; out[3] = plan.ngg; out[4] = plan.gpg;
+    out[5] = plan.wa_res; out[6] = plan.rows; out[7] = plan.w1_stride_q;
+    out[8] = plan.tm_wa + (adjoint ? 2 * PHX_ROWS_NFS * 4 * plan.rows : 0);
+    out[9] = (int32_t)plan.smem_bytes;
+    return PHX_OK;
+}
+
+size_t phx_rows_workspace_bytes(const phx_ctx* ctx, int G, int H, int N, int T, int adjoint) {
+    if (!ctx || N < 1 || T < 2) return 0;
+    RowsPlan plan;
+    if (phx_rows_plan(ctx->num_sms, G, H, adjoint, &plan) != PHX_OK) return 0;
+    return phx_rows_workspace_floats(G, H, N, T, plan.rows, adjoint, nullptr, nullptr) * sizeof(float);
+}
+
+int phx_solve_forward_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const float* y0, const double* t_host,
+                           int T, int t_is_f32, int reversed, int method, double rtol, double atol, int64_t max_num_steps,
+                           float* y_out, void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                           int steplog_cap, void* stream) {
+    g_err[0] = 0;
+    if (!y0 || !y_out) {
+        phx_set_error("null y0 / y_out");
+        return PHX_ERR_INVALID;
+    }
+    ResParams p;
+    RowsPlan plan;
+    int rc = rows_common(ctx, G, H, N, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 0, workspace,
+                         workspace_bytes, status, steplog, steplog_cap, (cudaStream_t)stream, &p, &plan, nullptr);
+    if (rc != PHX_OK) return rc;
+    p.y0 = y0;
+    p.yout = y_out;
+    p.fsign = reversed ? -1.f : 1.f;
+    return phx_rows_launch(p, plan, (cudaStream_t)stream);
+}
+
+int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, float* grads_flat, int accumulate,
+                     void* stream) {
+    if (!ctx || !check_dims(G, H, 1) || !packed_grads || !grads_flat) return PHX_ERR_INVALID;
+    const int Hp = phx_Hp(H), K2 = 2 * Hp;
+    const PhxPackedGradOff po = phx_packed_grad_offsets(G, H);
+    const PhxGradOff fo = phx_grad_offsets(G, H);
+    dim3 grid((G + 31) / 32, (K2 + 31) / 32), block(32, 8);
+    unpack_w1_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(G, H, Hp, K2, packed_grads + po.W1, grads_flat + fo.Ws,
+                                                               grads_flat + fo.Wp, accumulate);
+    unpack_rest_kernel<<<ctx->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(
+        G, H, Hp, K2, packed_grads + po.WA, packed_grads + po.bias, packed_grads + po.m, grads_flat + fo.Wa,
+        grads_flat + fo.bs, grads_flat + fo.bp, grads_flat + fo.m, accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("unpack_grads launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+size_t phx_packed_grad_bytes(int G, int H) { return phx_packed_grad_offsets(G, H).total * sizeof(float); }
+
+int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const double* t_host, int T,
+                           int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
+                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_sum,
+                           int accumulate, void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                           int steplog_cap, void* stream) {
+    g_err[0] = 0;
+    if (!y_saved || !grad_y || !adj_y0 || !grads_packed_sum) {
+        phx_set_error("null y_saved / grad_y / adj_y0 / grads_packed_sum");
+        return PHX_ERR_INVALID;
+    }
+    if ((uintptr_t)grads_packed_sum & 15) {
+        phx_set_error("grads_packed_sum must be 16-byte aligned");
+        return PHX_ERR_INVALID;
+    }
+    ResParams p;
+    RowsPlan plan;
+    size_t o_th = 0;
+    int rc = rows_common(ctx, G, H, N, packed, t_host, T, t_is_f32, method, rtol, atol, max_num_steps, 1, workspace,
+                         workspace_bytes, status, steplog, steplog_cap, (cudaStream_t)stream, &p, &plan, &o_th);
+    if (rc != PHX_OK) return rc;
+    p.ysaved = y_saved;
+    p.grad_y = grad_y;
+    p.adj_y0 = adj_y0;
+    p.theta_ws = (float*)workspace + o_th;
+    p.gsum = grads_packed_sum;
+    p.gsum_acc = accumulate;
+    return phx_rows_launch(p, plan, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -82,6 +82,23 @@ static inline __host__ __device__ PhxGradOff phx_grad_offsets(int G, int H) {
     return o;
 }
 
+// Parameter cotangents in the PACKED layout = the layout of the packed weights themselves: W1bar[G][K2] (row g =
+// [Wsbar[:, g] | Wpbar[:, g]]), WAbar[G][K2], biasbar[K2] ([bs | bp]), mbar[G]; every row 16-byte aligned, the rows of one
+// CTA's gene slice contiguous.  phx_unpack_grads converts to the reference's flat order.
+struct PhxPackedGradOff {
+    size_t W1, WA, bias, m, total;
+};
+static inline __host__ __device__ PhxPackedGradOff phx_packed_grad_offsets(int G, int H) {
+    const size_t K2 = (size_t)phx_K2(H);
+    PhxPackedGradOff o;
+    o.W1 = 0;
+    o.WA = (size_t)G * K2;
+    o.bias = 2 * (size_t)G * K2;
+    o.m = o.bias + K2;
+    o.total = (o.m + (size_t)G + 3) & ~(size_t)3;
+    return o;
+}
+
 // ---- inter-CTA exchange area ("LL" = low-latency tagged slots), at the START of every resident-solver workspace -----
 // Each slot is one naturally aligned 64-bit word {fp32 payload, 32-bit epoch tag} written with a single relaxed
 // gpu-scope store and polled with relaxed gpu-scope loads until the tag matches: the payload arrives with its flag, so
@@ -91,7 +108,7 @@ static inline __host__ __device__ PhxGradOff phx_grad_offsets(int G, int H) {
 #define PHX_LL_MAXC 160                      /* CTAs (>= SM count of any sm_100 part)                    */
 #define PHX_LL_NMAX 4096                     /* longest all-reduced vector: max rows (8) x max K2 (512)  */
 #define PHX_LL_YMAX 16384                    /* one-phase exchange: nCTA * n <= YMAX                     */
-#define PHX_LL_DMAX 16                       /* scalar (norm) exchange: floats per CTA                   */
+#define PHX_LL_DMAX 64                       /* scalar (norm) exchange: floats per CTA (hi/lo pairs of <= 32 sums) */
 #define PHX_LL_RCOPIES 8                     /* replicas of every reduced result: CTA c polls copy c % R, so the
                                                 readers of one exchange spread over R x as many L2 slices */
 struct PhxLL {
@@ -128,8 +145,13 @@ struct SmemOff {
     unsigned ring, bar, resbar, ctrl, dred, gram, dst16, ystage, bias, relum, maskm, sp, xv, red, st;
     unsigned acts, actl, ysb, jb, acts2, actl2, ysb2, asb, gjb, ub, vb, mt;
     unsigned FG, FSP, FS, FL, FGJ, FM, ppa;
+    // rows kernels (phx_rows.cuh): J partials per quad-warp, stage inputs kept for the theta passes, next-stage
+    // activation staging, per-row controller block, per-row block sums
+    unsigned jred, ysf, actS, actL, rctl, rsum;
 };
 #define PHX_CTRL_BYTES 1024  /* >= sizeof(Ctrl) in phx_resident.cuh (static_assert there) */
+#define PHX_ROWS_MAX 4        /* independent problems in lock-step per pass of the rows kernels */
+#define PHX_RCTL_BYTES 2048   /* >= sizeof(RowsCtl) in phx_rows.cuh (static_assert there) */
 
 static inline int phx_QB(int B) { return (7 * (B > 1 ? 4 : 1) + 3) & ~3; }
 static inline bool phx_use_y(int nCTA, int B, int K2, int adjoint) {
@@ -200,7 +222,7 @@ struct ResParams {
     long long max_steps;
     PhxPacked w;
     const double* t;       // [T] device copy of the output times (only used when T > PHX_T_INLINE)
-    double t_small[16];    // the output times themselves when T <= PHX_T_INLINE (no host->device copy per call)
+    double t_small[64];    // the output times themselves when nprob * T <= PHX_T_INLINE (no host->device copy per call)
     // forward
     const float* y0;       // [B][G]
     float* yout;           // [T][B][G]
@@ -220,15 +242,90 @@ struct ResParams {
     double* steplog;
     int steplog_cap;
     long long* prof;       // optional [PHX_PROF_SLOTS] phase-timer accumulators (phx_ctx_set_profile), else nullptr
+    // rows kernels (phx_rows.cuh): `ntot` independent one-row problems, `rows` of them in lock-step per pass, each with its
+    // own step controller; thread mapping constants; parameter cotangents in the PACKED layout (phx_packed_grad_*)
+    int rows, ntot, nqw, ngg, gpg, tm_wa, tm_fac;
+    float* theta_ws;       // [rows][2][ppk] per-row packed cotangent double buffers (workspace)
+    float* gsum;           // [ppk] packed cotangents summed over all problems of the launch
+    int gsum_acc;          // != 0: add to gsum instead of overwriting it
+    long long ppk;
 };
 #define PHX_PROF_SLOTS 32
-#define PHX_T_INLINE 16
+#define PHX_T_INLINE 64
 
 struct ResLaunchPlan {
     int nCTA, gpc, NV, ring_rows, ring_stages, w1_res, wa_res;
     size_t smem_bytes;
     SmemOff so;
 };
+
+
+// ---- rows kernels (phx_rows.cuh): shared-memory layout and launch plan --------------------------------------------------
+#define PHX_ROWS_NFS 6   /* factor slots per row: dopri5 stages {0,2,3,4,5,6} (stage 1 has zero weight in the solution,
+                            error and mid-point combinations, dopri5.py:15-30); rk4: its 4 stages */
+struct RowsPlan {
+    int nCTA, gpc, nqw, ngg, gpg, wa_res, rows, w1_stride_q, tm_wa, tm_fac;
+    size_t smem_bytes;
+    SmemOff so;
+};
+// wa_res: 1 = WA slice in shared memory, 2 = in tensor memory.  Per-(gene,row) arrays are [gpc][PHX_ROWS_MAX].
+static inline size_t phx_rows_smem_layout(int nCTA, int K2, int gpc, int adjoint, int wa_res, int nqw, int w1_stride_q,
+                                          SmemOff* o) {
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t at = off;
+        off += (bytes + 15) & ~size_t(15);
+        return (unsigned)at;
+    };
+    SmemOff t;
+    const unsigned none = PHX_NONE;
+    const int RMx = PHX_ROWS_MAX, ngg = PHX_WARPS / nqw;
+    const size_t bl = sizeof(float) * RMx * gpc;
+    t.w1r = take(sizeof(float) * 4 * (size_t)gpc * w1_stride_q);
+    t.war = wa_res == 1 ? take(sizeof(float) * (size_t)gpc * K2) : none;
+    t.watm = take(16);                       // tcgen05.alloc result (tensor memory is always allocated: factor tables)
+    t.ring = none;
+    t.bar = take(sizeof(unsigned long long));
+    t.resbar = take(sizeof(unsigned long long));
+    t.ctrl = take(PHX_CTRL_BYTES);           // phase-timer staging lives in its tail, as in the resident kernels
+    t.rctl = take(PHX_RCTL_BYTES);
+    t.dred = take(sizeof(double) * PHX_WARPS * 8);
+    t.rsum = take(sizeof(double) * (PHX_WARPS + 1) * RMx * 8);
+    t.gram = adjoint ? take(sizeof(double) * 4 * RMx * 12) : none;
+    t.dst16 = take(sizeof(float) * PHX_LL_DMAX);
+    const int nvec = RMx * K2 * (adjoint ? 2 : 1);
+    t.ystage = ((size_t)nCTA * nvec <= 4096) ? take(sizeof(float) * (size_t)nCTA * nvec) : none;
+    t.bias = take(sizeof(float) * K2);
+    t.relum = take(sizeof(float) * gpc);
+    t.maskm = take(sizeof(float) * gpc);
+    t.sp = take(sizeof(float) * RMx * K2);
+    t.xv = adjoint ? take(sizeof(float) * 2 * RMx * K2) : none;
+    // cross-group fold buffer [ngg/2][RM][K2] followed by the J partials [nqw][gpc][RM]: together they are the scratch
+    // of the theta passes (per-gene activation tables rebuilt from the stored stage inputs)
+    t.red = take(sizeof(float) * (ngg / 2) * RMx * K2);
+    t.jred = take(sizeof(float) * nqw * RMx * gpc);
+    if (adjoint) {
+        const size_t have = off - t.red, need = 2 * sizeof(float) * PHX_ROWS_NFS * RMx * gpc;
+        if (have < need) take(need - have);
+    }
+    t.st = take((adjoint ? 18 : 9) * bl);
+    t.ysb = take(bl); t.acts = take(bl); t.actL = take(bl);
+    t.actl = t.jb = none;
+    t.acts2 = t.actl2 = t.ysb2 = t.asb = t.gjb = t.ub = t.vb = t.mt = none;
+    t.FG = t.FSP = t.FS = t.FL = t.FGJ = t.FM = t.ppa = t.ysf = t.actS = none;
+    if (adjoint) {
+        t.ysb2 = take(bl); t.acts2 = take(bl); t.asb = take(bl); t.gjb = take(bl);
+        t.ysf = take(PHX_ROWS_NFS * bl);
+        t.FGJ = take(PHX_ROWS_NFS * bl);
+        t.FM = take(PHX_ROWS_NFS * bl);
+        t.ppa = take(1024);
+    }
+    if (o) *o = t;
+    return off;
+}
+int phx_rows_plan(int num_sms, int G, int H, int adjoint, RowsPlan* plan);
+size_t phx_rows_workspace_floats(int G, int H, int N, int T, int rows, int adjoint, size_t* off_t, size_t* off_theta);
+int phx_rows_launch(const ResParams& p, const RowsPlan& plan, cudaStream_t stream);
 
 // host helpers implemented in phx_resident.cu
 int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPlan* plan);

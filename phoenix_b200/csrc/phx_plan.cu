@@ -118,3 +118,75 @@ int phx_resident_launch(const ResParams& p, const ResLaunchPlan& plan, cudaStrea
     if (plan.NV == 2) return phx_launch_fwd_nv2(p, plan, stream);
     return phx_launch_fwd_nv4(p, plan, stream);
 }
+
+
+// ---- rows kernels ------------------------------------------------------------------------------------------------------
+int phx_launch_rows_fwd(const ResParams&, const RowsPlan&, cudaStream_t);
+int phx_launch_rows_adj(const ResParams&, const RowsPlan&, cudaStream_t);
+
+int phx_rows_plan(int num_sms, int G, int H, int adjoint, RowsPlan* plan) {
+    const int K2 = phx_K2(H), K2q = K2 / 4;
+    if (K2q > 128) {
+        phx_set_error("rows solver supports neurons <= 256 (got H=%d)", H);
+        return PHX_ERR_UNSUPPORTED;
+    }
+    if (getenv("PHX_NO_ROWS")) {
+        phx_set_error("rows solver disabled (PHX_NO_ROWS)");
+        return PHX_ERR_UNSUPPORTED;
+    }
+    if (num_sms > PHX_LL_MAXC) num_sms = PHX_LL_MAXC;
+    int gpc = (G + num_sms - 1) / num_sms;
+    int gmin = (G >= 256 && G <= 2048) ? 32 : 16;
+    if (const char* e = getenv("PHX_MIN_GENES_PER_CTA")) gmin = atoi(e) > 0 ? atoi(e) : gmin;
+    if (gpc < gmin) gpc = gmin;
+    const int nCTA = (G + gpc - 1) / gpc;
+    // a quad-warp covers 32 float4 columns of the K2-long rows; the 16 warps are nqw quad-warps x ngg gene groups
+    int nqw = K2q <= 32 ? 1 : (K2q <= 64 ? 2 : 4);
+    // W1 rows are padded in shared memory so that two consecutive rows are 64 bytes apart modulo 128: the
+    // (gene, 4 k-chunks) threads of the state-cotangent pass then hit distinct banks
+    int w1s = K2q;
+    while ((w1s & 7) != 4) ++w1s;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        const int ngg = PHX_WARPS / nqw;
+        const int gpg = phx_round_up((gpc + ngg - 1) / ngg, 4);
+        for (int wa_res = 1; wa_res <= 2; ++wa_res) {
+            if (wa_res == 2 && nqw != 4) continue;   // tensor-memory lanes are tied to the warp's quarter: lane = quad
+            const int tm_wa = wa_res == 2 ? 4 * ngg * gpg : 0;
+            int rows = PHX_ROWS_MAX;
+            if (adjoint)
+                while (rows > 0 && tm_wa + 2 * PHX_ROWS_NFS * 4 * rows > 512) --rows;
+            else if (tm_wa > 512) rows = 0;
+            if (rows == 0) continue;
+            SmemOff so;
+            size_t bytes = phx_rows_smem_layout(nCTA, K2, gpc, adjoint, wa_res, nqw, w1s, &so);
+            if (bytes > PHX_SMEM_LIMIT) continue;
+            plan->nCTA = nCTA; plan->gpc = gpc; plan->nqw = nqw; plan->ngg = ngg; plan->gpg = gpg;
+            plan->wa_res = wa_res; plan->rows = rows; plan->w1_stride_q = w1s; plan->tm_wa = tm_wa;
+            plan->tm_fac = tm_wa; plan->smem_bytes = bytes; plan->so = so;
+            return PHX_OK;
+        }
+        if (nqw == 4) break;
+        nqw = 4;   // second attempt: the tensor-memory placement needs the 4 x 4 warp grid
+    }
+    phx_set_error("rows solver: the weight slices of G=%d H=%d do not fit on chip", G, H);
+    return PHX_ERR_UNSUPPORTED;
+}
+
+// workspace: [ LL exchange area | t[N*T] doubles | per-row packed cotangent double buffers (adjoint) ]
+size_t phx_rows_workspace_floats(int G, int H, int N, int T, int rows, int adjoint, size_t* off_t, size_t* off_theta) {
+    size_t off = phx_ll_words() * 2;
+    auto take = [&](size_t nfloats) {
+        size_t o = off;
+        off += (nfloats + 31) & ~size_t(31);
+        return o;
+    };
+    size_t o_t = take(2 * (size_t)T * N);
+    size_t o_th = adjoint ? take(2 * (size_t)rows * phx_packed_grad_offsets(G, H).total) : 0;
+    if (off_t) *off_t = o_t;
+    if (off_theta) *off_theta = o_th;
+    return off;
+}
+
+int phx_rows_launch(const ResParams& p, const RowsPlan& plan, cudaStream_t stream) {
+    return p.adjoint ? phx_launch_rows_adj(p, plan, stream) : phx_launch_rows_fwd(p, plan, stream);
+}

@@ -280,7 +280,8 @@ __device__ __forceinline__ void grid_sum_d(const ResParams& p, Smem& s, double* 
         if (!isfinite(hi)) w = hi;  // inf / nan: both halves carry it
         ll_put(p.ll.dpart + (size_t)blockIdx.x * PHX_LL_DMAX + threadIdx.x, w, tag);
     }
-    if (blockIdx.x == 0 && warp < nd) {
+    if (blockIdx.x == 0) {
+      for (int vi = warp; vi < nd; vi += WARPS) {   // one warp per value (nd <= PHX_LL_DMAX / 2)
         // every round (re)polls all five CTAs of the lane in one round trip; lanes past the grid re-read the last CTA
         // (unconditional loads keep the slots in registers)
         unsigned long long w0[5], w1[5];
@@ -290,7 +291,7 @@ __device__ __forceinline__ void grid_sum_d(const ResParams& p, Smem& s, double* 
 #pragma unroll
             for (int u = 0; u < 5; ++u) {
                 const int c = min(lane + 32 * u, nC - 1);
-                ll_ld2(p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * warp, w0[u], w1[u]);
+                ll_ld2(p.ll.dpart + (size_t)c * PHX_LL_DMAX + 2 * vi, w0[u], w1[u]);
             }
 #pragma unroll
             for (int u = 0; u < 5; ++u) ok = ok && (unsigned)(w0[u] >> 32) == tag && (unsigned)(w1[u] >> 32) == tag;
@@ -307,8 +308,9 @@ __device__ __forceinline__ void grid_sum_d(const ResParams& p, Smem& s, double* 
         if (lane < PHX_LL_RCOPIES) {
             float hi = (float)t;
             float lo = isfinite(hi) ? (float)(t - (double)hi) : hi;
-            ll_put2(p.ll.dres + (size_t)lane * PHX_LL_DMAX + 2 * warp, hi, lo, tag);
+            ll_put2(p.ll.dres + (size_t)lane * PHX_LL_DMAX + 2 * vi, hi, lo, tag);
         }
+      }
     }
     if (threadIdx.x < 2 * nd)
         s.dst16()[threadIdx.x] =

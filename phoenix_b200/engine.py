@@ -17,7 +17,7 @@ from . import _lib
 SYNC_ERRORS = False
 STEP_LOGGING = False
 STEPLOG_CAP = 4096
-FORCE_ENGINE = None  # None | "resident" | "stream"  (tests compare the two engines on the same inputs)
+FORCE_ENGINE = None  # None | "rows" | "resident" | "stream"  (tests compare the engines on the same inputs)
 
 class _State:
     """Process-wide bookkeeping (NOT thread-local: autograd runs backward() on its own worker thread)."""
@@ -28,6 +28,7 @@ class _State:
         self.free_status = []
         self.last_log = None
         self.last_status = None
+        self.last_status_block = None
         self.workspaces = {}
 
 
@@ -194,14 +195,20 @@ def check_errors(synchronize=True):
         _raise_for(*err)
 
 
-def last_step_log():
-    """(t0, dt, accepted) rows of the most recent solve (requires set_step_logging(True)); synchronises."""
+def last_step_log(problem=None):
+    """(t0, dt, accepted) rows of the most recent solve (requires set_step_logging(True)); synchronises.  After a
+    multi-problem call ``problem`` selects the sample (default: the last one, like a loop of single calls would leave)."""
     tls = _tls()
     if tls.last_log is None:
         return []
     torch.cuda.synchronize()
+    log = tls.last_log
+    if log.dim() == 3:
+        i = log.shape[0] - 1 if problem is None else problem
+        n = _status_struct(tls.last_status_block[i]).n_logged
+        return [tuple(r) for r in log[i, :n].tolist()]
     n = _status_struct(tls.last_status).n_logged
-    return [tuple(r) for r in tls.last_log[:n].tolist()]
+    return [tuple(r) for r in log[:n].tolist()]
 
 
 def last_status():
@@ -316,6 +323,79 @@ def _pick_engine(lib, dev, G, H, B, T, adjoint):
     return "stream", nb
 
 
+_rows_cache = {}
+
+
+def _rows_per_pass(lib, dev, G, H, adjoint):
+    """Rows (independent one-row problems) the rows kernels advance per pass for this model; 0: not supported."""
+    key = (dev, G, H, int(adjoint))
+    r = _rows_cache.get(key)
+    if r is None:
+        r = _rows_cache[key] = int(lib.phx_rows_supported(_lib.ctx(dev), G, H, int(adjoint)))
+    return r
+
+
+def _use_rows(lib, dev, G, H, B, adjoint):
+    """One-row problems go to the rows kernels (phx_rows.cuh) unless a test forces another engine."""
+    return B == 1 and FORCE_ENGINE in (None, "rows") and _rows_per_pass(lib, dev, G, H, adjoint) > 0
+
+
+def _steplog_rows(n):
+    tls = _tls()
+    if not STEP_LOGGING:
+        tls.last_log = None
+        return None, 0
+    log = torch.zeros(n, STEPLOG_CAP, 3, dtype=torch.float64).pin_memory()
+    tls.last_log = log
+    return log, STEPLOG_CAP
+
+
+def _forward_rows(lib, net, packed, G, H, dev, y0c, t_rows, t_is_f32, reversed_time, method, rtol, atol, max_num_steps,
+                  out_shape):
+    """N one-row problems (y0c [N, G]) in lock-step; returns yout of shape out_shape (= [N, T, ..., G] memory order)."""
+    N, T = len(t_rows), len(t_rows[0])
+    nb = lib.phx_rows_workspace_bytes(_lib.ctx(dev), G, H, N, T, 0)
+    ws = _workspace(dev, nb, "solve")
+    yout = torch.empty(out_shape, dtype=torch.float32, device=y0c.device)
+    stn = _new_status_block(N)
+    log, cap = _steplog_rows(N)
+    flat_t = (ctypes.c_double * (N * T))(*[x for r in t_rows for x in r])
+    rc = lib.phx_solve_forward_rows(_lib.ctx(dev), G, H, N, _ptr(packed), _ptr(y0c), flat_t, T, int(t_is_f32),
+                                    int(reversed_time), _lib.METHOD_IDS[method], float(rtol), float(atol),
+                                    int(max_num_steps), _ptr(yout), _ptr(ws), ws.numel(), _ptr(stn), _ptr(log), cap,
+                                    _stream_ptr(dev))
+    _lib.check(rc, "solve_forward_rows")
+    _tls().last_status_block = stn
+    for i in range(N):
+        _finish(stn[i], "forward solve %d" % i if N > 1 else "forward solve", dev)
+    return yout
+
+
+def _adjoint_rows(lib, net, packed, G, H, dev, t_rows, t_is_f32, method, rtol, atol, max_num_steps, ys, gy, adj_shape):
+    """Backward sweeps of N one-row problems (ys, gy: [N, T, ..., G] memory order): adj_y0 and the SUM over the problems of
+    the six parameter cotangents (flat, reference order)."""
+    N, T = len(t_rows), len(t_rows[0])
+    nb = lib.phx_rows_workspace_bytes(_lib.ctx(dev), G, H, N, T, 1)
+    ws = _workspace(dev, nb, "solve")
+    adj_y0 = torch.empty(adj_shape, dtype=torch.float32, device=ys.device)
+    gpk = torch.empty(lib.phx_packed_grad_bytes(G, H) // 4, dtype=torch.float32, device=ys.device)
+    P = 4 * G * H + 2 * H + G
+    flat = torch.empty(P, dtype=torch.float32, device=ys.device)
+    stn = _new_status_block(N)
+    log, cap = _steplog_rows(N)
+    flat_t = (ctypes.c_double * (N * T))(*[x for r in t_rows for x in r])
+    ctx, sp = _lib.ctx(dev), _stream_ptr(dev)
+    rc = lib.phx_solve_adjoint_rows(ctx, G, H, N, _ptr(packed), flat_t, T, int(t_is_f32), _lib.METHOD_IDS[method],
+                                    float(rtol), float(atol), int(max_num_steps), _ptr(ys), _ptr(gy), _ptr(adj_y0),
+                                    _ptr(gpk), 0, _ptr(ws), ws.numel(), _ptr(stn), _ptr(log), cap, sp)
+    _lib.check(rc, "solve_adjoint_rows")
+    _lib.check(lib.phx_unpack_grads(ctx, G, H, _ptr(gpk), _ptr(flat), 0, sp), "unpack_grads")
+    _tls().last_status_block = stn
+    for i in range(N):
+        _finish(stn[i], "adjoint solve %d" % i if N > 1 else "adjoint solve", dev)
+    return adj_y0, split_flat_grads(flat, G, H)
+
+
 def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, max_num_steps):
     packed, G, H, dev = packed_weights(net)
     if y0.shape[-1] != G:
@@ -326,6 +406,9 @@ def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, 
     B = y0c.numel() // G
     T = len(t_list)
     lib = _lib.load()
+    if _use_rows(lib, dev, G, H, B, False):
+        return _forward_rows(lib, net, packed, G, H, dev, y0c, [t_list], t_is_f32, reversed_time, method, rtol, atol,
+                             max_num_steps, (T,) + tuple(y0c.shape))
     engine, nb = _pick_engine(lib, dev, G, H, B, T, False)
     ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     yout = torch.empty((T,) + tuple(y0c.shape), dtype=torch.float32, device=y0c.device)
@@ -347,6 +430,9 @@ def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_sa
     T = len(t_list)
     B = ys[0].numel() // G
     lib = _lib.load()
+    if _use_rows(lib, dev, G, H, B, True):
+        return _adjoint_rows(lib, net, packed, G, H, dev, [t_list], t_is_f32, method, rtol, atol, max_num_steps, ys, gy,
+                             tuple(ys[0].shape))
     engine, nb = _pick_engine(lib, dev, G, H, B, T, True)
     ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     adj_y0 = torch.empty_like(ys[0])
@@ -437,6 +523,9 @@ def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_st
     N, T = len(t_rows), len(t_rows[0])
     B = y0c[0].numel() // G
     lib = _lib.load()
+    if _use_rows(lib, dev, G, H, B, False):
+        return _forward_rows(lib, net, packed, G, H, dev, y0c, t_rows, t_is_f32, False, method, rtol, atol, max_num_steps,
+                             (N, T) + tuple(y0c.shape[1:]))
     engine, nb = _pick_engine(lib, dev, G, H, B, T, False)
     ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     yout = torch.empty((N, T) + tuple(y0c.shape[1:]), dtype=torch.float32, device=y0c.device)
@@ -495,6 +584,9 @@ def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps,
     N, T = len(t_rows), len(t_rows[0])
     B = ys[0, 0].numel() // G
     lib = _lib.load()
+    if _use_rows(lib, dev, G, H, B, True):
+        return _adjoint_rows(lib, net, packed, G, H, dev, t_rows, t_is_f32, method, rtol, atol, max_num_steps, ys, gy,
+                             tuple(ys[:, 0].shape))
     engine, nb = _pick_engine(lib, dev, G, H, B, T, True)
     ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     adj_y0 = torch.empty_like(ys[:, 0])

@@ -74,3 +74,36 @@ def assert_logs_close(mine, ref, dt_rtol, what="", first_rtol=1e-4):
     att_tol = max(2, int(0.25 * len(ref))) if dt_rtol < 0.1 else max(3, int(0.4 * len(ref)))
     assert abs(len(mine) - len(ref)) <= att_tol, (what, "attempts", len(mine), len(ref), msg)
     return msg
+
+
+# ---- BASELINE-config goldens on the reference's real data (tests/golden/make_golden_big.py) ------------------------------
+def manifest_big():
+    with open(os.path.join(GOLDEN_DIR, "manifest_big.json")) as fh:
+        return json.load(fh)
+
+
+def big_case_inputs(m, d):
+    """(weights, y0 [N,1,G], t [N,2], target [N,1,G]) of a `batch` golden; the weights are regenerated from the seed and
+    verified against the stored checksums."""
+    from oracle.phoenix_oracle import make_weights
+    w = make_weights(m["G"], m["H"], m["seed"], dense=False)
+    chk = np.array([float(p.double().sum()) for p in w.as_list()] + [float(p.double().abs().sum()) for p in w.as_list()])
+    assert np.allclose(chk, d["wsum"], rtol=1e-12, atol=0), "regenerated weights differ from the golden's"
+    return w, torch.from_numpy(d["y0"]), torch.from_numpy(d["t"]), torch.from_numpy(d["target"])
+
+
+def check_big_case(m, d, pred, loss, adj_y0, grads, ytol, gtol):
+    """Compare outputs with a `batch` golden: full tensors of size G, strided subsample + norm of the six gradients."""
+    assert rel_l2(pred, d["pred"]) < ytol, ("pred", rel_l2(pred, d["pred"]))
+    assert abs(float(loss) - float(d["loss"])) <= 10 * ytol * abs(float(d["loss"]))
+    assert rel_l2(adj_y0, d["adj_y0"]) < gtol, ("adj_y0", rel_l2(adj_y0, d["adj_y0"]))
+    for i, g in enumerate(grads):
+        g = torch.as_tensor(g).detach().cpu()
+        stride = int(d["grad%d_stride" % i])
+        sub = g.reshape(-1)[::stride]
+        ref_norm = float(d["grad%d_norm" % i])
+        # the subsample is compared against the FULL tensor's scale (a strided sample of a sparse gradient may be tiny)
+        scale = ref_norm * (sub.numel() / g.numel()) ** 0.5
+        err = (sub.double() - torch.from_numpy(d["grad%d_sub" % i]).double()).norm().item()
+        assert err <= gtol * max(scale, 1e-30), (m["name"], "grad", i, err / max(scale, 1e-30))
+        assert abs(g.double().norm().item() - ref_norm) <= gtol * ref_norm, (m["name"], "grad norm", i)

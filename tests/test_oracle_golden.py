@@ -3,7 +3,8 @@ import pytest
 import torch
 
 from oracle import phoenix_oracle as O
-from golden_util import assert_logs_close, compare_logs, load, manifest, rel_l2, weights_of
+from golden_util import (assert_logs_close, big_case_inputs, check_big_case, compare_logs, load, manifest,
+                         manifest_big, rel_l2, weights_of)
 
 RHS = [m["name"] for m in manifest("rhs")]
 SOLVE = [m for m in manifest("solve")]
@@ -61,3 +62,34 @@ def test_solve_and_adjoint_match_reference(m):
         # the explicit-formula VJP differs from autograd by rounding only; a mismatch here is reported, and is an
         # error only if the values above also failed
         print(m["name"], "adjoint step log vs reference:", msg)
+
+
+BIG = manifest_big()
+
+
+@pytest.mark.parametrize("m", BIG, ids=[m["name"] for m in BIG])
+def test_baseline_configs_on_real_data_match_reference(m):
+    """C3 (yeast, real 24-point series, dt = 5 / 10) and C4 (breast, real rows, dt = 0.0051): the per-sample loop of
+    training_step (train_insilico.py:128-138) restated with the oracle against the reference's own outputs."""
+    d = load(m["name"])
+    w, y0, t, target = big_case_inputs(m, d)
+    preds, flogs = [], []
+    for i in range(m["N"]):
+        y, fl = O.odeint(w, y0[i], t[i], method=m["method"])
+        preds.append(y)
+        flogs.append(fl.steps)
+    pred = torch.stack([y[1] for y in preds])
+    loss, gpred = O.mse_loss_and_grad(pred, target)
+    adys, total = [], None
+    for i in range(m["N"]):
+        gy = torch.zeros_like(preds[i])
+        gy[1] = gpred[i]
+        ady, grads, bl = O.adjoint_backward(w, t[i], preds[i], gy, method=m["method"])
+        adys.append(ady)
+        total = grads if total is None else [a + b for a, b in zip(total, grads)]
+        if m["method"] == "dopri5" and m["stable"]:
+            assert compare_logs(flogs[i], d["flog%d" % i], 1e-6)[1] == "identical"
+            assert compare_logs(bl.steps, d["blog%d" % i], 1e-4)[1] == "identical"
+    dop = m["method"] == "dopri5"
+    check_big_case(m, d, pred, loss, torch.stack(adys), total, 1e-6 if m["stable"] else 1e-5,
+                   (3e-5 if m["stable"] else 2e-4) if dop else 1e-5)
