@@ -10,8 +10,9 @@ ODENet(ndim=11165, neurons=200); one step = one training-step batch of the hot p
 Synthetic expression values U[0,1), weights with the reference init distribution (odenet.py:61-75).
 
 metric  gene-steps/s = B * G * (RHS evals forward + RHS-VJP evals adjoint) / time, evaluations counted by the solver.
-value   device-resident inputs, C-ABI calls (phx_solve_forward_many / phx_solve_adjoint_many, 8 samples per persistent
-        launch, every sample its own solve) issued back to back.
+value   device-resident inputs, C-ABI calls (phx_solve_forward_rows / phx_solve_adjoint_rows: the 17 samples of the
+        step as rows of one persistent launch each, 4 in lock-step per pass, every sample its own solve with its own
+        step controller; phx_unpack_grads) issued back to back.
 e2e     the same step through the public Python API from pinned HOST buffers, H2D of the samples and D2H of the loss
         inside the timed region: phoenix_b200.odeint_adjoint_many (the per-sample loop of training_step as one call,
         identical solves) + backward; the literal per-sample loop over phoenix_b200.odeint_adjoint is timed beside it
@@ -240,49 +241,53 @@ def run_ours(args):
     y0_d, target_d = y0_h.to(dev), target_h.to(dev)
     tl = [[float(a), float(b)] for a, b in t_h.tolist()]
     tarr = [(ctypes.c_double * 2)(*x) for x in tl]
-    ws_f = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 0), dtype=torch.uint8, device=dev)
-    ws_a = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 1), dtype=torch.uint8, device=dev)
+    ws_f = torch.empty(lib.phx_rows_workspace_bytes(ctx, G, H, BATCH, 2, 0), dtype=torch.uint8, device=dev)
+    ws_a = torch.empty(lib.phx_rows_workspace_bytes(ctx, G, H, BATCH, 2, 1), dtype=torch.uint8, device=dev)
     for ws in (ws_f, ws_a):   # one-time zeroing of the inter-CTA exchange area (include/phoenix_b200.h)
         _lib.check(lib.phx_solve_workspace_init(ctypes.c_void_p(ws.data_ptr()), ws.numel(), sp), "workspace_init")
     yout = torch.empty(BATCH, 2, 1, G, device=dev)
     grad_y = torch.zeros(BATCH, 2, 1, G, device=dev)
     adj_y0 = torch.empty(BATCH, 1, G, device=dev)
-    grads = torch.empty(BATCH, P, device=dev)
+    nparts = lib.phx_rows_grad_parts(ctx, G, H, BATCH)
+    gpk = torch.empty(nparts * lib.phx_packed_grad_bytes(G, H) // 4, device=dev)
     gsum = torch.empty(P, device=dev)
     st_f = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
     st_a = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
     mid = _lib.METHOD_IDS[METHOD]
     ptr = lambda x: ctypes.c_void_p(x.data_ptr())
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    adj_ev = []
+    adj_ev, fwd_ev = [], []
+    rows_per_pass = lib.phx_rows_supported(ctx, G, H, 1)
 
-    # the 17 independent samples go through the multi-problem entry points 8 at a time (N * T <= 16 output times per
-    # launch): every sample is its own solve with its own step controller, the weights are staged on chip once per launch
-    PER = 8
-    chunks = [(lo, min(PER, BATCH - lo)) for lo in range(0, BATCH, PER)]
-    tflat = {lo: (ctypes.c_double * (2 * n))(*[x for i in range(lo, lo + n) for x in tl[i]]) for lo, n in chunks}
+    # the 17 independent samples of the step go through the rows entry points: ONE persistent launch for the forward
+    # solves and ONE for the adjoint sweeps, `rows_per_pass` samples in lock-step per pass, every sample its own solve with
+    # its own step controller; the parameter cotangents leave the adjoint kernel already summed over the samples
+    tflat = (ctypes.c_double * (2 * BATCH))(*[x for r in tl for x in r])
 
     def step_resident(record):
-        for lo, n in chunks:
-            rc = lib.phx_solve_forward_many(ctx, G, H, 1, n, ptr(packed), ptr(y0_d[lo]), tflat[lo], 2, 1, mid, 1e-7,
-                                            1e-9, 2 ** 31 - 1, ptr(yout[lo]), ptr(ws_f), ws_f.numel(), ptr(st_f[lo]),
-                                            sp)
-            _lib.check(rc, "solve_forward_many")
+        if record:
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+        rc = lib.phx_solve_forward_rows(ctx, G, H, BATCH, ptr(packed), ptr(y0_d), tflat, 2, 1, 0, mid, 1e-7, 1e-9,
+                                        2 ** 31 - 1, ptr(yout), ptr(ws_f), ws_f.numel(), ptr(st_f), None, 0, sp)
+        _lib.check(rc, "solve_forward_rows")
+        if record:
+            f1.record(stream)
+            fwd_ev.append((f0, f1, BATCH))
         # d loss / d y(t1) for loss = mean((pred - target)^2) over the batch (train_insilico.py:132)
         torch.sub(yout[:, 1], target_d, out=grad_y[:, 1])
         grad_y[:, 1].mul_(2.0 / (BATCH * G))
-        for lo, n in chunks:
-            if record:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record(stream)
-            rc = lib.phx_solve_adjoint_many(ctx, G, H, 1, n, ptr(packed), tflat[lo], 2, 1, mid, 1e-7, 1e-9,
-                                            2 ** 31 - 1, ptr(yout[lo]), ptr(grad_y[lo]), ptr(adj_y0[lo]),
-                                            ptr(grads[lo]), ptr(ws_a), ws_a.numel(), ptr(st_a[lo]), sp)
-            _lib.check(rc, "solve_adjoint_many")
-            if record:
-                e1.record(stream)
-                adj_ev.append((e0, e1, n))
-        torch.sum(grads, dim=0, out=gsum)                # autograd's accumulation of the per-sample .grad
+        if record:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+        rc = lib.phx_solve_adjoint_rows(ctx, G, H, BATCH, ptr(packed), tflat, 2, 1, mid, 1e-7, 1e-9, 2 ** 31 - 1,
+                                        ptr(yout), ptr(grad_y), ptr(adj_y0), ptr(gpk), ptr(ws_a), ws_a.numel(),
+                                        ptr(st_a), None, 0, sp)
+        _lib.check(rc, "solve_adjoint_rows")
+        if record:
+            e1.record(stream)
+            adj_ev.append((e0, e1, BATCH))
+        _lib.check(lib.phx_unpack_grads(ctx, G, H, ptr(gpk), nparts, ptr(gsum), 0, sp), "unpack_grads")
         if world > 1:
             dist.all_reduce(gsum)
 
@@ -314,7 +319,9 @@ def run_ours(args):
             raise SystemExit("solver status non-zero: %s %s" % (st_f[i, :5].tolist(), st_a[i, :5].tolist()))
     n_attempts = sum(int(st_a[i, 1]) + int(st_a[i, 2]) for i in range(BATCH)) / BATCH
     n_vjp = sum(int(st_a[i, 3]) for i in range(BATCH)) / BATCH
-    adj_ms = sum(a.elapsed_time(b) for a, b, _ in adj_ev) / sum(n for _, _, n in adj_ev)   # per problem
+    adj_ms = sum(a.elapsed_time(b) for a, b, _ in adj_ev) / sum(n for _, _, n in adj_ev)   # per sample
+    fwd_ms = sum(a.elapsed_time(b) for a, b, _ in fwd_ev) / sum(n for _, _, n in fwd_ev)
+    n_fwd = sum(int(st_f[i, 3]) for i in range(BATCH)) / BATCH
 
     # ---- end-to-end leg: reference-facing Python API from pinned host buffers ------------------------------
     y0_p, target_p = y0_h.pin_memory(), target_h.pin_memory()
@@ -415,12 +422,18 @@ def run_ours(args):
                            "loss.backward(), pinned host inputs",
                     "per_sample_api_value": work_per_step / (ms_e2e_loop / args.steps / 1e3),
                     "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130"},
-            "gpu_launches": args.steps * len(chunks) * 2,
+            "gpu_launches": args.steps * 4,   # forward rows, adjoint rows, 2 x unpack (+ 2 ATen elementwise for the loss grad)
             "roofline": {"bound": "hbm", "kernel": "phx_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "launch_ms": adj_ms, "algorithmic_bytes": alg,
-                         "per": "one sample's adjoint sweep (a launch holds up to 8); achieved, launch_ms, "
-                                "algorithmic_bytes and traffic are all per sample",
+                         "per": "one sample's adjoint sweep = the 17-sample phx_rows_adj_kernel launch / 17 (%d samples in "
+                                "lock-step per pass); achieved, launch_ms, algorithmic_bytes and traffic are per sample; "
+                                "algorithmic = n_vjp*(32GH+16G) + n_attempts*8P (SURVEY 8d), the weights never leave "
+                                "the chip so this is algorithmic-bytes throughput, not DRAM traffic" % rows_per_pass,
+                         "forward": {"kernel": "phx_rows_fwd_kernel", "launch_ms": fwd_ms,
+                                     "algorithmic_bytes": n_fwd * (16.0 * G * H + 8.0 * G),
+                                     "achieved": n_fwd * (16.0 * G * H + 8.0 * G) / (fwd_ms * 1e-3) / 1e9,
+                                     "frac": n_fwd * (16.0 * G * H + 8.0 * G) / (fwd_ms * 1e-3) / 1e9 / peak},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650"},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"

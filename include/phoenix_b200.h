@@ -202,18 +202,20 @@ int phx_solve_forward_rows(phx_ctx* ctx, int G, int H, int N, const float* packe
                            int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
                            phx_status* status, double* steplog, int steplog_cap, void* stream);
 /* OdeintAdjointMethod.backward (adjoint.py:32-162) of the N problems: y_saved / grad_y [N][T][G], adj_y0 [N][G], and the
- * parameter cotangents SUMMED over the problems (what autograd accumulates into .grad) in the PACKED layout --
- * W1bar[G][K2] | WAbar[G][K2] | biasbar[K2] | mbar[G], the layout of phx_pack_weights, phx_packed_grad_bytes() bytes,
- * 16-byte aligned; accumulate != 0 adds to grads_packed_sum.  phx_unpack_grads converts to the reference's flat order
- * (gene_multipliers, Wp, bp, Ws, bs, Wa), optionally accumulating into grads_flat. */
+ * parameter cotangents in the PACKED layout -- W1bar[G][K2] | WAbar[G][K2] | biasbar[K2] | mbar[G], the layout of
+ * phx_pack_weights, phx_packed_grad_bytes() bytes, 16-byte aligned -- as phx_rows_grad_parts() PARTIAL SUMS (one per pass
+ * of phx_rows_supported() problems): grads_packed_parts [parts][phx_packed_grad_bytes / 4].  phx_unpack_grads adds the
+ * parts in a fixed order and converts to the reference's flat order (gene_multipliers, Wp, bp, Ws, bs, Wa): what autograd
+ * accumulates into .grad over the samples; accumulate != 0 adds to grads_flat instead of overwriting it. */
 int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const double* t_host, int T,
                            int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
-                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_sum,
-                           int accumulate, void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_parts,
+                           void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                            int steplog_cap, void* stream);
 size_t phx_packed_grad_bytes(int G, int H);
-int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, float* grads_flat, int accumulate,
-                     void* stream);
+int phx_rows_grad_parts(const phx_ctx* ctx, int G, int H, int N);
+int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int nparts, float* grads_flat,
+                     int accumulate, void* stream);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,7 @@ EXPORTS = [
     "phx_solve_adjoint", "phx_solve_forward_many", "phx_solve_adjoint_many",
     "phx_stream_workspace_bytes", "phx_stream_solve_forward", "phx_stream_solve_adjoint",
     "phx_rows_supported", "phx_rows_plan_describe", "phx_rows_workspace_bytes", "phx_solve_forward_rows",
-    "phx_solve_adjoint_rows", "phx_unpack_grads", "phx_packed_grad_bytes",
+    "phx_solve_adjoint_rows", "phx_unpack_grads", "phx_packed_grad_bytes", "phx_rows_grad_parts",
 ]
 
 
@@ -121,13 +121,15 @@ def _declare(lib):
     #  steplog, steplog_cap, stream)
     lib.phx_solve_forward_rows.argtypes = fwd
     lib.phx_solve_forward_rows.restype = c_int
-    # (ctx, G, H, N, packed, t, T, t_is_f32, method, rtol, atol, max_steps, y_saved, grad_y, adj_y0, grads_packed_sum,
-    #  accumulate, ws, ws_bytes, status, steplog, steplog_cap, stream)
+    # (ctx, G, H, N, packed, t, T, t_is_f32, method, rtol, atol, max_steps, y_saved, grad_y, adj_y0, grads_packed_parts,
+    #  ws, ws_bytes, status, steplog, steplog_cap, stream)
     lib.phx_solve_adjoint_rows.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, ctypes.POINTER(c_double), c_int, c_int,
                                            c_int, c_double, c_double, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
-                                           c_int, c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]
+                                           c_void_p, c_size_t, c_void_p, c_void_p, c_int, c_void_p]
     lib.phx_solve_adjoint_rows.restype = c_int
-    lib.phx_unpack_grads.argtypes = [c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
+    lib.phx_unpack_grads.argtypes = [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_int, c_void_p]
+    lib.phx_rows_grad_parts.argtypes = [c_void_p, c_int, c_int, c_int]
+    lib.phx_rows_grad_parts.restype = c_int
     lib.phx_unpack_grads.restype = c_int
     lib.phx_packed_grad_bytes.argtypes = [c_int, c_int]
     lib.phx_packed_grad_bytes.restype = c_size_t

@@ -62,13 +62,16 @@ __global__ void pack_kernel(int G, int H, int Hp, int K2, const float* __restric
 // packed-layout cotangents (phx_packed_grad_offsets) -> the reference's flat order (phx_grad_offsets).  The two branch
 // matrices are transposed ([G][K2] gene-major -> [H][G]) through a 32 x 33 shared-memory tile so that both the reads
 // (along k) and the writes (along g) are coalesced.
-__global__ void unpack_w1_kernel(int G, int H, int Hp, int K2, const float* __restrict__ w1bar, float* __restrict__ Ws,
-                                 float* __restrict__ Wp, int accumulate) {
+__global__ void unpack_w1_kernel(int G, int H, int Hp, int K2, const float* __restrict__ w1bar, int nparts, size_t pstride,
+                                 float* __restrict__ Ws, float* __restrict__ Wp, int accumulate) {
     __shared__ float tile[32][33];
     const int g0 = blockIdx.x * 32, k0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
         const int g = g0 + r, k = k0 + threadIdx.x;
-        tile[r][threadIdx.x] = (g < G && k < K2) ? w1bar[(size_t)g * K2 + k] : 0.f;
+        float t = 0.f;
+        if (g < G && k < K2)
+            for (int q = 0; q < nparts; ++q) t += w1bar[q * pstride + (size_t)g * K2 + k];   // fixed order over the parts
+        tile[r][threadIdx.x] = t;
     }
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += blockDim.y) {
@@ -82,23 +85,31 @@ __global__ void unpack_w1_kernel(int G, int H, int Hp, int K2, const float* __re
     }
 }
 __global__ void unpack_rest_kernel(int G, int H, int Hp, int K2, const float* __restrict__ wabar,
-                                   const float* __restrict__ biasbar, const float* __restrict__ mbar,
-                                   float* __restrict__ Wa, float* __restrict__ bs, float* __restrict__ bp,
-                                   float* __restrict__ m, int accumulate) {
+                                   const float* __restrict__ biasbar, const float* __restrict__ mbar, int nparts,
+                                   size_t pstride, float* __restrict__ Wa, float* __restrict__ bs,
+                                   float* __restrict__ bp, float* __restrict__ m, int accumulate) {
+    auto psum = [&](const float* base, size_t i) {
+        float t = 0.f;
+        for (int q = 0; q < nparts; ++q) t += base[q * pstride + i];
+        return t;
+    };
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     const size_t n = (size_t)G * 2 * H;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         const size_t g = i / (2 * H);
         const int kk = (int)(i - g * 2 * H);
-        const float v = wabar[g * K2 + (kk < H ? kk : Hp + kk - H)];
+        const float v = psum(wabar, g * K2 + (kk < H ? kk : Hp + kk - H));
         Wa[i] = accumulate ? Wa[i] + v : v;
     }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)H; i += stride) {
-        bs[i] = accumulate ? bs[i] + biasbar[i] : biasbar[i];
-        bp[i] = accumulate ? bp[i] + biasbar[Hp + i] : biasbar[Hp + i];
+        const float vs = psum(biasbar, i), vp = psum(biasbar, Hp + i);
+        bs[i] = accumulate ? bs[i] + vs : vs;
+        bp[i] = accumulate ? bp[i] + vp : vp;
     }
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)G; i += stride)
-        m[i] = accumulate ? m[i] + mbar[i] : mbar[i];
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < (size_t)G; i += stride) {
+        const float vm = psum(mbar, i);
+        m[i] = accumulate ? m[i] + vm : vm;
+    }
 }
 
 bool check_dims(int G, int H, int B) {
@@ -548,18 +559,25 @@ int phx_solve_forward_rows(phx_ctx* ctx, int G, int H, int N, const float* packe
     return phx_rows_launch(p, plan, (cudaStream_t)stream);
 }
 
-int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, float* grads_flat, int accumulate,
-                     void* stream) {
-    if (!ctx || !check_dims(G, H, 1) || !packed_grads || !grads_flat) return PHX_ERR_INVALID;
+int phx_rows_grad_parts(const phx_ctx* ctx, int G, int H, int N) {
+    if (!ctx || N < 1) return 0;
+    RowsPlan plan;
+    if (phx_rows_plan(ctx->num_sms, G, H, 1, &plan) != PHX_OK) return 0;
+    return (N + plan.rows - 1) / plan.rows;
+}
+
+int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int nparts, float* grads_flat,
+                     int accumulate, void* stream) {
+    if (!ctx || !check_dims(G, H, 1) || !packed_grads || !grads_flat || nparts < 1) return PHX_ERR_INVALID;
     const int Hp = phx_Hp(H), K2 = 2 * Hp;
     const PhxPackedGradOff po = phx_packed_grad_offsets(G, H);
     const PhxGradOff fo = phx_grad_offsets(G, H);
     dim3 grid((G + 31) / 32, (K2 + 31) / 32), block(32, 8);
-    unpack_w1_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(G, H, Hp, K2, packed_grads + po.W1, grads_flat + fo.Ws,
-                                                               grads_flat + fo.Wp, accumulate);
+    unpack_w1_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(G, H, Hp, K2, packed_grads + po.W1, nparts, po.total,
+                                                               grads_flat + fo.Ws, grads_flat + fo.Wp, accumulate);
     unpack_rest_kernel<<<ctx->num_sms * 4, 256, 0, (cudaStream_t)stream>>>(
-        G, H, Hp, K2, packed_grads + po.WA, packed_grads + po.bias, packed_grads + po.m, grads_flat + fo.Wa,
-        grads_flat + fo.bs, grads_flat + fo.bp, grads_flat + fo.m, accumulate);
+        G, H, Hp, K2, packed_grads + po.WA, packed_grads + po.bias, packed_grads + po.m, nparts, po.total,
+        grads_flat + fo.Wa, grads_flat + fo.bs, grads_flat + fo.bp, grads_flat + fo.m, accumulate);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         phx_set_error("unpack_grads launch: %s", cudaGetErrorString(e));
@@ -572,16 +590,16 @@ size_t phx_packed_grad_bytes(int G, int H) { return phx_packed_grad_offsets(G, H
 
 int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const double* t_host, int T,
                            int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
-                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_sum,
-                           int accumulate, void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
+                           const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_parts,
+                           void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                            int steplog_cap, void* stream) {
     g_err[0] = 0;
-    if (!y_saved || !grad_y || !adj_y0 || !grads_packed_sum) {
-        phx_set_error("null y_saved / grad_y / adj_y0 / grads_packed_sum");
+    if (!y_saved || !grad_y || !adj_y0 || !grads_packed_parts) {
+        phx_set_error("null y_saved / grad_y / adj_y0 / grads_packed_parts");
         return PHX_ERR_INVALID;
     }
-    if ((uintptr_t)grads_packed_sum & 15) {
-        phx_set_error("grads_packed_sum must be 16-byte aligned");
+    if ((uintptr_t)grads_packed_parts & 15) {
+        phx_set_error("grads_packed_parts must be 16-byte aligned");
         return PHX_ERR_INVALID;
     }
     ResParams p;
@@ -594,8 +612,8 @@ int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packe
     p.grad_y = grad_y;
     p.adj_y0 = adj_y0;
     p.theta_ws = (float*)workspace + o_th;
-    p.gsum = grads_packed_sum;
-    p.gsum_acc = accumulate;
+    p.gsum = grads_packed_parts;
+    p.gsum_acc = 0;
     return phx_rows_launch(p, plan, (cudaStream_t)stream);
 }
 

@@ -405,7 +405,26 @@ __device__ __forceinline__ void grid_allreduce_f(const ResParams& p, Smem& s, fl
                     (lane & 1) ? a3 : a1, tag);
     }
     const unsigned long long* res = p.ll.xres + (size_t)(blockIdx.x % PHX_LL_RCOPIES) * PHX_LL_NMAX;
-    for (int i = 2 * threadIdx.x; i < n; i += 2 * THREADS) ll_get2(res + i, tag, vec[i], vec[i + 1]);
+    for (int i0 = 2 * threadIdx.x; i0 < n; i0 += 8 * THREADS) {
+        // up to four pairs per thread, all (re)polled in the same round trip (past the end: the last pair again)
+        unsigned long long w[4][2];
+        bool ok;
+        do {
+            ok = true;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ll_ld2(res + min(i0 + u * 2 * THREADS, n - 2), w[u][0], w[u][1]);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) ok = ok && (unsigned)(w[u][0] >> 32) == tag && (unsigned)(w[u][1] >> 32) == tag;
+        } while (!ok);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + u * 2 * THREADS;
+            if (i < n) {
+                vec[i] = __uint_as_float((unsigned)w[u][0]);
+                vec[i + 1] = __uint_as_float((unsigned)w[u][1]);
+            }
+        }
+    }
     __syncthreads();
 }
 

@@ -38,11 +38,11 @@ struct RowCtl {
     int n_acc, n_rej, n_rhs, n_log, n_steps_interval, next_out;
     int slot[7];    // physical state slot (K / KY / KA) of logical stage q; FSAL swaps 0 <-> 6
     int fslot[7];   // physical factor slot of logical stage q (-1: the stage keeps no factors)
-    int cur, theta_zero, pend;
+    int cur, theta_zero, pend, spec_done;
 };
 struct RowsCtl {
     RowCtl r[RM];
-    int all_done, any_pending;
+    int all_done, any_pending, spec_valid, spec_pass, redo;
 };
 static_assert(sizeof(RowsCtl) <= PHX_RCTL_BYTES, "PHX_RCTL_BYTES too small");
 
@@ -397,6 +397,7 @@ __device__ __forceinline__ void row_init(RowCtl& c, bool valid) {
     c.cur = 0;
     c.theta_zero = 1;
     c.pend = 0;
+    c.spec_done = 0;
 }
 __device__ __forceinline__ void row_log_step(const ResParams& p, RowCtl& c, int q, double t0, double dt, int accepted) {
     if (blockIdx.x == 0 && p.steplog && c.n_log < p.steplog_cap) {
@@ -820,45 +821,44 @@ __device__ __forceinline__ void rows_adj_eval(const ResParams& __restrict__ p, S
     }
     grid_allreduce_f(p, s, s.xv(), has_next ? 2 * n : n);
     pf.tick(PT_ALLRED2);
-    // ---- finalize: gLP = gPr * Pr (exp backward), record the stage's K2-long theta factors in tensor memory, next
-    // stage's branch vector (bias, exp).  Warps 0..3 (one per tensor-memory lane quarter) read everything first.
+    // ---- finalize: gLP = gPr * Pr (exp backward), next stage's branch vector (bias, exp) -- every quad by ONE thread --
+    // then the stage's K2-long theta factors go to tensor memory: warps 0..3 (one per lane quarter) each store the quad
+    // block their quarter serves (S|Pr staged through the idle fold buffer, gS|gLP read back from xv).
     {
         float4* sp4 = reinterpret_cast<float4*>(s.sp());
         float4* xv4 = reinterpret_cast<float4*>(s.xv());
+        float4* stage4 = s.at<float4>(p.so.red);
         const float4* bias4 = reinterpret_cast<const float4*>(s.bias());
-        float4 spv[RM], gv[RM], nx[RM];
-        const int fq = 32 * (v.warp % p.nqw) + v.lane;   // for warps 0..3: warp % nqw is the quad block of the quarter
-        const bool fok = v.warp < 4 && fq < K2q;
-        if (v.warp < 4) {
-#pragma unroll
-            for (int b = 0; b < RM; ++b) {
-                spv[b] = fok ? sp4[b * K2q + fq] : zero4();
-                gv[b] = fok ? xv4[b * K2q + fq] : zero4();
-                if (fq >= Hq) gv[b] = mul4(gv[b], spv[b]);
-                nx[b] = zero4();
-                if (has_next && fok) {
+        if (v.gg < RM && v.qok) {   // warp (quad block, gene group g) finalises row g
+            const int fq = v.q;
+            {
+                const int b = v.gg;
+                const float4 spv = sp4[b * K2q + fq];
+                float4 gv = xv4[b * K2q + fq];
+                if (fq >= Hq) gv = mul4(gv, spv);
+                xv4[b * K2q + fq] = gv;
+                stage4[b * K2q + fq] = spv;
+                if (has_next) {
                     const float4 t = xv4[(RM + b) * K2q + fq], bq = bias4[fq];
                     float x[4] = {t.x + bq.x, t.y + bq.y, t.z + bq.z, t.w + bq.w};
                     if (fq >= Hq) {
 #pragma unroll
                         for (int e4 = 0; e4 < 4; ++e4) x[e4] = (4 * fq + e4 - p.Hp < p.H) ? expf(x[e4]) : 0.f;
                     }
-                    nx[b] = make_float4(x[0], x[1], x[2], x[3]);
+                    sp4[b * K2q + fq] = make_float4(x[0], x[1], x[2], x[3]);
                 }
             }
         }
         __syncthreads();
         if (v.warp < 4) {
+            const int fq = 32 * (v.warp % p.nqw) + v.lane;   // warp % nqw: the quad block this lane quarter serves
+            const bool fok = fq < K2q;
 #pragma unroll
             for (int b = 0; b < RM; ++b) {
                 const int fs = rc->r[b].fslot[sid];
                 if (fs >= 0) {   // uniform over the warp
-                    tm_st4(v.col_fsp(fs, b), spv[b]);
-                    tm_st4(v.col_fg(fs, b), gv[b]);
-                }
-                if (v.warp < p.nqw && fok) {
-                    xv4[b * K2q + fq] = gv[b];
-                    if (has_next) sp4[b * K2q + fq] = nx[b];
+                    tm_st4(v.col_fsp(fs, b), fok ? stage4[b * K2q + fq] : zero4());
+                    tm_st4(v.col_fg(fs, b), fok ? xv4[b * K2q + fq] : zero4());
                 }
             }
             tm_wait_st();
@@ -868,48 +868,68 @@ __device__ __forceinline__ void rows_adj_eval(const ResParams& __restrict__ p, S
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     }
     pf.tick(PT_FINALIZE);
-    // ---- pass 2 over W1: u = W1[g][:Hp] . gS, v = W1[g][Hp:] . gLP; thread = (gene, k-chunk c); lane c owns row c -------
+    // ---- pass 2 over W1: u = W1[g][:Hp] . gS, v = W1[g][Hp:] . gLP.  Same mapping as pass 1 (thread = quad x gene group,
+    // the lane's gS|gLP quad in registers, one 16-byte shared-memory read per gene): a warp whose quads all lie in one half
+    // contributes to u or to v only; the warp straddling Hp runs the transposing butterfly twice.
     {
         const float4* g4 = reinterpret_cast<const float4*>(s.xv());
         const float4* w1 = v.w1();
         const int ws = p.ring_rows;
-        for (int e0 = 0; e0 < s.n_loc * 4; e0 += THREADS) {
-            const int e = e0 + threadIdx.x;
-            const int j = min(e >> 2, s.n_loc - 1), c = e & 3;   // tail threads recompute the last gene (shuffles stay full)
-            const float4* row = w1 + (size_t)j * ws;
-            float u[RM] = {0.f, 0.f, 0.f, 0.f}, vv[RM] = {0.f, 0.f, 0.f, 0.f};
-            int qq = c;
-            for (; qq < Hq; qq += 4) {
-                const float4 w = row[qq];
+        float4 gq[RM];
 #pragma unroll
-                for (int b = 0; b < RM; ++b) u[b] += dot4(w, g4[b * K2q + qq]);
-            }
-            for (; qq < K2q; qq += 4) {
-                const float4 w = row[qq];
+        for (int b = 0; b < RM; ++b) gq[b] = v.qok ? g4[b * K2q + v.q] : zero4();
+        const int qlo = 32 * v.qw, qhi = min(qlo + 31, K2q - 1);
+        const bool has_u = qlo < Hq, has_v = qhi >= Hq;     // warp-uniform
+        const bool mine_u = v.q < Hq;
+        float* ur = v.jred() + (size_t)v.qw * RM * p.gpc;                 // u partials [qw][gene][row]
+        float* vr = s.at<float>(p.so.red) + (size_t)v.qw * RM * p.gpc;    // v partials (fold buffer is idle here)
+        const int j0 = v.gg * p.gpg;
+        const int jend = min(j0 + p.gpg, (s.n_loc + 3) & ~3);
+        for (int jc = j0; jc < jend; jc += 4) {
+            float pu[16], pv[16];
 #pragma unroll
-                for (int b = 0; b < RM; ++b) vv[b] += dot4(w, g4[b * K2q + qq]);
-            }
+            for (int gi = 0; gi < 4; ++gi) {
+                const float4 w = (v.qok && jc + gi < s.n_loc) ? w1[(size_t)(jc + gi) * ws + v.q] : zero4();
 #pragma unroll
-            for (int b = 0; b < RM; ++b) {
-                u[b] += __shfl_xor_sync(0xffffffffu, u[b], 1);
-                u[b] += __shfl_xor_sync(0xffffffffu, u[b], 2);
-                vv[b] += __shfl_xor_sync(0xffffffffu, vv[b], 1);
-                vv[b] += __shfl_xor_sync(0xffffffffu, vv[b], 2);
-            }
-            if ((e >> 2) < s.n_loc) {
-                const int b = c, li = j * RM + b;
-                const float uu = (b == 0) ? u[0] : (b == 1 ? u[1] : (b == 2 ? u[2] : u[3]));
-                const float vw = (b == 0) ? vv[0] : (b == 1 ? vv[1] : (b == 2 ? vv[2] : vv[3]));
-                const float z = s.ysb()[li] - 0.5f;
-                const float den = 1.0f + fabsf(z);
-                const float yb = (uu + vw / (1.0f + s.acts()[li])) / (den * den);
-                const float ka = yb - s.gjb()[li];
-                v.st(11 + rc->r[b].slot[sid])[li] = ka;
-                const float an = anext(b, j, li, ka);
-                if (has_next) {
-                    s.asb()[li] = an;
-                    s.gjb()[li] = an * s.relum()[j];
+                for (int b = 0; b < RM; ++b) {
+                    const float d = dot4(w, gq[b]);
+                    pu[gi * RM + b] = mine_u ? d : 0.f;
+                    pv[gi * RM + b] = mine_u ? 0.f : d;
                 }
+            }
+            const int idx = (v.lane >> 1) & 15;
+            const bool wr = (v.lane & 1) == 0 && jc + (idx >> 2) < p.gpc;
+            const int o = (jc + (idx >> 2)) * RM + (idx & 3);
+            if (has_u) {
+                const float r = transpose_reduce16(pu);
+                if (wr) ur[o] = r;
+            } else if (wr) {
+                ur[o] = 0.f;
+            }
+            if (has_v) {
+                const float r = transpose_reduce16(pv);
+                if (wr) vr[o] = r;
+            } else if (wr) {
+                vr[o] = 0.f;
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < tot; e += THREADS) {
+            const int j = e >> 2, b = e & 3;
+            float uu = v.jred()[e], vw = s.at<float>(p.so.red)[e];
+            for (int w = 1; w < p.nqw; ++w) {
+                uu += v.jred()[w * BL + e];
+                vw += s.at<float>(p.so.red)[w * BL + e];
+            }
+            const float z = s.ysb()[e] - 0.5f;
+            const float den = 1.0f + fabsf(z);
+            const float yb = (uu + vw / (1.0f + s.acts()[e])) / (den * den);
+            const float ka = yb - s.gjb()[e];
+            v.st(11 + rc->r[b].slot[sid])[e] = ka;
+            const float an = anext(b, j, e, ka);
+            if (has_next) {
+                s.asb()[e] = an;
+                s.gjb()[e] = an * s.relum()[j];
             }
         }
     }
@@ -923,90 +943,56 @@ __device__ __forceinline__ void rows_adj_eval(const ResParams& __restrict__ p, S
 //   WAbar: U = gJ (FGJ), V = S|Pr (FSP);  W1bar: U = s (k < Hp) or l (k >= Hp), V = gS|gLP (FG);
 //   biasbar[k] = V = gS|gLP (CTA 0);  mbar[j] = FM.
 enum { TP_D01 = 0, TP_D2 = 1, TP_STEP = 2, TP_FIXED = 3 };
+// Per-row arguments of a theta pass.  Weights are indexed by PHYSICAL factor slot.  The value written by a step / fixed
+// pass is  th0 + sum_f wo[f] k[f]:  for an ordinary step wo == cs (the solution weights dt * beta_6); for the step that
+// ends the interval it is the quartic dense output at t_end (interp.py:1-47) written as ONE linear combination -- the
+// interpolant is linear in (y0, y1, y_mid, f0, f1), y1 and y_mid are th0 + linear combinations of the stage derivatives,
+// and the coefficient of th0 collapses to exactly 1 (rows_interp_weights); euler / midpoint / rk4: wo = dt * b.
 struct RowPP {
     float* src;   // theta at step start; nullptr while it is identically zero
     float* dst;   // may alias src
-    float cs[NFS], ce[NFS], cm[NFS];   // solution / error / mid-point weights by PHYSICAL factor slot
-    float xs[4];
-    float dtf;
-    int active, last, kf, kl, s0, s1, method;
+    float cs[NFS], ce[NFS], wo[NFS];
+    int active, last, s0, s1;
+    // speculative final step (see phx_rows_adj_kernel): the written value is ADDED to the group's packed sum `acc` instead
+    // of stored in the row's own buffer: 1 = first such row of the pass (plain store), 2 = read-modify-write
+    int spec;
+    float* acc;
 };
 static_assert(sizeof(RowPP) * RM <= 1024, "RowPP block must fit its shared-memory slot");
 
-struct TPAcc {
-    float a0, a1;
-};
-
-// one float4 of theta elements: k[fs] = u[fs] * V[fs]
-template <int MODE>
-__device__ __forceinline__ void theta_quad(const float atol_f, const float rtol_f, const RowPP& a, const float (&u)[NFS],
-                                           const float4 (&V)[NFS], size_t idx, TPAcc& acc) {
-    float o[4];
-    const float4 th4 = a.src ? *reinterpret_cast<const float4*>(a.src + idx) : zero4();
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-        const float th0 = comp4(th4, e);
-        float k[NFS];
-#pragma unroll
-        for (int f = 0; f < NFS; ++f) k[f] = u[f] * comp4(V[f], e);
-        if (MODE == TP_D01) {
-            const float scale = atol_f + fabsf(th0) * rtol_f;
-            const float r0 = th0 / scale, r1 = k[0] / scale;   // k[0]: the caller put slot s0 first
-            acc.a0 += r0 * r0;
-            acc.a1 += r1 * r1;
-        } else if (MODE == TP_D2) {
-            const float scale = atol_f + fabsf(th0) * rtol_f;
-            const float r = (k[1] - k[0]) / scale;               // slots (s0, s1) first
-            acc.a0 += r * r;
-        } else if (MODE == TP_FIXED) {
-            float r;
-            if (a.method == PHX_EULER) r = th0 + a.dtf * k[0];
-            else if (a.method == PHX_MIDPOINT) r = th0 + a.dtf * k[1];
-            else r = th0 + (k[0] + 3.f * (k[1] + k[2]) + k[3]) * a.dtf * 0.125f;
-            o[e] = r;
-        } else {
-            float inc = k[0] * a.cs[0], er = k[0] * a.ce[0];
-#pragma unroll
-            for (int f = 1; f < NFS; ++f) {
-                inc = fmaf(k[f], a.cs[f], inc);
-                er = fmaf(k[f], a.ce[f], er);
-            }
-            const float th1 = th0 + inc;
-            const float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
-            const float r = er / tol;
-            acc.a0 += r * r;
-            if (!isfinite(th1)) acc.a1 += 1.f;
-            if (a.last) {
-                float md = k[0] * a.cm[0];
-                float kf = 0.f, kl = 0.f;
-#pragma unroll
-                for (int f = 0; f < NFS; ++f) {
-                    if (f > 0) md = fmaf(k[f], a.cm[f], md);
-                    kf = (f == a.kf) ? k[f] : kf;
-                    kl = (f == a.kl) ? k[f] : kl;
-                }
-                o[e] = interp_eval(th0, th1, th0 + md, kf, kl, a.dtf, a.xs);
-            } else {
-                o[e] = th1;
-            }
-        }
+// weights of the dense output at x = (t_end - t0) / dt as a linear combination of the stage derivatives (see RowPP)
+__device__ __forceinline__ void rows_interp_weights(const RowCtl& c, RowPP& a) {
+    const double x = c.xs[0], x2 = c.xs[1], x3 = c.xs[2], x4 = c.xs[3], dt = c.dtf;
+    const double wy1 = -5.0 * x2 + 14.0 * x3 - 8.0 * x4;        // coefficient of (y1 - y0)
+    const double wym = 16.0 * x2 - 32.0 * x3 + 16.0 * x4;       // coefficient of (y_mid - y0)
+    const double wf0 = dt * (x - 4.0 * x2 + 5.0 * x3 - 2.0 * x4);
+    const double wf1 = dt * (x2 - 3.0 * x3 + 2.0 * x4);
+    for (int qq = 0; qq < 7; ++qq) {
+        const int fs = c.fslot[qq];
+        if (fs < 0) continue;
+        double w = wy1 * (double)((qq < 6) ? c.cb[5][qq] : 0.f) + wym * (double)c.cmid[qq];
+        if (qq == 0) w += wf0;
+        if (qq == 6) w += wf1;
+        a.wo[fs] = (float)w;
     }
-    if (MODE == TP_FIXED || MODE == TP_STEP) *reinterpret_cast<float4*>(a.dst + idx) = make_float4(o[0], o[1], o[2], o[3]);
 }
 
 // One pass over this CTA's share of every ACTIVE row's packed cotangent vector.  out[b * 2 + {0,1}] (shared memory, doubles)
-// receives this CTA's partial sums per row.  Ends with a block barrier.
+// receives this CTA's partial sums per row: STEP (sum (err/tol)^2, non-finite count), D01 (sum (th/scale)^2,
+// sum (k/scale)^2), D2 (sum ((k1-k0)/scale)^2, -).  Ends with a block barrier.
 template <int MODE>
 __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, int g_lo, int n_loc, uint32_t tmem, double* out) {
     Smem s(p);
     s.tmem = tmem;
     RowsView v(p, s);
     v.tq = tm_quarter(tmem);
-    const int BL = RM * p.gpc, K2q = p.K2q, Hq = p.Hp >> 2;
+    const int BL = RM * p.gpc, Hq = p.Hp >> 2;
     const int tot = n_loc * RM;
     const PhxPackedGradOff off = phx_packed_grad_offsets(p.G, p.H);
     const float atol_f = p.atol_f, rtol_f = p.rtol_f;
     const RowPP* pp = s.at<RowPP>(p.so.ppa);
+    constexpr bool WRITES = MODE == TP_STEP || MODE == TP_FIXED;
+    constexpr int NV = (MODE == TP_D01) ? 1 : (MODE == TP_D2 ? 2 : NFS);   // factor slots the mode touches
     // activation tables of the stored stage inputs (the scratch aliases the fold / J-partial buffers, idle here)
     float* US = s.at<float>(p.so.red);
     float* UL = US + NFS * BL;
@@ -1017,106 +1003,114 @@ __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, in
         US[fs * BL + e] = sv;
         UL[fs * BL + e] = lv;
     }
+    double* dred = s.dred();
+    if (threadIdx.x < WARPS * 8) dred[threadIdx.x] = 0.0;
     __syncthreads();
-    double d0[RM] = {0, 0, 0, 0}, d1[RM] = {0, 0, 0, 0};
     const int j0 = v.gg * p.gpg, jend = min(j0 + p.gpg, n_loc);
 #pragma unroll 1
     for (int b = 0; b < RM; ++b) {
-        const RowPP a = pp[b];
-        if (!a.active) continue;
-        TPAcc acc = {0.f, 0.f};
-        // slot order seen by theta_quad: D01 / D2 put (s0[, s1]) first, the others use the physical order
-        int ord[NFS];
+        if (!pp[b].active) continue;
+        float* const src = pp[b].src;
+        const int spec = WRITES ? pp[b].spec : 0;
+        float* const dst = spec ? pp[b].acc : pp[b].dst;
+        float a0 = 0.f, a1 = 0.f;
+        int sl[NV];
+        float cs[NV], ce[NV], wo[NV];
 #pragma unroll
-        for (int f = 0; f < NFS; ++f) ord[f] = f;
-        if (MODE == TP_D01 || MODE == TP_D2) { ord[0] = a.s0; ord[1] = a.s1; }
+        for (int f = 0; f < NV; ++f) {
+            sl[f] = (MODE == TP_D01) ? pp[b].s0 : (MODE == TP_D2 ? (f == 0 ? pp[b].s0 : pp[b].s1) : f);
+            cs[f] = pp[b].cs[f];
+            ce[f] = pp[b].ce[f];
+            wo[f] = pp[b].wo[f];
+        }
+        const bool sep = MODE == TP_STEP && pp[b].last;    // the written value is not th1: a third combination
+        // per theta element: k[f] = u[f] * V[f]
+        auto elem = [&](const float th0, const float (&k)[NV], float& o) {
+            if (MODE == TP_D01) {
+                const float scale = atol_f + fabsf(th0) * rtol_f;
+                const float r0 = __fdividef(th0, scale), r1 = __fdividef(k[0], scale);
+                a0 = fmaf(r0, r0, a0);
+                a1 = fmaf(r1, r1, a1);
+            } else if (MODE == TP_D2) {
+                const float scale = atol_f + fabsf(th0) * rtol_f;
+                const float r = __fdividef(k[1] - k[0], scale);
+                a0 = fmaf(r, r, a0);
+            } else if (MODE == TP_FIXED) {
+                float acc = k[0] * wo[0];
+#pragma unroll
+                for (int f = 1; f < NV; ++f) acc = fmaf(k[f], wo[f], acc);
+                o = th0 + acc;
+            } else {
+                float inc = k[0] * cs[0], er = k[0] * ce[0];
+#pragma unroll
+                for (int f = 1; f < NV; ++f) {
+                    inc = fmaf(k[f], cs[f], inc);
+                    er = fmaf(k[f], ce[f], er);
+                }
+                const float th1 = th0 + inc;
+                const float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
+                const float r = __fdividef(er, tol);
+                a0 = fmaf(r, r, a0);
+                a1 = fmaf(th1, 0.f, a1);      // 0 while finite, NaN once th1 is inf / NaN
+                o = th1;
+                if (sep) {
+                    float acc = k[0] * wo[0];
+#pragma unroll
+                    for (int f = 1; f < NV; ++f) acc = fmaf(k[f], wo[f], acc);
+                    o = th0 + acc;
+                }
+            }
+        };
+        auto quad = [&](const float (&u)[NV], const float4 (&V)[NV], const size_t idx) {
+            const float4 th4 = src ? *reinterpret_cast<const float4*>(src + idx) : zero4();
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                float k[NV];
+#pragma unroll
+                for (int f = 0; f < NV; ++f) k[f] = u[f] * comp4(V[f], e);
+                elem(comp4(th4, e), k, o[e]);
+            }
+            if (WRITES) {
+                float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+                if (spec == 2) o4 = add4(*reinterpret_cast<const float4*>(dst + idx), o4);
+                *reinterpret_cast<float4*>(dst + idx) = o4;
+            }
+        };
 #pragma unroll 1
-        for (int blk = 0; blk < 2; ++blk) {   // 0: WAbar (V = FSP, U = gJ), 1: W1bar (V = FG, U = s | l)
-            float4 V[NFS];
+        for (int blk = 0; blk < 2; ++blk) {   // 0: WAbar (V = S|Pr, U = gJ), 1: W1bar (V = gS|gLP, U = s | l)
+            float4 V[NV];
 #pragma unroll
-            for (int f = 0; f < NFS; ++f) tm_ld4(blk == 0 ? v.col_fsp(ord[f], b) : v.col_fg(ord[f], b), V[f]);
+            for (int f = 0; f < NV; ++f) tm_ld4(blk == 0 ? v.col_fsp(sl[f], b) : v.col_fg(sl[f], b), V[f]);
             if (!v.qok) continue;
-            const float* U = blk == 0 ? v.fgj() : (v.q >= Hq ? UL : US);
+            const float* U = (blk == 0 ? v.fgj() : (v.q >= Hq ? UL : US)) + b;
             const size_t base = (blk == 0 ? off.WA : off.W1) + (size_t)g_lo * p.K2 + 4 * (size_t)v.q;
+#pragma unroll 1
             for (int j = j0; j < jend; ++j) {
-                float u[NFS];
+                float u[NV];
 #pragma unroll
-                for (int f = 0; f < NFS; ++f) u[f] = U[ord[f] * BL + j * RM + b];
-                theta_quad<MODE>(atol_f, rtol_f, a, u, V, base + (size_t)j * p.K2, acc);
+                for (int f = 0; f < NV; ++f) u[f] = U[sl[f] * BL + j * RM];
+                quad(u, V, base + (size_t)j * p.K2);
             }
             if (blk == 1 && blockIdx.x == 0 && v.gg == 0) {   // biases: stage derivative = gS | gLP itself
-                float u[NFS];
+                float u[NV];
 #pragma unroll
-                for (int f = 0; f < NFS; ++f) u[f] = 1.f;
-                theta_quad<MODE>(atol_f, rtol_f, a, u, V, off.bias + 4 * (size_t)v.q, acc);
+                for (int f = 0; f < NV; ++f) u[f] = 1.f;
+                quad(u, V, off.bias + 4 * (size_t)v.q);
             }
         }
-        d0[b] += (double)acc.a0;
-        d1[b] += (double)acc.a1;
-    }
-    // gene multipliers: one thread per (gene, row)
-    for (int e = threadIdx.x; e < tot; e += THREADS) {
-        const int j = e >> 2, b = e & 3;
-        const RowPP& a = pp[b];
-        if (!a.active) continue;
-        float k[NFS];
+        // gene multipliers: threads e = (gene, row) with row == b
+        for (int e = 4 * (int)threadIdx.x + b; e < tot; e += 4 * THREADS) {
+            float k[NV];
 #pragma unroll
-        for (int f = 0; f < NFS; ++f) k[f] = v.fm()[f * BL + e];
-        if (MODE == TP_D01 || MODE == TP_D2) {
-            const float k0 = v.fm()[a.s0 * BL + e], k1 = v.fm()[a.s1 * BL + e];
-            k[0] = k0;
-            k[1] = k1;
+            for (int f = 0; f < NV; ++f) k[f] = v.fm()[sl[f] * BL + e];
+            const size_t idx = off.m + g_lo + (e >> 2);
+            float o = 0.f;
+            elem(src ? src[idx] : 0.f, k, o);
+            if (WRITES) dst[idx] = (spec == 2) ? dst[idx] + o : o;
         }
-        const size_t idx = off.m + g_lo + j;
-        const float th0 = a.src ? a.src[idx] : 0.f;
-        float o = th0, r0 = 0.f, r1 = 0.f;
-        if (MODE == TP_D01) {
-            const float scale = atol_f + fabsf(th0) * rtol_f;
-            const float x0 = th0 / scale, x1 = k[0] / scale;
-            r0 = x0 * x0;
-            r1 = x1 * x1;
-        } else if (MODE == TP_D2) {
-            const float scale = atol_f + fabsf(th0) * rtol_f;
-            const float x = (k[1] - k[0]) / scale;
-            r0 = x * x;
-        } else if (MODE == TP_FIXED) {
-            if (a.method == PHX_EULER) o = th0 + a.dtf * k[0];
-            else if (a.method == PHX_MIDPOINT) o = th0 + a.dtf * k[1];
-            else o = th0 + (k[0] + 3.f * (k[1] + k[2]) + k[3]) * a.dtf * 0.125f;
-        } else {
-            float inc = k[0] * a.cs[0], er = k[0] * a.ce[0], md = k[0] * a.cm[0];
-            float kf = 0.f, kl = 0.f;
-#pragma unroll
-            for (int f = 0; f < NFS; ++f) {
-                if (f > 0) {
-                    inc = fmaf(k[f], a.cs[f], inc);
-                    er = fmaf(k[f], a.ce[f], er);
-                    md = fmaf(k[f], a.cm[f], md);
-                }
-                kf = (f == a.kf) ? k[f] : kf;
-                kl = (f == a.kl) ? k[f] : kl;
-            }
-            const float th1 = th0 + inc;
-            const float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
-            const float x = er / tol;
-            r0 = x * x;
-            if (!isfinite(th1)) r1 = 1.f;
-            o = a.last ? interp_eval(th0, th1, th0 + md, kf, kl, a.dtf, a.xs) : th1;
-        }
-        if (MODE == TP_FIXED || MODE == TP_STEP) a.dst[idx] = o;
-#pragma unroll
-        for (int bb = 0; bb < RM; ++bb) {
-            if (bb == b) {
-                d0[bb] += (double)r0;
-                d1[bb] += (double)r1;
-            }
-        }
-    }
-    // block totals
-    double* dred = s.dred();
-#pragma unroll
-    for (int b = 0; b < RM; ++b) {
-        const double t0 = warp_sum_d(d0[b]), t1 = warp_sum_d(d1[b]);
+        const double t0 = warp_sum_d((double)a0);
+        const double t1 = (MODE == TP_STEP) ? warp_sum_d(isfinite(a1) ? 0.0 : 1.0) : warp_sum_d((double)a1);
         if (v.lane == 0) {
             dred[v.warp * 8 + 2 * b] = t0;
             dred[v.warp * 8 + 2 * b + 1] = t1;
@@ -1132,23 +1126,27 @@ __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, in
 }
 
 // gsum (+)= sum over the valid rows of their final packed cotangents; every element is read by the thread that wrote it
-__device__ __noinline__ void rows_theta_sum(const ResParams& __restrict__ p, int g_lo, int n_loc, bool accumulate) {
+__device__ __noinline__ void rows_theta_sum(const ResParams& __restrict__ p, int g_lo, int n_loc, float* gsum,
+                                            bool accumulate) {
     Smem s(p);
     RowsView v(p, s);
     const RowsCtl* rc = v.rc();
     const PhxPackedGradOff off = phx_packed_grad_offsets(p.G, p.H);
     const float* src[RM];
+    bool any = false;
 #pragma unroll
     for (int b = 0; b < RM; ++b) {
         const RowCtl& c = rc->r[b];
-        src[b] = (c.valid && !c.theta_zero) ? p.theta_ws + (size_t)(2 * b + c.cur) * p.ppk : nullptr;
+        src[b] = (c.valid && !c.theta_zero && !c.spec_done) ? p.theta_ws + (size_t)(2 * b + c.cur) * p.ppk : nullptr;
+        any |= src[b] != nullptr;
     }
+    if (!any && accumulate) return;   // everything is already in the group's sum
     auto quad = [&](size_t idx) {
-        float4 t = accumulate ? *reinterpret_cast<const float4*>(p.gsum + idx) : zero4();
+        float4 t = accumulate ? *reinterpret_cast<const float4*>(gsum + idx) : zero4();
 #pragma unroll
         for (int b = 0; b < RM; ++b)
             if (src[b]) t = add4(t, *reinterpret_cast<const float4*>(src[b] + idx));
-        *reinterpret_cast<float4*>(p.gsum + idx) = t;
+        *reinterpret_cast<float4*>(gsum + idx) = t;
     };
     const int j0 = v.gg * p.gpg, jend = min(j0 + p.gpg, n_loc);
     if (v.qok) {
@@ -1164,11 +1162,11 @@ __device__ __noinline__ void rows_theta_sum(const ResParams& __restrict__ p, int
     for (int e = threadIdx.x; e < n_loc * RM; e += THREADS) {
         if ((e & 3) != 0) continue;
         const size_t idx = off.m + g_lo + (e >> 2);
-        float t = accumulate ? p.gsum[idx] : 0.f;
+        float t = accumulate ? gsum[idx] : 0.f;
 #pragma unroll
         for (int b = 0; b < RM; ++b)
             if (src[b]) t += src[b][idx];
-        p.gsum[idx] = t;
+        gsum[idx] = t;
     }
 }
 
@@ -1279,13 +1277,36 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
 
     for (int q0 = 0; q0 < p.ntot; q0 += p.rows) {
         const int nr = min(p.rows, p.ntot - q0);
+        float* const gacc = p.gsum + (size_t)(q0 / p.rows) * p.ppk;   // this group's packed cotangent sum
         if (threadIdx.x < RM) {
             RowCtl& c = rc->r[threadIdx.x];
             row_init(c, (int)threadIdx.x < nr);
             if (!dop)
                 for (int i = 0; i < 7; ++i) c.fslot[i] = i < NFS ? i : -1;
         }
+        if (threadIdx.x == 0) rc->spec_valid = rc->spec_pass = rc->redo = 0;
         __syncthreads();
+        // Speculative final step.  When EVERY row still active is on the step that (if accepted) ends its last interval,
+        // the theta pass adds the rows' final values straight into the group's sum instead of storing them per row and
+        // summing afterwards (35.8 MB written + read back per sample at the headline shape).  Acceptance is only known
+        // after the pass: if a row is rejected the sum is void, the accepted rows are re-run into their own buffers (their
+        // factors are still on chip) and the group falls back to the explicit sum.
+        auto plan_spec = [&](bool final_iv) {   // thread 0, after the RowPP block is filled
+            bool any = false, all = true;
+            for (int b = 0; b < RM; ++b) {
+                if (!pp[b].active) continue;
+                any = true;
+                all = all && pp[b].last && final_iv;
+            }
+            const bool spec = any && all && !rc->spec_valid;
+            rc->spec_pass = spec;
+            bool first = true;
+            for (int b = 0; b < RM; ++b) {
+                pp[b].acc = gacc;
+                pp[b].spec = (spec && pp[b].active) ? (first ? 1 : 2) : 0;
+                if (pp[b].spec) first = false;
+            }
+        };
         auto set_input = [&](int e, int j, float ys, float as, int fs) {
             s.ysb()[e] = ys;
             float sv, lv, den;
@@ -1334,10 +1355,20 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
                     float* th = p.theta_ws + (size_t)(2 * threadIdx.x) * p.ppk;
                     a.src = c.theta_zero ? nullptr : th;
                     a.dst = th;
-                    a.dtf = c.dtf;
-                    a.method = p.method;
+                    for (int f = 0; f < NFS; ++f) a.cs[f] = a.ce[f] = a.wo[f] = 0.f;
+                    if (p.method == PHX_EULER) {
+                        a.wo[0] = c.dtf;
+                    } else if (p.method == PHX_MIDPOINT) {
+                        a.wo[1] = c.dtf;
+                    } else {   // 3/8 rule: (k1 + 3 (k2 + k3) + k4) dt / 8
+                        a.wo[0] = a.wo[3] = c.dtf * 0.125f;
+                        a.wo[1] = a.wo[2] = 3.f * c.dtf * 0.125f;
+                    }
+                    a.last = 1;
                     a.active = !c.done;
                 }
+                __syncthreads();
+                if (threadIdx.x == 0) plan_spec(iv == 1);
                 for (int st = 0; st < nst; ++st) {
                     const bool last = st + 1 == nst;
                     rows_adj_eval(
@@ -1372,12 +1403,13 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
                 if (threadIdx.x < RM) {
                     RowCtl& c = rc->r[threadIdx.x];
                     if (!c.done) {
-                        c.theta_zero = 0;
-                        c.cur = 0;
+                        if (pp[threadIdx.x].spec) c.spec_done = 1;
+                        else { c.theta_zero = 0; c.cur = 0; }
                         c.n_rhs += nst;
                         c.tcur = c.t_end;
                     }
                 }
+                if (threadIdx.x == 0 && rc->spec_pass) rc->spec_valid = 1;
                 __syncthreads();
             } else {
                 // ------------------------------ dopri5 on the augmented state, one controller per row -----------------
@@ -1546,7 +1578,6 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
                         float* t1 = t0 + p.ppk;
                         a.src = c.theta_zero ? nullptr : (c.cur ? t1 : t0);
                         a.dst = c.theta_zero ? t0 : (c.cur ? t0 : t1);
-                        a.dtf = c.dtf;
                         a.last = c.last;
                         a.active = !c.done;
                         for (int qq = 0; qq < 7; ++qq) {
@@ -1554,12 +1585,12 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
                             if (fs < 0) continue;
                             a.cs[fs] = (qq < 6) ? c.cb[5][qq] : 0.f;
                             a.ce[fs] = c.cerr[qq];
-                            a.cm[fs] = c.cmid[qq];
+                            a.wo[fs] = a.cs[fs];
                         }
-                        a.kf = c.fslot[0];
-                        a.kl = c.fslot[6];
-                        for (int i = 0; i < 4; ++i) a.xs[i] = c.xs[i];
+                        if (c.last) rows_interp_weights(c, a);
                     }
+                    __syncthreads();
+                    if (threadIdx.x == 0) plan_spec(iv == 1);
                     __syncthreads();
                     pf.tick(PT_COMBINE);
                     rows_theta_pass<TP_STEP>(p, g_lo, n_loc, s.tmem, tsum);
@@ -1599,6 +1630,24 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
                         }
                     }
                     __syncthreads();
+                    if (rc->spec_pass) {
+                        // did every speculating row accept?  otherwise materialise the accepted ones
+                        if (threadIdx.x == 0) {
+                            bool ok = true;
+                            for (int b = 0; b < RM; ++b) ok = ok && (!pp[b].spec || rc->r[b].accept);
+                            rc->spec_valid = ok;
+                            rc->redo = !ok;
+                            for (int b = 0; b < RM; ++b) {
+                                if (ok && pp[b].spec) rc->r[b].spec_done = 1;
+                                if (!ok) {
+                                    pp[b].active = pp[b].spec && rc->r[b].accept;
+                                    pp[b].spec = 0;
+                                }
+                            }
+                        }
+                        __syncthreads();
+                        if (rc->redo) rows_theta_pass<TP_STEP>(p, g_lo, n_loc, s.tmem, tsum);
+                    }
                     for (int e = threadIdx.x; e < tot; e += THREADS) {
                         const RowCtl& c = rc->r[e & 3];
                         if (!c.accept) continue;
@@ -1618,7 +1667,9 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
                     if (threadIdx.x < RM) {
                         RowCtl& c = rc->r[threadIdx.x];
                         if (c.accept) {
-                            if (c.theta_zero) { c.cur = 0; c.theta_zero = 0; } else c.cur ^= 1;
+                            if (!c.spec_done) {
+                                if (c.theta_zero) { c.cur = 0; c.theta_zero = 0; } else c.cur ^= 1;
+                            }
                             if (c.last) {
                                 c.done = 1;
                             } else {
@@ -1643,7 +1694,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
             const int j = e >> 2, b = e & 3;
             if (b < nr) p.adj_y0[(size_t)(q0 + b) * p.adj_stride + g_lo + j] = A[e];
         }
-        rows_theta_sum(p, g_lo, n_loc, p.gsum_acc != 0 || q0 > 0);
+        rows_theta_sum(p, g_lo, n_loc, gacc, rc->spec_valid != 0);
         pf.tick(PT_PP_COPY);
         if (threadIdx.x < nr) row_write_status(p, q0 + threadIdx.x, rc->r[threadIdx.x]);
         __syncthreads();

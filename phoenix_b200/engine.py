@@ -378,18 +378,20 @@ def _adjoint_rows(lib, net, packed, G, H, dev, t_rows, t_is_f32, method, rtol, a
     nb = lib.phx_rows_workspace_bytes(_lib.ctx(dev), G, H, N, T, 1)
     ws = _workspace(dev, nb, "solve")
     adj_y0 = torch.empty(adj_shape, dtype=torch.float32, device=ys.device)
-    gpk = torch.empty(lib.phx_packed_grad_bytes(G, H) // 4, dtype=torch.float32, device=ys.device)
+    ctx = _lib.ctx(dev)
+    parts = lib.phx_rows_grad_parts(ctx, G, H, N)
+    gpk = _workspace(dev, parts * lib.phx_packed_grad_bytes(G, H), "gradparts")
     P = 4 * G * H + 2 * H + G
     flat = torch.empty(P, dtype=torch.float32, device=ys.device)
     stn = _new_status_block(N)
     log, cap = _steplog_rows(N)
     flat_t = (ctypes.c_double * (N * T))(*[x for r in t_rows for x in r])
-    ctx, sp = _lib.ctx(dev), _stream_ptr(dev)
+    sp = _stream_ptr(dev)
     rc = lib.phx_solve_adjoint_rows(ctx, G, H, N, _ptr(packed), flat_t, T, int(t_is_f32), _lib.METHOD_IDS[method],
                                     float(rtol), float(atol), int(max_num_steps), _ptr(ys), _ptr(gy), _ptr(adj_y0),
-                                    _ptr(gpk), 0, _ptr(ws), ws.numel(), _ptr(stn), _ptr(log), cap, sp)
+                                    _ptr(gpk), _ptr(ws), ws.numel(), _ptr(stn), _ptr(log), cap, sp)
     _lib.check(rc, "solve_adjoint_rows")
-    _lib.check(lib.phx_unpack_grads(ctx, G, H, _ptr(gpk), _ptr(flat), 0, sp), "unpack_grads")
+    _lib.check(lib.phx_unpack_grads(ctx, G, H, _ptr(gpk), parts, _ptr(flat), 0, sp), "unpack_grads")
     _tls().last_status_block = stn
     for i in range(N):
         _finish(stn[i], "adjoint solve %d" % i if N > 1 else "adjoint solve", dev)

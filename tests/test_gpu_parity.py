@@ -371,11 +371,11 @@ def test_multi_problem_entry_points_check_their_limits(pb):
     lib = _lib.load()
     packed, G, H, dev = engine.packed_weights(net)
     ctx = _lib.ctx(dev)
-    y0 = torch.rand(9, 1, G).cuda()
-    yout = torch.empty(9, 2, 1, G).cuda()
+    y0 = torch.rand(33, 1, G).cuda()
+    yout = torch.empty(33, 2, 1, G).cuda()
     ws = torch.empty(lib.phx_solve_workspace_bytes(ctx, G, H, 1, 2, 0), dtype=torch.uint8, device="cuda")
     lib.phx_solve_workspace_init(ctypes.c_void_p(ws.data_ptr()), ws.numel(), None)
-    st = torch.zeros(9, 10, dtype=torch.int32).pin_memory()
+    st = torch.zeros(33, 10, dtype=torch.int32).pin_memory()
     ptr = lambda t: ctypes.c_void_p(t.data_ptr())
 
     def call(n, times):
@@ -383,12 +383,16 @@ def test_multi_problem_entry_points_check_their_limits(pb):
         return lib.phx_solve_forward_many(ctx, G, H, 1, n, ptr(packed), ptr(y0), tarr, 2, 1, 2, 1e-7, 1e-9, 2 ** 31 - 1,
                                           ptr(yout), ptr(ws), ws.numel(), ptr(st), None)
 
-    assert call(9, [0.0, 1.0] * 9) != 0 and "16" in _lib.last_error()          # 9 * 2 > 16 output times
+    assert call(33, [0.0, 1.0] * 33) != 0 and "64" in _lib.last_error()        # 33 * 2 > 64 output times
     assert call(2, [0.0, 1.0, 1.0, 0.5]) != 0                                   # second problem's times decrease
     assert call(8, [0.0, 0.5] * 8) == 0
     torch.cuda.synchronize()
-    with torch.no_grad():
-        ref = pb.odeint(net, y0[3], torch.tensor([0.0, 0.5]), method="rk4")
+    pb.engine.FORCE_ENGINE = "resident"    # the same kernel as phx_solve_forward_many, one problem per launch
+    try:
+        with torch.no_grad():
+            ref = pb.odeint(net, y0[3], torch.tensor([0.0, 0.5]), method="rk4")
+    finally:
+        pb.engine.FORCE_ENGINE = None
     assert torch.equal(yout[3], ref)
     assert all(int(st[i, 0]) == 0 and int(st[i, 3]) == 4 for i in range(8))     # code OK, 4 RHS evaluations each
 

@@ -21,11 +21,12 @@ def main():
     method = sys.argv[3] if len(sys.argv) > 3 else "dopri5"
     dt = float(sys.argv[4]) if len(sys.argv) > 4 else 0.0051
     reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+    N = int(sys.argv[6]) if len(sys.argv) > 6 else 1     # samples per call (rows kernels: 4 in lock-step per pass)
     lib = _lib.load()
     ctx = _lib.ctx(0)
     net = pb.ODENet("cuda:0", G, neurons=H)
-    y0 = torch.rand(1, G, device="cuda")
-    t = torch.tensor([0.0, dt])
+    y0 = torch.rand(N, 1, G, device="cuda")
+    t = torch.tensor([[0.0, dt]] * N)
     n = lib.phx_profile_slots()
     prof = torch.zeros(n, dtype=torch.int64, device="cuda")
     mhz = torch.cuda.clock_rate() / 1e3 if hasattr(torch.cuda, "clock_rate") else 1900.0
@@ -43,8 +44,8 @@ def main():
 
     for _ in range(3):
         y0g = y0.clone().requires_grad_(True)
-        y = pb.odeint_adjoint(net, y0g, t, method=method)
-        (y[1] ** 2).mean().backward()
+        y = pb.odeint_adjoint_many(net, y0g, t, method=method)
+        (y[:, 1] ** 2).mean().backward()
     torch.cuda.synchronize()
     _lib.check(lib.phx_ctx_set_profile(ctx, ctypes.c_void_p(prof.data_ptr())), "set_profile")
     evs = []
@@ -53,21 +54,21 @@ def main():
         y0g = y0.clone().requires_grad_(True)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        y = pb.odeint_adjoint(net, y0g, t, method=method)
+        y = pb.odeint_adjoint_many(net, y0g, t, method=method)
         b.record()
         evs.append((a, b))
         ys.append((y, y0g))
-    show("FORWARD  G=%d H=%d %s dt=%g" % (G, H, method, dt), evs)
+    show("FORWARD  G=%d H=%d %s dt=%g N=%d" % (G, H, method, dt, N), evs)
     print("   status", pb.last_status())
     evs = []
     for y, y0g in ys:
-        loss = (y[1] ** 2).mean()
+        loss = (y[:, 1] ** 2).mean()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
         loss.backward()
         b.record()
         evs.append((a, b))
-    show("ADJOINT  G=%d H=%d %s dt=%g" % (G, H, method, dt), evs)
+    show("ADJOINT  G=%d H=%d %s dt=%g N=%d" % (G, H, method, dt, N), evs)
     print("   status", pb.last_status())
     lib.phx_ctx_set_profile(ctx, None)
 
