@@ -123,7 +123,7 @@ struct RowsView {
     __device__ __forceinline__ float* st(int i) const { return s.at<float>(p.so.st) + (size_t)i * RM * p.gpc; }
     __device__ __forceinline__ float* jred() const { return s.at<float>(p.so.jred); }
     __device__ __forceinline__ float* actL() const { return s.at<float>(p.so.actL); }
-    __device__ __forceinline__ float* ysf() const { return s.at<float>(p.so.ysf); }       // [NFS][gpc][RM]
+    __device__ __forceinline__ float* ysf() const { return s.at<float>(p.so.ysf); }       // [gpc][RM][NFS] (fgj, fm too)
     __device__ __forceinline__ float* fgj() const { return s.at<float>(p.so.FGJ); }
     __device__ __forceinline__ float* fm() const { return s.at<float>(p.so.FM); }
     __device__ __forceinline__ const float4* w1() const { return s.at<float4>(p.so.w1r); }
@@ -798,8 +798,8 @@ __device__ __forceinline__ void rows_adj_eval(const ResParams& __restrict__ p, S
             v.st(4 + c.slot[sid])[e] = ky;
             const int fs = c.fslot[sid];
             if (fs >= 0) {
-                v.fm()[fs * BL + e] = (s.asb()[e] * jm) * s.maskm()[j];
-                v.fgj()[fs * BL + e] = s.gjb()[e];
+                v.fm()[e * NFS + fs] = (s.asb()[e] * jm) * s.maskm()[j];
+                v.fgj()[e * NFS + fs] = s.gjb()[e];
             }
             if (has_next) {
                 const float yn = ynext(b, j, e, ky);
@@ -809,7 +809,7 @@ __device__ __forceinline__ void rows_adj_eval(const ResParams& __restrict__ p, S
                 s.acts2()[e] = sv;
                 v.actL()[e] = lv;
                 const int fsn = c.fslot[sid_next];
-                if (fsn >= 0) v.ysf()[fsn * BL + e] = yn;
+                if (fsn >= 0) v.ysf()[e * NFS + fsn] = yn;
             }
         }
     }
@@ -977,31 +977,41 @@ __device__ __forceinline__ void rows_interp_weights(const RowCtl& c, RowPP& a) {
     }
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {   // MUFU.RCP, 1 ulp; callers pass normal-range values (>= atol)
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float2 bc2(float x) { return make_float2(x, x); }
+
 // One pass over this CTA's share of every ACTIVE row's packed cotangent vector.  out[b * 2 + {0,1}] (shared memory, doubles)
 // receives this CTA's partial sums per row: STEP (sum (err/tol)^2, non-finite count), D01 (sum (th/scale)^2,
 // sum (k/scale)^2), D2 (sum ((k1-k0)/scale)^2, -).  Ends with a block barrier.
+// The step / fixed passes are instruction-bound (8.9 M elements x rows at the headline shape): the three 6-term
+// combinations of an element pair run as packed fp32x2 FMAs (FFMA2), the tolerance division is MUFU.RCP + FMUL (the error
+// ratio only feeds the accept test and the step-size law), a non-finite theta is caught by a NaN-propagating FMA.
 template <int MODE>
 __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, int g_lo, int n_loc, uint32_t tmem, double* out) {
     Smem s(p);
     s.tmem = tmem;
     RowsView v(p, s);
     v.tq = tm_quarter(tmem);
-    const int BL = RM * p.gpc, Hq = p.Hp >> 2;
+    const int Hq = p.Hp >> 2;
     const int tot = n_loc * RM;
     const PhxPackedGradOff off = phx_packed_grad_offsets(p.G, p.H);
     const float atol_f = p.atol_f, rtol_f = p.rtol_f;
     const RowPP* pp = s.at<RowPP>(p.so.ppa);
     constexpr bool WRITES = MODE == TP_STEP || MODE == TP_FIXED;
     constexpr int NV = (MODE == TP_D01) ? 1 : (MODE == TP_D2 ? 2 : NFS);   // factor slots the mode touches
-    // activation tables of the stored stage inputs (the scratch aliases the fold / J-partial buffers, idle here)
+    // activation tables of the stored stage inputs, [gene][row][slot] like the other per-gene factor tables (the scratch
+    // aliases the fold / J-partial buffers, idle here)
     float* US = s.at<float>(p.so.red);
-    float* UL = US + NFS * BL;
+    float* UL = US + NFS * RM * p.gpc;
     for (int i = threadIdx.x; i < NFS * tot; i += THREADS) {
-        const int fs = i / tot, e = i - fs * tot;
         float sv, lv, den;
-        hill(v.ysf()[fs * BL + e], sv, lv, den);
-        US[fs * BL + e] = sv;
-        UL[fs * BL + e] = lv;
+        hill(v.ysf()[i], sv, lv, den);
+        US[i] = sv;
+        UL[i] = lv;
     }
     double* dred = s.dred();
     if (threadIdx.x < WARPS * 8) dred[threadIdx.x] = 0.0;
@@ -1024,55 +1034,66 @@ __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, in
             wo[f] = pp[b].wo[f];
         }
         const bool sep = MODE == TP_STEP && pp[b].last;    // the written value is not th1: a third combination
-        // per theta element: k[f] = u[f] * V[f]
-        auto elem = [&](const float th0, const float (&k)[NV], float& o) {
-            if (MODE == TP_D01) {
-                const float scale = atol_f + fabsf(th0) * rtol_f;
-                const float r0 = __fdividef(th0, scale), r1 = __fdividef(k[0], scale);
-                a0 = fmaf(r0, r0, a0);
-                a1 = fmaf(r1, r1, a1);
-            } else if (MODE == TP_D2) {
-                const float scale = atol_f + fabsf(th0) * rtol_f;
-                const float r = __fdividef(k[1] - k[0], scale);
-                a0 = fmaf(r, r, a0);
-            } else if (MODE == TP_FIXED) {
-                float acc = k[0] * wo[0];
+        // scalar tail of a step element: error-ratio term, non-finite flag
+        auto tail = [&](const float th0, const float inc, const float er) {
+            const float th1 = th0 + inc;
+            const float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
+            const float r = er * rcp_approx(tol);
+            a0 = fmaf(r, r, a0);
+            a1 = fmaf(th1, 0.f, a1);      // 0 while finite, NaN once th1 is inf / NaN
+            return th1;
+        };
+        // two theta elements (k = u * V) at once
+        auto pair = [&](const float2 th0, const float (&u)[NV], const float2 (&Vp)[NV], float2& o) {
+            float2 k[NV];
 #pragma unroll
-                for (int f = 1; f < NV; ++f) acc = fmaf(k[f], wo[f], acc);
-                o = th0 + acc;
+            for (int f = 0; f < NV; ++f) k[f] = __fmul2_rn(bc2(u[f]), Vp[f]);
+            if (MODE == TP_D01) {
+                const float sx = atol_f + fabsf(th0.x) * rtol_f, sy = atol_f + fabsf(th0.y) * rtol_f;
+                const float ix = rcp_approx(sx), iy = rcp_approx(sy);
+                a0 = fmaf(th0.x * ix, th0.x * ix, a0);
+                a0 = fmaf(th0.y * iy, th0.y * iy, a0);
+                a1 = fmaf(k[0].x * ix, k[0].x * ix, a1);
+                a1 = fmaf(k[0].y * iy, k[0].y * iy, a1);
+            } else if (MODE == TP_D2) {
+                const float sx = atol_f + fabsf(th0.x) * rtol_f, sy = atol_f + fabsf(th0.y) * rtol_f;
+                const float rx = (k[1].x - k[0].x) * rcp_approx(sx), ry = (k[1].y - k[0].y) * rcp_approx(sy);
+                a0 = fmaf(rx, rx, a0);
+                a0 = fmaf(ry, ry, a0);
+            } else if (MODE == TP_FIXED) {
+                float2 acc = __fmul2_rn(k[0], bc2(wo[0]));
+#pragma unroll
+                for (int f = 1; f < NV; ++f) acc = __ffma2_rn(k[f], bc2(wo[f]), acc);
+                o = __fadd2_rn(th0, acc);
             } else {
-                float inc = k[0] * cs[0], er = k[0] * ce[0];
+                float2 inc = __fmul2_rn(k[0], bc2(cs[0])), er = __fmul2_rn(k[0], bc2(ce[0]));
 #pragma unroll
                 for (int f = 1; f < NV; ++f) {
-                    inc = fmaf(k[f], cs[f], inc);
-                    er = fmaf(k[f], ce[f], er);
+                    inc = __ffma2_rn(k[f], bc2(cs[f]), inc);
+                    er = __ffma2_rn(k[f], bc2(ce[f]), er);
                 }
-                const float th1 = th0 + inc;
-                const float tol = atol_f + rtol_f * fmaxf(fabsf(th0), fabsf(th1));
-                const float r = __fdividef(er, tol);
-                a0 = fmaf(r, r, a0);
-                a1 = fmaf(th1, 0.f, a1);      // 0 while finite, NaN once th1 is inf / NaN
-                o = th1;
+                o.x = tail(th0.x, inc.x, er.x);
+                o.y = tail(th0.y, inc.y, er.y);
                 if (sep) {
-                    float acc = k[0] * wo[0];
+                    float2 acc = __fmul2_rn(k[0], bc2(wo[0]));
 #pragma unroll
-                    for (int f = 1; f < NV; ++f) acc = fmaf(k[f], wo[f], acc);
-                    o = th0 + acc;
+                    for (int f = 1; f < NV; ++f) acc = __ffma2_rn(k[f], bc2(wo[f]), acc);
+                    o = __fadd2_rn(th0, acc);
                 }
             }
         };
         auto quad = [&](const float (&u)[NV], const float4 (&V)[NV], const size_t idx) {
             const float4 th4 = src ? *reinterpret_cast<const float4*>(src + idx) : zero4();
-            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            float2 lo[NV], hi[NV], o0 = make_float2(0.f, 0.f), o1 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                float k[NV];
-#pragma unroll
-                for (int f = 0; f < NV; ++f) k[f] = u[f] * comp4(V[f], e);
-                elem(comp4(th4, e), k, o[e]);
+            for (int f = 0; f < NV; ++f) {
+                lo[f] = make_float2(V[f].x, V[f].y);
+                hi[f] = make_float2(V[f].z, V[f].w);
             }
+            pair(make_float2(th4.x, th4.y), u, lo, o0);
+            pair(make_float2(th4.z, th4.w), u, hi, o1);
             if (WRITES) {
-                float4 o4 = make_float4(o[0], o[1], o[2], o[3]);
+                float4 o4 = make_float4(o0.x, o0.y, o1.x, o1.y);
                 if (spec == 2) o4 = add4(*reinterpret_cast<const float4*>(dst + idx), o4);
                 *reinterpret_cast<float4*>(dst + idx) = o4;
             }
@@ -1083,13 +1104,23 @@ __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, in
 #pragma unroll
             for (int f = 0; f < NV; ++f) tm_ld4(blk == 0 ? v.col_fsp(sl[f], b) : v.col_fg(sl[f], b), V[f]);
             if (!v.qok) continue;
-            const float* U = (blk == 0 ? v.fgj() : (v.q >= Hq ? UL : US)) + b;
+            const float* U = (blk == 0 ? v.fgj() : (v.q >= Hq ? UL : US)) + b * NFS;
             const size_t base = (blk == 0 ? off.WA : off.W1) + (size_t)g_lo * p.K2 + 4 * (size_t)v.q;
 #pragma unroll 1
             for (int j = j0; j < jend; ++j) {
                 float u[NV];
+                if (NV == NFS) {
+                    const float2* u2 = reinterpret_cast<const float2*>(U + j * (RM * NFS));
 #pragma unroll
-                for (int f = 0; f < NV; ++f) u[f] = U[sl[f] * BL + j * RM];
+                    for (int f = 0; f < NFS / 2; ++f) {
+                        const float2 t = u2[f];
+                        u[(2 * f) % NV] = t.x;
+                        u[(2 * f + 1) % NV] = t.y;
+                    }
+                } else {
+#pragma unroll
+                    for (int f = 0; f < NV; ++f) u[f] = U[j * (RM * NFS) + sl[f]];
+                }
                 quad(u, V, base + (size_t)j * p.K2);
             }
             if (blk == 1 && blockIdx.x == 0 && v.gg == 0) {   // biases: stage derivative = gS | gLP itself
@@ -1099,15 +1130,24 @@ __device__ __noinline__ void rows_theta_pass(const ResParams& __restrict__ p, in
                 quad(u, V, off.bias + 4 * (size_t)v.q);
             }
         }
-        // gene multipliers: threads e = (gene, row) with row == b
-        for (int e = 4 * (int)threadIdx.x + b; e < tot; e += 4 * THREADS) {
-            float k[NV];
+        // gene multipliers: two genes per thread (elements e = (gene, row b)); an odd tail pairs with an all-zero element,
+        // which adds exactly 0 to every sum
+        for (int jp = 2 * (int)threadIdx.x; jp < n_loc; jp += 2 * THREADS) {
+            const bool two = jp + 1 < n_loc;
+            const int e0 = jp * RM + b, e1 = (two ? jp + 1 : jp) * RM + b;
+            float u[NV];
+            float2 Vp[NV], o = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int f = 0; f < NV; ++f) k[f] = v.fm()[sl[f] * BL + e];
-            const size_t idx = off.m + g_lo + (e >> 2);
-            float o = 0.f;
-            elem(src ? src[idx] : 0.f, k, o);
-            if (WRITES) dst[idx] = (spec == 2) ? dst[idx] + o : o;
+            for (int f = 0; f < NV; ++f) {
+                u[f] = 1.f;
+                Vp[f] = make_float2(v.fm()[e0 * NFS + sl[f]], two ? v.fm()[e1 * NFS + sl[f]] : 0.f);
+            }
+            const size_t idx = off.m + g_lo + jp;
+            pair(make_float2(src ? src[idx] : 0.f, (src && two) ? src[idx + 1] : 0.f), u, Vp, o);
+            if (WRITES) {
+                dst[idx] = (spec == 2) ? dst[idx] + o.x : o.x;
+                if (two) dst[idx + 1] = (spec == 2) ? dst[idx + 1] + o.y : o.y;
+            }
         }
         const double t0 = warp_sum_d((double)a0);
         const double t1 = (MODE == TP_STEP) ? warp_sum_d(isfinite(a1) ? 0.0 : 1.0) : warp_sum_d((double)a1);
@@ -1213,13 +1253,13 @@ __device__ __noinline__ double rows_theta_zero_norm(const ResParams& __restrict_
         const RowCtl& c = rc->r[e & 3];
         const int f1 = c.fslot[sid1], f0 = sid0 >= 0 ? c.fslot[sid0] : c.fslot[sid1];
         float s1, l1, s0, l0, den;
-        hill(v.ysf()[f1 * BL + e], s1, l1, den);
-        hill(v.ysf()[f0 * BL + e], s0, l0, den);
-        const double gj1 = v.fgj()[f1 * BL + e], gj0 = v.fgj()[f0 * BL + e];
+        hill(v.ysf()[e * NFS + f1], s1, l1, den);
+        hill(v.ysf()[e * NFS + f0], s0, l0, den);
+        const double gj1 = v.fgj()[e * NFS + f1], gj0 = v.fgj()[e * NFS + f0];
         ug[0] += gj1 * gj1; ug[1] += gj1 * gj0; ug[2] += gj0 * gj0;
         ug[3] += (double)s1 * s1; ug[4] += (double)s1 * s0; ug[5] += (double)s0 * s0;
         ul[0] += (double)l1 * l1; ul[1] += (double)l1 * l0; ul[2] += (double)l0 * l0;
-        const float km = v.fm()[f1 * BL + e] - (sid0 >= 0 ? v.fm()[f0 * BL + e] : 0.f);
+        const float km = v.fm()[e * NFS + f1] - (sid0 >= 0 ? v.fm()[e * NFS + f0] : 0.f);
         ul[3] += (double)km * (double)km;
     }
     double* tot = s.at<double>(p.so.rsum) + WARPS * RM * 8;   // [RM][8] x 2 (the tail of the per-row sum buffer)
@@ -1315,7 +1355,7 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
             v.actL()[e] = lv;
             s.asb()[e] = as;
             s.gjb()[e] = as * s.relum()[j];
-            if (fs >= 0) v.ysf()[fs * BL + e] = ys;
+            if (fs >= 0) v.ysf()[e * NFS + fs] = ys;
         };
         auto no_y = [](int, int, int, float) { return 0.f; };
 
