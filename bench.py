@@ -92,6 +92,21 @@ def cpu_sample(w, y0, target, t, n_samples):
     return evals, dt
 
 
+def cpu_prior_step(w, K, gen):
+    """One prior-loss evaluation of training_step on the CPU port: prior_only_forward on K rows + its backward
+    (train_insilico.py:134-138)."""
+    from oracle import phoenix_oracle as O
+    if not isinstance(w, O.Weights):
+        w = O.Weights(*w)
+    x = torch.rand(K, 1, G, generator=gen) - 0.5
+    pg = torch.randn(K, 1, G, generator=gen) * 0.1
+    t0 = time.perf_counter()
+    J = O.rhs(w, x, decay=False)
+    g = 2.0 * (J - pg) / J.numel()
+    O.rhs_vjp(w, x, g, decay=False)
+    return time.perf_counter() - t0
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -111,7 +126,10 @@ def run_reference(args):
     value = G * evals / secs
     sample = "%d of the %d samples of a step per timed step (fwd+adjoint, %s)" % (n_samples, BATCH, METHOD)
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "impl": "reference", "reference_is": "CPU port of the reference (oracle/phoenix_oracle.py, pinned to the "
+        "reference's own outputs by tests/golden); the reference is pure Python over torch-CPU and cannot be installed "
+        "on the GPU box, see DESIGN.md section 5",
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "breast 11165 genes x 200 neurons, %s, dt=0.0051 (bounded sample)" % METHOD,
@@ -339,7 +357,7 @@ def run_ours(args):
         loss = torch.mean((torch.stack(preds) - tgt) ** 2)
         loss.backward()
         if world > 1:
-            parallel.allreduce_grads(net)
+            parallel.allreduce_grads(net, average=False)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
     def step_e2e():
@@ -351,9 +369,13 @@ def run_ours(args):
         loss = torch.mean((pred - tgt) ** 2)
         loss.backward()
         if world > 1:
-            parallel.allreduce_grads(net)
+            parallel.allreduce_grads(net, average=False)
         loss_host.copy_(loss.detach().reshape(1), non_blocking=True)
 
+    # the per-sample loop is timed with lazy error checking (explicit opt-in: the host runs ahead of the GPU and the
+    # status records are inspected at the next call / check_errors()); the default raises at the call site like the
+    # reference, at the cost of one stream synchronisation per solve
+    pb.set_sync_errors(False)
     for _ in range(args.warmup):
         step_e2e()
         step_e2e_loop()
@@ -363,6 +385,36 @@ def run_ours(args):
     pb.check_errors()
     sampler.stop_flag = True
     sampler.join(timeout=2)
+
+    # ---- dense ("trained-like") weights: the same device-resident step with N(0, 0.05^2) matrices -------------------
+    dense = None
+    if not int(os.environ.get("PHX_BENCH_SKIP_DENSE", "0")):
+        wd = synthetic_weights(1003, True)
+        with torch.no_grad():
+            for p_, src in zip(net.parameters(), wd):
+                p_.copy_(src)
+        packed, _, _, _ = engine.packed_weights(net)
+        for _ in range(3):
+            step_resident(False)
+        torch.cuda.synchronize()
+        ds = max(3, args.steps // 2)
+        ms_dense = timed(lambda: step_resident(False), ds) / ds
+        ev_d = sum(int(st_f[i, 3]) + int(st_a[i, 3]) for i in range(BATCH))
+        dense = {"ms_per_step": ms_dense, "value_this_rank": G * ev_d / (ms_dense * 1e-3), "steps": ds,
+                 "rhs_evals_per_step": ev_d, "weights": "N(0, 0.05^2) dense matrices (SURVEY 8d 'trained-like')"}
+        with torch.no_grad():
+            for p_, src in zip(net.parameters(), w):
+                p_.copy_(src)
+        packed, _, _, _ = engine.packed_weights(net)
+
+    # ---- BASELINE metric 2: train epoch time of the breast config at N GPUs (strong scaling: the 17 samples and the
+    # 10 000 prior rows of every step are split over the ranks; tools/train_epoch.py = the reference's training loop) ---
+    epoch = None
+    if not int(os.environ.get("PHX_BENCH_SKIP_EPOCH", "0")):
+        sys.path.insert(0, os.path.join(REPO, "tools"))
+        import train_epoch
+        epoch = train_epoch.run_epochs("breast", epochs=2, many=True, instrument=(world == 1))
+        torch.cuda.empty_cache()
 
     # ---- tensor-core leg (rank 0, N = 1 only; bounded): the batched RHS of BASELINE config 5 ---------------------
     tensor = None
@@ -401,11 +453,21 @@ def run_ours(args):
         except Exception:
             pass
         cores = os.cpu_count() or 1
+        cpu8 = cpu_epoch = None
         if world == 1:
             torch.set_num_threads(cores)
             cpu_sample(w, y0_h, target_h, t_h, 1)
             ce, cs = cpu_sample(w, y0_h, target_h, t_h, 3)
             cpu_value = G * ce / cs
+            t_prior = cpu_prior_step(w, 10000, torch.Generator().manual_seed(3))
+            # epoch time of the CPU port = 10 steps x (17 samples + one 10 000-row prior loss), from the timed sample
+            cpu_epoch = {"epoch_s": 10 * (BATCH * cs / 3 + t_prior), "cores": cores,
+                         "sample": "extrapolated from 3 samples (fwd+adjoint) and one 10 000-row prior forward+backward; "
+                                   "optimiser step not included", "prior_step_s": t_prior, "sample_s": cs / 3}
+            torch.set_num_threads(8)
+            e8, s8 = cpu_sample(w, y0_h, target_h, t_h, 1)
+            cpu8 = G * e8 / s8
+            torch.set_num_threads(cores)
         else:
             cpu_value = None   # measured at N = 1 only (torchrun pins the ranks to one OpenMP thread)
         line = {
@@ -436,10 +498,17 @@ def run_ours(args):
                                      "frac": n_fwd * (16.0 * G * H + 8.0 * G) / (fwd_ms * 1e-3) / 1e9 / peak},
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (burst)" if peaks else "fallback 6650"},
             "cpu_baseline": {"value": cpu_value, "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample"
+                             "value_8_threads": cpu8,
+                             "sample": "3 of the 17 samples of one step (fwd+adjoint), after 1 warm-up sample; "
+                                       "value_8_threads: 1 sample with torch.set_num_threads(8)"
                                        if world == 1 else "measured at N=1 only"},
             "clocks": sampler.summary(),
         }
+        if dense is not None:
+            line["dense_weights"] = dense
+        if epoch is not None:
+            epoch["cpu_port"] = cpu_epoch
+            line["train_epoch"] = epoch
         if tensor is not None:
             bf16 = float(peaks.get("bf16_tflops", 1590.0))
             tpeak = bf16 / 2.0                            # TF32 dense = half the bf16 rate (B200_PROFILING.md)

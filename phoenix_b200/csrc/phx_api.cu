@@ -180,6 +180,9 @@ int phx_ctx_create(int device, phx_ctx** out) {
 void phx_ctx_destroy(phx_ctx* ctx) { delete ctx; }
 
 int phx_ctx_num_sms(const phx_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
+}  // extern "C"
+int phx_ctx_device(const phx_ctx* ctx) { return ctx ? ctx->device : 0; }
+extern "C" {
 
 int phx_ctx_set_profile(phx_ctx* ctx, void* slots) {
     if (!ctx) return PHX_ERR_INVALID;
@@ -222,6 +225,7 @@ size_t phx_packed_bytes(int G, int H) { return phx_packed_floats(G, H) * sizeof(
 
 int phx_pack_weights(phx_ctx* ctx, int G, int H, const float* m, const float* Wp, const float* bp, const float* Ws,
                      const float* bs, const float* Wa, float* packed, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     if (!ctx || !check_dims(G, H, 1) || !m || !Wp || !bp || !Ws || !bs || !Wa || !packed) return PHX_ERR_INVALID;
     const int Hp = phx_Hp(H), K2 = 2 * Hp;
     PhxPacked v = phx_packed_view(packed, G, H);
@@ -244,6 +248,7 @@ size_t phx_rhs_workspace_bytes(int G, int H, int B) { return phx_rhs_workspace_f
 
 int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, float* f, int decay,
                     void* workspace, size_t workspace_bytes, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     if (!ctx || !check_dims(G, H, B) || !packed || !y || !f || !workspace) return PHX_ERR_INVALID;
     if (workspace_bytes < phx_rhs_workspace_bytes(G, H, B)) {
         phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
@@ -258,6 +263,7 @@ int phx_rhs_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, cons
 int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y, const float* g, int decay,
                 float* ybar, float* grads_flat, int accumulate, void* workspace, size_t workspace_bytes,
                 void* stream) {
+    PhxDevGuard dev_guard(ctx);
     if (!ctx || !check_dims(G, H, B) || !packed || !y || !g || !workspace) return PHX_ERR_INVALID;
     if (workspace_bytes < phx_rhs_workspace_bytes(G, H, B)) {
         phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
@@ -364,6 +370,7 @@ int phx_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, co
                       const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol, double atol,
                       int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
                       phx_status* status, double* steplog, int steplog_cap, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     g_err[0] = 0;
     if (!y0 || !y_out) {
         phx_set_error("null y0 / y_out");
@@ -384,6 +391,7 @@ int phx_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* packed, co
                       int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
                       const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat, void* workspace,
                       size_t workspace_bytes, phx_status* status, double* steplog, int steplog_cap, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     g_err[0] = 0;
     if (!y_saved || !grad_y || !adj_y0 || !grads_flat) {
         phx_set_error("null y_saved / grad_y / adj_y0 / grads_flat");
@@ -406,6 +414,7 @@ int phx_solve_forward_many(phx_ctx* ctx, int G, int H, int B, int N, const float
                            const double* t_host, int T, int t_is_f32, int method, double rtol, double atol,
                            int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
                            phx_status* status, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     g_err[0] = 0;
     if (!y0 || !y_out) {
         phx_set_error("null y0 / y_out");
@@ -427,6 +436,7 @@ int phx_solve_adjoint_many(phx_ctx* ctx, int G, int H, int B, int N, const float
                            int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,
                            const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
                            void* workspace, size_t workspace_bytes, phx_status* status, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     g_err[0] = 0;
     if (!y_saved || !grad_y || !adj_y0 || !grads_flat) {
         phx_set_error("null y_saved / grad_y / adj_y0 / grads_flat");
@@ -543,6 +553,7 @@ int phx_solve_forward_rows(phx_ctx* ctx, int G, int H, int N, const float* packe
                            int T, int t_is_f32, int reversed, int method, double rtol, double atol, int64_t max_num_steps,
                            float* y_out, void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                            int steplog_cap, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     g_err[0] = 0;
     if (!y0 || !y_out) {
         phx_set_error("null y0 / y_out");
@@ -568,6 +579,7 @@ int phx_rows_grad_parts(const phx_ctx* ctx, int G, int H, int N) {
 
 int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int nparts, float* grads_flat,
                      int accumulate, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     if (!ctx || !check_dims(G, H, 1) || !packed_grads || !grads_flat || nparts < 1) return PHX_ERR_INVALID;
     const int Hp = phx_Hp(H), K2 = 2 * Hp;
     const PhxPackedGradOff po = phx_packed_grad_offsets(G, H);
@@ -593,6 +605,7 @@ int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packe
                            const float* y_saved, const float* grad_y, float* adj_y0, float* grads_packed_parts,
                            void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                            int steplog_cap, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     g_err[0] = 0;
     if (!y_saved || !grad_y || !adj_y0 || !grads_packed_parts) {
         phx_set_error("null y_saved / grad_y / adj_y0 / grads_packed_parts");

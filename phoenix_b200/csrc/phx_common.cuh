@@ -358,3 +358,20 @@ int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const floa
                              float* grads_flat, int accumulate, float* tcws, cudaStream_t stream);
 
 void phx_set_error(const char* fmt, ...);
+int phx_ctx_device(const phx_ctx* ctx);
+// Every entry point that enqueues work makes the context's device current for the duration of the call (the caller may be
+// sitting on another GPU) and restores the previous one.
+struct PhxDevGuard {
+    int prev = -1;
+    bool sw = false;
+    explicit PhxDevGuard(const phx_ctx* ctx) {
+        if (!ctx) return;
+        const int d = phx_ctx_device(ctx);
+        if (cudaGetDevice(&prev) == cudaSuccess && prev != d) sw = cudaSetDevice(d) == cudaSuccess;
+    }
+    ~PhxDevGuard() {
+        if (sw) cudaSetDevice(prev);
+    }
+    PhxDevGuard(const PhxDevGuard&) = delete;
+    PhxDevGuard& operator=(const PhxDevGuard&) = delete;
+};

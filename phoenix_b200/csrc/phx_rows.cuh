@@ -755,6 +755,14 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_fwd_kernel(const __gr
             __syncthreads();
             pf.tick(PT_CTRL);
         }
+        // a row stopped by a solver assertion never reached its remaining output times: they read NaN, not garbage
+        for (int e = threadIdx.x; e < tot; e += THREADS) {
+            const int j = e >> 2, b = e & 3;
+            const RowCtl& c = rc->r[b];
+            if (b < nr && c.code != PHX_ST_OK)
+                for (int i = c.next_out; i < p.T; ++i)
+                    p.yout[(size_t)(q0 + b) * p.yout_stride + (size_t)i * p.G + g_lo + j] = nanf("");
+        }
         if (threadIdx.x < nr) row_write_status(p, q0 + threadIdx.x, rc->r[threadIdx.x]);
         __syncthreads();
     }
@@ -1314,6 +1322,20 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
     double* tsum = s.at<double>(p.so.dred) + 112;  // [2 * RM] theta-pass totals
     RowPP* pp = s.at<RowPP>(p.so.ppa);
     const bool dop = p.method == PHX_DOPRI5;
+    // factor slots a method never writes (euler: 1..5, ...) enter the theta passes with weight 0: they must hold finite
+    // values, so every table starts at zero (shared memory and tensor memory)
+    for (int i = threadIdx.x; i < NFS * BL; i += THREADS) {
+        v.ysf()[i] = 0.5f;
+        v.fgj()[i] = 0.f;
+        v.fm()[i] = 0.f;
+    }
+    if (v.warp < 4) {
+        for (int c = 0; c < 2 * NFS * RM; ++c) tm_st4(v.tq + (uint32_t)(p.tm_fac + 4 * c), zero4());
+        tm_wait_st();
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 
     for (int q0 = 0; q0 < p.ntot; q0 += p.rows) {
         const int nr = min(p.rows, p.ntot - q0);
@@ -1732,7 +1754,8 @@ __global__ void __launch_bounds__(PHX_THREADS, 1) phx_rows_adj_kernel(const __gr
         }
         for (int e = threadIdx.x; e < tot; e += THREADS) {
             const int j = e >> 2, b = e & 3;
-            if (b < nr) p.adj_y0[(size_t)(q0 + b) * p.adj_stride + g_lo + j] = A[e];
+            if (b < nr)   // (NaN for a row stopped by a solver assertion)
+                p.adj_y0[(size_t)(q0 + b) * p.adj_stride + g_lo + j] = rc->r[b].code == PHX_ST_OK ? A[e] : nanf("");
         }
         rows_theta_sum(p, g_lo, n_loc, gacc, rc->spec_valid != 0);
         pf.tick(PT_PP_COPY);

@@ -603,6 +603,7 @@ int phx_stream_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* pac
                              const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol,
                              double atol, int64_t max_num_steps, float* y_out, void* workspace, size_t workspace_bytes,
                              phx_status* status, double* steplog, int steplog_cap, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     Stream S;
     float* base;
     cudaStream_t st = (cudaStream_t)stream;
@@ -649,6 +650,7 @@ int phx_stream_solve_adjoint(phx_ctx* ctx, int G, int H, int B, const float* pac
                              const float* y_saved, const float* grad_y, float* adj_y0, float* grads_flat,
                              void* workspace, size_t workspace_bytes, phx_status* status, double* steplog,
                              int steplog_cap, void* stream) {
+    PhxDevGuard dev_guard(ctx);
     Stream S;
     float* base;
     cudaStream_t st = (cudaStream_t)stream;

@@ -11,10 +11,11 @@ import torch
 from . import _lib
 
 # solver "assert" conditions (rk_common.py:154,175-176) are checked when the status record is read.  With
-# SYNC_ERRORS the stream is synchronised after every solve and the reference's AssertionError is raised at the call
-# site (exact reference behaviour); otherwise the records are inspected lazily (next call / check_errors()), which
-# keeps the host running ahead of the GPU.
-SYNC_ERRORS = False
+# SYNC_ERRORS (the default: exact reference behaviour) the stream is synchronised after every solve and the reference's
+# AssertionError is raised at the call site.  set_sync_errors(False) is an explicit opt-in to lazy checking, which keeps
+# the host running ahead of the GPU (a loop of per-sample calls pipelines): the records are then inspected at the start
+# of every later solve, by check_errors(), and at interpreter exit; outputs a failed solve did not reach are NaN.
+SYNC_ERRORS = True
 STEP_LOGGING = False
 STEPLOG_CAP = 4096
 FORCE_ENGINE = None  # None | "rows" | "resident" | "stream"  (tests compare the engines on the same inputs)
@@ -39,6 +40,20 @@ _last_rhs = {}   # rhs workspace data_ptr -> signature of the phx_rhs_forward ca
 def set_sync_errors(flag):
     global SYNC_ERRORS
     SYNC_ERRORS = bool(flag)
+
+
+def _report_pending_at_exit():
+    try:
+        check_errors()
+    except AssertionError as exc:   # lazy mode only: a failed solve nobody asked about
+        import sys
+        sys.stderr.write("phoenix_b200: a solve hit a solver assertion that was never checked: %s\n" % exc)
+    except Exception:
+        pass
+
+
+import atexit  # noqa: E402
+atexit.register(_report_pending_at_exit)
 
 
 def set_step_logging(flag):
@@ -118,6 +133,22 @@ def net_dims(net):
 _pack_cache = weakref.WeakKeyDictionary()
 
 
+def _on_model_device(fn):
+    """Run an entry point with the model's device current (the caller may sit on another GPU): launches, workspaces
+    and streams all follow torch's current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(net, *args, **kwargs):
+        p0 = net._parameters["gene_multipliers"]
+        if p0.is_cuda and p0.device.index != torch.cuda.current_device():
+            with torch.cuda.device(p0.device):
+                return fn(net, *args, **kwargs)
+        return fn(net, *args, **kwargs)
+    return wrapper
+
+
+@_on_model_device
 def packed_weights(net):
     """Kernel-layout copy of the parameters, rebuilt only when a parameter changed (``_version`` / storage)."""
     params = net_params(net)
@@ -147,9 +178,30 @@ def packed_weights(net):
     return buf, G, H, dev
 
 
+def invalidate(net=None):
+    """Drop the cached kernel-layout copy of `net`'s parameters (all models if None).  The cache is keyed on each
+    parameter's storage pointer and autograd version counter; edits that bypass the counter -- ``p.data.mul_()``,
+    ``torch.distributed.broadcast(p)`` under no_grad, writes through a raw pointer -- must be followed by a call to this
+    function (``parallel.broadcast_parameters`` does it), otherwise the kernels keep integrating the old weights."""
+    if net is None:
+        for k in list(_pack_cache.keys()):
+            del _pack_cache[k]
+    elif net in _pack_cache:
+        del _pack_cache[net]
+    with _state.lock:
+        _last_rhs.clear()
+
+
 # ---- status records -----------------------------------------------------------------------------------------------------
+def _poll_pending():
+    """Lazy mode: raise for any solve that has already finished with a solver assertion (no synchronisation)."""
+    if not SYNC_ERRORS and _tls().pending:
+        check_errors(synchronize=False)
+
+
 def _new_status():
     tls = _tls()
+    _poll_pending()
     if tls.free_status:
         st = tls.free_status.pop()
     else:
@@ -254,6 +306,7 @@ def _rhs_signature(net, packed, y2, B):
             prec)
 
 
+@_on_model_device
 def rhs_forward(net, y, decay):
     packed, G, H, dev = packed_weights(net)
     if y.shape[-1] != G:
@@ -271,6 +324,7 @@ def rhs_forward(net, y, decay):
     return f
 
 
+@_on_model_device
 def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True):
     packed, G, H, dev = packed_weights(net)
     y2 = y.detach().to(torch.float32).contiguous()
@@ -398,6 +452,7 @@ def _adjoint_rows(lib, net, packed, G, H, dev, t_rows, t_is_f32, method, rtol, a
     return adj_y0, split_flat_grads(flat, G, H)
 
 
+@_on_model_device
 def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, max_num_steps):
     packed, G, H, dev = packed_weights(net)
     if y0.shape[-1] != G:
@@ -425,6 +480,7 @@ def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, 
     return yout
 
 
+@_on_model_device
 def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_saved, grad_y):
     packed, G, H, dev = packed_weights(net)
     ys = y_saved.detach().contiguous()
@@ -465,6 +521,7 @@ def _problems_per_launch(T):
 
 def _new_status_block(n):
     """n contiguous pinned status records (one per problem of a multi-problem launch), all marked RUNNING."""
+    _poll_pending()
     words = ctypes.sizeof(_lib.PhxStatus) // 4
     st = torch.empty(n, words, dtype=torch.int32).pin_memory()
     ctypes.memset(st.data_ptr(), 0, n * ctypes.sizeof(_lib.PhxStatus))
@@ -511,6 +568,7 @@ def _fan_in(dev, streams):
         main.wait_event(ev)
 
 
+@_on_model_device
 def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_steps):
     """y0 ``[N, *S, G]``: N independent problems, problem i integrated over its own times ``t_rows[i]`` (all of length
     T).  Every problem is one resident launch with its own step controller -- exactly the reference's per-sample call
@@ -577,6 +635,7 @@ def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_st
     return yout
 
 
+@_on_model_device
 def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps, y_saved, grad_y):
     """Backward sweeps of N independent problems (``y_saved``, ``grad_y``: ``[N, T, *S, G]``): adj_y0 ``[N, *S, G]`` and
     the six parameter cotangents summed over the problems (what autograd accumulates into ``.grad``)."""

@@ -35,8 +35,14 @@ def unflatten_grads_(net, flat):
         o += n
 
 
-def allreduce_grads(net, group=None, average=False, extra=None):
-    """Sum the parameter gradients (and optional extra scalars such as the loss) over all ranks in ONE collective."""
+def allreduce_grads(net, group=None, average=True, extra=None):
+    """Combine the parameter gradients (and optional extra scalars such as the loss) of all ranks in ONE collective.
+
+    ``average=True`` (default) divides the sum by the world size: the reference's losses are ``torch.mean`` over the
+    LOCAL samples (train_insilico.py:132,135), so with the samples of a step sharded over the ranks the averaged gradient
+    is the single-GPU gradient (exactly when the shards are equal, up to the shard-size weighting otherwise) and the
+    learning rate keeps its meaning as N grows.  A caller that normalises its losses by the GLOBAL batch size itself
+    (tools/train_epoch.py) passes ``average=False`` to get the plain sum."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return extra
     flat = flatten_grads(net)
@@ -57,3 +63,4 @@ def broadcast_parameters(net, src=0, group=None):
     with torch.no_grad():
         for p in engine.net_params(net):
             dist.broadcast(p, src=src, group=group)
+    engine.invalidate(net)   # the collective writes the storages without bumping the version counters

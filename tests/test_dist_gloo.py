@@ -29,8 +29,13 @@ def _worker(rank, world, port, out):
     for i, p in enumerate(net.parameters()):            # fake per-rank gradients: (i+1) * number of local samples
         p.grad = torch.full_like(p, float((i + 1) * (hi - lo)))
     loss = torch.tensor([float(hi - lo)])
-    total = parallel.allreduce_grads(net, extra=loss)
+    total = parallel.allreduce_grads(net, extra=loss, average=False)
     ok = all(torch.allclose(p.grad, torch.full_like(p, float((i + 1) * 5))) for i, p in enumerate(net.parameters()))
+    # default: the average over the ranks (the reference's losses are means over the LOCAL samples)
+    for i, p in enumerate(net.parameters()):
+        p.grad = torch.full_like(p, float((i + 1) * (rank + 1)))
+    parallel.allreduce_grads(net)
+    ok = ok and all(torch.allclose(p.grad, torch.full_like(p, float((i + 1) * 1.5))) for i, p in enumerate(net.parameters()))
     w0 = net.net_sums.linear_out.weight.detach().clone()
     gathered = [torch.zeros_like(w0) for _ in range(world)]
     dist.all_gather(gathered, w0)

@@ -67,6 +67,8 @@ def main():
     quick = len(sys.argv) > 1 and sys.argv[1] == "quick"
     case(37, 5, 1, "euler", 0.7, 1)
     case(37, 5, 3, "rk4", 0.7, 2)
+    case(37, 5, 3, "euler", 0.4, 21, T=3)
+    case(129, 33, 2, "midpoint", 0.3, 22, T=3)
     case(129, 33, 5, "rk4", 0.3, 3, T=3)
     case(129, 33, 2, "midpoint", 0.3, 4)
     case(37, 5, 2, "dopri5", 0.7, 5)

@@ -59,7 +59,7 @@ def main():
                 (y[1] ** 2).mean().backward()
                 nb = pb.last_status()["n_rhs"]
                 if world > 1:
-                    parallel.allreduce_grads(net)
+                    parallel.allreduce_grads(net, average=False)
                 return nf + nb
             run()
             torch.cuda.synchronize()

@@ -32,19 +32,14 @@ CONFIGS = {
 }
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--config", default="breast", choices=sorted(CONFIGS))
-    ap.add_argument("--epochs", type=int, default=3)
-    ap.add_argument("--many", action="store_true", help="sample loop inside the library (odeint_adjoint_many)")
-    a = ap.parse_args()
+def run_epochs(config, epochs=3, many=True, instrument=True):
+    """Time `epochs` epochs of the reference's training loop on this rank's share (call under torchrun for N > 1; the
+    process group must already exist).  Returns the dict that main() prints (rank 0) or None."""
     import torch.distributed as dist
-    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
     dev = torch.device("cuda", torch.cuda.current_device())
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    G, H, batch, steps, dt, method, lam, K, pscale = CONFIGS[a.config]
+    G, H, batch, steps, dt, method, lam, K, pscale = CONFIGS[config]
     torch.manual_seed(0)
     odenet = pb.ODENet(dev, G, neurons=H)
     parallel.broadcast_parameters(odenet)
@@ -71,13 +66,16 @@ def main():
         t0 = time.perf_counter()
         opt.zero_grad()
         b, t, tg = data[i], tt[i], target[i]
-        if a.many:
+        if b.shape[0] == 0:
+            loss_data = torch.zeros((), device=dev)
+        elif many:
             predictions = pb.odeint_adjoint_many(odenet, b, t, method=method)[:, 1]
+            loss_data = torch.sum((predictions - tg) ** 2) / (batch * G)
         else:
             predictions = torch.zeros(b.shape, device=dev)
             for index, (time_, batch_point) in enumerate(zip(t, b)):
                 predictions[index, :, :] = pb.odeint_adjoint(odenet, batch_point, time_, method=method)[1]
-        loss_data = torch.sum((predictions - tg) ** 2) / (batch * G)
+            loss_data = torch.sum((predictions - tg) ** 2) / (batch * G)
         if timed:
             torch.cuda.synchronize(); t1 = time.perf_counter()
         pred_grad = odenet.prior_only_forward(t, batch_for_prior)
@@ -87,7 +85,7 @@ def main():
             torch.cuda.synchronize(); t2 = time.perf_counter()
         composed_loss.backward()
         if world > 1:
-            parallel.allreduce_grads(odenet)
+            parallel.allreduce_grads(odenet, average=False)   # losses are normalised by the GLOBAL batch / K above
         opt.step()
         if timed:
             torch.cuda.synchronize(); t3 = time.perf_counter()
@@ -98,31 +96,50 @@ def main():
         training_step(i, False)
     torch.cuda.synchronize()
     times = []
-    for ep in range(a.epochs):
+    for ep in range(epochs):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         for i in range(steps):
-            ld, lp = training_step(i, ep == a.epochs - 1 and False)
+            ld, lp = training_step(i, False)
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
-    for i in range(steps):          # one more, instrumented epoch for the phase split (synchronises between phases)
-        training_step(i, True)
+    if instrument:
+        for i in range(steps):      # one more, instrumented epoch for the phase split (synchronises between phases)
+            training_step(i, True)
     pb.check_errors()
     best = min(times)
     if world > 1:
         tbest = torch.tensor([best], dtype=torch.float64, device=dev)
         dist.all_reduce(tbest, op=dist.ReduceOp.MAX)
         best = float(tbest)
-    if rank == 0:
-        tot = sum(ph.values())
-        print(json.dumps({"metric": "train epoch time", "config": a.config, "genes": G, "neurons": H, "n_gpus": world,
-                          "batch_size": batch, "steps_per_epoch": steps, "method": method, "prior_rows": K,
-                          "sample_loop": "odeint_adjoint_many" if a.many else "per-sample odeint_adjoint",
-                          "epoch_s": best, "ms_per_step": 1e3 * best / steps,
-                          "phase_share": {k: v / tot for k, v in ph.items()},
-                          "loss_data": float(ld), "loss_prior": float(lp)}), flush=True)
+    if rank != 0:
+        return None
+    tot = sum(ph.values()) or 1.0
+    return {"metric": "train epoch time", "config": config, "genes": G, "neurons": H, "n_gpus": world,
+            "batch_size": batch, "steps_per_epoch": steps, "method": method, "prior_rows": K,
+            "sample_loop": "odeint_adjoint_many" if many else "per-sample odeint_adjoint",
+            "epoch_s": best, "ms_per_step": 1e3 * best / steps,
+            "phase_share": {k: v / tot for k, v in ph.items()} if instrument else None,
+            "loss_data": float(ld), "loss_prior": float(lp)}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", default="breast", choices=sorted(CONFIGS))
+    ap.add_argument("--epochs", type=int, default=3)
+    ap.add_argument("--many", action="store_true", help="sample loop inside the library (odeint_adjoint_many)")
+    a = ap.parse_args()
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    out = run_epochs(a.config, a.epochs, a.many)
+    if out is not None:
+        print(json.dumps(out), flush=True)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
