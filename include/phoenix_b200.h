@@ -96,6 +96,11 @@ int phx_tc_min_rows(void);
  * cotangents) and M rows is split over CTAs.  out = {128-row tiles, K-splits of the prods half, k-blocks per split,
  * K-splits of the sums half, k-blocks per split, partial-sum slots}; a k-block is 16 k-elements. */
 int phx_tc_plan_describe(int K, int M, int32_t out[6]);
+/* Diagnostics (no reference counterpart).  phx_tc_set_pair(1): run the branch-type tensor-core contractions as CTA pairs
+ * (tcgen05 cta_group::2) -- bit-identical results, measured slower on B200, off by default (tests compare the two).
+ * phx_tc_prof_dump: print and reset the device counters collected when the process runs with PHX_TC_PROF=1. */
+void phx_tc_set_pair(int on);
+void phx_tc_prof_dump(void);
 
 /* ---- weights --------------------------------------------------------------------------------------------- */
 /* Bytes of the packed (kernel-layout) copy of the six parameters for an ODENet(ndim=G, neurons=H). */
@@ -122,6 +127,19 @@ int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const fl
                 float* ybar, float* grads_flat, int accumulate, void* workspace, size_t workspace_bytes,
                 void* stream);
 size_t phx_rhs_workspace_bytes(int G, int H, int B);
+
+/* ---- prior-constrained loss term of training_step (train_insilico.py:134-137, 208-209) -------------------------------- */
+/* loss[0] = mean((prior_only_forward(x) - prior_grad)^2) over the B rows (device scalar) and
+ * gcot[B][G] = scale * (prior_only_forward(x) - prior_grad) -- with scale = 2 / (B * G) the cotangent of that mean --
+ * in one fused pass (B >= phx_tc_min_rows(): the joint contraction's epilogue compares with prior_grad, the joint itself
+ * never goes to memory).  `workspace` is an RHS workspace (phx_rhs_workspace_bytes); it is left holding [S|P] of x, so the
+ * backward is  phx_rhs_vjp(ctx, G, H, B, packed, x, gcot, 0, NULL, grads_flat, PHX_VJP_REUSE_FORWARD, workspace, ...). */
+int phx_prior_loss(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* x, const float* prior_grad,
+                   float scale, float* gcot, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* prior_grad[B][G] = x[B][G] @ prior_mat[G][G] (train_insilico.py:209) for a sparse prior in CSC form (column j of
+ * prior_mat = rows rowidx[colptr[j] .. colptr[j+1]) with values val[...]; all device pointers). */
+int phx_prior_setup(phx_ctx* ctx, int G, int B, const float* x, const int32_t* colptr, const int32_t* rowidx,
+                    const float* val, float* out, void* stream);
 
 /* ---- odeint (torchdiffeq/_impl/odeint.py:25-69) ---------------------------------------------------------- */
 size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint);

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 
 # (object name, source, extra defines)
 UNITS = [("phx_api", "phx_api.cu", []), ("phx_plan", "phx_plan.cu", []), ("phx_rhs", "phx_rhs.cu", []),
-         ("phx_stream", "phx_stream.cu", []), ("phx_microbench", "phx_microbench.cu", []), ("phx_tc", "phx_tc.cu", [])]
+         ("phx_stream", "phx_stream.cu", []), ("phx_tc", "phx_tc.cu", [])]
 for kind in (0, 1):
     UNITS.append(("phx_rows_%s" % ("adj" if kind else "fwd"), "phx_rows_inst.cu", ["-DPHX_KIND_ADJ=%d" % kind]))
     for nv in (1, 2, 4):

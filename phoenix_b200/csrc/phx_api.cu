@@ -276,6 +276,27 @@ int phx_rhs_vjp(phx_ctx* ctx, int G, int H, int B, const float* packed, const fl
                               (cudaStream_t)stream);
 }
 
+int phx_prior_loss(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* x, const float* prior_grad,
+                   float scale, float* gcot, float* loss, void* workspace, size_t workspace_bytes, void* stream) {
+    PhxDevGuard dev_guard(ctx);
+    if (!ctx || !check_dims(G, H, B) || !packed || !x || !prior_grad || !gcot || !loss || !workspace) return PHX_ERR_INVALID;
+    if (workspace_bytes < phx_rhs_workspace_bytes(G, H, B)) {
+        phx_set_error("rhs workspace too small: %zu < %zu", workspace_bytes, phx_rhs_workspace_bytes(G, H, B));
+        return PHX_ERR_WORKSPACE;
+    }
+    PhxPacked w;
+    int rc = phx_tc_prepare(ctx, G, H, B, packed, &w, (cudaStream_t)stream);
+    if (rc != PHX_OK) return rc;
+    return phx_prior_loss_launch(G, H, B, w, x, prior_grad, scale, gcot, loss, (float*)workspace, (cudaStream_t)stream);
+}
+
+int phx_prior_setup(phx_ctx* ctx, int G, int B, const float* x, const int32_t* colptr, const int32_t* rowidx,
+                    const float* val, float* out, void* stream) {
+    PhxDevGuard dev_guard(ctx);
+    if (!ctx || G < 1 || B < 1 || !x || !colptr || !rowidx || !val || !out) return PHX_ERR_INVALID;
+    return phx_prior_setup_launch(G, B, x, colptr, rowidx, val, out, (cudaStream_t)stream);
+}
+
 size_t phx_solve_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint) {
     if (!ctx) return 0;
     ResLaunchPlan plan;

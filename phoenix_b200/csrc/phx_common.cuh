@@ -339,6 +339,10 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
                        float* ybar, float* grads_flat, int accumulate, float* f_out, float fscale, float* ws,
                        cudaStream_t stream);
 size_t phx_rhs_workspace_floats(int G, int H, int B);
+int phx_prior_loss_launch(int G, int H, int B, const PhxPacked& w, const float* x, const float* prior_grad, float scale,
+                          float* gcot, float* loss, float* ws, cudaStream_t stream);
+int phx_prior_setup_launch(int G, int B, const float* x, const int* colptr, const int* rowidx, const float* val,
+                           float* out, cudaStream_t stream);
 
 // tensor-core path (phx_tc.cu).  phx_tc_prepare (phx_api.cu) decides per call whether the contractions of a B-row call
 // run on tcgen05 (ctx precision, shape), (re)builds the operand images in the tail of `packed` if phx_pack_weights has
@@ -354,6 +358,8 @@ int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float
                             float* ybar, const float* SP, float* GS, float* J, float* tcws, cudaStream_t stream);
 int phx_tc_joint_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
                         float* tcws, cudaStream_t stream);
+int phx_tc_prior_loss_launch(int G, int H, int B, const PhxPacked& w, const float* x, const float* prior_grad, float scale,
+                             float* gcot, float* loss, float* SP, double* part, float* tcws, cudaStream_t stream);
 int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
                              float* grads_flat, int accumulate, float* tcws, cudaStream_t stream);
 

@@ -262,7 +262,9 @@ __global__ void colsum_mult_kernel(const float* g, const float* f_nodecay, const
 
 static size_t rhs_base_floats(int G, int H, int B) {
     size_t K2 = (size_t)phx_K2(H);
-    return 2 * (size_t)B * K2 + (size_t)B * G + 16;
+    // SP, GS, J (+ 16, rounded to an even count), then 2 * 8 * 160 floats = the per-warp double partial sums of the fused
+    // prior loss
+    return ((2 * (size_t)B * K2 + (size_t)B * G + 16 + 1) & ~(size_t)1) + 2 * 8 * 160;
 }
 size_t phx_rhs_workspace_floats(int G, int H, int B) {
     size_t K2 = (size_t)phx_K2(H);
@@ -401,6 +403,91 @@ int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         phx_set_error("rhs_vjp launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+
+// ---- prior-constrained loss (train_insilico.py:134-135, 208-209) ---------------------------------------------------------
+namespace {
+// fallback for batches below the tensor-core threshold / fp32 precision: J is materialised, then one elementwise pass
+__global__ void prior_loss_elem_kernel(const float* __restrict__ J, const float* __restrict__ pg, size_t n, float scale,
+                                       float* __restrict__ gcot, double* __restrict__ part) {
+    double sq = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        const float d = J[i] - pg[i];
+        sq += (double)(d * d);
+        gcot[i] = scale * d;
+    }
+    __shared__ double red[256];
+    red[threadIdx.x] = sq;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) part[blockIdx.x] = red[0];
+}
+__global__ void prior_loss_sum_kernel(const double* __restrict__ part, int n, double inv_n, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += part[i];
+        *loss = (float)(t * inv_n);
+    }
+}
+// prior_grad = batch_for_prior @ prior_mat (train_insilico.py:209) with the 0.5-3 % dense prior in CSC form: one CTA per
+// batch row (staged in shared memory), one thread per output gene walking that gene's column of the prior.
+__global__ void prior_setup_kernel(int G, const float* __restrict__ x, const int* __restrict__ colptr,
+                                   const int* __restrict__ rowidx, const float* __restrict__ val, float* __restrict__ out) {
+    extern __shared__ float xrow[];
+    const size_t b = blockIdx.x;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) xrow[i] = x[b * G + i];
+    __syncthreads();
+    for (int j = threadIdx.x; j < G; j += blockDim.x) {
+        float t = 0.f;
+        for (int e = colptr[j]; e < colptr[j + 1]; ++e) t = fmaf(xrow[rowidx[e]], val[e], t);
+        out[b * G + j] = t;
+    }
+}
+}  // namespace
+
+int phx_prior_loss_launch(int G, int H, int B, const PhxPacked& w, const float* x, const float* prior_grad, float scale,
+                          float* gcot, float* loss, float* ws, cudaStream_t st) {
+    const int K2 = phx_K2(H);
+    float* SP = ws;
+    float* J = ws + 2 * (size_t)B * K2;
+    double* part = reinterpret_cast<double*>(ws + rhs_base_floats(G, H, B) - 2 * 8 * 160);
+    if (w.tc && phx_tc_shape_ok(H, B))
+        return phx_tc_prior_loss_launch(G, H, B, w, x, prior_grad, scale, gcot, loss, SP, part,
+                                        ws + rhs_base_floats(G, H, B), st);
+    int rc = phx_rhs_forward_launch(G, H, B, w, x, J, 0, 1.f, ws, st);
+    if (rc != PHX_OK) return rc;
+    const size_t n = (size_t)B * G;
+    const int blocks = (int)((n + 255) / 256 < 1024 ? (n + 255) / 256 : 1024);
+    prior_loss_elem_kernel<<<blocks, 256, 0, st>>>(J, prior_grad, n, scale, gcot, part);
+    prior_loss_sum_kernel<<<1, 32, 0, st>>>(part, blocks, 1.0 / (double)n, loss);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("prior_loss launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
+
+int phx_prior_setup_launch(int G, int B, const float* x, const int* colptr, const int* rowidx, const float* val,
+                           float* out, cudaStream_t st) {
+    const size_t smem = (size_t)G * sizeof(float);
+    if (smem > 200 * 1024) {
+        phx_set_error("prior_setup supports up to 51200 genes (got %d)", G);
+        return PHX_ERR_UNSUPPORTED;
+    }
+    cudaFuncSetAttribute(prior_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prior_setup_kernel<<<B, 512, smem, st>>>(G, x, colptr, rowidx, val, out);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("prior_setup launch: %s", cudaGetErrorString(e));
         return PHX_ERR_CUDA;
     }
     return PHX_OK;

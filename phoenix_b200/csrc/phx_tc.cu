@@ -783,6 +783,8 @@ struct JointParams {
     int emode;            // epilogue: 0 f = fscale*(decay ? relu(m)*(acc - y) : acc); 1 f = acc; 2 state cotangent:
                           //   f = (f + acc/(1+s(y))) / (1+|y-.5|)^2 - (decay ? g*relu(m) : 0)   (f holds u on entry);
                           // 3 the same with u and v accumulated side by side (k-blocks below / above the middle)
+                          // 4 prior loss (train_insilico.py:134-135): f = fscale * (acc - g) with g = prior_grad, and the
+                          //   sum of (acc - g)^2 per epilogue warp -> part (the joint itself is never written)
     float fscale;
     const float* waimg;   // A image: [GT][KB2][hi|lo][128 x 16]
     const float* spimg;   // B image: [BT][KB2][hi|lo][256 x 16]
@@ -790,6 +792,7 @@ struct JointParams {
     const float* g;       // [B][G] cotangent (emode 2 with decay)
     const float* relum;   // [G]
     float* f;             // [B][G]
+    double* part;         // emode 4: [gridDim.x][8] per-epilogue-warp sums of (acc - g)^2
 };
 constexpr int K2_THREADS = 320;   // bulk-copy issuer, MMA issuer, 8 epilogue warps
 constexpr int K2_STAGES = 4;
@@ -889,6 +892,7 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
         // the next 16 columns are always in flight while the current 16 are combined and stored.
         const int q = warp & 3, half = (warp - 2) >> 2;
         int j = 0;
+        double sq = 0.0;   // EMODE 4
         for (int t = blockIdx.x; t < ntiles; t += gridDim.x, ++j) {
             const int gt = t / p.BT, bt = t % p.BT;
             const int buf = EMODE == 3 ? 0 : (j & 1);
@@ -898,9 +902,9 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             const float rm = (gok && p.decay) ? p.relum[g] : 1.f;
             const int b0 = bt * 256 + half * 128;
             const int ncol = min(128, p.B - b0);   // valid batch rows of this warp's half (may be <= 0)
-            const bool need_y = EMODE >= 2 || (EMODE == 0 && p.decay);
+            const bool need_y = (EMODE >= 2 && EMODE != 4) || (EMODE == 0 && p.decay);
             constexpr bool need_u = EMODE == 2;
-            const bool need_g = EMODE >= 2 && p.decay;
+            const bool need_g = EMODE == 4 || (EMODE >= 2 && p.decay);
             float yv[16], yn[16], uv[16], un[16], gv[16], gn[16];
             auto loadin = [&](int c0, float (&dy)[16], float (&du)[16], float (&dg)[16]) {
 #pragma unroll
@@ -938,6 +942,10 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
                             r = p.fscale * (p.decay ? rm * (v[jj] - yv[jj]) : v[jj]);
                         } else if (EMODE == 1) {
                             r = v[jj];
+                        } else if (EMODE == 4) {
+                            const float d = v[jj] - gv[jj];
+                            sq += (double)(d * d);
+                            r = p.fscale * d;
                         } else {
                             const float z = yv[jj] - 0.5f;
                             const float den = 1.0f + fabsf(z);
@@ -953,10 +961,24 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty0 + 8 * buf);
         }
+        if (EMODE == 4) {   // fixed-order butterfly over the lanes, one slot per (CTA, epilogue warp)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+            if (lane == 0) p.part[blockIdx.x * 8 + (warp - 2)] = sq;
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_free512(tmem);
+}
+
+// loss = (sum of the per-warp partial sums, fixed order) * inv_n
+__global__ void prior_loss_finish_kernel(const double* __restrict__ part, int n, double inv_n, float* __restrict__ loss) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < n; ++i) t += part[i];
+        *loss = (float)(t * inv_n);
+    }
 }
 
 // PHX_TC_PROF=1: 16 device counters, printed (and reset) by phx_tc_prof_dump()
@@ -1047,6 +1069,7 @@ void set_attrs() {
     cudaFuncSetAttribute(tc_branch_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_joint_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     done = true;
@@ -1156,15 +1179,15 @@ int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, c
 }
 
 // out^T tiles = Aimg[genes x k-blocks kb_lo..kb_hi) x Bimg[batch rows]^T with the epilogue `emode`
-void launch_joint(int G, int H, int B, int nterms, const float* aimg, const float* bimg, int kb_lo, int kb_hi, int emode,
-                  int decay, float fscale, const float* y, const float* g, const float* relum, float* out,
-                  cudaStream_t st) {
+int launch_joint(int G, int H, int B, int nterms, const float* aimg, const float* bimg, int kb_lo, int kb_hi, int emode,
+                 int decay, float fscale, const float* y, const float* g, const float* relum, float* out,
+                 cudaStream_t st, double* part = nullptr) {
     JointParams jp;
     jp.G = G; jp.B = B; jp.KB2 = phx_tc_KB2(H); jp.GT = phx_tc_GT(G); jp.BT = phx_tc_BT(B); jp.nterms = nterms;
     jp.decay = decay; jp.fscale = fscale; jp.kb_lo = kb_lo; jp.kb_hi = kb_hi; jp.emode = emode;
     jp.a_lbo = 16 * 128; jp.a_sbo = 128; jp.b_lbo = 32 * 128; jp.b_sbo = 128;
     jp.a_kadv = 2 * jp.a_lbo; jp.b_kadv = 2 * jp.b_lbo;
-    jp.waimg = aimg; jp.spimg = bimg; jp.y = y; jp.g = g; jp.relum = relum; jp.f = out;
+    jp.waimg = aimg; jp.spimg = bimg; jp.y = y; jp.g = g; jp.relum = relum; jp.f = out; jp.part = part;
     const int ntiles = jp.GT * jp.BT;
     const int grid = ntiles < PHX_TC_SMS ? ntiles : PHX_TC_SMS;
     set_attrs();
@@ -1172,7 +1195,9 @@ void launch_joint(int G, int H, int B, int nterms, const float* aimg, const floa
     if (emode == 0) tc_joint_kernel<0><<<grid, K2_THREADS, smem2, st>>>(jp);
     else if (emode == 1) tc_joint_kernel<1><<<grid, K2_THREADS, smem2, st>>>(jp);
     else if (emode == 2) tc_joint_kernel<2><<<grid, K2_THREADS, smem2, st>>>(jp);
-    else tc_joint_kernel<3><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else if (emode == 3) tc_joint_kernel<3><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else tc_joint_kernel<4><<<grid, K2_THREADS, smem2, st>>>(jp);
+    return grid;
 }
 
 int check_launch(const char* what) {
@@ -1249,6 +1274,23 @@ int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const floa
     tc_gradfinish_kernel<<<blocks, 256, 0, st>>>(0, G, phx_round_up(pl.mtiles, 2) * 128, H, Hn, pl.ks_s, pl.ks_p, sc.gslots,
                                                  grads + off.Ws, grads + off.Wp, accumulate);
     return check_launch("tc vjp_params");
+}
+
+// Prior-constrained loss term of training_step (train_insilico.py:134-135) on the tensor cores, fused: [S|P] from x, then
+// the joint contraction whose epilogue compares with prior_grad on the fly -- gcot = scale * (J - prior_grad) is the
+// cotangent the backward needs, loss = mean((J - prior_grad)^2); J itself never goes to memory.  The scratch keeps
+// [S|P] and its images for the parameter contractions of the backward (phx_rhs_vjp with PHX_VJP_REUSE_FORWARD).
+// part: >= 8 * PHX_TC_SMS doubles.
+int phx_tc_prior_loss_launch(int G, int H, int B, const PhxPacked& w, const float* x, const float* prior_grad, float scale,
+                             float* gcot, float* loss, float* SP, double* part, float* tcws, cudaStream_t st) {
+    const TcScratch sc = carve(G, H, B, tcws);
+    const int nterms = (w.tc == 1) ? 1 : 3;
+    int rc = launch_branch(0, G, H, B, nterms, x, nullptr, w.w1img, w.bias, SP, sc.spimg, sc.sptimg, sc.spart, st);
+    if (rc != PHX_OK) return rc;
+    const int grid = launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 4, 0, scale, nullptr, prior_grad,
+                                  w.relum, gcot, st, part);
+    prior_loss_finish_kernel<<<1, 32, 0, st>>>(part, grid * 8, 1.0 / ((double)B * (double)G), loss);
+    return check_launch("tc prior_loss");
 }
 
 extern "C" void phx_tc_set_pair(int on) { g_pair = on ? 1 : 0; }

@@ -39,5 +39,29 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert lib.phx_rhs_workspace_bytes(G, H, 7) >= 4 * (2 * 7 * 80 + 7 * G)
 
 
+def test_library_exports_nothing_the_header_does_not_declare():
+    """Every extern "C" phx_* symbol of the product library is part of the documented boundary (diagnostics included)."""
+    import shutil
+    import subprocess
+    if not shutil.which("nm"):
+        return
+    out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    exported = sorted(line.split()[-1] for line in out.splitlines()
+                      if " T " in line and line.split()[-1].startswith("phx_"))
+    assert exported == declared_symbols()
+
+
+def test_rows_plans_for_the_baseline_shapes():
+    """Host-only planning of the rows kernels: all BASELINE training shapes take 4 samples per pass; the genome-scale
+    model parks its WA slice in tensor memory; the 20 000-gene sweep shape does not fit on chip (streaming engine)."""
+    lib = _lib.load()
+    out = (ctypes.c_int32 * 10)()
+    for G, H, wa in ((350, 40, 1), (690, 40, 1), (3551, 120, 1), (11165, 40, 1), (11165, 200, 2)):
+        for adj in (0, 1):
+            assert lib.phx_rows_plan_describe(148, G, H, adj, out) == 0, (G, H, adj, _lib.last_error())
+            assert out[6] == 4 and out[5] == wa and out[9] <= 227 * 1024 and out[8] <= 512
+    assert lib.phx_rows_plan_describe(148, 20000, 200, 1, out) != 0
+
+
 def test_status_struct_matches_header():
     assert ctypes.sizeof(_lib.PhxStatus) == 40

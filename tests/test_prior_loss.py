@@ -1,0 +1,95 @@
+"""The prior-constrained loss path (train_insilico.py:64-68, 134-138, 208-209) against a golden produced by
+the unmodified reference on the SHIPPED prior matrix edge_prior_matrix_G690_noise_0.0.csv (tests/golden/
+make_golden_prior.py).  CPU: the oracle restatement; GPU: the sparse set-up product and the fused loss + backward.
+Tolerance: relative L2 <= 1e-5 (fp32; 3xTF32 contractions)."""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import load, rel_l2
+from oracle import phoenix_oracle as O
+
+
+def _golden():
+    d = load("prior_g690_h40_k256")
+    G, H = int(d["G"]), int(d["H"])
+    w = O.make_weights(G, H, int(d["seed"]), dense=False)
+    prior = torch.zeros(G, G)
+    prior[torch.from_numpy(d["prior_rows"]).long(), torch.from_numpy(d["prior_cols"]).long()] = torch.from_numpy(d["prior_vals"])
+    return d, w, prior
+
+
+def test_oracle_prior_loss_matches_reference():
+    d, w, prior = _golden()
+    x = torch.from_numpy(d["batch_for_prior"])
+    pg = torch.matmul(x, prior)
+    assert torch.equal(pg, torch.from_numpy(d["prior_grad"]))      # same ATen matmul as the reference
+    J = O.rhs(w, x, decay=False)
+    loss = torch.mean((J - pg) ** 2)
+    assert abs(float(loss) - float(d["loss_prior"])) <= 1e-6 * float(d["loss_prior"])
+    _, _, pbar = O.rhs_vjp(w, x, 2.0 * (J - pg) / J.numel(), decay=False)
+    for i, g in enumerate(pbar):
+        ref = d["grad%d" % i]
+        if not ref.any():
+            assert not g.any()
+        else:
+            assert rel_l2(g, ref) < 2e-6, (i, rel_l2(g, ref))
+
+
+@pytest.mark.gpu
+def test_prior_setup_and_fused_loss_match_reference():
+    import phoenix_b200 as pb
+    d, w, prior = _golden()
+    net = pb.ODENet("cuda", w.G, neurons=w.H)
+    with torch.no_grad():
+        for p, src in zip(net.parameters(), w.as_list()):
+            p.copy_(src)
+    x = torch.from_numpy(d["batch_for_prior"]).cuda()
+    # set-up product: dense and sparse inputs, CPU or CUDA prior matrix
+    for pm in (prior, prior.cuda(), prior.to_sparse()):
+        pg = pb.prior_grad_from_matrix(x, pm)
+        assert pg.shape == x.shape and rel_l2(pg.cpu(), d["prior_grad"]) < 1e-6
+    # fused loss + backward
+    net.zero_grad()
+    loss = pb.prior_loss(net, x, pg)
+    (0.01 * loss).backward()          # the (1 - lambda) weight of composed_loss, train_insilico.py:137
+    assert abs(float(loss) - float(d["loss_prior"])) <= 1e-5 * float(d["loss_prior"])
+    for i, p in enumerate(net.parameters()):
+        ref = d["grad%d" % i]
+        if not ref.any():
+            assert p.grad is None or not p.grad.any()
+        else:
+            assert rel_l2(p.grad.cpu(), 0.01 * ref) < 1e-5, (i, rel_l2(p.grad.cpu(), 0.01 * ref))
+    # the reference's two unfused lines on the same inputs give the same thing
+    net.zero_grad()
+    loss2 = torch.mean((net.prior_only_forward(None, x) - pg) ** 2)
+    (0.01 * loss2).backward()
+    assert abs(float(loss2) - float(loss)) <= 1e-5 * float(loss)
+    for i, p in enumerate(net.parameters()):
+        if d["grad%d" % i].any():
+            assert rel_l2(p.grad.cpu(), 0.01 * d["grad%d" % i]) < 1e-5
+
+
+@pytest.mark.gpu
+def test_fused_prior_loss_small_batch_and_large_shape():
+    """Below the tensor-core threshold (B = 3: fp32 path) and at the breast shape with 1 024 rows."""
+    import phoenix_b200 as pb
+    for G, H, K in ((97, 12, 3), (11165, 200, 1024)):
+        w = O.make_weights(G, H, 6100 + K, dense=False)
+        net = pb.ODENet("cuda", G, neurons=H)
+        with torch.no_grad():
+            for p, src in zip(net.parameters(), w.as_list()):
+                p.copy_(src)
+        gen = torch.Generator().manual_seed(K)
+        x = torch.rand(K, 1, G, generator=gen) - 0.5
+        pg = torch.randn(K, 1, G, generator=gen) * 0.1
+        loss = pb.prior_loss(net, x.cuda(), pg.cuda())
+        loss.backward()
+        J = O.rhs(w, x, decay=False)
+        _, _, pbar = O.rhs_vjp(w, x, 2.0 * (J - pg) / J.numel(), decay=False)
+        assert abs(float(loss) - float(torch.mean((J - pg) ** 2))) <= 1e-5 * float(loss)
+        for i, (p, ref) in enumerate(zip(net.parameters(), pbar)):
+            if i == 0:
+                assert p.grad is None or not p.grad.any()
+            else:
+                assert rel_l2(p.grad.cpu(), ref) < 2e-5, (G, i, rel_l2(p.grad.cpu(), ref))

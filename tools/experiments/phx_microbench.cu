@@ -1,5 +1,5 @@
 // Micro-benchmarks of the building blocks of the resident kernels (diagnostics only; tools/microbench.py).
-#include "phx_resident.cuh"
+#include "../../phoenix_b200/csrc/phx_resident.cuh"
 
 namespace {
 

@@ -12,7 +12,12 @@ from phoenix_b200 import _lib, engine  # noqa: E402
 
 
 def main():
-    lib = ctypes.CDLL(_lib.LIB_PATH)
+    mb = os.path.join(os.path.dirname(os.path.abspath(__file__)), "experiments", "libphx_microbench.so")
+    if not os.path.exists(mb):   # diagnostics live outside the product library
+        import subprocess
+        subprocess.check_call([os.path.join(os.path.dirname(mb), "build_microbench.sh")])
+    ctypes.CDLL(_lib.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(mb)
     _lib.load()
     ctx = _lib.ctx(0)
     fn = lib.phx_microbench

@@ -11,7 +11,12 @@ from phoenix_b200 import _lib  # noqa: E402
 
 
 def main():
-    lib = ctypes.CDLL(_lib.LIB_PATH)
+    mb = os.path.join(os.path.dirname(os.path.abspath(__file__)), "experiments", "libphx_microbench.so")
+    if not os.path.exists(mb):   # diagnostics live outside the product library
+        import subprocess
+        subprocess.check_call([os.path.join(os.path.dirname(mb), "build_microbench.sh")])
+    ctypes.CDLL(_lib.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(mb)
     fn = lib.phx_microbench_sync
     fn.argtypes = [ctypes.c_int] * 4 + [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
     fn.restype = ctypes.c_int

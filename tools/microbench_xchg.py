@@ -1,4 +1,4 @@
-"""Where the cycles of the two-phase all-reduce go (instrumented copy in csrc/phx_microbench.cu)."""
+"""Where the cycles of the two-phase all-reduce go (instrumented copy in tools/experiments/phx_microbench.cu)."""
 import ctypes
 import os
 import sys
@@ -11,7 +11,12 @@ from phoenix_b200 import _lib  # noqa: E402
 
 
 def main():
-    lib = ctypes.CDLL(_lib.LIB_PATH)
+    mb = os.path.join(os.path.dirname(os.path.abspath(__file__)), "experiments", "libphx_microbench.so")
+    if not os.path.exists(mb):   # diagnostics live outside the product library
+        import subprocess
+        subprocess.check_call([os.path.join(os.path.dirname(mb), "build_microbench.sh")])
+    ctypes.CDLL(_lib.LIB_PATH, mode=ctypes.RTLD_GLOBAL)
+    lib = ctypes.CDLL(mb)
     L = _lib.load()
     ctx = _lib.ctx(0)
     fn = lib.phx_microbench_xchg

@@ -32,7 +32,7 @@ CONFIGS = {
 }
 
 
-def run_epochs(config, epochs=3, many=True, instrument=True):
+def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True):
     """Time `epochs` epochs of the reference's training loop on this rank's share (call under torchrun for N > 1; the
     process group must already exist).  Returns the dict that main() prints (rank 0) or None."""
     import torch.distributed as dist
@@ -54,7 +54,7 @@ def run_epochs(config, epochs=3, many=True, instrument=True):
     # prior: sparse +-0.5 matrix at 3 % density; prior_grad = batch_for_prior @ prior_mat once at start-up
     prior_mat = (torch.rand(G, G, device=dev, generator=gen) < 0.03).float() * 0.5
     batch_for_prior = (torch.rand(khi - klo, 1, G, device=dev, generator=gen) - 0.5) * pscale
-    prior_grad = torch.matmul(batch_for_prior, prior_mat)
+    prior_grad = pb.prior_grad_from_matrix(batch_for_prior, prior_mat)   # sparse product (train_insilico.py:209)
     del prior_mat
     data = torch.rand(steps, hi - lo, 1, G, device=dev, generator=gen)
     target = torch.rand(steps, hi - lo, 1, G, device=dev, generator=gen)
@@ -78,8 +78,11 @@ def run_epochs(config, epochs=3, many=True, instrument=True):
             loss_data = torch.sum((predictions - tg) ** 2) / (batch * G)
         if timed:
             torch.cuda.synchronize(); t1 = time.perf_counter()
-        pred_grad = odenet.prior_only_forward(t, batch_for_prior)
-        loss_prior = torch.sum((pred_grad - prior_grad) ** 2) / (K * G)
+        if fused_prior:   # the two lines of train_insilico.py:134-135 as one fused operation (phoenix_b200.prior_loss)
+            loss_prior = pb.prior_loss(odenet, batch_for_prior, prior_grad) * ((khi - klo) / K)
+        else:
+            pred_grad = odenet.prior_only_forward(t, batch_for_prior)
+            loss_prior = torch.sum((pred_grad - prior_grad) ** 2) / (K * G)
         composed_loss = lam * loss_data + (1 - lam) * loss_prior
         if timed:
             torch.cuda.synchronize(); t2 = time.perf_counter()
@@ -120,6 +123,7 @@ def run_epochs(config, epochs=3, many=True, instrument=True):
     return {"metric": "train epoch time", "config": config, "genes": G, "neurons": H, "n_gpus": world,
             "batch_size": batch, "steps_per_epoch": steps, "method": method, "prior_rows": K,
             "sample_loop": "odeint_adjoint_many" if many else "per-sample odeint_adjoint",
+            "prior_term": "phoenix_b200.prior_loss (fused)" if fused_prior else "prior_only_forward + torch ops",
             "epoch_s": best, "ms_per_step": 1e3 * best / steps,
             "phase_share": {k: v / tot for k, v in ph.items()} if instrument else None,
             "loss_data": float(ld), "loss_prior": float(lp)}
@@ -130,6 +134,7 @@ def main():
     ap.add_argument("--config", default="breast", choices=sorted(CONFIGS))
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--many", action="store_true", help="sample loop inside the library (odeint_adjoint_many)")
+    ap.add_argument("--unfused-prior", action="store_true", help="the reference's two prior-loss lines as they are")
     a = ap.parse_args()
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -137,7 +142,7 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    out = run_epochs(a.config, a.epochs, a.many)
+    out = run_epochs(a.config, a.epochs, a.many, fused_prior=not a.unfused_prior)
     if out is not None:
         print(json.dumps(out), flush=True)
     if world > 1:
