@@ -43,6 +43,9 @@ def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True):
     torch.manual_seed(0)
     odenet = pb.ODENet(dev, G, neurons=H)
     parallel.broadcast_parameters(odenet)
+    # explicit opt-in to lazy solver-error checking: the host runs ahead of the GPU instead of synchronising after every
+    # solve (the default, which raises the reference's AssertionError at the call site); checked once per epoch below
+    pb.set_sync_errors(False)
     opt = optim.Adam([
         {'params': odenet.net_sums.linear_out.weight}, {'params': odenet.net_sums.linear_out.bias},
         {'params': odenet.net_prods.linear_out.weight}, {'params': odenet.net_prods.linear_out.bias},
@@ -108,6 +111,7 @@ def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True):
             ld, lp = training_step(i, False)
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
+        pb.check_errors()
     if instrument:
         for i in range(steps):      # one more, instrumented epoch for the phase split (synchronises between phases)
             training_step(i, True)
