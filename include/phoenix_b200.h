@@ -191,6 +191,15 @@ int phx_solve_adjoint_many(phx_ctx* ctx, int G, int H, int B, int N, const float
  * (find_gene_influences.py:64-73 with B=60, the 4096-row synthetic sweep).  Identical arguments and semantics; with
  * method = PHX_DOPRI5 the call synchronises `stream` once per attempted step (host-side step controller). */
 size_t phx_stream_workspace_bytes(const phx_ctx* ctx, int G, int H, int B, int T, int adjoint);
+/* Exact-global-norm mode for a batched dopri5 FORWARD solve whose rows are sharded over several GPUs: the
+ * reference's error norm is the RMS over ALL rows of the batch (torchdiffeq/_impl/misc.py:10-11), so every rank must take
+ * the same accept / reject decisions.  With a hook installed, phx_stream_solve_forward calls it once per norm evaluation
+ * with the DEVICE array of this rank's n partial sums (float64), enqueued on `stream`; the hook must sum the array over
+ * the ranks in place (an NCCL all-reduce of n doubles) and every rank then counts world_size x its own elements.  All
+ * ranks must hold the same number of rows.  The adjoint keeps per-shard controllers (its norm involves the parameter
+ * cotangents of the WHOLE batch).  hook = NULL switches the mode off. */
+typedef void (*phx_sum_hook)(double* sums_device, int n, void* stream, void* user);
+int phx_ctx_set_global_norm(phx_ctx* ctx, phx_sum_hook hook, void* user, int world_size);
 int phx_stream_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* y0,
                              const double* t_host, int T, int t_is_f32, int reversed, int method, double rtol,
                              double atol, int64_t max_num_steps, float* y_out, void* workspace,

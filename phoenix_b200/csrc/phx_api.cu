@@ -26,6 +26,9 @@ struct phx_ctx {
     int precision;                                   // PHX_PREC_*
     std::mutex mu;
     std::unordered_map<const float*, int> tc_valid;  // packed buffer -> its tensor-core images are current
+    phx_sum_hook sum_hook;                           // exact-global-norm mode of sharded batched dopri5 solves
+    void* sum_user;
+    int sum_world;
 };
 
 namespace {
@@ -167,6 +170,9 @@ int phx_ctx_create(int device, phx_ctx** out) {
     c->coop = prop.cooperativeLaunch;
     c->prof = nullptr;
     c->precision = PHX_PREC_3XTF32;
+    c->sum_hook = nullptr;
+    c->sum_user = nullptr;
+    c->sum_world = 1;
     if (const char* e = getenv("PHX_PRECISION")) c->precision = atoi(e);
     if (!c->coop) {
         delete c;
@@ -182,6 +188,12 @@ void phx_ctx_destroy(phx_ctx* ctx) { delete ctx; }
 int phx_ctx_num_sms(const phx_ctx* ctx) { return ctx ? ctx->num_sms : 0; }
 }  // extern "C"
 int phx_ctx_device(const phx_ctx* ctx) { return ctx ? ctx->device : 0; }
+int phx_ctx_sum_hook(const phx_ctx* ctx, phx_sum_hook* hook, void** user) {
+    if (!ctx || !ctx->sum_hook) return 1;
+    *hook = ctx->sum_hook;
+    *user = ctx->sum_user;
+    return ctx->sum_world;
+}
 extern "C" {
 
 int phx_ctx_set_profile(phx_ctx* ctx, void* slots) {
@@ -212,6 +224,13 @@ int phx_ctx_set_precision(phx_ctx* ctx, int precision) {
     return PHX_OK;
 }
 int phx_ctx_get_precision(const phx_ctx* ctx) { return ctx ? ctx->precision : PHX_ERR_INVALID; }
+int phx_ctx_set_global_norm(phx_ctx* ctx, phx_sum_hook hook, void* user, int world_size) {
+    if (!ctx || world_size < 1) return PHX_ERR_INVALID;
+    ctx->sum_hook = hook;
+    ctx->sum_user = user;
+    ctx->sum_world = hook ? world_size : 1;
+    return PHX_OK;
+}
 int phx_tc_min_rows(void) { return phx_tc_min_rows_rt(); }
 
 int phx_tc_plan_describe(int K, int M, int32_t out[6]) {

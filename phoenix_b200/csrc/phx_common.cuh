@@ -365,6 +365,7 @@ int phx_tc_vjp_params_launch(int G, int H, int B, const PhxPacked& w, const floa
 
 void phx_set_error(const char* fmt, ...);
 int phx_ctx_device(const phx_ctx* ctx);
+int phx_ctx_sum_hook(const phx_ctx* ctx, phx_sum_hook* hook, void** user);   // returns the world size (1: no hook)
 // Every entry point that enqueues work makes the context's device current for the duration of the call (the caller may be
 // sitting on another GPU) and restores the previous one.
 struct PhxDevGuard {

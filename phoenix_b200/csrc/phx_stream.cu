@@ -271,6 +271,9 @@ struct Stream {
     double* steplog;
     int steplog_cap;
     std::vector<double> log;
+    phx_sum_hook sum_hook = nullptr;   // exact-global-norm mode (forward solves only)
+    void* sum_user = nullptr;
+    int sum_world = 1;
 
     // stage derivative `slot` of every segment at the current stage inputs
     int eval(int slot) {
@@ -297,6 +300,7 @@ struct Stream {
             fixed_kernel<1><<<nblk(n), EB, 0, st>>>(mode, out, x0, k1, k2, k3, k4, dt, n);
     }
     int fetch_sums() {
+        if (sum_hook) sum_hook(sums_dev, 3 * (int)segs.size(), (void*)st, sum_user);   // sum over the ranks, in place
         cudaError_t e = cudaMemcpyAsync(sums_host, sums_dev, sizeof(double) * 3 * segs.size(), cudaMemcpyDeviceToHost,
                                         st);
         if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -312,7 +316,7 @@ struct Stream {
         for (size_t si = 0; si < segs.size(); ++si) {
             double s = sums_host[3 * si + q];
             if (isnan(s)) any_nan = true;
-            m = fmaxf(m, sqrtf((float)(s / segs[si].count)));
+            m = fmaxf(m, sqrtf((float)(s / (segs[si].count * (double)sum_world))));
         }
         return any_nan ? nanf("") : m;
     }
@@ -566,6 +570,7 @@ int setup(Stream& S, phx_ctx* ctx, int G, int H, int B, const float* packed, con
     }
     float* ws = (float*)workspace;
     S.ctx = ctx; S.G = G; S.H = H; S.B = B; S.T = T; S.method = method; S.t_is_f32 = t_is_f32; S.adjoint = adjoint;
+    if (!adjoint) S.sum_world = phx_ctx_sum_hook(ctx, &S.sum_hook, &S.sum_user);
     S.rtol_f = (float)rtol; S.atol_f = (float)atol; S.fsign = 1.f; S.max_steps = (long long)max_steps;
     int rc_tc = phx_tc_prepare(ctx, G, H, B, packed, &S.w, st);
     if (rc_tc != PHX_OK) return rc_tc;

@@ -325,7 +325,7 @@ def rhs_forward(net, y, decay):
 
 
 @_on_model_device
-def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True):
+def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True, flat=False):
     packed, G, H, dev = packed_weights(net)
     y2 = y.detach().to(torch.float32).contiguous()
     g2 = g.detach().to(torch.float32).contiguous()
@@ -342,6 +342,8 @@ def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True):
         reuse = _last_rhs.pop(ws.data_ptr(), None) == _rhs_signature(net, packed, y2, B)
     _lib.check(lib.phx_rhs_vjp(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(g2), int(decay), _ptr(ybar),
                                _ptr(grads), 2 if reuse else 0, _ptr(ws), ws.numel(), _stream_ptr(dev)), "rhs_vjp")
+    if flat:   # the caller scales / splits the [P] vector itself
+        return ybar, grads
     return ybar, (split_flat_grads(grads, G, H) if need_grads else None)
 
 

@@ -68,11 +68,14 @@ class _PriorLoss(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, grad_out):
-        _, grads = engine.rhs_vjp(ctx.net, ctx.x2, ctx.gcot, False, need_ybar=False, need_grads=True)
+        _, flat = engine.rhs_vjp(ctx.net, ctx.x2, ctx.gcot, False, need_ybar=False, need_grads=True, flat=True)
+        flat *= grad_out          # one pass over the flat [P] vector; the six gradients stay views of ONE buffer
+        G = ctx.x2.shape[-1]
+        grads = engine.split_flat_grads(flat, G, (flat.numel() - G) // (4 * G + 2))
         out = [None, None, None]
         for i, need in enumerate(ctx.needs_input_grad[3:]):
             # gene_multipliers do not enter prior_only_forward (odenet.py:93-98): the reference leaves that .grad untouched
-            out.append(grads[i] * grad_out if (need and i > 0) else None)
+            out.append(grads[i] if (need and i > 0) else None)
         return tuple(out)
 
 

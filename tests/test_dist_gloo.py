@@ -36,6 +36,16 @@ def _worker(rank, world, port, out):
         p.grad = torch.full_like(p, float((i + 1) * (rank + 1)))
     parallel.allreduce_grads(net)
     ok = ok and all(torch.allclose(p.grad, torch.full_like(p, float((i + 1) * 1.5))) for i, p in enumerate(net.parameters()))
+    # after the gathered path .grad are views of ONE flat buffer: the next collective runs in place on it
+    flat = parallel.flat_grad_view(net)
+    ok = ok and flat is not None and flat.numel() == sum(p.numel() for p in net.parameters())
+    ptr = flat.data_ptr()
+    flat.fill_(float(rank + 1))
+    extra = parallel.allreduce_grads(net, average=False, extra=torch.tensor([2.0, float(rank)]))
+    ok = ok and parallel.flat_grad_view(net).data_ptr() == ptr and bool((flat == 3.0).all())
+    ok = ok and all(bool((p.grad == 3.0).all()) for p in net.parameters()) and extra.tolist() == [4.0, 1.0]
+    net.gene_multipliers.grad = torch.zeros_like(net.gene_multipliers)      # no longer one buffer
+    ok = ok and parallel.flat_grad_view(net) is None
     w0 = net.net_sums.linear_out.weight.detach().clone()
     gathered = [torch.zeros_like(w0) for _ in range(world)]
     dist.all_gather(gathered, w0)

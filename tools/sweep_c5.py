@@ -28,6 +28,12 @@ def main():
     ap.add_argument("--neurons", type=int, default=200)
     ap.add_argument("--rows", type=int, default=4096)
     ap.add_argument("--cpu-rows", type=int, default=0)
+    ap.add_argument("--strong", action="store_true", help="--rows is the TOTAL batch, split evenly over the ranks")
+    ap.add_argument("--global-norm", action="store_true",
+                    help="dopri5 forward: all-reduce the error-norm sums over the ranks every step (one controller for the "
+                         "whole batch, exactly like the unsharded call)")
+    ap.add_argument("--rtol", type=float, default=1e-7)
+    ap.add_argument("--atol", type=float, default=1e-9)
     a = ap.parse_args()
     G, H, B = a.genes, a.neurons, a.rows
     import torch.distributed as dist
@@ -39,11 +45,16 @@ def main():
     torch.manual_seed(5)
     net = pb.ODENet("cuda", G, neurons=H)
     parallel.broadcast_parameters(net)
+    if a.strong:
+        assert B % world == 0, "--strong needs a batch divisible by the number of ranks"
+        B = B // world
     torch.manual_seed(100 + rank)
     y0 = torch.rand(B, G, device="cuda")
     pb.set_sync_errors(True)
+    if a.global_norm and world > 1:
+        parallel.enable_global_norm()
     for method, t, kw in (("rk4", torch.tensor([0.0, 0.1]), {}),
-                          ("dopri5", torch.tensor([0.0, 0.1]), {"rtol": 1e-5, "atol": 1e-7})):
+                          ("dopri5", torch.tensor([0.0, 0.1]), {"rtol": a.rtol, "atol": a.atol})):
         for leg in ("forward", "forward+adjoint"):
             def run():
                 if leg == "forward":
@@ -80,6 +91,8 @@ def main():
                 ms, work = float(mx[0]), float(st[1])
             if rank == 0:
                 print(json.dumps({"n_gpus": world, "G": G, "H": H, "rows_per_gpu": B, "method": method, "leg": leg,
+                                  "scaling": "strong" if a.strong else "weak", "rtol": kw.get("rtol"),
+                                  "global_norm": bool(a.global_norm and world > 1 and method == "dopri5"),
                                   "rhs_evals": evals, "ms": ms, "gene_steps_per_s": work / (ms * 1e-3)}), flush=True)
     if a.cpu_rows and rank == 0 and world == 1:
         from oracle import phoenix_oracle as O
