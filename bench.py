@@ -268,7 +268,11 @@ def run_ours(args):
     adj_y0 = torch.empty(BATCH, 1, G, device=dev)
     nparts = lib.phx_rows_grad_parts(ctx, G, H, BATCH)
     gpk = torch.empty(nparts * lib.phx_packed_grad_bytes(G, H) // 4, device=dev)
-    gsum = torch.empty(P, device=dev)
+    # N > 1: the flat gradient is written straight into a peer-mapped buffer and summed over the ranks by ONE kernel per
+    # rank over NVLink peer memory (phoenix_b200/csrc/phx_peer.cu); PHX_BENCH_NCCL=1 keeps the NCCL all-reduce instead
+    use_peer = world > 1 and not int(os.environ.get("PHX_BENCH_NCCL", "0"))
+    peer = parallel.enable_peer_allreduce(net) if use_peer else None
+    gsum = peer.buffer[:P] if use_peer else torch.empty(P, device=dev)
     st_f = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
     st_a = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
     mid = _lib.METHOD_IDS[METHOD]
@@ -306,7 +310,9 @@ def run_ours(args):
             e1.record(stream)
             adj_ev.append((e0, e1, BATCH))
         _lib.check(lib.phx_unpack_grads(ctx, G, H, ptr(gpk), nparts, ptr(gsum), 0, sp), "unpack_grads")
-        if world > 1:
+        if use_peer:
+            peer.reduce(numel=P)
+        elif world > 1:
             dist.all_reduce(gsum)
 
     def timed(step_fn, steps):
@@ -477,7 +483,9 @@ def run_ours(args):
             "config": {"workload": "breast 11165 genes x 200 neurons, batch 17 x (odeint_adjoint %s dt=0.0051 + "
                                    "backward)" % METHOD, "genes": G, "neurons": H, "samples_per_step": BATCH,
                        "rhs_evals_per_step": evals_total / world, "l2": "flushed between timed steps (256 MiB write)",
-                       "parallelism": "dp%d (samples sharded, 1 grad allreduce/step)" % world},
+                       "parallelism": "dp%d (samples sharded, 1 grad allreduce/step%s)" % (
+                           world, "" if world == 1 else (": phx_peer_allreduce over NVLink peer memory" if use_peer
+                                                         else ": NCCL"))},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
                     "h2d_bytes_per_step": 2 * BATCH * G * 4, "d2h_bytes_per_step": 4,
                     "api": "phoenix_b200.odeint_adjoint_many (sample loop of training_step inside the library) + "

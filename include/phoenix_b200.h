@@ -244,6 +244,17 @@ int phx_rows_grad_parts(const phx_ctx* ctx, int G, int H, int N);
 int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int nparts, float* grads_flat,
                      int accumulate, void* stream);
 
+/* ---- multi-GPU: the one exchange of the path ------------------------------------------------------------------
+ * The reference has no distributed code; with the samples of train_insilico.py:128-130 sharded over the GPUs of one box
+ * the parameter gradients must be summed once per optimiser step.  phx_peer_allreduce does that sum IN PLACE over peer
+ * memory (NVLink 5 / NVSwitch), one kernel per rank, no NCCL call: bufs[r] / flags[r] are the device pointers of rank r's
+ * gradient buffer (n floats, 16-byte aligned) and flag pad (2 * world uint32, zeroed once) as mapped into THIS process
+ * (e.g. torch symmetric memory); `epoch` grows by one per call and is the same on every rank; every rank's buffer ends up
+ * holding scale * (sum over ranks), bit-identical everywhere, summed in rank order.  world in {2, 4, 8}.  The call is
+ * asynchronous on `stream`; all ranks must make it (it spins on the peers' flags). */
+int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* flags, int rank, int world, size_t n,
+                       unsigned epoch, float scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@ NVCC_FLAGS = [
 
 # (object name, source, extra defines)
 UNITS = [("phx_api", "phx_api.cu", []), ("phx_plan", "phx_plan.cu", []), ("phx_rhs", "phx_rhs.cu", []),
-         ("phx_stream", "phx_stream.cu", []), ("phx_tc", "phx_tc.cu", [])]
+         ("phx_stream", "phx_stream.cu", []), ("phx_tc", "phx_tc.cu", []), ("phx_peer", "phx_peer.cu", [])]
 for kind in (0, 1):
     UNITS.append(("phx_rows_%s" % ("adj" if kind else "fwd"), "phx_rows_inst.cu", ["-DPHX_KIND_ADJ=%d" % kind]))
     for nv in (1, 2, 4):
@@ -48,6 +48,8 @@ def _stale(target, deps):
 
 def _compile(unit, verbose):
     name, src, defs = unit
+    if os.environ.get("PHX_TC_PROFILE_BUILD") and name == "phx_tc":   # in-kernel cycle counters of the tcgen05 kernels
+        defs = defs + ["-DPHX_TC_PROFILE=1"]
     obj = os.path.join(OBJ, name + ".o")
     cmd = [_nvcc()] + NVCC_FLAGS + defs + (["-Xptxas", "-v"] if verbose else []) + \
           ["-c", os.path.join(CSRC, src), "-o", obj]

@@ -33,6 +33,13 @@ namespace {
 
 constexpr int BK = PHX_TC_BK;
 
+// in-kernel cycle counters of the branch kernel (tools/tc_check.py with PHX_TC_PROF=1): compiled in only with
+// -DPHX_TC_PROFILE=1 (PHX_TC_PROFILE_BUILD=1 python -m phoenix_b200.build --force) -- the producers are instruction-bound
+#ifndef PHX_TC_PROFILE
+#define PHX_TC_PROFILE 0
+#endif
+#define PROF(p) (PHX_TC_PROFILE ? (p).prof : (unsigned long long*)nullptr)
+
 __device__ __forceinline__ unsigned smem_u32(const void* ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
 
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count) {
@@ -142,6 +149,18 @@ __device__ __forceinline__ void mma_tf32(unsigned tmem_d, uint64_t adesc, uint64
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// the same with the A operand read from TENSOR memory (lane = row, 8 consecutive 32-bit columns = the K = 8 slice)
+__device__ __forceinline__ void mma_tf32_ts(unsigned tmem_d, unsigned tmem_a, uint64_t bdesc, unsigned idesc,
+                                            unsigned accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
 // arrives on the mbarrier once every MMA issued so far by this thread has completed (implies fence::before_thread_sync)
 __device__ __forceinline__ void mma_commit(unsigned bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -185,7 +204,10 @@ __device__ __forceinline__ float tf32_rna(float x) {
 }
 __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     hi = tf32_rna(x);
-    lo = tf32_rna(x - hi);
+    // rna_tf32(x - hi) on the bit pattern (add half an ulp of the 10-bit mantissa, clear the low 13 bits): the same value
+    // as cvt.rna.tf32 for every finite input in two integer instructions instead of four (cvt.rna.tf32.f32 is expanded
+    // into add / non-finite test / select / mask).  A non-finite x already makes hi non-finite, so the product stays so.
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
 }
 
 // ---- operand images of the weights -------------------------------------------------------------------------------------
@@ -238,11 +260,75 @@ __global__ void tc_pack_kernel(int G, int H, int Hp, int K2, int Hn, const float
     }
 }
 
-__device__ __forceinline__ void hill(float y, float& s, float& l, int want_l) {
-    float z = y - 0.5f;
-    float den = 1.0f + fabsf(z);
-    s = __fdividef(z, den);   // den in [1, inf): no range issue; <= 2 ulp, far inside the 3xTF32 error budget
-    l = want_l ? log1pf(s) : 0.f;
+// hi / lo split of a FINITE value of moderate magnitude (|x| < 1e38): round-to-nearest on the bit pattern, no non-finite test
+__device__ __forceinline__ void split_tf32_finite(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u);
+    lo = __uint_as_float((__float_as_uint(x - hi) + 0x1000u) & 0xffffe000u);
+}
+__device__ __forceinline__ float rcp_fast(float x) {   // MUFU.RCP, 1 ulp; callers pass x >= 1
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+// soft-sign s = z / (1 + |z|), z = y - 0.5 (odenet.py:21-27): the denominator is >= 1, so the range handling of a generic
+// fast division is dead weight in the producers, which are instruction-bound
+__device__ __forceinline__ float hill_s(float y) {
+    const float z = y - 0.5f;
+    return z * rcp_fast(1.0f + fabsf(z));
+}
+// l = log1p(s) (odenet.py:29-35).  With s = z / (1 + |z|):  log1p(s) = 2 atanh(u), u = s / (2 + s) = z / (2 + 2|z| + z),
+// so l needs ONE reciprocal and an odd series in u.  For |z| <= 0.65 (y in [-0.15, 1.15]: expression data live in [0, 1])
+// |u| <= 0.246 and five series terms leave a truncation error below 5e-9; measured <= 2.5 ulp against float64 (log1pf:
+// 1.9 ulp).  Anything outside takes the library log1pf.
+constexpr float HILL_L_SERIES_MAX = 0.65f;
+__device__ __forceinline__ float hill_l_series(float z, float az) {   // valid for az = |z| <= HILL_L_SERIES_MAX
+    const float u = z * rcp_fast(fmaf(2.f, az, 2.f) + z);
+    const float w = u * u;
+    float p = fmaf(w, 0.09090909090909091f, 0.1111111111111111f);
+    p = fmaf(w, p, 0.14285714285714285f);
+    p = fmaf(w, p, 0.2f);
+    p = fmaf(w, p, 0.3333333333333333f);
+    const float u2 = u + u;
+    return fmaf(u2, w * p, u2);
+}
+__device__ __forceinline__ float hill_l(float y) {
+    const float z = y - 0.5f, az = fabsf(z);
+    if (az <= HILL_L_SERIES_MAX) return hill_l_series(z, az);
+    return log1pf(z * rcp_fast(1.0f + az));   // NaN lands here too
+}
+// The producers' conversion of four source values into hi / lo A-operand values.  The common case -- every value of the
+// WARP finite and, for the log1p branch, inside the series range -- is decided with ONE vote and runs as straight-line
+// code for the four elements (the producers are instruction-bound: 18 instructions per element on the log1p branch
+// instead of ~30 with per-element range and non-finite tests); anything else takes the guarded per-element path.  Both
+// paths give the same bits for the values the fast one accepts.
+template <int MODE>
+__device__ __forceinline__ void convert4(const float (&x)[4], const float (&sc)[4], int br, float (&hi)[4], float (&lo)[4]) {
+    float v[4], m = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        v[j] = MODE ? x[j] * sc[j] : x[j] - 0.5f;
+        m = fmaxf(m, fabsf(v[j]));   // fmaxf drops a NaN operand: tested separately below
+    }
+    const bool fin = (v[0] - v[0]) + (v[1] - v[1]) + (v[2] - v[2]) + (v[3] - v[3]) == 0.f;   // false with any NaN / inf
+    const float lim = (!MODE && br) ? HILL_L_SERIES_MAX : 1e38f;
+    if (__all_sync(0xffffffffu, fin && m <= lim)) {
+        if (MODE) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32_finite(v[j], hi[j], lo[j]);
+        } else if (br) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32_finite(hill_l_series(v[j], fabsf(v[j])), hi[j], lo[j]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) split_tf32_finite(v[j] * rcp_fast(1.0f + fabsf(v[j])), hi[j], lo[j]);
+        }
+        return;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float a = MODE ? v[j] : (br ? hill_l(x[j]) : hill_s(x[j]));
+        split_tf32(a, hi[j], lo[j]);
+    }
 }
 
 // ---- kernel 1: branch contraction ----------------------------------------------------------------------------------------
@@ -265,6 +351,8 @@ struct BranchParams {
     const float* w1img;
     float* spart;         // [slot][Bpad][2*Hn]; sums branch uses slots < ks_s, prods branch slots < ks_p
     unsigned long long* prof;   // optional cycle counters (PHX_TC_PROF): see tools/tc_check.py
+    int a_stages;               // TS = 1: depth of the A ring in tensor memory and the columns of its hi / lo tiles
+    int a_hi_col[4], a_lo_col[4];
 };
 constexpr int K1_PWARPS = 16;                      // producer warps
 constexpr int K1_DWARPS = 4;                       // drain warps (one per TMEM lane quarter)
@@ -317,8 +405,16 @@ __device__ __forceinline__ uint64_t desc_at(uint64_t hi_part, unsigned saddr) {
 // k-block from ~107 KB to ~73 KB -- the bound of the single-CTA kernel.  Producer arrivals and the "B half landed"
 // signal of the peer CTA reach the leader's full barrier as remote (cluster-scope) arrives; slot release and chunk
 // completion come back to both CTAs by multicast tcgen05.commit.
-template <int MODE, int TRANS, int PAIR>
+//
+// TS = 1 (single CTA only): the A tiles live in TENSOR memory instead of shared memory.  The producers tcgen05.st their
+// hi / lo values straight into spare columns next to the two accumulators (thread = tile row = its TMEM lane, so the row a
+// thread converts is fixed by its warp's lane quarter) and the MMAs take A as a tensor-memory operand.  Per k-block this
+// removes the 16 KB of A-tile stores and the 24 KB of A-operand reads from the shared-memory pipe -- the bound of the
+// TS = 0 kernel (123 KB per k-block against 128 B/clk) -- leaving the B operand: 40 KB of reads + 27 KB of bulk copy.
+// The ring of B stages (shared memory) and the ring of A stages (tensor memory, 2-4 deep) run on separate barriers.
+template <int MODE, int TRANS, int PAIR, int TS>
 __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p) {
+    static_assert(!(TS && PAIR), "the tensor-memory A operand is implemented for the single-CTA kernel");
     extern __shared__ __align__(1024) unsigned char smem[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // work item: branch, 128-row tile (PAIR: tile pair), K range (a whole number of chunks)
@@ -338,20 +434,28 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
     const int Hb = PAIR ? Hn >> 1 : Hn;                 // B rows staged by this CTA
     const unsigned b_tile = (unsigned)Hb * BK * 4;
     const unsigned b_bytes = 2 * b_tile;
-    const unsigned stage_bytes = K1_A_BYTES + b_bytes;
+    constexpr unsigned A_SMEM = TS ? 0u : K1_A_BYTES;   // bytes of the A tiles inside a shared-memory stage
+    const unsigned stage_bytes = A_SMEM + b_bytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)S * stage_bytes);
     const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + S), done = smem_u32(bars + 2 * S),
                    drained = smem_u32(bars + 2 * S + 1);
-    unsigned* slot = reinterpret_cast<unsigned*>(bars + 2 * S + 2);
+    const unsigned fullA0 = smem_u32(bars + 2 * S + 2), emptyA0 = smem_u32(bars + 2 * S + 6);   // TS: A ring, <= 4 stages
+    unsigned* slot = reinterpret_cast<unsigned*>(bars + 2 * S + 10);
     const unsigned stage0 = smem_u32(smem);
+    const int SA = TS ? p.a_stages : S;
 
     if (tid == 0) {
         for (int s = 0; s < S; ++s) {
             // single CTA: producer warps + the bulk-copy issuer (expect_tx).  Pair, leader: + the peer's producer warps
             // and its "B half landed" relay; pair, peer: the barrier only tracks the peer's own bulk copy.
-            mbar_init(full0 + 8 * s, !PAIR ? K1_PWARPS + 1 : (leader ? 2 * K1_PWARPS + 2 : 1));
+            mbar_init(full0 + 8 * s, TS ? 1 : (!PAIR ? K1_PWARPS + 1 : (leader ? 2 * K1_PWARPS + 2 : 1)));
             mbar_init(empty0 + 8 * s, 1);              // tcgen05.commit (multicast to both CTAs of a pair)
         }
+        if (TS)
+            for (int s = 0; s < SA; ++s) {
+                mbar_init(fullA0 + 8 * s, K1_PWARPS);  // every producer warp has stored its columns of the A tile
+                mbar_init(emptyA0 + 8 * s, 1);         // tcgen05.commit
+            }
         mbar_init(done, 1);
         mbar_init(drained, PAIR ? 2 * K1_DWARPS : K1_DWARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -368,12 +472,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 
     if (warp < K1_PWARPS) {
         // ---- producers: Hill activation of this CTA's 128 x 16 slab of y, hi/lo split, core-matrix layout ----
-        const int rl = TRANS ? (warp & 3) * 32 + lane : warp * 8 + (lane & 7);   // row rl of the tile
-        const int kc = TRANS ? warp >> 2 : lane >> 3;                           // k-chunk kc (4 floats)
+        // row rl of the tile, k-chunk kc (4 floats).  TS: the row is the thread's tensor-memory lane
+        const int rl = (TRANS || TS) ? (warp & 3) * 32 + lane : warp * 8 + (lane & 7);
+        const int kc = (TRANS || TS) ? warp >> 2 : lane >> 3;
         const int row = m0 + rl;
         const float* src = TRANS ? p.y + row : p.y + (size_t)row * p.ld;
         const bool rok = row < p.B;
         const float rscale = (MODE && TRANS && p.ascale && rok) ? __ldg(p.ascale + row) : 1.f;
+        const bool asc_vec = (reinterpret_cast<uintptr_t>(p.ascale) & 15) == 0;
         const unsigned a_off = (unsigned)phx_tc_btile_off(128, rl, kc * 4) * 4u;
         // y is read in super-blocks of K1_PF k-blocks, the loads of the NEXT super-block in flight while the current one is
         // converted and handed to the MMAs.
@@ -386,10 +492,29 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         float cur[K1_PF][4], nxt[K1_PF][4];
         constexpr int SBF = K1_PF * BK;          // floats of one row in a super-block (64)
         constexpr int SROW = SBF + 4;            // padded row stride of the staging buffer
-        float* stg = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + 256) + (size_t)warp * 2 * 8 * SROW;
+        // TS = 0: a private buffer per warp (its 8 rows).  TS = 1: one buffer per lane quarter, shared by the four warps
+        // (w & 3) == quarter: warp (quarter, j) loads rows 8j .. 8j+7 of the quarter and reads row `lane`, k-chunk j;
+        // the hand-over is a 128-thread named barrier instead of __syncwarp.
+        float* stg = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + 256) +
+                     (TS ? (size_t)(warp & 3) * 2 * 32 * SROW : (size_t)warp * 2 * 8 * SROW);
+        constexpr int SBUF = (TS ? 32 : 8) * SROW;                  // floats of one staging buffer
+        const int srow0 = TS ? (warp >> 2) * 8 : 0;                 // first staging row this warp fills
+        const int srd = TS ? lane : (lane & 7);                     // staging row this thread reads
+        auto stage_sync = [&]() {
+            if (TS) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
+            else __syncwarp();
+        };
         const float padv = MODE ? 0.f : 0.5f;    // pads contribute zero: s(0.5) = l(0.5) = 0
         auto load = [&](int i, float (&v)[K1_PF][4]) {   // k-blocks kb0 + i .. kb0 + i + K1_PF - 1
             if (TRANS) {
+                if (i + K1_PF <= nkb && (kb0 + i + K1_PF) * BK <= p.G) {   // interior super-block: only the row test
+                    const float* q = src + (size_t)((kb0 + i) * BK + kc * 4) * p.ld;
+#pragma unroll
+                    for (int u = 0; u < K1_PF; ++u)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) v[u][j] = rok ? __ldg(q + (size_t)(u * BK + j) * p.ld) : padv;
+                    return;
+                }
 #pragma unroll
                 for (int u = 0; u < K1_PF; ++u) {
 #pragma unroll
@@ -401,9 +526,21 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             } else {
                 // v[rr/2][(rr%2)*2 + h] = element (lane + 32 h) of row rr of this warp
                 const int kvalid = min(p.G - (kb0 + i) * BK, (nkb - i) * BK);   // valid floats of the piece
+                const int rbase = m0 + (TS ? (warp & 3) * 32 + srow0 : warp * 8);
+                if (kvalid >= SBF && rbase + 8 <= p.B) {   // interior: no predicates
+                    const float* rp = p.y + (size_t)rbase * p.ld + (size_t)(kb0 + i) * BK + lane;
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h)
+                            asm volatile("ld.global.nc.L2::256B.f32 %0, [%1];"
+                                         : "=f"(v[rr >> 1][(rr & 1) * 2 + h])
+                                         : "l"(rp + (size_t)rr * p.ld + 32 * h));
+                    return;
+                }
 #pragma unroll
                 for (int rr = 0; rr < 8; ++rr) {
-                    const int row8 = m0 + warp * 8 + rr;
+                    const int row8 = m0 + (TS ? (warp & 3) * 32 + srow0 : warp * 8) + rr;
                     const float* rp = p.y + (size_t)row8 * p.ld + (size_t)(kb0 + i) * BK;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
@@ -417,13 +554,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             }
         };
         auto stage_put = [&](int buf, const float (&v)[K1_PF][4]) {   // TRANS = 0: registers -> staging buffer
-            float* d = stg + buf * 8 * SROW;
+            float* d = stg + buf * SBUF + srow0 * SROW;
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
                 for (int h = 0; h < 2; ++h) d[rr * SROW + lane + 32 * h] = v[rr >> 1][(rr & 1) * 2 + h];
         };
-        long long t_empty = 0, t0 = clock64();
+        long long t_empty = 0, t_load = 0, t_conv = 0, t_store = 0, t0 = clock64();
         int s = 0;           // ring slot of k-block i
         unsigned ph = 0;     // its phase parity
         int sbuf = 0;
@@ -432,49 +569,76 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         } else {
             load(0, nxt);
             stage_put(0, nxt);
-            __syncwarp();
+            stage_sync();
         }
+        int sa = 0;          // TS: A-ring slot of k-block i and its phase parity
+        unsigned pha = 0;
+        const unsigned tq = TS ? tmem + ((unsigned)((warp & 3) * 32) << 16) + 4u * (unsigned)kc : 0u;
         for (int i0 = 0; i0 < nkb; i0 += K1_PF) {
+            const long long tl0 = PROF(p) ? clock64() : 0;
             if (i0 + K1_PF < nkb) load(i0 + K1_PF, nxt);
+            if (PROF(p)) t_load += clock64() - tl0;
 #pragma unroll
             for (int u = 0; u < K1_PF; ++u) {
                 const int i = i0 + u;
                 if (i < nkb) {
+                    const long long tc0 = PROF(p) ? clock64() : 0;
                     float xin[4];
                     if (TRANS) {
 #pragma unroll
                         for (int j = 0; j < 4; ++j) xin[j] = cur[u][j];
                     } else {
                         const float4 t =
-                            *reinterpret_cast<const float4*>(stg + sbuf * 8 * SROW + (lane & 7) * SROW + u * BK + kc * 4);
+                            *reinterpret_cast<const float4*>(stg + sbuf * SBUF + srd * SROW + u * BK + kc * 4);
                         xin[0] = t.x; xin[1] = t.y; xin[2] = t.z; xin[3] = t.w;
                     }
                     float hi[4], lo[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        float sv, lv;
-                        if (MODE) {
-                            // the per-gene factor is applied here, NOT where the load is issued: a use right behind
-                            // the load would wait for it and serialise the prefetch
-                            float sc = 1.f;
-                            if (p.ascale) {
-                                if (TRANS) {
-                                    sc = rscale;
-                                } else {
-                                    const int gi = (kb0 + i) * BK + kc * 4 + j;
-                                    sc = gi < p.G ? __ldg(p.ascale + gi) : 0.f;
-                                }
-                            }
-                            sv = lv = xin[j] * sc;
+                    float sc4[4] = {rscale, rscale, rscale, rscale};
+                    if (MODE && !TRANS && p.ascale) {   // per-gene factors of this thread's k-chunk: one 16-byte load
+                        const int g0 = (kb0 + i) * BK + kc * 4;
+                        if (asc_vec && g0 + 3 < p.G) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.ascale + g0));
+                            sc4[0] = t.x; sc4[1] = t.y; sc4[2] = t.z; sc4[3] = t.w;
                         } else {
-                            hill(xin[j], sv, lv, br);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) sc4[j] = g0 + j < p.G ? __ldg(p.ascale + g0 + j) : 0.f;
                         }
-                        split_tf32(br ? lv : sv, hi[j], lo[j]);
                     }
-                    const long long tw = p.prof ? clock64() : 0;
+                    // (MODE 1: the per-gene factor is applied here, NOT where the load of y is issued: a use right behind
+                    // the load would wait for it and serialise the prefetch)
+                    convert4<MODE>(xin, sc4, br, hi, lo);
+                    const long long tw = PROF(p) ? clock64() : 0;
+                    if (PROF(p)) t_conv += tw - tc0 + (long long)(__float_as_uint(hi[0]) & 0u);
+                    if (TS) {
+                        if (lane == 0) mbar_wait(emptyA0 + 8 * sa, pha ^ 1u);   // the MMAs that read this slot are done
+                        __syncwarp();
+                        tc_fence_after();
+                        const long long ts0 = PROF(p) ? clock64() : 0;
+                        if (PROF(p)) t_empty += ts0 - tw;
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(
+                                         tq + (unsigned)p.a_hi_col[sa]),
+                                     "r"(__float_as_uint(hi[0])), "r"(__float_as_uint(hi[1])), "r"(__float_as_uint(hi[2])),
+                                     "r"(__float_as_uint(hi[3]))
+                                     : "memory");
+                        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1,%2,%3,%4};" ::"r"(
+                                         tq + (unsigned)p.a_lo_col[sa]),
+                                     "r"(__float_as_uint(lo[0])), "r"(__float_as_uint(lo[1])), "r"(__float_as_uint(lo[2])),
+                                     "r"(__float_as_uint(lo[3]))
+                                     : "memory");
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fullA0 + 8 * sa);
+                        if (PROF(p)) t_store += clock64() - ts0;
+                        if (++sa == SA) {
+                            sa = 0;
+                            pha ^= 1u;
+                        }
+                        continue;
+                    }
                     if (lane == 0) mbar_wait(empty0 + 8 * s, ph ^ 1u);   // one poller per warp
                     __syncwarp();
-                    if (p.prof) t_empty += clock64() - tw;
+                    if (PROF(p)) t_empty += clock64() - tw;
                     unsigned char* a = smem + (size_t)s * stage_bytes + a_off;
                     *reinterpret_cast<float4*>(a) = make_float4(hi[0], hi[1], hi[2], hi[3]);
                     *reinterpret_cast<float4*>(a + K1_A_TILE) = make_float4(lo[0], lo[1], lo[2], lo[3]);
@@ -496,15 +660,20 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
 #pragma unroll
                     for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
             } else if (i0 + K1_PF < nkb) {
+                const long long tl1 = PROF(p) ? clock64() : 0;
                 sbuf ^= 1;
-                stage_put(sbuf, nxt);   // the other buffer: last read one super-block ago (ordered by the __syncwarp)
-                __syncwarp();
+                stage_put(sbuf, nxt);   // the other buffer: last read one super-block ago (ordered by the hand-over sync)
+                stage_sync();
+                if (PROF(p)) t_load += clock64() - tl1;
             }
         }
-        if (p.prof && tid == 0) {
-            unsigned long long* q = p.prof + 8 * br + 4;
+        if (PROF(p) && tid == 0) {
+            unsigned long long* q = PROF(p) + 8 * br + 4;
             atomicAdd(q + 0, (unsigned long long)(clock64() - t0));
             atomicAdd(q + 1, (unsigned long long)t_empty);
+            atomicAdd(PROF(p) + 16 + 8 * br + 0, (unsigned long long)t_load);
+            atomicAdd(PROF(p) + 16 + 8 * br + 1, (unsigned long long)t_conv);
+            atomicAdd(PROF(p) + 16 + 8 * br + 2, (unsigned long long)t_store);
         }
     } else if (warp == K1_W_BULK) {
         if (lane == 0) {
@@ -514,7 +683,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 if (!PAIR) {
                     mbar_expect_tx(full0 + 8 * s, b_bytes);
-                    bulk_g2s(stage0 + s * stage_bytes + K1_A_BYTES,
+                    bulk_g2s(stage0 + s * stage_bytes + A_SMEM,
                              p.w1img + ((size_t)(kb0 + i) * 4 + 2 * br) * Hn * BK, b_bytes, full0 + 8 * s);
                 } else {
                     // this CTA's half of the rows: in the image the rows of one k-chunk are contiguous, so the half
@@ -552,8 +721,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         const unsigned idesc = idesc_tf32(PAIR ? 256 : 128, Hn);
         const unsigned lt = PHX_TC_BRANCH_SW64 ? 4u : 0u;
         const uint64_t a_hi_part = smem_desc(0, p.a_lbo, p.a_sbo, lt), b_hi_part = smem_desc(0, p.b_lbo, p.b_sbo, lt);
-        int s = 0, c = 0, ic = 0;
-        unsigned ph = 0;
+        int s = 0, c = 0, ic = 0, sa = 0;
+        unsigned ph = 0, pha = 0;
         long long t_full = 0, t_drained = 0, t0 = clock64();
         if (PAIR && !leader) {
             for (int i = 0; i < nkb; ++i) {
@@ -570,18 +739,43 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         } else
         for (int i = 0; i < nkb; ++i) {
             if (ic == 0 && c > 0) {   // the previous chunk's sum must have left the chunk accumulator (both CTAs)
-                const long long tw = p.prof ? clock64() : 0;
+                const long long tw = PROF(p) ? clock64() : 0;
                 if (PAIR) mbar_wait_cluster(drained, (unsigned)(c - 1) & 1u);
                 else mbar_wait(drained, (unsigned)(c - 1) & 1u);
-                if (p.prof) t_drained += clock64() - tw;
+                if (PROF(p)) t_drained += clock64() - tw;
             }
-            const long long tw = p.prof ? clock64() : 0;
+            const long long tw = PROF(p) ? clock64() : 0;
             if (PAIR) mbar_wait_cluster(full0 + 8 * s, ph);
             else mbar_wait(full0 + 8 * s, ph);
-            if (p.prof) t_full += clock64() - tw;
+            if (TS) mbar_wait(fullA0 + 8 * sa, pha);
+            if (PROF(p)) t_full += clock64() - tw;
             tc_fence_after();
-            const unsigned a_base = stage0 + s * stage_bytes, b_base = a_base + K1_A_BYTES;
-            if (elect_one()) {
+            const unsigned a_base = stage0 + s * stage_bytes, b_base = a_base + A_SMEM;
+            if (TS) {
+                if (elect_one()) {
+                    const unsigned ta_hi = tmem + (unsigned)p.a_hi_col[sa], ta_lo = tmem + (unsigned)p.a_lo_col[sa];
+#pragma unroll
+                    for (int k8 = 0; k8 < BK / 8; ++k8) {
+                        const uint64_t b_hi = desc_at(b_hi_part, b_base + k8 * p.b_kadv);
+                        const uint64_t b_lo = desc_at(b_hi_part, b_base + b_tile + k8 * p.b_kadv);
+                        const unsigned acc = (ic > 0 || k8 > 0) ? 1u : 0u;
+                        if (p.nterms == 3) {
+                            mma_tf32_ts(tmem, ta_lo + 8u * k8, b_hi, idesc, acc);
+                            mma_tf32_ts(tmem, ta_hi + 8u * k8, b_lo, idesc, 1u);
+                            mma_tf32_ts(tmem, ta_hi + 8u * k8, b_hi, idesc, 1u);
+                        } else {
+                            mma_tf32_ts(tmem, ta_hi + 8u * k8, b_hi, idesc, acc);
+                        }
+                    }
+                    mma_commit(emptyA0 + 8 * sa);
+                    mma_commit(empty0 + 8 * s);
+                    if (ic == p.chunk - 1 || i == nkb - 1) mma_commit(done);
+                }
+                if (++sa == SA) {
+                    sa = 0;
+                    pha ^= 1u;
+                }
+            } else if (elect_one()) {
 #pragma unroll
                 for (int k8 = 0; k8 < BK / 8; ++k8) {
                     const uint64_t a_hi = desc_at(a_hi_part, a_base + k8 * p.a_kadv);
@@ -623,8 +817,8 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 ++c;
             }
         }
-        if (p.prof && lane == 0) {
-            unsigned long long* q = p.prof + 8 * br;
+        if (PROF(p) && lane == 0) {
+            unsigned long long* q = PROF(p) + 8 * br;
             atomicAdd(q + 0, (unsigned long long)(clock64() - t0));
             atomicAdd(q + 1, (unsigned long long)t_full);
             atomicAdd(q + 2, (unsigned long long)t_drained);
@@ -640,7 +834,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         for (int c = 0; c < nchunks; ++c) {
             if (lane == 0) mbar_wait(done, (unsigned)c & 1u);
             __syncwarp();
-            const long long tw = p.prof ? clock64() : 0;
+            const long long tw = PROF(p) ? clock64() : 0;
             tc_fence_after();
             const bool last = c == nchunks - 1;
             for (int c0 = 0; c0 < Hn; c0 += 32) {
@@ -681,9 +875,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 if (PAIR && !leader) mbar_arrive_remote(drained, 0u);
                 else mbar_arrive(drained);
             }
-            if (p.prof) t_drain += clock64() - tw;
+            if (PROF(p)) t_drain += clock64() - tw;
         }
-        if (p.prof && warp == K1_W_DRAIN && lane == 0) atomicAdd(p.prof + 8 * br + 6, (unsigned long long)t_drain);
+        if (PROF(p) && warp == K1_W_DRAIN && lane == 0) atomicAdd(PROF(p) + 8 * br + 6, (unsigned long long)t_drain);
     }
     tc_fence_before();
     __syncthreads();
@@ -989,8 +1183,8 @@ unsigned long long* phx_tc_prof_buffer() {
         const char* e = getenv("PHX_TC_PROF");
         on = (e && atoi(e)) ? 1 : 0;
         if (on) {
-            cudaMalloc((void**)&g_prof, 16 * sizeof(unsigned long long));
-            cudaMemset(g_prof, 0, 16 * sizeof(unsigned long long));
+            cudaMalloc((void**)&g_prof, 32 * sizeof(unsigned long long));
+            cudaMemset(g_prof, 0, 32 * sizeof(unsigned long long));
         }
     }
     return g_prof;
@@ -1008,6 +1202,35 @@ int uv_fused() {
 
 // EXPERIMENTAL, off by default (PHX_TC_PAIR=1 or phx_tc_set_pair): the branch-type contractions as CTA pairs (tcgen05
 // cta_group::2).  Bit-identical results; measured SLOWER on B200 than the single-CTA kernel.
+// A operand of the branch-type contractions in tensor memory (tc_branch_kernel<.., TS = 1>): default on, PHX_TC_TS=0 keeps
+// the shared-memory A tiles (bit-identical results either way: same operands, same MMA order).
+int ts_mode() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("PHX_TC_TS");
+        v = e ? atoi(e) : 1;
+    }
+    return v;
+}
+// columns of the A ring in tensor memory: the spare columns behind the chunk accumulator [0, Hn) and behind the running sum
+// [256, 256 + Hn); a stage is 16 (hi) + 16 (lo) columns.  Returns the ring depth (0: no room, use the TS = 0 kernel).
+int ts_plan(int Hn, int (&hi)[4], int (&lo)[4]) {
+    const int W = 256 - Hn, n1 = W / 32;
+    int n = 0;
+    for (int r = 0; r < 2; ++r)
+        for (int i = 0; i < n1 && n < 4; ++i) {
+            hi[n] = r * 256 + Hn + 32 * i;
+            lo[n] = hi[n] + 16;
+            ++n;
+        }
+    if (W % 32 >= 16 && n < 4) {
+        hi[n] = Hn + 32 * n1;
+        lo[n] = 256 + Hn + 32 * n1;
+        ++n;
+    }
+    return n >= 2 ? n : 0;
+}
+
 int g_pair = -1;
 int pair_mode() {
     if (g_pair < 0) {
@@ -1059,14 +1282,18 @@ TcScratch carve(int G, int H, int B, float* tcws) {
 void set_attrs() {
     static bool done = false;
     if (done) return;
-    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
-    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 0, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<0, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_branch_kernel<1, 1, 0, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
@@ -1108,7 +1335,9 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
 #endif
     bp.y = src; bp.w1img = bimg; bp.spart = spart;
     bp.prof = phx_tc_prof_buffer();
-    const size_t stage1 = K1_A_BYTES + (size_t)2 * Hb * BK * 4;
+    bp.a_stages = (!pair && ts_mode()) ? ts_plan(Hn, bp.a_hi_col, bp.a_lo_col) : 0;
+    const int ts = bp.a_stages > 0;
+    const size_t stage1 = (ts ? 0 : K1_A_BYTES) + (size_t)2 * Hb * BK * 4;
     const size_t staging = trans ? 0 : (size_t)K1_PWARPS * 2 * 8 * (K1_PF * BK + 4) * sizeof(float);
     int S1 = (int)((PHX_SMEM_LIMIT - 256 - staging) / stage1);
     if (S1 > 6) S1 = 6;
@@ -1125,12 +1354,20 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     const size_t smem1 = (size_t)S1 * stage1 + 256 + staging;
     if (!pair) {
         const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
-        if (!trans) {
-            if (mode == 0) tc_branch_kernel<0, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
-            else tc_branch_kernel<1, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+        if (ts) {
+            if (!trans) {
+                if (mode == 0) tc_branch_kernel<0, 0, 0, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+                else tc_branch_kernel<1, 0, 0, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            } else {
+                if (mode == 0) tc_branch_kernel<0, 1, 0, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+                else tc_branch_kernel<1, 1, 0, 1><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            }
+        } else if (!trans) {
+            if (mode == 0) tc_branch_kernel<0, 0, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            else tc_branch_kernel<1, 0, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
         } else {
-            if (mode == 0) tc_branch_kernel<0, 1, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
-            else tc_branch_kernel<1, 1, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            if (mode == 0) tc_branch_kernel<0, 1, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
+            else tc_branch_kernel<1, 1, 0, 0><<<grid1, K1_THREADS, smem1, st>>>(bp);
         }
         return PHX_OK;
     }
@@ -1149,11 +1386,11 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     cfg.numAttrs = 1;
     cudaError_t e;
     if (!trans) {
-        e = mode == 0 ? cudaLaunchKernelEx(&cfg, tc_branch_kernel<0, 0, 1>, bp)
-                      : cudaLaunchKernelEx(&cfg, tc_branch_kernel<1, 0, 1>, bp);
+        e = mode == 0 ? cudaLaunchKernelEx(&cfg, tc_branch_kernel<0, 0, 1, 0>, bp)
+                      : cudaLaunchKernelEx(&cfg, tc_branch_kernel<1, 0, 1, 0>, bp);
     } else {
-        e = mode == 0 ? cudaLaunchKernelEx(&cfg, tc_branch_kernel<0, 1, 1>, bp)
-                      : cudaLaunchKernelEx(&cfg, tc_branch_kernel<1, 1, 1>, bp);
+        e = mode == 0 ? cudaLaunchKernelEx(&cfg, tc_branch_kernel<0, 1, 1, 0>, bp)
+                      : cudaLaunchKernelEx(&cfg, tc_branch_kernel<1, 1, 1, 0>, bp);
     }
     if (e != cudaSuccess) {
         phx_set_error("tc branch pair launch: %s", cudaGetErrorString(e));
@@ -1297,7 +1534,7 @@ extern "C" void phx_tc_set_pair(int on) { g_pair = on ? 1 : 0; }
 
 extern "C" void phx_tc_prof_dump(void) {
     if (!g_prof) return;
-    unsigned long long h[16];
+    unsigned long long h[32];
     cudaMemcpy(h, g_prof, sizeof(h), cudaMemcpyDeviceToHost);
     cudaMemset(g_prof, 0, sizeof(h));
     for (int br = 0; br < 2; ++br) {
@@ -1306,5 +1543,8 @@ extern "C" void phx_tc_prof_dump(void) {
         printf("tc_branch %s: k-blocks %llu | MMA thread cycles/k-block: total %.0f wait_full %.0f wait_drained %.0f | "
                "producer warp 0: total %.0f wait_empty %.0f drain %.0f\n",
                br ? "prods" : "sums", q[3], q[0] / n, q[1] / n, q[2] / n, q[4] / n, q[5] / n, q[6] / n);
+        const unsigned long long* r = h + 16 + 8 * br;
+        printf("          producer warp 0 phases / k-block: load+stage %.0f  convert %.0f  store+signal %.0f\n", r[0] / n,
+               r[1] / n, r[2] / n);
     }
 }

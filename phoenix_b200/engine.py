@@ -347,6 +347,20 @@ def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True, flat=False):
     return ybar, (split_flat_grads(grads, G, H) if need_grads else None)
 
 
+# net id -> callable(P) returning a [P] float32 tensor on the model's device for the flat parameter cotangents, or None
+# (parallel.enable_peer_allreduce: the adjoint writes straight into the peer-mapped buffer the collective works on)
+_flat_alloc = {}
+
+
+def new_flat_grads(net, P, device):
+    hook = _flat_alloc.get(id(net))
+    if hook is not None:
+        t = hook(P)
+        if t is not None:
+            return t
+    return torch.empty(P, dtype=torch.float32, device=device)
+
+
 def split_flat_grads(flat, G, H):
     """Views of the flat cotangent vector in the reference parameter order and shapes."""
     o, out = 0, []
@@ -438,7 +452,7 @@ def _adjoint_rows(lib, net, packed, G, H, dev, t_rows, t_is_f32, method, rtol, a
     parts = lib.phx_rows_grad_parts(ctx, G, H, N)
     gpk = _workspace(dev, parts * lib.phx_packed_grad_bytes(G, H), "gradparts")
     P = 4 * G * H + 2 * H + G
-    flat = torch.empty(P, dtype=torch.float32, device=ys.device)
+    flat = new_flat_grads(net, P, ys.device)
     stn = _new_status_block(N)
     log, cap = _steplog_rows(N)
     flat_t = (ctypes.c_double * (N * T))(*[x for r in t_rows for x in r])

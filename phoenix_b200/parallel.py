@@ -79,6 +79,9 @@ def allreduce_grads(net, group=None, average=True, extra=None):
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size(group) == 1:
         return extra
     world = dist.get_world_size(group)
+    pr = _peer.get(id(net))
+    if pr is not None:
+        return _peer_allreduce_grads(net, pr, average, extra)
     flat = flat_grad_view(net)
     if flat is not None:
         work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group, async_op=extra is not None)
@@ -102,6 +105,108 @@ def allreduce_grads(net, group=None, average=True, extra=None):
         flat /= world
     adopt_flat_grads_(net, flat[:n])
     return flat[n:].view_as(extra) if extra is not None else None
+
+
+# ---- gradient all-reduce over peer memory (csrc/phx_peer.cu) -----------------------------------------------------------------
+class PeerAllReduce:
+    """In-place sum of a flat float32 vector over the GPUs of one NVSwitch box through peer memory: ONE kernel per rank
+    (``phx_peer_allreduce``: reduce-scatter by slices with remote loads, all-gather with remote stores, rank-ordered sums,
+    bit-identical results on every rank), no NCCL call on the data path.  torch symmetric memory only provides the
+    peer-mapped allocation and the pointer exchange.  ``buffer`` is this rank's vector (``numel`` floats): write the local
+    gradient into it, call ``reduce()``; afterwards it holds ``scale * sum``."""
+
+    def __init__(self, numel, device=None, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import _lib
+        self.group = dist.group.WORLD if group is None else group
+        self.world, self.rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if self.world not in (2, 4, 8):
+            raise NotImplementedError("peer all-reduce: 2, 4 or 8 ranks (got %d)" % self.world)
+        self.dev = torch.cuda.current_device() if device is None else torch.device(device).index
+        d = torch.device("cuda", self.dev)
+        self.numel = int(numel)
+        self.buffer = symm_mem.empty((self.numel + 3) // 4 * 4, dtype=torch.float32, device=d)
+        self.flags = symm_mem.empty(64, dtype=torch.int32, device=d)
+        self.flags.zero_()
+        self.buffer.zero_()
+        hb = symm_mem.rendezvous(self.buffer, self.group)
+        hf = symm_mem.rendezvous(self.flags, self.group)
+        import ctypes
+        self._bufs = (ctypes.c_void_p * self.world)(*[int(x) for x in hb.buffer_ptrs])
+        self._flags = (ctypes.c_void_p * self.world)(*[int(x) for x in hf.buffer_ptrs])
+        self._handles = (hb, hf)
+        self.epoch = 0
+        self._lib, self._ctx = _lib.load(), _lib.ctx(self.dev)
+        self._check = _lib.check
+        torch.cuda.synchronize(d)
+        dist.barrier(group=self.group)      # every rank's flag pad is zero before anyone signals
+
+    def reduce(self, scale=1.0, numel=None):
+        self.epoch += 1
+        n = self.numel if numel is None else int(numel)
+        self._check(self._lib.phx_peer_allreduce(self._ctx, self._bufs, self._flags, self.rank, self.world, n,
+                                                 self.epoch & 0x7fffffff, float(scale),
+                                                 engine._stream_ptr(self.dev)), "peer_allreduce")
+        return self.buffer[:n]
+
+
+_peer = {}
+
+
+def enable_peer_allreduce(net, group=None):
+    """Route ``allreduce_grads(net)`` through ``PeerAllReduce`` (one peer-memory kernel instead of an NCCL all-reduce).
+    Collective: call on every rank.  Returns the PeerAllReduce object (``.buffer`` can be written directly)."""
+    params = engine.net_params(net)
+    P = sum(p.numel() for p in params)
+    pr = PeerAllReduce(P + 64, device=params[0].device, group=group)     # 64 spare floats for the `extra` scalars
+    _peer[id(net)] = pr
+    base = pr.buffer.untyped_storage().data_ptr()
+
+    def alloc(n):
+        # the adjoint kernels write the flat gradient straight into the peer-mapped buffer -- unless a .grad of an earlier
+        # backward still lives there (gradient accumulation over several backward calls)
+        for p in params:
+            if p.grad is not None and p.grad.untyped_storage().data_ptr() == base:
+                return None
+        return pr.buffer[:n] if n == P else None
+
+    engine._flat_alloc[id(net)] = alloc
+    return pr
+
+
+def disable_peer_allreduce(net):
+    _peer.pop(id(net), None)
+    engine._flat_alloc.pop(id(net), None)
+
+
+def _peer_allreduce_grads(net, pr, average, extra):
+    params = engine.net_params(net)
+    P = sum(p.numel() for p in params)
+    flat = flat_grad_view(net)
+    buf = pr.buffer
+    in_place = flat is not None and flat.data_ptr() == buf.data_ptr()
+    if not in_place:
+        if flat is not None:
+            buf[:P].copy_(flat)
+        else:   # gradients in several storages (some may already sit at their place in the peer buffer)
+            o = 0
+            for p in params:
+                k = p.numel()
+                if p.grad is None:
+                    buf[o:o + k].zero_()
+                elif p.grad.data_ptr() != buf.data_ptr() + 4 * o:
+                    buf[o:o + k].copy_(p.grad.reshape(-1))
+                o += k
+    n = P
+    if extra is not None:
+        if extra.numel() > 64:
+            raise ValueError("allreduce_grads: at most 64 extra scalars ride with the gradient")
+        buf[P:P + extra.numel()].copy_(extra.reshape(-1))
+        n = P + extra.numel()
+    pr.reduce(scale=(1.0 / pr.world) if average else 1.0, numel=n)
+    if not in_place:
+        adopt_flat_grads_(net, buf[:P])
+    return buf[P:n].clone().view_as(extra) if extra is not None else None
 
 
 def broadcast_parameters(net, src=0, group=None):

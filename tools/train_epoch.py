@@ -32,7 +32,7 @@ CONFIGS = {
 }
 
 
-def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True):
+def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True, fused_adam=True, peer=True):
     """Time `epochs` epochs of the reference's training loop on this rank's share (call under torchrun for N > 1; the
     process group must already exist).  Returns the dict that main() prints (rank 0) or None."""
     import torch.distributed as dist
@@ -50,7 +50,12 @@ def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True):
         {'params': odenet.net_sums.linear_out.weight}, {'params': odenet.net_sums.linear_out.bias},
         {'params': odenet.net_prods.linear_out.weight}, {'params': odenet.net_prods.linear_out.bias},
         {'params': odenet.net_alpha_combine.linear_out.weight},
-        {'params': odenet.gene_multipliers, 'lr': 5 * 1e-3}], lr=1e-3, weight_decay=0.0)
+        {'params': odenet.gene_multipliers, 'lr': 5 * 1e-3}], lr=1e-3, weight_decay=0.0,
+        # the reference constructs optim.Adam(...) with defaults (train_insilico.py:245-253: the for-each implementation,
+        # 42 launches per step over the six groups); fused=True is the same update as 6 launches
+        **({"fused": True} if fused_adam else {}))
+    if world > 1 and peer:   # gradient sum over NVLink peer memory (one kernel per rank) instead of an NCCL all-reduce
+        parallel.enable_peer_allreduce(odenet)
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     lo, hi = parallel.shard_range(batch, rank, world)
     klo, khi = parallel.shard_range(K, rank, world)
@@ -128,6 +133,8 @@ def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True):
             "batch_size": batch, "steps_per_epoch": steps, "method": method, "prior_rows": K,
             "sample_loop": "odeint_adjoint_many" if many else "per-sample odeint_adjoint",
             "prior_term": "phoenix_b200.prior_loss (fused)" if fused_prior else "prior_only_forward + torch ops",
+            "optimizer": "torch.optim.Adam(fused=True)" if fused_adam else "torch.optim.Adam (for-each, the default)",
+            "grad_allreduce": None if world == 1 else ("phx_peer_allreduce" if peer else "NCCL"),
             "epoch_s": best, "ms_per_step": 1e3 * best / steps,
             "phase_share": {k: v / tot for k, v in ph.items()} if instrument else None,
             "loss_data": float(ld), "loss_prior": float(lp)}
@@ -139,6 +146,8 @@ def main():
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--many", action="store_true", help="sample loop inside the library (odeint_adjoint_many)")
     ap.add_argument("--unfused-prior", action="store_true", help="the reference's two prior-loss lines as they are")
+    ap.add_argument("--foreach-adam", action="store_true", help="torch.optim.Adam with its defaults, as the reference builds it")
+    ap.add_argument("--nccl", action="store_true", help="NCCL all-reduce of the gradients instead of the peer-memory kernel")
     a = ap.parse_args()
     import torch.distributed as dist
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -146,7 +155,8 @@ def main():
     dev = torch.device("cuda", torch.cuda.current_device())
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    out = run_epochs(a.config, a.epochs, a.many, fused_prior=not a.unfused_prior)
+    out = run_epochs(a.config, a.epochs, a.many, fused_prior=not a.unfused_prior, fused_adam=not a.foreach_adam,
+                     peer=not a.nccl)
     if out is not None:
         print(json.dumps(out), flush=True)
     if world > 1:
