@@ -21,10 +21,12 @@ def main():
     dist.init_process_group("nccl", device_id=dev)
     G, H = 11165, 200
     P = 4 * G * H + 2 * H + G          # 8 943 565 floats: not a multiple of 4 -> exercises the tail path
-    pr = parallel.PeerAllReduce(P, device=dev)
+    pr = parallel.PeerAllReduce(P, device=dev, nvls=False)
+    has_mc = pr._mc != 0
     ok = True
     outs = []
-    for rep in range(3):
+    for rep in range(5 if has_mc else 3):
+        pr.nvls = rep >= 3          # the last two rounds: sums formed inside the NVSwitch (multimem)
         torch.manual_seed(100 * rep + rank)
         x = torch.randn(P, device=dev)
         ref = x.clone()
@@ -39,9 +41,16 @@ def main():
         dist.all_gather(gathered, out)
         ok = ok and all(torch.equal(g, gathered[0]) for g in gathered)      # bit-identical on every rank
         outs.append((x, out))
+    pr.nvls = False
     x, out = outs[0]
     pr.buffer[:P].copy_(x)
     ok = ok and torch.equal(pr.reduce().clone(), out)                        # deterministic
+    if has_mc:
+        pr.nvls = True
+        x, out = outs[3]
+        pr.buffer[:P].copy_(x)
+        ok = ok and torch.equal(pr.reduce().clone(), out)
+        pr.nvls = False
     # timing: device time of one collective, max over ranks
     def timed(fn, n=20):
         for _ in range(3):
@@ -60,12 +69,17 @@ def main():
     y = torch.randn(P, device=dev)
     t_nccl = timed(lambda: dist.all_reduce(y))
     t_peer = timed(lambda: pr.reduce())
+    t_nvls = float("nan")
+    if has_mc:
+        pr.nvls = True
+        t_nvls = timed(lambda: pr.reduce())
     flag = torch.tensor([int(ok)], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         print("peer all-reduce, %d ranks, %d floats (%.1f MB): max rel. error vs NCCL < 1e-6, bit-identical across ranks, "
-              "deterministic: %s | device time per call: peer kernel %.1f us, NCCL all_reduce %.1f us  ->  %s" % (
-                  world, P, P * 4 / 1e6, bool(int(flag)), 1e3 * t_peer, 1e3 * t_nccl, "PASS" if int(flag) else "FAIL"),
+              "deterministic: %s | device time per call: peer kernel %.1f us, NVLS (multimem) kernel %.1f us, NCCL all_reduce "
+              "%.1f us  ->  %s" % (world, P, P * 4 / 1e6, bool(int(flag)), 1e3 * t_peer, 1e3 * t_nvls, 1e3 * t_nccl,
+                                   "PASS" if int(flag) else "FAIL"),
               flush=True)
     dist.barrier()
     dist.destroy_process_group()
