@@ -254,6 +254,10 @@ int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int 
  * asynchronous on `stream`; all ranks must make it (it spins on the peers' flags). */
 int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* flags, int rank, int world, size_t n,
                        unsigned epoch, float scale, void* stream);
+/* The same with the sums formed inside the NVSwitch (NVLS: multimem.ld_reduce / multimem.st): multicast_buf is the
+ * multicast address of the W gradient buffers (cuMulticast* / torch symmetric memory `multicast_ptr`). */
+int phx_peer_allreduce_nvls(phx_ctx* ctx, void* multicast_buf, void* const* flags, int rank, int world, size_t n,
+                            unsigned epoch, float scale, void* stream);
 
 #ifdef __cplusplus
 }

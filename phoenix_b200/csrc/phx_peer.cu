@@ -120,13 +120,69 @@ __global__ void __launch_bounds__(PEER_THREADS, 1) peer_allreduce_kernel(const P
     }
 }
 
+// The same collective with the reduction done INSIDE the NVSwitch (NVLS): `mc` is the multicast address of the buffers
+// (one address that stands for the same offset in every rank's buffer).  multimem.ld_reduce returns the sum over all
+// ranks of an element in ONE load (the switch pulls and adds), multimem.st writes the result to every rank in ONE store:
+// per GPU and direction the links carry about (W-1)/W n + n/W floats instead of 2 (W-1)/W n.
+template <int W>
+__global__ void __launch_bounds__(PEER_THREADS, 1) peer_allreduce_nvls_kernel(const PeerParams p, float* mc) {
+    if (blockIdx.x == 0 && threadIdx.x < W) st_release_sys(p.flag[threadIdx.x] + p.rank, p.epoch);
+    if (threadIdx.x < W)
+        while (!epoch_reached(ld_acquire_sys(p.flag[p.rank] + threadIdx.x), p.epoch)) {}
+    __syncthreads();
+    const unsigned long long n4 = p.n >> 2, per = (n4 + W - 1) / W;
+    const unsigned long long lo = per * (unsigned long long)p.rank, hi = lo + per < n4 ? lo + per : n4;
+    constexpr int U = 4;
+    const unsigned long long stride = (unsigned long long)gridDim.x * blockDim.x;
+    for (unsigned long long i0 = lo + (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < hi; i0 += U * stride) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned long long i = i0 + u * stride;
+            if (i < hi)
+                asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0,%1,%2,%3}, [%4];"
+                             : "=f"(v[u].x), "=f"(v[u].y), "=f"(v[u].z), "=f"(v[u].w)
+                             : "l"(mc + 4 * i)
+                             : "memory");
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const unsigned long long i = i0 + u * stride;
+            if (i < hi)
+                asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(mc + 4 * i),
+                             "f"(v[u].x * p.scale), "f"(v[u].y * p.scale), "f"(v[u].z * p.scale), "f"(v[u].w * p.scale)
+                             : "memory");
+        }
+    }
+    if (p.rank == W - 1 && blockIdx.x == 0 && threadIdx.x < (unsigned)(p.n & 3)) {
+        const unsigned long long i = (n4 << 2) + threadIdx.x;
+        float a;
+        asm volatile("multimem.ld_reduce.relaxed.sys.global.add.f32 %0, [%1];" : "=f"(a) : "l"(mc + i) : "memory");
+        asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc + i), "f"(a * p.scale) : "memory");
+    }
+    __threadfence_system();
+    __syncthreads();
+    __shared__ unsigned last;
+    if (threadIdx.x == 0) {
+        const unsigned ticket = atomicAdd(p.counter, 1u);
+        last = ticket == gridDim.x - 1;
+        if (last) *p.counter = 0u;
+    }
+    __syncthreads();
+    if (last && threadIdx.x < W) {
+        __threadfence_system();
+        st_release_sys(p.flag[threadIdx.x] + W + p.rank, p.epoch);
+        while (!epoch_reached(ld_acquire_sys(p.flag[p.rank] + W + threadIdx.x), p.epoch)) {}
+    }
+}
+
 unsigned* g_counter[16] = {};
 
 }  // namespace
 
-extern "C" int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* flags, int rank, int world, size_t n,
-                                  unsigned epoch, float scale, void* stream) {
-    if (!ctx || !bufs || !flags || world < 2 || world > PEER_MAXW || (world & (world - 1)) || rank < 0 || rank >= world) {
+static int peer_allreduce_impl(phx_ctx* ctx, void* const* bufs, void* multicast, void* const* flags, int rank, int world,
+                              size_t n, unsigned epoch, float scale, void* stream) {
+    if (!ctx || !flags || world < 2 || world > PEER_MAXW || (world & (world - 1)) || rank < 0 || rank >= world) {
         phx_set_error("peer all-reduce: world size must be 2, 4 or 8 and 0 <= rank < world (got rank %d of %d)", rank,
                       world);
         return PHX_ERR_INVALID;
@@ -134,7 +190,21 @@ extern "C" int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* 
     PhxDevGuard dev_guard(ctx);
     const int dev = phx_ctx_device(ctx);
     PeerParams p;
+    if (multicast && ((uintptr_t)multicast & 15)) {
+        phx_set_error("peer all-reduce: multicast address is not 16-byte aligned");
+        return PHX_ERR_INVALID;
+    }
     for (int r = 0; r < world; ++r) {
+        if (!multicast && !bufs) {
+            phx_set_error("peer all-reduce: null buffer list");
+            return PHX_ERR_INVALID;
+        }
+        if (multicast) {
+            if (!flags[r]) return PHX_ERR_INVALID;
+            p.buf[r] = nullptr;
+            p.flag[r] = (unsigned*)flags[r];
+            continue;
+        }
         if (!bufs[r] || !flags[r] || ((uintptr_t)bufs[r] & 15)) {
             phx_set_error("peer all-reduce: buffer %d is null or not 16-byte aligned", r);
             return PHX_ERR_INVALID;
@@ -154,7 +224,12 @@ extern "C" int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* 
     // every block must be resident (blocks spin on the peers' flags): one 1024-thread block per SM
     const int grid = phx_ctx_num_sms(ctx);
     cudaStream_t st = (cudaStream_t)stream;
-    if (world == 2) peer_allreduce_kernel<2><<<grid, PEER_THREADS, 0, st>>>(p);
+    if (multicast) {
+        float* mc = (float*)multicast;
+        if (world == 2) peer_allreduce_nvls_kernel<2><<<grid, PEER_THREADS, 0, st>>>(p, mc);
+        else if (world == 4) peer_allreduce_nvls_kernel<4><<<grid, PEER_THREADS, 0, st>>>(p, mc);
+        else peer_allreduce_nvls_kernel<8><<<grid, PEER_THREADS, 0, st>>>(p, mc);
+    } else if (world == 2) peer_allreduce_kernel<2><<<grid, PEER_THREADS, 0, st>>>(p);
     else if (world == 4) peer_allreduce_kernel<4><<<grid, PEER_THREADS, 0, st>>>(p);
     else peer_allreduce_kernel<8><<<grid, PEER_THREADS, 0, st>>>(p);
     cudaError_t e = cudaGetLastError();
@@ -163,4 +238,17 @@ extern "C" int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* 
         return PHX_ERR_CUDA;
     }
     return PHX_OK;
+}
+
+extern "C" int phx_peer_allreduce(phx_ctx* ctx, void* const* bufs, void* const* flags, int rank, int world, size_t n,
+                                  unsigned epoch, float scale, void* stream) {
+    return peer_allreduce_impl(ctx, bufs, nullptr, flags, rank, world, n, epoch, scale, stream);
+}
+extern "C" int phx_peer_allreduce_nvls(phx_ctx* ctx, void* multicast_buf, void* const* flags, int rank, int world,
+                                       size_t n, unsigned epoch, float scale, void* stream) {
+    if (!multicast_buf) {
+        phx_set_error("peer all-reduce (NVLS): null multicast address");
+        return PHX_ERR_INVALID;
+    }
+    return peer_allreduce_impl(ctx, nullptr, multicast_buf, flags, rank, world, n, epoch, scale, stream);
 }

@@ -115,7 +115,7 @@ class PeerAllReduce:
     peer-mapped allocation and the pointer exchange.  ``buffer`` is this rank's vector (``numel`` floats): write the local
     gradient into it, call ``reduce()``; afterwards it holds ``scale * sum``."""
 
-    def __init__(self, numel, device=None, group=None):
+    def __init__(self, numel, device=None, group=None, nvls=None):
         import torch.distributed._symmetric_memory as symm_mem
         from . import _lib
         self.group = dist.group.WORLD if group is None else group
@@ -135,6 +135,17 @@ class PeerAllReduce:
         self._bufs = (ctypes.c_void_p * self.world)(*[int(x) for x in hb.buffer_ptrs])
         self._flags = (ctypes.c_void_p * self.world)(*[int(x) for x in hf.buffer_ptrs])
         self._handles = (hb, hf)
+        # NVLS (sums formed inside the NVSwitch, phx_peer_allreduce_nvls) when the buffer has a multicast address:
+        # nvls=None -> PHX_PEER_NVLS (default: on from 4 ranks), True / False force it
+        try:
+            self._mc = int(hb.multicast_ptr or 0)
+        except Exception:   # no multicast support on this box / torch build
+            self._mc = 0
+        if nvls is None:
+            import os
+            env = os.environ.get("PHX_PEER_NVLS")
+            nvls = (self.world >= 4) if env is None else bool(int(env))
+        self.nvls = bool(nvls) and self._mc != 0
         self.epoch = 0
         self._lib, self._ctx = _lib.load(), _lib.ctx(self.dev)
         self._check = _lib.check
@@ -144,9 +155,14 @@ class PeerAllReduce:
     def reduce(self, scale=1.0, numel=None):
         self.epoch += 1
         n = self.numel if numel is None else int(numel)
-        self._check(self._lib.phx_peer_allreduce(self._ctx, self._bufs, self._flags, self.rank, self.world, n,
-                                                 self.epoch & 0x7fffffff, float(scale),
-                                                 engine._stream_ptr(self.dev)), "peer_allreduce")
+        if self.nvls:
+            self._check(self._lib.phx_peer_allreduce_nvls(self._ctx, self._mc, self._flags, self.rank, self.world, n,
+                                                          self.epoch & 0x7fffffff, float(scale),
+                                                          engine._stream_ptr(self.dev)), "peer_allreduce_nvls")
+        else:
+            self._check(self._lib.phx_peer_allreduce(self._ctx, self._bufs, self._flags, self.rank, self.world, n,
+                                                     self.epoch & 0x7fffffff, float(scale),
+                                                     engine._stream_ptr(self.dev)), "peer_allreduce")
         return self.buffer[:n]
 
 
