@@ -39,5 +39,49 @@ def main():
     pb.check_errors()
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and not (len(sys.argv) > 1 and sys.argv[1] == "single"):
     main()
+
+
+def single_call_engines():
+    """Device-limited time of ONE-sample calls (the literal loop of train_insilico.py:128-130): 20 calls enqueued back to back,
+    rows kernels against the one-problem resident kernels."""
+    from phoenix_b200 import engine
+    G, H, dt = 11165, 200, 0.0051
+    net = pb.ODENet("cuda:0", G, neurons=H)
+    pb.set_sync_errors(False)
+    t = torch.tensor([0.0, dt])
+    y0 = torch.rand(1, G, device="cuda")
+    res = {}
+    for eng in ("rows", "resident"):
+        engine.FORCE_ENGINE = eng
+        outs = None
+        for rep in range(3):
+            ys = [y0.clone().requires_grad_(True) for _ in range(20)]
+            a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+            torch.cuda.synchronize()
+            a.record()
+            outs = [pb.odeint_adjoint(net, y, t, method="dopri5") for y in ys]
+            b.record()
+            loss = sum((o[1] ** 2).mean() for o in outs)
+            torch.cuda.synchronize()
+            b2 = torch.cuda.Event(enable_timing=True)
+            b2.record()
+            loss.backward()
+            c.record()
+            torch.cuda.synchronize()
+        res[eng] = (outs[0].detach().clone(), net.net_sums.linear_out.weight.grad.clone())
+        net.zero_grad()
+        print("engine %-8s one-sample calls: forward %.1f us / call, backward %.1f us / call" % (
+            eng, 1e3 * a.elapsed_time(b) / 20, 1e3 * b2.elapsed_time(c) / 20), flush=True)
+    engine.FORCE_ENGINE = None
+    y_r, g_r = res["rows"]
+    y_s, g_s = res["resident"]
+    print("rows vs resident: y identical %s (rel %.2e), grad identical %s (rel %.2e)" % (
+        torch.equal(y_r, y_s), float((y_r - y_s).norm() / y_s.norm()), torch.equal(g_r, g_s),
+        float((g_r - g_s).norm() / g_s.norm())))
+    pb.check_errors()
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "single":
+    single_call_engines()
