@@ -351,6 +351,7 @@ struct BranchParams {
     const float* w1img;
     float* spart;         // [slot][Bpad][2*Hn]; sums branch uses slots < ks_s, prods branch slots < ks_p
     unsigned long long* prof;   // optional cycle counters (PHX_TC_PROF): see tools/tc_check.py
+    unsigned stg_bytes;         // bytes of the producers' staging area (the TS running sum sits behind it)
     int a_stages;               // TS = 1: depth of the A ring in tensor memory and the columns of its hi / lo tiles
     int a_hi_col[4], a_lo_col[4];
 };
@@ -437,10 +438,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
     constexpr unsigned A_SMEM = TS ? 0u : K1_A_BYTES;   // bytes of the A tiles inside a shared-memory stage
     const unsigned stage_bytes = A_SMEM + b_bytes;
     unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + (size_t)S * stage_bytes);
+    // done / drained: one barrier each, or (TS) one pair per chunk accumulator: chunk c lives in accumulator c & 1
     const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + S), done = smem_u32(bars + 2 * S),
-                   drained = smem_u32(bars + 2 * S + 1);
-    const unsigned fullA0 = smem_u32(bars + 2 * S + 2), emptyA0 = smem_u32(bars + 2 * S + 6);   // TS: A ring, <= 4 stages
-    unsigned* slot = reinterpret_cast<unsigned*>(bars + 2 * S + 10);
+                   drained = smem_u32(bars + 2 * S + 2);
+    const unsigned fullA0 = smem_u32(bars + 2 * S + 4), emptyA0 = smem_u32(bars + 2 * S + 8);   // TS: A ring, <= 4 stages
+    unsigned* slot = reinterpret_cast<unsigned*>(bars + 2 * S + 12);
     const unsigned stage0 = smem_u32(smem);
     const int SA = TS ? p.a_stages : S;
 
@@ -458,6 +460,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             }
         mbar_init(done, 1);
         mbar_init(drained, PAIR ? 2 * K1_DWARPS : K1_DWARPS);
+        if (TS) {
+            mbar_init(done + 8, 1);
+            mbar_init(drained + 8, K1_DWARPS);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == K1_W_BULK) {
@@ -468,7 +474,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
     __syncthreads();
     if (PAIR) cluster_sync_all();   // both CTAs' barriers exist before any remote arrive / multicast commit
     tc_fence_after();
-    const unsigned tmem = *slot;   // chunk accumulator: columns [0, Hn); running sum: columns [256, 256 + Hn)
+    // TS = 0: chunk accumulator in columns [0, Hn), running sum in [256, 256 + Hn).  TS = 1: TWO chunk accumulators
+    // (columns [0, Hn) and [256, 256 + Hn), chunk c in accumulator c & 1) and the running sum in shared memory, so the
+    // fold of chunk c overlaps the MMAs of chunk c + 1.
+    const unsigned tmem = *slot;
 
     if (warp < K1_PWARPS) {
         // ---- producers: Hill activation of this CTA's 128 x 16 slab of y, hi/lo split, core-matrix layout ----
@@ -496,8 +505,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         // (w & 3) == quarter: warp (quarter, j) loads rows 8j .. 8j+7 of the quarter and reads row `lane`, k-chunk j;
         // the hand-over is a 128-thread named barrier instead of __syncwarp.
         float* stg = reinterpret_cast<float*>(smem + (size_t)S * stage_bytes + 256) +
-                     (TS ? (size_t)(warp & 3) * 2 * 32 * SROW : (size_t)warp * 2 * 8 * SROW);
+                     (TS ? (size_t)(warp & 3) * 32 * SROW : (size_t)warp * 2 * 8 * SROW);
         constexpr int SBUF = (TS ? 32 : 8) * SROW;                  // floats of one staging buffer
+        constexpr int NSBUF = TS ? 1 : 2;                           // TS: single-buffered (the running sum needs the room)
         const int srow0 = TS ? (warp >> 2) * 8 : 0;                 // first staging row this warp fills
         const int srd = TS ? lane : (lane & 7);                     // staging row this thread reads
         auto stage_sync = [&]() {
@@ -661,8 +671,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
             } else if (i0 + K1_PF < nkb) {
                 const long long tl1 = PROF(p) ? clock64() : 0;
-                sbuf ^= 1;
-                stage_put(sbuf, nxt);   // the other buffer: last read one super-block ago (ordered by the hand-over sync)
+                if (NSBUF == 2) sbuf ^= 1;   // the other buffer: last read one super-block ago (ordered by the hand-over sync)
+                else stage_sync();           // single buffer: every warp of the group has read this super-block
+                stage_put(sbuf, nxt);
                 stage_sync();
                 if (PROF(p)) t_load += clock64() - tl1;
             }
@@ -738,7 +749,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             }
         } else
         for (int i = 0; i < nkb; ++i) {
-            if (ic == 0 && c > 0) {   // the previous chunk's sum must have left the chunk accumulator (both CTAs)
+            if (TS) {
+                if (ic == 0 && c >= 2) {   // chunk c - 2 must have left this accumulator
+                    const long long tw = PROF(p) ? clock64() : 0;
+                    mbar_wait(drained + 8 * (c & 1), (unsigned)((c >> 1) - 1) & 1u);
+                    if (PROF(p)) t_drained += clock64() - tw;
+                }
+            } else if (ic == 0 && c > 0) {   // the previous chunk's sum must have left the chunk accumulator (both CTAs)
                 const long long tw = PROF(p) ? clock64() : 0;
                 if (PAIR) mbar_wait_cluster(drained, (unsigned)(c - 1) & 1u);
                 else mbar_wait(drained, (unsigned)(c - 1) & 1u);
@@ -754,22 +771,23 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             if (TS) {
                 if (elect_one()) {
                     const unsigned ta_hi = tmem + (unsigned)p.a_hi_col[sa], ta_lo = tmem + (unsigned)p.a_lo_col[sa];
+                    const unsigned tacc = tmem + ((c & 1) ? 256u : 0u);
 #pragma unroll
                     for (int k8 = 0; k8 < BK / 8; ++k8) {
                         const uint64_t b_hi = desc_at(b_hi_part, b_base + k8 * p.b_kadv);
                         const uint64_t b_lo = desc_at(b_hi_part, b_base + b_tile + k8 * p.b_kadv);
                         const unsigned acc = (ic > 0 || k8 > 0) ? 1u : 0u;
                         if (p.nterms == 3) {
-                            mma_tf32_ts(tmem, ta_lo + 8u * k8, b_hi, idesc, acc);
-                            mma_tf32_ts(tmem, ta_hi + 8u * k8, b_lo, idesc, 1u);
-                            mma_tf32_ts(tmem, ta_hi + 8u * k8, b_hi, idesc, 1u);
+                            mma_tf32_ts(tacc, ta_lo + 8u * k8, b_hi, idesc, acc);
+                            mma_tf32_ts(tacc, ta_hi + 8u * k8, b_lo, idesc, 1u);
+                            mma_tf32_ts(tacc, ta_hi + 8u * k8, b_hi, idesc, 1u);
                         } else {
-                            mma_tf32_ts(tmem, ta_hi + 8u * k8, b_hi, idesc, acc);
+                            mma_tf32_ts(tacc, ta_hi + 8u * k8, b_hi, idesc, acc);
                         }
                     }
                     mma_commit(emptyA0 + 8 * sa);
                     mma_commit(empty0 + 8 * s);
-                    if (ic == p.chunk - 1 || i == nkb - 1) mma_commit(done);
+                    if (ic == p.chunk - 1 || i == nkb - 1) mma_commit(done + 8 * (c & 1));
                 }
                 if (++sa == SA) {
                     sa = 0;
@@ -831,6 +849,52 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         const unsigned trow = tmem + ((unsigned)(q * 32) << 16);
         float* dst = p.spart + ((size_t)ks * p.Bpad + (m0 + q * 32 + lane)) * (2 * Hn) + br * Hn;
         long long t_drain = 0;
+        // TS: running sum in shared memory as [column quad][row] float4 (consecutive lanes -> consecutive 16 bytes)
+        float4* rs = reinterpret_cast<float4*>(smem + (size_t)S * stage_bytes + 256 + p.stg_bytes) + (q * 32 + lane);
+        if (TS) {
+            for (int c = 0; c < nchunks; ++c) {
+                if (lane == 0) mbar_wait(done + 8 * (c & 1), (unsigned)(c >> 1) & 1u);
+                __syncwarp();
+                const long long tw = PROF(p) ? clock64() : 0;
+                tc_fence_after();
+                const bool last = c == nchunks - 1;
+                const unsigned tacc = trow + ((c & 1) ? 256u : 0u);
+                for (int c0 = 0; c0 < Hn; c0 += 32) {
+                    const bool two = c0 + 16 < Hn;
+                    unsigned v0[16], v1[16];
+                    tmem_ld16_nowait(tacc + c0, v0);
+                    if (two) tmem_ld16_nowait(tacc + c0 + 16, v1);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        float4 a = make_float4(__uint_as_float(v0[j]), __uint_as_float(v0[j + 1]), __uint_as_float(v0[j + 2]),
+                                               __uint_as_float(v0[j + 3]));
+                        float4* r = rs + (size_t)((c0 + j) >> 2) * 128;
+                        if (c > 0) {
+                            const float4 o = *r;
+                            a.x = o.x + a.x; a.y = o.y + a.y; a.z = o.z + a.z; a.w = o.w + a.w;
+                        }
+                        if (last) *reinterpret_cast<float4*>(dst + c0 + j) = a;
+                        else *r = a;
+                        if (two) {
+                            float4 b = make_float4(__uint_as_float(v1[j]), __uint_as_float(v1[j + 1]),
+                                                   __uint_as_float(v1[j + 2]), __uint_as_float(v1[j + 3]));
+                            float4* r1 = rs + (size_t)((c0 + 16 + j) >> 2) * 128;
+                            if (c > 0) {
+                                const float4 o = *r1;
+                                b.x = o.x + b.x; b.y = o.y + b.y; b.z = o.z + b.z; b.w = o.w + b.w;
+                            }
+                            if (last) *reinterpret_cast<float4*>(dst + c0 + 16 + j) = b;
+                            else *r1 = b;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(drained + 8 * (c & 1));
+                if (PROF(p)) t_drain += clock64() - tw;
+            }
+        } else
         for (int c = 0; c < nchunks; ++c) {
             if (lane == 0) mbar_wait(done, (unsigned)c & 1u);
             __syncwarp();
@@ -1336,10 +1400,23 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     bp.y = src; bp.w1img = bimg; bp.spart = spart;
     bp.prof = phx_tc_prof_buffer();
     bp.a_stages = (!pair && ts_mode()) ? ts_plan(Hn, bp.a_hi_col, bp.a_lo_col) : 0;
-    const int ts = bp.a_stages > 0;
-    const size_t stage1 = (ts ? 0 : K1_A_BYTES) + (size_t)2 * Hb * BK * 4;
-    const size_t staging = trans ? 0 : (size_t)K1_PWARPS * 2 * 8 * (K1_PF * BK + 4) * sizeof(float);
-    int S1 = (int)((PHX_SMEM_LIMIT - 256 - staging) / stage1);
+    int ts = bp.a_stages > 0;
+    size_t stage1 = (size_t)2 * Hb * BK * 4;
+    // TS: single-buffered staging (4 lane quarters x 32 rows) and the running sum [Hn / 4][128] float4 behind it
+    size_t staging = trans ? 0 : (size_t)4 * 32 * (K1_PF * BK + 4) * sizeof(float);
+    size_t running = (size_t)Hn * 128 * sizeof(float);
+    if (ts && (PHX_SMEM_LIMIT - 256 - staging - running) / stage1 < 2) ts = 0;   // no room for a B ring: shared-memory A
+    // the tensor-memory form pays off through the overlapped chunk folds: a CTA needs at least two chunks of K (measured:
+    // 3 551 x 120 x 1 024, one chunk per CTA, is 3-15 % slower with it; 20 000 x 200 x 4 096 is 8 % faster)
+    if (ts && (pl.per_p > pl.per_s ? pl.per_p : pl.per_s) < 2 * bp.chunk && !getenv("PHX_TC_TS_FORCE")) ts = 0;
+    if (!ts) {
+        bp.a_stages = 0;
+        stage1 += K1_A_BYTES;
+        staging = trans ? 0 : (size_t)K1_PWARPS * 2 * 8 * (K1_PF * BK + 4) * sizeof(float);
+        running = 0;
+    }
+    bp.stg_bytes = (unsigned)staging;
+    int S1 = (int)((PHX_SMEM_LIMIT - 256 - staging - running) / stage1);
     if (S1 > 6) S1 = 6;
     if (const char* e = getenv("PHX_TC_STAGES")) {   // experiment
         int v = atoi(e);
@@ -1351,7 +1428,7 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     }
     bp.stages = S1;
     set_attrs();
-    const size_t smem1 = (size_t)S1 * stage1 + 256 + staging;
+    const size_t smem1 = (size_t)S1 * stage1 + 256 + staging + running;
     if (!pair) {
         const dim3 grid1(pl.mtiles * (pl.ks_p + pl.ks_s));
         if (ts) {
