@@ -19,6 +19,12 @@ SYNC_ERRORS = True
 STEP_LOGGING = False
 STEPLOG_CAP = 4096
 FORCE_ENGINE = None  # None | "rows" | "resident" | "stream"  (tests compare the engines on the same inputs)
+# A ONE-sample odeint / odeint_adjoint call (the literal loop of train_insilico.py:128-130) on a model whose solve fills the
+# GPU: "resident" = the one-problem persistent kernels (forward 79 us + backward 370 us per call at 11 165 x 200, flat
+# gradient written directly), "rows" = the lock-step rows kernels with a single row (107 + 425 us: a pass costs the same
+# with 1 row as with 4, plus the packed -> flat conversion) -- bit-identical to odeint_adjoint_many, which always uses them.
+SINGLE_CALL_ENGINE = "resident"
+SINGLE_CALL_MIN_GENES = 2048
 
 class _State:
     """Process-wide bookkeeping (NOT thread-local: autograd runs backward() on its own worker thread)."""
@@ -405,9 +411,15 @@ def _rows_per_pass(lib, dev, G, H, adjoint):
     return r
 
 
-def _use_rows(lib, dev, G, H, B, adjoint):
-    """One-row problems go to the rows kernels (phx_rows.cuh) unless a test forces another engine."""
-    return B == 1 and FORCE_ENGINE in (None, "rows") and _rows_per_pass(lib, dev, G, H, adjoint) > 0
+def _use_rows(lib, dev, G, H, B, adjoint, single=False, T=2):
+    """One-row problems go to the rows kernels (phx_rows.cuh) unless a test forces another engine -- or the call holds a
+    single sample of a GPU-filling model and the one-problem resident kernels take it (SINGLE_CALL_ENGINE)."""
+    if B != 1 or FORCE_ENGINE not in (None, "rows") or _rows_per_pass(lib, dev, G, H, adjoint) <= 0:
+        return False
+    if (single and FORCE_ENGINE is None and SINGLE_CALL_ENGINE == "resident" and G >= SINGLE_CALL_MIN_GENES
+            and lib.phx_solve_workspace_bytes(_lib.ctx(dev), G, H, 1, T, int(adjoint)) > 0):
+        return False
+    return True
 
 
 def _steplog_rows(n):
@@ -479,7 +491,7 @@ def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, 
     B = y0c.numel() // G
     T = len(t_list)
     lib = _lib.load()
-    if _use_rows(lib, dev, G, H, B, False):
+    if _use_rows(lib, dev, G, H, B, False, single=True, T=T):
         return _forward_rows(lib, net, packed, G, H, dev, y0c, [t_list], t_is_f32, reversed_time, method, rtol, atol,
                              max_num_steps, (T,) + tuple(y0c.shape))
     engine, nb = _pick_engine(lib, dev, G, H, B, T, False)
@@ -504,14 +516,14 @@ def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_sa
     T = len(t_list)
     B = ys[0].numel() // G
     lib = _lib.load()
-    if _use_rows(lib, dev, G, H, B, True):
+    if _use_rows(lib, dev, G, H, B, True, single=True, T=T):
         return _adjoint_rows(lib, net, packed, G, H, dev, [t_list], t_is_f32, method, rtol, atol, max_num_steps, ys, gy,
                              tuple(ys[0].shape))
     engine, nb = _pick_engine(lib, dev, G, H, B, T, True)
     ws = _workspace(dev, nb, "solve" if engine == "resident" else "stream")
     adj_y0 = torch.empty_like(ys[0])
     P = 4 * G * H + 2 * H + G
-    grads = torch.empty(P, dtype=torch.float32, device=ys.device)
+    grads = new_flat_grads(net, P, ys.device)
     st = _new_status()
     log, cap = _steplog()
     fn = lib.phx_solve_adjoint if engine == "resident" else lib.phx_stream_solve_adjoint

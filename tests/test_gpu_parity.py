@@ -344,21 +344,35 @@ def test_odeint_adjoint_many_equals_the_per_sample_loop(pb, G, H, N):
     tau = torch.rand(N, generator=gen)
     t = torch.stack([tau, tau + 0.5, tau + 1.25], dim=1)
     target = torch.rand(N, 1, G, generator=gen).cuda()
-    for method in ("dopri5", "rk4"):
-        net.zero_grad()
-        ya = y0.clone().requires_grad_(True)
-        many = pb.odeint_adjoint_many(net, ya, t, method=method)
-        torch.mean((many[:, 2] - target) ** 2).backward()
-        g_many = [ya.grad.clone()] + [p.grad.clone() for p in net.parameters()]
-        net.zero_grad()
-        yb = y0.clone().requires_grad_(True)
-        loop = torch.stack([pb.odeint_adjoint(net, yb[i], t[i], method=method) for i in range(N)])
-        torch.mean((loop[:, 2] - target) ** 2).backward()
-        g_loop = [yb.grad.clone()] + [p.grad.clone() for p in net.parameters()]
-        assert torch.equal(many, loop)
-        assert torch.equal(g_many[0], g_loop[0])
-        for a, b in zip(g_many[1:], g_loop[1:]):
-            assert rel_l2(a.cpu(), b.cpu()) < 1e-6
+    saved = pb.engine.SINGLE_CALL_ENGINE
+    try:
+        # "rows": one-sample calls run the same kernels as odeint_adjoint_many => bit-identical.  Default ("resident" for
+        # models that fill the GPU, here 3 551 genes): another kernel, another summation order => rounding-level agreement
+        for single in ("rows", saved):
+            pb.engine.SINGLE_CALL_ENGINE = single
+            same_kernels = single == "rows" or G < pb.engine.SINGLE_CALL_MIN_GENES
+            for method in ("dopri5", "rk4"):
+                net.zero_grad()
+                ya = y0.clone().requires_grad_(True)
+                many = pb.odeint_adjoint_many(net, ya, t, method=method)
+                torch.mean((many[:, 2] - target) ** 2).backward()
+                g_many = [ya.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+                net.zero_grad()
+                yb = y0.clone().requires_grad_(True)
+                loop = torch.stack([pb.odeint_adjoint(net, yb[i], t[i], method=method) for i in range(N)])
+                torch.mean((loop[:, 2] - target) ** 2).backward()
+                g_loop = [yb.grad.clone()] + [p.grad.clone() for p in net.parameters()]
+                if same_kernels:
+                    assert torch.equal(many, loop)
+                    assert torch.equal(g_many[0], g_loop[0])
+                else:
+                    # two kernels, two summation orders: the tolerances of the parity tests against the oracle
+                    assert rel_l2(many.cpu(), loop.cpu()) < 1e-6
+                    assert rel_l2(g_many[0].cpu(), g_loop[0].cpu()) < (2e-4 if method == "dopri5" else 1e-5)
+                for a, b in zip(g_many[1:], g_loop[1:]):
+                    assert rel_l2(a.cpu(), b.cpu()) < (1e-6 if same_kernels else (2e-4 if method == "dopri5" else 1e-5))
+    finally:
+        pb.engine.SINGLE_CALL_ENGINE = saved
 
 
 def test_multi_problem_entry_points_check_their_limits(pb):
@@ -411,7 +425,12 @@ def test_many_reports_a_failing_problem_and_finishes_the_others(pb):
         with torch.no_grad():
             pb.odeint_adjoint_many(net, bad, t, method="dopri5")
     pb.check_errors()            # nothing left pending
-    with torch.no_grad():
-        good = pb.odeint_adjoint_many(net, y0, t, method="dopri5")
-        ref = pb.odeint(net, y0[3], t[3], method="dopri5")
+    saved = pb.engine.SINGLE_CALL_ENGINE
+    pb.engine.SINGLE_CALL_ENGINE = "rows"     # the same kernels as the many-call: identical bits
+    try:
+        with torch.no_grad():
+            good = pb.odeint_adjoint_many(net, y0, t, method="dopri5")
+            ref = pb.odeint(net, y0[3], t[3], method="dopri5")
+    finally:
+        pb.engine.SINGLE_CALL_ENGINE = saved
     assert torch.isfinite(good).all() and torch.equal(good[3], ref)

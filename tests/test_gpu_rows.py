@@ -18,7 +18,13 @@ pytestmark = pytest.mark.gpu
 def pb():
     import phoenix_b200 as pb
     pb.set_sync_errors(True)
+    # this file is about the rows kernels: one-sample calls go through them too (by default a one-sample call of a
+    # GPU-filling model takes the one-problem resident kernels, engine.SINGLE_CALL_ENGINE), which is what makes
+    # "one call at a time" bit-identical to odeint_adjoint_many
+    saved = pb.engine.SINGLE_CALL_ENGINE
+    pb.engine.SINGLE_CALL_ENGINE = "rows"
     yield pb
+    pb.engine.SINGLE_CALL_ENGINE = saved
     pb.set_sync_errors(True)
 
 
