@@ -455,7 +455,9 @@ def run_ours(args):
         achieved = alg / (adj_ms * 1e-3) / 1e9
         traffic = None
         try:
-            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("phx_adj_kernel")
+            # dram__bytes_read.sum + dram__bytes_write.sum of ONE ncu --set full capture of the 17-sample
+            # phx_rows_adj_kernel launch (profiles/r02f_ncu_full.txt), per sample like achieved / algorithmic_bytes
+            traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get("phx_rows_adj_kernel") / BATCH
         except Exception:
             pass
         cores = os.cpu_count() or 1
@@ -493,7 +495,7 @@ def run_ours(args):
                     "per_sample_api_value": work_per_step / (ms_e2e_loop / args.steps / 1e3),
                     "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130"},
             "gpu_launches": args.steps * 4,   # forward rows, adjoint rows, 2 x unpack (+ 2 ATen elementwise for the loss grad)
-            "roofline": {"bound": "hbm", "kernel": "phx_adj_kernel", "achieved": achieved, "peak": peak,
+            "roofline": {"bound": "hbm", "kernel": "phx_rows_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "launch_ms": adj_ms, "algorithmic_bytes": alg,
                          "per": "one sample's adjoint sweep = the 17-sample phx_rows_adj_kernel launch / 17 (%d samples in "

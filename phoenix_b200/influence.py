@@ -13,31 +13,80 @@ from . import parallel
 from .torchdiffeq import odeint
 
 
+def _score_one(odenet, g, this_init, pert_col, t, method, G):
+    unpert_out = odeint(odenet, this_init, t, method=method)
+    this_init = this_init.clone()
+    this_init[:, 0, g] = pert_col
+    pert_out = odeint(odenet, this_init, t, method=method)
+    # mean over times 1.., rows and all genes but g (find_gene_influences.py:71-72)
+    d = (unpert_out[1:] - pert_out[1:]).abs()
+    total = d.sum(dtype=torch.float64) - d[..., g].sum(dtype=torch.float64)
+    return total / (d[..., 0].numel() * (G - 1))
+
+
 def gene_influence_scores(odenet, genes, n_random_inputs_per_gene=60, time_pts=None, method="dopri5", generator=None,
-                          inits=None):
+                          inits=None, workers=4):
     """Scores of ``genes`` (iterable of gene indices).  ``inits`` (optional, for parity tests): a list of
     ``(this_init [n,1,G], this_pert_col [n])`` CPU tensors per gene; otherwise they are drawn on the model's device from
-    ``generator`` exactly like find_gene_influences.py:65,67 (``torch.rand(...) - 0.5``)."""
+    ``generator`` exactly like find_gene_influences.py:65,67 (``torch.rand(...) - 0.5``), gene by gene in scan order.
+
+    A 60-row solve keeps about half of the GPU busy and its adaptive step controller runs on the host (one small read-back
+    per attempted step), so ``workers`` genes are scanned side by side: one host thread and one CUDA stream per worker (the
+    solver's host loop runs outside the GIL).  Every gene's two solves are still their own ``odeint`` calls with their own
+    step sequences: the scores do not depend on ``workers``."""
+    import concurrent.futures as cf
     p0 = odenet.gene_multipliers
     dev, G = p0.device, odenet.ndim
     t = torch.from_numpy(np.arange(0, 1, 0.1)) if time_pts is None else time_pts
-    scores = []
+    genes = list(genes)
+    if not genes:
+        return torch.empty(0)
+    workers = max(1, min(int(workers), len(genes)))
+    main = torch.cuda.current_stream(dev)
+    streams = [torch.cuda.Stream(device=dev) for _ in range(workers)] if workers > 1 else [main]
+
+    def draw(k):
+        if inits is not None:
+            return inits[k][0].to(dev), inits[k][1].to(dev)
+        return (torch.rand(n_random_inputs_per_gene, 1, G, device=dev, generator=generator) - 0.5,
+                torch.rand(n_random_inputs_per_gene, device=dev, generator=generator) - 0.5)
+
+    def run(k, g, this_init, pert_col, ready):
+        s = streams[k % workers]
+        with torch.cuda.device(dev), torch.cuda.stream(s), torch.no_grad():
+            s.wait_event(ready)
+            out = _score_one(odenet, g, this_init, pert_col, t, method, G)
+            this_init.record_stream(s)
+            pert_col.record_stream(s)
+            return out
+
+    scores = [None] * len(genes)
     with torch.no_grad():
-        for k, g in enumerate(genes):
-            if inits is not None:
-                this_init, pert_col = inits[k][0].to(dev), inits[k][1].to(dev)
-            else:
-                this_init = torch.rand(n_random_inputs_per_gene, 1, G, device=dev, generator=generator) - 0.5
-                pert_col = torch.rand(n_random_inputs_per_gene, device=dev, generator=generator) - 0.5
-            unpert_out = odeint(odenet, this_init, t, method=method)
-            this_init = this_init.clone()
-            this_init[:, 0, g] = pert_col
-            pert_out = odeint(odenet, this_init, t, method=method)
-            # mean over times 1.., rows and all genes but g (find_gene_influences.py:71-72)
-            d = (unpert_out[1:] - pert_out[1:]).abs()
-            total = d.sum(dtype=torch.float64) - d[..., g].sum(dtype=torch.float64)
-            scores.append(total / (d[..., 0].numel() * (G - 1)))
-    return torch.stack(scores).to(torch.float32) if scores else torch.empty(0)
+        if workers == 1:
+            for k, g in enumerate(genes):
+                this_init, pert_col = draw(k)
+                scores[k] = _score_one(odenet, g, this_init, pert_col, t, method, G)
+        else:
+            # the draws stay on the caller's stream, in scan order (same random numbers as the sequential scan); a worker
+            # is handed a gene only when its stream's previous gene has been submitted, so each stream sees its genes
+            # in order and at most `workers` bundles of trajectories are alive
+            with cf.ThreadPoolExecutor(max_workers=workers) as ex:
+                pending = [None] * workers
+                for k, g in enumerate(genes):
+                    w = k % workers
+                    if pending[w] is not None:
+                        kk, fut = pending[w]
+                        scores[kk] = fut.result()
+                    this_init, pert_col = draw(k)
+                    ready = torch.cuda.Event()
+                    ready.record(main)
+                    pending[w] = (k, ex.submit(run, k, g, this_init, pert_col, ready))
+                for item in pending:
+                    if item is not None:
+                        scores[item[0]] = item[1].result()
+            for s in streams:
+                main.wait_stream(s)
+    return torch.stack(scores).to(torch.float32)
 
 
 def shard_genes(n_genes, rank, world_size):

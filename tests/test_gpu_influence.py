@@ -37,3 +37,11 @@ def test_influence_scores_match_the_oracle():
     for m, r in zip(mine, ref):
         assert abs(m - r) <= 5e-3 * abs(r), (mine, ref)
     assert list(influence.shard_genes(10, 1, 3)) == [4, 5, 6]
+    # genes scanned side by side on several streams / host threads: the very same scores as the sequential scan
+    seq = influence.gene_influence_scores(net, genes, inits=inits, workers=1)
+    par = influence.gene_influence_scores(net, genes, inits=inits, workers=3)
+    assert torch.equal(seq, par) and torch.equal(seq.cpu(), torch.tensor(mine))
+    g1, g2 = (torch.Generator(device="cuda").manual_seed(5) for _ in range(2))
+    a = influence.gene_influence_scores(net, range(6), generator=g1, workers=1)
+    b = influence.gene_influence_scores(net, range(6), generator=g2, workers=4)
+    assert torch.equal(a, b)

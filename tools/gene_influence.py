@@ -26,6 +26,7 @@ def main():
     ap.add_argument("--count", type=int, default=0)
     ap.add_argument("--method", default="dopri5")
     ap.add_argument("--out", default="")
+    ap.add_argument("--workers", type=int, default=4, help="genes scanned side by side (host threads / CUDA streams)")
     a = ap.parse_args()
     import torch.distributed as dist
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
@@ -40,12 +41,13 @@ def main():
     if a.count:
         genes = genes[:a.count]
     gen = torch.Generator(device=dev).manual_seed(100 + rank)
-    influence.gene_influence_scores(odenet, genes[:2], method=a.method, generator=gen)     # warm-up
+    influence.gene_influence_scores(odenet, genes[:2 * a.workers], method=a.method, generator=gen,
+                                    workers=a.workers)     # warm-up (every worker stream gets its workspaces)
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    scores = influence.gene_influence_scores(odenet, genes, method=a.method, generator=gen)
+    scores = influence.gene_influence_scores(odenet, genes, method=a.method, generator=gen, workers=a.workers)
     torch.cuda.synchronize()
     secs = time.perf_counter() - t0
     stats = torch.tensor([secs, float(len(genes))], dtype=torch.float64, device=dev)
@@ -64,7 +66,7 @@ def main():
     if rank == 0:
         rate = n_done / secs
         print(json.dumps({"metric": "gene-influence scan", "genes": a.genes, "neurons": a.neurons, "n_gpus": world,
-                          "method": a.method, "rows_per_solve": 60, "output_times": 10, "genes_scanned": int(n_done),
+                          "method": a.method, "workers": a.workers, "rows_per_solve": 60, "output_times": 10, "genes_scanned": int(n_done),
                           "seconds": secs, "genes_per_s": rate, "solves_per_s": 2 * rate,
                           "full_scan_projected_s": a.genes / rate,
                           "scores_head": [float(x) for x in scores[:4].tolist()]}), flush=True)
