@@ -275,12 +275,15 @@ struct Stream {
     void* sum_user = nullptr;
     int sum_world = 1;
 
-    // stage derivative `slot` of every segment at the current stage inputs
-    int eval(int slot) {
+    // stage derivative `slot` of every segment at the current stage inputs (at_x0: at the step's start values themselves,
+    // read in place -- no copy into the stage-input buffers)
+    enum { AT_XS = 0, AT_X0 = 1, AT_X1 = 2 };
+    int eval(int slot, int at = AT_XS) {
+        auto in = [&](Seg& s) -> const float* { return at == AT_X0 ? s.x0 : (at == AT_X1 ? s.x1 : s.xs); };
         if (!adjoint)
-            return phx_rhs_forward_launch(G, H, B, w, segs[0].xs, segs[0].k[slot], 1, fsign, rhs_ws, st);
+            return phx_rhs_forward_launch(G, H, B, w, in(segs[0]), segs[0].k[slot], 1, fsign, rhs_ws, st);
         // reverse time: ky = -f, ka = VJP_y(cotangent a), ktheta = VJP_theta(cotangent a)
-        return phx_rhs_vjp_launch(G, H, B, w, segs[0].xs, segs[1].xs, 1, segs[1].k[slot], segs[2].k[slot], 0,
+        return phx_rhs_vjp_launch(G, H, B, w, in(segs[0]), in(segs[1]), 1, segs[1].k[slot], segs[2].k[slot], 0,
                                   segs[0].k[slot], -1.f, rhs_ws, st);
     }
     // reduce a 3-value kernel result for segment si into sums_dev[si]
@@ -339,28 +342,25 @@ struct Stream {
         }
         return a;
     }
-    void copy_to_inputs() {
-        for (auto& s : segs)
-            if (s.xs) cudaMemcpyAsync(s.xs, s.x0, s.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-    }
-
-    // ---- one fixed-grid step of size dtf on all segments (x0 updated in place) ----
-    int fixed_step(float dtf) {
+    // ---- one fixed-grid step of size dtf on all segments.  The new values replace x0 in place -- or, with `dst0`
+    // (forward solves: the caller's output slice of this interval), segment 0's go straight there and x0 is re-pointed
+    // at them: no copy of the state into the output, and the start values of a solve are read where the caller put them ----
+    int fixed_step(float dtf, float* dst0 = nullptr) {
         int rc;
-        copy_to_inputs();
-        if ((rc = eval(0)) != PHX_OK) return rc;
+        if ((rc = eval(0, AT_X0)) != PHX_OK) return rc;
+        auto endp = [&](Seg& s) { return (dst0 && &s == &segs[0]) ? dst0 : s.x0; };
         auto fx = [&](int mode, Seg& s, float* out, float dt) {
             fixed(mode, out, s.x0, s.k[0], s.k[1], s.k[2], s.k[3], dt, s.n);
         };
         if (method == PHX_EULER) {
-            for (auto& s : segs) fx(FX_EULER_END, s, s.x0, dtf);
+            for (auto& s : segs) fx(FX_EULER_END, s, endp(s), dtf);
             status.n_rhs += 1;
         } else if (method == PHX_MIDPOINT) {
             for (auto& s : segs)
                 if (s.xs) fx(FX_MID_IN, s, s.xs, 0.5f * dtf);
             if ((rc = eval(1)) != PHX_OK) return rc;
             for (auto& s : segs)
-                fixed(FX_EULER_END, s.x0, s.x0, s.k[1], nullptr, nullptr, nullptr, dtf, s.n);
+                fixed(FX_EULER_END, endp(s), s.x0, s.k[1], nullptr, nullptr, nullptr, dtf, s.n);
             status.n_rhs += 2;
         } else {
             for (auto& s : segs)
@@ -372,9 +372,10 @@ struct Stream {
             for (auto& s : segs)
                 if (s.xs) fx(FX_RK4_IN4, s, s.xs, dtf);
             if ((rc = eval(3)) != PHX_OK) return rc;
-            for (auto& s : segs) fx(FX_RK4_END, s, s.x0, dtf);
+            for (auto& s : segs) fx(FX_RK4_END, s, endp(s), dtf);
             status.n_rhs += 4;
         }
+        if (dst0) segs[0].x0 = dst0;
         return PHX_OK;
     }
 
@@ -385,8 +386,7 @@ struct Stream {
         int rc;
         const size_t ns = segs.size();
         int sl[7] = {0, 1, 2, 3, 4, 5, 6};
-        copy_to_inputs();
-        if ((rc = eval(0)) != PHX_OK) return rc;
+        if ((rc = eval(0, AT_X0)) != PHX_OK) return rc;
         for (size_t si = 0; si < ns; ++si) {
             Seg& s = segs[si];
             init01_kernel<<<nblk(s.n), EB, 0, st>>>(s.x0, s.k[0], rtol_f, atol_f, s.n, partial);
@@ -435,14 +435,10 @@ struct Stream {
                 for (size_t si = 0; si < ns; ++si) {
                     Seg& s = segs[si];
                     KSet a = kset((int)si, sl, cb[stg - 1], stg);
-                    if (stg == 6) {
-                        combine(s.x1, s.x0, a, s.n);
-                        if (s.xs) cudaMemcpyAsync(s.xs, s.x1, s.n * sizeof(float), cudaMemcpyDeviceToDevice, st);
-                    } else if (s.xs) {
-                        combine(s.xs, s.x0, a, s.n);
-                    }
+                    if (stg == 6) combine(s.x1, s.x0, a, s.n);   // y1: the last stage is evaluated there, in place
+                    else if (s.xs) combine(s.xs, s.x0, a, s.n);
                 }
-                if ((rc = eval(sl[stg])) != PHX_OK) return rc;
+                if ((rc = eval(sl[stg], stg == 6 ? AT_X1 : AT_XS)) != PHX_OK) return rc;
             }
             for (size_t si = 0; si < ns; ++si) {
                 Seg& s = segs[si];
@@ -626,15 +622,13 @@ int phx_stream_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* pac
     y.x0 = base; y.x1 = base + BG; y.xs = base + 2 * BG;
     for (int i = 0; i < 7; ++i) y.k[i] = base + (3 + i) * BG;
     S.segs.push_back(y);
-    cudaMemcpyAsync(y.x0, y0, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
     cudaMemcpyAsync(y_out, y0, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
     if (method != PHX_DOPRI5) {
-        for (int i = 0; i + 1 < T && rc == PHX_OK; ++i) {
-            rc = S.fixed_step(fixed_dt(t_host, i, t_is_f32));
-            cudaMemcpyAsync(y_out + (size_t)(i + 1) * BG, S.segs[0].x0, BG * sizeof(float), cudaMemcpyDeviceToDevice,
-                            st);
-        }
+        // fixed grid: the state of interval i is read from the output slice i and written to slice i + 1
+        S.segs[0].x0 = y_out;
+        for (int i = 0; i + 1 < T && rc == PHX_OK; ++i) rc = S.fixed_step(fixed_dt(t_host, i, t_is_f32), y_out + (size_t)(i + 1) * BG);
     } else {
+        cudaMemcpyAsync(y.x0, y0, BG * sizeof(float), cudaMemcpyDeviceToDevice, st);
         rc = S.dopri5(t_host[0], t_host + 1, T - 1,
                       [&](int j, const float* xs, const int* sl, float dtf, const float* cmid) {
                           S.interp_seg(0, y_out + (size_t)(j + 1) * BG, xs, sl, dtf, cmid);
