@@ -59,6 +59,20 @@ __device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity) {
             : "memory");
     }
 }
+// one non-blocking test of the phase with parity `parity` (1: that phase has completed)
+__device__ __forceinline__ unsigned mbar_test(unsigned bar, unsigned parity) {
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return done;
+}
 __device__ __forceinline__ void mbar_arrive(unsigned bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
@@ -584,6 +598,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         int sa = 0;          // TS: A-ring slot of k-block i and its phase parity
         unsigned pha = 0;
         const unsigned tq = TS ? tmem + ((unsigned)((warp & 3) * 32) << 16) + 4u * (unsigned)kc : 0u;
+        int signal_sa = -1;  // TS: A slot whose "full" arrive is still owed
         for (int i0 = 0; i0 < nkb; i0 += K1_PF) {
             const long long tl0 = PROF(p) ? clock64() : 0;
             if (i0 + K1_PF < nkb) load(i0 + K1_PF, nxt);
@@ -593,6 +608,9 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 const int i = i0 + u;
                 if (i < nkb) {
                     const long long tc0 = PROF(p) ? clock64() : 0;
+                    // TS: test the A slot of this k-block NOW, so that the barrier round trip hides behind the conversion
+                    unsigned slot_free = 0;
+                    if (TS && lane == 0) slot_free = mbar_test(emptyA0 + 8 * sa, pha ^ 1u);
                     float xin[4];
                     if (TRANS) {
 #pragma unroll
@@ -620,7 +638,14 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     const long long tw = PROF(p) ? clock64() : 0;
                     if (PROF(p)) t_conv += tw - tc0 + (long long)(__float_as_uint(hi[0]) & 0u);
                     if (TS) {
-                        if (lane == 0) mbar_wait(emptyA0 + 8 * sa, pha ^ 1u);   // the MMAs that read this slot are done
+                        // hand over the PREVIOUS k-block first: its tcgen05.st have had the whole conversion to complete
+                        if (signal_sa >= 0) {
+                            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(fullA0 + 8 * signal_sa);
+                        }
+                        if (lane == 0 && !slot_free) mbar_wait(emptyA0 + 8 * sa, pha ^ 1u);   // the MMAs of this slot are done
                         __syncwarp();
                         tc_fence_after();
                         const long long ts0 = PROF(p) ? clock64() : 0;
@@ -635,10 +660,7 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                                      "r"(__float_as_uint(lo[0])), "r"(__float_as_uint(lo[1])), "r"(__float_as_uint(lo[2])),
                                      "r"(__float_as_uint(lo[3]))
                                      : "memory");
-                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(fullA0 + 8 * sa);
+                        signal_sa = sa;   // signalled after the next k-block's conversion (or after the loop)
                         if (PROF(p)) t_store += clock64() - ts0;
                         if (++sa == SA) {
                             sa = 0;
@@ -671,12 +693,25 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
             } else if (i0 + K1_PF < nkb) {
                 const long long tl1 = PROF(p) ? clock64() : 0;
+                if (TS && signal_sa >= 0) {   // do not keep the MMAs waiting across the staging barriers
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(fullA0 + 8 * signal_sa);
+                    signal_sa = -1;
+                }
                 if (NSBUF == 2) sbuf ^= 1;   // the other buffer: last read one super-block ago (ordered by the hand-over sync)
                 else stage_sync();           // single buffer: every warp of the group has read this super-block
                 stage_put(sbuf, nxt);
                 stage_sync();
                 if (PROF(p)) t_load += clock64() - tl1;
             }
+        }
+        if (TS && signal_sa >= 0) {
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(fullA0 + 8 * signal_sa);
         }
         if (PROF(p) && tid == 0) {
             unsigned long long* q = PROF(p) + 8 * br + 4;
