@@ -598,7 +598,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         int sa = 0;          // TS: A-ring slot of k-block i and its phase parity
         unsigned pha = 0;
         const unsigned tq = TS ? tmem + ((unsigned)((warp & 3) * 32) << 16) + 4u * (unsigned)kc : 0u;
-        int signal_sa = -1;  // TS: A slot whose "full" arrive is still owed
         for (int i0 = 0; i0 < nkb; i0 += K1_PF) {
             const long long tl0 = PROF(p) ? clock64() : 0;
             if (i0 + K1_PF < nkb) load(i0 + K1_PF, nxt);
@@ -638,13 +637,6 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     const long long tw = PROF(p) ? clock64() : 0;
                     if (PROF(p)) t_conv += tw - tc0 + (long long)(__float_as_uint(hi[0]) & 0u);
                     if (TS) {
-                        // hand over the PREVIOUS k-block first: its tcgen05.st have had the whole conversion to complete
-                        if (signal_sa >= 0) {
-                            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                            tc_fence_before();
-                            __syncwarp();
-                            if (lane == 0) mbar_arrive(fullA0 + 8 * signal_sa);
-                        }
                         if (lane == 0 && !slot_free) mbar_wait(emptyA0 + 8 * sa, pha ^ 1u);   // the MMAs of this slot are done
                         __syncwarp();
                         tc_fence_after();
@@ -660,7 +652,11 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                                      "r"(__float_as_uint(lo[0])), "r"(__float_as_uint(lo[1])), "r"(__float_as_uint(lo[2])),
                                      "r"(__float_as_uint(lo[3]))
                                      : "memory");
-                        signal_sa = sa;   // signalled after the next k-block's conversion (or after the loop)
+                        // (deferring this hand-over behind the next k-block's conversion was tried: the MMAs starve, 3 % slower)
+                        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(fullA0 + 8 * sa);
                         if (PROF(p)) t_store += clock64() - ts0;
                         if (++sa == SA) {
                             sa = 0;
@@ -693,25 +689,12 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                     for (int j = 0; j < 4; ++j) cur[u][j] = nxt[u][j];
             } else if (i0 + K1_PF < nkb) {
                 const long long tl1 = PROF(p) ? clock64() : 0;
-                if (TS && signal_sa >= 0) {   // do not keep the MMAs waiting across the staging barriers
-                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(fullA0 + 8 * signal_sa);
-                    signal_sa = -1;
-                }
                 if (NSBUF == 2) sbuf ^= 1;   // the other buffer: last read one super-block ago (ordered by the hand-over sync)
                 else stage_sync();           // single buffer: every warp of the group has read this super-block
                 stage_put(sbuf, nxt);
                 stage_sync();
                 if (PROF(p)) t_load += clock64() - tl1;
             }
-        }
-        if (TS && signal_sa >= 0) {
-            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(fullA0 + 8 * signal_sa);
         }
         if (PROF(p) && tid == 0) {
             unsigned long long* q = PROF(p) + 8 * br + 4;
