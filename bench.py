@@ -271,7 +271,8 @@ def run_ours(args):
     # N > 1: the flat gradient is written straight into a peer-mapped buffer and summed over the ranks by ONE kernel per
     # rank over NVLink peer memory (phoenix_b200/csrc/phx_peer.cu); PHX_BENCH_NCCL=1 keeps the NCCL all-reduce instead
     use_peer = world > 1 and not int(os.environ.get("PHX_BENCH_NCCL", "0"))
-    peer = parallel.enable_peer_allreduce(net) if use_peer else None
+    peer = parallel.try_enable_peer_allreduce(net) if use_peer else None
+    use_peer = peer is not None
     gsum = peer.buffer[:P] if use_peer else torch.empty(P, device=dev)
     st_f = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()
     st_a = torch.zeros(BATCH, 10, dtype=torch.int32).pin_memory()

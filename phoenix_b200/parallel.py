@@ -136,7 +136,8 @@ class PeerAllReduce:
         self._flags = (ctypes.c_void_p * self.world)(*[int(x) for x in hf.buffer_ptrs])
         self._handles = (hb, hf)
         # NVLS (sums formed inside the NVSwitch, phx_peer_allreduce_nvls) when the buffer has a multicast address:
-        # nvls=None -> PHX_PEER_NVLS (default: on from 4 ranks), True / False force it
+        # nvls=None -> PHX_PEER_NVLS (default: on at 8 ranks -- measured for the 35.8 MB gradient: 4 GPUs 105 us peer
+        # loads / stores vs 127 us NVLS, 8 GPUs 147 vs 134 us), True / False force it
         try:
             self._mc = int(hb.multicast_ptr or 0)
         except Exception:   # no multicast support on this box / torch build
@@ -144,7 +145,7 @@ class PeerAllReduce:
         if nvls is None:
             import os
             env = os.environ.get("PHX_PEER_NVLS")
-            nvls = (self.world >= 4) if env is None else bool(int(env))
+            nvls = (self.world >= 8) if env is None else bool(int(env))
         self.nvls = bool(nvls) and self._mc != 0
         self.epoch = 0
         self._lib, self._ctx = _lib.load(), _lib.ctx(self.dev)
@@ -188,6 +189,40 @@ def enable_peer_allreduce(net, group=None):
 
     engine._flat_alloc[id(net)] = alloc
     return pr
+
+
+def try_enable_peer_allreduce(net, group=None):
+    """``enable_peer_allreduce`` that falls back to NCCL (returns None) when peer-mapped memory cannot be set up on this
+    box / torch build.  The ranks agree on the outcome (a failure on one rank disables it everywhere)."""
+    import sys
+    dev = engine.net_params(net)[0].device
+
+    def agree(ok):
+        flag = torch.tensor([1 if ok else 0], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        return int(flag) == 1
+
+    pr, err = None, None
+    try:
+        pr = enable_peer_allreduce(net, group=group)
+    except Exception as e:   # noqa: BLE001 -- any set-up failure means "use NCCL"
+        err = e
+    ok = agree(pr is not None)          # before the first kernel: a rank without buffers must not leave the others spinning
+    if ok:
+        try:
+            pr.buffer[:4].fill_(1.0)
+            pr.reduce(numel=4)
+            torch.cuda.synchronize()
+            ok = abs(float(pr.buffer[0]) - pr.world) < 1e-3
+        except Exception as e:   # noqa: BLE001
+            ok, err = False, e
+        ok = agree(ok)
+    if ok:
+        return pr
+    disable_peer_allreduce(net)
+    if dist.get_rank(group) == 0:
+        sys.stderr.write("phoenix_b200: peer-memory all-reduce unavailable (%s); using NCCL\n" % (err,))
+    return None
 
 
 def disable_peer_allreduce(net):

@@ -55,7 +55,7 @@ def run_epochs(config, epochs=3, many=True, instrument=True, fused_prior=True, f
         # 42 launches per step over the six groups); fused=True is the same update as 6 launches
         **({"fused": True} if fused_adam else {}))
     if world > 1 and peer:   # gradient sum over NVLink peer memory (one kernel per rank) instead of an NCCL all-reduce
-        parallel.enable_peer_allreduce(odenet)
+        peer = parallel.try_enable_peer_allreduce(odenet) is not None
     gen = torch.Generator(device=dev).manual_seed(1000 + rank)
     lo, hi = parallel.shard_range(batch, rank, world)
     klo, khi = parallel.shard_range(K, rank, world)
