@@ -529,6 +529,10 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
             else __syncwarp();
         };
         const float padv = MODE ? 0.f : 0.5f;    // pads contribute zero: s(0.5) = l(0.5) = 0
+        // rows whose stride and base are multiples of 16 bytes (e.g. 20 000 genes): interior super-blocks are fetched with
+        // four 16-byte loads per thread (lane = 16-byte piece of one of two rows) instead of sixteen 4-byte ones
+        const bool vec_rows = !TRANS && (p.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 15) == 0;
+        bool nxt_vec = false;                    // register layout of `nxt` (set by load, used by stage_put)
         auto load = [&](int i, float (&v)[K1_PF][4]) {   // k-blocks kb0 + i .. kb0 + i + K1_PF - 1
             if (TRANS) {
                 if (i + K1_PF <= nkb && (kb0 + i + K1_PF) * BK <= p.G) {   // interior super-block: only the row test
@@ -551,6 +555,17 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
                 // v[rr/2][(rr%2)*2 + h] = element (lane + 32 h) of row rr of this warp
                 const int kvalid = min(p.G - (kb0 + i) * BK, (nkb - i) * BK);   // valid floats of the piece
                 const int rbase = m0 + (TS ? (warp & 3) * 32 + srow0 : warp * 8);
+                nxt_vec = false;
+                if (vec_rows && kvalid >= SBF && rbase + 8 <= p.B) {
+                    nxt_vec = true;
+                    const float* rp = p.y + (size_t)(rbase + (lane >> 4)) * p.ld + (size_t)(kb0 + i) * BK + 4 * (lane & 15);
+#pragma unroll
+                    for (int q2 = 0; q2 < 4; ++q2)   // rows rbase + 2 q2 + (lane >> 4)
+                        asm volatile("ld.global.nc.L2::256B.v4.f32 {%0,%1,%2,%3}, [%4];"
+                                     : "=f"(v[q2][0]), "=f"(v[q2][1]), "=f"(v[q2][2]), "=f"(v[q2][3])
+                                     : "l"(rp + (size_t)(2 * q2) * p.ld));
+                    return;
+                }
                 if (kvalid >= SBF && rbase + 8 <= p.B) {   // interior: no predicates
                     const float* rp = p.y + (size_t)rbase * p.ld + (size_t)(kb0 + i) * BK + lane;
 #pragma unroll
@@ -579,6 +594,13 @@ __global__ void __launch_bounds__(K1_THREADS, 1) tc_branch_kernel(BranchParams p
         };
         auto stage_put = [&](int buf, const float (&v)[K1_PF][4]) {   // TRANS = 0: registers -> staging buffer
             float* d = stg + buf * SBUF + srow0 * SROW;
+            if (nxt_vec) {
+#pragma unroll
+                for (int q2 = 0; q2 < 4; ++q2)
+                    *reinterpret_cast<float4*>(d + (2 * q2 + (lane >> 4)) * SROW + 4 * (lane & 15)) =
+                        make_float4(v[q2][0], v[q2][1], v[q2][2], v[q2][3]);
+                return;
+            }
 #pragma unroll
             for (int rr = 0; rr < 8; ++rr)
 #pragma unroll
