@@ -1414,13 +1414,9 @@ int launch_branch_mma(int mode, int trans, int G, int H, int B, int nterms, cons
     const int Hn = phx_tc_Hn(H);
     const int Kdim = trans ? B : G, Mdim = trans ? G : B;
     PhxTcBranchPlan pl = phx_tc_branch_plan(Kdim, Mdim);
-    if (mode == 1) {   // both halves cost the same: equal K ranges (never more slots than the plan reserved)
-        const int chunk = phx_tc_chunk(), nch = (phx_tc_KB1(Kdim) + chunk - 1) / chunk;
-        int ks = (pl.ks_p + pl.ks_s) / 2;
-        if (ks < 1) ks = 1;
-        const int per = (nch + ks - 1) / ks * chunk;
-        pl.per_p = pl.per_s = per;
-        pl.ks_p = pl.ks_s = (phx_tc_KB1(Kdim) + per - 1) / per;
+    if (mode == 1) {   // both halves cost the same: equal K ranges (the planner's equal-cost split)
+        pl.per_p = pl.per_s = pl.per_e;
+        pl.ks_p = pl.ks_s = pl.ks_e;
     }
     *plan = pl;
     BranchParams bp;

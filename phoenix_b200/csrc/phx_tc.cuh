@@ -23,6 +23,7 @@
 // Hn = round_up(H, 16) (UMMA N granularity at M = 128); pads are zero in every image.
 #pragma once
 #include <stdlib.h>
+#include <mutex>
 // (included from phx_common.cuh after phx_round_up)
 
 #define PHX_TC_BK 16
@@ -90,29 +91,98 @@ static inline int phx_tc_chunk() {
     }
     return chunk;
 }
-// Work split of the branch contraction (tc_branch_kernel): every CTA owns one branch, one 128-row tile and a K range
-// of whole chunks.  Aim at two CTAs per SM in total (the hardware scheduler balances them; the log1p CTAs are launched
-// first).  Measured on B200 a log1p CTA needs ~1.2x the time of a soft-sign CTA per k-block (both are bound by the
-// shared-memory traffic of the 3xTF32 operand reads), so the soft-sign branch gets 4/9 of the K-splits.
+// Work split of the branch contraction (tc_branch_kernel): every CTA owns one branch, one 128-row tile and a K range of
+// whole chunks; one CTA runs per SM at a time and the hardware hands the next CTA (prods CTAs are launched first) to the
+// first SM that frees up.  The numbers of K ranges per branch (ks_p, ks_s) are chosen by SIMULATING that dispatch with the
+// measured cost per k-block (log1p CTAs ~1 245 cycles, soft-sign ~1 160, cotangent operand ~1 100; ~30 000 cycles of
+// prologue + final fold per CTA; each further partial-sum slot costs the finishing pass a read of the slot) and taking
+// the split with the shortest makespan -- with few row tiles "two CTAs per SM" quantises badly: 79 tiles (the 10 000-row
+// prior batch) gave 2 + 1 ranges and a 1.6-wave schedule 28 % above the balanced time.
 struct PhxTcBranchPlan {
     int mtiles, ks_p, per_p, ks_s, per_s, slots;
+    int ks_e, per_e;   // equal-cost halves (MODE 1: the cotangent operand): ranges per half
 };
+static inline double phx_tc_makespan(int mt, int n_first, double d_first, int n_second, double d_second) {
+    // n_first CTAs of duration d_first, then n_second of d_second, dispatched in order to PHX_TC_SMS SMs
+    double t[PHX_TC_SMS];
+    for (int i = 0; i < PHX_TC_SMS; ++i) t[i] = 0.0;
+    // equal durations within a class: fill in rounds -- SM free times stay sorted ascending if we always take the minimum;
+    // keep a simple binary heap
+    auto sift = [&](int i) {
+        for (;;) {
+            int l = 2 * i + 1, r = l + 1, m = i;
+            if (l < PHX_TC_SMS && t[l] < t[m]) m = l;
+            if (r < PHX_TC_SMS && t[r] < t[m]) m = r;
+            if (m == i) break;
+            double x = t[i]; t[i] = t[m]; t[m] = x;
+            i = m;
+        }
+    };
+    (void)mt;
+    for (int c = 0; c < n_first + n_second; ++c) {
+        t[0] += c < n_first ? d_first : d_second;
+        sift(0);
+    }
+    double mx = 0.0;
+    for (int i = 0; i < PHX_TC_SMS; ++i) mx = t[i] > mx ? t[i] : mx;
+    return mx;
+}
+static inline PhxTcBranchPlan phx_tc_branch_plan_compute(int G, int B);
+// the simulation costs milliseconds: plans are cached per (K, M) (a handful of shapes per process; per translation unit)
 static inline PhxTcBranchPlan phx_tc_branch_plan(int G, int B) {
+    struct Entry { int G, B; PhxTcBranchPlan pl; };
+    static Entry cache[64];
+    static int n = 0;
+    static std::mutex mu;
+    std::lock_guard<std::mutex> lock(mu);
+    for (int i = 0; i < n; ++i)
+        if (cache[i].G == G && cache[i].B == B) return cache[i].pl;
+    PhxTcBranchPlan pl = phx_tc_branch_plan_compute(G, B);
+    if (n < 64) {
+        cache[n].G = G; cache[n].B = B; cache[n].pl = pl;
+        ++n;
+    }
+    return pl;
+}
+static inline PhxTcBranchPlan phx_tc_branch_plan_compute(int G, int B) {
     PhxTcBranchPlan pl;
     const int KB1 = phx_tc_KB1(G), chunk = phx_tc_chunk();
     const int nch = (KB1 + chunk - 1) / chunk;   // chunks along K
     pl.mtiles = (B + 127) / 128;
-    int ks_total = (2 * PHX_TC_SMS) / pl.mtiles;
-    if (ks_total < 2) ks_total = 2;
-    int ks_p = (ks_total * 5 + 4) / 9, ks_s = ks_total - ks_p;
-    if (ks_s < 1) ks_s = 1;
-    if (ks_p > nch) ks_p = nch;
-    if (ks_s > nch) ks_s = nch;
-    pl.per_p = (nch + ks_p - 1) / ks_p * chunk;
-    pl.per_s = (nch + ks_s - 1) / ks_s * chunk;
+    const double c_p = 1245.0, c_s = 1160.0, c_e = 1100.0, ovh = 30000.0;
+    const int kmax = nch < 24 ? nch : 24;
+    const double slot_cost = 6.0 * pl.mtiles * 128.0 / PHX_TC_SMS * 2.0;   // finishing pass: cycles per extra slot (rough)
+    double best = -1.0;
+    int bp = 1, bs = 1;
+    for (int kp = 1; kp <= kmax; ++kp) {
+        const int per_p = (nch + kp - 1) / kp;   // chunks per prods CTA
+        if ((nch + per_p - 1) / per_p != kp) continue;   // same split as a smaller kp
+        for (int ks = 1; ks <= kmax; ++ks) {
+            const int per_s = (nch + ks - 1) / ks;
+            if ((nch + per_s - 1) / per_s != ks) continue;
+            if ((long long)pl.mtiles * (kp + ks) > 16 * PHX_TC_SMS) continue;
+            const double m = phx_tc_makespan(pl.mtiles, pl.mtiles * kp, ovh + per_p * chunk * c_p, pl.mtiles * ks,
+                                             ovh + per_s * chunk * c_s) + slot_cost * (kp > ks ? kp : ks);
+            if (best < 0.0 || m < best) { best = m; bp = kp; bs = ks; }
+        }
+    }
+    pl.per_p = (nch + bp - 1) / bp * chunk;
+    pl.per_s = (nch + bs - 1) / bs * chunk;
     pl.ks_p = (KB1 + pl.per_p - 1) / pl.per_p;
     pl.ks_s = (KB1 + pl.per_s - 1) / pl.per_s;
+    best = -1.0;
+    int be = 1;
+    for (int ke = 1; ke <= kmax; ++ke) {
+        const int per_e = (nch + ke - 1) / ke;
+        if ((nch + per_e - 1) / per_e != ke) continue;
+        if ((long long)pl.mtiles * 2 * ke > 16 * PHX_TC_SMS) continue;
+        const double m = phx_tc_makespan(pl.mtiles, pl.mtiles * 2 * ke, ovh + per_e * chunk * c_e, 0, 0.0) + slot_cost * ke;
+        if (best < 0.0 || m < best) { best = m; be = ke; }
+    }
+    pl.per_e = (nch + be - 1) / be * chunk;
+    pl.ks_e = (KB1 + pl.per_e - 1) / pl.per_e;
     pl.slots = pl.ks_p > pl.ks_s ? pl.ks_p : pl.ks_s;
+    if (pl.ks_e > pl.slots) pl.slots = pl.ks_e;
     return pl;
 }
 // scratch of the tensor-core RHS in floats (partial-sum slots + [S|P] operand image), 128-byte aligned inside

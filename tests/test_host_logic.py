@@ -164,8 +164,9 @@ def test_resident_plan_places_the_weight_slices():
 
 def test_tensor_core_work_split_covers_k_exactly():
     """phx_tc_plan_describe (host only): every K-split is a whole number of 16-k-block chunks, the splits of each half
-    cover all k-blocks with no empty split, the partial-sum slots bound both halves, and the grid stays near two CTAs
-    per SM (148 SMs) unless the row tiles alone exceed that."""
+    cover all k-blocks with no empty split, the partial-sum slots bound both halves (and the equal-cost split of the
+    cotangent contractions), and the grid stays within 16 CTAs per SM (148 SMs) -- the splits come from a simulation of the
+    CTA dispatch (phx_tc.cuh) -- unless the row tiles alone exceed that."""
     import ctypes
     from phoenix_b200 import _lib
     lib = _lib.load()
@@ -179,6 +180,6 @@ def test_tensor_core_work_split_covers_k_exactly():
             for ks, per in ((ks_p, per_p), (ks_s, per_s)):
                 assert per % 16 == 0 and per >= 16
                 assert ks >= 1 and ks * per >= kb and (ks - 1) * per < kb, (K, M, ks, per, kb)
-            assert slots == max(ks_p, ks_s)
-            assert mtiles * (ks_p + ks_s) <= max(2 * 148 + 2 * mtiles, 2 * mtiles), (K, M, list(out))
+            assert slots >= max(ks_p, ks_s) and slots <= 24
+            assert mtiles * (ks_p + ks_s) <= max(16 * 148, 2 * mtiles), (K, M, list(out))
     assert lib.phx_tc_plan_describe(0, 5, out) != 0
