@@ -22,6 +22,7 @@
 //     gsimg  = spimg layout holding gSP
 // Hn = round_up(H, 16) (UMMA N granularity at M = 128); pads are zero in every image.
 #pragma once
+#include <stdio.h>
 #include <stdlib.h>
 #include <mutex>
 // (included from phx_common.cuh after phx_round_up)
@@ -164,6 +165,13 @@ static inline PhxTcBranchPlan phx_tc_branch_plan_compute(int G, int B) {
             const double m = phx_tc_makespan(pl.mtiles, pl.mtiles * kp, ovh + per_p * chunk * c_p, pl.mtiles * ks,
                                              ovh + per_s * chunk * c_s) + slot_cost * (kp > ks ? kp : ks);
             if (best < 0.0 || m < best) { best = m; bp = kp; bs = ks; }
+        }
+    }
+    if (const char* e = getenv("PHX_TC_KS")) {   // experiments: "ks_p,ks_s" for every shape of the process
+        int a = 0, b2 = 0;
+        if (sscanf(e, "%d,%d", &a, &b2) == 2 && a >= 1 && b2 >= 1) {
+            bp = a < nch ? a : nch;
+            bs = b2 < nch ? b2 : nch;
         }
     }
     pl.per_p = (nch + bp - 1) / bp * chunk;
