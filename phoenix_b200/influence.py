@@ -13,6 +13,9 @@ from . import parallel
 from .torchdiffeq import odeint
 
 
+_worker_streams = {}
+
+
 def _score_one(odenet, g, this_init, pert_col, t, method, G):
     unpert_out = odeint(odenet, this_init, t, method=method)
     this_init = this_init.clone()
@@ -43,7 +46,13 @@ def gene_influence_scores(odenet, genes, n_random_inputs_per_gene=60, time_pts=N
         return torch.empty(0)
     workers = max(1, min(int(workers), len(genes)))
     main = torch.cuda.current_stream(dev)
-    streams = [torch.cuda.Stream(device=dev) for _ in range(workers)] if workers > 1 else [main]
+    if workers > 1:   # the worker streams are kept: the solver workspaces are cached per stream (engine._workspace)
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), workers)
+        streams = _worker_streams.get(key)
+        if streams is None:
+            streams = _worker_streams[key] = [torch.cuda.Stream(device=dev) for _ in range(workers)]
+    else:
+        streams = [main]
 
     def draw(k):
         if inits is not None:
