@@ -149,11 +149,15 @@ class ClockSampler(threading.Thread):
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, rank=0):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rank, self.rows, self.stop_flag = index, rank, [], False
 
     def run(self):
+        # only rank 0 polls (its own GPU): an nvidia-smi process every 200 ms on each of 8 ranks is a host load the
+        # end-to-end leg can see.  (In-process NVML polling was tried instead: it slows the launch path, 1.88 -> 1.90 ms.)
+        if self.rank != 0:
+            return
         while not self.stop_flag:
             try:
                 out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
@@ -334,7 +338,7 @@ def run_ours(args):
     for _ in range(args.warmup):
         step_resident(False)
     torch.cuda.synchronize()
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(local, rank)
     sampler.start()
     ms_res = timed(lambda: step_resident(True), args.steps)
     evals = 0
