@@ -302,8 +302,8 @@ def run_ours(args):
             f1.record(stream)
             fwd_ev.append((f0, f1, BATCH))
         # d loss / d y(t1) for loss = mean((pred - target)^2) over the batch (train_insilico.py:132)
-        torch.sub(yout[:, 1], target_d, out=grad_y[:, 1])
-        grad_y[:, 1].mul_(2.0 / (BATCH * G))
+        _lib.check(lib.phx_mse_grad(ctx, BATCH, G, ctypes.c_void_p(yout.data_ptr() + 4 * G), 2 * G, ptr(target_d),
+                                    2.0 / (BATCH * G), ctypes.c_void_p(grad_y.data_ptr() + 4 * G), 2 * G, sp), "mse_grad")
         if record:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
@@ -499,7 +499,7 @@ def run_ours(args):
                            "loss.backward(), pinned host inputs",
                     "per_sample_api_value": work_per_step / (ms_e2e_loop / args.steps / 1e3),
                     "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130"},
-            "gpu_launches": args.steps * 4,   # forward rows, adjoint rows, 2 x unpack (+ 2 ATen elementwise for the loss grad)
+            "gpu_launches": args.steps * 5,   # forward rows, loss cotangent, adjoint rows, 2 x unpack
             "roofline": {"bound": "hbm", "kernel": "phx_rows_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "launch_ms": adj_ms, "algorithmic_bytes": alg,

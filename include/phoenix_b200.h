@@ -243,6 +243,13 @@ size_t phx_packed_grad_bytes(int G, int H);
 int phx_rows_grad_parts(const phx_ctx* ctx, int G, int H, int N);
 int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int nparts, float* grads_flat,
                      int accumulate, void* stream);
+/* Cotangent of the data loss of training_step, loss = torch.mean((predictions - targets)**2) (train_insilico.py:132):
+ * grad[r][g] = scale * (pred[r][g] - target[r][g]) for `rows` samples of G genes, scale = 2 / (rows * G); pred and grad
+ * rows are pred_stride / grad_stride floats apart (the t1 slices of the [N][T][G] solver output and of grad_y), target is
+ * dense [rows][G].  What autograd computes for that line; lets a C-ABI caller go from phx_solve_forward_rows to
+ * phx_solve_adjoint_rows without leaving the library. */
+int phx_mse_grad(phx_ctx* ctx, int rows, int G, const float* pred, size_t pred_stride, const float* target, float scale,
+                 float* grad, size_t grad_stride, void* stream);
 
 /* ---- multi-GPU: the one exchange of the path ------------------------------------------------------------------
  * The reference has no distributed code; with the samples of train_insilico.py:128-130 sharded over the GPUs of one box

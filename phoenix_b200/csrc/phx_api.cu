@@ -87,6 +87,17 @@ __global__ void unpack_w1_kernel(int G, int H, int Hp, int K2, const float* __re
         *dst = accumulate ? *dst + v : v;
     }
 }
+// cotangent of the data loss of training_step (train_insilico.py:132, torch.mean((predictions - targets)**2)):
+// grad[r][g] = scale * (pred[r][g] - target[r][g]), rows of pred / grad `stride` floats apart (the t1 slices of [N][T][G])
+__global__ void mse_grad_kernel(int rows, int G, const float* __restrict__ pred, size_t pred_stride,
+                                const float* __restrict__ target, float scale, float* __restrict__ grad,
+                                size_t grad_stride) {
+    const size_t n = (size_t)rows * G, step = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const size_t r = i / G, g = i - r * G;
+        grad[r * grad_stride + g] = scale * (pred[r * pred_stride + g] - target[i]);
+    }
+}
 __global__ void unpack_rest_kernel(int G, int H, int Hp, int K2, const float* __restrict__ wabar,
                                    const float* __restrict__ biasbar, const float* __restrict__ mbar, int nparts,
                                    size_t pstride, float* __restrict__ Wa, float* __restrict__ bs,
@@ -639,6 +650,25 @@ int phx_unpack_grads(phx_ctx* ctx, int G, int H, const float* packed_grads, int 
 }
 
 size_t phx_packed_grad_bytes(int G, int H) { return phx_packed_grad_offsets(G, H).total * sizeof(float); }
+
+int phx_mse_grad(phx_ctx* ctx, int rows, int G, const float* pred, size_t pred_stride, const float* target, float scale,
+                 float* grad, size_t grad_stride, void* stream) {
+    if (!ctx || rows < 1 || G < 1 || !pred || !target || !grad) {
+        phx_set_error("mse_grad: invalid argument");
+        return PHX_ERR_INVALID;
+    }
+    PhxDevGuard dev_guard(ctx);
+    const size_t n = (size_t)rows * G;
+    int blocks = (int)((n + 255) / 256);
+    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
+    mse_grad_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(rows, G, pred, pred_stride, target, scale, grad, grad_stride);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        phx_set_error("mse_grad launch: %s", cudaGetErrorString(e));
+        return PHX_ERR_CUDA;
+    }
+    return PHX_OK;
+}
 
 int phx_solve_adjoint_rows(phx_ctx* ctx, int G, int H, int N, const float* packed, const double* t_host, int T,
                            int t_is_f32, int method, double rtol, double atol, int64_t max_num_steps,

@@ -68,3 +68,25 @@ def test_training_step_gradients_match_the_oracle(method):
         assert abs(lp - loss_prior) <= 1e-5 * abs(loss_prior)
         for i, (g, r) in enumerate(zip(grads, ref)):
             assert rel_l2(g, r) < 5e-5, (method, many, i, rel_l2(g, r))
+
+
+def test_mse_grad_entry_point_matches_autograd():
+    """phx_mse_grad = the cotangent autograd forms for torch.mean((predictions - targets)**2) (train_insilico.py:132), on
+    the t1 slices of a [N][T][G] solver output (strided rows), bit for bit the same arithmetic (one sub, one mul)."""
+    import ctypes
+    from phoenix_b200 import _lib
+    lib, ctx = _lib.load(), _lib.ctx(0)
+    N, T, G = 5, 2, 1037
+    gen = torch.Generator().manual_seed(3)
+    yout = torch.rand(N, T, 1, G, generator=gen).cuda()
+    target = torch.rand(N, 1, G, generator=gen).cuda()
+    pred = yout[:, 1].clone().requires_grad_(True)
+    torch.mean((pred - target) ** 2).backward()
+    gy = torch.zeros_like(yout)
+    sp = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    rc = lib.phx_mse_grad(ctx, N, G, ctypes.c_void_p(yout.data_ptr() + 4 * G), T * G, ctypes.c_void_p(target.data_ptr()),
+                          2.0 / (N * G), ctypes.c_void_p(gy.data_ptr() + 4 * G), T * G, sp)
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert float(gy[:, 0].abs().max()) == 0.0
+    assert float((gy[:, 1] - pred.grad).abs().max()) <= 1e-7 * float(pred.grad.abs().max())
