@@ -136,6 +136,15 @@ size_t phx_rhs_workspace_bytes(int G, int H, int B);
  * backward is  phx_rhs_vjp(ctx, G, H, B, packed, x, gcot, 0, NULL, grads_flat, PHX_VJP_REUSE_FORWARD, workspace, ...). */
 int phx_prior_loss(phx_ctx* ctx, int G, int H, int B, const float* packed, const float* x, const float* prior_grad,
                    float scale, float* gcot, float* loss, void* workspace, size_t workspace_bytes, void* stream);
+/* Cached Hill activations of a CONSTANT input.  batch_for_prior is drawn once before the epoch loop
+ * (train_insilico.py:208) and is the same matrix at every optimiser step; phx_hill_planes evaluates
+ * s = SoftsignMod(x) and l = LogShiftedSoftSignMod(x) (odenet.py:21-35) for n = rows * G elements once, and while
+ * phx_hill_cache_set(ctx, x, n, s, l) is in force every tensor-core contraction whose activation operand is that x
+ * (phx_prior_loss, phx_rhs_forward, the Ws_bar | Wp_bar part of phx_rhs_vjp) reads the planes instead of
+ * re-evaluating the activations (same values bit for bit).  The caller scopes the entry around its launches and
+ * clears it with s = l = NULL; the planes must stay valid until the enqueued work has run. */
+int phx_hill_planes(phx_ctx* ctx, size_t n, const float* x, float* s_plane, float* l_plane, void* stream);
+int phx_hill_cache_set(phx_ctx* ctx, const float* x, size_t n, const float* s_plane, const float* l_plane);
 /* prior_grad[B][G] = x[B][G] @ prior_mat[G][G] (train_insilico.py:209) for a sparse prior in CSC form (column j of
  * prior_mat = rows rowidx[colptr[j] .. colptr[j+1]) with values val[...]; all device pointers). */
 int phx_prior_setup(phx_ctx* ctx, int G, int B, const float* x, const int32_t* colptr, const int32_t* rowidx,

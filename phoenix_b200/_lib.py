@@ -25,7 +25,7 @@ EXPORTS = [
     "phx_stream_workspace_bytes", "phx_stream_solve_forward", "phx_stream_solve_adjoint",
     "phx_rows_supported", "phx_rows_plan_describe", "phx_rows_workspace_bytes", "phx_solve_forward_rows",
     "phx_solve_adjoint_rows", "phx_unpack_grads", "phx_packed_grad_bytes", "phx_rows_grad_parts",
-    "phx_prior_loss", "phx_prior_setup", "phx_tc_set_pair", "phx_tc_prof_dump", "phx_ctx_set_global_norm", "phx_peer_allreduce", "phx_peer_allreduce_nvls", "phx_mse_grad",
+    "phx_prior_loss", "phx_prior_setup", "phx_tc_set_pair", "phx_tc_prof_dump", "phx_ctx_set_global_norm", "phx_peer_allreduce", "phx_peer_allreduce_nvls", "phx_mse_grad", "phx_hill_planes", "phx_hill_cache_set",
 ]
 
 
@@ -145,6 +145,10 @@ def _declare(lib):
     lib.phx_mse_grad.argtypes = [c_void_p, c_int, c_int, c_void_p, c_size_t, c_void_p, ctypes.c_float, c_void_p, c_size_t,
                                  c_void_p]
     lib.phx_mse_grad.restype = c_int
+    lib.phx_hill_planes.argtypes = [c_void_p, c_size_t, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.phx_hill_planes.restype = c_int
+    lib.phx_hill_cache_set.argtypes = [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]
+    lib.phx_hill_cache_set.restype = c_int
     lib.phx_peer_allreduce_nvls.argtypes = [c_void_p, c_void_p, c_void_p, c_int, c_int, c_size_t, ctypes.c_uint,
                                             ctypes.c_float, c_void_p]
     lib.phx_peer_allreduce_nvls.restype = c_int

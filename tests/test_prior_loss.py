@@ -93,3 +93,41 @@ def test_fused_prior_loss_small_batch_and_large_shape():
                 assert p.grad is None or not p.grad.any()
             else:
                 assert rel_l2(p.grad.cpu(), ref) < 2e-5, (G, i, rel_l2(p.grad.cpu(), ref))
+
+
+@pytest.mark.gpu
+def test_cached_activations_of_the_prior_batch_change_nothing():
+    """prior_loss caches soft-sign / log1p of the constant prior batch (phx_hill_planes) and feeds the contractions from
+    the planes: same loss and gradients as the uncached path (rounding level: the K ranges of the two launches differ),
+    recomputed when the batch is modified in place."""
+    import phoenix_b200 as pb
+    from phoenix_b200 import prior
+    torch.manual_seed(3)
+    G, H, K = 1037, 56, 700
+    net = pb.ODENet("cuda", G, neurons=H)
+    x = (torch.rand(K, 1, G, device="cuda") - 0.5) * 3.0       # beyond the series range of log1p as well
+    pg = torch.randn(K, 1, G, device="cuda") * 0.1
+
+    def run():
+        net.zero_grad()
+        loss = pb.prior_loss(net, x, pg)
+        loss.backward()
+        return float(loss), [p.grad.clone() for p in net.parameters() if p.grad is not None]
+
+    prior.CACHE_ACTIVATIONS = False
+    l0, g0 = run()
+    prior.CACHE_ACTIVATIONS = True
+    try:
+        l1, g1 = run()
+        l2, g2 = run()                       # second call: planes come from the cache
+        assert len(prior._hill_planes) == 1
+        assert abs(l1 - l0) <= 1e-6 * abs(l0) and l2 == l1
+        for a, b, c in zip(g0, g1, g2):
+            assert float((a - b).norm() / a.norm()) < 2e-6 and torch.equal(b, c)
+        x.mul_(0.5)                           # in-place edit: the planes are recomputed
+        l3, _ = run()
+        prior.CACHE_ACTIVATIONS = False
+        l4, _ = run()
+        assert abs(l3 - l4) <= 1e-6 * abs(l4) and abs(l3 - l1) > 1e-3 * abs(l1)
+    finally:
+        prior.CACHE_ACTIVATIONS = True
