@@ -304,6 +304,70 @@ def _steplog():
     return log, STEPLOG_CAP
 
 
+# ---- cached Hill activations of constant inputs (csrc/phx_tc.cu, "cached Hill activations") ------------------------------
+# (data_ptr, numel) -> (weakref to the caller's tensor, its version, s plane, l plane)
+_hill_planes = {}
+_hill_seen = {}
+CACHE_ACTIVATIONS = True   # 2 x the size of the cached input in HBM (0.9 GB for the 10 000 x 11 165 prior batch)
+
+
+def hill_planes_for(x2, src, dev):
+    """s(x), l(x) planes of x2 (contiguous fp32 view of the caller's tensor `src`), cached while `src` is alive and
+    unmodified; None when caching is off or x2 is a converted copy."""
+    import weakref
+    if not CACHE_ACTIVATIONS or x2.data_ptr() != src.data_ptr():
+        return None
+    key = (x2.data_ptr(), x2.numel())
+    ent = _hill_planes.get(key)
+    if ent is not None and ent[0]() is src and ent[1] == src._version:
+        return ent[2], ent[3]
+    for k in [k for k, v in _hill_planes.items() if v[0]() is None]:   # the owner is gone: drop its planes
+        del _hill_planes[k]
+    lib = _lib.load()
+    sp, lp = torch.empty_like(x2), torch.empty_like(x2)
+    _lib.check(lib.phx_hill_planes(_lib.ctx(dev), x2.numel(), _ptr(x2), _ptr(sp), _ptr(lp), _stream_ptr(dev)),
+               "hill_planes")
+    _hill_planes[key] = (weakref.ref(src), src._version, sp, lp)
+    return sp, lp
+
+
+def _auto_hill_planes(x2, src, dev):
+    """prior_only_forward is only ever fed the constant prior batch (train_insilico.py:134): the second time the same
+    unmodified tensor comes by, its activations are cached (the first sighting only leaves a note)."""
+    import weakref
+    if not CACHE_ACTIVATIONS or x2.data_ptr() != src.data_ptr():
+        return None
+    key = (x2.data_ptr(), x2.numel())
+    ent = _hill_planes.get(key)
+    if ent is not None and ent[0]() is src and ent[1] == src._version:
+        return ent[2], ent[3]
+    seen = _hill_seen.get(key)
+    if seen is not None and seen[0]() is src and seen[1] == src._version:
+        return hill_planes_for(x2, src, dev)
+    if len(_hill_seen) > 64:
+        _hill_seen.clear()
+    _hill_seen[key] = (weakref.ref(src), src._version)
+    return None
+
+
+class hill_cache:
+    """Scope in which the library reads cached planes for the contractions over x2.  The entry is set right before and
+    cleared right after the launches: a stale one would silently feed another tensor allocated at the same address."""
+
+    def __init__(self, dev, x2, planes):
+        self.dev, self.x2, self.planes = dev, x2, planes
+
+    def __enter__(self):
+        if self.planes is not None:
+            _lib.load().phx_hill_cache_set(_lib.ctx(self.dev), _ptr(self.x2), self.x2.numel(), _ptr(self.planes[0]),
+                                           _ptr(self.planes[1]))
+
+    def __exit__(self, *exc):
+        if self.planes is not None:
+            _lib.load().phx_hill_cache_set(_lib.ctx(self.dev), None, 0, None, None)
+        return False
+
+
 # ---- RHS -----------------------------------------------------------------------------------------------------------------
 def _rhs_signature(net, packed, y2, B):
     key = _pack_cache.get(net)
@@ -323,8 +387,10 @@ def rhs_forward(net, y, decay):
     f = torch.empty_like(y2)
     nb = lib.phx_rhs_workspace_bytes(G, H, B)
     ws = _workspace(dev, nb, "rhs")
-    _lib.check(lib.phx_rhs_forward(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(f), int(decay), _ptr(ws),
-                                   ws.numel(), _stream_ptr(dev)), "rhs_forward")
+    planes = _auto_hill_planes(y2, y, dev) if (not decay and B >= lib.phx_tc_min_rows()) else None
+    with hill_cache(dev, y2, planes):
+        _lib.check(lib.phx_rhs_forward(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(f), int(decay), _ptr(ws),
+                                       ws.numel(), _stream_ptr(dev)), "rhs_forward")
     with _state.lock:
         _last_rhs[ws.data_ptr()] = _rhs_signature(net, packed, y2, B)
     return f
@@ -346,8 +412,12 @@ def rhs_vjp(net, y, g, decay, need_ybar=True, need_grads=True, flat=False):
     # forward, then composed_loss.backward()): tell the library not to recompute it
     with _state.lock:
         reuse = _last_rhs.pop(ws.data_ptr(), None) == _rhs_signature(net, packed, y2, B)
-    _lib.check(lib.phx_rhs_vjp(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(g2), int(decay), _ptr(ybar),
-                               _ptr(grads), 2 if reuse else 0, _ptr(ws), ws.numel(), _stream_ptr(dev)), "rhs_vjp")
+    ent = _hill_planes.get((y2.data_ptr(), y2.numel())) if (not decay and CACHE_ACTIVATIONS) else None
+    planes = (ent[2], ent[3]) if (ent is not None and ent[0]() is not None and ent[1] == y._version
+                                  and y2.data_ptr() == y.data_ptr()) else None
+    with hill_cache(dev, y2, planes):
+        _lib.check(lib.phx_rhs_vjp(_lib.ctx(dev), G, H, B, _ptr(packed), _ptr(y2), _ptr(g2), int(decay), _ptr(ybar),
+                                   _ptr(grads), 2 if reuse else 0, _ptr(ws), ws.numel(), _stream_ptr(dev)), "rhs_vjp")
     if flat:   # the caller scales / splits the [P] vector itself
         return ybar, grads
     return ybar, (split_flat_grads(grads, G, H) if need_grads else None)

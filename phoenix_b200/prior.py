@@ -44,46 +44,8 @@ def prior_grad_from_matrix(batch_for_prior, prior_mat):
     return out
 
 
-# Hill activations of the (constant) prior batch, evaluated once: (data_ptr, version, numel) -> (weakref to x, s, l)
-_hill_planes = {}
-CACHE_ACTIVATIONS = True   # 2 x the size of batch_for_prior in HBM (0.9 GB at 10 000 x 11 165)
-
-
-def _planes_for(x2, src, dev):
-    """s(x), l(x) planes of x2 (contiguous fp32), cached while `src` (the caller's tensor) is alive and unmodified."""
-    import weakref
-    if not CACHE_ACTIVATIONS or x2.data_ptr() != src.data_ptr():   # a converted copy of the caller's tensor: not cacheable
-        return None
-    key = (x2.data_ptr(), x2.numel())
-    ent = _hill_planes.get(key)
-    if ent is not None and ent[0]() is src and ent[1] == src._version:
-        return ent[2], ent[3]
-    for k in [k for k, e in _hill_planes.items() if e[0]() is None]:   # the owner is gone: drop its planes
-        del _hill_planes[k]
-    lib = _lib.load()
-    sp, lp = torch.empty_like(x2), torch.empty_like(x2)
-    _lib.check(lib.phx_hill_planes(_lib.ctx(dev), x2.numel(), engine._ptr(x2), engine._ptr(sp), engine._ptr(lp),
-                                   engine._stream_ptr(dev)), "hill_planes")
-    _hill_planes[key] = (weakref.ref(src), src._version, sp, lp)
-    return sp, lp
-
-
-class _hill_cache:
-    """Scope in which the library reads the cached planes for contractions over x2 (prior.py only: a stale entry would
-    silently feed another tensor at the same address, so it is set right before and cleared right after the launches)."""
-
-    def __init__(self, dev, x2, planes):
-        self.dev, self.x2, self.planes = dev, x2, planes
-
-    def __enter__(self):
-        if self.planes is not None:
-            _lib.load().phx_hill_cache_set(_lib.ctx(self.dev), engine._ptr(self.x2), self.x2.numel(),
-                                           engine._ptr(self.planes[0]), engine._ptr(self.planes[1]))
-
-    def __exit__(self, *exc):
-        if self.planes is not None:
-            _lib.load().phx_hill_cache_set(_lib.ctx(self.dev), None, 0, None, None)
-        return False
+_planes_for = engine.hill_planes_for
+_hill_cache = engine.hill_cache
 
 
 class _PriorLoss(torch.autograd.Function):
@@ -100,7 +62,7 @@ class _PriorLoss(torch.autograd.Function):
             ws = engine._workspace(dev, lib.phx_rhs_workspace_bytes(G, H, B), "rhs")
             gcot = torch.empty_like(x2)
             loss = torch.empty(1, dtype=torch.float32, device=x2.device)
-            planes = _planes_for(x2, x, dev) if B >= lib.phx_tc_min_rows() else None
+            planes = engine.hill_planes_for(x2, x, dev) if B >= lib.phx_tc_min_rows() else None
             with _hill_cache(dev, x2, planes):
                 _lib.check(lib.phx_prior_loss(_lib.ctx(dev), G, H, B, engine._ptr(packed), engine._ptr(x2),
                                               engine._ptr(pg), ctypes.c_float(2.0 / (B * G)), engine._ptr(gcot),

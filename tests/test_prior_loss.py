@@ -101,7 +101,7 @@ def test_cached_activations_of_the_prior_batch_change_nothing():
     the planes: same loss and gradients as the uncached path (rounding level: the K ranges of the two launches differ),
     recomputed when the batch is modified in place."""
     import phoenix_b200 as pb
-    from phoenix_b200 import prior
+    from phoenix_b200 import engine as prior      # the cache lives in the engine
     torch.manual_seed(3)
     G, H, K = 1037, 56, 700
     net = pb.ODENet("cuda", G, neurons=H)
@@ -129,5 +129,24 @@ def test_cached_activations_of_the_prior_batch_change_nothing():
         prior.CACHE_ACTIVATIONS = False
         l4, _ = run()
         assert abs(l3 - l4) <= 1e-6 * abs(l4) and abs(l3 - l1) > 1e-3 * abs(l1)
+        # the reference's own two lines (train_insilico.py:134-135): prior_only_forward caches from the second sighting on
+        prior.CACHE_ACTIVATIONS = True
+        prior._hill_planes.clear()
+        prior._hill_seen.clear()
+        outs = []
+        for _ in range(3):
+            net.zero_grad()
+            lp = torch.mean((net.prior_only_forward(None, x) - pg) ** 2)
+            lp.backward()
+            outs.append((float(lp), net.net_sums.linear_out.weight.grad.clone()))
+        assert len(prior._hill_planes) == 1
+        assert abs(outs[1][0] - outs[0][0]) <= 1e-6 * abs(outs[0][0]) and outs[2][0] == outs[1][0]
+        assert float((outs[1][1] - outs[0][1]).norm() / outs[0][1].norm()) < 2e-6 and torch.equal(outs[1][1], outs[2][1])
+        assert abs(outs[0][0] - l3) <= 1e-5 * abs(l3)
+        # ODENet.forward (the ODE right-hand side, a new state every call) never caches
+        y = torch.rand(K, G, device="cuda")
+        for _ in range(3):
+            net(None, y)
+        assert len(prior._hill_planes) == 1
     finally:
         prior.CACHE_ACTIVATIONS = True
