@@ -498,7 +498,8 @@ def run_ours(args):
                     "api": "phoenix_b200.odeint_adjoint_many (sample loop of training_step inside the library) + "
                            "loss.backward(), pinned host inputs",
                     "per_sample_api_value": work_per_step / (ms_e2e_loop / args.steps / 1e3),
-                    "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130"},
+                    "per_sample_api": "phoenix_b200.odeint_adjoint once per sample, as train_insilico.py:128-130 (17 forward "
+                                      "launches; the 17 adjoint nodes of the backward pass share one lock-step call)"},
             "gpu_launches": args.steps * 5,   # forward rows, loss cotangent, adjoint rows, 2 x unpack
             "roofline": {"bound": "hbm", "kernel": "phx_rows_adj_kernel", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,

@@ -8,8 +8,8 @@ from . import engine
 from .engine import check_errors, last_status, last_step_log, set_precision, set_step_logging, set_sync_errors
 from .odenet import ODENet, LogShiftedSoftSignMod, SoftsignMod
 from .prior import prior_grad_from_matrix, prior_loss
-from .torchdiffeq import odeint, odeint_adjoint, odeint_adjoint_many
+from .torchdiffeq import odeint, odeint_adjoint, odeint_adjoint_many, set_deferred_adjoint
 
 __all__ = ["ODENet", "SoftsignMod", "LogShiftedSoftSignMod", "odeint", "odeint_adjoint", "odeint_adjoint_many", "prior_loss",
            "prior_grad_from_matrix", "engine", "check_errors",
-           "last_status", "last_step_log", "set_precision", "set_step_logging", "set_sync_errors"]
+           "last_status", "last_step_log", "set_precision", "set_step_logging", "set_sync_errors", "set_deferred_adjoint"]

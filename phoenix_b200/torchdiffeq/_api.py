@@ -1,6 +1,8 @@
 """``odeint`` / ``odeint_adjoint`` with the reference's call surface (torchdiffeq/_impl/odeint.py:25-69,
 adjoint.py:165-204) — argument normalisation follows misc.py:165-241 — dispatching to the CUDA solvers."""
+import threading
 import warnings
+import weakref
 
 import torch
 import torch.nn as nn
@@ -77,9 +79,92 @@ def odeint(func, y0, t, rtol=1e-7, atol=1e-9, method=None, options=None):
         return engine.solve_forward(func, y0, tl, t_is_f32, rev, method, rtol, atol, max_steps)
 
 
+# ---- the per-sample loop of training_step, backward side ----------------------------------------------------------------
+# train_insilico.py:128-130 calls odeint once per sample and backpropagates one loss, so autograd meets N independent
+# adjoint nodes of the same model in one backward pass.  Each is a one-row problem, and a pass of the rows kernels
+# costs the same with one row as with four -- so the nodes of one backward pass hand their cotangents to
+# the LAST of them to run, which solves all the sweeps in one lock-step call (engine.solve_adjoint_many, the backward of
+# odeint_adjoint_many) and returns the summed parameter cotangents as its own; the others return None (= zero).  What
+# autograd accumulates -- into .grad or into torch.autograd.grad's outputs -- is the same sum.  A node whose y0 needs a
+# gradient, or that is alone in its pass, runs its own sweep as before.
+DEFER_ADJOINT = True
+_NOT_DEFERRED = object()
+_defer_lock = threading.RLock()
+_live_nodes = weakref.WeakKeyDictionary()   # ODENet -> WeakSet of adjoint nodes (autograd contexts) built on it
+_deferred = {}                               # (graph task id, group key) -> [expected count, [(seq, y, grad_y, tl), ...]]
+_node_seq = [0]
+
+
+def set_deferred_adjoint(flag):
+    """Batch the backward sweeps of the per-sample ``odeint_adjoint`` nodes of one backward pass (default on)."""
+    global DEFER_ADJOINT
+    DEFER_ADJOINT = bool(flag)
+
+
+def _register_node(ctx, func, y0, tl, t_is_f32, adj):
+    """Forward side: note the node if its backward may be batched with its siblings' (a one-row state that needs no
+    gradient itself -- the training loop's case)."""
+    ctx.group = None
+    if not DEFER_ADJOINT or ctx.needs_input_grad[8] or y0.numel() != y0.shape[-1]:
+        return
+    with _defer_lock:
+        _node_seq[0] += 1
+        ctx.seq = _node_seq[0]
+        ctx.group = (len(tl), t_is_f32, adj, tuple(y0.shape), y0.device, tuple(ctx.needs_input_grad[9:]))
+        nodes = _live_nodes.get(func)
+        if nodes is None:
+            nodes = _live_nodes[func] = weakref.WeakSet()
+        nodes.add(ctx)
+
+
+def _unresolved(key):
+    def check():
+        with _defer_lock:
+            ent = _deferred.pop(key, None)
+        if ent is not None:
+            raise RuntimeError("phoenix_b200: %d of %d odeint_adjoint nodes of this backward pass handed their cotangents "
+                               "to a sibling that never ran, so their parameter gradients are missing; call "
+                               "phoenix_b200.torchdiffeq.set_deferred_adjoint(False) and report this"
+                               % (len(ent[1]), ent[0]))
+    return check
+
+
+def _defer(ctx, y, grad_y):
+    """Backward side.  Returns _NOT_DEFERRED (the caller solves its own sweep), the all-None tuple (the cotangent waits for
+    the last sibling) or, in the last sibling, (t_rows, ys, gys) of every waiting node in creation order."""
+    try:
+        gid = torch._C._current_graph_task_id()
+        will_run = torch._C._will_engine_execute_node
+        queue_callback = torch.autograd.Variable._execution_engine.queue_callback
+    except AttributeError:
+        return _NOT_DEFERRED
+    if gid < 0:
+        return _NOT_DEFERRED
+    key = (gid, id(ctx.func), ctx.group)
+    with _defer_lock:
+        ent = _deferred.get(key)
+        if ent is None:
+            try:
+                peers = [c for c in list(_live_nodes.get(ctx.func, ())) if c.group == ctx.group and will_run(c)]
+            except Exception:
+                return _NOT_DEFERRED
+            if len(peers) < 2 or not any(c is ctx for c in peers):
+                return _NOT_DEFERRED
+            for k in [k for k in _deferred if k[0] < gid - 8]:   # passes that died with an exception
+                del _deferred[k]
+            ent = _deferred[key] = [len(peers), []]
+            queue_callback(_unresolved(key))   # runs when this backward pass ends: loud if a counted sibling never came
+        ent[1].append((ctx.seq, y, grad_y, ctx.tl))
+        if len(ent[1]) < ent[0]:
+            return None
+        del _deferred[key]
+    items = sorted(ent[1], key=lambda it: it[0])
+    return [it[3] for it in items], torch.stack([it[1] for it in items]), torch.stack([it[2] for it in items])
+
+
 class OdeintAdjointMethod(torch.autograd.Function):
     """adjoint.py:10-162: forward = solve under no_grad, keep only y(t); backward = one device-side sweep of the
-    augmented system per output interval."""
+    augmented system per output interval (batched with the sibling nodes of the same backward pass, see above)."""
 
     @staticmethod
     def forward(ctx, func, tl, t_is_f32, method, rtol, atol, max_steps, adj, y0, *adjoint_params):
@@ -87,15 +172,24 @@ class OdeintAdjointMethod(torch.autograd.Function):
         with torch.no_grad():
             y = engine.solve_forward(func, y0, tl, t_is_f32, False, method, rtol, atol, max_steps)
         ctx.save_for_backward(y)
+        _register_node(ctx, func, y0, tl, t_is_f32, adj)
         return y
 
     @staticmethod
     def backward(ctx, grad_y):
         (y,) = ctx.saved_tensors
         a_method, a_rtol, a_atol, a_max = ctx.adj
+        batch = _defer(ctx, y, grad_y) if (ctx.group is not None and DEFER_ADJOINT) else _NOT_DEFERRED
+        if batch is None:
+            return (None,) * (9 + len(ctx.needs_input_grad[9:]))
         with torch.no_grad():
-            adj_y0, grads = engine.solve_adjoint(ctx.func, ctx.tl, ctx.t_is_f32, a_method, a_rtol, a_atol, a_max,
-                                                 y, grad_y)
+            if batch is _NOT_DEFERRED:
+                adj_y0, grads = engine.solve_adjoint(ctx.func, ctx.tl, ctx.t_is_f32, a_method, a_rtol, a_atol, a_max,
+                                                     y, grad_y)
+            else:
+                t_rows, ys, gys = batch
+                adj_y0, grads = engine.solve_adjoint_many(ctx.func, t_rows, ctx.t_is_f32, a_method, a_rtol, a_atol,
+                                                          a_max, ys, gys)
         out = [None] * 8 + [adj_y0 if ctx.needs_input_grad[8] else None]
         for i, need in enumerate(ctx.needs_input_grad[9:]):
             out.append(grads[i] if need else None)

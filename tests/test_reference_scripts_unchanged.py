@@ -86,6 +86,12 @@ def _oracle_engine(monkeypatch):
                                            atol=atol)
         return ady, grads
 
+    def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps, y_saved, grad_y):
+        # the sibling nodes of one backward pass share one call (_api.py, "backward side"): sum over the samples
+        parts = [solve_adjoint(net, t_rows[i], t_is_f32, method, rtol, atol, max_num_steps, y_saved[i], grad_y[i])
+                 for i in range(len(t_rows))]
+        return torch.stack([p[0] for p in parts]), [sum(p[1][k] for p in parts) for k in range(6)]
+
     def rhs_forward(net, y, decay):
         return O.rhs(weights(net), y.detach(), decay=bool(decay))
 
@@ -93,7 +99,8 @@ def _oracle_engine(monkeypatch):
         _, ybar, pbar = O.rhs_vjp(weights(net), y.detach(), g.detach(), decay=bool(decay))
         return ybar, pbar
 
-    for name, fn in (("solve_forward", solve_forward), ("solve_adjoint", solve_adjoint), ("rhs_forward", rhs_forward),
+    for name, fn in (("solve_forward", solve_forward), ("solve_adjoint", solve_adjoint),
+                     ("solve_adjoint_many", solve_adjoint_many), ("rhs_forward", rhs_forward),
                      ("rhs_vjp", rhs_vjp)):
         monkeypatch.setattr(engine, name, fn)
 
