@@ -332,9 +332,46 @@ int phx_resident_plan(int num_sms, int G, int H, int B, int adjoint, ResLaunchPl
 size_t phx_resident_workspace_floats(int G, int H, int B, int T, int adjoint, size_t* off_t, size_t* off_theta1);
 int phx_resident_launch(const ResParams& p, const ResLaunchPlan& plan, cudaStream_t stream);
 
-// host helpers implemented in phx_rhs.cu
+// ---- RK stage algebra fused into the RHS (streaming solvers, forward solves on the tensor-core path) ------------------
+// With k = the stage derivative a forward RHS launch produces, the epilogue of the joint contraction also writes
+//   PHX_POST_CHAIN : out = x0 + (c[0] k[0] + ... + c[nk-1] k[nk-1] + cr k)   one fmaf chain in this order (the adaptive
+//                    solver's next stage input / y1, rk_common.py:66)
+//   PHX_POST_FX_*  : one of the fixed-grid formulas exactly as fixed_grid.py / rk_common.py:96-103 write them, with k in
+//                    the place of the newest derivative and k[0..] the older ones
+// next to (store_f) or instead of k itself.  out may be the buffer the launch reads its state from: every element is read
+// and written by the same thread.  phx_fixed_formula is THE definition both the fused epilogue and the stand-alone
+// elementwise kernels of phx_stream.cu evaluate (no FMA contraction: the library is built with -fmad=false).
+enum { PHX_POST_NONE = 0, PHX_POST_CHAIN = 1, PHX_POST_FX = 2 };   // mode = PHX_POST_FX + one of the PHX_FX_* below
+enum { PHX_FX_EULER_END = 0, PHX_FX_MID_IN = 1, PHX_FX_RK4_IN2 = 2, PHX_FX_RK4_IN3 = 3, PHX_FX_RK4_IN4 = 4,
+       PHX_FX_RK4_END = 5 };
+struct PhxRhsPost {
+    int mode;      // PHX_POST_*
+    int nk;        // older derivatives read from k[0..nk-1]
+    int store_f;   // 0: the launch's own f is not written (the last stage of a fixed-grid step)
+    float dt;      // PHX_POST_FX_*: the step (half the step for PHX_FX_MID_IN)
+    const float* x0;
+    const float* k[6];
+    float c[6];    // PHX_POST_CHAIN: coefficients of k[0..nk-1]
+    float cr;      // PHX_POST_CHAIN: coefficient of the launch's own derivative
+    float* out;
+};
+static __host__ __device__ __forceinline__ float phx_fixed_formula(int mode, float x, float a1, float a2, float a3, float a4,
+                                                            float dt) {
+    const float third = (float)(1.0 / 3.0);
+    switch (mode) {
+        case PHX_FX_EULER_END: return x + dt * a1;
+        case PHX_FX_MID_IN: return x + a1 * dt;  // dt carries half_dt here
+        case PHX_FX_RK4_IN2: return x + dt * a1 * third;
+        case PHX_FX_RK4_IN3: return x + dt * (a2 - a1 * third);
+        case PHX_FX_RK4_IN4: return x + dt * (a1 - a2 + a3);
+        default: return x + (a1 + 3.f * (a2 + a3) + a4) * dt * 0.125f;
+    }
+}
+
+// host helpers implemented in phx_rhs.cu.  `post` (optional) needs phx_rhs_post_supported(w, H, B).
 int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
-                           float* ws, cudaStream_t stream);
+                           float* ws, cudaStream_t stream, const PhxRhsPost* post = nullptr);
+bool phx_rhs_post_supported(const PhxPacked& w, int H, int B);
 int phx_rhs_vjp_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,
                        float* ybar, float* grads_flat, int accumulate, float* f_out, float fscale, float* ws,
                        cudaStream_t stream);
@@ -351,7 +388,7 @@ struct phx_ctx;
 int phx_tc_prepare(phx_ctx* ctx, int G, int H, int B, const float* packed, PhxPacked* view, cudaStream_t stream);
 int phx_tc_pack_launch(int G, int H, const PhxPacked& w, cudaStream_t stream);
 int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay,
-                              float fscale, float* SP, float* tcws, cudaStream_t stream);
+                              float fscale, float* SP, float* tcws, cudaStream_t stream, const PhxRhsPost* post = nullptr);
 // after phx_tc_rhs_forward_launch on the same scratch: GS = (g relu(m)) WA (prods half scaled by Pr) and, if ybar != 0,
 // ybar = (GS_s Ws + (GS_p Wp)/(1+s)) / (1+|y-.5|)^2 - g relu(m); if J != 0 also the un-decayed joint J = [S|P] WA^T
 int phx_tc_vjp_state_launch(int G, int H, int B, const PhxPacked& w, const float* y, const float* g, int decay,

@@ -283,12 +283,18 @@ static void rhs_sp(int G, int H, int B, const PhxPacked& w, const float* y, floa
     }
 }
 
+bool phx_rhs_post_supported(const PhxPacked& w, int H, int B) { return w.tc && phx_tc_shape_ok(H, B); }
+
 int phx_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay, float fscale,
-                           float* ws, cudaStream_t st) {
+                           float* ws, cudaStream_t st, const PhxRhsPost* post) {
     const int K2 = phx_K2(H);
     float* SP = ws;
     if (w.tc && phx_tc_shape_ok(H, B))   // tcgen05 path: both contractions on the tensor cores
-        return phx_tc_rhs_forward_launch(G, H, B, w, y, f, decay, fscale, SP, ws + rhs_base_floats(G, H, B), st);
+        return phx_tc_rhs_forward_launch(G, H, B, w, y, f, decay, fscale, SP, ws + rhs_base_floats(G, H, B), st, post);
+    if (post && post->mode != PHX_POST_NONE) {
+        phx_set_error("rhs_forward: the fused stage algebra needs the tensor-core path (phx_rhs_post_supported)");
+        return PHX_ERR_INVALID;
+    }
     rhs_sp(G, H, B, w, y, SP, st);
     LoadRowMajorA la{SP, K2, 0};
     LoadWcol lb{reinterpret_cast<const float*>(w.WA), K2, 0};

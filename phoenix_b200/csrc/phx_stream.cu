@@ -3,11 +3,15 @@
 // stage is: one fused elementwise combine over the state -> the batched RHS / RHS-VJP contractions of phx_rhs.cu.
 // Fixed-grid methods stay fully asynchronous; dopri5 reads ONE small record (the error sums) back per step attempt
 // for the controller, negligible next to the B*G*H contractions of a step at these sizes.
-//
-// The adjoint treats (y, adj_y, adj_params) as three flat segments with identical elementwise arithmetic
-// (adjoint.py:86-151); at large B the parameter-cotangent stage derivatives are genuine rank-B contractions
-// (gJ^T SP etc., K = B) and are materialised per stage like the reference does.
+// Forward solves on the tensor-core path can go one step further (`fuse`, PHX_STREAM_FUSE=1): the stage algebra that
+// FOLLOWS a stage derivative -- the next stage input, y1, the end value of a fixed-grid step -- evaluated in the epilogue
+// of the joint contraction that produces the derivative (PhxRhsPost, phx_common.cuh): a fixed-grid step is then RHS
+// launches only (its last derivative is never written), a dopri5 attempt keeps one stand-alone combine (the first stage
+// input, which needs the step size the controller has just chosen) and the error pass.  Same formulas, same operation
+// order: bit-identical to the stand-alone kernels -- and measured SLOWER than them at every shape, so it is off by
+// default (numbers and the reason in phx_stream_solve_forward).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 #include <stdint.h>
 #include <vector>
@@ -71,18 +75,12 @@ __global__ void combine_kernel(float* out, const float* x0, KSet a, size_t n) {
     }
 }
 
-// fixed-grid formulas, exactly as written in fixed_grid.py / rk_common.py:96-103
-enum { FX_EULER_END = 0, FX_MID_IN = 1, FX_RK4_IN2 = 2, FX_RK4_IN3 = 3, FX_RK4_IN4 = 4, FX_RK4_END = 5 };
+// fixed-grid formulas, exactly as written in fixed_grid.py / rk_common.py:96-103 (phx_fixed_formula, phx_common.cuh: the
+// fused epilogue evaluates the very same function)
+enum { FX_EULER_END = PHX_FX_EULER_END, FX_MID_IN = PHX_FX_MID_IN, FX_RK4_IN2 = PHX_FX_RK4_IN2, FX_RK4_IN3 = PHX_FX_RK4_IN3,
+       FX_RK4_IN4 = PHX_FX_RK4_IN4, FX_RK4_END = PHX_FX_RK4_END };
 __device__ __forceinline__ float fixed_one(int mode, float x, float a1, float a2, float a3, float a4, float dt) {
-    const float third = (float)(1.0 / 3.0);
-    switch (mode) {
-        case FX_EULER_END: return x + dt * a1;
-        case FX_MID_IN: return x + a1 * dt;  // dt carries half_dt here
-        case FX_RK4_IN2: return x + dt * a1 * third;
-        case FX_RK4_IN3: return x + dt * (a2 - a1 * third);
-        case FX_RK4_IN4: return x + dt * (a1 - a2 + a3);
-        default: return x + (a1 + 3.f * (a2 + a3) + a4) * dt * 0.125f;
-    }
+    return phx_fixed_formula(mode, x, a1, a2, a3, a4, dt);
 }
 template <int V>
 __global__ void fixed_kernel(int mode, float* out, const float* x0, const float* k1, const float* k2, const float* k3,
@@ -274,14 +272,15 @@ struct Stream {
     phx_sum_hook sum_hook = nullptr;   // exact-global-norm mode (forward solves only)
     void* sum_user = nullptr;
     int sum_world = 1;
+    bool fuse = false;                 // stage algebra in the RHS epilogue (forward solves on the tensor-core path)
 
     // stage derivative `slot` of every segment at the current stage inputs (at_x0: at the step's start values themselves,
     // read in place -- no copy into the stage-input buffers)
     enum { AT_XS = 0, AT_X0 = 1, AT_X1 = 2 };
-    int eval(int slot, int at = AT_XS) {
+    int eval(int slot, int at = AT_XS, const PhxRhsPost* post = nullptr) {
         auto in = [&](Seg& s) -> const float* { return at == AT_X0 ? s.x0 : (at == AT_X1 ? s.x1 : s.xs); };
         if (!adjoint)
-            return phx_rhs_forward_launch(G, H, B, w, in(segs[0]), segs[0].k[slot], 1, fsign, rhs_ws, st);
+            return phx_rhs_forward_launch(G, H, B, w, in(segs[0]), segs[0].k[slot], 1, fsign, rhs_ws, st, post);
         // reverse time: ky = -f, ka = VJP_y(cotangent a), ktheta = VJP_theta(cotangent a)
         return phx_rhs_vjp_launch(G, H, B, w, in(segs[0]), in(segs[1]), 1, segs[1].k[slot], segs[2].k[slot], 0,
                                   segs[0].k[slot], -1.f, rhs_ws, st);
@@ -345,8 +344,48 @@ struct Stream {
     // ---- one fixed-grid step of size dtf on all segments.  The new values replace x0 in place -- or, with `dst0`
     // (forward solves: the caller's output slice of this interval), segment 0's go straight there and x0 is re-pointed
     // at them: no copy of the state into the output, and the start values of a solve are read where the caller put them ----
+    // fixed-grid stage record: the derivative of this launch is the newest of `nk + 1`, the older ones sit in k[0..nk-1]
+    PhxRhsPost fx_post(int fx, int nk, float dt, float* out, bool store) {
+        PhxRhsPost po;
+        memset(&po, 0, sizeof(po));
+        Seg& s = segs[0];
+        po.mode = PHX_POST_FX + fx; po.nk = nk; po.store_f = store ? 1 : 0; po.dt = dt; po.x0 = s.x0; po.out = out;
+        for (int j = 0; j < nk; ++j) po.k[j] = s.k[j];
+        return po;
+    }
+    int fixed_step_fused(float dtf, float* dst0) {
+        int rc;
+        Seg& s = segs[0];
+        float* end = dst0 ? dst0 : s.x1;   // never x0 itself: other threads still read x0 while this one writes
+        PhxRhsPost po;
+        if (method == PHX_EULER) {
+            po = fx_post(FX_EULER_END, 0, dtf, end, false);
+            if ((rc = eval(0, AT_X0, &po)) != PHX_OK) return rc;
+            status.n_rhs += 1;
+        } else if (method == PHX_MIDPOINT) {
+            po = fx_post(FX_MID_IN, 0, 0.5f * dtf, s.xs, false);   // k1 is only ever used here
+            if ((rc = eval(0, AT_X0, &po)) != PHX_OK) return rc;
+            po = fx_post(FX_EULER_END, 0, dtf, end, false);   // x + dt * k2: k2 is this launch's own derivative
+            if ((rc = eval(1, AT_XS, &po)) != PHX_OK) return rc;
+            status.n_rhs += 2;
+        } else {
+            po = fx_post(FX_RK4_IN2, 0, dtf, s.xs, true);
+            if ((rc = eval(0, AT_X0, &po)) != PHX_OK) return rc;
+            po = fx_post(FX_RK4_IN3, 1, dtf, s.xs, true);
+            if ((rc = eval(1, AT_XS, &po)) != PHX_OK) return rc;
+            po = fx_post(FX_RK4_IN4, 2, dtf, s.xs, true);
+            if ((rc = eval(2, AT_XS, &po)) != PHX_OK) return rc;
+            po = fx_post(FX_RK4_END, 3, dtf, end, false);
+            if ((rc = eval(3, AT_XS, &po)) != PHX_OK) return rc;
+            status.n_rhs += 4;
+        }
+        if (dst0) s.x0 = dst0;
+        else std::swap(s.x0, s.x1);
+        return PHX_OK;
+    }
     int fixed_step(float dtf, float* dst0 = nullptr) {
         int rc;
+        if (fuse) return fixed_step_fused(dtf, dst0);
         if ((rc = eval(0, AT_X0)) != PHX_OK) return rc;
         auto endp = [&](Seg& s) { return (dst0 && &s == &segs[0]) ? dst0 : s.x0; };
         auto fx = [&](int mode, Seg& s, float* out, float dt) {
@@ -432,11 +471,26 @@ struct Stream {
             }
             for (int stg = 1; stg <= 6; ++stg) {
                 // stage input from beta[stg-1]; the last one is y1 and is written to x1 as well
-                for (size_t si = 0; si < ns; ++si) {
-                    Seg& s = segs[si];
-                    KSet a = kset((int)si, sl, cb[stg - 1], stg);
-                    if (stg == 6) combine(s.x1, s.x0, a, s.n);   // y1: the last stage is evaluated there, in place
-                    else if (s.xs) combine(s.xs, s.x0, a, s.n);
+                if (!fuse || stg == 1) {
+                    for (size_t si = 0; si < ns; ++si) {
+                        Seg& s = segs[si];
+                        KSet a = kset((int)si, sl, cb[stg - 1], stg);
+                        if (stg == 6) combine(s.x1, s.x0, a, s.n);   // y1: the last stage is evaluated there, in place
+                        else if (s.xs) combine(s.xs, s.x0, a, s.n);
+                    }
+                }
+                if (fuse && stg < 6) {
+                    // this launch's derivative k_stg closes the chain of the NEXT stage input (y1 after stage 5)
+                    Seg& s = segs[0];
+                    PhxRhsPost po;
+                    memset(&po, 0, sizeof(po));
+                    po.mode = PHX_POST_CHAIN; po.nk = stg; po.store_f = 1; po.x0 = s.x0;
+                    po.out = stg == 5 ? s.x1 : s.xs;
+                    for (int j = 0; j < stg; ++j) po.k[j] = s.k[sl[j]];
+                    for (int j = 0; j < stg; ++j) po.c[j] = cb[stg][j];
+                    po.cr = cb[stg][stg];
+                    if ((rc = eval(sl[stg], AT_XS, &po)) != PHX_OK) return rc;
+                    continue;
                 }
                 if ((rc = eval(sl[stg], stg == 6 ? AT_X1 : AT_XS)) != PHX_OK) return rc;
             }
@@ -616,6 +670,17 @@ int phx_stream_solve_forward(phx_ctx* ctx, int G, int H, int B, const float* pac
                    workspace_bytes, steplog, steplog_cap, st, &base);
     if (rc != PHX_OK) return rc;
     S.fsign = reversed ? -1.f : 1.f;
+    {
+        // OFF unless PHX_STREAM_FUSE=1: measured slower at every shape (tools/stream_fuse_ab.py,
+        // profiles/r04d_stream_fuse_ab.txt -- 60 rows x 11 165 genes rk4 0.40 ms fused / 0.34 ms not; 4 096 x 20 000:
+        // 4.68 / 3.59 ms; the scan 242 / 261 genes/s).  The eight epilogue warps of a joint CTA hold at most ~48 loads
+        // per thread in flight (168 registers at 320 threads), wait for them chunk by chunk, and the MMAs of the next tile
+        // wait for the epilogue; the 1 184-block elementwise kernels stream the same arrays at HBM speed and cost one
+        // launch.  Kept because it is bit-identical (tests/test_gpu_stream_fused.py) and documents the experiment.
+        const char* e = getenv("PHX_STREAM_FUSE");
+        const bool want = e && e[0] == '1';
+        S.fuse = want && phx_rhs_post_supported(S.w, H, B);
+    }
     const size_t BG = (size_t)B * G;
     Seg y;
     y.n = BG; y.count = (double)BG;

@@ -1086,6 +1086,8 @@ struct JointParams {
                           // 3 the same with u and v accumulated side by side (k-blocks below / above the middle)
                           // 4 prior loss (train_insilico.py:134-135): f = fscale * (acc - g) with g = prior_grad, and the
                           //   sum of (acc - g)^2 per epilogue warp -> part (the joint itself is never written)
+                          // 5 = 0, then `post`: the next stage input / the step's end value from f, x0 and the older
+                          //   stage derivatives, in the same pass (no separate elementwise kernel over the state)
     float fscale;
     const float* waimg;   // A image: [GT][KB2][hi|lo][128 x 16]
     const float* spimg;   // B image: [BT][KB2][hi|lo][256 x 16]
@@ -1094,6 +1096,7 @@ struct JointParams {
     const float* relum;   // [G]
     float* f;             // [B][G]
     double* part;         // emode 4: [gridDim.x][8] per-epilogue-warp sums of (acc - g)^2
+    PhxRhsPost post;      // emode 5 = emode 0 followed by the RK stage algebra of the streaming solvers (phx_common.cuh)
 };
 constexpr int K2_THREADS = 320;   // bulk-copy issuer, MMA issuer, 8 epilogue warps
 constexpr int K2_STAGES = 4;
@@ -1203,16 +1206,18 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
             const float rm = (gok && p.decay) ? p.relum[g] : 1.f;
             const int b0 = bt * 256 + half * 128;
             const int ncol = min(128, p.B - b0);   // valid batch rows of this warp's half (may be <= 0)
-            const bool need_y = (EMODE >= 2 && EMODE != 4) || (EMODE == 0 && p.decay);
+            const bool need_y = (EMODE >= 2 && EMODE < 4) || ((EMODE == 0 || EMODE == 5) && p.decay);
             constexpr bool need_u = EMODE == 2;
-            const bool need_g = EMODE == 4 || (EMODE >= 2 && p.decay);
+            const bool need_g = EMODE == 4 || (EMODE >= 2 && EMODE < 4 && p.decay);
             float yv[16], yn[16], uv[16], un[16], gv[16], gn[16];
             auto loadin = [&](int c0, float (&dy)[16], float (&du)[16], float (&dg)[16]) {
 #pragma unroll
                 for (int jj = 0; jj < 16; ++jj) {
                     const bool ok = gok && c0 + jj < ncol;
                     const size_t idx = (size_t)(b0 + c0 + jj) * p.G + g;
-                    dy[jj] = (need_y && ok) ? __ldg(p.y + idx) : 0.f;
+                    // EMODE 5 may write the next stage input over the state it reads (same thread, same element): no
+                    // non-coherent loads from that buffer
+                    dy[jj] = (need_y && ok) ? (EMODE == 5 ? p.y[idx] : __ldg(p.y + idx)) : 0.f;
                     du[jj] = (need_u && ok) ? p.f[idx] : 0.f;
                     dg[jj] = (need_g && ok) ? __ldg(p.g + idx) : 0.f;
                 }
@@ -1228,6 +1233,81 @@ __global__ void __launch_bounds__(K2_THREADS, 1) tc_joint_kernel(JointParams p) 
                     gv[jj] = gn[jj];
                 }
                 if (c0 + 16 < ncol) loadin(c0 + 16, yn, un, gn);
+                if (EMODE == 5) {
+                    // f as in EMODE 0, then the RK stage algebra that follows it (PhxRhsPost).  The loads do not depend on
+                    // the MMAs: x0 and the two oldest derivatives are in flight before the accumulator is read, the
+                    // others follow two arrays (32 loads per thread) at a time -- what fits the 168 registers of a
+                    // 320-thread CTA without spilling loaded values (a spilled load serialises on its latency).
+                    const PhxRhsPost& po = p.post;
+                    const int nk = po.nk;
+                    float xv[16], ka[16], kb[16], r[16], o[16];
+                    auto ld16 = [&](const float* src, float (&d)[16], bool use) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const bool ok = use && gok && c0 + jj < ncol;
+                            d[jj] = ok ? __ldg(src + (size_t)(b0 + c0 + jj) * p.G + g) : 0.f;
+                        }
+                    };
+                    ld16(po.x0, xv, true);
+                    ld16(po.k[0], ka, nk > 0);
+                    ld16(po.k[1], kb, nk > 1);
+                    float v[16];
+                    tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * 256 + half * 128 + c0), v);
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) r[jj] = p.fscale * (p.decay ? rm * (v[jj] - yv[jj]) : v[jj]);
+                    if (po.mode == PHX_POST_CHAIN) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            o[jj] = ka[jj] * po.c[0];
+                            if (nk > 1) o[jj] = fmaf(kb[jj], po.c[1], o[jj]);
+                        }
+                        if (nk > 2) {
+                            ld16(po.k[2], ka, true);
+                            ld16(po.k[3], kb, nk > 3);
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) {
+                                o[jj] = fmaf(ka[jj], po.c[2], o[jj]);
+                                if (nk > 3) o[jj] = fmaf(kb[jj], po.c[3], o[jj]);
+                            }
+                        }
+                        if (nk > 4) {
+                            ld16(po.k[4], ka, true);
+                            ld16(po.k[5], kb, nk > 5);
+#pragma unroll
+                            for (int jj = 0; jj < 16; ++jj) {
+                                o[jj] = fmaf(ka[jj], po.c[4], o[jj]);
+                                if (nk > 5) o[jj] = fmaf(kb[jj], po.c[5], o[jj]);
+                            }
+                        }
+                        const float cl = po.cr;
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            o[jj] = nk == 0 ? r[jj] * cl : fmaf(r[jj], cl, o[jj]);
+                            o[jj] = xv[jj] + o[jj];
+                        }
+                    } else {
+                        // the newest derivative is r, the older ones a1.. = k[0..nk-1] (at most three)
+                        const int fx = po.mode - PHX_POST_FX;
+                        if (nk > 2) ld16(po.k[2], o, true);
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj) {
+                            const float a1 = nk > 0 ? ka[jj] : r[jj];
+                            const float a2 = nk > 1 ? kb[jj] : (nk == 1 ? r[jj] : 0.f);
+                            const float a3 = nk > 2 ? o[jj] : (nk == 2 ? r[jj] : 0.f);
+                            const float a4 = nk == 3 ? r[jj] : 0.f;
+                            o[jj] = phx_fixed_formula(fx, xv[jj], a1, a2, a3, a4, po.dt);
+                        }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 16; ++jj) {
+                        if (gok && c0 + jj < ncol) {
+                            const size_t idx = (size_t)(b0 + c0 + jj) * p.G + g;
+                            po.out[idx] = o[jj];
+                            if (po.store_f) p.f[idx] = r[jj];
+                        }
+                    }
+                    continue;
+                }
                 float v[16];
                 tmem_ld16(tmem + ((unsigned)(q * 32) << 16) + (unsigned)(buf * 256 + half * 128 + c0), v);
                 if (EMODE == 3) {   // u from the first half of tensor memory, v from the second
@@ -1430,6 +1510,7 @@ void set_attrs() {
     cudaFuncSetAttribute(tc_joint_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     cudaFuncSetAttribute(tc_joint_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
+    cudaFuncSetAttribute(tc_joint_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, PHX_SMEM_LIMIT);
     done = true;
 }
 
@@ -1570,8 +1651,10 @@ int launch_branch(int mode, int G, int H, int B, int nterms, const float* src, c
 // out^T tiles = Aimg[genes x k-blocks kb_lo..kb_hi) x Bimg[batch rows]^T with the epilogue `emode`
 int launch_joint(int G, int H, int B, int nterms, const float* aimg, const float* bimg, int kb_lo, int kb_hi, int emode,
                  int decay, float fscale, const float* y, const float* g, const float* relum, float* out,
-                 cudaStream_t st, double* part = nullptr) {
+                 cudaStream_t st, double* part = nullptr, const PhxRhsPost* post = nullptr) {
     JointParams jp;
+    memset(&jp.post, 0, sizeof(jp.post));
+    if (post) jp.post = *post;
     jp.G = G; jp.B = B; jp.KB2 = phx_tc_KB2(H); jp.GT = phx_tc_GT(G); jp.BT = phx_tc_BT(B); jp.nterms = nterms;
     jp.decay = decay; jp.fscale = fscale; jp.kb_lo = kb_lo; jp.kb_hi = kb_hi; jp.emode = emode;
     jp.a_lbo = 16 * 128; jp.a_sbo = 128; jp.b_lbo = 32 * 128; jp.b_sbo = 128;
@@ -1585,6 +1668,7 @@ int launch_joint(int G, int H, int B, int nterms, const float* aimg, const float
     else if (emode == 1) tc_joint_kernel<1><<<grid, K2_THREADS, smem2, st>>>(jp);
     else if (emode == 2) tc_joint_kernel<2><<<grid, K2_THREADS, smem2, st>>>(jp);
     else if (emode == 3) tc_joint_kernel<3><<<grid, K2_THREADS, smem2, st>>>(jp);
+    else if (emode == 5) tc_joint_kernel<5><<<grid, K2_THREADS, smem2, st>>>(jp);
     else tc_joint_kernel<4><<<grid, K2_THREADS, smem2, st>>>(jp);
     return grid;
 }
@@ -1602,12 +1686,22 @@ int check_launch(const char* what) {
 
 // SP (plain [B][K2], bias/exp applied) and, if f != 0, f; tcws = scratch of phx_tc_scratch_floats(G, H, B) floats
 int phx_tc_rhs_forward_launch(int G, int H, int B, const PhxPacked& w, const float* y, float* f, int decay,
-                              float fscale, float* SP, float* tcws, cudaStream_t st) {
+                              float fscale, float* SP, float* tcws, cudaStream_t st, const PhxRhsPost* post) {
     const TcScratch sc = carve(G, H, B, tcws);
     const int nterms = (w.tc == 1) ? 1 : 3;
+    const bool fused = post && post->mode != PHX_POST_NONE;
+    if (fused && (!post->x0 || !post->out || post->nk < 0 || post->nk > 6 || (post->mode == PHX_POST_CHAIN && post->nk > 6) || (post->store_f && !f) ||
+                  (post->mode >= PHX_POST_FX && post->nk > 3))) {
+        phx_set_error("tc rhs_forward: malformed stage-algebra record");
+        return PHX_ERR_INVALID;
+    }
     int rc = launch_branch(0, G, H, B, nterms, y, nullptr, w.w1img, w.bias, SP, sc.spimg, sc.sptimg, sc.spart, st);
     if (rc != PHX_OK) return rc;
-    if (f) launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 0, decay, fscale, y, nullptr, w.relum, f, st);
+    if (fused)
+        launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 5, decay, fscale, y, nullptr, w.relum, f, st,
+                     nullptr, post);
+    else if (f)
+        launch_joint(G, H, B, nterms, w.waimg, sc.spimg, 0, phx_tc_KB2(H), 0, decay, fscale, y, nullptr, w.relum, f, st);
     return check_launch("tc rhs_forward");
 }
 
