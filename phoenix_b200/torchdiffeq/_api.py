@@ -105,8 +105,9 @@ def _register_node(ctx, func, y0, tl, t_is_f32, adj):
     """Forward side: note the node if its backward may be batched with its siblings' (a one-row state that needs no
     gradient itself -- the training loop's case)."""
     ctx.group = None
-    if not DEFER_ADJOINT or ctx.needs_input_grad[8] or y0.numel() != y0.shape[-1]:
-        return
+    if (not DEFER_ADJOINT or ctx.needs_input_grad[8] or not any(ctx.needs_input_grad[9:])
+            or y0.numel() != y0.shape[-1]):
+        return   # (nothing to differentiate -- e.g. a validation pass under no_grad -- is not a node at all)
     with _defer_lock:
         _node_seq[0] += 1
         ctx.seq = _node_seq[0]
