@@ -444,18 +444,41 @@ __global__ void prior_loss_sum_kernel(const double* __restrict__ part, int n, do
     }
 }
 // prior_grad = batch_for_prior @ prior_mat (train_insilico.py:209) with the 0.5-3 % dense prior in CSC form: one CTA per
-// batch row (staged in shared memory), one thread per output gene walking that gene's column of the prior.
-__global__ void prior_setup_kernel(int G, const float* __restrict__ x, const int* __restrict__ colptr,
+// R batch rows (staged in shared memory, interleaved [gene][R]), one thread per output gene walking that gene's column of
+// the prior -- every (row index, value) pair fetched from L2 serves R rows.  Each output is one fmaf chain over its
+// column in storage order, whatever R is.
+template <int R>
+__global__ void prior_setup_kernel(int G, int B, const float* __restrict__ x, const int* __restrict__ colptr,
                                    const int* __restrict__ rowidx, const float* __restrict__ val, float* __restrict__ out) {
     extern __shared__ float xrow[];
-    const size_t b = blockIdx.x;
-    for (int i = threadIdx.x; i < G; i += blockDim.x) xrow[i] = x[b * G + i];
+    const size_t b0 = (size_t)blockIdx.x * R;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) xrow[(size_t)i * R + r] = (b0 + r < (size_t)B) ? x[(b0 + r) * G + i] : 0.f;
+    }
     __syncthreads();
     for (int j = threadIdx.x; j < G; j += blockDim.x) {
-        float t = 0.f;
-        for (int e = colptr[j]; e < colptr[j + 1]; ++e) t = fmaf(xrow[rowidx[e]], val[e], t);
-        out[b * G + j] = t;
+        float t[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) t[r] = 0.f;
+        for (int e = colptr[j]; e < colptr[j + 1]; ++e) {
+            const float v = val[e];
+            const float* xr = xrow + (size_t)rowidx[e] * R;
+#pragma unroll
+            for (int r = 0; r < R; ++r) t[r] = fmaf(xr[r], v, t[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (b0 + r < (size_t)B) out[(b0 + r) * G + j] = t[r];
     }
+}
+template <int R>
+cudaError_t prior_setup_run(int G, int B, const float* x, const int* colptr, const int* rowidx, const float* val,
+                            float* out, cudaStream_t st) {
+    const size_t smem = (size_t)G * R * sizeof(float);
+    cudaFuncSetAttribute(prior_setup_kernel<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    prior_setup_kernel<R><<<(B + R - 1) / R, 512, smem, st>>>(G, B, x, colptr, rowidx, val, out);
+    return cudaGetLastError();
 }
 }  // namespace
 
@@ -484,14 +507,16 @@ int phx_prior_loss_launch(int G, int H, int B, const PhxPacked& w, const float* 
 
 int phx_prior_setup_launch(int G, int B, const float* x, const int* colptr, const int* rowidx, const float* val,
                            float* out, cudaStream_t st) {
-    const size_t smem = (size_t)G * sizeof(float);
-    if (smem > 200 * 1024) {
+    const size_t row = (size_t)G * sizeof(float), budget = 200 * 1024;
+    if (row > budget) {
         phx_set_error("prior_setup supports up to 51200 genes (got %d)", G);
         return PHX_ERR_UNSUPPORTED;
     }
-    cudaFuncSetAttribute(prior_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    prior_setup_kernel<<<B, 512, smem, st>>>(G, x, colptr, rowidx, val, out);
-    cudaError_t e = cudaGetLastError();
+    // as many batch rows per CTA as fit beside each other in shared memory (4 at 11 165 genes, 2 at 20 000)
+    cudaError_t e;
+    if (4 * row <= budget) e = prior_setup_run<4>(G, B, x, colptr, rowidx, val, out, st);
+    else if (2 * row <= budget) e = prior_setup_run<2>(G, B, x, colptr, rowidx, val, out, st);
+    else e = prior_setup_run<1>(G, B, x, colptr, rowidx, val, out, st);
     if (e != cudaSuccess) {
         phx_set_error("prior_setup launch: %s", cudaGetErrorString(e));
         return PHX_ERR_CUDA;

@@ -150,3 +150,22 @@ def test_cached_activations_of_the_prior_batch_change_nothing():
         assert len(prior._hill_planes) == 1
     finally:
         prior.CACHE_ACTIVATIONS = True
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("G,B", [(129, 7), (690, 1), (11165, 10), (20000, 5), (26000, 3)],
+                         ids=["g129_b7", "g690_b1", "g11165_b10_4rows", "g20000_b5_2rows", "g26000_b3_1row"])
+def test_prior_setup_ragged_rows(G, B):
+    """phx_prior_setup puts 4 / 2 / 1 batch rows side by side in a CTA's shared memory depending on G; the last CTA of
+    a batch that is not a multiple of that holds fewer.  Against the float64 product (train_insilico.py:209)."""
+    import phoenix_b200 as pb
+    gen = torch.Generator().manual_seed(G + B)
+    nnz = 20 * G
+    rows = torch.randint(0, G, (nnz,), generator=gen)
+    cols = torch.randint(0, G, (nnz,), generator=gen)
+    vals = torch.rand(nnz, generator=gen) - 0.5
+    prior = torch.sparse_coo_tensor(torch.stack([rows, cols]), vals, (G, G)).coalesce()
+    x = torch.rand(B, 1, G, generator=gen) - 0.5
+    pg = pb.prior_grad_from_matrix(x.cuda(), prior)
+    ref = torch.sparse.mm(prior.double().t(), x.view(B, G).double().t()).t().reshape(B, 1, G)
+    assert pg.shape == x.shape and rel_l2(pg.cpu(), ref) < 1e-6

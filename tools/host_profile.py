@@ -29,6 +29,15 @@ def step():
 for _ in range(3):
     step()
 torch.cuda.synchronize()
+# wall time per step when the host runs free (GPU time + host gaps) against the host's own time per step (enqueue only)
+import time  # noqa: E402
+t0 = time.perf_counter()
+for _ in range(20):
+    step()
+t_enq = time.perf_counter() - t0
+torch.cuda.synchronize()
+t_all = time.perf_counter() - t0
+print("per step: host enqueue %.3f ms, wall to completion %.3f ms" % (t_enq / 20 * 1e3, t_all / 20 * 1e3))
 pr = cProfile.Profile()
 pr.enable()
 for _ in range(20):
