@@ -128,7 +128,8 @@ def run_reference(args):
     line = {
         "impl": "reference", "reference_is": "CPU port of the reference (oracle/phoenix_oracle.py, pinned to the "
         "reference's own outputs by tests/golden); the reference is pure Python over torch-CPU and cannot be installed "
-        "on the GPU box, see DESIGN.md section 5",
+        "on the GPU box, see DESIGN.md section 5; timed side by side in the build container the port is ~10 % faster "
+        "than the unmodified reference (profiles/r04j_port_vs_reference.txt)",
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * secs / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
