@@ -450,6 +450,15 @@ def split_flat_grads(flat, G, H):
 
 
 # ---- solves ----------------------------------------------------------------------------------------------------------------
+def _zero_param_grads(net, G, H, device):
+    """A single output time leaves nothing to integrate: the solution is y0 itself (solvers.py:26-30 fills solution[0]
+    and the loop over the later times is empty) and the backward sweep (adjoint.py:137-154, an empty loop as well)
+    returns grad_y[0] for y0 and ZERO -- not missing -- parameter cotangents."""
+    flat = new_flat_grads(net, 4 * G * H + 2 * H + G, device)
+    flat.zero_()
+    return split_flat_grads(flat, G, H)
+
+
 def _t_array(t_list):
     arr = (ctypes.c_double * len(t_list))(*t_list)
     return arr
@@ -560,6 +569,8 @@ def solve_forward(net, y0, t_list, t_is_f32, reversed_time, method, rtol, atol, 
     y0c = y0.detach().contiguous()
     B = y0c.numel() // G
     T = len(t_list)
+    if T == 1:
+        return y0c.unsqueeze(0).clone()
     lib = _lib.load()
     if _use_rows(lib, dev, G, H, B, False, single=True, T=T):
         return _forward_rows(lib, net, packed, G, H, dev, y0c, [t_list], t_is_f32, reversed_time, method, rtol, atol,
@@ -584,6 +595,8 @@ def solve_adjoint(net, t_list, t_is_f32, method, rtol, atol, max_num_steps, y_sa
     ys = y_saved.detach().contiguous()
     gy = grad_y.detach().to(torch.float32).contiguous()
     T = len(t_list)
+    if T == 1:
+        return gy[0].clone(), _zero_param_grads(net, G, H, ys.device)
     B = ys[0].numel() // G
     lib = _lib.load()
     if _use_rows(lib, dev, G, H, B, True, single=True, T=T):
@@ -679,6 +692,8 @@ def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_st
         raise RuntimeError("y0 and the ODENet parameters must be on the same CUDA device")
     y0c = y0.detach().contiguous()
     N, T = len(t_rows), len(t_rows[0])
+    if T == 1:
+        return y0c.unsqueeze(1).clone()
     B = y0c[0].numel() // G
     lib = _lib.load()
     if _use_rows(lib, dev, G, H, B, False):
@@ -741,6 +756,8 @@ def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps,
     ys = y_saved.detach().contiguous()
     gy = grad_y.detach().to(torch.float32).contiguous()
     N, T = len(t_rows), len(t_rows[0])
+    if T == 1:
+        return gy[:, 0].clone(), _zero_param_grads(net, G, H, ys.device)
     B = ys[0, 0].numel() // G
     lib = _lib.load()
     if _use_rows(lib, dev, G, H, B, True):

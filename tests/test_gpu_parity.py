@@ -318,6 +318,43 @@ def test_solver_assertions_surface_like_the_reference(pb):
     assert torch.isfinite(y).all()
 
 
+def test_a_single_output_time_is_the_initial_state(pb):
+    """len(t) == 1: the reference returns y0 as the only slice (solvers.py:26-30), and its backward gives grad_y[0] to y0
+    and ZERO (not missing) parameter gradients (adjoint.py:137-162; checked against the reference itself for dopri5, rk4
+    and euler).  No kernel has anything to do; every entry point must still answer, in every time dtype."""
+    G, H, N = 129, 33, 5
+    w = O.make_weights(G, H, 11, dense=True)
+    net = make_net(pb, w)
+    gen = torch.Generator().manual_seed(2)
+    for method in ("dopri5", "rk4", "euler"):
+        for tdt in (torch.float32, torch.float64):
+            y0 = torch.rand(3, 1, G, generator=gen).cuda().requires_grad_(True)
+            t = torch.tensor([0.3], dtype=tdt)
+            with torch.no_grad():
+                assert torch.equal(pb.odeint(net, y0, t, method=method), y0.detach()[None])
+            net.zero_grad()
+            y = pb.odeint_adjoint(net, y0, t, method=method)
+            assert y.shape == (1, 3, 1, G) and torch.equal(y.detach()[0], y0.detach())
+            (y ** 2).sum().backward()
+            assert torch.equal(y0.grad, 2 * y0.detach())
+            assert all(p.grad is not None and not p.grad.any() for p in net.parameters())
+    # the many-problem call and the per-sample loop (whose sibling nodes share one backward call)
+    yb = torch.rand(N, 1, G, generator=gen).cuda()
+    tb = torch.rand(N, 1)
+    net.zero_grad()
+    ya = yb.clone().requires_grad_(True)
+    many = pb.odeint_adjoint_many(net, ya, tb, method="dopri5")
+    assert many.shape == (N, 1, 1, G) and torch.equal(many.detach()[:, 0], yb)
+    (3 * many).sum().backward()
+    assert torch.equal(ya.grad, torch.full_like(yb, 3.0))
+    assert all(p.grad is not None and not p.grad.any() for p in net.parameters())
+    net.zero_grad()
+    preds = [pb.odeint_adjoint(net, yb[i], tb[i], method="dopri5")[0] for i in range(N)]
+    assert torch.equal(torch.stack(preds).detach(), yb)
+    torch.stack(preds).sum().backward()
+    assert all(p.grad is not None and not p.grad.any() for p in net.parameters())
+
+
 def test_ragged_and_edge_shapes(pb):
     """G not a multiple of 4, H not a multiple of 4, a single gene per CTA, many output times."""
     for G, H, B in ((5, 3, 1), (37, 5, 2), (129, 33, 1), (1001, 100, 1)):
