@@ -93,3 +93,20 @@ def test_baseline_configs_on_real_data_match_reference(m):
     dop = m["method"] == "dopri5"
     check_big_case(m, d, pred, loss, torch.stack(adys), total, 1e-6 if m["stable"] else 1e-5,
                    (3e-5 if m["stable"] else 2e-4) if dop else 1e-5)
+
+
+def test_single_output_time_is_the_initial_state():
+    """len(t) == 1 (solvers.py:26-30, adjoint.py:137-162: both loops are empty): y0 is the only slice, its cotangent is
+    grad_y[0], the parameter cotangents are zero.  Checked against the reference itself for dopri5 / rk4 / euler when this
+    case was added; the CUDA path is held to the same answers in tests/test_gpu_parity.py."""
+    w = O.make_weights(20, 4, 1, dense=True)
+    y0 = torch.rand(2, 1, 20, generator=torch.Generator().manual_seed(0))
+    for method in ("dopri5", "rk4", "euler", "midpoint"):
+        for dt in (torch.float32, torch.float64):
+            t = torch.tensor([0.3], dtype=dt)
+            y, _ = O.odeint(w, y0, t, method=method)
+            assert y.shape == (1, 2, 1, 20) and torch.equal(y[0], y0)
+            gy = torch.rand(1, 2, 1, 20, generator=torch.Generator().manual_seed(1))
+            ady, grads, _ = O.adjoint_backward(w, t, y, gy, method=method)
+            assert torch.equal(ady, gy[0])
+            assert len(grads) == 6 and all(not g.any() for g in grads)
