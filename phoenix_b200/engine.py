@@ -726,25 +726,27 @@ def solve_forward_many(net, y0, t_rows, t_is_f32, method, rtol, atol, max_num_st
             for i in range(n):
                 _finish(stn[i], "forward solve %d" % (lo + i), dev)
         return yout
-    for i in range(N):
-        st = _new_status()
-        log, cap = _steplog()
+    try:   # an error raised for one problem must not leave the caller's stream un-ordered after the side streams
+        for i in range(N):
+            st = _new_status()
+            log, cap = _steplog()
+            if streams:
+                with torch.cuda.stream(streams[i % len(streams)]):
+                    wsi = _workspace(dev, nb, "solve")
+                    rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
+                            float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride),
+                            _ptr(wsi), wsi.numel(), _ptr(st), _ptr(log), cap, _stream_ptr(dev))
+                    _lib.check(rc, "solve_forward")
+                    _finish(st, "forward solve %d" % i, dev)
+                continue
+            rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
+                    float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride), wsp, wsn,
+                    _ptr(st), _ptr(log), cap, sp)
+            _lib.check(rc, "solve_forward")
+            _finish(st, "forward solve %d" % i, dev)
+    finally:
         if streams:
-            with torch.cuda.stream(streams[i % len(streams)]):
-                wsi = _workspace(dev, nb, "solve")
-                rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
-                        float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride),
-                        _ptr(wsi), wsi.numel(), _ptr(st), _ptr(log), cap, _stream_ptr(dev))
-                _lib.check(rc, "solve_forward")
-                _finish(st, "forward solve %d" % i, dev)
-            continue
-        rc = fn(ctx, G, H, B, pk, ctypes.c_void_p(ybase + i * ystride), tarr[i], T, int(t_is_f32), 0, mid,
-                float(rtol), float(atol), int(max_num_steps), ctypes.c_void_p(obase + i * ostride), wsp, wsn,
-                _ptr(st), _ptr(log), cap, sp)
-        _lib.check(rc, "solve_forward")
-        _finish(st, "forward solve %d" % i, dev)
-    if streams:
-        _fan_in(dev, streams)
+            _fan_in(dev, streams)
     return yout
 
 
@@ -798,27 +800,29 @@ def solve_adjoint_many(net, t_rows, t_is_f32, method, rtol, atol, max_num_steps,
             continue
         if streams:
             _fan_out(dev, streams)
-        for i in range(lo, hi):
-            st = _new_status()
-            log, cap = _steplog()
-            args = (ctypes.c_void_p(ys.data_ptr() + i * stride), ctypes.c_void_p(gy.data_ptr() + i * stride),
-                    ctypes.c_void_p(adj_y0.data_ptr() + i * astride),
-                    ctypes.c_void_p(grads.data_ptr() + (i - lo) * P * 4))
+        try:
+            for i in range(lo, hi):
+                st = _new_status()
+                log, cap = _steplog()
+                args = (ctypes.c_void_p(ys.data_ptr() + i * stride), ctypes.c_void_p(gy.data_ptr() + i * stride),
+                        ctypes.c_void_p(adj_y0.data_ptr() + i * astride),
+                        ctypes.c_void_p(grads.data_ptr() + (i - lo) * P * 4))
+                if streams:
+                    with torch.cuda.stream(streams[i % len(streams)]):
+                        wsi = _workspace(dev, nb, "solve")
+                        rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol),
+                                int(max_num_steps), *args, _ptr(wsi), wsi.numel(), _ptr(st), _ptr(log), cap,
+                                _stream_ptr(dev))
+                        _lib.check(rc, "solve_adjoint")
+                        _finish(st, "adjoint solve %d" % i, dev)
+                    continue
+                rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
+                        *args, wsp, wsn, _ptr(st), _ptr(log), cap, sp)
+                _lib.check(rc, "solve_adjoint")
+                _finish(st, "adjoint solve %d" % i, dev)
+        finally:
             if streams:
-                with torch.cuda.stream(streams[i % len(streams)]):
-                    wsi = _workspace(dev, nb, "solve")
-                    rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol),
-                            int(max_num_steps), *args, _ptr(wsi), wsi.numel(), _ptr(st), _ptr(log), cap,
-                            _stream_ptr(dev))
-                    _lib.check(rc, "solve_adjoint")
-                    _finish(st, "adjoint solve %d" % i, dev)
-                continue
-            rc = fn(ctx, G, H, B, pk, tarr[i], T, int(t_is_f32), mid, float(rtol), float(atol), int(max_num_steps),
-                    *args, wsp, wsn, _ptr(st), _ptr(log), cap, sp)
-            _lib.check(rc, "solve_adjoint")
-            _finish(st, "adjoint solve %d" % i, dev)
-        if streams:
-            _fan_in(dev, streams)
+                _fan_in(dev, streams)
         part = grads[:hi - lo].sum(dim=0)
         total = part if total is None else total + part
     return adj_y0, split_flat_grads(total, G, H)
