@@ -1,7 +1,7 @@
 """BASELINE config 5 (synthetic scaling sweep): 20 000 genes x 4 096 trajectories in ONE batched odeint call,
 rk4 and dopri5, forward solve and forward + adjoint, on one B200 (streaming engine + tcgen05 contractions).
 
-    python tools/sweep_c5.py [--genes 20000] [--neurons 200] [--rows 4096] [--cpu-rows 8]
+    python tools/sweep_c5.py [--genes 20000] [--neurons 200] [--rows 4096] [--t1 0.1] [--cpu-rows 8]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 tools/sweep_c5.py ...
 
 Under torchrun the rows are sharded over the ranks (weak scaling: --rows is PER RANK), weights are broadcast from rank
@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--global-norm", action="store_true",
                     help="dopri5 forward: all-reduce the error-norm sums over the ranks every step (one controller for the "
                          "whole batch, exactly like the unsharded call)")
+    ap.add_argument("--t1", type=float, default=0.1, help="the call integrates t = [0, T1] (SURVEY 8d grid: 0.01, 0.1, 1)")
     ap.add_argument("--rtol", type=float, default=1e-7)
     ap.add_argument("--atol", type=float, default=1e-9)
     a = ap.parse_args()
@@ -53,8 +54,8 @@ def main():
     pb.set_sync_errors(True)
     if a.global_norm and world > 1:
         parallel.enable_global_norm()
-    for method, t, kw in (("rk4", torch.tensor([0.0, 0.1]), {}),
-                          ("dopri5", torch.tensor([0.0, 0.1]), {"rtol": a.rtol, "atol": a.atol})):
+    for method, t, kw in (("rk4", torch.tensor([0.0, a.t1]), {}),
+                          ("dopri5", torch.tensor([0.0, a.t1]), {"rtol": a.rtol, "atol": a.atol})):
         for leg in ("forward", "forward+adjoint"):
             def run():
                 if leg == "forward":
@@ -91,7 +92,7 @@ def main():
                 ms, work = float(mx[0]), float(st[1])
             if rank == 0:
                 print(json.dumps({"n_gpus": world, "G": G, "H": H, "rows_per_gpu": B, "method": method, "leg": leg,
-                                  "scaling": "strong" if a.strong else "weak", "rtol": kw.get("rtol"),
+                                  "scaling": "strong" if a.strong else "weak", "rtol": kw.get("rtol"), "t1": a.t1,
                                   "global_norm": bool(a.global_norm and world > 1 and method == "dopri5"),
                                   "rhs_evals": evals, "ms": ms, "gene_steps_per_s": work / (ms * 1e-3)}), flush=True)
     if a.cpu_rows and rank == 0 and world == 1:
@@ -99,9 +100,9 @@ def main():
         torch.set_num_threads(os.cpu_count() or 1)
         w = O.Weights(*[p.detach().cpu() for p in net.parameters()]) if hasattr(O, "Weights") else None
         yc = y0[:a.cpu_rows].cpu()
-        O.odeint(w, yc, torch.tensor([0.0, 0.1]), method="rk4")
+        O.odeint(w, yc, torch.tensor([0.0, a.t1]), method="rk4")
         t0 = time.perf_counter()
-        _, log = O.odeint(w, yc, torch.tensor([0.0, 0.1]), method="rk4")
+        _, log = O.odeint(w, yc, torch.tensor([0.0, a.t1]), method="rk4")
         dt = time.perf_counter() - t0
         print(json.dumps({"cpu_port": True, "rows": a.cpu_rows, "method": "rk4", "leg": "forward", "s": dt,
                           "gene_steps_per_s": a.cpu_rows * G * 4 / dt, "cores": os.cpu_count()}), flush=True)
